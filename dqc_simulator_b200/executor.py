@@ -1,0 +1,565 @@
+"""Executor: walks the compiled per-QPU op lists and drives a state backend.
+
+This is the host side of the drop-in boundary.  It consumes exactly what the reference's
+compilers emit -- ``qpu_op_dict = {node_name: [[op, ...] per time slice]}``
+(``software/compilers.py:665-792``) -- and reproduces the control flow of
+``InterpreterProtocol`` / ``DQCMasterProtocol`` (``software/dqc_control.py:899-949,
+1170-1202``) without NetSquid's discrete-event kernel:
+
+* :class:`QuantumProgram` mirrors ``QuantumProgram.apply(instruction, qubit_indices,
+  operator=None, output_key="last")`` and ``program.output[key]``
+  (``dqc_control.py:191-196, 307, 371, 464-465, 787``).
+* :meth:`QPU.execute_program` is the level-2 boundary: it plays the
+  role of ``QuantumProcessor.execute_program`` -- consume the instruction's duration, apply
+  memory noise for the idle time of every touched position, apply the instruction and its
+  attached noise model in the order fixed by ``hardware/quantum_processors.py:344-456`` --
+  but instead of NumPy arithmetic it *enqueues* ops on the backend (the CUDA engine's gate
+  queue; flushed into fused, batched launches by the C library).
+* Remote-gate roles: cat ``entangle / correct / disentangle_start / disentangle_end``
+  (``dqc_control.py:266-403``), tp ``bsm / correct / correct4tele_only /
+  swap_then_correct / correct_manually`` (``:405-613, 686-750``), ``logged``
+  (``:754-791``), ``distribute_ebit`` (``:803-832``).
+
+Batched shots: measurement results never come back to the host.  A measurement writes a
+per-shot classical bit on the device (:class:`CBit`); the classically controlled X / Z
+corrections become per-shot *predicated* gates.  With ``host_branching=True`` (batch 1
+only) the executor instead reads each outcome and branches exactly like the reference
+(including the outcome-dependent simulated durations).
+
+Qubits are materialised lazily: ``INSTR_INIT`` only records the time at which the memory-noise
+clock of a position starts (the reference's tests pin "decoherence starts after
+initialisation", ``tests/unit_tests/hardware/test_noise_model.py:913-993``); an engine axis
+is claimed on first use.  An untouched |0> qubit is a product factor, so this is exact and
+keeps the joint register small (SURVEY.md section 7 "comm-qubit axes blow up memory").
+"""
+import math
+
+import numpy as np
+
+from . import instructions as ins
+from .hardware import DQCSpec
+
+
+class UnfinishedQuantumCircuitError(Exception):
+    """Same name and role as ``dqc_control.py:25-30``."""
+
+
+class CBit:
+    """Handle to a per-shot classical bit held on the device."""
+
+    __slots__ = ("index",)
+
+    def __init__(self, index):
+        self.index = index
+
+    def __repr__(self):
+        return f"CBit({self.index})"
+
+
+class QuantumProgram:
+    """List of pending instructions; ``output[key]`` is filled by ``execute_program``."""
+
+    def __init__(self):
+        self.instructions = []
+        self.output = {}
+
+    def apply(self, instruction, qubit_indices, operator=None, output_key="last", predicate=None):
+        if isinstance(qubit_indices, (int, np.integer)):
+            qubit_indices = [int(qubit_indices)]
+        else:
+            qubit_indices = [int(q) for q in qubit_indices]
+        self.instructions.append((instruction, qubit_indices, operator, output_key, predicate))
+
+    def __len__(self):
+        return len(self.instructions)
+
+
+class _CregAllocator:
+    def __init__(self, nbits):
+        self.nbits = nbits
+        self.free = list(range(nbits))
+        self.peak = 0
+
+    def alloc(self):
+        if not self.free:
+            raise RuntimeError("out of classical bits; create the engine with more creg bits")
+        b = self.free.pop(0)
+        self.peak = max(self.peak, self.nbits - len(self.free))
+        return b
+
+    def release(self, b):
+        self.free.append(b)
+        self.free.sort()
+
+
+class QPU:
+    """Per-node memory bookkeeping + ``execute_program``."""
+
+    def __init__(self, spec, executor):
+        self.spec = spec
+        self.name = spec.name
+        self.ex = executor
+        self.comm_qubit_positions = spec.comm_qubit_positions
+        self.processing_qubit_positions = spec.processing_qubit_positions
+        self.comm_qubits_free = list(self.comm_qubit_positions)  # quantum_processors.py:122
+        self.ebit_ready = False                                   # never set True upstream
+        self.clock = 0.0
+        self.axis = {}         # pos -> engine axis (materialised qubits)
+        self.pending = {}      # pos -> time the fresh |0> became valid (not yet materialised)
+        self.last_access = {}  # pos -> time of last access (materialised qubits)
+
+    # ---- qubit materialisation -------------------------------------------------
+    def occupied(self, pos):
+        return pos in self.axis or pos in self.pending
+
+    def _materialise(self, pos):
+        if pos in self.axis:
+            return self.axis[pos]
+        if pos not in self.pending:
+            raise RuntimeError(f"{self.name}: memory position {pos} holds no qubit")
+        ax = self.ex._claim_axis(pos in self.comm_qubit_positions)
+        self.ex.backend.alloc_axis(ax)
+        self.axis[pos] = ax
+        self.last_access[pos] = self.pending.pop(pos)
+        return ax
+
+    def _drop(self, pos):
+        """Throw away whatever sits at ``pos``."""
+        if pos in self.axis:
+            ax = self.axis.pop(pos)
+            self.ex.backend.free_axis(ax)
+            self.ex._release_axis(ax)
+            self.last_access.pop(pos, None)
+        self.pending.pop(pos, None)
+
+    def _memory_noise(self, pos, now):
+        """Idle-time channel on access: p = 1 - exp(-dt * 1e-9 * rate)
+        (``noise_models.py:248-253``; NetSquid ``DepolarNoiseModel`` time dependent)."""
+        dt = now - self.last_access[pos]
+        if dt <= 0:
+            return
+        be, ax, sp = self.ex.backend, self.axis[pos], self.spec
+        rate = sp.mem_rate(pos)
+        if rate > 0:
+            be.depolarize([ax], 1.0 - math.exp(-dt * 1e-9 * rate))
+        if sp.mem_dephase_rate > 0:
+            pz = 0.5 * (1.0 - math.exp(-dt * 1e-9 * sp.mem_dephase_rate))
+            be.pauli_channel(ax, [1.0 - pz, 0.0, 0.0, pz])
+        if sp.mem_amp_damp_rate > 0:
+            g = 1.0 - math.exp(-dt * 1e-9 * sp.mem_amp_damp_rate)
+            be.kraus_1q(ax, [[[1, 0], [0, math.sqrt(1 - g)]], [[0, math.sqrt(g)], [0, 0]]])
+
+    def touch(self, positions, now):
+        axes = []
+        for pos in positions:
+            ax = self._materialise(pos)
+            self._memory_noise(pos, now)
+            axes.append(ax)
+        return axes
+
+    # ---- the boundary ----------------------------------------------------------
+    def execute_program(self, program):
+        """Run the program's instructions in order on this QPU's clock."""
+        be = self.ex.backend
+        for instruction, positions, operator, key, predicate in program.instructions:
+            tok, mat = ins.resolve((instruction, operator) if operator is not None else instruction)
+            ph = self.spec.phys(tok)
+            if tok.kind == "init":
+                # fresh |0> replaces any occupant; noise clock starts when INIT completes
+                for pos in positions:
+                    self._drop(pos)
+                self.clock += ph.duration
+                for pos in positions:
+                    self.pending[pos] = self.clock
+                continue
+            if tok.kind == "discard":
+                for pos in positions:
+                    self._drop(pos)
+                self.clock += ph.duration
+                continue
+            if tok.kind == "measure":
+                (pos,) = positions
+                (ax,) = self.touch(positions, self.clock)
+                bit = self.ex.creg.alloc()
+                forced = self.ex._next_forced()
+                be.measure(ax, bit, forced, ph.discard, ph.prob)
+                self.clock += ph.duration
+                if ph.discard:
+                    self.axis.pop(pos)
+                    self.last_access.pop(pos, None)
+                    self.ex._release_axis(ax)
+                else:
+                    self.last_access[pos] = self.clock
+                program.output[key] = [self.ex._deliver(bit)]
+                continue
+            if tok is ins.INSTR_SWAP and self.ex.swap_as_three_cnots:
+                # NoisyQPU composite instruction (quantum_processors.py:901-909)
+                a, b = positions
+                sub = QuantumProgram()
+                sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
+                sub.apply(ins.INSTR_CNOT, [b, a], predicate=predicate)
+                sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
+                self.execute_program(sub)
+                continue
+            axes = self.touch(positions, self.clock)
+            pred = -1 if predicate is None else predicate.index
+            if pred >= 0:
+                be.set_predicate(pred)
+            if len(axes) == 1:
+                be.apply_1q(axes[0], mat)
+            elif len(axes) == 2:
+                be.apply_2q(axes[0], axes[1], mat)
+            else:
+                raise NotImplementedError("only 1- and 2-qubit instructions exist upstream")
+            if ph.noise in ("depol1", "depolk") and ph.prob > 0:
+                be.depolarize(axes, ph.prob)
+            if pred >= 0:
+                be.set_predicate(-1)
+            self.clock += ph.duration
+            for pos in positions:
+                self.last_access[pos] = self.clock
+            program.output[key] = []
+        # a classical bit is dead once its predicated gate has been enqueued (stream order)
+        for b in {pr.index for *_, pr in program.instructions if pr is not None}:
+            self.ex.creg.release(b)
+        self.ex.programs_executed += 1
+        self.ex._events += 1
+
+
+class _Blocked(Exception):
+    pass
+
+
+class DQCExecutor:
+    """Runs ``qpu_op_dict`` on ``backend`` following the reference's interpreter.
+
+    Parameters
+    ----------
+    qpu_op_dict : dict   node name -> list of time slices -> list of op tuples
+    dqc : DQCSpec
+    backend : object implementing the engine vocabulary (``dqc_simulator_b200.engine.Engine``)
+    forced_outcomes : optional iterable of 0/1/-1 consumed in measurement issue order
+    host_branching : read outcomes on the host and branch like the reference (batch 1 only)
+    """
+
+    def __init__(self, qpu_op_dict, dqc, backend, forced_outcomes=None, host_branching=False,
+                 swap_as_three_cnots=True, creg_bits=64, axis_pool=None):
+        self.ops = qpu_op_dict
+        self.dqc = dqc if isinstance(dqc, DQCSpec) else DQCSpec(list(dqc))
+        self.backend = backend
+        self.host_branching = host_branching
+        self.swap_as_three_cnots = swap_as_three_cnots
+        self.creg = _CregAllocator(creg_bits)
+        self._forced = list(forced_outcomes) if forced_outcomes is not None else None
+        self._forced_i = 0
+        self.qpus = {name: QPU(self.dqc.qpu(name), self) for name in qpu_op_dict}
+        n_axes = backend.max_qubits if axis_pool is None else axis_pool
+        self._n_axes = n_axes
+        self._free_axes = list(range(n_axes))
+        self.peak_axes = 0
+        self.programs_executed = 0
+        self.measurements = 0
+        self.ebits = 0
+        self.mailbox = {}     # (src, dst) -> list of (arrival_time, payload)
+        self.ebit_requests = {}  # frozenset({a,b}) -> {node: (role, pos, time)}
+        self.logged_results = []  # (node, position, CBit|int) in issue order
+        self.end_time = 0.0
+        self.finished = False
+        self._events = 0
+
+    # ---- resources -------------------------------------------------------------
+    def _claim_axis(self, is_comm):
+        """Processing qubits take the lowest free axis, comm qubits the highest: while a comm
+        axis is free the active sub-block of the state stays contiguous in memory."""
+        if not self._free_axes:
+            raise RuntimeError("engine register too small for the live qubits of this circuit")
+        ax = self._free_axes.pop(-1 if is_comm else 0)
+        self.peak_axes = max(self.peak_axes, self._n_axes - len(self._free_axes))
+        return ax
+
+    def _release_axis(self, ax):
+        self._free_axes.append(ax)
+        self._free_axes.sort()
+
+    def _next_forced(self):
+        self.measurements += 1
+        if self._forced is None:
+            return -1
+        if self._forced_i >= len(self._forced):
+            return -1
+        v = self._forced[self._forced_i]
+        self._forced_i += 1
+        return int(v)
+
+    def _deliver(self, bit):
+        if self.host_branching:
+            v = int(self.backend.read_creg(bit)[0])
+            self.creg.release(bit)
+            return v
+        return CBit(bit)
+
+    # ---- classical network ------------------------------------------------------
+    def _send(self, src, dst, payload):
+        t = self.qpus[src].clock + self.dqc.classical_delay
+        self.mailbox.setdefault((src, dst), []).append((t, payload))
+        self._events += 1
+
+    def _recv(self, src, dst):
+        """generator: blocks until a message from src is available."""
+        box = self.mailbox.setdefault((src, dst), [])
+        while not box:
+            yield "recv"
+        t, payload = box.pop(0)
+        self._events += 1
+        q = self.qpus[dst]
+        q.clock = max(q.clock, t)
+        return payload
+
+    def _request_entanglement(self, node, role, other, pos):
+        """Rendezvous of the two link-layer requests, then the ebit lands on both comm
+        positions (``dqc_control.py:198-264``; ``physical_layer.py:206-335, 451-479``).
+        Timeline: client handshake -> server reply (one classical hop each way) ->
+        source trigger -> both photons arrive ``ent_delay`` later."""
+        key = frozenset((node, other))
+        link = self.ebit_requests.setdefault(key, {"req": {}, "done": {}})
+        link["req"][node] = (pos, self.qpus[node].clock)
+        self._events += 1
+        if other in link["req"]:
+            first, second = sorted((node, other))   # qout0 -> side A, qout1 -> side B
+            (pa, ta), (pb, tb) = link["req"][first], link["req"][second]
+            t_arrive = max(ta, tb) + 2 * self.dqc.classical_delay + self.dqc.ent_delay
+            qa, qb = self.qpus[first], self.qpus[second]
+            qa._drop(pa)
+            qb._drop(pb)
+            ax_a = self._claim_axis(True)
+            ax_b = self._claim_axis(True)
+            self.backend.inject_2q(ax_a, ax_b, self.dqc.state4distribution, self.dqc.ebit_is_dm)
+            qa.axis[pa], qb.axis[pb] = ax_a, ax_b
+            qa.last_access[pa] = qb.last_access[pb] = t_arrive
+            self.ebits += 1
+            link["req"] = {}
+            link["done"] = {first: t_arrive, second: t_arrive}
+        while node not in link["done"]:
+            yield "ebit"
+        t_arrive = link["done"].pop(node)
+        self._events += 1
+        self.qpus[node].clock = max(self.qpus[node].clock, t_arrive)
+
+    # ---- interpreter ------------------------------------------------------------
+    def _flush(self, q, program):
+        q.execute_program(program)
+        return QuantumProgram()
+
+    def _apply_if(self, program, instruction, pos, outcome):
+        """X / Z correction conditioned on a measurement outcome."""
+        if isinstance(outcome, CBit):
+            program.apply(instruction, pos, predicate=outcome)
+        elif outcome == 1:
+            program.apply(instruction, pos)
+        elif outcome != 0:
+            raise ValueError(
+                "Measurement result must be an integer with value 0 or 1. The current value, "
+                f"{outcome}, does not meet this criteria.")
+
+    def _node_process(self, name, slice_ops):
+        q = self.qpus[name]
+        program = QuantumProgram()
+        comm = float("nan")
+        for op in slice_ops:
+            last = op[-1]
+            if len(op) == 2:                                   # single-qubit gate / INIT
+                program.apply(_instr_of(op[0]), op[1], operator=_op_of(op[0]))
+            elif last == "logged":                              # dqc_control.py:754-791
+                program = self._flush(q, program)
+                program.apply(_instr_of(op[0]), op[1], operator=_op_of(op[0]), output_key="result")
+                q.execute_program(program)
+                res = program.output["result"]
+                self.logged_results.append((name, op[1], res[0] if res else None))
+                program = QuantumProgram()
+            elif last == "distribute_ebit":                     # dqc_control.py:803-832
+                pos = q.comm_qubits_free[0]
+                yield from self._request_entanglement(name, op[1], op[0], pos)
+                del q.comm_qubits_free[0]
+            elif isinstance(last, str) and op[-2] in ("cat", "tp"):
+                if len(op) == 4:
+                    data, other, scheme, role = op
+                else:
+                    data = None
+                    other, scheme, role = op
+                if scheme == "cat":
+                    comm, program = yield from self._cat(q, role, program, other, data, comm)
+                else:
+                    comm, program = yield from self._tp(q, role, program, other, data, comm)
+            elif isinstance(last, (int, np.integer)):           # local two-qubit gate
+                q0 = comm if op[1] == -1 else op[1]
+                program.apply(_instr_of(op[0]), [q0, op[2]], operator=_op_of(op[0]))
+            else:
+                raise ValueError(f"cannot interpret op {op!r}")
+        self._flush(q, program)
+
+    def _no_comm_free(self, q):
+        if not q.comm_qubits_free:
+            raise Exception(f"Scheduling error: No comm-qubits free. There are too many remote "
+                            f"gates on {q.name} in this time slice")
+
+    def _cat(self, q, role, program, other, data, comm):
+        name = q.name
+        if role == "entangle":                                  # dqc_control.py:266-314
+            program = self._flush(q, program)
+            self._no_comm_free(q)
+            c = q.comm_qubits_free[0]
+            yield from self._request_entanglement(name, "client", other, c)
+            program.apply(ins.INSTR_CNOT, [data, c])
+            program.apply(ins.INSTR_MEASURE, [c], output_key="ma")
+            q.execute_program(program)
+            (ma,) = program.output["ma"]
+            self._send(name, other, ma)
+            return comm, QuantumProgram()
+        if role == "correct":                                   # :316-359
+            program = self._flush(q, program)
+            self._no_comm_free(q)
+            c = q.comm_qubits_free[0]
+            yield from self._request_entanglement(name, "server", other, c)
+            del q.comm_qubits_free[0]
+            ma = yield from self._recv(other, name)
+            self._apply_if(program, ins.INSTR_X, c, ma)
+            return c, program
+        if role == "disentangle_start":                         # :361-380
+            program.apply(ins.INSTR_H, comm)
+            program.apply(ins.INSTR_MEASURE, comm, output_key="mb")
+            q.execute_program(program)
+            (mb,) = program.output["mb"]
+            self._send(name, other, mb)
+            q.comm_qubits_free = sorted(q.comm_qubits_free + [comm])
+            return comm, QuantumProgram()
+        if role == "disentangle_end":                           # :382-403
+            mb = yield from self._recv(other, name)
+            if isinstance(mb, CBit) or mb == 1:
+                self._apply_if(program, ins.INSTR_Z, data, mb)
+                q.execute_program(program)
+                program = QuantumProgram()
+            elif mb != 0:
+                raise ValueError("Measurement result must be an integer with value 0 or 1. "
+                                 f"The current value, {mb}, does not meet this criteria.")
+            return comm, program
+        raise ValueError("final element of gate_tuple is not valid role")
+
+    def _tp(self, q, role, program, other, data, comm):
+        name = q.name
+        if role == "bsm":                                       # dqc_control.py:405-489
+            program = self._flush(q, program)
+            self._no_comm_free(q)
+            c = q.comm_qubits_free[0]
+            if data == -1 and len(q.comm_qubits_free) < len(q.comm_qubit_positions):
+                data = c - 1
+            yield from self._request_entanglement(name, "client", other, c)
+            program.apply(ins.INSTR_CNOT, [data, c])
+            program.apply(ins.INSTR_H, [data])
+            program.apply(ins.INSTR_MEASURE, [c], output_key="m1")
+            program.apply(ins.INSTR_MEASURE, [data], output_key="m2")
+            q.execute_program(program)
+            (m1,) = program.output["m1"]
+            (m2,) = program.output["m2"]
+            program = QuantumProgram()
+            program.apply(ins.INSTR_INIT, data)
+            q.execute_program(program)
+            self._send(name, other, (m1, m2))
+            if data in q.comm_qubit_positions:
+                q.comm_qubits_free = sorted(q.comm_qubits_free + [data])
+            return comm, QuantumProgram()
+        flags = {  # role -> (reserve_comm_qubit, swap_commNdata, manual)   :701-746
+            "correct": (True, False, False),
+            "correct4tele_only": (False, False, False),
+            "swap_then_correct": (False, True, False),
+            "correct_manually": (True, False, True),
+        }
+        if role not in flags:
+            raise ValueError(f"final element, {role} of gate_tuple is not a valid role")
+        reserve, swap, manual = flags[role]                     # :508-613
+        program = self._flush(q, program)
+        self._no_comm_free(q)
+        c = data if manual else q.comm_qubits_free[0]
+        if reserve:
+            del q.comm_qubits_free[q.comm_qubits_free.index(c)]
+        yield from self._request_entanglement(name, "server", other, c)
+        m1, m2 = yield from self._recv(other, name)
+        tgt = c
+        if swap:
+            program.apply(ins.INSTR_SWAP, [c, data])
+            tgt = data
+        self._apply_if(program, ins.INSTR_X, tgt, m1)
+        self._apply_if(program, ins.INSTR_Z, tgt, m2)
+        q.execute_program(program)
+        return c, QuantumProgram()
+
+    # ---- master ------------------------------------------------------------------
+    def run(self):
+        """Time-slice loop of ``DQCMasterProtocol.run`` (``dqc_control.py:1170-1202``): all
+        QPUs start a slice together and the next slice starts when every QPU has finished."""
+        n_slices = max(len(v) for v in self.ops.values())
+        for s in range(n_slices):
+            start = max(q.clock for q in self.qpus.values())
+            procs = {}
+            for name, slices in self.ops.items():
+                if s < len(slices):
+                    self.qpus[name].clock = start
+                    procs[name] = self._node_process(name, slices[s])
+            while procs:
+                progressed = False
+                for name in list(procs):
+                    try:
+                        before = self._progress_marker()
+                        next(procs[name])
+                        if self._progress_marker() != before:
+                            progressed = True
+                    except StopIteration:
+                        del procs[name]
+                        progressed = True
+                if not progressed and procs:
+                    # one more full round with no state change anywhere = deadlock
+                    if getattr(self, "_stalled", False):
+                        raise UnfinishedQuantumCircuitError(
+                            "Not all operations in the quantum circuit have run. Evaluation "
+                            f"stopped in time slice {s} out of {n_slices - 1}; blocked QPUs: "
+                            f"{sorted(procs)}")
+                    self._stalled = True
+                else:
+                    self._stalled = False
+        self.end_time = max(q.clock for q in self.qpus.values())
+        self.finished = True
+        return self
+
+    def _progress_marker(self):
+        return self._events
+
+    # ---- read-out ----------------------------------------------------------------
+    def axes_of(self, qubits, apply_memory_noise=True):
+        """[(position, node_name), ...] -> engine axes, like ``qmemory.pop(positions)`` at the
+        end of the run (memory noise up to ``end_time``; ``util/helper.py:136-151``)."""
+        axes = []
+        for pos, node in qubits:
+            q = self.qpus[node if isinstance(node, str) else node.name]
+            if apply_memory_noise:
+                (ax,) = q.touch([pos], self.end_time)
+                q.last_access[pos] = self.end_time
+            else:
+                ax = q._materialise(pos)
+            axes.append(ax)
+        return axes
+
+    def processing_qubits(self):
+        """All initialised processing qubits, node by node (``run_experiment.py:38-43``)."""
+        out = []
+        for name, q in self.qpus.items():
+            for pos in q.processing_qubit_positions:
+                if q.occupied(pos):
+                    out.append((pos, name))
+        return out
+
+
+def _instr_of(head):
+    return head[0] if isinstance(head, (tuple, list)) else head
+
+
+def _op_of(head):
+    return head[1] if isinstance(head, (tuple, list)) else None

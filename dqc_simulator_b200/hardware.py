@@ -1,0 +1,122 @@
+"""Hardware specification consumed by the executor: which noise channel and which simulated
+duration attach to which instruction.
+
+Mirrors the *parameters* of the reference's hardware layer without any of its DES plumbing:
+
+* :class:`QPUSpec`  <- ``QPU`` / ``NoisyQPU`` (``hardware/quantum_processors.py:83-123,
+  796-909``): memory layout (comm positions first, then processing,
+  ``quantum_processors.py:147-181``), the physical-instruction table of
+  ``_phys_instructions_4_standard_lib_gates_and_convenience_ops`` (``:306-457``) and the
+  SWAP = 3 CNOT composite (``:901-909``).
+* :class:`DQCSpec`  <- ``DQC`` (``hardware/dqc_creation.py:443-617``) with a
+  ``BlackBoxEntanglingQsourceConnection`` (``hardware/connections.py:85-172``):
+  ``state4distribution`` + ``delay`` and 2 m classical fibres (``dqc_creation.py:512-516``;
+  ``FibreDelayModel`` default c = 200 000 km/s).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_S2 = 1.0 / np.sqrt(2.0)
+B00 = np.array([_S2, 0, 0, _S2], dtype=complex)  # ks.b00
+
+
+def werner_state(F):
+    """``qlib/states.py:63-84``: F |b00><b00| + (1-F)/3 (|b01><b01| + |b10><b10| + |b11><b11|)."""
+    b01 = np.array([0, _S2, _S2, 0], dtype=complex)
+    b10 = np.array([_S2, 0, 0, -_S2], dtype=complex)
+    b11 = np.array([0, _S2, -_S2, 0], dtype=complex)
+    out = F * np.outer(B00, B00.conj())
+    for b in (b01, b10, b11):
+        out = out + (1 - F) / 3 * np.outer(b, b.conj())
+    return out
+
+
+@dataclass
+class PhysInstr:
+    duration: float
+    noise: str = "none"  # "none" | "depol1" | "depolk" | "flip_before"
+    prob: float = 0.0
+    discard: bool = False
+
+
+@dataclass
+class QPUSpec:
+    """Defaults are ``NoisyQPU``'s (``quantum_processors.py:849-866``)."""
+    name: str = "node_0"
+    num_positions: int = 20
+    num_comm_qubits: int = 2
+    p_depolar_error_cnot: float = 0.0
+    single_qubit_gate_error_prob: float = 0.0
+    meas_error_prob: float = 0.0
+    comm_qubit_depolar_rate: float = 0.0
+    proc_qubit_depolar_rate: float = 0.0
+    single_qubit_gate_time: float = 135e3
+    two_qubit_gate_time: float = 600e3
+    measurement_time: float = 600e4
+    init_time: float = 3.0
+    measure_discards: bool = True
+    # optional extra memory channel per position type (north_star: dephasing / amplitude
+    # damping).  Not wired by any reference hardware spec; rates in Hz.
+    mem_dephase_rate: float = 0.0
+    mem_amp_damp_rate: float = 0.0
+
+    @property
+    def comm_qubit_positions(self):
+        return list(range(self.num_comm_qubits))
+
+    @property
+    def processing_qubit_positions(self):
+        return list(range(self.num_comm_qubits, self.num_positions))
+
+    def mem_rate(self, pos):
+        return self.comm_qubit_depolar_rate if pos < self.num_comm_qubits else self.proc_qubit_depolar_rate
+
+    def phys(self, token):
+        """Row of the physical-instruction table for an instruction token."""
+        if token.kind == "init":
+            return PhysInstr(self.init_time)
+        if token.kind == "measure":
+            return PhysInstr(self.measurement_time, "flip_before", self.meas_error_prob,
+                             discard=self.measure_discards)
+        if token.kind == "discard":
+            return PhysInstr(self.single_qubit_gate_time, discard=True)
+        if "neglig" in token.name or "neglible" in token.name:
+            return PhysInstr(3.0)
+        if token.num_qubits == 1:
+            return PhysInstr(self.single_qubit_gate_time, "depol1", self.single_qubit_gate_error_prob)
+        return PhysInstr(self.two_qubit_gate_time, "depolk", self.p_depolar_error_cnot)
+
+
+@dataclass
+class DQCSpec:
+    qpus: list = field(default_factory=list)
+    state4distribution: np.ndarray = None  # ket (4,) or dm (4,4); default ks.b00
+    ent_delay: float = 1e9 / 182.0         # ns (examples/setup_hardware.py:18,38)
+    node_separation_km: float = 2e-3       # dqc_creation.py:512-516
+    handshake_wait: float = 600e3          # physical_layer.py:286
+
+    def __post_init__(self):
+        if self.state4distribution is None:
+            self.state4distribution = B00
+
+    @property
+    def classical_delay(self):
+        return 1e9 * self.node_separation_km / 200000.0  # FibreDelayModel [NS-doc]
+
+    @property
+    def ebit_is_dm(self):
+        return np.asarray(self.state4distribution).size == 16
+
+    def qpu(self, name):
+        for q in self.qpus:
+            if q.name == name:
+                return q
+        raise KeyError(name)
+
+    @classmethod
+    def uniform(cls, num_qpus, state4distribution=None, ent_delay=1e9 / 182.0, **qpu_kwargs):
+        """Like ``DQC(entangling_connection_class, num_qpus, ..., qpu_class=NoisyQPU, **kw)``:
+        nodes are named ``node_{i}`` (``dqc_creation.py:541-548``)."""
+        return cls([QPUSpec(name=f"node_{i}", **qpu_kwargs) for i in range(num_qpus)],
+                   state4distribution, ent_delay)
