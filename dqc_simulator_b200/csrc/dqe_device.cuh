@@ -1,0 +1,685 @@
+// dqe_device.cuh -- device side of the B200 quantum-state engine (sm_100a).
+//
+// One kernel does the heavy lifting: k_tile_pass.  A *pass* reads a tile of 2^t complex128
+// amplitudes of one shot into shared memory (the lowest live bits of the register -- long
+// contiguous runs in HBM -- plus the few high bits the queued ops mix), runs a micro-program
+// of gate / channel / measurement ops on the tile while it is on chip, and writes it back:
+// one HBM read + one HBM write per pass, however many ops were queued.
+//
+// State layout (see include/dqc_engine.h): ket = 2^P amplitudes per shot, P = max_qubits;
+// dm = 4^max_qubits, P = 2*max_qubits, row bits above column bits, so a density matrix is
+// handled as a "ket" on 2n bits: U rho U^dagger is U on the row bit and conj(U) on the column
+// bit, and a channel is a 4x4 superoperator on (row bit, column bit) -- one pass over rho.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dqe {
+
+enum OpType : int32_t {
+  OP_MAT1 = 1,        // 2x2 on one tile bit, optional control mask
+  OP_MAT2 = 2,        // 4x4 on two tile bits (ket 2q gate, dm one-sided 2q, dm 1q superoperator)
+  OP_DIAG = 3,        // phase table over <= 4 bits (tile or outer)
+  OP_PAULI1 = 4,      // dm 1q Pauli channel, closed form on (row, col) bits
+  OP_DEPOL2 = 5,      // dm 2q depolarising, closed form on (ra, rb, ca, cb)
+  OP_PROBS = 6,       // partial outcome probabilities of one axis -> partials[]
+  OP_COLLAPSE = 7,    // project on recorded outcome, renormalise, optional move to |0>
+  OP_TRACE = 8,       // dm partial trace of one axis (result left in the |0><0| block)
+  OP_INJECT = 9,      // write a 2-qubit state onto two fresh axes
+  OP_PAULI_SAMPLED = 10,  // ket: apply a Pauli string drawn per shot from Philox
+  OP_MAT1X2 = 11,     // dm controlled/one-qubit gate, row side + column side in one sweep
+};
+
+constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
+constexpr int kMaxOpsPerPass = 48;
+constexpr int kThreads = 256;
+
+struct __align__(16) MicroOp {
+  int32_t type;
+  int32_t pred_bit;     // creg bit that must be 1 for the shot, -1 = unconditional
+  uint32_t lctrl;       // control mask, tile-local bits
+  uint32_t nb;          // number of entries of b[] in use
+  uint64_t octrl;       // control mask, physical bits outside the tile (tested on the tile base)
+  uint8_t b[8];         // bit positions (tile-local, or kOuter + physical)
+  int32_t c_off;        // offset of this op's constants in the pass constant pool (double2 units)
+  int32_t flags;
+  int32_t aux;          // PROBS: physical bit of the axis; sampled ops: draw index
+  uint32_t lctrl2;      // MAT1X2: control mask of the column side
+  uint64_t octrl2;
+  double p[4];
+};
+
+struct Seg {  // bits [src, src+len) of a dense index go to physical bits [dst, dst+len)
+  uint8_t src, len, dst, pad;
+};
+
+struct MeasRec {
+  double scale;
+  int32_t outcome;
+  int32_t pad;
+};
+
+struct PassParams {
+  double2* state;
+  const uint64_t* creg;
+  double* partials;
+  const MeasRec* rec;
+  const MicroOp* ops;
+  const double2* consts;
+  uint64_t seed, shot_offset;
+  int32_t nops, t, P, nmax;
+  int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
+  int32_t store_back, pad0;
+  Seg tile_segs[16];
+  Seg outer_segs[24];
+};
+
+// ------------------------------------------------------------------------------------------
+// complex helpers
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 acc) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double2 conj2(double2 a) { return make_double2(a.x, -a.y); }
+
+// insert a zero bit at position j
+__device__ __forceinline__ uint32_t ins0(uint32_t p, int j) {
+  const uint32_t lo = (1u << j) - 1u;
+  return ((p & ~lo) << 1) | (p & lo);
+}
+
+template <typename SegT>
+__device__ __forceinline__ uint64_t deposit(uint64_t x, const SegT* segs, int n) {
+  uint64_t r = 0;
+  for (int s = 0; s < n; ++s) {
+    r |= ((x >> segs[s].src) & ((1ull << segs[s].len) - 1ull)) << segs[s].dst;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (shot_lo, shot_hi, draw_lo, draw_hi), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ double uniform53(uint32_t hi, uint32_t lo) {
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ void shot_uniforms(uint64_t seed, uint64_t shot, uint64_t draw, double& u, double& u2) {
+  uint32_t c[4] = {(uint32_t)shot, (uint32_t)(shot >> 32), (uint32_t)draw, (uint32_t)(draw >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  u = uniform53(c[0], c[1]);
+  u2 = uniform53(c[2], c[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// micro-ops on the shared-memory tile
+__device__ __forceinline__ void apply_mat1(double2* tile, uint32_t T, int j, uint32_t lc,
+                                           double2 m00, double2 m01, double2 m10, double2 m11) {
+  for (uint32_t p = threadIdx.x; p < (T >> 1); p += kThreads) {
+    const uint32_t i0 = ins0(p, j);
+    if ((i0 & lc) != lc) continue;
+    const uint32_t i1 = i0 | (1u << j);
+    const double2 a = tile[i0], b = tile[i1];
+    tile[i0] = cfma(m01, b, cmul(m00, a));
+    tile[i1] = cfma(m11, b, cmul(m10, a));
+  }
+}
+
+__device__ __forceinline__ void op_mat1(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
+  apply_mat1(tile, T, op.b[0], op.lctrl, __ldg(cs + 0), __ldg(cs + 1), __ldg(cs + 2), __ldg(cs + 3));
+}
+
+// dm: U on the row bit (control mask lctrl) then conj(U) on the column bit (control lctrl2),
+// on the 4 elements (r, c) in registers -- one shared-memory round trip for U rho U^dagger.
+__device__ __forceinline__ void op_mat1x2(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
+                                          bool row_on, bool col_on) {
+  const int jr = op.b[0], jc = op.b[1];
+  const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+  const double2 m00 = __ldg(cs + 0), m01 = __ldg(cs + 1), m10 = __ldg(cs + 2), m11 = __ldg(cs + 3);
+  const double2 n00 = conj2(m00), n01 = conj2(m01), n10 = conj2(m10), n11 = conj2(m11);
+  const uint32_t lr = op.lctrl, lc = op.lctrl2;
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+    const bool do_r = row_on && ((i00 & lr) == lr);   // row-side control lives on row bits
+    const bool do_c = col_on && ((i00 & lc) == lc);
+    if (!do_r && !do_c) continue;
+    const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+    double2 e00 = tile[i00], e01 = tile[i01], e10 = tile[i10], e11 = tile[i11];
+    if (do_r) {  // mixes r for fixed c
+      double2 a = e00, b = e10;
+      e00 = cfma(m01, b, cmul(m00, a)); e10 = cfma(m11, b, cmul(m10, a));
+      a = e01; b = e11;
+      e01 = cfma(m01, b, cmul(m00, a)); e11 = cfma(m11, b, cmul(m10, a));
+    }
+    if (do_c) {  // mixes c for fixed r
+      double2 a = e00, b = e01;
+      e00 = cfma(n01, b, cmul(n00, a)); e01 = cfma(n11, b, cmul(n10, a));
+      a = e10; b = e11;
+      e10 = cfma(n01, b, cmul(n00, a)); e11 = cfma(n11, b, cmul(n10, a));
+    }
+    tile[i00] = e00; tile[i01] = e01; tile[i10] = e10; tile[i11] = e11;
+  }
+}
+
+__device__ __forceinline__ void op_mat2(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
+  const int jh = op.b[0], jl = op.b[1];
+  const int jlo = jh < jl ? jh : jl, jhi = jh < jl ? jl : jh;
+  const uint32_t lc = op.lctrl;
+  double2 m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = __ldg(cs + i);
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    const uint32_t i0 = ins0(ins0(p, jlo), jhi);
+    if ((i0 & lc) != lc) continue;
+    const uint32_t i1 = i0 | (1u << jl), i2 = i0 | (1u << jh), i3 = i1 | (1u << jh);
+    const double2 v0 = tile[i0], v1 = tile[i1], v2 = tile[i2], v3 = tile[i3];
+    tile[i0] = cfma(m[3], v3, cfma(m[2], v2, cfma(m[1], v1, cmul(m[0], v0))));
+    tile[i1] = cfma(m[7], v3, cfma(m[6], v2, cfma(m[5], v1, cmul(m[4], v0))));
+    tile[i2] = cfma(m[11], v3, cfma(m[10], v2, cfma(m[9], v1, cmul(m[8], v0))));
+    tile[i3] = cfma(m[15], v3, cfma(m[14], v2, cfma(m[13], v1, cmul(m[12], v0))));
+  }
+}
+
+__device__ __forceinline__ void op_diag(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
+                                        uint64_t base) {
+  const int nb = op.nb;
+  uint32_t fixed = 0;
+  int lb[4], ls[4], nl = 0;
+  for (int s = 0; s < nb; ++s) {
+    const int sh = nb - 1 - s;
+    if (op.b[s] >= kOuter) fixed |= (uint32_t)((base >> (op.b[s] - kOuter)) & 1ull) << sh;
+    else { lb[nl] = op.b[s]; ls[nl] = sh; ++nl; }
+  }
+  if (nl == 0) {
+    const double2 d = __ldg(cs + fixed);
+    for (uint32_t i = threadIdx.x; i < T; i += kThreads) tile[i] = cmul(tile[i], d);
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+    uint32_t idx = fixed;
+    for (int s = 0; s < nl; ++s) idx |= ((i >> lb[s]) & 1u) << ls[s];
+    tile[i] = cmul(tile[i], __ldg(cs + idx));
+  }
+}
+
+__device__ __forceinline__ void op_pauli1(double2* tile, uint32_t T, const MicroOp& op) {
+  const int jr = op.b[0], jc = op.b[1];
+  const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+  const double a = op.p[0], b = op.p[1], c = op.p[2], d = op.p[3];
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+    const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+    const double2 e00 = tile[i00], e01 = tile[i01], e10 = tile[i10], e11 = tile[i11];
+    tile[i00] = make_double2(fma(a, e00.x, b * e11.x), fma(a, e00.y, b * e11.y));
+    tile[i11] = make_double2(fma(a, e11.x, b * e00.x), fma(a, e11.y, b * e00.y));
+    tile[i01] = make_double2(fma(c, e01.x, d * e10.x), fma(c, e01.y, d * e10.y));
+    tile[i10] = make_double2(fma(c, e10.x, d * e01.x), fma(c, e10.y, d * e01.y));
+  }
+}
+
+__device__ __forceinline__ uint32_t ins0_4(uint32_t p, const int* sorted) {
+  p = ins0(p, sorted[0]); p = ins0(p, sorted[1]); p = ins0(p, sorted[2]); p = ins0(p, sorted[3]);
+  return p;
+}
+__device__ __forceinline__ void sort4(const uint8_t* b, int* s) {
+  s[0] = b[0]; s[1] = b[1]; s[2] = b[2]; s[3] = b[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3 - i; ++j)
+      if (s[j] > s[j + 1]) { int t = s[j]; s[j] = s[j + 1]; s[j + 1] = t; }
+}
+
+// (1-p) rho + p * (I/4 (x) Tr_ab rho) on bits (ra, rb, ca, cb)
+__device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const MicroOp& op) {
+  int s[4];
+  sort4(op.b, s);
+  const uint32_t mra = 1u << op.b[0], mrb = 1u << op.b[1], mca = 1u << op.b[2], mcb = 1u << op.b[3];
+  const double pp = op.p[0], keep = 1.0 - pp, mix = 0.25 * pp;
+  for (uint32_t p = threadIdx.x; p < (T >> 4); p += kThreads) {
+    const uint32_t i0 = ins0_4(p, s);
+    const uint32_t d0 = i0, d1 = i0 | mrb | mcb, d2 = i0 | mra | mca, d3 = d1 | mra | mca;
+    const double2 v0 = tile[d0], v1 = tile[d1], v2 = tile[d2], v3 = tile[d3];
+    const double sx = mix * (v0.x + v1.x + v2.x + v3.x), sy = mix * (v0.y + v1.y + v2.y + v3.y);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t ro = ((r & 2) ? mra : 0u) | ((r & 1) ? mrb : 0u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t idx = i0 | ro | ((c & 2) ? mca : 0u) | ((c & 1) ? mcb : 0u);
+        double2 v = tile[idx];
+        v.x *= keep; v.y *= keep;
+        if (r == c) { v.x += sx; v.y += sy; }
+        tile[idx] = v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                         uint64_t base, uint64_t blk, double* red) {
+  double a0 = 0.0, a1 = 0.0;
+  const int abit = op.aux;
+  if (pp.formalism == 0) {
+    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+      const uint64_t phys = base | deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs);
+      const double2 v = tile[i];
+      const double w = fma(v.x, v.x, v.y * v.y);
+      if ((phys >> abit) & 1ull) a1 += w; else a0 += w;
+    }
+  } else {
+    const uint64_t cm = (1ull << pp.nmax) - 1ull;
+    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+      const uint64_t phys = base | deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs);
+      if ((phys >> pp.nmax) == (phys & cm)) {
+        const double w = tile[i].x;
+        if ((phys >> abit) & 1ull) a1 += w; else a0 += w;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+    pp.partials[2 * blk] = s0;
+    pp.partials[2 * blk + 1] = s1;
+  }
+}
+
+__device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                            uint64_t shot) {
+  const MeasRec r = pp.rec[shot];
+  const int m = r.outcome;
+  const double sc = r.scale;
+  const bool discard = op.flags & 1;
+  const double2 zero = make_double2(0.0, 0.0);
+  if (pp.formalism == 0) {
+    const int j = op.b[0];
+    for (uint32_t p = threadIdx.x; p < (T >> 1); p += kThreads) {
+      const uint32_t i0 = ins0(p, j), i1 = i0 | (1u << j);
+      const double2 kept = cscale(tile[m ? i1 : i0], sc);
+      if (discard || m == 0) { tile[i0] = kept; tile[i1] = zero; }
+      else { tile[i1] = kept; tile[i0] = zero; }
+    }
+  } else {
+    const int jr = op.b[0], jc = op.b[1];
+    const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+    const double e = op.p[0];
+    for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+      const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+      const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+      const double2 same = tile[m ? i11 : i00], flip = tile[m ? i00 : i11];
+      double2 kept;
+      kept.x = ((1.0 - e) * same.x + e * flip.x) * sc;
+      kept.y = ((1.0 - e) * same.y + e * flip.y) * sc;
+      tile[i01] = zero; tile[i10] = zero;
+      if (discard || m == 0) { tile[i00] = kept; tile[i11] = zero; }
+      else { tile[i11] = kept; tile[i00] = zero; }
+    }
+  }
+}
+
+__device__ __forceinline__ void op_trace(double2* tile, uint32_t T, const MicroOp& op) {
+  const int jr = op.b[0], jc = op.b[1];
+  const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+  const double2 zero = make_double2(0.0, 0.0);
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+    const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+    tile[i00] = cadd(tile[i00], tile[i11]);
+    tile[i01] = zero; tile[i10] = zero; tile[i11] = zero;
+  }
+}
+
+__device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                          const double2* cs, uint64_t shot) {
+  if (pp.formalism == 0) {
+    const int ja = op.b[0], jb = op.b[1];
+    const int jlo = ja < jb ? ja : jb, jhi = ja < jb ? jb : ja;
+    int choice = 0;
+    if (op.flags & 2) {  // mixture: component drawn per shot
+      double u, u2;
+      shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
+      choice = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
+    }
+    const double2 k0 = __ldg(cs + 4 * choice), k1 = __ldg(cs + 4 * choice + 1),
+                  k2 = __ldg(cs + 4 * choice + 2), k3 = __ldg(cs + 4 * choice + 3);
+    for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+      const uint32_t i0 = ins0(ins0(p, jlo), jhi);
+      const double2 x = tile[i0];
+      tile[i0] = cmul(x, k0);
+      tile[i0 | (1u << jb)] = cmul(x, k1);
+      tile[i0 | (1u << ja)] = cmul(x, k2);
+      tile[i0 | (1u << ja) | (1u << jb)] = cmul(x, k3);
+    }
+  } else {
+    int s[4];
+    sort4(op.b, s);
+    const uint32_t mra = 1u << op.b[0], mrb = 1u << op.b[1], mca = 1u << op.b[2], mcb = 1u << op.b[3];
+    for (uint32_t p = threadIdx.x; p < (T >> 4); p += kThreads) {
+      const uint32_t i0 = ins0_4(p, s);
+      const double2 x = tile[i0];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t ro = ((r & 2) ? mra : 0u) | ((r & 1) ? mrb : 0u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t idx = i0 | ro | ((c & 2) ? mca : 0u) | ((c & 1) ? mcb : 0u);
+          tile[idx] = cmul(x, __ldg(cs + 4 * r + c));
+        }
+      }
+    }
+  }
+}
+
+// ket: Pauli string drawn per shot.  flags: 0 = 1q channel with cumulative thresholds p[0..2] on u,
+// 1 = k-qubit depolarising (w0 = p[0], w = p[1]) on u, 2 = X if u2 < p[0] (measurement flip).
+__device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, const MicroOp& op,
+                                                 const PassParams& pp, uint64_t shot) {
+  double u, u2;
+  shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
+  const int k = op.nb;
+  int digits[2] = {0, 0};
+  if (op.flags == 0) {
+    digits[0] = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
+  } else if (op.flags == 1) {
+    const double w0 = op.p[0], w = op.p[1];
+    const int n = (k == 1) ? 4 : 16;
+    long long s = 0;
+    if (!(u < w0) && w > 0.0) {
+      s = 1 + (long long)floor((u - w0) / w);
+      if (s > n - 1) s = n - 1;
+    }
+    if (k == 1) digits[0] = (int)s;
+    else { digits[0] = (int)(s >> 2) & 3; digits[1] = (int)s & 3; }
+  } else {
+    digits[0] = (u2 < op.p[0]) ? 1 : 0;
+  }
+  const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), mone = make_double2(-1.0, 0.0);
+  const double2 pi = make_double2(0.0, 1.0), mi = make_double2(0.0, -1.0);
+  for (int q = 0; q < k; ++q) {
+    const int d = digits[q];
+    if (d == 0) continue;
+    if (q > 0) __syncthreads();
+    if (d == 1) apply_mat1(tile, T, op.b[q], 0u, zero, one, one, zero);
+    else if (d == 2) apply_mat1(tile, T, op.b[q], 0u, zero, mi, pi, zero);
+    else apply_mat1(tile, T, op.b[q], 0u, one, zero, zero, mone);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_tile_pass(const __grid_constant__ PassParams pp) {
+  extern __shared__ double2 tile[];
+  __shared__ MicroOp s_ops[kMaxOpsPerPass];
+  __shared__ double s_red[2 * (kThreads / 32)];
+
+  const uint64_t blk = blockIdx.x;
+  const uint64_t shot = blk >> pp.outer_bits;
+  const uint64_t tix = blk & ((1ull << pp.outer_bits) - 1ull);
+  const uint64_t base = deposit(tix, pp.outer_segs, pp.n_outer_segs);
+  double2* __restrict__ sp = pp.state + (shot << pp.P) + base;
+  const uint32_t T = 1u << pp.t;
+
+  {  // stage the micro-program
+    const int nw = pp.nops * (int)(sizeof(MicroOp) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.ops);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
+    for (int i = threadIdx.x; i < nw; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  // tile load: local index i -> physical offset; the low segment is contiguous in HBM
+  const int c0 = pp.tile_segs[0].len;  // tile_segs[0] always maps local bits [0,c0) to physical [0,c0)... or dst>0
+  if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+    const int nhs = pp.n_tile_segs - 1;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+      const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
+      tile[i] = sp[off];
+    }
+  } else {
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < T; i += kThreads)
+      tile[i] = sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)];
+  }
+  const uint64_t cw = pp.creg[shot];
+  __syncthreads();
+
+  for (int o = 0; o < pp.nops; ++o) {
+    const MicroOp& op = s_ops[o];
+    if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
+    const double2* cs = pp.consts + op.c_off;
+    switch (op.type) {
+      case OP_MAT1:
+        if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
+        break;
+      case OP_MAT1X2: {
+        const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
+        if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
+        break;
+      }
+      case OP_MAT2:
+        if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
+        break;
+      case OP_DIAG: op_diag(tile, T, op, cs, base); break;
+      case OP_PAULI1: op_pauli1(tile, T, op); break;
+      case OP_DEPOL2: op_depol2(tile, T, op); break;
+      case OP_PROBS: op_probs(tile, T, op, pp, base, blk, s_red); break;
+      case OP_COLLAPSE: op_collapse(tile, T, op, pp, shot); break;
+      case OP_TRACE: op_trace(tile, T, op); break;
+      case OP_INJECT: op_inject(tile, T, op, pp, cs, shot); break;
+      case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
+      default: break;
+    }
+    __syncthreads();
+  }
+
+  if (pp.store_back) {
+    if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+      const int nhs = pp.n_tile_segs - 1;
+#pragma unroll 4
+      for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+        const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
+        sp[off] = tile[i];
+      }
+    } else {
+#pragma unroll 4
+      for (uint32_t i = threadIdx.x; i < T; i += kThreads)
+        sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)] = tile[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// measurement finish: one warp per shot sums the tile partials in a fixed order, adds the
+// X-flip noise, draws the outcome from Philox and records (outcome, renormalisation) + creg bit.
+struct FinishParams {
+  const double* partials;
+  MeasRec* rec;
+  uint64_t* creg;
+  uint64_t seed, shot_offset, draw;
+  int64_t batch;
+  uint64_t tiles_per_shot;
+  double flip;   // dm only (ket applies the flip as a sampled X before the probabilities)
+  int32_t forced, creg_bit, is_dm, pad;
+};
+
+__global__ void __launch_bounds__(128) k_finish_measure(const FinishParams fp) {
+  const int64_t shot = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (shot >= fp.batch) return;
+  const double* ps = fp.partials + 2ull * (uint64_t)shot * fp.tiles_per_shot;
+  double p0 = 0.0, p1 = 0.0;
+  for (uint64_t i = lane; i < fp.tiles_per_shot; i += 32) { p0 += ps[2 * i]; p1 += ps[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+  }
+  if (lane != 0) return;
+  const double e = fp.flip;
+  const double q0 = (1.0 - e) * p0 + e * p1, q1 = (1.0 - e) * p1 + e * p0;
+  const double tot = q0 + q1;
+  double u, u2;
+  shot_uniforms(fp.seed, fp.shot_offset + (uint64_t)shot, fp.draw, u, u2);
+  int m = fp.forced >= 0 ? fp.forced : ((u * tot < q1) ? 1 : 0);
+  const double pm = m ? q1 : q0;
+  MeasRec r;
+  r.outcome = m;
+  r.pad = 0;
+  r.scale = pm > 0.0 ? (fp.is_dm ? 1.0 / pm : 1.0 / sqrt(pm)) : 0.0;
+  fp.rec[shot] = r;
+  if (fp.creg_bit >= 0) {
+    const uint64_t bit = 1ull << fp.creg_bit;
+    fp.creg[shot] = (fp.creg[shot] & ~bit) | ((uint64_t)m << fp.creg_bit);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_init_state(double2* state, int64_t batch, int P) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < batch) state[(uint64_t)s << P] = make_double2(1.0, 0.0);
+}
+
+__global__ void k_extract_bit(const uint64_t* creg, int bit, int8_t* out, int64_t batch) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < batch) out[s] = (int8_t)((creg[s] >> bit) & 1ull);
+}
+
+struct HistParams {
+  const uint64_t* creg;
+  unsigned long long* bins;
+  int64_t batch;
+  int32_t k;
+  int32_t bits[24];
+};
+__global__ void k_histogram(const HistParams hp) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= hp.batch) return;
+  const uint64_t w = hp.creg[s];
+  uint32_t idx = 0;
+  for (int i = 0; i < hp.k; ++i) idx = (idx << 1) | (uint32_t)((w >> hp.bits[i]) & 1ull);
+  atomicAdd(hp.bins + idx, 1ull);
+}
+
+// reduced density matrix / fidelity of <= 5 axes.  `rest` enumerates the live bits that are
+// traced over (dense index -> physical offset through segs).
+struct ReadoutParams {
+  const double2* state;   // shot 0
+  const double2* ket;     // fidelity only
+  double2* out_rdm;       // 4^k
+  double* out_fid;        // batch
+  int64_t batch;
+  int32_t P, nmax, formalism, k;
+  int32_t axes[8];        // physical column/ket bit of each listed axis (first = MSB)
+  int32_t rest_bits, n_rest_segs;
+  Seg rest_segs[24];
+};
+
+__device__ __forceinline__ uint64_t sel_offset(const ReadoutParams& rp, uint32_t i, int shift) {
+  uint64_t off = 0;
+  for (int s = 0; s < rp.k; ++s)
+    off |= (uint64_t)((i >> (rp.k - 1 - s)) & 1u) << (rp.axes[s] + shift);
+  return off;
+}
+
+// grid = (4^k, 1): block (i, j) of one shot
+__global__ void __launch_bounds__(256) k_reduced_dm(const ReadoutParams rp, int64_t shot) {
+  const uint32_t dim = 1u << rp.k;
+  const uint32_t i = blockIdx.x / dim, j = blockIdx.x % dim;
+  const double2* st = rp.state + ((uint64_t)shot << rp.P);
+  const uint64_t nrest = 1ull << rp.rest_bits;
+  double ax = 0.0, ay = 0.0;
+  if (rp.formalism == 0) {
+    const uint64_t oi = sel_offset(rp, i, 0), oj = sel_offset(rp, j, 0);
+    for (uint64_t r = threadIdx.x; r < nrest; r += blockDim.x) {
+      const uint64_t ro = deposit(r, rp.rest_segs, rp.n_rest_segs);
+      const double2 a = st[oi | ro], b = st[oj | ro];
+      ax += a.x * b.x + a.y * b.y;   // a * conj(b)
+      ay += a.y * b.x - a.x * b.y;
+    }
+  } else {
+    const uint64_t oi = sel_offset(rp, i, rp.nmax), oj = sel_offset(rp, j, 0);
+    for (uint64_t r = threadIdx.x; r < nrest; r += blockDim.x) {
+      const uint64_t ro = deposit(r, rp.rest_segs, rp.n_rest_segs);
+      const double2 a = st[oi | oj | (ro << rp.nmax) | ro];
+      ax += a.x; ay += a.y;
+    }
+  }
+  __shared__ double sx[8], sy[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ax += __shfl_xor_sync(0xffffffffu, ax, o);
+    ay += __shfl_xor_sync(0xffffffffu, ay, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sx[threadIdx.x >> 5] = ax; sy[threadIdx.x >> 5] = ay; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tx = 0.0, ty = 0.0;
+    for (int w = 0; w < 8; ++w) { tx += sx[w]; ty += sy[w]; }
+    rp.out_rdm[blockIdx.x] = make_double2(tx, ty);
+  }
+}
+
+// one block per shot: F = <phi| rho_S |phi>
+__global__ void __launch_bounds__(128) k_fidelity_ket(const ReadoutParams rp) {
+  const int64_t shot = blockIdx.x;
+  const uint32_t dim = 1u << rp.k;
+  const double2* st = rp.state + ((uint64_t)shot << rp.P);
+  const uint64_t nrest = 1ull << rp.rest_bits;
+  double acc = 0.0;
+  if (rp.formalism == 0) {
+    for (uint64_t r = threadIdx.x; r < nrest; r += blockDim.x) {
+      const uint64_t ro = deposit(r, rp.rest_segs, rp.n_rest_segs);
+      double2 s = make_double2(0.0, 0.0);
+      for (uint32_t i = 0; i < dim; ++i) s = cfma(conj2(rp.ket[i]), st[sel_offset(rp, i, 0) | ro], s);
+      acc += s.x * s.x + s.y * s.y;
+    }
+  } else {
+    for (uint64_t r = threadIdx.x; r < nrest; r += blockDim.x) {
+      const uint64_t ro = deposit(r, rp.rest_segs, rp.n_rest_segs);
+      const uint64_t rr = (ro << rp.nmax) | ro;
+      for (uint32_t i = 0; i < dim; ++i) {
+        const uint64_t oi = sel_offset(rp, i, rp.nmax);
+        const double2 ci = conj2(rp.ket[i]);
+        for (uint32_t j = 0; j < dim; ++j) {
+          const double2 v = cmul(cmul(ci, st[oi | sel_offset(rp, j, 0) | rr]), rp.ket[j]);
+          acc += v.x;
+        }
+      }
+    }
+  }
+  __shared__ double sa[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sa[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) rp.out_fid[shot] = sa[0] + sa[1] + sa[2] + sa[3];
+}
+
+}  // namespace dqe

@@ -1,0 +1,1039 @@
+// dqe_engine.cu -- host side of libdqcengine.so: handle, gate queue, pass planner ("gate-queue
+// flusher"), launches and the extern "C" ABI declared in include/dqc_engine.h.
+//
+// The reference executes one QuantumProgram instruction at a time through NetSquid
+// (software/dqc_control.py:899-949 -> QuantumProcessor.execute_program); here the same
+// instruction stream is only *queued*, and dqe_flush() cuts the queue into passes.  A pass is one
+// launch of k_tile_pass: every queued op whose target bits fit the shared-memory tile is applied
+// in the same read-modify-write sweep of the state.  Measurement needs a per-shot global sum, so
+// it splits a pass in two (probabilities at the end of one, collapse at the start of the next)
+// with a tiny finish kernel in between; outcomes stay on the device.
+#include "dqe_device.cuh"
+#include "../../include/dqc_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dqe;
+typedef std::complex<double> cplx;
+
+namespace {
+
+struct HostOp {
+  int kind;            // 0 = micro-op, 1 = measurement finish (pass barrier)
+  MicroOp m;           // bit fields hold PHYSICAL positions until the planner localises them
+  uint64_t pctrl, pctrl2;  // physical control masks
+  uint64_t need;       // physical bits that must lie inside the tile
+  uint64_t live_after; // physical live mask after this op
+  int nconst;          // number of double2 constants (stored at m.c_off in the pool)
+  // finish parameters
+  double flip;
+  int forced, creg_bit;
+  uint64_t draw;
+};
+
+struct PlannedPass {
+  PassParams pp;
+  size_t op_begin;     // offset into the device op array
+  uint64_t grid;
+  size_t smem;
+  uint64_t amps;       // amplitudes touched per shot
+  bool is_finish;
+  FinishParams fp;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct dqe_engine {
+  int formalism, nmax, P, device;
+  int64_t batch;
+  cudaStream_t stream;
+  bool own_stream, own_state;
+  double2* state;
+  uint64_t* creg;
+  double* partials;
+  size_t partials_cap;
+  MeasRec* rec;
+  MicroOp* d_ops;
+  size_t d_ops_cap;
+  double2* d_consts;
+  size_t d_consts_cap;
+  uint64_t live_axes;       // axis mask
+  uint64_t planned_live;    // physical live mask at the head of the queue
+  uint64_t seed, shot_offset, draw;
+  int pred;
+  std::vector<HostOp> queue;
+  std::vector<double2> cpool;
+  std::string err;
+  int cuda_failed;
+  int tile_bits, min_run_bits, fuse;
+  int64_t stats[8];
+  bool timing;
+  cudaEvent_t ev0, ev1;
+  double t_ms;
+  int64_t t_passes, t_amps;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<uint64_t> ev_amps;
+};
+
+namespace {
+
+int fail(dqe_t* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      h->cuda_failed = 1;                                                               \
+      return fail(h, DQE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    }                                                                                   \
+  } while (0)
+
+inline uint64_t phys_live(const dqe_t* h, uint64_t axes) {
+  return h->formalism == DQE_KET ? axes : (axes | (axes << h->nmax));
+}
+inline int rowbit(const dqe_t* h, int a) { return a + h->nmax; }
+
+int check_ready(dqe_t* h) {
+  if (!h) return DQE_EINVAL;
+  if (h->cuda_failed) return DQE_ECUDA;
+  return 0;
+}
+int check_live(dqe_t* h, int axis, const char* what) {
+  if (axis < 0 || axis >= h->nmax) return fail(h, DQE_EINVAL, std::string(what) + ": axis out of range");
+  if (!((h->live_axes >> axis) & 1ull))
+    return fail(h, DQE_EINVAL, std::string(what) + ": axis " + std::to_string(axis) + " holds no qubit");
+  return 0;
+}
+
+int add_consts(dqe_t* h, const cplx* c, int n) {
+  int off = (int)h->cpool.size();
+  for (int i = 0; i < n; ++i) h->cpool.push_back(make_double2(c[i].real(), c[i].imag()));
+  return off;
+}
+
+HostOp blank(dqe_t* h, int type) {
+  HostOp o;
+  memset(&o, 0, sizeof(o));
+  o.kind = 0;
+  o.m.type = type;
+  o.m.pred_bit = h->pred;
+  o.live_after = phys_live(h, h->live_axes);
+  return o;
+}
+void push(dqe_t* h, HostOp& o) {
+  h->queue.push_back(o);
+  h->stats[4] += 0;
+}
+
+// -------- lowering helpers (physical bits) --------------------------------------------------
+void q_mat1(dqe_t* h, int bit, const cplx* m, uint64_t pctrl) {
+  HostOp o = blank(h, OP_MAT1);
+  o.m.b[0] = (uint8_t)bit; o.m.nb = 1;
+  o.pctrl = pctrl;
+  o.need = 1ull << bit;
+  o.m.c_off = add_consts(h, m, 4); o.nconst = 4;
+  push(h, o);
+}
+void q_mat1x2(dqe_t* h, int rbit, int cbit, const cplx* m, uint64_t pctrl_r, uint64_t pctrl_c) {
+  HostOp o = blank(h, OP_MAT1X2);
+  o.m.b[0] = (uint8_t)rbit; o.m.b[1] = (uint8_t)cbit; o.m.nb = 2;
+  o.pctrl = pctrl_r; o.pctrl2 = pctrl_c;
+  o.need = (1ull << rbit) | (1ull << cbit);
+  o.m.c_off = add_consts(h, m, 4); o.nconst = 4;
+  push(h, o);
+}
+void q_mat2(dqe_t* h, int bh, int bl, const cplx* m, uint64_t pctrl) {
+  HostOp o = blank(h, OP_MAT2);
+  o.m.b[0] = (uint8_t)bh; o.m.b[1] = (uint8_t)bl; o.m.nb = 2;
+  o.pctrl = pctrl;
+  o.need = (1ull << bh) | (1ull << bl);
+  o.m.c_off = add_consts(h, m, 16); o.nconst = 16;
+  push(h, o);
+}
+void q_diag(dqe_t* h, int nb, const int* bits, const cplx* table) {
+  HostOp o = blank(h, OP_DIAG);
+  o.m.nb = nb;
+  for (int i = 0; i < nb; ++i) o.m.b[i] = (uint8_t)bits[i];
+  o.need = 0;
+  o.m.c_off = add_consts(h, table, 1 << nb); o.nconst = 1 << nb;
+  push(h, o);
+}
+void q_pauli1(dqe_t* h, int axis, double pI, double pX, double pY, double pZ) {
+  HostOp o = blank(h, OP_PAULI1);
+  o.m.b[0] = (uint8_t)rowbit(h, axis); o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
+  o.need = (1ull << rowbit(h, axis)) | (1ull << axis);
+  o.m.p[0] = pI + pZ; o.m.p[1] = pX + pY; o.m.p[2] = pI - pZ; o.m.p[3] = pX - pY;
+  push(h, o);
+}
+
+bool is_zero(cplx z) { return z.real() == 0.0 && z.imag() == 0.0; }
+bool is_one(cplx z) { return z.real() == 1.0 && z.imag() == 0.0; }
+
+// ket-or-dm diagonal gate on k axes (first = MSB); dm table = d[r] conj(d[c]) over (rows, cols)
+int lower_diag(dqe_t* h, int k, const int* axes, const cplx* d) {
+  if (h->formalism == DQE_KET) {
+    if (k > 4) return fail(h, DQE_EUNSUPPORTED, "diag: k <= 4 (ket)");
+    q_diag(h, k, axes, d);
+    return 0;
+  }
+  if (k > 2) return fail(h, DQE_EUNSUPPORTED, "diag: k <= 2 (dm)");
+  int bits[4];
+  cplx table[16];
+  for (int i = 0; i < k; ++i) { bits[i] = rowbit(h, axes[i]); bits[k + i] = axes[i]; }
+  const int n = 1 << k;
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) table[r * n + c] = d[r] * std::conj(d[c]);
+  q_diag(h, 2 * k, bits, table);
+  return 0;
+}
+
+int lower_1q(dqe_t* h, int axis, const cplx* m) {
+  if (is_zero(m[1]) && is_zero(m[2])) {
+    const cplx d[2] = {m[0], m[3]};
+    return lower_diag(h, 1, &axis, d);
+  }
+  if (h->formalism == DQE_KET) {
+    q_mat1(h, axis, m, 0);
+  } else {
+    cplx S[16];  // S[(r,c),(r',c')] = U[r,r'] conj(U[c,c'])
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 2; ++c)
+        for (int r2 = 0; r2 < 2; ++r2)
+          for (int c2 = 0; c2 < 2; ++c2)
+            S[(r * 2 + c) * 4 + (r2 * 2 + c2)] = m[r * 2 + r2] * std::conj(m[c * 2 + c2]);
+    q_mat2(h, rowbit(h, axis), axis, S, 0);
+  }
+  return 0;
+}
+
+int lower_ctrl_1q(dqe_t* h, int c, int t, const cplx* m) {
+  if (is_zero(m[1]) && is_zero(m[2])) {
+    const int axes[2] = {c, t};
+    const cplx d[4] = {1.0, 1.0, m[0], m[3]};
+    return lower_diag(h, 2, axes, d);
+  }
+  if (h->formalism == DQE_KET) q_mat1(h, t, m, 1ull << c);
+  else q_mat1x2(h, rowbit(h, t), t, m, 1ull << rowbit(h, c), 1ull << c);
+  return 0;
+}
+
+int lower_2q(dqe_t* h, int a, int b, const cplx* m) {
+  bool diag = true, ctrl = true;
+  for (int i = 0; i < 4 && (diag || ctrl); ++i)
+    for (int j = 0; j < 4; ++j) {
+      if (i != j && !is_zero(m[i * 4 + j])) diag = false;
+      if ((i < 2 || j < 2) && !(i >= 2 && j >= 2)) {
+        if (i == j ? !is_one(m[i * 4 + j]) : !is_zero(m[i * 4 + j])) ctrl = false;
+      }
+    }
+  if (diag) {
+    const int axes[2] = {a, b};
+    const cplx d[4] = {m[0], m[5], m[10], m[15]};
+    return lower_diag(h, 2, axes, d);
+  }
+  if (ctrl) {
+    const cplx u[4] = {m[10], m[11], m[14], m[15]};
+    return lower_ctrl_1q(h, a, b, u);
+  }
+  if (h->formalism == DQE_KET) {
+    q_mat2(h, a, b, m, 0);
+  } else {
+    cplx mc[16];
+    for (int i = 0; i < 16; ++i) mc[i] = std::conj(m[i]);
+    q_mat2(h, rowbit(h, a), rowbit(h, b), m, 0);
+    q_mat2(h, a, b, mc, 0);
+  }
+  return 0;
+}
+
+void q_sampled(dqe_t* h, int k, const int* axes, int mode, uint64_t draw, double p0, double p1, double p2) {
+  HostOp o = blank(h, OP_PAULI_SAMPLED);
+  o.m.nb = k;
+  for (int i = 0; i < k; ++i) { o.m.b[i] = (uint8_t)axes[i]; o.need |= 1ull << axes[i]; }
+  o.m.flags = mode;
+  o.m.aux = (int32_t)draw;
+  o.m.p[0] = p0; o.m.p[1] = p1; o.m.p[2] = p2;
+  push(h, o);
+}
+
+int lower_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, double e) {
+  const uint64_t draw = h->draw++;
+  if (h->formalism == DQE_KET && e > 0.0) q_sampled(h, 1, &axis, 2, draw, e, 0, 0);
+  {
+    HostOp o = blank(h, OP_PROBS);
+    o.m.pred_bit = -1;
+    o.m.aux = axis;
+    push(h, o);
+  }
+  {
+    HostOp f;
+    memset(&f, 0, sizeof(f));
+    f.kind = 1;
+    f.flip = h->formalism == DQE_DM ? e : 0.0;
+    f.forced = forced; f.creg_bit = creg_bit; f.draw = draw;
+    f.live_after = phys_live(h, h->live_axes);
+    h->queue.push_back(f);
+  }
+  if (discard) h->live_axes &= ~(1ull << axis);
+  HostOp o = blank(h, OP_COLLAPSE);   // live_after already reflects a discard
+  o.m.pred_bit = -1;
+  o.m.flags = discard ? 1 : 0;
+  o.m.p[0] = h->formalism == DQE_DM ? e : 0.0;
+  if (h->formalism == DQE_KET) { o.m.b[0] = (uint8_t)axis; o.m.nb = 1; o.need = 1ull << axis; }
+  else {
+    o.m.b[0] = (uint8_t)rowbit(h, axis); o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
+    o.need = (1ull << rowbit(h, axis)) | (1ull << axis);
+  }
+  push(h, o);
+  return 0;
+}
+
+// -------- planner --------------------------------------------------------------------------
+int build_segs(uint64_t mask, Seg* segs, int cap) {
+  int n = 0, src = 0;
+  for (int b = 0; b < 64;) {
+    if ((mask >> b) & 1ull) {
+      int len = 0;
+      while (b + len < 64 && ((mask >> (b + len)) & 1ull)) ++len;
+      if (n >= cap) return -1;
+      segs[n].src = (uint8_t)src; segs[n].len = (uint8_t)len; segs[n].dst = (uint8_t)b; segs[n].pad = 0;
+      ++n; src += len; b += len;
+    } else ++b;
+  }
+  return n;
+}
+
+// tile = lowest c live bits + the needed bits above them; returns the tile mask or 0 if the
+// needed bits do not fit with a contiguous low run of at least min_run bits.
+bool choose_tile(const dqe_t* h, uint64_t need, uint64_t live, bool force, uint64_t* tile_out, int* t_out) {
+  const int L = __builtin_popcountll(live);
+  const int t = std::min(h->tile_bits, L);
+  int pos[64];
+  int n = 0;
+  for (int b = 0; b < 64; ++b) if ((live >> b) & 1ull) pos[n++] = b;
+  for (int c = t; c >= 0; --c) {
+    int hi = 0;
+    for (int r = c; r < L; ++r) if ((need >> pos[r]) & 1ull) ++hi;
+    if (c + hi <= t) {
+      if (!force && c < std::min(h->min_run_bits, L) && c + hi < L) return false;
+      uint64_t tile = 0;
+      for (int r = 0; r < c; ++r) tile |= 1ull << pos[r];
+      tile |= need;
+      // when fewer than t bits are used (c == t impossible here), extend with next live bits
+      int used = c + hi;
+      for (int r = c; r < L && used < t; ++r)
+        if (!((tile >> pos[r]) & 1ull)) { tile |= 1ull << pos[r]; ++used; }
+      *t_out = used;
+      *tile_out = tile;
+      return true;
+    }
+  }
+  return false;
+}
+
+int local_of(uint64_t tile, int phys) { return __builtin_popcountll(tile & ((1ull << phys) - 1ull)); }
+
+struct Planner {
+  dqe_t* h;
+  std::vector<PlannedPass> passes;
+  std::vector<MicroOp> dev_ops;
+  std::string err;
+
+  bool close(std::vector<const HostOp*>& cur, uint64_t need, uint64_t live) {
+    if (cur.empty()) return true;
+    int t = 0;
+    uint64_t tile = 0;
+    if (!choose_tile(h, need, live, true, &tile, &t)) {
+      err = "planner: op needs more target bits than the tile holds";
+      return false;
+    }
+    PlannedPass P;
+    memset(&P, 0, sizeof(P));
+    P.is_finish = false;
+    PassParams& pp = P.pp;
+    pp.t = t; pp.P = h->P; pp.nmax = h->nmax; pp.formalism = h->formalism;
+    const uint64_t outer = live & ~tile;
+    pp.outer_bits = __builtin_popcountll(outer);
+    pp.n_tile_segs = build_segs(tile, pp.tile_segs, 16);
+    pp.n_outer_segs = build_segs(outer, pp.outer_segs, 24);
+    if (pp.n_tile_segs < 0 || pp.n_outer_segs < 0) { err = "planner: too many bit segments"; return false; }
+    if (pp.n_tile_segs == 0) { pp.n_tile_segs = 1; pp.tile_segs[0] = Seg{0, 0, 0, 0}; }
+    pp.nops = (int)cur.size();
+    pp.seed = h->seed; pp.shot_offset = h->shot_offset;
+    P.op_begin = dev_ops.size();
+    bool writes = false;
+    for (const HostOp* ho : cur) {
+      MicroOp m = ho->m;
+      if (m.type != OP_PROBS) writes = true;
+      if (m.type == OP_DIAG) {
+        for (uint32_t i = 0; i < m.nb; ++i) {
+          const int ph = ho->m.b[i];
+          m.b[i] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
+        }
+      } else if (m.type != OP_PROBS) {
+        for (uint32_t i = 0; i < m.nb; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
+      }
+      m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
+      for (int b = 0; b < 64; ++b) {
+        if ((ho->pctrl >> b) & 1ull) {
+          if ((tile >> b) & 1ull) m.lctrl |= 1u << local_of(tile, b); else m.octrl |= 1ull << b;
+        }
+        if ((ho->pctrl2 >> b) & 1ull) {
+          if ((tile >> b) & 1ull) m.lctrl2 |= 1u << local_of(tile, b); else m.octrl2 |= 1ull << b;
+        }
+      }
+      dev_ops.push_back(m);
+    }
+    pp.store_back = writes ? 1 : 0;
+    P.grid = (uint64_t)h->batch << pp.outer_bits;
+    P.smem = sizeof(double2) << t;
+    P.amps = 1ull << __builtin_popcountll(live);
+    passes.push_back(P);
+    cur.clear();
+    return true;
+  }
+
+  bool plan() {
+    std::vector<const HostOp*> cur;
+    uint64_t live_now = h->planned_live, need = 0, live = live_now;
+    for (const HostOp& op : h->queue) {
+      if (op.kind == 1) {
+        // the PROBS op is the tail of `cur`
+        if (!close(cur, need, live)) return false;
+        const PlannedPass& last = passes.back();
+        PlannedPass F;
+        memset(&F, 0, sizeof(F));
+        F.is_finish = true;
+        F.fp.seed = h->seed; F.fp.shot_offset = h->shot_offset; F.fp.draw = op.draw;
+        F.fp.batch = h->batch;
+        F.fp.tiles_per_shot = 1ull << last.pp.outer_bits;
+        F.fp.flip = op.flip; F.fp.forced = op.forced; F.fp.creg_bit = op.creg_bit;
+        F.fp.is_dm = h->formalism == DQE_DM;
+        passes.push_back(F);
+        need = 0; live = live_now;
+        continue;
+      }
+      uint64_t need2 = need | op.need;
+      uint64_t live2 = live | op.live_after | op.need;
+      int t = 0;
+      uint64_t tile = 0;
+      const bool fits = cur.empty() || (h->fuse && (int)cur.size() < kMaxOpsPerPass &&
+                                        choose_tile(h, need2, live2, false, &tile, &t));
+      if (!fits) {
+        if (!close(cur, need, live)) return false;
+        need2 = op.need;
+        live2 = live_now | op.live_after | op.need;
+      }
+      cur.push_back(&op);
+      need = need2; live = live2;
+      live_now = op.live_after;
+    }
+    if (!close(cur, need, live)) return false;
+    h->planned_live = live_now;
+    return true;
+  }
+};
+
+int ensure_partials(dqe_t* h, size_t n) {
+  if (n <= h->partials_cap) return 0;
+  if (h->partials) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->partials)); h->partials = nullptr; }
+  CK(cudaMalloc(&h->partials, n * sizeof(double)));
+  h->partials_cap = n;
+  return 0;
+}
+
+int do_flush(dqe_t* h) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->queue.empty()) return 0;
+  Planner pl;
+  pl.h = h;
+  if (!pl.plan()) {
+    h->queue.clear(); h->cpool.clear();
+    return fail(h, DQE_EINVAL, pl.err);
+  }
+  CK(cudaSetDevice(h->device));
+  // upload micro-ops + constants
+  if (pl.dev_ops.size() > h->d_ops_cap) {
+    if (h->d_ops) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_ops)); }
+    h->d_ops_cap = std::max<size_t>(pl.dev_ops.size() * 2, 1024);
+    CK(cudaMalloc(&h->d_ops, h->d_ops_cap * sizeof(MicroOp)));
+  }
+  if (h->cpool.size() > h->d_consts_cap) {
+    if (h->d_consts) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_consts)); }
+    h->d_consts_cap = std::max<size_t>(h->cpool.size() * 2, 4096);
+    CK(cudaMalloc(&h->d_consts, h->d_consts_cap * sizeof(double2)));
+  }
+  if (!pl.dev_ops.empty())
+    CK(cudaMemcpyAsync(h->d_ops, pl.dev_ops.data(), pl.dev_ops.size() * sizeof(MicroOp),
+                       cudaMemcpyHostToDevice, h->stream));
+  if (!h->cpool.empty())
+    CK(cudaMemcpyAsync(h->d_consts, h->cpool.data(), h->cpool.size() * sizeof(double2),
+                       cudaMemcpyHostToDevice, h->stream));
+  // partials: sized for the widest grid of a pass that ends in PROBS
+  size_t need_part = 0;
+  for (const PlannedPass& P : pl.passes)
+    if (!P.is_finish) need_part = std::max<size_t>(need_part, (size_t)P.grid * 2);
+  if (int rc = ensure_partials(h, need_part)) return rc;
+
+  for (PlannedPass& P : pl.passes) {
+    if (P.is_finish) {
+      P.fp.partials = h->partials; P.fp.rec = h->rec; P.fp.creg = h->creg;
+      const unsigned grid = (unsigned)((h->batch + 3) / 4);
+      k_finish_measure<<<grid, 128, 0, h->stream>>>(P.fp);
+      h->stats[2]++; h->stats[5]++;
+      continue;
+    }
+    if (P.grid > 0x7fffffffull) return fail(h, DQE_EUNSUPPORTED, "grid too large");
+    P.pp.state = h->state; P.pp.creg = h->creg; P.pp.partials = h->partials; P.pp.rec = h->rec;
+    P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, h->stream));
+    }
+    k_tile_pass<<<(unsigned)P.grid, kThreads, P.smem, h->stream>>>(P.pp);
+    if (h->timing) {
+      CK(cudaEventRecord(e1, h->stream));
+      h->ev_pool.push_back(std::make_pair(e0, e1));
+      h->ev_amps.push_back(P.amps * (uint64_t)h->batch);
+    }
+    h->stats[0]++; h->stats[2]++;
+    h->stats[1] += P.pp.nops;
+    h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
+  }
+  CK(cudaGetLastError());
+  h->queue.clear();
+  h->cpool.clear();
+  h->planned_live = phys_live(h, h->live_axes);
+  return 0;
+}
+
+int collect_timing(dqe_t* h) {
+  for (size_t i = 0; i < h->ev_pool.size(); ++i) {
+    float ms = 0.f;
+    CK(cudaEventSynchronize(h->ev_pool[i].second));
+    CK(cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
+    h->t_ms += ms; h->t_passes++; h->t_amps += (int64_t)h->ev_amps[i];
+    cudaEventDestroy(h->ev_pool[i].first); cudaEventDestroy(h->ev_pool[i].second);
+  }
+  h->ev_pool.clear(); h->ev_amps.clear();
+  return 0;
+}
+
+int build_readout(dqe_t* h, int k, const int* axes, ReadoutParams* rp) {
+  if (k < 1 || k > 5) return fail(h, DQE_EUNSUPPORTED, "read-out supports 1..5 axes");
+  memset(rp, 0, sizeof(*rp));
+  uint64_t sel = 0;
+  for (int i = 0; i < k; ++i) {
+    if (int rc = check_live(h, axes[i], "read-out")) return rc;
+    if ((sel >> axes[i]) & 1ull) return fail(h, DQE_EINVAL, "read-out: repeated axis");
+    sel |= 1ull << axes[i];
+    rp->axes[i] = axes[i];
+  }
+  const uint64_t rest = h->live_axes & ~sel;
+  rp->state = h->state; rp->batch = h->batch; rp->P = h->P; rp->nmax = h->nmax;
+  rp->formalism = h->formalism; rp->k = k;
+  rp->rest_bits = __builtin_popcountll(rest);
+  rp->n_rest_segs = build_segs(rest, rp->rest_segs, 24);
+  if (rp->n_rest_segs < 0) return fail(h, DQE_EUNSUPPORTED, "read-out: too many segments");
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* dqe_version(void) { return "dqc-b200-engine 0.1 (sm_100a)"; }
+
+const char* dqe_last_error(const dqe_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int device, void* ext_state,
+               void* stream) {
+  if (!out) return DQE_EINVAL;
+  *out = nullptr;
+  if (formalism != DQE_KET && formalism != DQE_DM) return fail(nullptr, DQE_EINVAL, "formalism must be 0 (ket) or 1 (dm)");
+  const int P = formalism == DQE_KET ? max_qubits : 2 * max_qubits;
+  if (max_qubits < 1 || P > 40) return fail(nullptr, DQE_EINVAL, "max_qubits out of range (ket <= 40, dm <= 20)");
+  if (batch < 1) return fail(nullptr, DQE_EINVAL, "batch must be >= 1");
+  dqe_t* h = new dqe_engine();
+  h->formalism = formalism; h->nmax = max_qubits; h->P = P; h->device = device; h->batch = batch;
+  h->own_stream = false; h->own_state = false; h->state = nullptr; h->creg = nullptr;
+  h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
+  h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
+  h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
+  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->timing = false;
+  h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
+  memset(h->stats, 0, sizeof(h->stats));
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    delete h;
+    return fail(nullptr, DQE_ECUDA, msg);
+  }
+  auto bail = [&](const char* what, cudaError_t err) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
+    dqe_destroy(h);
+    return fail(nullptr, err == cudaErrorMemoryAllocation ? DQE_ENOMEM : DQE_ECUDA, msg);
+  };
+  if (stream) h->stream = (cudaStream_t)stream;
+  else {
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->own_stream = true;
+  }
+  const size_t elems = (size_t)batch << P;
+  if (ext_state) h->state = (double2*)ext_state;
+  else {
+    e = cudaMalloc(&h->state, elems * sizeof(double2));
+    if (e != cudaSuccess) return bail("cudaMalloc(state)", e);
+    h->own_state = true;
+  }
+  if ((e = cudaMalloc(&h->creg, batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
+  if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
+  if ((e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute", e);
+  if ((e = cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream)) != cudaSuccess) return bail("memset", e);
+  if ((e = cudaMemsetAsync(h->creg, 0, batch * sizeof(uint64_t), h->stream)) != cudaSuccess) return bail("memset", e);
+  if ((e = cudaMemsetAsync(h->rec, 0, batch * sizeof(MeasRec), h->stream)) != cudaSuccess) return bail("memset", e);
+  k_init_state<<<(unsigned)((batch + 255) / 256), 256, 0, h->stream>>>(h->state, batch, P);
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail("k_init_state", e);
+  *out = h;
+  return 0;
+}
+
+int dqe_destroy(dqe_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (h->own_state && h->state) cudaFree(h->state);
+  if (h->creg) cudaFree(h->creg);
+  if (h->rec) cudaFree(h->rec);
+  if (h->partials) cudaFree(h->partials);
+  if (h->d_ops) cudaFree(h->d_ops);
+  if (h->d_consts) cudaFree(h->d_consts);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int dqe_seed(dqe_t* h, uint64_t seed, uint64_t shot_offset) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = do_flush(h)) return rc;
+  h->seed = seed; h->shot_offset = shot_offset; h->draw = 0;
+  return 0;
+}
+
+int dqe_alloc_axis(dqe_t* h, int axis) {
+  if (int rc = check_ready(h)) return rc;
+  if (axis < 0 || axis >= h->nmax) return fail(h, DQE_EINVAL, "alloc_axis: axis out of range");
+  if ((h->live_axes >> axis) & 1ull) return fail(h, DQE_EINVAL, "alloc_axis: axis already live");
+  h->live_axes |= 1ull << axis;
+  // a free axis is |0> by invariant: nothing to do on the device.  The queue still has to learn
+  // that the bits are live, which the next op's live_after carries.
+  if (h->queue.empty()) h->planned_live = phys_live(h, h->live_axes);
+  h->stats[4]++;
+  return 0;
+}
+
+int dqe_free_axis(dqe_t* h, int axis) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "free_axis")) return rc;
+  h->stats[4]++;
+  if (h->formalism == DQE_KET) return lower_measure(h, axis, -1, -1, 1, 0.0);
+  const int pred = h->pred;
+  h->pred = -1;
+  h->live_axes &= ~(1ull << axis);
+  HostOp o = blank(h, OP_TRACE);
+  o.m.b[0] = (uint8_t)rowbit(h, axis); o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
+  o.need = (1ull << rowbit(h, axis)) | (1ull << axis);
+  push(h, o);
+  h->pred = pred;
+  return 0;
+}
+
+int dqe_reset(dqe_t* h, int axis) {
+  if (int rc = check_ready(h)) return rc;
+  if (axis < 0 || axis >= h->nmax) return fail(h, DQE_EINVAL, "reset: axis out of range");
+  if ((h->live_axes >> axis) & 1ull)
+    if (int rc = dqe_free_axis(h, axis)) return rc;
+  return dqe_alloc_axis(h, axis);
+}
+
+int dqe_live_mask(dqe_t* h, uint64_t* mask) {
+  if (!h || !mask) return DQE_EINVAL;
+  *mask = h->live_axes;
+  return 0;
+}
+
+static void to_cplx(const double* in, cplx* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = cplx(in[2 * i], in[2 * i + 1]);
+}
+
+int dqe_enqueue_1q(dqe_t* h, int axis, const double* m) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "1q gate")) return rc;
+  cplx u[4];
+  to_cplx(m, u, 4);
+  h->stats[4]++;
+  return lower_1q(h, axis, u);
+}
+
+int dqe_enqueue_2q(dqe_t* h, int a, int b, const double* m) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, a, "2q gate")) return rc;
+  if (int rc = check_live(h, b, "2q gate")) return rc;
+  if (a == b) return fail(h, DQE_EINVAL, "2q gate: axes must differ");
+  cplx u[16];
+  to_cplx(m, u, 16);
+  h->stats[4]++;
+  return lower_2q(h, a, b, u);
+}
+
+int dqe_enqueue_ctrl_1q(dqe_t* h, int c, int t, const double* m) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, c, "ctrl gate")) return rc;
+  if (int rc = check_live(h, t, "ctrl gate")) return rc;
+  if (c == t) return fail(h, DQE_EINVAL, "ctrl gate: axes must differ");
+  cplx u[4];
+  to_cplx(m, u, 4);
+  h->stats[4]++;
+  return lower_ctrl_1q(h, c, t, u);
+}
+
+int dqe_enqueue_diag(dqe_t* h, int k, const int* axes, const double* d) {
+  if (int rc = check_ready(h)) return rc;
+  if (k < 1 || k > 4) return fail(h, DQE_EUNSUPPORTED, "diag: 1 <= k <= 4");
+  for (int i = 0; i < k; ++i) {
+    if (int rc = check_live(h, axes[i], "diag")) return rc;
+    for (int j = 0; j < i; ++j) if (axes[i] == axes[j]) return fail(h, DQE_EINVAL, "diag: repeated axis");
+  }
+  cplx t[16];
+  to_cplx(d, t, 1 << k);
+  h->stats[4]++;
+  return lower_diag(h, k, axes, t);
+}
+
+int dqe_set_predicate(dqe_t* h, int creg_bit) {
+  if (int rc = check_ready(h)) return rc;
+  if (creg_bit >= 64) return fail(h, DQE_EINVAL, "creg has 64 bits");
+  h->pred = creg_bit < 0 ? -1 : creg_bit;
+  return 0;
+}
+
+int dqe_enqueue_cond_1q(dqe_t* h, int axis, const double* m, int creg_bit) {
+  if (int rc = check_ready(h)) return rc;
+  if (creg_bit < 0 || creg_bit >= 64) return fail(h, DQE_EINVAL, "cond_1q: creg bit out of range");
+  const int pred = h->pred;
+  h->pred = creg_bit;
+  const int rc = dqe_enqueue_1q(h, axis, m);
+  h->pred = pred;
+  return rc;
+}
+
+int dqe_enqueue_pauli_channel(dqe_t* h, int axis, const double* p) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "pauli_channel")) return rc;
+  h->stats[4]++;
+  if (h->formalism == DQE_DM) {
+    q_pauli1(h, axis, p[0], p[1], p[2], p[3]);
+  } else {
+    const uint64_t draw = h->draw++;
+    q_sampled(h, 1, &axis, 0, draw, p[0], p[0] + p[1], p[0] + p[1] + p[2]);
+  }
+  return 0;
+}
+
+int dqe_enqueue_depolarize(dqe_t* h, int k, const int* axes, double p) {
+  if (int rc = check_ready(h)) return rc;
+  if (k != 1 && k != 2) return fail(h, DQE_EUNSUPPORTED, "depolarize: k = 1 or 2");
+  for (int i = 0; i < k; ++i) if (int rc = check_live(h, axes[i], "depolarize")) return rc;
+  if (k == 2 && axes[0] == axes[1]) return fail(h, DQE_EINVAL, "depolarize: axes must differ");
+  h->stats[4]++;
+  if (h->formalism == DQE_DM) {
+    if (k == 1) q_pauli1(h, axes[0], 1.0 - 0.75 * p, 0.25 * p, 0.25 * p, 0.25 * p);
+    else {
+      HostOp o = blank(h, OP_DEPOL2);
+      o.m.b[0] = (uint8_t)rowbit(h, axes[0]); o.m.b[1] = (uint8_t)rowbit(h, axes[1]);
+      o.m.b[2] = (uint8_t)axes[0]; o.m.b[3] = (uint8_t)axes[1]; o.m.nb = 4;
+      for (int i = 0; i < 4; ++i) o.need |= 1ull << o.m.b[i];
+      o.m.p[0] = p;
+      push(h, o);
+    }
+  } else {
+    const uint64_t draw = h->draw++;
+    const double n = k == 1 ? 4.0 : 16.0;
+    const double w = p / n, w0 = 1.0 - (n - 1.0) * w;
+    q_sampled(h, k, axes, 1, draw, w0, w, 0.0);
+  }
+  return 0;
+}
+
+int dqe_enqueue_kraus_1q(dqe_t* h, int axis, int nk, const double* K) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "kraus_1q")) return rc;
+  if (h->formalism != DQE_DM) return fail(h, DQE_EUNSUPPORTED, "generic Kraus channels are dm-only");
+  if (nk < 1 || nk > 16) return fail(h, DQE_EINVAL, "kraus_1q: 1 <= nk <= 16");
+  cplx S[16];
+  for (int i = 0; i < 16; ++i) S[i] = 0.0;
+  for (int q = 0; q < nk; ++q) {
+    cplx m[4];
+    to_cplx(K + 8 * q, m, 4);
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 2; ++c)
+        for (int r2 = 0; r2 < 2; ++r2)
+          for (int c2 = 0; c2 < 2; ++c2)
+            S[(r * 2 + c) * 4 + (r2 * 2 + c2)] += m[r * 2 + r2] * std::conj(m[c * 2 + c2]);
+  }
+  h->stats[4]++;
+  q_mat2(h, rowbit(h, axis), axis, S, 0);
+  return 0;
+}
+
+static int inject_common(dqe_t* h, int a, int b) {
+  if (a < 0 || a >= h->nmax || b < 0 || b >= h->nmax || a == b) return fail(h, DQE_EINVAL, "inject_2q: bad axes");
+  if (((h->live_axes >> a) & 1ull) || ((h->live_axes >> b) & 1ull))
+    return fail(h, DQE_EINVAL, "inject_2q: axis is occupied");
+  h->live_axes |= (1ull << a) | (1ull << b);
+  h->stats[4]++;
+  return 0;
+}
+
+int dqe_inject_2q(dqe_t* h, int a, int b, const double* state, int is_dm) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->formalism == DQE_KET && is_dm)
+    return fail(h, DQE_EUNSUPPORTED, "ket formalism: pass a decomposition to dqe_inject_2q_mixture");
+  if (int rc = inject_common(h, a, b)) return rc;
+  const int pred = h->pred;
+  h->pred = -1;
+  HostOp o = blank(h, OP_INJECT);
+  if (h->formalism == DQE_KET) {
+    cplx v[4];
+    to_cplx(state, v, 4);
+    o.m.b[0] = (uint8_t)a; o.m.b[1] = (uint8_t)b; o.m.nb = 2;
+    o.need = (1ull << a) | (1ull << b);
+    o.m.c_off = add_consts(h, v, 4); o.nconst = 4;
+  } else {
+    cplx sig[16];
+    if (is_dm) to_cplx(state, sig, 16);
+    else {
+      cplx v[4];
+      to_cplx(state, v, 4);
+      for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) sig[r * 4 + c] = v[r] * std::conj(v[c]);
+    }
+    o.m.b[0] = (uint8_t)rowbit(h, a); o.m.b[1] = (uint8_t)rowbit(h, b);
+    o.m.b[2] = (uint8_t)a; o.m.b[3] = (uint8_t)b; o.m.nb = 4;
+    for (int i = 0; i < 4; ++i) o.need |= 1ull << o.m.b[i];
+    o.m.c_off = add_consts(h, sig, 16); o.nconst = 16;
+  }
+  push(h, o);
+  h->pred = pred;
+  return 0;
+}
+
+int dqe_inject_2q_mixture(dqe_t* h, int a, int b, int ncomp, const double* probs, const double* kets) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->formalism != DQE_KET) return fail(h, DQE_EUNSUPPORTED, "inject_2q_mixture is ket-only (dm takes the matrix)");
+  if (ncomp < 1 || ncomp > 4) return fail(h, DQE_EINVAL, "inject_2q_mixture: 1 <= ncomp <= 4");
+  if (int rc = inject_common(h, a, b)) return rc;
+  const int pred = h->pred;
+  h->pred = -1;
+  HostOp o = blank(h, OP_INJECT);
+  cplx v[16];
+  for (int i = 0; i < 16; ++i) v[i] = 0.0;
+  to_cplx(kets, v, 4 * ncomp);
+  double cum[4] = {2.0, 2.0, 2.0, 2.0}, acc = 0.0;   // thresholds beyond the last component never fire
+  for (int i = 0; i < ncomp; ++i) { acc += probs[i]; cum[i] = acc; }
+  if (ncomp < 4) for (int i = ncomp - 1; i < 4; ++i) cum[i] = 2.0;
+  o.m.b[0] = (uint8_t)a; o.m.b[1] = (uint8_t)b; o.m.nb = 2;
+  o.need = (1ull << a) | (1ull << b);
+  o.m.flags = 2;
+  o.m.aux = (int32_t)h->draw++;
+  o.m.p[0] = cum[0]; o.m.p[1] = cum[1]; o.m.p[2] = cum[2];
+  o.m.c_off = add_consts(h, v, 16); o.nconst = 16;
+  push(h, o);
+  h->pred = pred;
+  return 0;
+}
+
+int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, double flip_prob) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "measure")) return rc;
+  if (creg_bit >= 64) return fail(h, DQE_EINVAL, "creg has 64 bits");
+  if (forced > 1) return fail(h, DQE_EINVAL, "forced outcome must be -1, 0 or 1");
+  h->stats[4]++;
+  const int pred = h->pred;
+  h->pred = -1;
+  const int rc = lower_measure(h, axis, creg_bit, forced, discard, flip_prob);
+  h->pred = pred;
+  return rc;
+}
+
+int dqe_flush(dqe_t* h) { return do_flush(h); }
+
+int dqe_sync(dqe_t* h) {
+  if (int rc = do_flush(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) return collect_timing(h);
+  return 0;
+}
+
+int dqe_read_creg(dqe_t* h, int bit, int8_t* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (bit < 0 || bit >= 64 || !out) return fail(h, DQE_EINVAL, "read_creg: bad argument");
+  int8_t* d = nullptr;
+  CK(cudaMalloc(&d, h->batch));
+  k_extract_bit<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(h->creg, bit, d, h->batch);
+  h->stats[2]++;
+  CK(cudaMemcpyAsync(out, d, h->batch, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(d));
+  return 0;
+}
+
+int dqe_read_creg_words(dqe_t* h, uint64_t* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (!out) return fail(h, DQE_EINVAL, "read_creg_words: null");
+  CK(cudaMemcpyAsync(out, h->creg, h->batch * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (k < 1 || k > 20 || !cbits || !out) return fail(h, DQE_EINVAL, "histogram: 1 <= k <= 20");
+  HistParams hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.creg = h->creg; hp.batch = h->batch; hp.k = k;
+  for (int i = 0; i < k; ++i) {
+    if (cbits[i] < 0 || cbits[i] >= 64) return fail(h, DQE_EINVAL, "histogram: creg bit out of range");
+    hp.bits[i] = cbits[i];
+  }
+  const size_t nb = (size_t)1 << k;
+  CK(cudaMalloc(&hp.bins, nb * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(hp.bins, 0, nb * sizeof(unsigned long long), h->stream));
+  k_histogram<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(hp);
+  h->stats[2]++;
+  CK(cudaMemcpyAsync(out, hp.bins, nb * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(hp.bins));
+  return 0;
+}
+
+int dqe_reduced_dm(dqe_t* h, int k, const int* axes, int64_t shot, double* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (shot < 0 || shot >= h->batch || !out) return fail(h, DQE_EINVAL, "reduced_dm: bad shot");
+  ReadoutParams rp;
+  if (int rc = build_readout(h, k, axes, &rp)) return rc;
+  const size_t n = (size_t)1 << (2 * k);
+  CK(cudaMalloc(&rp.out_rdm, n * sizeof(double2)));
+  k_reduced_dm<<<(unsigned)n, 256, 0, h->stream>>>(rp, shot);
+  h->stats[2]++;
+  CK(cudaMemcpyAsync(out, rp.out_rdm, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(rp.out_rdm));
+  return 0;
+}
+
+int dqe_fidelity_ket(dqe_t* h, int k, const int* axes, const double* ket, double* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (!ket || !out) return fail(h, DQE_EINVAL, "fidelity_ket: null");
+  ReadoutParams rp;
+  if (int rc = build_readout(h, k, axes, &rp)) return rc;
+  const size_t n = (size_t)1 << k;
+  double2* dk = nullptr;
+  CK(cudaMalloc(&dk, n * sizeof(double2)));
+  CK(cudaMalloc(&rp.out_fid, h->batch * sizeof(double)));
+  CK(cudaMemcpyAsync(dk, ket, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  rp.ket = dk;
+  k_fidelity_ket<<<(unsigned)h->batch, 128, 0, h->stream>>>(rp);
+  h->stats[2]++;
+  CK(cudaMemcpyAsync(out, rp.out_fid, h->batch * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(dk));
+  CK(cudaFree(rp.out_fid));
+  return 0;
+}
+
+int dqe_get_state(dqe_t* h, int64_t shot, double* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (shot < 0 || shot >= h->batch || !out) return fail(h, DQE_EINVAL, "get_state: bad shot");
+  const size_t n = (size_t)1 << h->P;
+  CK(cudaMemcpyAsync(out, h->state + (size_t)shot * n, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dqe_set_state(dqe_t* h, int64_t shot, const double* in, uint64_t live_mask) {
+  if (int rc = do_flush(h)) return rc;
+  if (shot < 0 || shot >= h->batch || !in) return fail(h, DQE_EINVAL, "set_state: bad shot");
+  if (h->nmax < 64 && (live_mask >> h->nmax)) return fail(h, DQE_EINVAL, "set_state: live mask out of range");
+  const size_t n = (size_t)1 << h->P;
+  CK(cudaMemcpyAsync(h->state + (size_t)shot * n, in, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->live_axes = live_mask;
+  h->planned_live = phys_live(h, live_mask);
+  return 0;
+}
+
+int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes) {
+  if (!h || !dev || !nbytes) return DQE_EINVAL;
+  *dev = h->state;
+  *nbytes = (int64_t)(((size_t)h->batch << h->P) * sizeof(double2));
+  return 0;
+}
+
+int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
+  if (!h || !key) return DQE_EINVAL;
+  if (int rc = do_flush(h)) return rc;
+  if (!strcmp(key, "tile_bits")) {
+    if (value < 4 || value > 13) return fail(h, DQE_EINVAL, "tile_bits in [4, 13]");
+    h->tile_bits = (int)value;
+  } else if (!strcmp(key, "min_run_bits")) {
+    if (value < 0 || value > 12) return fail(h, DQE_EINVAL, "min_run_bits in [0, 12]");
+    h->min_run_bits = (int)value;
+  } else if (!strcmp(key, "fuse")) {
+    h->fuse = value ? 1 : 0;
+  } else return fail(h, DQE_EINVAL, std::string("unknown option ") + key);
+  return 0;
+}
+
+int dqe_get_stats(dqe_t* h, int64_t* out) {
+  if (!h || !out) return DQE_EINVAL;
+  memcpy(out, h->stats, sizeof(h->stats));
+  return 0;
+}
+int dqe_reset_stats(dqe_t* h) {
+  if (!h) return DQE_EINVAL;
+  memset(h->stats, 0, sizeof(h->stats));
+  return 0;
+}
+
+int dqe_time_passes(dqe_t* h, int enable) {
+  if (int rc = dqe_sync(h)) return rc;
+  h->timing = enable != 0;
+  h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
+  return 0;
+}
+int dqe_pass_time_ms(dqe_t* h, double* total_ms, int64_t* n_passes, int64_t* amp_updates) {
+  if (int rc = dqe_sync(h)) return rc;
+  if (total_ms) *total_ms = h->t_ms;
+  if (n_passes) *n_passes = h->t_passes;
+  if (amp_updates) *amp_updates = h->t_amps;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+"""ctypes binding of ``libdqcengine.so`` (C-ABI in ``include/dqc_engine.h``).
+
+:class:`Engine` is the qstate backend the executor drives -- the stand-in for NetSquid's
+``KetRepr`` / ``DenseDMRepr`` behind ``qubitapi``.  Method names and
+argument meaning follow the op vocabulary of the boundary; every call lands in the CUDA
+library.  There is **no CPU fallback**: if the shared library is missing or no CUDA device is
+present, construction raises.
+
+PyTorch is used only for plumbing: ``Engine.state_tensor()`` wraps the device buffer zero-copy
+as a ``torch.complex128`` tensor, and an engine can adopt a caller-allocated torch tensor and
+CUDA stream.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+KET = 0
+DM = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdqcengine.so")
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_dbl_p = ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); the complete list of symbols include/dqc_engine.h declares
+ABI = {
+    "dqe_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "dqe_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "dqe_version": (ctypes.c_char_p, []),
+    "dqe_seed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
+    "dqe_alloc_axis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dqe_free_axis": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dqe_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dqe_live_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "dqe_enqueue_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_enqueue_2q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
+    "dqe_enqueue_ctrl_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
+    "dqe_enqueue_diag": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
+    "dqe_set_predicate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dqe_enqueue_cond_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
+    "dqe_enqueue_pauli_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_enqueue_depolarize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, ctypes.c_double]),
+    "dqe_enqueue_kraus_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
+    "dqe_inject_2q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
+    "dqe_inject_2q_mixture": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             _c_dbl_p, _c_dbl_p]),
+    "dqe_measure": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_double]),
+    "dqe_flush": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_read_creg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int8)]),
+    "dqe_read_creg_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "dqe_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, ctypes.POINTER(ctypes.c_int64)]),
+    "dqe_reduced_dm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, ctypes.c_int64, _c_dbl_p]),
+    "dqe_fidelity_ket": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p, _c_dbl_p]),
+    "dqe_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, _c_dbl_p]),
+    "dqe_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, _c_dbl_p, ctypes.c_uint64]),
+    "dqe_state_ptr": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.POINTER(ctypes.c_int64)]),
+    "dqe_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "dqe_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "dqe_reset_stats": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_time_passes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dqe_pass_time_ms": (ctypes.c_int, [ctypes.c_void_p, _c_dbl_p, ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_int64)]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the engine and bind every symbol of the C-ABI.  Raises if the library was not
+    built (``python -c 'import __graft_entry__ as g; g.build()'``) -- there is no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineError(f"{p} not found: build the CUDA engine first (__graft_entry__.build())")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _cbuf(a):
+    """complex array -> contiguous interleaved doubles + pointer."""
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.complex128))
+    return arr, arr.ctypes.data_as(_c_dbl_p)
+
+
+def _ibuf(a):
+    arr = np.ascontiguousarray(np.asarray(list(a), dtype=np.int32))
+    return arr, arr.ctypes.data_as(_c_int_p)
+
+
+class Engine:
+    """Batched ket / density-matrix register on one B200.
+
+    Same vocabulary as the test oracle (``oracle/numpy_engine.py``) so that the executor can
+    drive either; here every method is a thin call through the C-ABI.
+    """
+
+    STAT_NAMES = ("passes", "micro_ops", "kernel_launches", "amp_updates", "api_ops", "finish_launches")
+
+    def __init__(self, formalism, max_qubits, batch=1, seed=0, shot_offset=0, device=0,
+                 state_tensor=None, stream=None, tile_bits=None, fuse=True):
+        self._h = ctypes.c_void_p()
+        self._lib = load_library()
+        self.formalism = KET if formalism in (KET, "ket") else DM
+        self.max_qubits = int(max_qubits)
+        self.batch = int(batch)
+        self.device = int(device)
+        self._keepalive = state_tensor
+        ext = ctypes.c_void_p(state_tensor.data_ptr()) if state_tensor is not None else None
+        st = ctypes.c_void_p(int(stream)) if stream else None
+        rc = self._lib.dqe_create(ctypes.byref(self._h), self.formalism, self.max_qubits, self.batch,
+                                  self.device, ext, st)
+        if rc != 0:
+            msg = self._lib.dqe_last_error(None).decode()
+            self._h = ctypes.c_void_p()
+            raise EngineError(f"dqe_create failed ({rc}): {msg}")
+        self._ck(self._lib.dqe_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(shot_offset)))
+        if tile_bits is None and os.environ.get("DQE_TILE_BITS"):
+            tile_bits = int(os.environ["DQE_TILE_BITS"])
+        if tile_bits is not None:
+            self.set_option("tile_bits", tile_bits)
+        if not fuse or os.environ.get("DQE_FUSE") == "0":
+            self.set_option("fuse", 0)
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(f"engine error {rc}: {self._lib.dqe_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dqe_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        self._ck(self._lib.dqe_set_option(self._h, key.encode(), int(value)))
+
+    def seed(self, seed, shot_offset=0):
+        self._ck(self._lib.dqe_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(shot_offset)))
+
+    @property
+    def live(self):
+        m = ctypes.c_uint64()
+        self._ck(self._lib.dqe_live_mask(self._h, ctypes.byref(m)))
+        return [a for a in range(self.max_qubits) if (m.value >> a) & 1]
+
+    @property
+    def n_live(self):
+        return len(self.live)
+
+    # ------------------------------------------------------------------ register
+    def alloc_axis(self, axis=-1):
+        if axis < 0:
+            live = set(self.live)
+            axis = min(a for a in range(self.max_qubits) if a not in live)
+        self._ck(self._lib.dqe_alloc_axis(self._h, int(axis)))
+        return axis
+
+    def free_axis(self, axis):
+        self._ck(self._lib.dqe_free_axis(self._h, int(axis)))
+
+    def reset(self, axis):
+        self._ck(self._lib.dqe_reset(self._h, int(axis)))
+
+    # ------------------------------------------------------------------ unitaries
+    def apply_1q(self, axis, m):
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2, 2))
+        self._ck(self._lib.dqe_enqueue_1q(self._h, int(axis), p))
+
+    def apply_2q(self, a, b, m):
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(4, 4))
+        self._ck(self._lib.dqe_enqueue_2q(self._h, int(a), int(b), p))
+
+    def apply_ctrl_1q(self, c, t, m):
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2, 2))
+        self._ck(self._lib.dqe_enqueue_ctrl_1q(self._h, int(c), int(t), p))
+
+    def apply_diag(self, axes, d):
+        _a, pa = _ibuf(axes)
+        _k, p = _cbuf(np.asarray(d, dtype=complex).reshape(-1))
+        self._ck(self._lib.dqe_enqueue_diag(self._h, len(_a), pa, p))
+
+    def set_predicate(self, creg_bit):
+        self._ck(self._lib.dqe_set_predicate(self._h, int(creg_bit)))
+
+    def cond_1q(self, axis, m, creg_bit):
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2, 2))
+        self._ck(self._lib.dqe_enqueue_cond_1q(self._h, int(axis), p, int(creg_bit)))
+
+    # ------------------------------------------------------------------ channels
+    def pauli_channel(self, axis, p):
+        arr = np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(4))
+        self._ck(self._lib.dqe_enqueue_pauli_channel(self._h, int(axis), arr.ctypes.data_as(_c_dbl_p)))
+
+    def depolarize(self, axes, p):
+        _a, pa = _ibuf(axes)
+        self._ck(self._lib.dqe_enqueue_depolarize(self._h, len(_a), pa, float(p)))
+
+    def kraus_1q(self, axis, ks):
+        arr = np.asarray(ks, dtype=complex).reshape(-1, 2, 2)
+        _k, p = _cbuf(arr)
+        self._ck(self._lib.dqe_enqueue_kraus_1q(self._h, int(axis), arr.shape[0], p))
+
+    # ------------------------------------------------------------------ injection
+    def inject_2q(self, a, b, state, is_dm):
+        """``state``: ket (4,) or density matrix (4, 4); a = most significant qubit."""
+        if self.formalism == KET and is_dm:
+            # spectral decomposition on the host, largest eigenvalue first, so that the
+            # per-shot component draw is reproducible
+            sig = np.asarray(state, dtype=complex).reshape(4, 4)
+            lam, vec = np.linalg.eigh(sig)
+            lam = np.clip(lam[::-1], 0, None)
+            vec = vec[:, ::-1]
+            probs = np.ascontiguousarray(lam / lam.sum(), dtype=np.float64)
+            _k, pk = _cbuf(vec.T)
+            self._ck(self._lib.dqe_inject_2q_mixture(self._h, int(a), int(b), 4,
+                                                     probs.ctypes.data_as(_c_dbl_p), pk))
+            return
+        arr = np.asarray(state, dtype=complex).reshape(16 if is_dm else 4)
+        _k, p = _cbuf(arr)
+        self._ck(self._lib.dqe_inject_2q(self._h, int(a), int(b), p, 1 if is_dm else 0))
+
+    # ------------------------------------------------------------------ measurement
+    def measure(self, axis, creg_bit, forced=-1, discard=False, flip_prob=0.0):
+        cb = -1 if creg_bit is None else int(creg_bit)
+        f = -1 if forced is None else int(forced)
+        self._ck(self._lib.dqe_measure(self._h, int(axis), cb, f, 1 if discard else 0, float(flip_prob)))
+
+    # ------------------------------------------------------------------ execution / read-out
+    def flush(self):
+        self._ck(self._lib.dqe_flush(self._h))
+
+    def sync(self):
+        self._ck(self._lib.dqe_sync(self._h))
+
+    def read_creg(self, bit):
+        out = np.empty(self.batch, dtype=np.int8)
+        self._ck(self._lib.dqe_read_creg(self._h, int(bit), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int8))))
+        return out
+
+    def read_creg_words(self):
+        out = np.empty(self.batch, dtype=np.uint64)
+        self._ck(self._lib.dqe_read_creg_words(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
+    def histogram(self, cbits):
+        _a, pa = _ibuf(cbits)
+        out = np.zeros(2 ** len(_a), dtype=np.int64)
+        self._ck(self._lib.dqe_histogram(self._h, len(_a), pa, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+        return out
+
+    def reduced_dm(self, axes, shot=0):
+        _a, pa = _ibuf(axes)
+        k = len(_a)
+        out = np.empty((2 ** k, 2 ** k), dtype=np.complex128)
+        self._ck(self._lib.dqe_reduced_dm(self._h, k, pa, int(shot), out.ctypes.data_as(_c_dbl_p)))
+        return out
+
+    def fidelity_ket_all(self, axes, ket):
+        _a, pa = _ibuf(axes)
+        _k, pk = _cbuf(np.asarray(ket, dtype=complex).reshape(-1))
+        out = np.empty(self.batch, dtype=np.float64)
+        self._ck(self._lib.dqe_fidelity_ket(self._h, len(_a), pa, pk, out.ctypes.data_as(_c_dbl_p)))
+        return out
+
+    def fidelity_ket(self, axes, ket, shot=0):
+        return float(self.fidelity_ket_all(axes, ket)[shot])
+
+    def full_state(self, shot=None):
+        """Raw fixed-layout state: (b, 2^n) ket or (b, 2^n, 2^n) dm, like the oracle's."""
+        shots = range(self.batch) if shot is None else [shot]
+        n = self.max_qubits
+        dim = 2 ** n if self.formalism == KET else 4 ** n
+        out = np.empty((len(shots), dim), dtype=np.complex128)
+        for i, s in enumerate(shots):
+            self._ck(self._lib.dqe_get_state(self._h, int(s), out[i].ctypes.data_as(_c_dbl_p)))
+        if self.formalism == DM:
+            out = out.reshape(len(shots), 2 ** n, 2 ** n)
+        return out
+
+    def set_state(self, shot, raw, live_axes):
+        arr, p = _cbuf(np.asarray(raw, dtype=complex).reshape(-1))
+        mask = 0
+        for a in live_axes:
+            mask |= 1 << int(a)
+        self._ck(self._lib.dqe_set_state(self._h, int(shot), p, mask))
+
+    def state_tensor(self):
+        """Zero-copy torch view of the device buffer (complex128, flat)."""
+        import torch
+
+        dev = ctypes.c_void_p()
+        nbytes = ctypes.c_int64()
+        self._ck(self._lib.dqe_state_ptr(self._h, ctypes.byref(dev), ctypes.byref(nbytes)))
+        n = nbytes.value // 16
+
+        class _Holder:
+            __cuda_array_interface__ = {
+                "shape": (n * 2,), "typestr": "<f8", "data": (dev.value, False), "version": 2}
+
+        t = torch.as_tensor(_Holder(), device=f"cuda:{self.device}")
+        return torch.view_as_complex(t.view(n, 2))
+
+    # ------------------------------------------------------------------ instrumentation
+    def stats(self):
+        out = (ctypes.c_int64 * 8)()
+        self._ck(self._lib.dqe_get_stats(self._h, out))
+        return dict(zip(self.STAT_NAMES, list(out)[:6]))
+
+    def reset_stats(self):
+        self._ck(self._lib.dqe_reset_stats(self._h))
+
+    def time_passes(self, enable=True):
+        self._ck(self._lib.dqe_time_passes(self._h, 1 if enable else 0))
+
+    def pass_time(self):
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        amps = ctypes.c_int64()
+        self._ck(self._lib.dqe_pass_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(amps)))
+        return ms.value, n.value, amps.value

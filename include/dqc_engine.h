@@ -1,0 +1,163 @@
+/* dqc_engine.h -- C-ABI of the B200 quantum-state engine (libdqcengine.so).
+ *
+ * This is the drop-in boundary for the one hot path under km-campbell/dqc_simulator:
+ * evolving the joint ket / density-matrix state that NetSquid's qubit formalism maintains
+ * while a partitioned circuit runs.  The reference itself contains no arithmetic; it calls
+ * the closed NetSquid wheel through
+ *
+ *   QuantumProcessor.execute_program(QuantumProgram)   software/dqc_control.py:269,300,317,
+ *                                                      367,391,409,460,474,556,608,778,786,945
+ *                                                      software/physical_layer.py:719,740
+ *   qubitapi.stochastic_operate / apply_pauli_noise /
+ *            assign_qstate                             hardware/noise_models.py:130,305,364
+ *   QSource + StateSampler (2-qubit state injection)   hardware/connections.py:145-150
+ *   qapi.reduced_dm / qapi.fidelity                    util/helper.py:151,209-214
+ *
+ * Each entry point below names the reference interface it replaces.  Plain pointers and
+ * sizes only; no torch / C++ types cross the boundary.  Complex numbers are interleaved
+ * (re, im) doubles.  Matrices are row-major; for multi-qubit operators the FIRST listed
+ * axis is the MOST significant index (NetSquid's big-endian convention, pinned by
+ * tests/unit_tests/qlib/test_circuit_identities.py:93-96).
+ *
+ * Model
+ * -----
+ * A handle owns a batch of `batch` independent registers ("shots" / noisy trajectories) of
+ * `max_qubits` axes each, in one of two formalisms:
+ *   ket : batch x 2^max_qubits complex128, axis a = bit a of the flat index
+ *   dm  : batch x 4^max_qubits complex128, flat index = row << max_qubits | col,
+ *         axis a = bit (a + max_qubits) of the row part and bit a of the column part
+ * Axes are made live / freed dynamically (communication qubits come and go with every remote
+ * gate).  A free axis is in |0> and costs no memory traffic: kernels enumerate live bits only.
+ * Every shot has a 64-bit classical register; measurement outcomes are written there on the
+ * device and classically-controlled corrections are *predicated* per shot, so a circuit runs
+ * without any host round trip.
+ *
+ * enqueue-style calls only append to the handle's gate queue.  dqe_flush() (or any read)
+ * cuts the queue into passes -- one pass = one read + one write of the live state, with every
+ * queued op whose target bits fit the pass's shared-memory tile applied while the tile is
+ * on chip -- and launches them on the handle's stream.
+ *
+ * Errors: every function returns 0 on success or a negative DQE_E* code; the message is
+ * available from dqe_last_error().  No exception crosses the ABI.  CUDA errors are sticky.
+ * Threading: a handle is bound to one device + one stream and is not thread-safe.
+ */
+#ifndef DQC_ENGINE_H
+#define DQC_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dqe_engine dqe_t;
+
+#define DQE_KET 0
+#define DQE_DM  1
+
+#define DQE_OK          0
+#define DQE_EINVAL     -1   /* bad argument / axis state */
+#define DQE_ECUDA      -2   /* CUDA runtime error (sticky) */
+#define DQE_ENOMEM     -3
+#define DQE_EUNSUPPORTED -4
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Replaces: ns.set_qstate_formalism(QFormalism.KET|DM) + the QState NetSquid creates per
+ * entangled group (SURVEY.md Appendix A last row).  `ext_state` may be NULL (the engine
+ * allocates batch * 2^max_qubits (ket) or batch * 4^max_qubits (dm) complex128) or a device
+ * pointer to a caller-owned buffer of that size (e.g. a torch tensor's data_ptr()).
+ * `stream` is a cudaStream_t cast to void* (NULL = a new non-blocking stream owned by the
+ * handle).  State starts as |0..0> with no live axis. */
+int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int device,
+               void* ext_state, void* stream);
+int dqe_destroy(dqe_t* h);
+const char* dqe_last_error(const dqe_t* h);   /* h may be NULL: error of a failed dqe_create */
+const char* dqe_version(void);
+
+/* Philox4x32-10 stream: key = seed, counter = (global shot id, draw index).  `shot_offset`
+ * is the global id of this handle's shot 0 so sampling is invariant under shot sharding.
+ * Resets the draw index to 0. */
+int dqe_seed(dqe_t* h, uint64_t seed, uint64_t shot_offset);
+
+/* ---- register bookkeeping (INSTR_INIT / discard; dqc_control.py:473,
+ *      compiler_preprocessing.py:46-53, quantum_processors.py:414-422) ------------------- */
+int dqe_alloc_axis(dqe_t* h, int axis);   /* make a free axis live in |0> */
+int dqe_free_axis(dqe_t* h, int axis);    /* dm: partial trace; ket: unrecorded sampled measurement */
+int dqe_reset(dqe_t* h, int axis);        /* INSTR_INIT on an occupied position */
+int dqe_live_mask(dqe_t* h, uint64_t* mask);
+
+/* ---- unitaries (qubitapi.operate via QuantumProgram.apply, dqc_control.py:191-196;
+ *      operator matrices qlib/gates.py:29-220).  Matrices need not be unitary
+ *      (make_state_gen_op, gates.py:45-48). ------------------------------------------------- */
+int dqe_enqueue_1q(dqe_t* h, int axis, const double* m /*2x2 complex*/);
+int dqe_enqueue_2q(dqe_t* h, int a, int b, const double* m /*4x4 complex, a = MSB*/);
+int dqe_enqueue_ctrl_1q(dqe_t* h, int c, int t, const double* m /*2x2*/);  /* Operator.ctrl */
+int dqe_enqueue_diag(dqe_t* h, int k, const int* axes, const double* d /*2^k complex*/);
+
+/* Ops enqueued until dqe_set_predicate(h, -1) act only on shots whose creg bit is 1
+ * (classically controlled X / Z corrections, dqc_control.py:347-348, 387-390, 497-503). */
+int dqe_set_predicate(dqe_t* h, int creg_bit);
+int dqe_enqueue_cond_1q(dqe_t* h, int axis, const double* m, int creg_bit);
+
+/* ---- channels (hardware/noise_models.py:33-131, 226-253, 295-307, 343-366;
+ *      NetSquid DepolarNoiseModel wired at quantum_processors.py:868-877).
+ *      dm: applied analytically in one pass; ket: one branch sampled per shot. ------------- */
+int dqe_enqueue_pauli_channel(dqe_t* h, int axis, const double* p /*pI,pX,pY,pZ*/);
+int dqe_enqueue_depolarize(dqe_t* h, int k, const int* axes, double p);  /* k = 1, 2 */
+int dqe_enqueue_kraus_1q(dqe_t* h, int axis, int nk, const double* K /*nk x 2x2 complex*/);
+
+/* ---- 2-qubit state injection (BlackBoxEntanglingQsourceConnection,
+ *      hardware/connections.py:145-150; physical_layer.py:451-479).  `state` is a ket
+ *      (4 complex) or a density matrix (16 complex, is_dm = 1); a = MSB.  Both axes must be
+ *      free.  ket formalism + mixed state: an eigen-component is sampled per shot. --------- */
+int dqe_inject_2q(dqe_t* h, int a, int b, const double* state, int is_dm);
+/* ket formalism, mixed source state: per shot, component i (a ket of 4 complex) is injected
+ * with probability probs[i]; ncomp <= 4.  The decomposition (eigenvectors of the 4x4 state,
+ * e.g. werner_state(F), qlib/states.py:63-84) is the caller's so that it is reproducible. */
+int dqe_inject_2q_mixture(dqe_t* h, int a, int b, int ncomp, const double* probs,
+                          const double* kets /*ncomp x 4 complex*/);
+
+/* ---- measurement (INSTR_MEASURE, dqc_control.py:298,366,446-459,783-787; physical
+ *      instruction quantum_processors.py:414-422: noise BEFORE, optional discard).
+ *      Z basis.  creg_bit < 0: outcome not recorded.  forced = 0/1 overrides sampling
+ *      (-1 = sample).  flip_prob = MeasurementNoiseModel X-flip probability
+ *      (noise_models.py:295-307). ---------------------------------------------------------- */
+int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, double flip_prob);
+
+/* ---- execution + read-out ------------------------------------------------------------------ */
+int dqe_flush(dqe_t* h);                 /* plan + launch everything queued (asynchronous) */
+int dqe_sync(dqe_t* h);                  /* flush + wait for the stream */
+int dqe_read_creg(dqe_t* h, int bit, int8_t* out /*batch*/);
+int dqe_read_creg_words(dqe_t* h, uint64_t* out /*batch*/);
+int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out /*2^k, first bit = MSB*/);
+/* qapi.reduced_dm(qubits) (util/helper.py:209-214; examples/run_experiment.py:74-75):
+ * list order = big-endian.  out: 2^k x 2^k complex, row-major. */
+int dqe_reduced_dm(dqe_t* h, int k, const int* axes, int64_t shot, double* out);
+/* qapi.fidelity(qubits, ket, squared=True) (util/helper.py:151) for every shot. */
+int dqe_fidelity_ket(dqe_t* h, int k, const int* axes, const double* ket, double* out /*batch*/);
+/* Raw state of one shot in the fixed layout (2^max_qubits or 4^max_qubits complex). */
+int dqe_get_state(dqe_t* h, int64_t shot, double* out);
+/* Overwrite one shot's raw state and declare which axes are live (test / restart hook). */
+int dqe_set_state(dqe_t* h, int64_t shot, const double* in, uint64_t live_mask);
+/* Device pointer + size of the whole state buffer (wrap zero-copy as a torch tensor). */
+int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes);
+
+/* ---- tuning + instrumentation --------------------------------------------------------------- */
+/* key: "tile_bits" (log2 amplitudes staged per CTA, default 12), "min_run_bits" (log2 of the
+ * shortest contiguous run a tile may be built from, default 5), "fuse" (0: one op per pass). */
+int dqe_set_option(dqe_t* h, const char* key, int64_t value);
+/* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
+ * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates
+ * (elements read+written once per pass)  [4] queued API ops  [5] measure-finish launches. */
+int dqe_get_stats(dqe_t* h, int64_t* out /*8*/);
+int dqe_reset_stats(dqe_t* h);
+/* When enabled, every tile pass is bracketed by CUDA events on the handle's stream;
+ * dqe_pass_time_ms returns the accumulated device time and pass count since enabling. */
+int dqe_time_passes(dqe_t* h, int enable);
+int dqe_pass_time_ms(dqe_t* h, double* total_ms, int64_t* n_passes, int64_t* amp_updates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQC_ENGINE_H */

@@ -1,0 +1,293 @@
+"""CUDA engine vs oracle, through the C-ABI, on identical seeded op streams.
+
+Bar (BASELINE.json north_star): amplitudes / rho within 1e-10 max-abs (complex128); classical
+register contents, live-axis bookkeeping and forced-outcome measurements bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle.numpy_engine import OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def _engine(*a, **k):
+    from dqc_simulator_b200.engine import Engine
+
+    return Engine(*a, **k)
+
+
+def rand_unitary(rng, d):
+    z = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    q, r = np.linalg.qr(z)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+X = np.array([[0, 1], [1, 0]], dtype=complex)
+Z = np.diag([1, -1]).astype(complex)
+H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+CNOT = np.eye(4, dtype=complex)[[0, 1, 3, 2]]
+SWAP = np.eye(4, dtype=complex)[[0, 2, 1, 3]]
+
+
+def werner(F):
+    s = 2 ** -0.5
+    b = [np.array(v, dtype=complex) for v in ([s, 0, 0, s], [0, s, s, 0], [s, 0, 0, -s], [0, s, -s, 0])]
+    out = F * np.outer(b[0], b[0].conj())
+    for v in b[1:]:
+        out = out + (1 - F) / 3 * np.outer(v, v.conj())
+    return out
+
+
+class Both:
+    """Drives the CUDA engine and the oracle in lock step."""
+
+    def __init__(self, formalism, n, batch, seed, **kw):
+        self.g = _engine(formalism, n, batch, seed=seed, shot_offset=11, **kw)
+        self.o = OracleEngine(formalism, n, batch, seed=seed, shot_offset=11)
+        self.n = n
+
+    def __getattr__(self, name):
+        gf, of = getattr(self.g, name), getattr(self.o, name)
+
+        def call(*a, **k):
+            of(*a, **k)
+            return gf(*a, **k)
+
+        return call
+
+    def check(self, what=""):
+        gs, os_ = self.g.full_state(), self.o.full_state()
+        err = float(np.abs(gs - os_).max())
+        assert err < TOL, f"{what}: max-abs {err:.3e}"
+        assert sorted(self.g.live) == sorted(self.o.live)
+        assert np.array_equal(self.g.read_creg_words(), self.o.creg), what
+        return err
+
+
+def random_program(b, rng, steps, formalism, check_every=0):
+    n = b.n
+    cbit = 0
+    for step in range(steps):
+        live = list(b.o.live)
+        free = [a for a in range(n) if a not in live]
+        choices = []
+        if free:
+            choices += ["alloc"] * 2
+        if len(free) >= 2:
+            choices += ["inject"] * 2
+        if live:
+            choices += ["1q"] * 4 + ["diag1", "pauli", "depol1", "measure", "measure", "x", "h", "pred1q"]
+            if formalism == "dm":
+                choices += ["kraus"]
+        if len(live) >= 2:
+            choices += ["2q"] * 2 + ["cnot"] * 3 + ["ctrl", "cz", "diag2", "depol2", "depol2", "swap"]
+        if len(live) >= 3:
+            choices += ["free", "reset"]
+            if formalism == "ket":
+                choices += ["diag3"]
+        c = rng.choice(choices)
+        pick = lambda k: [int(x) for x in rng.choice(live, size=k, replace=False)]
+        if c == "alloc":
+            b.alloc_axis(int(rng.choice(free)))
+        elif c == "inject":
+            a0, a1 = [int(x) for x in rng.choice(free, size=2, replace=False)]
+            kind = rng.integers(3)
+            if kind == 0:
+                b.inject_2q(a0, a1, np.array([1, 0, 0, 1]) / np.sqrt(2), False)
+            elif kind == 1:
+                v = rng.normal(size=4) + 1j * rng.normal(size=4)
+                b.inject_2q(a0, a1, v / np.linalg.norm(v), False)
+            else:
+                b.inject_2q(a0, a1, werner(0.9), True)
+        elif c == "1q":
+            b.apply_1q(pick(1)[0], rand_unitary(rng, 2))
+        elif c == "x":
+            b.apply_1q(pick(1)[0], X)
+        elif c == "h":
+            b.apply_1q(pick(1)[0], H)
+        elif c == "diag1":
+            b.apply_1q(pick(1)[0], np.diag(np.exp(1j * rng.normal(size=2))))
+        elif c == "pred1q":
+            bit = int(rng.integers(0, max(cbit, 1))) % 64
+            if rng.integers(2):
+                b.cond_1q(pick(1)[0], X if rng.integers(2) else Z, bit)
+            else:
+                b.set_predicate(bit)
+                b.apply_1q(pick(1)[0], rand_unitary(rng, 2))
+                if len(live) >= 2:
+                    b.apply_2q(*pick(2), CNOT)
+                    b.depolarize(pick(2), 0.05)
+                b.set_predicate(-1)
+        elif c == "pauli":
+            p = rng.dirichlet([8, 1, 1, 1])
+            b.pauli_channel(pick(1)[0], p)
+        elif c == "depol1":
+            b.depolarize(pick(1), float(rng.uniform(0, 0.3)))
+        elif c == "depol2":
+            b.depolarize(pick(2), float(rng.uniform(0, 0.3)))
+        elif c == "kraus":
+            g = float(rng.uniform(0, 0.5))
+            b.kraus_1q(pick(1)[0], [[[1, 0], [0, np.sqrt(1 - g)]], [[0, np.sqrt(g)], [0, 0]]])
+        elif c == "2q":
+            b.apply_2q(*pick(2), rand_unitary(rng, 4))
+        elif c == "cnot":
+            b.apply_2q(*pick(2), CNOT)
+        elif c == "swap":
+            b.apply_2q(*pick(2), SWAP)
+        elif c == "cz":
+            b.apply_2q(*pick(2), np.diag([1, 1, 1, -1]).astype(complex))
+        elif c == "ctrl":
+            b.apply_ctrl_1q(*pick(2), rand_unitary(rng, 2))
+        elif c == "diag2":
+            b.apply_diag(pick(2), np.exp(1j * rng.normal(size=4)))
+        elif c == "diag3":
+            b.apply_diag(pick(3), np.exp(1j * rng.normal(size=8)))
+        elif c == "measure":
+            forced = -1 if rng.integers(4) else int(rng.integers(2))
+            b.measure(pick(1)[0], cbit % 64, forced, bool(rng.integers(2)), float(rng.choice([0.0, 0.0, 0.05])))
+            cbit += 1
+        elif c == "free":
+            b.free_axis(pick(1)[0])
+        elif c == "reset":
+            b.reset(pick(1)[0])
+        if check_every and (step + 1) % check_every == 0:
+            b.check(f"step {step} ({c})")
+    b.check("end")
+
+
+@pytest.mark.parametrize("formalism,n,batch", [("ket", 6, 5), ("dm", 4, 5), ("ket", 10, 3), ("dm", 6, 2)])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_programs_stepwise(formalism, n, batch, seed):
+    rng = np.random.default_rng(1000 * seed + n)
+    b = Both(formalism, n, batch, seed)
+    random_program(b, rng, 60, formalism, check_every=1)
+
+
+@pytest.mark.parametrize("formalism,n,batch,tile", [("ket", 12, 2, 8), ("ket", 14, 1, 10), ("dm", 7, 2, 9),
+                                                     ("dm", 7, 3, 12), ("ket", 9, 4, 5), ("dm", 5, 3, 6)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_random_programs_fused(formalism, n, batch, tile, fuse):
+    """Long queues, one flush: exercises the pass planner (tiles smaller than the register, ops
+    with target bits outside the contiguous run, controls / diagonals on outer bits)."""
+    rng = np.random.default_rng(77 + n + tile)
+    b = Both(formalism, n, batch, 5, tile_bits=tile, fuse=fuse)
+    random_program(b, rng, 150, formalism, check_every=50)
+    st = b.g.stats()
+    assert st["passes"] > 0 and st["micro_ops"] >= st["passes"]
+    if fuse:
+        assert st["micro_ops"] > st["passes"]
+
+
+@pytest.mark.parametrize("formalism", ["ket", "dm"])
+def test_forced_outcomes_bit_exact(formalism):
+    n = 5
+    b = Both(formalism, n, 4, 3)
+    for a in range(n):
+        b.alloc_axis(a)
+        b.apply_1q(a, H)
+    for i, (a, f) in enumerate([(0, 1), (3, 0), (1, 1)]):
+        b.measure(a, i, f, False, 0.0)
+    b.check()
+    words = b.g.read_creg_words()
+    assert np.all(words == 0b101)
+    assert np.array_equal(b.g.histogram([0, 1, 2]), b.o.histogram([0, 1, 2]))
+    assert np.array_equal(b.g.read_creg(0), b.o.read_creg(0))
+
+
+@pytest.mark.parametrize("formalism", ["ket", "dm"])
+def test_readout_matches_oracle(formalism):
+    rng = np.random.default_rng(5)
+    n = 6
+    b = Both(formalism, n, 3, 9)
+    for a in (0, 2, 3, 5, 1):
+        b.alloc_axis(a)
+        b.apply_1q(a, rand_unitary(rng, 2))
+    for _ in range(12):
+        a0, a1 = [int(x) for x in rng.choice(b.o.live, size=2, replace=False)]
+        b.apply_2q(a0, a1, rand_unitary(rng, 4))
+        b.depolarize([a0, a1], 0.02) if formalism == "dm" else None
+    b.measure(2, 0, -1, False, 0.0)
+    for axes in ([3], [5, 0], [1, 3, 0], [0, 1, 2, 3, 5]):
+        for shot in range(3):
+            assert np.abs(b.g.reduced_dm(axes, shot) - b.o.reduced_dm(axes, shot)).max() < TOL
+        ket = rng.normal(size=2 ** len(axes)) + 1j * rng.normal(size=2 ** len(axes))
+        ket /= np.linalg.norm(ket)
+        fg = b.g.fidelity_ket_all(axes, ket)
+        fo = [b.o.fidelity_ket(axes, ket, s) for s in range(3)]
+        assert np.abs(fg - fo).max() < TOL
+
+
+def test_sampling_is_sharding_invariant():
+    """Shots [0, 8) in one engine == shots [0, 4) + [4, 8) in two engines (Philox keyed by
+    global shot id): the property multi-GPU shot sharding relies on."""
+    def run(batch, offset):
+        from dqc_simulator_b200.engine import Engine
+
+        e = Engine("ket", 3, batch, seed=42, shot_offset=offset)
+        for a in range(3):
+            e.alloc_axis(a)
+            e.apply_1q(a, H)
+        e.apply_2q(0, 1, CNOT)
+        e.depolarize([0, 1], 0.3)
+        for a in range(3):
+            e.measure(a, a, -1, False, 0.1)
+        return e.read_creg_words(), e.full_state()
+
+    w, s = run(8, 0)
+    w0, s0 = run(4, 0)
+    w1, s1 = run(4, 4)
+    assert np.array_equal(w, np.concatenate([w0, w1]))
+    assert np.array_equal(s, np.concatenate([s0, s1]))
+
+
+def test_chi_square_histogram():
+    """Sampled outcome histogram vs exact probabilities of the oracle state (chi-square, 1e5 shots)."""
+    from dqc_simulator_b200.engine import Engine
+
+    rng = np.random.default_rng(0)
+    n, shots = 4, 100000
+    us = [rand_unitary(rng, 2) for _ in range(n)]
+    u2 = rand_unitary(rng, 4)
+    e = Engine("ket", n, shots, seed=2024)
+    o = OracleEngine("ket", n, 1, seed=0)
+    for be in (e, o):
+        for a in range(n):
+            be.alloc_axis(a)
+            be.apply_1q(a, us[a])
+        be.apply_2q(0, 2, u2)
+        be.apply_2q(1, 3, CNOT)
+    # exact distribution of (q3 q2 q1 q0) read as bits [0..3] -> histogram index with bit 0 = MSB
+    psi = o.full_state(0).reshape(-1)
+    probs = np.abs(psi) ** 2
+    for a in range(n):
+        e.measure(a, a, -1, False, 0.0)
+    hist = e.histogram(list(range(n)))
+    # histogram index = sum creg_bit[a] << (n-1-a); state index = sum bit_a << a
+    exp = np.zeros(2 ** n)
+    for idx in range(2 ** n):
+        h = 0
+        for a in range(n):
+            h |= ((idx >> a) & 1) << (n - 1 - a)
+        exp[h] = probs[idx] * shots
+    chi2 = float(((hist - exp) ** 2 / exp).sum())
+    # dof = 15; P(chi2 > 50) ~ 1e-5
+    assert hist.sum() == shots
+    assert chi2 < 50.0, chi2
+
+
+def test_errors_are_reported_not_thrown_across_abi():
+    from dqc_simulator_b200.engine import Engine, EngineError
+
+    e = Engine("ket", 3, 1)
+    with pytest.raises(EngineError, match="holds no qubit"):
+        e.apply_1q(0, X)
+    e.alloc_axis(0)
+    with pytest.raises(EngineError, match="already live"):
+        e.alloc_axis(0)
+    with pytest.raises(EngineError, match="dm-only"):
+        e.kraus_1q(0, [np.eye(2)])
+    e.apply_1q(0, X)
+    assert abs(e.full_state(0)[0, 1] - 1) < 1e-15
