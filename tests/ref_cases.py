@@ -1,0 +1,204 @@
+"""Known-answer cases lifted from the reference's own tests, written against the boundary
+(``QuantumProgram.apply`` / ``QPU.execute_program`` / compiled ``qpu_op_dict``), so the same
+case runs on the oracle (CPU suite, pins the oracle) and on the CUDA engine (``-m gpu``).
+
+Every case cites the reference test it restates (paths relative to /root/reference/tests).
+The reference asserts ``qapi.fidelity(qubits, desired) ~ 1`` to 3-5 places; here the reduced
+density matrix is compared element-wise (stronger), tolerance 1e-12 unless stated.
+"""
+import functools as ft
+import os
+
+import numpy as np
+
+from dqc_simulator_b200 import executor, hardware, opstream
+from dqc_simulator_b200 import instructions as ins
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+S0 = np.array([1, 0], dtype=complex)
+S1 = np.array([0, 1], dtype=complex)
+H0 = (S0 + S1) / np.sqrt(2)
+B00 = np.array([1, 0, 0, 1], dtype=complex) / np.sqrt(2)
+DM0 = np.outer(S0, S0)
+
+
+def ket2dm(v):
+    v = np.asarray(v, dtype=complex).reshape(-1)
+    return np.outer(v, v.conj())
+
+
+def single_qpu(make_backend, formalism="dm", max_qubits=8, batch=1, **spec):
+    """One bare processor, like the ``QuantumProcessor`` the hardware unit tests build."""
+    spec.setdefault("num_positions", 7)
+    spec.setdefault("num_comm_qubits", 2)
+    qs = hardware.QPUSpec(name="node_0", **spec)
+    be = make_backend(formalism, max_qubits, batch)
+    ex = executor.DQCExecutor({"node_0": []}, hardware.DQCSpec([qs]), be)
+    return ex, ex.qpus["node_0"], be
+
+
+def peek(ex, be, positions, at_time=None, node="node_0", shot=0):
+    """``processor.peek(positions)`` after ``ns.sim_run(at_time)`` -> reduced dm (big-endian)."""
+    if at_time is not None:
+        ex.end_time = at_time
+    axes = ex.axes_of([(p, node) for p in positions])
+    return be.reduced_dm(axes, shot)
+
+
+def bell_after_depol(p):
+    return np.array([[(2 - p) / 4, 0, 0, (1 - p) / 2], [0, p / 4, 0, 0], [0, 0, p / 4, 0],
+                     [(1 - p) / 2, 0, 0, (2 - p) / 4]], dtype=complex)
+
+
+# ---- unit_tests/hardware/test_noise_model.py ------------------------------------------------
+def noise_entangling_gate_10_percent(make_backend):
+    """:23-108  INIT[0,1]; H 0; CNOT 0,1 with p = 0.1 two-qubit depolarising after the CNOT."""
+    ex, qpu, be = single_qpu(make_backend, p_depolar_error_cnot=0.1)
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, [0, 1])
+    prog.apply(ins.INSTR_H, [0])
+    prog.apply(ins.INSTR_CNOT, [0, 1])
+    qpu.execute_program(prog)
+    return peek(ex, be, [0, 1]), bell_after_depol(0.1)
+
+
+def _diag_with_coherence(d, i, j, c):
+    m = np.diag(np.array(d, dtype=complex))
+    m[i, j] = m[j, i] = c
+    return m
+
+
+def noise_entangling_gate_extra_qubit(make_backend, precombine=False):
+    """:110-204 (spectator qubit) and :206-302 (inputs pre-combined by two noiseless CNOTs)."""
+    p = 0.5
+    ex, qpu, be = single_qpu(make_backend, p_depolar_error_cnot=p)
+    noisy, ideal = qpu.spec, hardware.QPUSpec(name="node_0", num_positions=7)
+    qpu.spec = ideal
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, [0, 1, 2])
+    prog.apply(ins.INSTR_H, [0])
+    if precombine:
+        prog.apply(ins.INSTR_CNOT, [0, 2])
+        prog.apply(ins.INSTR_CNOT, [0, 2])
+    qpu.execute_program(prog)
+    qpu.spec = noisy
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_CNOT, [0, 1])
+    qpu.execute_program(prog)
+    want = _diag_with_coherence([(2 - p) / 4, 0, p / 4, 0, p / 4, 0, (2 - p) / 4, 0], 0, 6, (1 - p) / 2)
+    return peek(ex, be, [0, 1, 2]), want
+
+
+def noise_recover_ideal_when_error_0(make_backend):
+    """:304-384  p = 0 leaves (|000> + |110>)/sqrt2 (alpha = 1, beta = 0 state-gen is the identity case)."""
+    ex, qpu, be = single_qpu(make_backend, p_depolar_error_cnot=0.0)
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, [0, 1, 2])
+    prog.apply(ins.INSTR_H, [0])
+    prog.apply(ins.INSTR_CNOT, [0, 1])
+    qpu.execute_program(prog)
+    v = (np.kron(S0, np.kron(S0, S0)) + np.kron(S1, np.kron(S1, S0))) / np.sqrt(2)
+    return peek(ex, be, [0, 1, 2]), ket2dm(v)
+
+
+def noise_02_entangling_gate(make_backend, precombine=False):
+    """:386-480 and :482-578  CNOT on positions (0, 2) of a 3-qubit register, p = 0.5."""
+    p = 0.5
+    ex, qpu, be = single_qpu(make_backend, p_depolar_error_cnot=p)
+    noisy, ideal = qpu.spec, hardware.QPUSpec(name="node_0", num_positions=7)
+    qpu.spec = ideal
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, [0, 1, 2])
+    prog.apply(ins.INSTR_H, [0])
+    if precombine:
+        prog.apply(ins.INSTR_CNOT, [0, 1])
+        prog.apply(ins.INSTR_CNOT, [0, 1])
+    qpu.execute_program(prog)
+    qpu.spec = noisy
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_CNOT, [0, 2])
+    qpu.execute_program(prog)
+    want = _diag_with_coherence([(2 - p) / 4, p / 4, 0, 0, p / 4, (2 - p) / 4, 0, 0], 0, 5, (1 - p) / 2)
+    return peek(ex, be, [0, 1, 2]), want
+
+
+def memory_depol(make_backend, nq, init_time=0.0):
+    """:657-736 (1 qubit), :738-825 (2), :827-911 (10), :913-993 (INIT takes 1 s; the decoherence
+    clock starts when INIT completes): 10 s at 0.1 Hz -> diag((1 + 1/e)/2, (1 - 1/e)/2) each."""
+    ex, qpu, be = single_qpu(make_backend, max_qubits=max(nq, 2), num_positions=max(nq, 7), num_comm_qubits=0,
+                             proc_qubit_depolar_rate=0.1, init_time=init_time)
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, list(range(nq)))
+    qpu.execute_program(prog)
+    one = np.diag([(1 + np.exp(-1)) / 2, (1 - np.exp(-1)) / 2]).astype(complex)
+    got = [peek(ex, be, [q], at_time=init_time + 1e10) for q in range(nq)]
+    return got, [one] * nq
+
+
+# ---- unit_tests/hardware/test_quantum_processors.py -----------------------------------------------
+def qpu_mem_depol_by_position_type(make_backend, which):
+    """:77-103 (comm qubits only) / :105-130 (processing qubits only): 7 positions, 2 comm."""
+    kw = dict(comm_qubit_depolar_rate=0.1) if which == "comm" else dict(proc_qubit_depolar_rate=0.1)
+    ex, qpu, be = single_qpu(make_backend, **kw)
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, list(range(7)))
+    qpu.execute_program(prog)
+    one = np.diag([(1 + np.exp(-1)) / 2, (1 - np.exp(-1)) / 2]).astype(complex)
+    want = [one if ((q < 2) == (which == "comm")) else DM0 for q in range(7)]
+    got = [peek(ex, be, [q], at_time=1e10 + 3) for q in range(7)]
+    return got, want
+
+
+def qpu_cnot_depol_in_7_qubit_register(make_backend, a, b):
+    """:132-164 (comm positions 0,1) / :166-201 (processing positions 2,3), p = 0.1."""
+    ex, qpu, be = single_qpu(make_backend, p_depolar_error_cnot=0.1)
+    prog = executor.QuantumProgram()
+    prog.apply(ins.INSTR_INIT, list(range(7)))
+    prog.apply(ins.INSTR_H, [a])
+    prog.apply(ins.INSTR_CNOT, [a, b])
+    qpu.execute_program(prog)
+    others = [q for q in range(7) if q not in (a, b)]
+    got = [peek(ex, be, [a, b], at_time=1e10 + 3)] + [peek(ex, be, [q]) for q in others]
+    return got, [bell_after_depol(0.1)] + [DM0] * 5
+
+
+# ---- circuit-level cases: compiled by the reference's compiler into tests/golden/ref_*.json ------
+def run_golden(make_backend, name, formalism="dm", max_qubits=8, batch=1, num_qpus=2, forced=None,
+               host_branching=False, dqc=None, **spec):
+    ops, meta = opstream.load(os.path.join(GOLDEN, name))
+    spec.setdefault("num_positions", 8)
+    spec.setdefault("num_comm_qubits", 3)
+    if dqc is None:
+        dqc = hardware.DQCSpec.uniform(max(num_qpus, len(ops)), **spec)
+    be = make_backend(formalism, max_qubits, batch)
+    ex = executor.DQCExecutor(ops, dqc, be, forced_outcomes=forced, host_branching=host_branching).run()
+    return ex, be, meta
+
+
+def rdm(ex, be, qubits, shot=0):
+    return be.reduced_dm(ex.axes_of(qubits), shot)
+
+
+CIRCUIT_CASES = {
+    # unit_tests/software/test_dqc_control.py
+    "local_x": ("ref_local_x.json", [[(2, "node_0")], [(2, "node_1")]], [ket2dm(S1), ket2dm(S1)], ":62-80"),
+    "remote_cnot_cat": ("ref_remote_cnot_cat.json", [[(2, "node_0"), (2, "node_1")]], [ket2dm(B00)], ":82-96"),
+    "teleport_only": ("ref_teleport_only.json", [[(0, "node_1")]], [ket2dm(H0)], ":98-110"),
+    "remote_cnot_tp_safe": ("ref_remote_cnot_tp_safe.json", [[(2, "node_0"), (2, "node_1")]], [ket2dm(B00)],
+                            ":112-126"),
+    # three CNOTs in a row = one CNOT
+    "3x_remote_cnot_cat": ("ref_3x_remote_cnot_cat.json", [[(2, "node_0"), (2, "node_1")]], [ket2dm(B00)],
+                           ":128-144"),
+    "3x_remote_cnot_tp_safe": ("ref_3x_remote_cnot_tp_safe.json", [[(2, "node_0"), (2, "node_1")]],
+                               [ket2dm(B00)], ":146-162"),
+    "distribute_ebit": ("ref_distribute_ebit.json", [[(0, "node_0"), (0, "node_1")]], [ket2dm(B00)], ":273-283"),
+    "distribute_3_ebits": ("ref_distribute_3_ebits.json",
+                           [[(i, "node_0"), (i, "node_1")] for i in range(3)], [ket2dm(B00)] * 3, ":285-306"),
+    "remote_cnot_1tp": ("ref_remote_cnot_1tp.json", [[(2, "node_0")]], [None], "compilers.py:183-195"),
+}
+
+
+def toffoli_want(a, b, t):
+    """unit_tests/qlib/test_circuit_identities.py:60-427 truth table: target flips iff a = b = 1."""
+    out = [S1 if a else S0, S1 if b else S0, S1 if (t ^ (a & b)) else S0]
+    return ket2dm(ft.reduce(np.kron, out))

@@ -1,0 +1,149 @@
+"""The reference's known-answer cases (tests/ref_cases.py) and the committed reference-compiled
+circuits, run on the CUDA engine through the C-ABI, checked against the closed forms and against
+the oracle on the same seeded inputs (1e-10 max-abs, classical bits bit-exact)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import ref_cases as rc
+from dqc_simulator_b200 import hardware
+from oracle.numpy_engine import OracleEngine
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def gpu(formalism, max_qubits, batch):
+    from dqc_simulator_b200.engine import Engine
+
+    return Engine(formalism, max_qubits, batch, seed=1)
+
+
+def cpu(formalism, max_qubits, batch):
+    return OracleEngine(formalism, max_qubits, batch, seed=1)
+
+
+def _cmp(got, want, tol=TOL):
+    if isinstance(got, list):
+        for g, w in zip(got, want):
+            _cmp(g, w, tol)
+        return
+    assert np.abs(np.asarray(got) - np.asarray(want)).max() < tol
+
+
+@pytest.mark.parametrize("case,args", [
+    (rc.noise_entangling_gate_10_percent, ()), (rc.noise_entangling_gate_extra_qubit, (False,)),
+    (rc.noise_entangling_gate_extra_qubit, (True,)), (rc.noise_recover_ideal_when_error_0, ()),
+    (rc.noise_02_entangling_gate, (False,)), (rc.noise_02_entangling_gate, (True,)),
+    (rc.memory_depol, (1, 0.0)), (rc.memory_depol, (2, 0.0)), (rc.memory_depol, (10, 0.0)),
+    (rc.memory_depol, (1, 1e9)), (rc.qpu_mem_depol_by_position_type, ("comm",)),
+    (rc.qpu_mem_depol_by_position_type, ("proc",)), (rc.qpu_cnot_depol_in_7_qubit_register, (0, 1)),
+    (rc.qpu_cnot_depol_in_7_qubit_register, (2, 3))])
+def test_reference_hardware_known_answers(case, args):
+    _cmp(*case(gpu, *args))
+
+
+@pytest.mark.parametrize("formalism", ["dm", "ket"])
+@pytest.mark.parametrize("case", sorted(rc.CIRCUIT_CASES))
+def test_reference_circuit_cases(case, formalism):
+    name, groups, wants, _ = rc.CIRCUIT_CASES[case]
+    ex, be, _ = rc.run_golden(gpu, name, formalism)
+    for qubits, want in zip(groups, wants):
+        if want is not None:
+            _cmp(rc.rdm(ex, be, qubits), want)
+
+
+@pytest.mark.parametrize("kind", ["local", "remote_cat"])
+@pytest.mark.parametrize("a,b,t", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)])
+def test_toffoli_truth_table(kind, a, b, t):
+    ex, be, _ = rc.run_golden(gpu, f"ref_toffoli_{kind}_{a}{b}{t}.json")
+    tq = (4, "node_0") if kind == "local" else (2, "node_1")
+    _cmp(rc.rdm(ex, be, [(2, "node_0"), (3, "node_0"), tq]), rc.toffoli_want(a, b, t))
+
+
+def test_logged_measurements_host_branching():
+    ex, be, _ = rc.run_golden(gpu, "ref_logged_meas.json", host_branching=True)
+    assert [r for _, _, r in ex.logged_results] == [1, 0, 1]
+
+
+@pytest.mark.parametrize("forced", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("formalism", ["ket", "dm"])
+def test_config1_ghz5_all_forced_outcomes(formalism, forced):
+    ex, be, meta = rc.run_golden(gpu, "c1_ghz5_2qpu_bisect_cat.json", formalism, max_qubits=7, forced=forced,
+                                 num_positions=5, num_comm_qubits=2)
+    data = [tuple(meta["qubit_map"][str(i)]) for i in range(5)]
+    ghz = np.zeros(32, dtype=complex)
+    ghz[0] = ghz[31] = 2 ** -0.5
+    _cmp(rc.rdm(ex, be, data), rc.ket2dm(ghz))
+
+
+NOISE = dict(p_depolar_error_cnot=1e-3, single_qubit_gate_error_prob=2e-5, meas_error_prob=3e-3,
+             comm_qubit_depolar_rate=0.055, proc_qubit_depolar_rate=0.055)
+
+
+def _c2_dqc(extra=None):
+    kw = dict(NOISE)
+    kw.update(extra or {})
+    return hardware.DQCSpec.uniform(3, state4distribution=hardware.werner_state(0.99), num_positions=10,
+                                    num_comm_qubits=2, **kw)
+
+
+@pytest.mark.parametrize("name", ["c2_ghz5_3qpu_cat.json", "c2_qft5_3qpu_cat.json", "c2_grover5_3qpu_cat.json"])
+def test_config2_noisy_dm_engine_vs_oracle(name):
+    """BASELINE config 2 at oracle size (4 shots): noisy DM, sampled outcomes from the shared Philox
+    stream -> same trajectories, rho to 1e-10, creg bit-exact."""
+    res = []
+    for mk in (gpu, cpu):
+        ex, be, meta = rc.run_golden(mk, name, "dm", max_qubits=7, batch=4, dqc=_c2_dqc())
+        data = [tuple(v) for v in meta["qubit_map"].values()]
+        axes = ex.axes_of(data)
+        res.append((be.full_state(), be.read_creg_words() if mk is gpu else be.creg,
+                    [be.reduced_dm(axes, s) for s in range(4)]))
+    assert np.abs(res[0][0] - res[1][0]).max() < TOL
+    assert np.array_equal(res[0][1], res[1][1])
+    _cmp(res[0][2], res[1][2])
+
+
+def test_config2_with_dephasing_and_amplitude_damping():
+    """north_star channels not wired by the reference: oracle-only parity."""
+    res = []
+    for mk in (gpu, cpu):
+        ex, be, _ = rc.run_golden(mk, "c2_qft5_3qpu_cat.json", "dm", max_qubits=7, batch=2,
+                                  dqc=_c2_dqc(dict(mem_dephase_rate=0.2, mem_amp_damp_rate=0.1)))
+        res.append(be.full_state())
+    assert np.abs(res[0] - res[1]).max() < TOL
+
+
+@pytest.mark.parametrize("name,nq,npos", [("c3_qft8_4qpu_cat.json", 10, 4), ("c3_ghz10_4qpu_cat.json", 12, 5),
+                                          ("c3_qft12_4qpu_cat.json", 14, 5)])
+def test_config3_shape_ket_engine_vs_oracle(name, nq, npos):
+    """BASELINE config 3 shape at oracle size: QFT/GHZ over 4 QPUs, cat-comm, ket, ideal."""
+    res = []
+    for mk in (gpu, cpu):
+        ex, be, meta = rc.run_golden(mk, name, "ket", max_qubits=nq, batch=2, num_qpus=4,
+                                     num_positions=npos, num_comm_qubits=2)
+        res.append((be.full_state(), be.read_creg_words() if mk is gpu else be.creg))
+    assert np.abs(res[0][0] - res[1][0]).max() < TOL
+    assert np.array_equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("name,formalism,nq", [("c4_qft6_mono.json", "dm", 6), ("c5_qft12_mono.json", "ket", 12),
+                                                ("c5_ghz12_mono.json", "ket", 12)])
+def test_config45_shape_engine_vs_oracle(name, formalism, nq):
+    res = []
+    noise = NOISE if formalism == "dm" else {}
+    for mk in (gpu, cpu):
+        ex, be, _ = rc.run_golden(mk, name, formalism, max_qubits=nq, batch=1, num_qpus=1,
+                                  num_positions=nq, num_comm_qubits=0, **noise)
+        res.append(be.full_state())
+    assert np.abs(res[0] - res[1]).max() < TOL
+
+
+def test_every_fixture_runs(golden_dir):
+    """All small committed op streams execute on the engine without planner errors."""
+    for path in sorted(glob.glob(os.path.join(golden_dir, "ref_*.json"))):
+        ex, be, _ = rc.run_golden(gpu, os.path.basename(path))
+        be.sync()
+        assert ex.finished

@@ -1,0 +1,91 @@
+"""CPU suite: Philox known answers, op-stream serialisation, synthetic circuits vs the reference's
+shipped QASM, and the C-ABI library loading with every declared symbol (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dqc_simulator_b200 import circuits, engine, opstream
+from oracle import philox
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors: philox4x32-10."""
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert tuple(int(x) for x in got) == want
+
+
+def test_uniforms_in_unit_interval_and_keyed_by_global_shot():
+    u, u2 = philox.shot_uniforms(2024, np.arange(1000), 3)
+    assert (u >= 0).all() and (u < 1).all() and (u2 >= 0).all() and (u2 < 1).all()
+    a, _ = philox.shot_uniforms(2024, np.arange(500, 1000), 3)
+    assert np.array_equal(u[500:], a)
+    assert abs(u.mean() - 0.5) < 0.05
+
+
+def test_opstream_roundtrip(golden_dir):
+    for name in ("c1_ghz5_2qpu_bisect_cat.json", "c2_qft5_3qpu_cat.json", "c3_qft26_4qpu_cat.json.gz"):
+        ops, meta = opstream.load(os.path.join(golden_dir, name))
+        doc = opstream.encode(ops, meta)
+        ops2, meta2 = opstream.decode(doc)
+        assert meta == meta2
+        assert opstream.encode(ops2, meta2) == doc
+
+
+def test_c1_fixture_matches_reference_compiler_golden(golden_dir):
+    """Shape pinned by the reference's tests/unit_tests/software/test_compiler.py:54-75 and the
+    SURVEY Appendix D probe of the bisected GHZ-5."""
+    ops, _ = opstream.load(os.path.join(golden_dir, "c1_ghz5_2qpu_bisect_cat.json"))
+    n0 = [tuple(getattr(e, "name", e) if not isinstance(e, list) else tuple(e) for e in op) for op in ops["node_0"][0]]
+    assert n0 == [("init", (0, 1, 2, 3, 4)), ("node_1", "cat", "correct"), ("cnot_gate", -1, 4),
+                  (4, "node_1", "cat", "disentangle_start"), ("cnot_gate", 4, 3), ("cnot_gate", 3, 2)]
+    n1 = [tuple(getattr(e, "name", e) if not isinstance(e, list) else tuple(e) for e in op) for op in ops["node_1"][0]]
+    assert n1 == [("init", (0, 1, 2, 3)), ("h_gate", 3), ("cnot_gate", 3, 2), (2, "node_0", "cat", "entangle"),
+                  (2, "node_0", "cat", "disentangle_end")]
+
+
+_REF_EXAMPLES = "/root/reference/examples"
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_EXAMPLES), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("kind", ["ghz", "qft"])
+def test_synthetic_circuit_equals_reference_qasm_at_5_qubits(kind):
+    def body(text):
+        return [ln.strip() for ln in text.splitlines()
+                if ln.strip() and not ln.startswith(("//", "OPENQASM", "include", "qreg", "creg"))]
+
+    ours = (circuits.ghz_qasm if kind == "ghz" else circuits.qft_qasm)(5)
+    with open(f"{_REF_EXAMPLES}/{kind}_5qubits.qasm") as f:
+        ref = f.read()
+    assert body(ours) == body(ref)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dqc_engine.h")).read()
+    declared = set(re.findall(r"\b(dqe_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("dqe_t")
+    assert declared == set(engine.ABI), declared ^ set(engine.ABI)
+    lib = engine.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.dqe_version()
+
+
+def test_create_reports_error_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.EngineError):
+        engine.Engine("ket", 3, 1)

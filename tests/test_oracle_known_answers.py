@@ -1,0 +1,148 @@
+"""Pins the oracle (and the executor above it) against every closed-form state the reference's
+own tests assert for the hot path.  CPU only."""
+import numpy as np
+import pytest
+
+import ref_cases as rc
+from oracle.numpy_engine import OracleEngine
+
+TOL = 1e-12
+
+
+def make(formalism, max_qubits, batch):
+    return OracleEngine(formalism, max_qubits, batch, seed=1)
+
+
+def _cmp(got, want, tol=TOL):
+    if isinstance(got, list):
+        for g, w in zip(got, want):
+            _cmp(g, w, tol)
+        return
+    assert np.abs(np.asarray(got) - np.asarray(want)).max() < tol
+
+
+def test_noise_entangling_gate_10_percent():
+    _cmp(*rc.noise_entangling_gate_10_percent(make))
+
+
+@pytest.mark.parametrize("precombine", [False, True])
+def test_noise_entangling_gate_extra_qubit(precombine):
+    _cmp(*rc.noise_entangling_gate_extra_qubit(make, precombine))
+
+
+def test_noise_recover_ideal_when_error_0():
+    _cmp(*rc.noise_recover_ideal_when_error_0(make))
+
+
+@pytest.mark.parametrize("precombine", [False, True])
+def test_noise_02_entangling_gate(precombine):
+    _cmp(*rc.noise_02_entangling_gate(make, precombine))
+
+
+@pytest.mark.parametrize("nq,init_time", [(1, 0.0), (2, 0.0), (10, 0.0), (1, 1e9)])
+def test_memory_depolarisation(nq, init_time):
+    _cmp(*rc.memory_depol(make, nq, init_time))
+
+
+@pytest.mark.parametrize("which", ["comm", "proc"])
+def test_qpu_mem_depol_by_position_type(which):
+    _cmp(*rc.qpu_mem_depol_by_position_type(make, which))
+
+
+@pytest.mark.parametrize("a,b", [(0, 1), (2, 3)])
+def test_qpu_cnot_depol_in_7_qubit_register(a, b):
+    _cmp(*rc.qpu_cnot_depol_in_7_qubit_register(make, a, b))
+
+
+@pytest.mark.parametrize("formalism", ["dm", "ket"])
+@pytest.mark.parametrize("case", sorted(rc.CIRCUIT_CASES))
+def test_circuit_cases(case, formalism):
+    name, groups, wants, _cite = rc.CIRCUIT_CASES[case]
+    ex, be, _ = rc.run_golden(make, name, formalism)
+    assert ex.finished
+    for qubits, want in zip(groups, wants):
+        if want is not None:
+            _cmp(rc.rdm(ex, be, qubits), want, 1e-10)
+
+
+@pytest.mark.parametrize("formalism", ["dm", "ket"])
+def test_remote_cnot_1tp_moves_control_to_remote_comm_qubit(formalism):
+    """1tp (compilers.py:183-195): after the remote CNOT the control lives on node_1's comm qubit 0
+    and the original position holds a fresh |0>: (comm0@node_1, data@node_1) is the Bell state."""
+    ex, be, _ = rc.run_golden(make, "ref_remote_cnot_1tp.json", formalism)
+    _cmp(rc.rdm(ex, be, [(0, "node_1"), (2, "node_1")]), rc.ket2dm(rc.B00), 1e-10)
+    _cmp(rc.rdm(ex, be, [(2, "node_0")]), rc.DM0, 1e-10)
+
+
+@pytest.mark.parametrize("kind", ["local", "remote_cat"])
+@pytest.mark.parametrize("a,b,t", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)])
+def test_toffoli_truth_table(kind, a, b, t):
+    """unit_tests/qlib/test_circuit_identities.py:60-427."""
+    ex, be, _ = rc.run_golden(make, f"ref_toffoli_{kind}_{a}{b}{t}.json")
+    tq = (4, "node_0") if kind == "local" else (2, "node_1")
+    _cmp(rc.rdm(ex, be, [(2, "node_0"), (3, "node_0"), tq]), rc.toffoli_want(a, b, t), 1e-10)
+
+
+def test_logged_measurements():
+    """test_dqc_control.py:249-271: results [1, 0, 1] come back in issue order."""
+    ex, be, _ = rc.run_golden(make, "ref_logged_meas.json", host_branching=True)
+    assert [r for _, _, r in ex.logged_results] == [1, 0, 1]
+    assert [p for _, p, _ in ex.logged_results] == [2, 3, 4]
+
+
+def test_logged_measurements_same_qubit_keep():
+    """The literal sequence of test_dqc_control.py:249-271 (X, M, X, M, X, M on one position) needs
+    the measured qubit to stay in memory: engine supports keep as well as discard."""
+    from dqc_simulator_b200 import executor, hardware
+    from dqc_simulator_b200 import instructions as ins
+
+    ops = {"node_0": [[(ins.INSTR_INIT, 2), (ins.INSTR_X, 2), (ins.INSTR_MEASURE, 2, "logged"),
+                       (ins.INSTR_X, 2), (ins.INSTR_MEASURE, 2, "logged"),
+                       (ins.INSTR_X, 2), (ins.INSTR_MEASURE, 2, "logged")]]}
+    dqc = hardware.DQCSpec.uniform(1, num_positions=5, measure_discards=False)
+    ex = executor.DQCExecutor(ops, dqc, make("dm", 3, 1), host_branching=True).run()
+    assert [r for _, _, r in ex.logged_results] == [1, 0, 1]
+
+
+@pytest.mark.parametrize("forced", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("formalism", ["ket", "dm"])
+def test_config1_ghz5_all_forced_outcomes(formalism, forced):
+    """BASELINE config 1: GHZ-5 bisected over 2 QPUs, cat-comm, ideal hardware."""
+    ex, be, meta = rc.run_golden(make, "c1_ghz5_2qpu_bisect_cat.json", formalism, max_qubits=7,
+                                 forced=forced, num_positions=5, num_comm_qubits=2)
+    data = [tuple(meta["qubit_map"][str(i)]) for i in range(5)]
+    ghz = np.zeros(32, dtype=complex)
+    ghz[0] = ghz[31] = 2 ** -0.5
+    _cmp(rc.rdm(ex, be, data), rc.ket2dm(ghz), 1e-12)
+    assert ex.measurements == 2 and ex.ebits == 1
+
+
+def test_ket_and_dm_agree_on_ideal_circuit():
+    exk, bek, meta = rc.run_golden(make, "c2_qft5_3qpu_cat.json", "ket", max_qubits=7, num_qpus=3,
+                                   forced=[0] * 64, num_positions=10, num_comm_qubits=2)
+    exd, bed, _ = rc.run_golden(make, "c2_qft5_3qpu_cat.json", "dm", max_qubits=7, num_qpus=3,
+                                forced=[0] * 64, num_positions=10, num_comm_qubits=2)
+    data = [tuple(v) for v in meta["qubit_map"].values()]
+    _cmp(rc.rdm(exk, bek, data), rc.rdm(exd, bed, data), 1e-10)
+
+
+def test_dm_trajectory_average_matches_ket_sampling():
+    """DM formalism applies channels analytically, ket samples one branch per shot: the ket
+    ensemble average must converge to the DM result (statistical, 4000 shots)."""
+    from dqc_simulator_b200 import executor, hardware
+    from dqc_simulator_b200 import instructions as ins
+
+    def run(formalism, batch):
+        be = OracleEngine(formalism, 2, batch, seed=3)
+        qs = hardware.QPUSpec(name="node_0", num_positions=4, num_comm_qubits=0, p_depolar_error_cnot=0.2,
+                              single_qubit_gate_error_prob=0.1)
+        ex = executor.DQCExecutor({"node_0": []}, hardware.DQCSpec([qs]), be)
+        prog = executor.QuantumProgram()
+        prog.apply(ins.INSTR_INIT, [0, 1])
+        prog.apply(ins.INSTR_H, [0])
+        prog.apply(ins.INSTR_CNOT, [0, 1])
+        ex.qpus["node_0"].execute_program(prog)
+        axes = ex.axes_of([(0, "node_0"), (1, "node_0")])
+        return np.mean([be.reduced_dm(axes, s) for s in range(batch)], axis=0)
+
+    assert np.abs(run("dm", 1) - run("ket", 4000)).max() < 0.03
