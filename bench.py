@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the state-evolution hot path (BASELINE.json config 2).
+
+Workload (one "step"): a batch of noisy shots of the MQT-bench Grover-5 circuit (or QFT-5 / GHZ-5
+with --circuit) partitioned over 3 QPUs with cat-comm remote gates, density-matrix formalism,
+depolarising gate / memory noise, measurement flips and Werner-state ebits -- exactly
+``examples/run_experiment.py:80-87`` on the hardware of ``examples/setup_hardware.py`` -- run
+through the executor + C-ABI on the B200 engine: 1e5 shots x 4^7 complex128 = 26 GB of state.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--circuit grover|qft|ghz] [--shots S]
+    python bench.py --impl reference ...      # CPU oracle port on the host cores (NetSquid, the
+                                              # real reference arithmetic, cannot be installed)
+
+N > 1 (torchrun): shots are sharded over ranks (weak scaling: --shots per GPU), Philox is keyed by
+global shot id, and the only collective is one NCCL all-reduce of the fidelity sum + outcome
+histogram at the end of each step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "noisy_shots_per_s"
+UNIT = "shots/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--circuit", default="grover", choices=["grover", "qft", "ghz"])
+    ap.add_argument("--shots", type=int, default=100000, help="shots per GPU per step")
+    ap.add_argument("--cpu-shots", type=int, default=48, help="shots of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-bits", type=int, default=None)
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"c2_{a.circuit}5_3qpu_cat: MQT-bench {a.circuit}_5qubits.qasm over 3 QPUs (cat-comm), "
+                    "density matrix, depolarising gate+memory noise, measurement flips, Werner ebits "
+                    "(examples/run_experiment.py:80-87)",
+        "formalism": "dm", "max_live_qubits": 7, "shots_per_gpu": a.shots, "shots_total": a.shots * n_gpus,
+        "state_bytes_per_gpu": a.shots * (4 ** 7) * 16,
+        "noise": {"F_werner": 0.99, "p_cnot": 1e-3, "p_1q": 2e-5, "p_meas": 3e-3, "mem_rate_hz": 0.055},
+        "sharding": f"shots x{n_gpus} (Philox keyed by global shot id; one all-reduce per step)",
+        "l2_policy": "state (26 GB) >> L2 (126 MB): every pass streams from HBM, no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_shots(args_tuple):
+    """CPU oracle port: `batch` noisy shots of the workload.  Only the cpu_baseline / reference legs
+    call this (oracle/ is test infrastructure, never on the product path)."""
+    circuit, batch, seed, offset = args_tuple
+    from dqc_simulator_b200 import executor, experiment
+    from oracle.numpy_engine import OracleEngine
+
+    ops, _ = experiment.load_c2(circuit)
+    dqc = experiment.c2_hardware(noisy=True)
+    be = OracleEngine("dm", 7, batch, seed=seed, shot_offset=offset)
+    t0 = time.perf_counter()
+    ex = executor.DQCExecutor(ops, dqc, be).run()
+    axes = ex.axes_of(ex.processing_qubits())
+    rho = [be.reduced_dm(axes, s) for s in range(batch)]
+    return time.perf_counter() - t0, float(np.real(rho[0][0, 0]))
+
+
+def cpu_baseline(a):
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        ctx = None
+    oracle_shots((a.circuit, 2, 2024, 0))  # warm-up (imports, fixture parse)
+    dt, _ = oracle_shots((a.circuit, a.cpu_shots, 2024, 0))
+    if ctx is not None:
+        ctx.restore_original_limits() if hasattr(ctx, "restore_original_limits") else None
+    return {"value": a.cpu_shots / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{a.cpu_shots} shots of the same circuit+noise on the NumPy oracle (batched over shots), "
+                      f"{dt:.1f} s on one host thread"}
+
+
+def run_reference(a):
+    """--impl reference: the CPU implementation of the path on all host cores.  The reference's
+    arithmetic is inside the closed NetSquid wheel (not installable), so this
+    is the oracle port, one process per core, each advancing a batch of shots per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    per = max(2, a.cpu_shots // 4)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(i):
+            jobs = [(a.circuit, per, 2024, (i * cores + c) * per) for c in range(cores)]
+            pool.map(oracle_shots, jobs)
+        for i in range(a.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            step(a.warmup + i)
+        dt = time.perf_counter() - t0
+    shots = per * cores * a.steps
+    val = shots / dt
+    cfg = workload_config(a, a.gpus)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "complex128", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per} shots x {cores} processes per step, NumPy oracle"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from dqc_simulator_b200 import experiment
+    from dqc_simulator_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    ops, _meta = experiment.load_c2(a.circuit)
+    dqc = experiment.c2_hardware(noisy=True)
+    stream = torch.cuda.Stream(device=local)
+    with torch.cuda.stream(stream):
+        mk = lambda f, n, b: Engine(f, n, b, device=local)
+        data, ideal = experiment.ideal_output_ket(ops, mk)
+        eng = Engine("dm", 7, a.shots, seed=2024, shot_offset=rank * a.shots, device=local,
+                     stream=stream.cuda_stream, tile_bits=a.tile_bits)
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        red = torch.zeros(2 + 64, dtype=torch.float64, device=f"cuda:{local}")
+
+        def step():
+            t0 = time.perf_counter()
+            res = experiment.run_shot_batch(ops, dqc, eng, data, ideal, before_flush=lambda: ev0.record(stream),
+                                            after_launch=lambda: ev1.record(stream))
+            hist = np.bincount((res.creg & np.uint64(63)).astype(np.int64), minlength=64)
+            if world > 1:  # the one collective of the path: fidelity sum + outcome histogram
+                red[0] = float(res.fidelity.sum()); red[1] = float(len(res.fidelity))
+                red[2:] = torch.from_numpy(hist.astype(np.float64)).to(red.device)
+                dist.all_reduce(red)
+                mean_f = float(red[0] / red[1])
+            else:
+                mean_f = float(res.fidelity.mean())
+            stream.synchronize()
+            wall = time.perf_counter() - t0
+            return wall, ev0.elapsed_time(ev1), mean_f
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(a.warmup):
+            step()
+        eng.reset_stats()
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        walls, devs, fids = [], [], []
+        for _ in range(a.steps):
+            w, d, f = step()
+            walls.append(w); devs.append(d); fids.append(f)
+        barrier()
+        t_total = time.perf_counter() - t0
+        clocks = sampler.stop()
+        st = eng.stats()
+
+        # roofline of the dominant kernel (k_tile_pass), measured live: per-pass CUDA events on the
+        # launching stream inside the library, one extra step
+        eng.time_passes(True)
+        step()
+        pass_ms, n_pass, amps = eng.pass_time()
+        eng.time_passes(False)
+
+    t = torch.tensor([t_total, sum(devs) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_total, t_dev = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    achieved = 32.0 * amps / (pass_ms * 1e-3) / 1e9
+    total_shots = a.shots * world
+    d2h = a.shots * 16  # per-shot fidelity (f64) + creg word (u64)
+    line = {
+        "metric": METRIC, "value": total_shots * a.steps / t_dev, "unit": UNIT, "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": workload_config(a, world),
+        "e2e": {"value": total_shots * a.steps / t_total, "unit": UNIT, "ms_per_step": 1e3 * t_total / a.steps,
+                "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": d2h},
+        "gpu_launches": st["kernel_launches"],
+        "gate_updates_per_s": st["api_ops"] / a.steps * total_shots / (t_dev / a.steps),
+        "amp_updates_per_s": st["amp_updates"] * world / t_dev,
+        "passes_per_step": st["passes"] // a.steps, "micro_ops_per_step": st["micro_ops"] // a.steps,
+        "api_ops_per_step": st["api_ops"] // a.steps,
+        "mean_fidelity": float(np.mean(fids)),
+        "reference_printed_fidelity": {"ghz": 0.9570522876374276, "grover": 0.1071574284590638,
+                                       "qft": 0.6470482939691747}[a.circuit],
+        "roofline": {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
+                     "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "clocks": clocks,
+    }
+    if not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -475,6 +475,7 @@ int do_flush(dqe_t* h) {
     h->d_consts_cap = std::max<size_t>(h->cpool.size() * 2, 4096);
     CK(cudaMalloc(&h->d_consts, h->d_consts_cap * sizeof(double2)));
   }
+  h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + h->cpool.size() * sizeof(double2));
   if (!pl.dev_ops.empty())
     CK(cudaMemcpyAsync(h->d_ops, pl.dev_ops.data(), pl.dev_ops.size() * sizeof(MicroOp),
                        cudaMemcpyHostToDevice, h->stream));
@@ -627,6 +628,20 @@ int dqe_destroy(dqe_t* h) {
   if (h->d_consts) cudaFree(h->d_consts);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return 0;
+}
+
+int dqe_reinit(dqe_t* h) {
+  if (int rc = check_ready(h)) return rc;
+  h->queue.clear(); h->cpool.clear();
+  h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1;
+  CK(cudaSetDevice(h->device));
+  const size_t elems = (size_t)h->batch << h->P;
+  CK(cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream));
+  CK(cudaMemsetAsync(h->creg, 0, h->batch * sizeof(uint64_t), h->stream));
+  k_init_state<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(h->state, h->batch, h->P);
+  h->stats[2]++;
+  CK(cudaGetLastError());
   return 0;
 }
 

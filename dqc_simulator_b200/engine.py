@@ -29,6 +29,7 @@ ABI = {
     "dqe_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
                                   ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "dqe_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_reinit": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "dqe_version": (ctypes.c_char_p, []),
     "dqe_seed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
@@ -113,7 +114,8 @@ class Engine:
     drive either; here every method is a thin call through the C-ABI.
     """
 
-    STAT_NAMES = ("passes", "micro_ops", "kernel_launches", "amp_updates", "api_ops", "finish_launches")
+    STAT_NAMES = ("passes", "micro_ops", "kernel_launches", "amp_updates", "api_ops", "finish_launches",
+                  "h2d_bytes")
 
     def __init__(self, formalism, max_qubits, batch=1, seed=0, shot_offset=0, device=0,
                  state_tensor=None, stream=None, tile_bits=None, fuse=True):
@@ -155,6 +157,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def reinit(self):
+        """Fresh |0..0> batch on the same buffers (next batch of shots)."""
+        self._ck(self._lib.dqe_reinit(self._h))
 
     def set_option(self, key, value):
         self._ck(self._lib.dqe_set_option(self._h, key.encode(), int(value)))
@@ -329,7 +335,7 @@ class Engine:
     def stats(self):
         out = (ctypes.c_int64 * 8)()
         self._ck(self._lib.dqe_get_stats(self._h, out))
-        return dict(zip(self.STAT_NAMES, list(out)[:6]))
+        return dict(zip(self.STAT_NAMES, list(out)[:7]))
 
     def reset_stats(self):
         self._ck(self._lib.dqe_reset_stats(self._h))

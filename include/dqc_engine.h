@@ -72,6 +72,10 @@ typedef struct dqe_engine dqe_t;
 int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int device,
                void* ext_state, void* stream);
 int dqe_destroy(dqe_t* h);
+/* Back to |0..0> with no live axis, creg = 0, draw index = 0, queue dropped: start the next batch
+ * of shots on the same buffers (the reference instead rebuilds the network per shot,
+ * docs/source/getting_started.rst:683-770). */
+int dqe_reinit(dqe_t* h);
 const char* dqe_last_error(const dqe_t* h);   /* h may be NULL: error of a failed dqe_create */
 const char* dqe_version(void);
 
@@ -149,7 +153,8 @@ int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes);
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates
- * (elements read+written once per pass)  [4] queued API ops  [5] measure-finish launches. */
+ * (elements read+written once per pass)  [4] queued API ops  [5] measure-finish launches
+ * [6] bytes of micro-ops + constants copied host->device. */
 int dqe_get_stats(dqe_t* h, int64_t* out /*8*/);
 int dqe_reset_stats(dqe_t* h);
 /* When enabled, every tile pass is bracketed by CUDA events on the handle's stream;
