@@ -15,6 +15,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,7 +74,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse;
+  int tile_bits, min_run_bits, fuse, merge;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -132,9 +133,20 @@ HostOp blank(dqe_t* h, int type) {
   o.live_after = phys_live(h, h->live_axes);
   return o;
 }
+bool try_merge(dqe_t* h, const HostOp& o, int axis);
 void push(dqe_t* h, HostOp& o) {
+  // axis-local candidates: ket MAT1 / 1-bit DIAG, dm MAT2 / PAULI1 / 2-bit DIAG on (row, col) of one axis
+  int axis = -1;
+  if (o.kind == 0 && !o.pctrl && !o.pctrl2) {
+    if (h->formalism == DQE_KET) {
+      if ((o.m.type == OP_MAT1 || o.m.type == OP_DIAG) && o.m.nb == 1) axis = o.m.b[0];
+    } else if ((o.m.type == OP_MAT2 || o.m.type == OP_PAULI1 || o.m.type == OP_DIAG) && o.m.nb == 2 &&
+               o.m.b[0] == o.m.b[1] + h->nmax) {
+      axis = o.m.b[1];
+    }
+  }
+  if (axis >= 0 && try_merge(h, o, axis)) return;
   h->queue.push_back(o);
-  h->stats[4] += 0;
 }
 
 // -------- lowering helpers (physical bits) --------------------------------------------------
@@ -180,6 +192,124 @@ void q_pauli1(dqe_t* h, int axis, double pI, double pX, double pY, double pZ) {
 
 bool is_zero(cplx z) { return z.real() == 0.0 && z.imag() == 0.0; }
 bool is_one(cplx z) { return z.real() == 1.0 && z.imag() == 0.0; }
+
+
+// -------- peephole: compose ops local to one axis ---------------------------------------------
+// dm: a 1q gate, Kraus/Pauli/depolarising channel or 1q diagonal is a 4x4 superoperator on the
+// (row, col) bits of its axis; ket: a 2x2 matrix on the axis bit.  A new axis-local op is folded
+// into the latest queued axis-local op of the same axis and predicate when everything queued in
+// between commutes with it (touches none of the axis' bits): memory noise -> gate -> gate noise
+// becomes ONE micro-op instead of three.
+uint64_t touched_bits(const HostOp& o) {
+  uint64_t t = o.need | o.pctrl | o.pctrl2;
+  if (o.m.type == OP_DIAG) for (uint32_t i = 0; i < o.m.nb; ++i) t |= 1ull << o.m.b[i];
+  return t;
+}
+
+// 4x4 (dm) / 2x2 (ket) matrix of a queued axis-local op, or false
+bool axis_local_matrix(const dqe_t* h, const HostOp& o, int axis, cplx* M) {
+  const int d = h->formalism == DQE_KET ? 2 : 4;
+  for (int i = 0; i < d * d; ++i) M[i] = 0.0;
+  if (o.kind != 0 || o.pctrl || o.pctrl2) return false;
+  if (h->formalism == DQE_KET) {
+    if (o.m.type == OP_MAT1 && o.m.b[0] == axis) {
+      for (int i = 0; i < 4; ++i) M[i] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+      return true;
+    }
+    if (o.m.type == OP_DIAG && o.m.nb == 1 && o.m.b[0] == axis) {
+      M[0] = cplx(h->cpool[o.m.c_off].x, h->cpool[o.m.c_off].y);
+      M[3] = cplx(h->cpool[o.m.c_off + 1].x, h->cpool[o.m.c_off + 1].y);
+      return true;
+    }
+    return false;
+  }
+  const int rb = axis + h->nmax;
+  if (o.m.type == OP_MAT2 && o.m.b[0] == rb && o.m.b[1] == axis) {
+    for (int i = 0; i < 16; ++i) M[i] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+    return true;
+  }
+  if (o.m.type == OP_PAULI1 && o.m.b[0] == rb && o.m.b[1] == axis) {
+    const double a = o.m.p[0], b = o.m.p[1], c = o.m.p[2], dd = o.m.p[3];
+    M[0] = a; M[3] = b; M[5] = c; M[6] = dd; M[9] = dd; M[10] = c; M[12] = b; M[15] = a;
+    return true;
+  }
+  if (o.m.type == OP_DIAG && o.m.nb == 2 && o.m.b[0] == rb && o.m.b[1] == axis) {
+    for (int i = 0; i < 4; ++i) M[i * 5] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+    return true;
+  }
+  return false;
+}
+
+// rewrite op `o` (kept in place) as the cheapest micro-op that applies matrix M on `axis`
+void set_axis_local(dqe_t* h, HostOp& o, int axis, const cplx* M) {
+  const int pred = o.m.pred_bit;
+  const uint64_t live_after = o.live_after;
+  memset(&o.m, 0, sizeof(o.m));
+  o.pctrl = o.pctrl2 = 0;
+  o.m.pred_bit = pred;
+  o.live_after = live_after;
+  if (h->formalism == DQE_KET) {
+    if (is_zero(M[1]) && is_zero(M[2])) {
+      const cplx d[2] = {M[0], M[3]};
+      o.m.type = OP_DIAG; o.m.nb = 1; o.m.b[0] = (uint8_t)axis; o.need = 0;
+      o.m.c_off = add_consts(h, d, 2); o.nconst = 2;
+    } else {
+      o.m.type = OP_MAT1; o.m.nb = 1; o.m.b[0] = (uint8_t)axis; o.need = 1ull << axis;
+      o.m.c_off = add_consts(h, M, 4); o.nconst = 4;
+    }
+    return;
+  }
+  const int rb = axis + h->nmax;
+  o.m.b[0] = (uint8_t)rb; o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
+  bool diag = true, pauli = true;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const cplx v = M[i * 4 + j];
+      if (i != j && !is_zero(v)) diag = false;
+      const bool in_pat = (i == j) || (i + j == 3);
+      if (!in_pat && !is_zero(v)) pauli = false;
+      if (in_pat && v.imag() != 0.0) pauli = false;
+    }
+  if (pauli) pauli = M[0] == M[15] && M[3] == M[12] && M[5] == M[10] && M[6] == M[9];
+  if (diag) {
+    const cplx d[4] = {M[0], M[5], M[10], M[15]};
+    o.m.type = OP_DIAG; o.need = 0;
+    o.m.c_off = add_consts(h, d, 4); o.nconst = 4;
+  } else if (pauli) {
+    o.m.type = OP_PAULI1; o.need = (1ull << rb) | (1ull << axis);
+    o.m.p[0] = M[0].real(); o.m.p[1] = M[3].real(); o.m.p[2] = M[5].real(); o.m.p[3] = M[6].real();
+  } else {
+    o.m.type = OP_MAT2; o.need = (1ull << rb) | (1ull << axis);
+    o.m.c_off = add_consts(h, M, 16); o.nconst = 16;
+  }
+}
+
+// try to fold the axis-local op `o` (about to be queued) into an earlier one; true = absorbed
+bool try_merge(dqe_t* h, const HostOp& o, int axis) {
+  if (!h->merge) return false;
+  const int d = h->formalism == DQE_KET ? 2 : 4;
+  cplx Mn[16], Mo[16], R[16];
+  if (!axis_local_matrix(h, o, axis, Mn)) return false;
+  const uint64_t mine = h->formalism == DQE_KET ? (1ull << axis) : ((1ull << axis) | (1ull << (axis + h->nmax)));
+  int depth = 0;
+  for (size_t k = h->queue.size(); k-- > 0 && depth < 96; ++depth) {
+    HostOp& e = h->queue[k];
+    if (e.kind != 0 || e.m.type == OP_PROBS) return false;
+    if (e.m.pred_bit == o.m.pred_bit && axis_local_matrix(h, e, axis, Mo)) {
+      for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+          cplx acc = 0.0;
+          for (int l = 0; l < d; ++l) acc += Mn[i * d + l] * Mo[l * d + j];
+          R[i * d + j] = acc;
+        }
+      set_axis_local(h, e, axis, R);
+      h->stats[7]++;
+      return true;
+    }
+    if (touched_bits(e) & mine) return false;
+  }
+  return false;
+}
 
 // ket-or-dm diagonal gate on k axes (first = MSB); dm table = d[r] conj(d[c]) over (rows, cols)
 int lower_diag(dqe_t* h, int k, const int* axes, const cplx* d) {
@@ -463,6 +593,32 @@ int do_flush(dqe_t* h) {
     h->queue.clear(); h->cpool.clear();
     return fail(h, DQE_EINVAL, pl.err);
   }
+  if (getenv("DQE_DUMP_PLAN")) {
+    static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
+                                  "INJECT", "PSAMPLED", "MAT1X2"};
+    for (PlannedPass& P : pl.passes) {
+      if (P.is_finish) { fprintf(stderr, "  finish\n"); continue; }
+      fprintf(stderr, "pass t=%d outer=%d nops=%d:", P.pp.t, P.pp.outer_bits, P.pp.nops);
+      for (int i = 0; i < P.pp.nops; ++i) {
+        const MicroOp& m = pl.dev_ops[P.op_begin + i];
+        fprintf(stderr, " %s%s(", names[m.type], m.pred_bit >= 0 ? "?" : "");
+        for (uint32_t b = 0; b < m.nb; ++b) fprintf(stderr, "%s%d", b ? "," : "", (int)m.b[b]);
+        fprintf(stderr, ")");
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  if (h->device < 0) {  // plan-only: account and drop
+    for (PlannedPass& P : pl.passes) {
+      if (P.is_finish) { h->stats[2]++; h->stats[5]++; continue; }
+      h->stats[0]++; h->stats[2]++; h->stats[1] += P.pp.nops;
+      h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
+    }
+    h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + h->cpool.size() * sizeof(double2));
+    h->queue.clear(); h->cpool.clear();
+    h->planned_live = phys_live(h, h->live_axes);
+    return 0;
+  }
   CK(cudaSetDevice(h->device));
   // upload micro-ops + constants
   if (pl.dev_ops.size() > h->d_ops_cap) {
@@ -575,9 +731,14 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->timing = false;
+  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
+  if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
+    h->stream = nullptr;
+    *out = h;
+    return 0;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) {
     std::string msg = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
@@ -617,6 +778,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
 
 int dqe_destroy(dqe_t* h) {
   if (!h) return 0;
+  if (h->device < 0) { delete h; return 0; }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -635,6 +797,7 @@ int dqe_reinit(dqe_t* h) {
   if (int rc = check_ready(h)) return rc;
   h->queue.clear(); h->cpool.clear();
   h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1;
+  if (h->device < 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t elems = (size_t)h->batch << h->P;
   CK(cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream));
@@ -899,8 +1062,11 @@ int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, doubl
 
 int dqe_flush(dqe_t* h) { return do_flush(h); }
 
+#define NEED_DEVICE(h) do { if ((h) && (h)->device < 0) return fail((h), DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state"); } while (0)
+
 int dqe_sync(dqe_t* h) {
   if (int rc = do_flush(h)) return rc;
+  if (h->device < 0) return 0;
   CK(cudaStreamSynchronize(h->stream));
   if (h->timing) return collect_timing(h);
   return 0;
@@ -908,6 +1074,7 @@ int dqe_sync(dqe_t* h) {
 
 int dqe_read_creg(dqe_t* h, int bit, int8_t* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (bit < 0 || bit >= 64 || !out) return fail(h, DQE_EINVAL, "read_creg: bad argument");
   int8_t* d = nullptr;
   CK(cudaMalloc(&d, h->batch));
@@ -921,6 +1088,7 @@ int dqe_read_creg(dqe_t* h, int bit, int8_t* out) {
 
 int dqe_read_creg_words(dqe_t* h, uint64_t* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (!out) return fail(h, DQE_EINVAL, "read_creg_words: null");
   CK(cudaMemcpyAsync(out, h->creg, h->batch * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -929,6 +1097,7 @@ int dqe_read_creg_words(dqe_t* h, uint64_t* out) {
 
 int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (k < 1 || k > 20 || !cbits || !out) return fail(h, DQE_EINVAL, "histogram: 1 <= k <= 20");
   HistParams hp;
   memset(&hp, 0, sizeof(hp));
@@ -950,6 +1119,7 @@ int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out) {
 
 int dqe_reduced_dm(dqe_t* h, int k, const int* axes, int64_t shot, double* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (shot < 0 || shot >= h->batch || !out) return fail(h, DQE_EINVAL, "reduced_dm: bad shot");
   ReadoutParams rp;
   if (int rc = build_readout(h, k, axes, &rp)) return rc;
@@ -965,6 +1135,7 @@ int dqe_reduced_dm(dqe_t* h, int k, const int* axes, int64_t shot, double* out) 
 
 int dqe_fidelity_ket(dqe_t* h, int k, const int* axes, const double* ket, double* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (!ket || !out) return fail(h, DQE_EINVAL, "fidelity_ket: null");
   ReadoutParams rp;
   if (int rc = build_readout(h, k, axes, &rp)) return rc;
@@ -985,6 +1156,7 @@ int dqe_fidelity_ket(dqe_t* h, int k, const int* axes, const double* ket, double
 
 int dqe_get_state(dqe_t* h, int64_t shot, double* out) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (shot < 0 || shot >= h->batch || !out) return fail(h, DQE_EINVAL, "get_state: bad shot");
   const size_t n = (size_t)1 << h->P;
   CK(cudaMemcpyAsync(out, h->state + (size_t)shot * n, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
@@ -994,6 +1166,7 @@ int dqe_get_state(dqe_t* h, int64_t shot, double* out) {
 
 int dqe_set_state(dqe_t* h, int64_t shot, const double* in, uint64_t live_mask) {
   if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
   if (shot < 0 || shot >= h->batch || !in) return fail(h, DQE_EINVAL, "set_state: bad shot");
   if (h->nmax < 64 && (live_mask >> h->nmax)) return fail(h, DQE_EINVAL, "set_state: live mask out of range");
   const size_t n = (size_t)1 << h->P;
@@ -1022,6 +1195,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->min_run_bits = (int)value;
   } else if (!strcmp(key, "fuse")) {
     h->fuse = value ? 1 : 0;
+  } else if (!strcmp(key, "merge")) {
+    h->merge = value ? 1 : 0;
   } else return fail(h, DQE_EINVAL, std::string("unknown option ") + key);
   return 0;
 }
@@ -1039,6 +1214,7 @@ int dqe_reset_stats(dqe_t* h) {
 
 int dqe_time_passes(dqe_t* h, int enable) {
   if (int rc = dqe_sync(h)) return rc;
+  NEED_DEVICE(h);
   h->timing = enable != 0;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   return 0;

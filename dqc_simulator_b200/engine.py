@@ -115,7 +115,7 @@ class Engine:
     """
 
     STAT_NAMES = ("passes", "micro_ops", "kernel_launches", "amp_updates", "api_ops", "finish_launches",
-                  "h2d_bytes")
+                  "h2d_bytes", "merged_ops")
 
     def __init__(self, formalism, max_qubits, batch=1, seed=0, shot_offset=0, device=0,
                  state_tensor=None, stream=None, tile_bits=None, fuse=True):
@@ -335,7 +335,7 @@ class Engine:
     def stats(self):
         out = (ctypes.c_int64 * 8)()
         self._ck(self._lib.dqe_get_stats(self._h, out))
-        return dict(zip(self.STAT_NAMES, list(out)[:7]))
+        return dict(zip(self.STAT_NAMES, list(out)[:8]))
 
     def reset_stats(self):
         self._ck(self._lib.dqe_reset_stats(self._h))

@@ -68,7 +68,10 @@ typedef struct dqe_engine dqe_t;
  * allocates batch * 2^max_qubits (ket) or batch * 4^max_qubits (dm) complex128) or a device
  * pointer to a caller-owned buffer of that size (e.g. a torch tensor's data_ptr()).
  * `stream` is a cudaStream_t cast to void* (NULL = a new non-blocking stream owned by the
- * handle).  State starts as |0..0> with no live axis. */
+ * handle).  State starts as |0..0> with no live axis.
+ * device < 0 creates a PLAN-ONLY handle: no CUDA call is made, enqueue / flush run the queue,
+ * peephole and pass planner and update the statistics, every read fails with DQE_EUNSUPPORTED
+ * (used to test the planner on a machine without a GPU; it computes nothing). */
 int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int device,
                void* ext_state, void* stream);
 int dqe_destroy(dqe_t* h);
@@ -154,7 +157,7 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates
  * (elements read+written once per pass)  [4] queued API ops  [5] measure-finish launches
- * [6] bytes of micro-ops + constants copied host->device. */
+ * [6] bytes of micro-ops + constants copied host->device  [7] ops folded by the peephole. */
 int dqe_get_stats(dqe_t* h, int64_t* out /*8*/);
 int dqe_reset_stats(dqe_t* h);
 /* When enabled, every tile pass is bracketed by CUDA events on the handle's stream;
