@@ -28,10 +28,26 @@ enum OpType : int32_t {
   OP_INJECT = 9,      // write a 2-qubit state onto two fresh axes
   OP_PAULI_SAMPLED = 10,  // ket: apply a Pauli string drawn per shot from Philox
   OP_MAT1X2 = 11,     // dm controlled/one-qubit gate, row side + column side in one sweep
+  // dm group sweep: every thread holds the 16 elements (ra, rb, ca, cb) of one qubit PAIR (A, B) in
+  // registers and runs the following `aux` sub-ops on them -- one shared-memory round trip for a
+  // whole run of gates / channels on those two qubits.
+  OP_GROUP = 12,
+  G_PAULI1 = 101,     // flags bit0 = role of the target axis (0 = A, 1 = B)
+  G_MAT2 = 102,       // 4x4 superoperator on (row, col) of one axis
+  G_MAT1X2 = 103,     // U on the row side / conj(U) on the column side; flags bit1/bit2: row/col control
+                      // is the OTHER axis of the group (else octrl/octrl2 on the tile base)
+  G_DEPOL2 = 104,
+  G_MAT2ROWS = 105,   // dense 4x4 on (ra, rb), A = MSB
+  G_MAT2COLS = 106,   // dense 4x4 on (ca, cb)
+  G_COLLAPSE = 107,
+  G_TRACE = 108,
+  G_INJECT = 109,
+  G_DIAG = 110,       // p[0..1] hold a 16-byte table-index LUT (one byte per element)
 };
 
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
+constexpr int kMaxConstsPerPass = 512;   // double2 entries staged in shared memory per pass (8 KiB)
 constexpr int kThreads = 256;
 
 struct __align__(16) MicroOp {
@@ -69,7 +85,8 @@ struct PassParams {
   uint64_t seed, shot_offset;
   int32_t nops, t, P, nmax;
   int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
-  int32_t store_back, pad0;
+  int32_t store_back, nconsts;
+  int32_t use_tma, pad1;
   Seg tile_segs[16];
   Seg outer_segs[24];
 };
@@ -146,7 +163,7 @@ __device__ __forceinline__ void apply_mat1(double2* tile, uint32_t T, int j, uin
 }
 
 __device__ __forceinline__ void op_mat1(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
-  apply_mat1(tile, T, op.b[0], op.lctrl, __ldg(cs + 0), __ldg(cs + 1), __ldg(cs + 2), __ldg(cs + 3));
+  apply_mat1(tile, T, op.b[0], op.lctrl, cs[0], cs[1], cs[2], cs[3]);
 }
 
 // dm: U on the row bit (control mask lctrl) then conj(U) on the column bit (control lctrl2),
@@ -155,7 +172,7 @@ __device__ __forceinline__ void op_mat1x2(double2* tile, uint32_t T, const Micro
                                           bool row_on, bool col_on) {
   const int jr = op.b[0], jc = op.b[1];
   const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
-  const double2 m00 = __ldg(cs + 0), m01 = __ldg(cs + 1), m10 = __ldg(cs + 2), m11 = __ldg(cs + 3);
+  const double2 m00 = cs[0], m01 = cs[1], m10 = cs[2], m11 = cs[3];
   const double2 n00 = conj2(m00), n01 = conj2(m01), n10 = conj2(m10), n11 = conj2(m11);
   const uint32_t lr = op.lctrl, lc = op.lctrl2;
   for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
@@ -185,9 +202,7 @@ __device__ __forceinline__ void op_mat2(double2* tile, uint32_t T, const MicroOp
   const int jh = op.b[0], jl = op.b[1];
   const int jlo = jh < jl ? jh : jl, jhi = jh < jl ? jl : jh;
   const uint32_t lc = op.lctrl;
-  double2 m[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) m[i] = __ldg(cs + i);
+  const double2* __restrict__ m = cs;
   for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
     const uint32_t i0 = ins0(ins0(p, jlo), jhi);
     if ((i0 & lc) != lc) continue;
@@ -211,14 +226,14 @@ __device__ __forceinline__ void op_diag(double2* tile, uint32_t T, const MicroOp
     else { lb[nl] = op.b[s]; ls[nl] = sh; ++nl; }
   }
   if (nl == 0) {
-    const double2 d = __ldg(cs + fixed);
+    const double2 d = cs[fixed];
     for (uint32_t i = threadIdx.x; i < T; i += kThreads) tile[i] = cmul(tile[i], d);
     return;
   }
   for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
     uint32_t idx = fixed;
     for (int s = 0; s < nl; ++s) idx |= ((i >> lb[s]) & 1u) << ls[s];
-    tile[i] = cmul(tile[i], __ldg(cs + idx));
+    tile[i] = cmul(tile[i], cs[idx]);
   }
 }
 
@@ -369,8 +384,8 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
       shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
       choice = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
     }
-    const double2 k0 = __ldg(cs + 4 * choice), k1 = __ldg(cs + 4 * choice + 1),
-                  k2 = __ldg(cs + 4 * choice + 2), k3 = __ldg(cs + 4 * choice + 3);
+    const double2 k0 = cs[4 * choice], k1 = cs[4 * choice + 1],
+                  k2 = cs[4 * choice + 2], k3 = cs[4 * choice + 3];
     for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
       const uint32_t i0 = ins0(ins0(p, jlo), jhi);
       const double2 x = tile[i0];
@@ -392,7 +407,7 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t idx = i0 | ro | ((c & 2) ? mca : 0u) | ((c & 1) ? mcb : 0u);
-          tile[idx] = cmul(x, __ldg(cs + 4 * r + c));
+          tile[idx] = cmul(x, cs[4 * r + c]);
         }
       }
     }
@@ -434,11 +449,217 @@ __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, cons
   }
 }
 
+
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_tile_pass(const __grid_constant__ PassParams pp) {
+// dm group sweep.  Register file layout: v[e], e = ra*8 + rb*4 + ca*2 + cb  (A = first axis).
+template <int ROLE>
+__device__ __forceinline__ constexpr int EI(int r, int c, int ro, int co) {
+  return ROLE == 0 ? (r * 8 + ro * 4 + c * 2 + co) : (ro * 8 + r * 4 + co * 2 + c);
+}
+
+template <int ROLE>
+__device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
+  const double a = op.p[0], b = op.p[1], c = op.p[2], d = op.p[3];
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      const double2 e00 = v[EI<ROLE>(0, 0, ro, co)], e01 = v[EI<ROLE>(0, 1, ro, co)];
+      const double2 e10 = v[EI<ROLE>(1, 0, ro, co)], e11 = v[EI<ROLE>(1, 1, ro, co)];
+      v[EI<ROLE>(0, 0, ro, co)] = make_double2(fma(a, e00.x, b * e11.x), fma(a, e00.y, b * e11.y));
+      v[EI<ROLE>(1, 1, ro, co)] = make_double2(fma(a, e11.x, b * e00.x), fma(a, e11.y, b * e00.y));
+      v[EI<ROLE>(0, 1, ro, co)] = make_double2(fma(c, e01.x, d * e10.x), fma(c, e01.y, d * e10.y));
+      v[EI<ROLE>(1, 0, ro, co)] = make_double2(fma(c, e10.x, d * e01.x), fma(c, e10.y, d * e01.y));
+    }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void g_mat2(double2 (&v)[16], const double2* __restrict__ cs) {
+  // matrix entries are re-read from shared memory (broadcast) per use: keeping 16 complex
+  // coefficients live next to the 16 data elements would cost 64 more registers per thread
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      const double2 x0 = v[EI<ROLE>(0, 0, ro, co)], x1 = v[EI<ROLE>(0, 1, ro, co)];
+      const double2 x2 = v[EI<ROLE>(1, 0, ro, co)], x3 = v[EI<ROLE>(1, 1, ro, co)];
+      v[EI<ROLE>(0, 0, ro, co)] = cfma(cs[3], x3, cfma(cs[2], x2, cfma(cs[1], x1, cmul(cs[0], x0))));
+      v[EI<ROLE>(0, 1, ro, co)] = cfma(cs[7], x3, cfma(cs[6], x2, cfma(cs[5], x1, cmul(cs[4], x0))));
+      v[EI<ROLE>(1, 0, ro, co)] = cfma(cs[11], x3, cfma(cs[10], x2, cfma(cs[9], x1, cmul(cs[8], x0))));
+      v[EI<ROLE>(1, 1, ro, co)] = cfma(cs[15], x3, cfma(cs[14], x2, cfma(cs[13], x1, cmul(cs[12], x0))));
+    }
+}
+
+// target axis = ROLE; the control (if any) is either the other axis of the group (in_r / in_c)
+// or outside the tile (r_on / c_on already evaluated on the tile base)
+template <int ROLE>
+__device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __restrict__ cs, bool r_on, bool c_on,
+                                         bool in_r, bool in_c) {
+  const double2 m00 = cs[0], m01 = cs[1], m10 = cs[2], m11 = cs[3];
+  if (r_on) {
+#pragma unroll
+    for (int ro = 0; ro < 2; ++ro) {
+      if (in_r && ro == 0) continue;
+#pragma unroll
+      for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const double2 a = v[EI<ROLE>(0, c, ro, co)], b = v[EI<ROLE>(1, c, ro, co)];
+          v[EI<ROLE>(0, c, ro, co)] = cfma(m01, b, cmul(m00, a));
+          v[EI<ROLE>(1, c, ro, co)] = cfma(m11, b, cmul(m10, a));
+        }
+    }
+  }
+  if (c_on) {
+    const double2 n00 = conj2(m00), n01 = conj2(m01), n10 = conj2(m10), n11 = conj2(m11);
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      if (in_c && co == 0) continue;
+#pragma unroll
+      for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double2 a = v[EI<ROLE>(r, 0, ro, co)], b = v[EI<ROLE>(r, 1, ro, co)];
+          v[EI<ROLE>(r, 0, ro, co)] = cfma(n01, b, cmul(n00, a));
+          v[EI<ROLE>(r, 1, ro, co)] = cfma(n11, b, cmul(n10, a));
+        }
+    }
+  }
+}
+
+__device__ __forceinline__ void g_depol2(double2 (&v)[16], double pp) {
+  const double keep = 1.0 - pp, mix = 0.25 * pp;
+  const double sx = mix * (v[0].x + v[5].x + v[10].x + v[15].x);
+  const double sy = mix * (v[0].y + v[5].y + v[10].y + v[15].y);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    v[e].x *= keep; v[e].y *= keep;
+    if ((e >> 2) == (e & 3)) { v[e].x += sx; v[e].y += sy; }
+  }
+}
+
+// V[R][C], R = (ra, rb), C = (ca, cb): rows side V <- M V ; cols side V[R][C] <- sum_C' mc[C][C'] V[R][C']
+template <bool ROWS>
+__device__ __forceinline__ void g_mat2side(double2 (&v)[16], const double2* __restrict__ m) {
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    double2 x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = ROWS ? v[j * 4 + f] : v[f * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 y = cfma(m[i * 4 + 3], x[3], cfma(m[i * 4 + 2], x[2], cfma(m[i * 4 + 1], x[1], cmul(m[i * 4], x[0]))));
+      if (ROWS) v[i * 4 + f] = y; else v[f * 4 + i] = y;
+    }
+  }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void g_collapse(double2 (&v)[16], int m, double sc, double e, bool discard) {
+  const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      const double2 e00 = v[EI<ROLE>(0, 0, ro, co)], e11 = v[EI<ROLE>(1, 1, ro, co)];
+      const double2 same = m ? e11 : e00, flip = m ? e00 : e11;
+      double2 kept;
+      kept.x = ((1.0 - e) * same.x + e * flip.x) * sc;
+      kept.y = ((1.0 - e) * same.y + e * flip.y) * sc;
+      const bool to0 = discard || m == 0;
+      v[EI<ROLE>(0, 0, ro, co)] = to0 ? kept : zero;
+      v[EI<ROLE>(1, 1, ro, co)] = to0 ? zero : kept;
+      v[EI<ROLE>(0, 1, ro, co)] = zero;
+      v[EI<ROLE>(1, 0, ro, co)] = zero;
+    }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void g_trace(double2 (&v)[16]) {
+  const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      v[EI<ROLE>(0, 0, ro, co)] = cadd(v[EI<ROLE>(0, 0, ro, co)], v[EI<ROLE>(1, 1, ro, co)]);
+      v[EI<ROLE>(0, 1, ro, co)] = zero; v[EI<ROLE>(1, 0, ro, co)] = zero; v[EI<ROLE>(1, 1, ro, co)] = zero;
+    }
+}
+
+__device__ __forceinline__ void run_group(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
+                                          const PassParams& pp, const double2* cs_base, uint64_t base,
+                                          uint64_t cw, uint64_t shot) {
+  int s4[4];
+  sort4(g.b, s4);
+  const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
+  const int nsub = g.aux;
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += kThreads) {
+    const uint32_t i0 = ins0_4(q, s4);
+    double2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      v[e] = tile[i0 | ((e & 8) ? mra : 0u) | ((e & 4) ? mrb : 0u) | ((e & 2) ? mca : 0u) | ((e & 1) ? mcb : 0u)];
+    for (int s = 0; s < nsub; ++s) {
+      const MicroOp& op = sub[s];
+      if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
+      const double2* cs = cs_base + op.c_off;
+      const int role = op.flags & 1;
+      switch (op.type) {
+        case G_PAULI1:
+          if (role) g_pauli1<1>(v, op); else g_pauli1<0>(v, op);
+          break;
+        case G_MAT2:
+          if (role) g_mat2<1>(v, cs); else g_mat2<0>(v, cs);
+          break;
+        case G_MAT1X2: {
+          const bool in_r = op.flags & 2, in_c = op.flags & 4;
+          const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
+          if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c); else g_mat1x2<0>(v, cs, r_on, c_on, in_r, in_c);
+          break;
+        }
+        case G_DEPOL2: g_depol2(v, op.p[0]); break;
+        case G_MAT2ROWS: g_mat2side<true>(v, cs); break;
+        case G_MAT2COLS: g_mat2side<false>(v, cs); break;
+        case G_COLLAPSE: {
+          const MeasRec r = pp.rec[shot];
+          if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
+          else g_collapse<0>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
+          break;
+        }
+        case G_TRACE:
+          if (role) g_trace<1>(v); else g_trace<0>(v);
+          break;
+        case G_INJECT: {
+          const double2 x = v[0];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = cmul(x, cs[e]);
+          break;
+        }
+        case G_DIAG: {
+          const uint8_t* lut = reinterpret_cast<const uint8_t*>(&op.p[0]);
+          uint32_t fixed = 0;
+          for (uint32_t i = 0; i < op.nb; ++i)
+            if (op.b[i] >= kOuter) fixed |= (uint32_t)((base >> (op.b[i] - kOuter)) & 1ull) << (op.nb - 1 - i);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], cs[lut[e] | fixed]);
+          break;
+        }
+        default: break;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      tile[i0 | ((e & 8) ? mra : 0u) | ((e & 4) ? mrb : 0u) | ((e & 2) ? mca : 0u) | ((e & 1) ? mcb : 0u)] = v[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ double2 tile[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
+  __shared__ double2 s_consts[kMaxConstsPerPass];
   __shared__ double s_red[2 * (kThreads / 32)];
+  __shared__ __align__(8) unsigned long long s_bar;
 
   const uint64_t blk = blockIdx.x;
   const uint64_t shot = blk >> pp.outer_bits;
@@ -452,10 +673,39 @@ __global__ void __launch_bounds__(kThreads) k_tile_pass(const __grid_constant__ 
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.ops);
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
     for (int i = threadIdx.x; i < nw; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < pp.nconsts; i += kThreads) s_consts[i] = __ldg(pp.consts + i);
   }
-  // tile load: local index i -> physical offset; the low segment is contiguous in HBM
-  const int c0 = pp.tile_segs[0].len;  // tile_segs[0] always maps local bits [0,c0) to physical [0,c0)... or dst>0
-  if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+  // tile load.  The low segment of the tile (local bits [0, c0) = physical bits [0, c0)) is a
+  // contiguous run of 2^c0 amplitudes in HBM: the tile is 2^(t-c0) such runs, fetched with TMA bulk
+  // copies (cp.async.bulk, completion on an mbarrier) issued by warp 0 -- no registers, no LSU
+  // instructions, all 64 KiB in flight at once.  Fallback: per-thread 16-byte loads.
+  const int c0 = pp.tile_segs[0].len;
+  const bool tma = pp.use_tma && pp.tile_segs[0].dst == 0 && c0 >= 3;
+  const uint32_t run_bytes = 16u << c0;
+  const uint32_t nruns = T >> c0;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  if (tma) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
+      __syncwarp();
+      const int nhs = pp.n_tile_segs - 1;
+      for (uint32_t r = threadIdx.x; r < nruns; r += 32) {
+        const uint64_t off = deposit((uint64_t)r << c0, pp.tile_segs + 1, nhs);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                tile_s + r * run_bytes),
+            "l"(sp + off), "r"(run_bytes), "r"(bar_s)
+            : "memory");
+      }
+    }
+  } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
     const int nhs = pp.n_tile_segs - 1;
 #pragma unroll 4
     for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
@@ -468,13 +718,29 @@ __global__ void __launch_bounds__(kThreads) k_tile_pass(const __grid_constant__ 
       tile[i] = sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)];
   }
   const uint64_t cw = pp.creg[shot];
+  if (tma) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar_s), "r"(0u)
+          : "memory");
+    }
+  }
   __syncthreads();
 
   for (int o = 0; o < pp.nops; ++o) {
     const MicroOp& op = s_ops[o];
     if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
-    const double2* cs = pp.consts + op.c_off;
+    const double2* cs = s_consts + op.c_off;
     switch (op.type) {
+      case OP_GROUP:
+        run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
+        o += op.aux;
+        break;
       case OP_MAT1:
         if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
         break;
@@ -500,7 +766,22 @@ __global__ void __launch_bounds__(kThreads) k_tile_pass(const __grid_constant__ 
   }
 
   if (pp.store_back) {
-    if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+    if (tma) {
+      // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int nhs = pp.n_tile_segs - 1;
+        for (uint32_t r = threadIdx.x; r < nruns; r += 32) {
+          const uint64_t off = deposit((uint64_t)r << c0, pp.tile_segs + 1, nhs);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(sp + off),
+                       "r"(tile_s + r * run_bytes), "r"(run_bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
       const int nhs = pp.n_tile_segs - 1;
 #pragma unroll 4
       for (uint32_t i = threadIdx.x; i < T; i += kThreads) {

@@ -41,6 +41,7 @@ struct HostOp {
 struct PlannedPass {
   PassParams pp;
   size_t op_begin;     // offset into the device op array
+  size_t const_begin;  // offset of this pass's constants in the device constant array
   uint64_t grid;
   size_t smem;
   uint64_t amps;       // amplitudes touched per shot
@@ -74,7 +75,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge;
+  int tile_bits, min_run_bits, fuse, merge, group, tma;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -479,7 +480,160 @@ struct Planner {
   dqe_t* h;
   std::vector<PlannedPass> passes;
   std::vector<MicroOp> dev_ops;
+  std::vector<double2> dev_consts;
   std::string err;
+
+  // ---- helpers ------------------------------------------------------------------------------
+  int copy_consts(const HostOp* ho, size_t pass_const_begin, const int* perm4 = nullptr) {
+    const int off = (int)(dev_consts.size() - pass_const_begin);
+    if (perm4) {  // 4x4 table re-indexed for swapped qubit order
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) dev_consts.push_back(h->cpool[ho->m.c_off + perm4[i] * 4 + perm4[j]]);
+    } else {
+      for (int i = 0; i < ho->nconst; ++i) dev_consts.push_back(h->cpool[ho->m.c_off + i]);
+    }
+    return off;
+  }
+
+  // localise one host op as a stand-alone micro-op of the pass
+  MicroOp localise(const HostOp* ho, uint64_t tile, size_t pass_const_begin) {
+    MicroOp m = ho->m;
+    if (m.type == OP_DIAG) {
+      for (uint32_t i = 0; i < m.nb; ++i) {
+        const int ph = ho->m.b[i];
+        m.b[i] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
+      }
+    } else if (m.type != OP_PROBS) {
+      for (uint32_t i = 0; i < m.nb; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
+    }
+    m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
+    for (int b = 0; b < 64; ++b) {
+      if ((ho->pctrl >> b) & 1ull) {
+        if ((tile >> b) & 1ull) m.lctrl |= 1u << local_of(tile, b); else m.octrl |= 1ull << b;
+      }
+      if ((ho->pctrl2 >> b) & 1ull) {
+        if ((tile >> b) & 1ull) m.lctrl2 |= 1u << local_of(tile, b); else m.octrl2 |= 1ull << b;
+      }
+    }
+    m.c_off = ho->nconst ? copy_consts(ho, pass_const_begin) : 0;
+    return m;
+  }
+
+  // dm: axes whose (row, col) bits an op mixes or uses as in-tile controls; false = not groupable
+  bool group_axes(const HostOp* ho, uint64_t tile, int* ax, int* nax) {
+    const int n = h->nmax;
+    *nax = 0;
+    auto both_in_tile = [&](int a) { return ((tile >> a) & 1ull) && ((tile >> (a + n)) & 1ull); };
+    auto add = [&](int a) {
+      for (int i = 0; i < *nax; ++i) if (ax[i] == a) return true;
+      if (*nax >= 2 || !both_in_tile(a)) return false;
+      ax[(*nax)++] = a;
+      return true;
+    };
+    const MicroOp& m = ho->m;
+    switch (m.type) {
+      case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE:
+        return add(m.b[1]);
+      case OP_MAT2:
+        if (ho->pctrl) return false;
+        if (m.b[0] == m.b[1] + n) return add(m.b[1]);
+        if (m.b[0] >= n && m.b[1] >= n) return add(m.b[0] - n) && add(m.b[1] - n);
+        if (m.b[0] < n && m.b[1] < n) return add(m.b[0]) && add(m.b[1]);
+        return false;
+      case OP_DEPOL2: case OP_INJECT:
+        return add(m.b[2]) && add(m.b[3]);
+      case OP_MAT1X2: {
+        if (!add(m.b[1])) return false;
+        if (__builtin_popcountll(ho->pctrl) > 1 || __builtin_popcountll(ho->pctrl2) > 1) return false;
+        const int rc = ho->pctrl ? __builtin_ctzll(ho->pctrl) - n : -1;    // control axis seen by the row side
+        const int cc = ho->pctrl2 ? __builtin_ctzll(ho->pctrl2) : -1;     // ... by the column side
+        if (rc >= 0 && cc >= 0 && rc != cc) return false;
+        const int c = rc >= 0 ? rc : cc;
+        if (c < 0) return true;
+        const bool r_local = rc >= 0 && ((tile >> (rc + n)) & 1ull), c_local = cc >= 0 && ((tile >> cc) & 1ull);
+        if (!r_local && !c_local) return true;   // control entirely outside the tile: uniform per CTA
+        return add(c);                           // needs both bits of the control axis in the tile
+      }
+      case OP_DIAG:
+        for (uint32_t i = 0; i < m.nb; ++i) {
+          const int ph = m.b[i];
+          if (!((tile >> ph) & 1ull)) continue;
+          if (!add(ph >= n ? ph - n : ph)) return false;
+        }
+        return true;
+      default:
+        return false;
+    }
+  }
+
+  MicroOp make_sub(const HostOp* ho, int A, int B, uint64_t tile, size_t pcb) {
+    static const int kSwap[4] = {0, 2, 1, 3};
+    const int n = h->nmax;
+    MicroOp m;
+    memset(&m, 0, sizeof(m));
+    const MicroOp& s = ho->m;
+    m.pred_bit = s.pred_bit;
+    auto role = [&](int axis) { return axis == A ? 0 : 1; };
+    switch (s.type) {
+      case OP_PAULI1:
+        m.type = G_PAULI1; m.flags = role(s.b[1]);
+        for (int i = 0; i < 4; ++i) m.p[i] = s.p[i];
+        break;
+      case OP_MAT2:
+        if (s.b[0] == s.b[1] + n) { m.type = G_MAT2; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb); }
+        else {
+          const bool rows = s.b[0] >= n;
+          const int x = rows ? s.b[0] - n : s.b[0];
+          m.type = rows ? G_MAT2ROWS : G_MAT2COLS;
+          m.c_off = copy_consts(ho, pcb, x == A ? nullptr : kSwap);
+        }
+        break;
+      case OP_MAT1X2: {
+        m.type = G_MAT1X2; m.flags = role(s.b[1]);
+        if (ho->pctrl) {
+          const int b = __builtin_ctzll(ho->pctrl);
+          if ((tile >> b) & 1ull) m.flags |= 2; else m.octrl = ho->pctrl;
+        }
+        if (ho->pctrl2) {
+          const int b = __builtin_ctzll(ho->pctrl2);
+          if ((tile >> b) & 1ull) m.flags |= 4; else m.octrl2 = ho->pctrl2;
+        }
+        m.c_off = copy_consts(ho, pcb);
+        break;
+      }
+      case OP_DEPOL2: m.type = G_DEPOL2; m.p[0] = s.p[0]; break;
+      case OP_COLLAPSE: m.type = G_COLLAPSE; m.flags = role(s.b[1]) | ((s.flags & 1) ? 8 : 0); m.p[0] = s.p[0]; break;
+      case OP_TRACE: m.type = G_TRACE; m.flags = role(s.b[1]); break;
+      case OP_INJECT:
+        m.type = G_INJECT;
+        m.c_off = copy_consts(ho, pcb, s.b[2] == A ? nullptr : kSwap);
+        break;
+      case OP_DIAG: {
+        m.type = G_DIAG; m.nb = s.nb;
+        uint8_t* lut = reinterpret_cast<uint8_t*>(&m.p[0]);
+        for (int e = 0; e < 16; ++e) lut[e] = 0;
+        for (uint32_t i = 0; i < s.nb; ++i) {
+          const int ph = s.b[i], sh = (int)s.nb - 1 - (int)i;
+          if (!((tile >> ph) & 1ull)) { m.b[i] = (uint8_t)(kOuter + ph); continue; }
+          m.b[i] = 0;
+          const int axis = ph >= n ? ph - n : ph;
+          const int slot = (ph >= n ? 2 : 0) + (axis == A ? 1 : 0);   // e bit: ra=3 rb=2 ca=1 cb=0
+          for (int e = 0; e < 16; ++e) lut[e] |= (uint8_t)(((e >> slot) & 1) << sh);
+        }
+        m.c_off = copy_consts(ho, pcb);
+        break;
+      }
+      default: break;
+    }
+    return m;
+  }
+
+  struct Item {
+    bool group;
+    std::vector<const HostOp*> ops;
+    int ax[2], nax;
+    uint64_t touched;
+  };
 
   bool close(std::vector<const HostOp*>& cur, uint64_t need, uint64_t live) {
     if (cur.empty()) return true;
@@ -500,32 +654,78 @@ struct Planner {
     pp.n_outer_segs = build_segs(outer, pp.outer_segs, 24);
     if (pp.n_tile_segs < 0 || pp.n_outer_segs < 0) { err = "planner: too many bit segments"; return false; }
     if (pp.n_tile_segs == 0) { pp.n_tile_segs = 1; pp.tile_segs[0] = Seg{0, 0, 0, 0}; }
-    pp.nops = (int)cur.size();
-    pp.seed = h->seed; pp.shot_offset = h->shot_offset;
+    pp.seed = h->seed; pp.shot_offset = h->shot_offset; pp.use_tma = h->tma;
     P.op_begin = dev_ops.size();
-    bool writes = false;
+    P.const_begin = dev_consts.size();
+
+    // ---- group ops by qubit pair (dm): an op joins the earliest group at or after its last
+    //      dependency (an item sharing any bit with it) that still spans <= 2 axes
+    std::vector<Item> items;
+    const bool grouping = h->formalism == DQE_DM && h->group && t >= 4;
     for (const HostOp* ho : cur) {
-      MicroOp m = ho->m;
-      if (m.type != OP_PROBS) writes = true;
-      if (m.type == OP_DIAG) {
-        for (uint32_t i = 0; i < m.nb; ++i) {
-          const int ph = ho->m.b[i];
-          m.b[i] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
+      uint64_t tb = touched_bits(*ho);
+      if (ho->m.type == OP_PROBS) tb = ~0ull;
+      int ax[2], nax = 0;
+      const bool can = grouping && group_axes(ho, tile, ax, &nax);
+      int dep = -1;
+      for (int k = (int)items.size() - 1; k >= 0; --k)
+        if (items[k].touched & tb) { dep = k; break; }
+      bool placed = false;
+      if (can) {
+        for (int k = std::max(dep, 0); k < (int)items.size() && !placed; ++k) {
+          Item& it = items[k];
+          if (!it.group) continue;
+          int u[4], nu = 0;
+          for (int i = 0; i < it.nax; ++i) u[nu++] = it.ax[i];
+          for (int i = 0; i < nax; ++i) {
+            bool seen = false;
+            for (int j = 0; j < nu; ++j) seen |= u[j] == ax[i];
+            if (!seen) u[nu++] = ax[i];
+          }
+          if (nu > 2) continue;
+          it.nax = nu; it.ax[0] = u[0]; if (nu > 1) it.ax[1] = u[1];
+          it.ops.push_back(ho); it.touched |= tb;
+          placed = true;
         }
-      } else if (m.type != OP_PROBS) {
-        for (uint32_t i = 0; i < m.nb; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
       }
-      m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
-      for (int b = 0; b < 64; ++b) {
-        if ((ho->pctrl >> b) & 1ull) {
-          if ((tile >> b) & 1ull) m.lctrl |= 1u << local_of(tile, b); else m.octrl |= 1ull << b;
-        }
-        if ((ho->pctrl2 >> b) & 1ull) {
-          if ((tile >> b) & 1ull) m.lctrl2 |= 1u << local_of(tile, b); else m.octrl2 |= 1ull << b;
-        }
+      if (!placed) {
+        Item it;
+        it.group = can; it.ops.push_back(ho); it.nax = nax; it.ax[0] = nax > 0 ? ax[0] : -1;
+        it.ax[1] = nax > 1 ? ax[1] : -1; it.touched = tb;
+        items.push_back(it);
       }
-      dev_ops.push_back(m);
     }
+
+    // ---- emit
+    bool writes = false;
+    const int n = h->nmax;
+    for (Item& it : items) {
+      bool as_group = it.group && it.ops.size() >= 2;
+      int A = it.ax[0], B = it.nax > 1 ? it.ax[1] : -1;
+      if (as_group && B < 0) {  // single-axis group: borrow any other axis fully inside the tile
+        for (int a = 0; a < n && B < 0; ++a)
+          if (a != A && ((tile >> a) & 1ull) && ((tile >> (a + n)) & 1ull)) B = a;
+        if (B < 0) as_group = false;
+      }
+      if (as_group) {
+        // for two-qubit matrices the first listed axis of the op is the MSB; keep A = that axis if any
+        MicroOp g;
+        memset(&g, 0, sizeof(g));
+        g.type = OP_GROUP; g.pred_bit = -1; g.nb = 4; g.aux = (int)it.ops.size();
+        g.b[0] = (uint8_t)local_of(tile, A + n); g.b[1] = (uint8_t)local_of(tile, B + n);
+        g.b[2] = (uint8_t)local_of(tile, A); g.b[3] = (uint8_t)local_of(tile, B);
+        dev_ops.push_back(g);
+        for (const HostOp* ho : it.ops) dev_ops.push_back(make_sub(ho, A, B, tile, P.const_begin));
+        writes = true;
+      } else {
+        for (const HostOp* ho : it.ops) {
+          if (ho->m.type != OP_PROBS) writes = true;
+          dev_ops.push_back(localise(ho, tile, P.const_begin));
+        }
+      }
+    }
+    pp.nops = (int)(dev_ops.size() - P.op_begin);
+    pp.nconsts = (int)(dev_consts.size() - P.const_begin);
     pp.store_back = writes ? 1 : 0;
     P.grid = (uint64_t)h->batch << pp.outer_bits;
     P.smem = sizeof(double2) << t;
@@ -538,6 +738,7 @@ struct Planner {
   bool plan() {
     std::vector<const HostOp*> cur;
     uint64_t live_now = h->planned_live, need = 0, live = live_now;
+    int nconst = 0;
     for (const HostOp& op : h->queue) {
       if (op.kind == 1) {
         // the PROBS op is the tail of `cur`
@@ -552,20 +753,24 @@ struct Planner {
         F.fp.flip = op.flip; F.fp.forced = op.forced; F.fp.creg_bit = op.creg_bit;
         F.fp.is_dm = h->formalism == DQE_DM;
         passes.push_back(F);
-        need = 0; live = live_now;
+        need = 0; live = live_now; nconst = 0;
         continue;
       }
       uint64_t need2 = need | op.need;
       uint64_t live2 = live | op.live_after | op.need;
       int t = 0;
       uint64_t tile = 0;
-      const bool fits = cur.empty() || (h->fuse && (int)cur.size() < kMaxOpsPerPass &&
+      // every op may need a group header in the worst case -> 2 slots per op
+      const bool fits = cur.empty() || (h->fuse && 2 * ((int)cur.size() + 1) <= kMaxOpsPerPass &&
+                                        nconst + op.nconst <= kMaxConstsPerPass &&
                                         choose_tile(h, need2, live2, false, &tile, &t));
       if (!fits) {
         if (!close(cur, need, live)) return false;
         need2 = op.need;
         live2 = live_now | op.live_after | op.need;
+        nconst = 0;
       }
+      nconst += op.nconst;
       cur.push_back(&op);
       need = need2; live = live2;
       live_now = op.live_after;
@@ -595,12 +800,15 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP"};
+    static const char* gnames[] = {"?", "gPAULI1", "gMAT2", "gMAT1X2", "gDEPOL2", "gROWS", "gCOLS", "gCOLLAPSE",
+                                   "gTRACE", "gINJECT", "gDIAG"};
     for (PlannedPass& P : pl.passes) {
       if (P.is_finish) { fprintf(stderr, "  finish\n"); continue; }
       fprintf(stderr, "pass t=%d outer=%d nops=%d:", P.pp.t, P.pp.outer_bits, P.pp.nops);
       for (int i = 0; i < P.pp.nops; ++i) {
         const MicroOp& m = pl.dev_ops[P.op_begin + i];
+        if (m.type > 100) { fprintf(stderr, " %s%s.%d", gnames[m.type - 100], m.pred_bit >= 0 ? "?" : "", m.flags & 1); continue; }
         fprintf(stderr, " %s%s(", names[m.type], m.pred_bit >= 0 ? "?" : "");
         for (uint32_t b = 0; b < m.nb; ++b) fprintf(stderr, "%s%d", b ? "," : "", (int)m.b[b]);
         fprintf(stderr, ")");
@@ -614,7 +822,7 @@ int do_flush(dqe_t* h) {
       h->stats[0]++; h->stats[2]++; h->stats[1] += P.pp.nops;
       h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
     }
-    h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + h->cpool.size() * sizeof(double2));
+    h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + pl.dev_consts.size() * sizeof(double2));
     h->queue.clear(); h->cpool.clear();
     h->planned_live = phys_live(h, h->live_axes);
     return 0;
@@ -626,17 +834,17 @@ int do_flush(dqe_t* h) {
     h->d_ops_cap = std::max<size_t>(pl.dev_ops.size() * 2, 1024);
     CK(cudaMalloc(&h->d_ops, h->d_ops_cap * sizeof(MicroOp)));
   }
-  if (h->cpool.size() > h->d_consts_cap) {
+  if (pl.dev_consts.size() > h->d_consts_cap) {
     if (h->d_consts) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_consts)); }
-    h->d_consts_cap = std::max<size_t>(h->cpool.size() * 2, 4096);
+    h->d_consts_cap = std::max<size_t>(pl.dev_consts.size() * 2, 4096);
     CK(cudaMalloc(&h->d_consts, h->d_consts_cap * sizeof(double2)));
   }
-  h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + h->cpool.size() * sizeof(double2));
+  h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + pl.dev_consts.size() * sizeof(double2));
   if (!pl.dev_ops.empty())
     CK(cudaMemcpyAsync(h->d_ops, pl.dev_ops.data(), pl.dev_ops.size() * sizeof(MicroOp),
                        cudaMemcpyHostToDevice, h->stream));
-  if (!h->cpool.empty())
-    CK(cudaMemcpyAsync(h->d_consts, h->cpool.data(), h->cpool.size() * sizeof(double2),
+  if (!pl.dev_consts.empty())
+    CK(cudaMemcpyAsync(h->d_consts, pl.dev_consts.data(), pl.dev_consts.size() * sizeof(double2),
                        cudaMemcpyHostToDevice, h->stream));
   // partials: sized for the widest grid of a pass that ends in PROBS
   size_t need_part = 0;
@@ -654,7 +862,7 @@ int do_flush(dqe_t* h) {
     }
     if (P.grid > 0x7fffffffull) return fail(h, DQE_EUNSUPPORTED, "grid too large");
     P.pp.state = h->state; P.pp.creg = h->creg; P.pp.partials = h->partials; P.pp.rec = h->rec;
-    P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts;
+    P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -731,7 +939,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->timing = false;
+  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -767,6 +975,9 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
   if ((e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
     return bail("cudaFuncSetAttribute", e);
+  if ((e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(carveout)", e);
   if ((e = cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMemsetAsync(h->creg, 0, batch * sizeof(uint64_t), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMemsetAsync(h->rec, 0, batch * sizeof(MeasRec), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -1197,6 +1408,10 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->fuse = value ? 1 : 0;
   } else if (!strcmp(key, "merge")) {
     h->merge = value ? 1 : 0;
+  } else if (!strcmp(key, "group")) {
+    h->group = value ? 1 : 0;
+  } else if (!strcmp(key, "tma")) {
+    h->tma = value ? 1 : 0;
   } else return fail(h, DQE_EINVAL, std::string("unknown option ") + key);
   return 0;
 }
