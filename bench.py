@@ -209,20 +209,14 @@ def main():
                      stream=stream.cuda_stream, tile_bits=a.tile_bits)
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
-        red = torch.zeros(2 + 64, dtype=torch.float64, device=f"cuda:{local}")
 
         def step():
             t0 = time.perf_counter()
             res = experiment.run_shot_batch(ops, dqc, eng, data, ideal, before_flush=lambda: ev0.record(stream),
                                             after_launch=lambda: ev1.record(stream))
-            hist = np.bincount((res.creg & np.uint64(63)).astype(np.int64), minlength=64)
-            if world > 1:  # the one collective of the path: fidelity sum + outcome histogram
-                red[0] = float(res.fidelity.sum()); red[1] = float(len(res.fidelity))
-                red[2:] = torch.from_numpy(hist.astype(np.float64)).to(red.device)
-                dist.all_reduce(red)
-                mean_f = float(red[0] / red[1])
-            else:
-                mean_f = float(res.fidelity.mean())
+            hist = experiment.outcome_histogram(res.creg)
+            # the one collective of the path: fidelity sum + outcome histogram (no-op at N = 1)
+            mean_f, _n, _h = experiment.all_reduce_results(res.fidelity, hist, device=f"cuda:{local}")
             stream.synchronize()
             wall = time.perf_counter() - t0
             return wall, ev0.elapsed_time(ev1), mean_f

@@ -69,3 +69,33 @@ def run_shot_batch(qpu_ops, dqc, engine, data_qubits, ideal_ket, before_flush=No
     fid = engine.fidelity_ket_all(axes, ideal_ket)
     creg = engine.read_creg_words()
     return ShotBatchResult(fid, creg, ex)
+
+
+def shard_range(total_shots, rank, world):
+    """Global shot ids [lo, hi) owned by `rank`: contiguous, sizes differ by at most one."""
+    base, rem = divmod(int(total_shots), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def outcome_histogram(creg_words, nbits=6):
+    """Counts of the low `nbits` classical bits of every shot."""
+    idx = (np.asarray(creg_words, dtype=np.uint64) & np.uint64((1 << nbits) - 1)).astype(np.int64)
+    return np.bincount(idx, minlength=1 << nbits).astype(np.int64)
+
+
+def all_reduce_results(fidelity, hist, device=None):
+    """The one collective of the shot-sharded path: sum over ranks of
+    [sum of fidelities, shot count, outcome histogram].  NCCL on GPUs, gloo in CPU tests.
+    Returns (mean fidelity over all shots, total shots, global histogram)."""
+    import torch
+    import torch.distributed as dist
+
+    buf = torch.zeros(2 + len(hist), dtype=torch.float64, device=device or "cpu")
+    buf[0] = float(np.sum(fidelity))
+    buf[1] = float(len(fidelity))
+    buf[2:] = torch.as_tensor(np.asarray(hist, dtype=np.float64)).to(buf.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf)
+    out = buf.cpu().numpy()
+    return float(out[0] / max(out[1], 1.0)), int(round(out[1])), np.rint(out[2:]).astype(np.int64)
