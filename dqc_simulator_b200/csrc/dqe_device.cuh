@@ -48,7 +48,7 @@ enum OpType : int32_t {
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
 constexpr int kMaxConstsPerPass = 512;   // double2 entries staged in shared memory per pass (8 KiB)
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
 struct __align__(16) MicroOp {
   int32_t type;
@@ -86,7 +86,9 @@ struct PassParams {
   int32_t nops, t, P, nmax;
   int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
   int32_t store_back, nconsts;
-  int32_t use_tma, pad1;
+  int32_t use_tma, nthreads;
+  int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
+  uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
   Seg tile_segs[16];
   Seg outer_segs[24];
 };
@@ -152,7 +154,7 @@ __device__ __forceinline__ void shot_uniforms(uint64_t seed, uint64_t shot, uint
 // micro-ops on the shared-memory tile
 __device__ __forceinline__ void apply_mat1(double2* tile, uint32_t T, int j, uint32_t lc,
                                            double2 m00, double2 m01, double2 m10, double2 m11) {
-  for (uint32_t p = threadIdx.x; p < (T >> 1); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 1); p += blockDim.x) {
     const uint32_t i0 = ins0(p, j);
     if ((i0 & lc) != lc) continue;
     const uint32_t i1 = i0 | (1u << j);
@@ -175,7 +177,7 @@ __device__ __forceinline__ void op_mat1x2(double2* tile, uint32_t T, const Micro
   const double2 m00 = cs[0], m01 = cs[1], m10 = cs[2], m11 = cs[3];
   const double2 n00 = conj2(m00), n01 = conj2(m01), n10 = conj2(m10), n11 = conj2(m11);
   const uint32_t lr = op.lctrl, lc = op.lctrl2;
-  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
     const uint32_t i00 = ins0(ins0(p, jlo), jhi);
     const bool do_r = row_on && ((i00 & lr) == lr);   // row-side control lives on row bits
     const bool do_c = col_on && ((i00 & lc) == lc);
@@ -203,7 +205,7 @@ __device__ __forceinline__ void op_mat2(double2* tile, uint32_t T, const MicroOp
   const int jlo = jh < jl ? jh : jl, jhi = jh < jl ? jl : jh;
   const uint32_t lc = op.lctrl;
   const double2* __restrict__ m = cs;
-  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
     const uint32_t i0 = ins0(ins0(p, jlo), jhi);
     if ((i0 & lc) != lc) continue;
     const uint32_t i1 = i0 | (1u << jl), i2 = i0 | (1u << jh), i3 = i1 | (1u << jh);
@@ -227,10 +229,10 @@ __device__ __forceinline__ void op_diag(double2* tile, uint32_t T, const MicroOp
   }
   if (nl == 0) {
     const double2 d = cs[fixed];
-    for (uint32_t i = threadIdx.x; i < T; i += kThreads) tile[i] = cmul(tile[i], d);
+    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) tile[i] = cmul(tile[i], d);
     return;
   }
-  for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
     uint32_t idx = fixed;
     for (int s = 0; s < nl; ++s) idx |= ((i >> lb[s]) & 1u) << ls[s];
     tile[i] = cmul(tile[i], cs[idx]);
@@ -241,7 +243,7 @@ __device__ __forceinline__ void op_pauli1(double2* tile, uint32_t T, const Micro
   const int jr = op.b[0], jc = op.b[1];
   const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
   const double a = op.p[0], b = op.p[1], c = op.p[2], d = op.p[3];
-  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
     const uint32_t i00 = ins0(ins0(p, jlo), jhi);
     const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
     const double2 e00 = tile[i00], e01 = tile[i01], e10 = tile[i10], e11 = tile[i11];
@@ -271,7 +273,7 @@ __device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const Micro
   sort4(op.b, s);
   const uint32_t mra = 1u << op.b[0], mrb = 1u << op.b[1], mca = 1u << op.b[2], mcb = 1u << op.b[3];
   const double pp = op.p[0], keep = 1.0 - pp, mix = 0.25 * pp;
-  for (uint32_t p = threadIdx.x; p < (T >> 4); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 4); p += blockDim.x) {
     const uint32_t i0 = ins0_4(p, s);
     const uint32_t d0 = i0, d1 = i0 | mrb | mcb, d2 = i0 | mra | mca, d3 = d1 | mra | mca;
     const double2 v0 = tile[d0], v1 = tile[d1], v2 = tile[d2], v3 = tile[d3];
@@ -294,21 +296,42 @@ __device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const Micro
 __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                          uint64_t base, uint64_t blk, double* red) {
   double a0 = 0.0, a1 = 0.0;
-  const int abit = op.aux;
+  const int abit = op.aux;   // physical (column) bit of the measured axis
   if (pp.formalism == 0) {
-    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
-      const uint64_t phys = base | deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs);
-      const double2 v = tile[i];
-      const double w = fma(v.x, v.x, v.y * v.y);
-      if ((phys >> abit) & 1ull) a1 += w; else a0 += w;
+    // b[0] = tile-local position of the axis bit, or kOuter + physical when it is fixed for the tile
+    const int jb = op.b[0];
+    if (jb >= kOuter) {
+      double a = 0.0;
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) { const double2 v = tile[i]; a += fma(v.x, v.x, v.y * v.y); }
+      if ((base >> (jb - kOuter)) & 1ull) a1 = a; else a0 = a;
+    } else {
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+        const double2 v = tile[i];
+        const double w = fma(v.x, v.x, v.y * v.y);
+        if ((i >> jb) & 1u) a1 += w; else a0 += w;
+      }
     }
   } else {
-    const uint64_t cm = (1ull << pp.nmax) - 1ull;
-    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
-      const uint64_t phys = base | deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs);
-      if ((phys >> pp.nmax) == (phys & cm)) {
+    // only the diagonal of rho matters: enumerate it directly.  Free variables = axes whose column
+    // bit is inside the tile; the row bit must repeat it (inside the tile, or fixed by the tile base).
+    const int n = pp.nmax;
+    int nfree = 0;
+    for (int a = 0; a < n; ++a) nfree += pp.ax_col[a] >= 0;
+    for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
+      uint32_t i = 0, va = 0;
+      bool ok = true;
+      int k = 0;
+      for (int a = 0; a < n; ++a) {
+        const int cl = pp.ax_col[a], rl = pp.ax_row[a];
+        const uint32_t v = cl >= 0 ? ((d >> k++) & 1u) : (uint32_t)((base >> a) & 1ull);
+        if (cl >= 0) i |= v << cl;
+        if (rl >= 0) i |= v << rl;
+        else ok = ok && (((base >> (a + n)) & 1ull) == v);
+        if (a == abit) va = v;
+      }
+      if (ok) {
         const double w = tile[i].x;
-        if ((phys >> abit) & 1ull) a1 += w; else a0 += w;
+        if (va) a1 += w; else a0 += w;
       }
     }
   }
@@ -322,7 +345,7 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
   __syncthreads();
   if (threadIdx.x == 0) {
     double s0 = 0.0, s1 = 0.0;
-    for (int i = 0; i < kThreads / 32; ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
     pp.partials[2 * blk] = s0;
     pp.partials[2 * blk + 1] = s1;
   }
@@ -337,7 +360,7 @@ __device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const Mic
   const double2 zero = make_double2(0.0, 0.0);
   if (pp.formalism == 0) {
     const int j = op.b[0];
-    for (uint32_t p = threadIdx.x; p < (T >> 1); p += kThreads) {
+    for (uint32_t p = threadIdx.x; p < (T >> 1); p += blockDim.x) {
       const uint32_t i0 = ins0(p, j), i1 = i0 | (1u << j);
       const double2 kept = cscale(tile[m ? i1 : i0], sc);
       if (discard || m == 0) { tile[i0] = kept; tile[i1] = zero; }
@@ -347,7 +370,7 @@ __device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const Mic
     const int jr = op.b[0], jc = op.b[1];
     const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
     const double e = op.p[0];
-    for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
       const uint32_t i00 = ins0(ins0(p, jlo), jhi);
       const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
       const double2 same = tile[m ? i11 : i00], flip = tile[m ? i00 : i11];
@@ -365,7 +388,7 @@ __device__ __forceinline__ void op_trace(double2* tile, uint32_t T, const MicroO
   const int jr = op.b[0], jc = op.b[1];
   const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
   const double2 zero = make_double2(0.0, 0.0);
-  for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
     const uint32_t i00 = ins0(ins0(p, jlo), jhi);
     const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
     tile[i00] = cadd(tile[i00], tile[i11]);
@@ -386,7 +409,7 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
     }
     const double2 k0 = cs[4 * choice], k1 = cs[4 * choice + 1],
                   k2 = cs[4 * choice + 2], k3 = cs[4 * choice + 3];
-    for (uint32_t p = threadIdx.x; p < (T >> 2); p += kThreads) {
+    for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
       const uint32_t i0 = ins0(ins0(p, jlo), jhi);
       const double2 x = tile[i0];
       tile[i0] = cmul(x, k0);
@@ -398,7 +421,7 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
     int s[4];
     sort4(op.b, s);
     const uint32_t mra = 1u << op.b[0], mrb = 1u << op.b[1], mca = 1u << op.b[2], mcb = 1u << op.b[3];
-    for (uint32_t p = threadIdx.x; p < (T >> 4); p += kThreads) {
+    for (uint32_t p = threadIdx.x; p < (T >> 4); p += blockDim.x) {
       const uint32_t i0 = ins0_4(p, s);
       const double2 x = tile[i0];
 #pragma unroll
@@ -593,7 +616,7 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
   sort4(g.b, s4);
   const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
   const int nsub = g.aux;
-  for (uint32_t q = threadIdx.x; q < (T >> 4); q += kThreads) {
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
     double2 v[16];
 #pragma unroll
@@ -672,15 +695,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
     const int nw = pp.nops * (int)(sizeof(MicroOp) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.ops);
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
-    for (int i = threadIdx.x; i < nw; i += kThreads) dst[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < pp.nconsts; i += kThreads) s_consts[i] = __ldg(pp.consts + i);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < pp.nconsts; i += blockDim.x) s_consts[i] = __ldg(pp.consts + i);
   }
   // tile load.  The low segment of the tile (local bits [0, c0) = physical bits [0, c0)) is a
   // contiguous run of 2^c0 amplitudes in HBM: the tile is 2^(t-c0) such runs, fetched with TMA bulk
   // copies (cp.async.bulk, completion on an mbarrier) issued by warp 0 -- no registers, no LSU
   // instructions, all 64 KiB in flight at once.  Fallback: per-thread 16-byte loads.
   const int c0 = pp.tile_segs[0].len;
-  const bool tma = pp.use_tma && pp.tile_segs[0].dst == 0 && c0 >= 3;
+  const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
   const uint32_t run_bytes = 16u << c0;
   const uint32_t nruns = T >> c0;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
@@ -691,30 +714,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      if (threadIdx.x == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
-      __syncwarp();
-      const int nhs = pp.n_tile_segs - 1;
-      for (uint32_t r = threadIdx.x; r < nruns; r += 32) {
-        const uint64_t off = deposit((uint64_t)r << c0, pp.tile_segs + 1, nhs);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
+      for (uint32_t r = 0; r < nruns; ++r) {
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                 tile_s + r * run_bytes),
-            "l"(sp + off), "r"(run_bytes), "r"(bar_s)
+            "l"(sp + ((uint64_t)pp.run_hi[r] << c0)), "r"(run_bytes), "r"(bar_s)
             : "memory");
       }
     }
   } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
     const int nhs = pp.n_tile_segs - 1;
 #pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
       const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
       tile[i] = sp[off];
     }
   } else {
 #pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < T; i += kThreads)
+    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
       tile[i] = sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)];
   }
   const uint64_t cw = pp.creg[shot];
@@ -770,11 +789,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
       // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
-      if (threadIdx.x < 32) {
-        const int nhs = pp.n_tile_segs - 1;
-        for (uint32_t r = threadIdx.x; r < nruns; r += 32) {
-          const uint64_t off = deposit((uint64_t)r << c0, pp.tile_segs + 1, nhs);
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(sp + off),
+      if (threadIdx.x == 0) {
+        for (uint32_t r = 0; r < nruns; ++r) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                           sp + ((uint64_t)pp.run_hi[r] << c0)),
                        "r"(tile_s + r * run_bytes), "r"(run_bytes)
                        : "memory");
         }
@@ -784,13 +802,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
     } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
       const int nhs = pp.n_tile_segs - 1;
 #pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < T; i += kThreads) {
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
         const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
         sp[off] = tile[i];
       }
     } else {
 #pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < T; i += kThreads)
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
         sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)] = tile[i];
     }
   }

@@ -75,7 +75,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -505,6 +505,9 @@ struct Planner {
       }
     } else if (m.type != OP_PROBS) {
       for (uint32_t i = 0; i < m.nb; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
+    } else {
+      const int ph = m.aux;   // measured axis: column / ket bit
+      m.b[0] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
     }
     m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
     for (int b = 0; b < 64; ++b) {
@@ -654,7 +657,28 @@ struct Planner {
     pp.n_outer_segs = build_segs(outer, pp.outer_segs, 24);
     if (pp.n_tile_segs < 0 || pp.n_outer_segs < 0) { err = "planner: too many bit segments"; return false; }
     if (pp.n_tile_segs == 0) { pp.n_tile_segs = 1; pp.tile_segs[0] = Seg{0, 0, 0, 0}; }
-    pp.seed = h->seed; pp.shot_offset = h->shot_offset; pp.use_tma = h->tma;
+    pp.seed = h->seed; pp.shot_offset = h->shot_offset; pp.nthreads = h->threads;
+    for (int a = 0; a < 24; ++a) { pp.ax_col[a] = -1; pp.ax_row[a] = -1; }
+    if (h->formalism == DQE_DM)
+      for (int a = 0; a < h->nmax; ++a) {
+        if ((tile >> a) & 1ull) pp.ax_col[a] = (int8_t)local_of(tile, a);
+        if ((tile >> (a + h->nmax)) & 1ull) pp.ax_row[a] = (int8_t)local_of(tile, a + h->nmax);
+      }
+    {  // TMA bulk path: low tile segment contiguous from physical bit 0, runs of >= 128 B, <= 128 runs
+      const int c0 = pp.tile_segs[0].len;
+      pp.use_tma = h->tma && pp.tile_segs[0].dst == 0 && c0 >= 3 && (t - c0) <= 7;
+      if (pp.use_tma) {
+        const uint32_t nruns = 1u << (t - c0);
+        for (uint32_t r = 0; r < nruns; ++r) {
+          uint64_t off = 0;
+          for (int sgi = 1; sgi < pp.n_tile_segs; ++sgi) {
+            const Seg& sg = pp.tile_segs[sgi];
+            off |= ((((uint64_t)r << c0) >> sg.src) & ((1ull << sg.len) - 1ull)) << sg.dst;
+          }
+          pp.run_hi[r] = (uint32_t)(off >> c0);
+        }
+      }
+    }
     P.op_begin = dev_ops.size();
     P.const_begin = dev_consts.size();
 
@@ -868,7 +892,7 @@ int do_flush(dqe_t* h) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, h->stream));
     }
-    k_tile_pass<<<(unsigned)P.grid, kThreads, P.smem, h->stream>>>(P.pp);
+    k_tile_pass<<<(unsigned)P.grid, h->threads, P.smem, h->stream>>>(P.pp);
     if (h->timing) {
       CK(cudaEventRecord(e1, h->stream));
       h->ev_pool.push_back(std::make_pair(e0, e1));
@@ -939,7 +963,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 12; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->timing = false;
+  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1412,6 +1436,9 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->group = value ? 1 : 0;
   } else if (!strcmp(key, "tma")) {
     h->tma = value ? 1 : 0;
+  } else if (!strcmp(key, "threads")) {
+    if (value != 64 && value != 128 && value != 256) return fail(h, DQE_EINVAL, "threads in {64, 128, 256}");
+    h->threads = (int)value;
   } else return fail(h, DQE_EINVAL, std::string("unknown option ") + key);
   return 0;
 }
