@@ -108,12 +108,14 @@ def _plan(circuit, **opts):
 def test_planner_measurement_bound_pass_count():
     """Every measurement needs a per-shot global sum, so it ends a pass; everything between two
     measurements of the config-2 circuits fuses into one pass (tile = 12 of the 14 dm bits)."""
-    st, ex = _plan("grover")
+    st, ex = _plan("grover", tile_bits=12)
     assert ex.measurements == 288 and st["finish_launches"] == 288
     assert 288 <= st["passes"] <= 288 + 20
     assert st["api_ops"] > 3000 and st["merged_ops"] > 500
-    st_q, ex_q = _plan("qft")
+    st_q, ex_q = _plan("qft", tile_bits=12)
     assert ex_q.measurements == 44 and 44 <= st_q["passes"] <= 50
+    st11, _ = _plan("grover", tile_bits=11)     # a smaller tile holds fewer high bits: more cuts
+    assert st["passes"] < st11["passes"] < 2 * st["passes"]
 
 
 def test_planner_switches():
