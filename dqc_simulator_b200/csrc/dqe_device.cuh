@@ -87,6 +87,8 @@ struct PassParams {
   int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
   int32_t store_back, nconsts;
   int32_t use_tma, nthreads;
+  int32_t nbuf, pad2;
+  uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
   Seg tile_segs[16];
@@ -677,141 +679,172 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 }
 
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
+                                              uint32_t T, int c0) {
+  const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
+  for (uint32_t r = 0; r < nruns; ++r) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_s + r * run_bytes),
+        "l"(sp + ((uint64_t)pp.run_hi[r] << c0)), "r"(run_bytes), "r"(bar_s)
+        : "memory");
+  }
+}
+
+// Persistent, double-buffered pass kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ... ; while
+// the micro-program runs on the tile in buffer b, the TMA load of the CTA's next tile streams into
+// buffer b^1 and the bulk store of the previous tile drains -- the HBM pipe never idles behind the
+// shared-memory / FP64 work of a fused pass.
 __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant__ PassParams pp) {
-  extern __shared__ double2 tile[];
+  extern __shared__ double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
   __shared__ double2 s_consts[kMaxConstsPerPass];
   __shared__ double s_red[2 * (kThreads / 32)];
-  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ __align__(8) unsigned long long s_bar[2];
 
-  const uint64_t blk = blockIdx.x;
-  const uint64_t shot = blk >> pp.outer_bits;
-  const uint64_t tix = blk & ((1ull << pp.outer_bits) - 1ull);
-  const uint64_t base = deposit(tix, pp.outer_segs, pp.n_outer_segs);
-  double2* __restrict__ sp = pp.state + (shot << pp.P) + base;
   const uint32_t T = 1u << pp.t;
+  const int c0 = pp.tile_segs[0].len;
+  const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
+  const int nbuf = pp.nbuf;           // 2 with TMA (prefetch distance 1), 1 otherwise
+  const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
+  const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 
-  {  // stage the micro-program
+  {  // stage the micro-program once per CTA
     const int nw = pp.nops * (int)(sizeof(MicroOp) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.ops);
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
     for (int i = threadIdx.x; i < pp.nconsts; i += blockDim.x) s_consts[i] = __ldg(pp.consts + i);
   }
-  // tile load.  The low segment of the tile (local bits [0, c0) = physical bits [0, c0)) is a
-  // contiguous run of 2^c0 amplitudes in HBM: the tile is 2^(t-c0) such runs, fetched with TMA bulk
-  // copies (cp.async.bulk, completion on an mbarrier) issued by warp 0 -- no registers, no LSU
-  // instructions, all 64 KiB in flight at once.  Fallback: per-thread 16-byte loads.
-  const int c0 = pp.tile_segs[0].len;
-  const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
-  const uint32_t run_bytes = 16u << c0;
-  const uint32_t nruns = T >> c0;
-  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar);
-  if (tma) {
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
-      for (uint32_t r = 0; r < nruns; ++r) {
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                tile_s + r * run_bytes),
-            "l"(sp + ((uint64_t)pp.run_hi[r] << c0)), "r"(run_bytes), "r"(bar_s)
-            : "memory");
-      }
-    }
-  } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
-    const int nhs = pp.n_tile_segs - 1;
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
-      const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
-      tile[i] = sp[off];
-    }
-  } else {
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
-      tile[i] = sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)];
-  }
-  const uint64_t cw = pp.creg[shot];
-  if (tma) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(bar_s), "r"(0u)
-          : "memory");
+  const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
+  const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+  uint64_t blk = blockIdx.x;
+  if (tma && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s + 8u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blk < pp.ntiles) {
+      const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
+      tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0);
     }
   }
   __syncthreads();
 
-  for (int o = 0; o < pp.nops; ++o) {
-    const MicroOp& op = s_ops[o];
-    if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
-    const double2* cs = s_consts + op.c_off;
-    switch (op.type) {
-      case OP_GROUP:
-        run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
-        o += op.aux;
-        break;
-      case OP_MAT1:
-        if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
-        break;
-      case OP_MAT1X2: {
-        const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
-        if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
-        break;
-      }
-      case OP_MAT2:
-        if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
-        break;
-      case OP_DIAG: op_diag(tile, T, op, cs, base); break;
-      case OP_PAULI1: op_pauli1(tile, T, op); break;
-      case OP_DEPOL2: op_depol2(tile, T, op); break;
-      case OP_PROBS: op_probs(tile, T, op, pp, base, blk, s_red); break;
-      case OP_COLLAPSE: op_collapse(tile, T, op, pp, shot); break;
-      case OP_TRACE: op_trace(tile, T, op); break;
-      case OP_INJECT: op_inject(tile, T, op, pp, cs, shot); break;
-      case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
-      default: break;
-    }
-    __syncthreads();
-  }
+  uint32_t parity[2] = {0u, 0u};
+  for (uint32_t it = 0; blk < pp.ntiles; blk += gridDim.x, ++it) {
+    const int b = (nbuf == 2) ? (int)(it & 1u) : 0;
+    double2* tile = dyn_tiles + (size_t)b * T;
+    const uint32_t tile_s = tiles_s + (uint32_t)b * T * 16u;
+    const uint64_t shot = blk >> pp.outer_bits;
+    const uint64_t base = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
+    double2* __restrict__ sp = pp.state + (shot << pp.P) + base;
 
-  if (pp.store_back) {
     if (tma) {
-      // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (uint32_t r = 0; r < nruns; ++r) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                           sp + ((uint64_t)pp.run_hi[r] << c0)),
-                       "r"(tile_s + r * run_bytes), "r"(run_bytes)
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      const uint64_t nxt = blk + gridDim.x;
+      if (threadIdx.x == 0 && nxt < pp.ntiles) {
+        // buffer b^1 was stored from at the end of the previous iteration: its reads must be done
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        const uint64_t nbase = deposit(nxt & outer_mask, pp.outer_segs, pp.n_outer_segs);
+        tma_load_tile(pp, pp.state + ((nxt >> pp.outer_bits) << pp.P) + nbase, tiles_s + (uint32_t)(b ^ 1) * T * 16u,
+                      bar0_s + 8u * (uint32_t)(b ^ 1), T, c0);
       }
-    } else if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
-      const int nhs = pp.n_tile_segs - 1;
-#pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
-        const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
-        sp[off] = tile[i];
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar0_s + 8u * (uint32_t)b), "r"(parity[b])
+            : "memory");
       }
+      parity[b] ^= 1u;
     } else {
+      if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+        const int nhs = pp.n_tile_segs - 1;
 #pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
-        sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)] = tile[i];
+        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+          const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
+          tile[i] = sp[off];
+        }
+      } else {
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
+          tile[i] = sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)];
+      }
+      __syncthreads();
+    }
+    const uint64_t cw = pp.creg[shot];
+
+    for (int o = 0; o < pp.nops; ++o) {
+      const MicroOp& op = s_ops[o];
+      if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
+      const double2* cs = s_consts + op.c_off;
+      switch (op.type) {
+        case OP_GROUP:
+          run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
+          o += op.aux;
+          break;
+        case OP_MAT1:
+          if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
+          break;
+        case OP_MAT1X2: {
+          const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
+          if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
+          break;
+        }
+        case OP_MAT2:
+          if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
+          break;
+        case OP_DIAG: op_diag(tile, T, op, cs, base); break;
+        case OP_PAULI1: op_pauli1(tile, T, op); break;
+        case OP_DEPOL2: op_depol2(tile, T, op); break;
+        case OP_PROBS: op_probs(tile, T, op, pp, base, blk, s_red); break;
+        case OP_COLLAPSE: op_collapse(tile, T, op, pp, shot); break;
+        case OP_TRACE: op_trace(tile, T, op); break;
+        case OP_INJECT: op_inject(tile, T, op, pp, cs, shot); break;
+        case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
+        default: break;
+      }
+      __syncthreads();
+    }
+
+    if (pp.store_back) {
+      if (tma) {
+        // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          for (uint32_t r = 0; r < nruns; ++r) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                             sp + ((uint64_t)pp.run_hi[r] << c0)),
+                         "r"(tile_s + r * run_bytes), "r"(run_bytes)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        if (pp.tile_segs[0].dst == 0 && c0 >= 8) {
+          const int nhs = pp.n_tile_segs - 1;
+#pragma unroll 4
+          for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+            const uint64_t off = (uint64_t)(i & ((1u << c0) - 1u)) | deposit((uint64_t)i, pp.tile_segs + 1, nhs);
+            sp[off] = tile[i];
+          }
+        } else {
+#pragma unroll 4
+          for (uint32_t i = threadIdx.x; i < T; i += blockDim.x)
+            sp[deposit((uint64_t)i, pp.tile_segs, pp.n_tile_segs)] = tile[i];
+        }
+        __syncthreads();   // single buffer: the next iteration's load overwrites the tile
+      }
+    } else if (!tma) {
+      __syncthreads();
     }
   }
+  // shared memory must stay valid until the last bulk store has read it
+  if (tma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------

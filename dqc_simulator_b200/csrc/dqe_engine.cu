@@ -75,7 +75,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -751,8 +751,22 @@ struct Planner {
     pp.nops = (int)(dev_ops.size() - P.op_begin);
     pp.nconsts = (int)(dev_consts.size() - P.const_begin);
     pp.store_back = writes ? 1 : 0;
-    P.grid = (uint64_t)h->batch << pp.outer_bits;
-    P.smem = sizeof(double2) << t;
+    pp.ntiles = (uint64_t)h->batch << pp.outer_bits;
+    if (h->persistent) {
+      // persistent grid + double buffering: as many CTAs as fit the machine (<= 512 threads per SM)
+      pp.nbuf = pp.use_tma ? 2 : 1;
+      P.smem = (sizeof(double2) << t) * pp.nbuf;
+      const size_t per_cta = P.smem + 14 * 1024;
+      int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / per_cta, (size_t)(512 / h->threads));
+      per_sm = std::max(1, std::min(per_sm, h->ctas_per_sm > 0 ? h->ctas_per_sm : 16));
+      P.grid = std::min<uint64_t>(pp.ntiles, (uint64_t)h->num_sms * per_sm);
+    } else {
+      // one tile per CTA; overlap of load / compute / store comes from 4+ resident CTAs per SM
+      pp.nbuf = 1;
+      P.smem = sizeof(double2) << t;
+      P.grid = pp.ntiles;
+      if (P.grid > 0x7fffffffull) { err = "grid too large: enable the persistent option"; return false; }
+    }
     P.amps = 1ull << __builtin_popcountll(live);
     passes.push_back(P);
     cur.clear();
@@ -873,7 +887,7 @@ int do_flush(dqe_t* h) {
   // partials: sized for the widest grid of a pass that ends in PROBS
   size_t need_part = 0;
   for (const PlannedPass& P : pl.passes)
-    if (!P.is_finish) need_part = std::max<size_t>(need_part, (size_t)P.grid * 2);
+    if (!P.is_finish) need_part = std::max<size_t>(need_part, (size_t)P.pp.ntiles * 2);
   if (int rc = ensure_partials(h, need_part)) return rc;
 
   for (PlannedPass& P : pl.passes) {
@@ -884,7 +898,7 @@ int do_flush(dqe_t* h) {
       h->stats[2]++; h->stats[5]++;
       continue;
     }
-    if (P.grid > 0x7fffffffull) return fail(h, DQE_EUNSUPPORTED, "grid too large");
+    if (P.pp.ntiles > (1ull << 40)) return fail(h, DQE_EUNSUPPORTED, "too many tiles");
     P.pp.state = h->state; P.pp.creg = h->creg; P.pp.partials = h->partials; P.pp.rec = h->rec;
     P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -963,7 +977,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->timing = false;
+  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -982,6 +996,10 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
     dqe_destroy(h);
     return fail(nullptr, err == cudaErrorMemoryAllocation ? DQE_ENOMEM : DQE_ECUDA, msg);
   };
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
+  }
   if (stream) h->stream = (cudaStream_t)stream;
   else {
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -1436,6 +1454,10 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->group = value ? 1 : 0;
   } else if (!strcmp(key, "tma")) {
     h->tma = value ? 1 : 0;
+  } else if (!strcmp(key, "persistent")) {
+    h->persistent = value ? 1 : 0;
+  } else if (!strcmp(key, "ctas_per_sm")) {
+    h->ctas_per_sm = (int)value;
   } else if (!strcmp(key, "threads")) {
     if (value != 64 && value != 128 && value != 256) return fail(h, DQE_EINVAL, "threads in {64, 128, 256}");
     h->threads = (int)value;

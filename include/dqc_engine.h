@@ -155,7 +155,8 @@ int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes);
  * 128 (default), 256), "min_run_bits" (log2 of the shortest contiguous run a tile may be built
  * from, default 5), "fuse" (0: one op per pass), "merge" (0: no host-side folding of axis-local
  * ops), "group" (0: no register-resident qubit-pair sweeps), "tma" (0: per-thread loads instead
- * of cp.async.bulk). */
+ * of cp.async.bulk), "persistent" (1: persistent CTAs with a double-buffered tile ring instead of
+ * one tile per CTA), "ctas_per_sm" (cap for the persistent grid). */
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates
