@@ -115,6 +115,11 @@ def oracle_shots(args_tuple):
     """CPU oracle port: `batch` noisy shots of the workload.  Only the cpu_baseline / reference legs
     call this (oracle/ is test infrastructure, never on the product path)."""
     circuit, batch, seed, offset = args_tuple
+    try:  # one BLAS / OpenMP thread per worker: parallelism comes from the process pool
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        pass
     from dqc_simulator_b200 import executor, experiment
     from oracle.numpy_engine import OracleEngine
 
@@ -129,15 +134,8 @@ def oracle_shots(args_tuple):
 
 
 def cpu_baseline(a):
-    try:
-        from threadpoolctl import threadpool_limits
-        ctx = threadpool_limits(limits=1)
-    except Exception:  # pragma: no cover
-        ctx = None
     oracle_shots((a.circuit, 2, 2024, 0))  # warm-up (imports, fixture parse)
     dt, _ = oracle_shots((a.circuit, a.cpu_shots, 2024, 0))
-    if ctx is not None:
-        ctx.restore_original_limits() if hasattr(ctx, "restore_original_limits") else None
     return {"value": a.cpu_shots / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{a.cpu_shots} shots of the same circuit+noise on the NumPy oracle (batched over shots), "
                       f"{dt:.1f} s on one host thread"}
@@ -153,7 +151,7 @@ def run_reference(a):
     import multiprocessing as mp
 
     cores = len(os.sched_getaffinity(0))
-    per = max(2, a.cpu_shots // 4)
+    per = max(2, a.cpu_shots)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         def step(i):
