@@ -679,11 +679,15 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 }
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
-                                              uint32_t T, int c0) {
-  const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
+// issue the bulk loads r0, r0+rstep, ... of one tile (a tile = 2^(t-c0) contiguous runs); the
+// issuing lanes of different warps work in parallel -- a single thread needs ~100 cycles per copy
+__device__ __forceinline__ void tma_expect(uint32_t bar_s, uint32_t T) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
-  for (uint32_t r = 0; r < nruns; ++r) {
+}
+__device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
+                                              uint32_t T, int c0, uint32_t r0, uint32_t rstep) {
+  const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
+  for (uint32_t r = r0; r < nruns; r += rstep) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             dst_s + r * run_bytes),
@@ -710,13 +714,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 
-  {  // stage the micro-program once per CTA
-    const int nw = pp.nops * (int)(sizeof(MicroOp) / 4);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(pp.ops);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < pp.nconsts; i += blockDim.x) s_consts[i] = __ldg(pp.consts + i);
-  }
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
   const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   uint64_t blk = blockIdx.x;
@@ -724,10 +721,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s + 8u));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (blk < pp.ntiles) {
-      const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
-      tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0);
-    }
+    if (blk < pp.ntiles) tma_expect(bar0_s, T);
+  }
+  __syncthreads();
+  const uint32_t wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool issuer = (threadIdx.x & 31u) == 0u;   // lane 0 of every warp issues its share of the copies
+  if (tma && issuer && blk < pp.ntiles) {
+    const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
+    tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0, wid, nwarps);
+  }
+  {  // stage the micro-program once per CTA -- after the first tile's loads are in flight, so the
+     // latency of these small global reads hides behind the HBM fetch
+    const int nw = pp.nops * (int)(sizeof(MicroOp) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(pp.ops);
+    uint4* dst = reinterpret_cast<uint4*>(s_ops);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < pp.nconsts; i += blockDim.x) s_consts[i] = __ldg(pp.consts + i);
   }
   __syncthreads();
 
@@ -746,8 +755,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
         // buffer b^1 was stored from at the end of the previous iteration: its reads must be done
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const uint64_t nbase = deposit(nxt & outer_mask, pp.outer_segs, pp.n_outer_segs);
+        tma_expect(bar0_s + 8u * (uint32_t)(b ^ 1), T);
         tma_load_tile(pp, pp.state + ((nxt >> pp.outer_bits) << pp.P) + nbase, tiles_s + (uint32_t)(b ^ 1) * T * 16u,
-                      bar0_s + 8u * (uint32_t)(b ^ 1), T, c0);
+                      bar0_s + 8u * (uint32_t)(b ^ 1), T, c0, 0u, 1u);
       }
       uint32_t done = 0;
       while (!done) {
@@ -815,8 +825,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
         // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (threadIdx.x == 0) {
-          for (uint32_t r = 0; r < nruns; ++r) {
+        const bool multi = nbuf == 1;   // persistent mode keeps every bulk group on thread 0
+        if (multi ? issuer : threadIdx.x == 0) {
+          for (uint32_t r = multi ? wid : 0u; r < nruns; r += multi ? nwarps : 1u) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
                              sp + ((uint64_t)pp.run_hi[r] << c0)),
                          "r"(tile_s + r * run_bytes), "r"(run_bytes)
@@ -844,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant
     }
   }
   // shared memory must stay valid until the last bulk store has read it
-  if (tma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (tma && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
