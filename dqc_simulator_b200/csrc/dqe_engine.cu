@@ -135,6 +135,8 @@ HostOp blank(dqe_t* h, int type) {
   return o;
 }
 bool try_merge(dqe_t* h, const HostOp& o, int axis);
+bool try_merge_pair(dqe_t* h, const HostOp& o);
+void diag_merge_at(dqe_t* h, size_t k);
 void push(dqe_t* h, HostOp& o) {
   // axis-local candidates: ket MAT1 / 1-bit DIAG, dm MAT2 / PAULI1 / 2-bit DIAG on (row, col) of one axis
   int axis = -1;
@@ -147,7 +149,9 @@ void push(dqe_t* h, HostOp& o) {
     }
   }
   if (axis >= 0 && try_merge(h, o, axis)) return;
+  if (h->formalism == DQE_KET && try_merge_pair(h, o)) return;
   h->queue.push_back(o);
+  if (h->formalism == DQE_KET && o.kind == 0 && o.m.type == OP_DIAG) diag_merge_at(h, h->queue.size() - 1);
 }
 
 // -------- lowering helpers (physical bits) --------------------------------------------------
@@ -310,6 +314,193 @@ bool try_merge(dqe_t* h, const HostOp& o, int axis) {
     if (touched_bits(e) & mine) return false;
   }
   return false;
+}
+
+
+// -------- ket peephole on qubit PAIRS: fused diagonal / controlled-phase runs ----------------------
+// The reference decomposes cp(t) a,b into p . CX . p . CX . p (qlib/macros4parsing.py:386-463), which
+// is a diagonal two-qubit gate.  Ops whose axes lie inside one pair {a, b} are composed into a 4x4
+// and re-emitted in the cheapest form (diagonal table / controlled 2x2 / dense); diagonal tables on
+// different bit sets are then merged up to 4 bits -- a whole run of controlled phases on one target
+// becomes ONE table look-up sweep that needs no tile bits at all.
+int op_axes(const HostOp& o, int* ax) {   // ket ops expressible on <= 2 axes; -1 = not mergeable
+  if (o.kind != 0 || o.pctrl2) return -1;
+  int n = 0;
+  auto add = [&](int a) { for (int i = 0; i < n; ++i) if (ax[i] == a) return; if (n < 3) ax[n] = a; ++n; };
+  if (o.m.type == OP_MAT1) {
+    if (__builtin_popcountll(o.pctrl) > 1) return -1;
+    add(o.m.b[0]);
+    if (o.pctrl) add(__builtin_ctzll(o.pctrl));
+  } else if (o.m.type == OP_MAT2) {
+    if (o.pctrl) return -1;
+    add(o.m.b[0]); add(o.m.b[1]);
+  } else if (o.m.type == OP_DIAG) {
+    if (o.m.nb > 2) return -1;
+    for (uint32_t i = 0; i < o.m.nb; ++i) add(o.m.b[i]);
+  } else return -1;
+  return n <= 2 ? n : -1;
+}
+
+// 4x4 of a queued ket op on the ordered pair (a, b), a = MSB
+bool pair_matrix(const dqe_t* h, const HostOp& o, int a, int b, cplx* M) {
+  for (int i = 0; i < 16; ++i) M[i] = 0.0;
+  auto cst = [&](int i) { return cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y); };
+  auto idx = [&](int va, int vb) { return va * 2 + vb; };
+  if (o.m.type == OP_MAT1) {
+    const int t = o.m.b[0];
+    const int c = o.pctrl ? __builtin_ctzll(o.pctrl) : -1;
+    if (t != a && t != b) return false;
+    if (c >= 0 && c != (t == a ? b : a)) return false;
+    for (int vo = 0; vo < 2; ++vo)          // value of the other axis
+      for (int r = 0; r < 2; ++r)
+        for (int q = 0; q < 2; ++q) {
+          cplx u = (c >= 0 && vo == 0) ? cplx(r == q ? 1.0 : 0.0) : cst(r * 2 + q);
+          const int row = t == a ? idx(r, vo) : idx(vo, r), col = t == a ? idx(q, vo) : idx(vo, q);
+          M[row * 4 + col] = u;
+        }
+    return true;
+  }
+  if (o.m.type == OP_MAT2) {
+    const int x = o.m.b[0], y = o.m.b[1];
+    static const int sw[4] = {0, 2, 1, 3};
+    if (x == a && y == b) { for (int i = 0; i < 16; ++i) M[i] = cst(i); return true; }
+    if (x == b && y == a) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M[i * 4 + j] = cst(sw[i] * 4 + sw[j]); return true; }
+    return false;
+  }
+  if (o.m.type == OP_DIAG) {
+    for (int va = 0; va < 2; ++va)
+      for (int vb = 0; vb < 2; ++vb) {
+        int t = 0;
+        for (uint32_t i = 0; i < o.m.nb; ++i) {
+          const int bit = o.m.b[i];
+          if (bit != a && bit != b) return false;
+          t |= (bit == a ? va : vb) << (o.m.nb - 1 - i);
+        }
+        M[idx(va, vb) * 5] = cst(t);
+      }
+    return true;
+  }
+  return false;
+}
+
+// rewrite `o` in place as the cheapest ket micro-op applying M on (a, b)
+void set_pair(dqe_t* h, HostOp& o, int a, int b, const cplx* M) {
+  const int pred = o.m.pred_bit;
+  const uint64_t live_after = o.live_after;
+  memset(&o.m, 0, sizeof(o.m));
+  o.pctrl = o.pctrl2 = 0;
+  o.m.pred_bit = pred;
+  o.live_after = live_after;
+  bool diag = true;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (i != j && !is_zero(M[i * 4 + j])) diag = false;
+  if (diag) {
+    const cplx d[4] = {M[0], M[5], M[10], M[15]};
+    o.m.type = OP_DIAG; o.m.nb = 2; o.m.b[0] = (uint8_t)a; o.m.b[1] = (uint8_t)b; o.need = 0;
+    o.m.c_off = add_consts(h, d, 4); o.nconst = 4;
+    return;
+  }
+  // controlled on a: rows/cols with a = 0 are the identity and do not mix with a = 1
+  bool ca = true, cb = true;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const cplx v = M[i * 4 + j];
+      const int ia = i >> 1, ja = j >> 1, ib = i & 1, jb = j & 1;
+      if (ia == 0 || ja == 0) { if (i == j ? !is_one(v) : !is_zero(v)) ca = false; }
+      if (ib == 0 || jb == 0) { if (i == j ? !is_one(v) : !is_zero(v)) cb = false; }
+    }
+  if (ca) {
+    const cplx u[4] = {M[10], M[11], M[14], M[15]};
+    o.m.type = OP_MAT1; o.m.nb = 1; o.m.b[0] = (uint8_t)b; o.pctrl = 1ull << a; o.need = 1ull << b;
+    o.m.c_off = add_consts(h, u, 4); o.nconst = 4;
+  } else if (cb) {
+    const cplx u[4] = {M[5], M[7], M[13], M[15]};
+    o.m.type = OP_MAT1; o.m.nb = 1; o.m.b[0] = (uint8_t)a; o.pctrl = 1ull << b; o.need = 1ull << a;
+    o.m.c_off = add_consts(h, u, 4); o.nconst = 4;
+  } else {
+    o.m.type = OP_MAT2; o.m.nb = 2; o.m.b[0] = (uint8_t)a; o.m.b[1] = (uint8_t)b;
+    o.need = (1ull << a) | (1ull << b);
+    o.m.c_off = add_consts(h, M, 16); o.nconst = 16;
+  }
+}
+
+bool try_merge_pair(dqe_t* h, const HostOp& o) {
+  if (!h->merge) return false;
+  int ax[3], ex[3];
+  const int n = op_axes(o, ax);
+  if (n < 1) return false;
+  uint64_t mine = 0;
+  for (int i = 0; i < n; ++i) mine |= 1ull << ax[i];
+  int depth = 0;
+  for (size_t k = h->queue.size(); k-- > 0 && depth < 96; ++depth) {
+    HostOp& e = h->queue[k];
+    if (e.kind != 0 || e.m.type == OP_PROBS) return false;
+    if (!(touched_bits(e) & mine)) continue;
+    if (e.m.pred_bit != o.m.pred_bit) return false;
+    const int m = op_axes(e, ex);
+    if (m < 1) return false;
+    int pr[4], np = 0;
+    for (int i = 0; i < m; ++i) pr[np++] = ex[i];
+    for (int i = 0; i < n; ++i) { bool seen = false; for (int j = 0; j < np; ++j) seen |= pr[j] == ax[i]; if (!seen) pr[np++] = ax[i]; }
+    if (np != 2) return false;   // np == 1 is the axis-local merge's job
+    cplx Mn[16], Mo[16], R[16];
+    if (!pair_matrix(h, o, pr[0], pr[1], Mn) || !pair_matrix(h, e, pr[0], pr[1], Mo)) return false;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        cplx acc = 0.0;
+        for (int l = 0; l < 4; ++l) acc += Mn[i * 4 + l] * Mo[l * 4 + j];
+        R[i * 4 + j] = acc;
+      }
+    set_pair(h, e, pr[0], pr[1], R);
+    h->stats[7]++;
+    if (e.m.type == OP_DIAG) diag_merge_at(h, k);
+    return true;
+  }
+  return false;
+}
+
+// queue[k] is a ket DIAG: fold it into an earlier DIAG when the union of their bits is <= 4 and
+// nothing in between mixes (targets) any of its bits -- diagonals commute with diagonals and controls
+void diag_merge_at(dqe_t* h, size_t k) {
+  if (!h->merge) return;
+  HostOp& d = h->queue[k];
+  uint64_t mine = 0;
+  for (uint32_t i = 0; i < d.m.nb; ++i) mine |= 1ull << d.m.b[i];
+  int depth = 0;
+  for (size_t j = k; j-- > 0 && depth < 96; ++depth) {
+    HostOp& e = h->queue[j];
+    if (e.kind != 0 || e.m.type == OP_PROBS) return;
+    if (e.m.type == OP_DIAG && e.m.pred_bit == d.m.pred_bit) {
+      uint8_t bits[8];
+      int nb = 0;
+      for (uint32_t i = 0; i < e.m.nb; ++i) bits[nb++] = e.m.b[i];
+      for (uint32_t i = 0; i < d.m.nb; ++i) { bool seen = false; for (int q = 0; q < nb; ++q) seen |= bits[q] == d.m.b[i]; if (!seen) bits[nb++] = d.m.b[i]; }
+      if (nb <= 4) {
+        cplx table[16];
+        for (int t = 0; t < (1 << nb); ++t) {
+          auto sub = [&](const HostOp& x) {
+            int idx = 0;
+            for (uint32_t i = 0; i < x.m.nb; ++i) {
+              int pos = 0;
+              while (bits[pos] != x.m.b[i]) ++pos;
+              idx |= ((t >> (nb - 1 - pos)) & 1) << (x.m.nb - 1 - i);
+            }
+            return cplx(h->cpool[x.m.c_off + idx].x, h->cpool[x.m.c_off + idx].y);
+          };
+          table[t] = sub(e) * sub(d);
+        }
+        e.m.nb = nb;
+        for (int i = 0; i < nb; ++i) e.m.b[i] = bits[i];
+        e.m.c_off = add_consts(h, table, 1 << nb); e.nconst = 1 << nb;
+        h->queue.erase(h->queue.begin() + k);
+        h->stats[7]++;
+        return;
+      }
+    }
+    if (e.need & mine) return;   // something mixes one of my bits: cannot move past it
+    if (e.m.type == OP_PAULI_SAMPLED || e.m.type == OP_COLLAPSE || e.m.type == OP_INJECT) {
+      if (touched_bits(e) & mine) return;
+    }
+  }
 }
 
 // ket-or-dm diagonal gate on k axes (first = MSB); dm table = d[r] conj(d[c]) over (rows, cols)
