@@ -498,6 +498,12 @@ __device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
     }
 }
 
+__device__ __forceinline__ double2 ldv(const double2* p) {   // ordered shared-memory read: stops ptxas from
+  double2 r;                                                  // hoisting a whole matrix into registers
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return r;
+}
+
 template <int ROLE>
 __device__ __forceinline__ void g_mat2(double2 (&v)[16], const double2* __restrict__ cs) {
   // matrix entries are re-read from shared memory (broadcast) per use: keeping 16 complex
@@ -700,7 +706,8 @@ __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double
 // the micro-program runs on the tile in buffer b, the TMA load of the CTA's next tile streams into
 // buffer b^1 and the bulk store of the previous tile drains -- the HBM pipe never idles behind the
 // shared-memory / FP64 work of a fused pass.
-__global__ void __launch_bounds__(kThreads, 2) k_tile_pass(const __grid_constant__ PassParams pp) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
   __shared__ double2 s_consts[kMaxConstsPerPass];

@@ -75,7 +75,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -1097,7 +1097,12 @@ int do_flush(dqe_t* h) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, h->stream));
     }
-    k_tile_pass<<<(unsigned)P.grid, h->threads, P.smem, h->stream>>>(P.pp);
+    switch (h->variant) {   // same code, different register budgets (launch bounds)
+      case 1: k_tile_pass<128, 3><<<(unsigned)P.grid, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+      case 2: k_tile_pass<128, 2><<<(unsigned)P.grid, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+      case 3: k_tile_pass<64, 5><<<(unsigned)P.grid, 64, P.smem, h->stream>>>(P.pp); break;
+      default: k_tile_pass<256, 2><<<(unsigned)P.grid, h->threads, P.smem, h->stream>>>(P.pp); break;
+    }
     if (h->timing) {
       CK(cudaEventRecord(e1, h->stream));
       h->ev_pool.push_back(std::make_pair(e0, e1));
@@ -1168,7 +1173,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->timing = false;
+  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1206,11 +1211,17 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   }
   if ((e = cudaMalloc(&h->creg, batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
   if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
-  if ((e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
-    return bail("cudaFuncSetAttribute", e);
-  if ((e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-    return bail("cudaFuncSetAttribute(carveout)", e);
+  {
+    const void* variants[4] = {(const void*)k_tile_pass<256, 2>, (const void*)k_tile_pass<128, 3>,
+                               (const void*)k_tile_pass<128, 2>, (const void*)k_tile_pass<64, 5>};
+    for (const void* fn : variants) {
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute", e);
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(carveout)", e);
+    }
+  }
   if ((e = cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMemsetAsync(h->creg, 0, batch * sizeof(uint64_t), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMemsetAsync(h->rec, 0, batch * sizeof(MeasRec), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -1645,6 +1656,9 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->group = value ? 1 : 0;
   } else if (!strcmp(key, "tma")) {
     h->tma = value ? 1 : 0;
+  } else if (!strcmp(key, "variant")) {
+    if (value < 0 || value > 3) return fail(h, DQE_EINVAL, "variant in [0, 3]");
+    h->variant = (int)value;
   } else if (!strcmp(key, "persistent")) {
     h->persistent = value ? 1 : 0;
   } else if (!strcmp(key, "ctas_per_sm")) {
