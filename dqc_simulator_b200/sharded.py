@@ -1,0 +1,277 @@
+"""State-vector sharded over GPUs by its high-order qubits (BASELINE config 5).
+
+One process per GPU.  A register of ``n`` logical axes is split over ``R = 2^g`` ranks: every rank
+holds ``2^(n-g)`` amplitudes in its own engine (all ``n-g`` local axes live), the ``g`` *global*
+axes are the bits of the rank id.  What needs communication and what does not:
+
+* gate on local axes only ............................ local pass, no communication
+* diagonal gate / phase touching a global axis ....... the rank's bit selects a sub-table: local, no comm
+* controlled gate whose CONTROL is global ............ ranks with bit 0 skip, ranks with bit 1 apply: no comm
+* gate that MIXES (targets) a global axis ............ swap that global axis with a free local axis:
+  pairwise half-shard exchange between ranks r and r ^ (1 << j) (NCCL send/recv over NVLink), then the
+  gate is local.  The axis stays local afterwards (slot map), so a QFT localises each axis about once.
+* measurement ........................................ local partial probabilities -> all_reduce(sum) ->
+  every rank draws the same Philox number -> local collapse.
+
+The local backend is any object with ``apply_1q / apply_2q / apply_ctrl_1q / apply_diag / sync`` and a
+``buffer()`` returning the flat complex128 torch tensor of the shard (``GpuShard`` below wraps
+:class:`dqc_simulator_b200.engine.Engine`; the CPU gloo tests use a NumPy stand-in).
+"""
+import numpy as np
+
+
+class GpuShard:
+    """Local shard on one B200: an Engine with every local axis live from the start."""
+
+    def __init__(self, m, device, first_rank, seed=0):
+        from .engine import Engine
+
+        self.m = m
+        self.eng = Engine("ket", m, 1, seed=seed, device=device)
+        for a in range(m):
+            self.eng.alloc_axis(a)
+        self.eng.sync()
+        if not first_rank:          # |0...0> lives on rank 0 only
+            self.buffer()[0] = 0
+            self._done()
+        self.apply_1q = self.eng.apply_1q
+        self.apply_2q = self.eng.apply_2q
+        self.apply_ctrl_1q = self.eng.apply_ctrl_1q
+        self.apply_diag = self.eng.apply_diag
+
+    def buffer(self):
+        return self.eng.state_tensor()
+
+    def sync(self):
+        import torch
+
+        self.eng.sync()
+        torch.cuda.synchronize()
+
+    def _done(self):
+        import torch
+
+        torch.cuda.synchronize()   # torch ops run on torch's stream, the engine on its own
+
+    def scale(self, s):
+        self.sync()
+        self.buffer().mul_(s)
+        self._done()
+
+    def norm2_by_bit(self, axis):
+        """(sum |amp|^2 over axis bit = 0, over bit = 1) of the local shard."""
+        self.sync()
+        b = self.buffer().view(-1, 2, 2 ** axis)
+        p = (b.real ** 2 + b.imag ** 2).sum(dim=(0, 2))
+        return float(p[0]), float(p[1])
+
+    def project(self, axis, outcome, scale):
+        self.sync()
+        b = self.buffer().view(-1, 2, 2 ** axis)
+        b[:, 1 - outcome, :] = 0
+        b[:, outcome, :] *= scale
+        self._done()
+
+
+class ShardedKet:
+    def __init__(self, n, shard, rank, world, group=None, seed=0):
+        g = int(round(np.log2(world)))
+        if 2 ** g != world:
+            raise ValueError("world size must be a power of two")
+        if g > n - 3:
+            raise ValueError("need at least 3 local axes")
+        self.n, self.g, self.m = n, g, n - g
+        self.rank, self.world, self.group = rank, world, group
+        self.shard = shard
+        self.max_qubits = n
+        self.formalism = 0
+        self.batch = 1
+        self.slot = list(range(n))       # logical axis -> physical slot; slots >= m are rank bits
+        self.live = []
+        self.exchanges = 0
+        self.exchanged_bytes = 0
+        self.exchange_seconds = 0.0
+        self._seed, self._draw = int(seed), 0
+
+    # ------------------------------------------------------------------ slots
+    def _is_global(self, a):
+        return self.slot[a] >= self.m
+
+    def _rank_bit(self, a):
+        return (self.rank >> (self.slot[a] - self.m)) & 1
+
+    def _axis_at(self, slot):
+        return self.slot.index(slot)
+
+    def _localise(self, a, busy):
+        """Make logical axis ``a`` local by swapping its global slot with a free local slot."""
+        if not self._is_global(a):
+            return
+        busy_slots = {self.slot[x] for x in busy}
+        L = next(s for s in range(self.m - 1, -1, -1) if s not in busy_slots)
+        j = self.slot[a] - self.m
+        self._exchange(j, L)
+        other = self._axis_at(L)
+        self.slot[other], self.slot[a] = self.slot[a], L
+
+    def _exchange(self, j, L):
+        """new[rank bit j = x, local bit L = y] = old[rank bit j = y, local bit L = x]."""
+        import torch
+        import torch.distributed as dist
+
+        import time
+
+        self.shard.sync()
+        t0 = time.perf_counter()
+        buf = self.shard.buffer()
+        mybit = (self.rank >> j) & 1
+        partner = self.rank ^ (1 << j)
+        view = buf.view(-1, 2, 2 ** L)[:, 1 - mybit, :]
+        send = torch.view_as_real(view.contiguous())
+        recv = torch.empty_like(send)
+        ops = [dist.P2POp(dist.isend, send, partner, group=self.group),
+               dist.P2POp(dist.irecv, recv, partner, group=self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        view.copy_(torch.view_as_complex(recv))
+        if buf.is_cuda:
+            torch.cuda.synchronize()
+        self.exchanges += 1
+        self.exchanged_bytes += send.numel() * 8
+        self.exchange_seconds += time.perf_counter() - t0
+
+    # ------------------------------------------------------------------ register
+    def alloc_axis(self, axis=-1):
+        if axis < 0:
+            axis = min(a for a in range(self.n) if a not in self.live)
+        self.live.append(axis)
+        return axis
+
+    def free_axis(self, axis):
+        raise NotImplementedError("sharded registers keep every axis (no comm-qubit churn in config 5)")
+
+    def set_predicate(self, bit):
+        if bit >= 0:
+            raise NotImplementedError("predicated ops need per-shot registers; sharded mode is single-shot")
+
+    # ------------------------------------------------------------------ gates
+    def apply_1q(self, axis, m):
+        m = np.asarray(m, dtype=complex).reshape(2, 2)
+        if m[0, 1] == 0 and m[1, 0] == 0:
+            return self.apply_diag([axis], [m[0, 0], m[1, 1]])
+        self._localise(axis, [axis])
+        self.shard.apply_1q(self.slot[axis], m)
+
+    def apply_ctrl_1q(self, c, t, m):
+        m = np.asarray(m, dtype=complex).reshape(2, 2)
+        if m[0, 1] == 0 and m[1, 0] == 0:
+            return self.apply_diag([c, t], [1, 1, m[0, 0], m[1, 1]])
+        self._localise(t, [c, t])
+        if self._is_global(c):
+            if self._rank_bit(c):
+                self.shard.apply_1q(self.slot[t], m)
+        else:
+            self.shard.apply_ctrl_1q(self.slot[c], self.slot[t], m)
+
+    def apply_2q(self, a, b, m):
+        m = np.asarray(m, dtype=complex).reshape(4, 4)
+        off = m - np.diag(np.diag(m))
+        if not off.any():
+            return self.apply_diag([a, b], np.diag(m))
+        if not m[:2, 2:].any() and not m[2:, :2].any() and np.array_equal(m[:2, :2], np.eye(2)):
+            return self.apply_ctrl_1q(a, b, m[2:, 2:])
+        self._localise(a, [a, b])
+        self._localise(b, [a, b])
+        self.shard.apply_2q(self.slot[a], self.slot[b], m)
+
+    def apply_diag(self, axes, d):
+        axes = list(axes)
+        k = len(axes)
+        d = np.asarray(d, dtype=complex).reshape((2,) * k)
+        local_axes = []
+        index = []
+        for a in axes:
+            if self._is_global(a):
+                index.append(self._rank_bit(a))
+            else:
+                index.append(slice(None))
+                local_axes.append(self.slot[a])
+        sub = d[tuple(index)]
+        if not local_axes:
+            if sub != 1:
+                self.shard.scale(complex(sub))
+            return
+        self.shard.apply_diag(local_axes, np.asarray(sub).reshape(-1))
+
+    def depolarize(self, axes, p):
+        if p:
+            raise NotImplementedError("sharded mode is the ideal state-vector configuration")
+
+    # ------------------------------------------------------------------ measurement
+    def measure(self, axis, creg_bit=None, forced=-1, discard=False, flip_prob=0.0):
+        """Z-basis measurement across shards; returns the outcome (identical on every rank)."""
+        import torch
+        import torch.distributed as dist
+
+        from .philox_host import shot_uniforms
+
+        if discard or flip_prob:
+            raise NotImplementedError
+        if self._is_global(axis):
+            self.shard.sync()
+            b = self.shard.buffer()
+            tot = float((b.real ** 2 + b.imag ** 2).sum())
+            p = [tot, 0.0] if self._rank_bit(axis) == 0 else [0.0, tot]
+        else:
+            p = list(self.shard.norm2_by_bit(self.slot[axis]))
+        t = torch.tensor(p, dtype=torch.float64, device=self.shard.buffer().device)
+        dist.all_reduce(t, group=self.group)
+        p0, p1 = float(t[0]), float(t[1])
+        u, _ = shot_uniforms(self._seed, 0, self._draw)
+        self._draw += 1
+        m = int(forced) if forced is not None and forced >= 0 else int(u * (p0 + p1) < p1)
+        pm = p1 if m else p0
+        scale = 1.0 / np.sqrt(pm) if pm > 0 else 0.0
+        if self._is_global(axis):
+            self.shard.scale(scale if self._rank_bit(axis) == m else 0.0)
+        else:
+            self.shard.project(self.slot[axis], m, scale)
+        return m
+
+    # ------------------------------------------------------------------ read-out
+    def flush(self):
+        self.shard.sync()
+
+    def sync(self):
+        self.shard.sync()
+
+    def norm2(self):
+        import torch
+        import torch.distributed as dist
+
+        self.shard.sync()
+        b = self.shard.buffer()
+        t = (b.real ** 2 + b.imag ** 2).sum().reshape(1).to(torch.float64)
+        dist.all_reduce(t, group=self.group)
+        return float(t[0])
+
+    def logical_index_of(self, local_index):
+        """Logical basis-state index (axis a = bit a) of local amplitude ``local_index`` on this rank."""
+        phys = local_index | (self.rank << self.m)
+        out = 0
+        for a in range(self.n):
+            out |= ((phys >> self.slot[a]) & 1) << a
+        return out
+
+    def gather_logical(self):
+        """Full state in logical order on every rank (tests only: 2^n amplitudes)."""
+        import torch
+        import torch.distributed as dist
+
+        self.shard.sync()
+        loc = torch.view_as_real(self.shard.buffer().clone()).contiguous()
+        parts = [torch.empty_like(loc) for _ in range(self.world)]
+        dist.all_gather(parts, loc, group=self.group)
+        phys = torch.view_as_complex(torch.cat(parts)).cpu().numpy()     # index = rank << m | local
+        perm = [self.n - 1 - self.slot[a] for a in range(self.n - 1, -1, -1)]
+        return phys.reshape((2,) * self.n).transpose(perm).reshape(-1)

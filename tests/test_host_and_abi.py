@@ -154,3 +154,12 @@ def test_oracle_reproduces_reference_printed_fidelities():
         ex = executor.DQCExecutor(ops, experiment.c2_hardware(noisy=True), be).run()
         f = be.fidelity_ket(ex.axes_of(data), ideal, 0)
         assert abs(f - want) / want < 1e-3, (circuit, f, want)
+
+
+def test_host_philox_matches_oracle_stream():
+    from dqc_simulator_b200 import philox_host
+
+    for seed, shot, draw in [(0, 0, 0), (2024, 7, 3), (2 ** 63 + 5, 2 ** 33 + 1, 2 ** 32 + 9)]:
+        u, u2 = philox.shot_uniforms(seed, np.array([shot]), draw)
+        hu, hu2 = philox_host.shot_uniforms(seed, shot, draw)
+        assert hu == float(u[0]) and hu2 == float(u2[0])
