@@ -91,6 +91,7 @@ class ShardedKet:
         self.exchanges = 0
         self.exchanged_bytes = 0
         self.exchange_seconds = 0.0
+        self._pending = 1.0 + 0.0j      # rank-local scalar phase not yet applied (folded into the next table)
         self._seed, self._draw = int(seed), 0
 
     # ------------------------------------------------------------------ slots
@@ -121,6 +122,7 @@ class ShardedKet:
 
         import time
 
+        self._apply_pending()       # the pending phase belongs to the data that is about to move
         self.shard.sync()
         t0 = time.perf_counter()
         buf = self.shard.buffer()
@@ -198,10 +200,13 @@ class ShardedKet:
                 local_axes.append(self.slot[a])
         sub = d[tuple(index)]
         if not local_axes:
-            if sub != 1:
-                self.shard.scale(complex(sub))
+            self._pending *= complex(sub)     # pure rank-dependent phase: no pass over the shard
             return
-        self.shard.apply_diag(local_axes, np.asarray(sub).reshape(-1))
+        table = np.asarray(sub).reshape(-1)
+        if self._pending != 1:
+            table = table * self._pending
+            self._pending = 1.0 + 0.0j
+        self.shard.apply_diag(local_axes, table)
 
     def depolarize(self, axes, p):
         if p:
@@ -217,6 +222,7 @@ class ShardedKet:
 
         if discard or flip_prob:
             raise NotImplementedError
+        self._apply_pending()
         if self._is_global(axis):
             self.shard.sync()
             b = self.shard.buffer()
@@ -239,17 +245,23 @@ class ShardedKet:
         return m
 
     # ------------------------------------------------------------------ read-out
+    def _apply_pending(self):
+        if self._pending != 1:
+            self.shard.scale(self._pending)
+            self._pending = 1.0 + 0.0j
+
     def flush(self):
+        self._apply_pending()
         self.shard.sync()
 
     def sync(self):
-        self.shard.sync()
+        self.flush()
 
     def norm2(self):
         import torch
         import torch.distributed as dist
 
-        self.shard.sync()
+        self.flush()
         b = self.shard.buffer()
         t = (b.real ** 2 + b.imag ** 2).sum().reshape(1).to(torch.float64)
         dist.all_reduce(t, group=self.group)
@@ -268,7 +280,7 @@ class ShardedKet:
         import torch
         import torch.distributed as dist
 
-        self.shard.sync()
+        self.flush()
         loc = torch.view_as_real(self.shard.buffer().clone()).contiguous()
         parts = [torch.empty_like(loc) for _ in range(self.world)]
         dist.all_gather(parts, loc, group=self.group)

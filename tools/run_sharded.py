@@ -1,6 +1,6 @@
 """BASELINE config 5: GHZ-n / QFT-n state vector sharded over N GPUs by its high-order qubits.
 Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P tools/run_sharded.py --n 30 [--circuit qft|ghz]
+        --master-port P tools/run_sharded.py --qubits 30 [--circuit qft|ghz]
 Self-checking (norm, closed-form amplitudes); rank 0 prints one JSON line."""
 import argparse
 import json
@@ -22,7 +22,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=30)
+    ap.add_argument("--qubits", dest="n", type=int, default=30)
     ap.add_argument("--circuit", default="qft")
     ap.add_argument("--reps", type=int, default=2)
     a = ap.parse_args()
