@@ -241,6 +241,51 @@ __device__ __forceinline__ void op_diag(double2* tile, uint32_t T, const MicroOp
   }
 }
 
+
+// a run of consecutive diagonal ops applied in ONE sweep: per amplitude one table look-up and one
+// complex multiply per op, one shared-memory round trip for the whole run (the controlled-phase
+// ladders of a QFT collapse into a few such sweeps).  Kept out of line so that its registers do not
+// weigh on the group-sweep path.
+struct DiagPrep {
+  int32_t c_off, nl, on;
+  uint32_t fixed;
+  uint32_t m0, m1, m2, m3;     // single-bit masks of the tile-local bits (0 when unused)
+  uint32_t s0, s1, s2, s3;     // their weights in the table index
+};
+constexpr int kMaxDiagRun = 16;
+
+__device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const MicroOp* ops, int count,
+                                         const double2* s_consts, uint64_t base, uint64_t cw, DiagPrep* prep) {
+  if ((int)threadIdx.x < count) {
+    const MicroOp& op = ops[threadIdx.x];
+    DiagPrep d;
+    d.c_off = op.c_off; d.nl = 0; d.fixed = 0;
+    d.on = !(op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull));
+    uint32_t mk[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};
+    const int nb = op.nb;
+    for (int s = 0; s < nb; ++s) {
+      const uint32_t w = 1u << (nb - 1 - s);
+      if (op.b[s] >= kOuter) { if ((base >> (op.b[s] - kOuter)) & 1ull) d.fixed |= w; }
+      else { mk[d.nl] = 1u << op.b[s]; sh[d.nl] = w; ++d.nl; }
+    }
+    d.m0 = mk[0]; d.m1 = mk[1]; d.m2 = mk[2]; d.m3 = mk[3];
+    d.s0 = sh[0]; d.s1 = sh[1]; d.s2 = sh[2]; d.s3 = sh[3];
+    prep[threadIdx.x] = d;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+    double2 v = tile[i];
+    for (int k = 0; k < count; ++k) {
+      const DiagPrep& d = prep[k];
+      if (!d.on) continue;
+      const uint32_t idx = d.fixed + ((i & d.m0) ? d.s0 : 0u) + ((i & d.m1) ? d.s1 : 0u) +
+                           ((i & d.m2) ? d.s2 : 0u) + ((i & d.m3) ? d.s3 : 0u);
+      v = cmul(v, s_consts[d.c_off + idx]);
+    }
+    tile[i] = v;
+  }
+}
+
 __device__ __forceinline__ void op_pauli1(double2* tile, uint32_t T, const MicroOp& op) {
   const int jr = op.b[0], jc = op.b[1];
   const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
@@ -295,11 +340,12 @@ __device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const Micro
   }
 }
 
+template <int FORM>
 __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                          uint64_t base, uint64_t blk, double* red) {
   double a0 = 0.0, a1 = 0.0;
   const int abit = op.aux;   // physical (column) bit of the measured axis
-  if (pp.formalism == 0) {
+  if constexpr (FORM == 0) {
     // b[0] = tile-local position of the axis bit, or kOuter + physical when it is fixed for the tile
     const int jb = op.b[0];
     if (jb >= kOuter) {
@@ -353,6 +399,7 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
   }
 }
 
+template <int FORM>
 __device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                             uint64_t shot) {
   const MeasRec r = pp.rec[shot];
@@ -360,7 +407,7 @@ __device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const Mic
   const double sc = r.scale;
   const bool discard = op.flags & 1;
   const double2 zero = make_double2(0.0, 0.0);
-  if (pp.formalism == 0) {
+  if constexpr (FORM == 0) {
     const int j = op.b[0];
     for (uint32_t p = threadIdx.x; p < (T >> 1); p += blockDim.x) {
       const uint32_t i0 = ins0(p, j), i1 = i0 | (1u << j);
@@ -398,9 +445,10 @@ __device__ __forceinline__ void op_trace(double2* tile, uint32_t T, const MicroO
   }
 }
 
+template <int FORM>
 __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                           const double2* cs, uint64_t shot) {
-  if (pp.formalism == 0) {
+  if constexpr (FORM == 0) {
     const int ja = op.b[0], jb = op.b[1];
     const int jlo = ja < jb ? ja : jb, jhi = ja < jb ? jb : ja;
     int choice = 0;
@@ -706,13 +754,14 @@ __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double
 // the micro-program runs on the tile in buffer b, the TMA load of the CTA's next tile streams into
 // buffer b^1 and the bulk store of the previous tile drains -- the HBM pipe never idles behind the
 // shared-memory / FP64 work of a fused pass.
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int FORM>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
   __shared__ double2 s_consts[kMaxConstsPerPass];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ DiagPrep s_diag[kMaxDiagRun];
 
   const uint32_t T = 1u << pp.t;
   const int c0 = pp.tile_segs[0].len;
@@ -798,31 +847,50 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       const MicroOp& op = s_ops[o];
       if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
       const double2* cs = s_consts + op.c_off;
-      switch (op.type) {
-        case OP_GROUP:
-          run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
-          o += op.aux;
-          break;
-        case OP_MAT1:
-          if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
-          break;
-        case OP_MAT1X2: {
-          const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
-          if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
-          break;
+      if constexpr (FORM == 0) {   // ---- ket micro-ops
+        switch (op.type) {
+          case OP_MAT1:
+            if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
+            break;
+          case OP_MAT2:
+            if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
+            break;
+          case OP_DIAG: {
+            int run = 1;
+            while (o + run < pp.nops && run < kMaxDiagRun && s_ops[o + run].type == OP_DIAG) ++run;
+            if (run == 1) op_diag(tile, T, op, cs, base);
+            else { op_diag_run(tile, T, &s_ops[o], run, s_consts, base, cw, s_diag); o += run - 1; }
+            break;
+          }
+          case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
+          case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, shot); break;
+          case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
+          case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
+          default: break;
         }
-        case OP_MAT2:
-          if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
-          break;
-        case OP_DIAG: op_diag(tile, T, op, cs, base); break;
-        case OP_PAULI1: op_pauli1(tile, T, op); break;
-        case OP_DEPOL2: op_depol2(tile, T, op); break;
-        case OP_PROBS: op_probs(tile, T, op, pp, base, blk, s_red); break;
-        case OP_COLLAPSE: op_collapse(tile, T, op, pp, shot); break;
-        case OP_TRACE: op_trace(tile, T, op); break;
-        case OP_INJECT: op_inject(tile, T, op, pp, cs, shot); break;
-        case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
-        default: break;
+      } else {                     // ---- density-matrix micro-ops
+        switch (op.type) {
+          case OP_GROUP:
+            run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
+            o += op.aux;
+            break;
+          case OP_MAT1X2: {
+            const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
+            if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
+            break;
+          }
+          case OP_MAT2:
+            if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
+            break;
+          case OP_DIAG: op_diag(tile, T, op, cs, base); break;
+          case OP_PAULI1: op_pauli1(tile, T, op); break;
+          case OP_DEPOL2: op_depol2(tile, T, op); break;
+          case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
+          case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, shot); break;
+          case OP_TRACE: op_trace(tile, T, op); break;
+          case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
+          default: break;
+        }
       }
       __syncthreads();
     }

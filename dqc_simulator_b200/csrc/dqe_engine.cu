@@ -1097,11 +1097,21 @@ int do_flush(dqe_t* h) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, h->stream));
     }
-    switch (h->variant) {   // same code, different register budgets (launch bounds)
-      case 1: k_tile_pass<128, 3><<<(unsigned)P.grid, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-      case 2: k_tile_pass<128, 2><<<(unsigned)P.grid, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-      case 3: k_tile_pass<64, 5><<<(unsigned)P.grid, 64, P.smem, h->stream>>>(P.pp); break;
-      default: k_tile_pass<256, 2><<<(unsigned)P.grid, h->threads, P.smem, h->stream>>>(P.pp); break;
+    // one kernel per formalism (their micro-op sets are disjoint enough that sharing one
+    // interpreter costs registers); variants = same code under different register budgets
+    const unsigned gr = (unsigned)P.grid;
+    if (h->formalism == DQE_KET) {
+      switch (h->variant) {
+        case 1: k_tile_pass<128, 3, 0><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+        case 2: k_tile_pass<128, 2, 0><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+        default: k_tile_pass<256, 2, 0><<<gr, h->threads, P.smem, h->stream>>>(P.pp); break;
+      }
+    } else {
+      switch (h->variant) {
+        case 1: k_tile_pass<128, 3, 1><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+        case 2: k_tile_pass<128, 2, 1><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
+        default: k_tile_pass<256, 2, 1><<<gr, h->threads, P.smem, h->stream>>>(P.pp); break;
+      }
     }
     if (h->timing) {
       CK(cudaEventRecord(e1, h->stream));
@@ -1212,8 +1222,9 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   if ((e = cudaMalloc(&h->creg, batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
   if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
   {
-    const void* variants[4] = {(const void*)k_tile_pass<256, 2>, (const void*)k_tile_pass<128, 3>,
-                               (const void*)k_tile_pass<128, 2>, (const void*)k_tile_pass<64, 5>};
+    const void* variants[6] = {(const void*)k_tile_pass<256, 2, 0>, (const void*)k_tile_pass<128, 3, 0>,
+                               (const void*)k_tile_pass<128, 2, 0>, (const void*)k_tile_pass<256, 2, 1>,
+                               (const void*)k_tile_pass<128, 3, 1>, (const void*)k_tile_pass<128, 2, 1>};
     for (const void* fn : variants) {
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
         return bail("cudaFuncSetAttribute", e);
@@ -1657,7 +1668,7 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "tma")) {
     h->tma = value ? 1 : 0;
   } else if (!strcmp(key, "variant")) {
-    if (value < 0 || value > 3) return fail(h, DQE_EINVAL, "variant in [0, 3]");
+    if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "variant in [0, 2]");
     h->variant = (int)value;
   } else if (!strcmp(key, "persistent")) {
     h->persistent = value ? 1 : 0;

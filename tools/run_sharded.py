@@ -37,9 +37,11 @@ def main():
     for rep in range(a.reps):
         shard = GpuShard(a.n - g, local, rank == 0)
         sk = ShardedKet(a.n, shard, rank, world)
+        shard.eng.time_passes(True)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         ex = executor.DQCExecutor(ops, dqc, sk).run()
+        t_host = time.perf_counter() - t0
         sk.sync()
         dist.barrier(); torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -59,10 +61,12 @@ def main():
             err = max(err, abs(int(cnt[0]) - 2))
         t = torch.tensor([err, dt, sk.exchange_seconds], dtype=torch.float64, device=buf.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pass_ms, n_pass, amps = shard.eng.pass_time()
         st = shard.eng.stats()
         res = dict(circuit=a.circuit, n=a.n, n_gpus=world, seconds=float(t[1]), max_abs_err=float(t[0]),
                    norm=norm, exchanges=sk.exchanges, exchange_bytes_per_rank=sk.exchanged_bytes,
-                   exchange_seconds=float(t[2]),
+                   exchange_seconds=float(t[2]), host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
+                   micro_ops=st["micro_ops"], pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
                    nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges else None,
                    passes_per_rank=st["passes"], api_ops=st["api_ops"], shard_bytes=(2 ** (a.n - g)) * 16,
                    gate_updates_per_s=len([1 for _ in range(1)]) and (sum(len(s) for sl in ops.values() for s in sl) / float(t[1])))
