@@ -741,6 +741,7 @@ __device__ __forceinline__ void tma_expect(uint32_t bar_s, uint32_t T) {
 __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
                                               uint32_t T, int c0, uint32_t r0, uint32_t rstep) {
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
+#pragma unroll 4
   for (uint32_t r = r0; r < nruns; r += rstep) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -902,6 +903,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         __syncthreads();
         const bool multi = nbuf == 1;   // persistent mode keeps every bulk group on thread 0
         if (multi ? issuer : threadIdx.x == 0) {
+#pragma unroll 4
           for (uint32_t r = multi ? wid : 0u; r < nruns; r += multi ? nwarps : 1u) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
                              sp + ((uint64_t)pp.run_hi[r] << c0)),
