@@ -1007,6 +1007,22 @@ __global__ void k_histogram(const HistParams hp) {
   atomicAdd(hp.bins + idx, 1ull);
 }
 
+// ------------------------------------------------------------------------------------------
+// fused gate + NVLink transfer for a state vector sharded over GPUs: 2x2 gate on a GLOBAL axis.
+// lo = shard holding the axis-bit-0 amplitudes, hi = the bit-1 shard (one of them is the partner's
+// memory, mapped through CUDA IPC).  This rank handles indices [begin, end) of BOTH shards.
+__global__ void __launch_bounds__(256) k_peer_1q(double2* __restrict__ lo, double2* __restrict__ hi, uint64_t begin,
+                                                 uint64_t end, uint64_t ctrl_mask, double2 m00, double2 m01,
+                                                 double2 m10, double2 m11) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    if ((i & ctrl_mask) != ctrl_mask) continue;
+    const double2 a = lo[i], b = hi[i];
+    lo[i] = cfma(m01, b, cmul(m00, a));
+    hi[i] = cfma(m11, b, cmul(m10, a));
+  }
+}
+
 // reduced density matrix / fidelity of <= 5 axes.  `rest` enumerates the live bits that are
 // traced over (dense index -> physical offset through segs).
 struct ReadoutParams {

@@ -1650,6 +1650,60 @@ int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes) {
   return 0;
 }
 
+int dqe_ipc_export(dqe_t* h, void* handle64) {
+  if (int rc = check_ready(h)) return rc;
+  NEED_DEVICE(h);
+  if (!handle64) return fail(h, DQE_EINVAL, "ipc_export: null");
+  if (!h->own_state) return fail(h, DQE_EUNSUPPORTED, "ipc_export: only engine-owned (cudaMalloc) state buffers");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, h->state));
+  memcpy(handle64, &hd, 64);
+  return 0;
+}
+
+int dqe_ipc_open(dqe_t* h, const void* handle64, void** peer_state) {
+  if (int rc = check_ready(h)) return rc;
+  NEED_DEVICE(h);
+  if (!handle64 || !peer_state) return fail(h, DQE_EINVAL, "ipc_open: null");
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  CK(cudaIpcOpenMemHandle(peer_state, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int dqe_ipc_close(dqe_t* h, void* peer_state) {
+  if (int rc = check_ready(h)) return rc;
+  NEED_DEVICE(h);
+  CK(cudaSetDevice(h->device));
+  CK(cudaIpcCloseMemHandle(peer_state));
+  return 0;
+}
+
+int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* m, int ctrl_axis) {
+  if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
+  if (h->formalism != DQE_KET || h->batch != 1) return fail(h, DQE_EUNSUPPORTED, "peer_1q: single-shot ket only");
+  if (!peer_state || !m || (my_bit | 1) != 1 || (half | 1) != 1) return fail(h, DQE_EINVAL, "peer_1q: bad argument");
+  if (h->live_axes != (h->nmax >= 64 ? ~0ull : ((1ull << h->nmax) - 1ull)))
+    return fail(h, DQE_EINVAL, "peer_1q: every local axis must be live");
+  if (ctrl_axis >= h->nmax) return fail(h, DQE_EINVAL, "peer_1q: control axis out of range");
+  const uint64_t n = 1ull << h->P, mid = n >> 1;
+  double2* lo = my_bit == 0 ? h->state : (double2*)peer_state;
+  double2* hi = my_bit == 0 ? (double2*)peer_state : h->state;
+  const uint64_t begin = half ? mid : 0, end = half ? n : mid;
+  const uint64_t cm = ctrl_axis >= 0 ? (1ull << ctrl_axis) : 0ull;
+  CK(cudaSetDevice(h->device));
+  k_peer_1q<<<h->num_sms * 8, 256, 0, h->stream>>>(lo, hi, begin, end, cm, make_double2(m[0], m[1]),
+                                                    make_double2(m[2], m[3]), make_double2(m[4], m[5]),
+                                                    make_double2(m[6], m[7]));
+  h->stats[2]++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (!h || !key) return DQE_EINVAL;
   if (int rc = do_flush(h)) return rc;

@@ -62,6 +62,11 @@ ABI = {
     "dqe_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, _c_dbl_p, ctypes.c_uint64]),
     "dqe_state_ptr": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                      ctypes.POINTER(ctypes.c_int64)]),
+    "dqe_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dqe_ipc_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "dqe_ipc_close": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dqe_peer_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p,
+                                   ctypes.c_int]),
     "dqe_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "dqe_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "dqe_reset_stats": (ctypes.c_int, [ctypes.c_void_p]),
@@ -334,6 +339,24 @@ class Engine:
 
         t = torch.as_tensor(_Holder(), device=f"cuda:{self.device}")
         return torch.view_as_complex(t.view(n, 2))
+
+    # ------------------------------------------------------------------ peer memory (sharded kets)
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._lib.dqe_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        self._ck(self._lib.dqe_ipc_open(self._h, ctypes.c_char_p(handle), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(self._lib.dqe_ipc_close(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_1q(self, peer_ptr, my_bit, half, m, ctrl_axis=-1):
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2, 2))
+        self._ck(self._lib.dqe_peer_1q(self._h, ctypes.c_void_p(peer_ptr), int(my_bit), int(half), p, int(ctrl_axis)))
 
     # ------------------------------------------------------------------ instrumentation
     def stats(self):

@@ -42,6 +42,21 @@ class GpuShard:
     def buffer(self):
         return self.eng.state_tensor()
 
+    # ---- peer memory: partners' shards mapped through CUDA IPC (NVLink loads / stores) -----------
+    def enable_peer_access(self, rank, world, group=None):
+        import torch.distributed as dist
+
+        handles = [None] * world
+        dist.all_gather_object(handles, self.eng.ipc_export(), group=group)
+        self._peer_handles, self._peer_ptrs, self._rank = handles, {}, rank
+
+    def peer_1q(self, partner, my_bit, m, ctrl_axis=-1):
+        """Fused gate + transfer on a global axis: this rank updates both shards on its half of the
+        local index range (kernel ``k_peer_1q``)."""
+        if partner not in self._peer_ptrs:
+            self._peer_ptrs[partner] = self.eng.ipc_open(self._peer_handles[partner])
+        self.eng.peer_1q(self._peer_ptrs[partner], my_bit, my_bit, m, ctrl_axis)
+
     def sync(self):
         import torch
 
@@ -74,7 +89,7 @@ class GpuShard:
 
 
 class ShardedKet:
-    def __init__(self, n, shard, rank, world, group=None, seed=0):
+    def __init__(self, n, shard, rank, world, group=None, seed=0, peer=False):
         g = int(round(np.log2(world)))
         if 2 ** g != world:
             raise ValueError("world size must be a power of two")
@@ -92,6 +107,12 @@ class ShardedKet:
         self.exchanged_bytes = 0
         self.exchange_seconds = 0.0
         self._pending = 1.0 + 0.0j      # rank-local scalar phase not yet applied (folded into the next table)
+        self.peer = bool(peer)          # gates on a global target run as ONE kernel over peer memory
+        self.peer_gates = 0
+        self.peer_seconds = 0.0
+        self._peer_uses = {}            # logical axis -> mixing gates served over peer memory while global
+        if self.peer:
+            shard.enable_peer_access(rank, world, group)
         self._seed, self._draw = int(seed), 0
 
     # ------------------------------------------------------------------ slots
@@ -114,6 +135,7 @@ class ShardedKet:
         self._exchange(j, L)
         other = self._axis_at(L)
         self.slot[other], self.slot[a] = self.slot[a], L
+        self._peer_uses[other] = 0
 
     def _exchange(self, j, L):
         """new[rank bit j = x, local bit L = y] = old[rank bit j = y, local bit L = x]."""
@@ -157,10 +179,43 @@ class ShardedKet:
             raise NotImplementedError("predicated ops need per-shot registers; sharded mode is single-shot")
 
     # ------------------------------------------------------------------ gates
+    def _use_peer(self, axis):
+        """Policy: the first gate that mixes a global axis runs over peer memory in place (cheaper than
+        a swap when the axis is mixed once, e.g. a GHZ ladder); a second one means the axis is hot (a
+        QFT target): swap it into a local slot and keep it there."""
+        if not (self.peer and self._is_global(axis)):
+            return False
+        if self._peer_uses.get(axis, 0) >= 1:
+            self._peer_uses[axis] = 0
+            return False
+        self._peer_uses[axis] = self._peer_uses.get(axis, 0) + 1
+        return True
+
+    def _peer_gate(self, axis, m, ctrl_slot=-1, active=True):
+        """2x2 gate on a GLOBAL axis without moving it: both ranks of every pair run k_peer_1q on
+        their half of the index range, reading / writing the partner's shard over NVLink."""
+        import time
+
+        import torch.distributed as dist
+
+        self._apply_pending()
+        self.shard.sync()
+        dist.barrier(group=self.group)          # every shard quiescent before anyone writes remotely
+        t0 = time.perf_counter()
+        if active:
+            j = self.slot[axis] - self.m
+            self.shard.peer_1q(self.rank ^ (1 << j), (self.rank >> j) & 1, m, ctrl_slot)
+        self.shard.sync()
+        dist.barrier(group=self.group)
+        self.peer_gates += 1
+        self.peer_seconds += time.perf_counter() - t0
+
     def apply_1q(self, axis, m):
         m = np.asarray(m, dtype=complex).reshape(2, 2)
         if m[0, 1] == 0 and m[1, 0] == 0:
             return self.apply_diag([axis], [m[0, 0], m[1, 1]])
+        if self._use_peer(axis):
+            return self._peer_gate(axis, m)
         self._localise(axis, [axis])
         self.shard.apply_1q(self.slot[axis], m)
 
@@ -168,6 +223,10 @@ class ShardedKet:
         m = np.asarray(m, dtype=complex).reshape(2, 2)
         if m[0, 1] == 0 and m[1, 0] == 0:
             return self.apply_diag([c, t], [1, 1, m[0, 0], m[1, 1]])
+        if self._use_peer(t):
+            if self._is_global(c):
+                return self._peer_gate(t, m, active=bool(self._rank_bit(c)))
+            return self._peer_gate(t, m, ctrl_slot=self.slot[c])
         self._localise(t, [c, t])
         if self._is_global(c):
             if self._rank_bit(c):

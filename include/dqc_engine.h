@@ -150,6 +150,23 @@ int dqe_set_state(dqe_t* h, int64_t shot, const double* in, uint64_t live_mask);
 /* Device pointer + size of the whole state buffer (wrap zero-copy as a torch tensor). */
 int dqe_state_ptr(dqe_t* h, void** dev, int64_t* nbytes);
 
+/* ---- peer-memory path for state vectors sharded over GPUs (one handle per rank) ------
+ * A gate that mixes a GLOBAL axis (a bit of the rank id) pairs every local amplitude with the
+ * amplitude at the same local index on the partner rank.  dqe_peer_1q fuses the gate with the
+ * transfer: this rank updates BOTH ranks' amplitudes for one half of the local index range
+ * (`half` = 0 or 1; the partner takes the other half), reading and writing the partner's shard
+ * directly over NVLink through an IPC-mapped pointer -- no staging buffer, no separate exchange, and
+ * race-free in place because the two ranks touch disjoint index ranges.  The caller synchronises the
+ * two ranks before and after (both shards quiescent / both halves done).
+ *   dqe_ipc_export : 64-byte cudaIpcMemHandle_t of this handle's state buffer (engine-owned only)
+ *   dqe_ipc_open   : map a partner's handle, returns a device pointer valid in this process
+ *   dqe_peer_1q    : my_bit = this rank's value of the global axis; m = 2x2 complex; ctrl_axis = a
+ *                    LOCAL axis that must be 1 (-1: none).  Requires every local axis live. */
+int dqe_ipc_export(dqe_t* h, void* handle64);
+int dqe_ipc_open(dqe_t* h, const void* handle64, void** peer_state);
+int dqe_ipc_close(dqe_t* h, void* peer_state);
+int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* m, int ctrl_axis);
+
 /* ---- tuning + instrumentation --------------------------------------------------------------- */
 /* key: "tile_bits" (log2 amplitudes staged per CTA, default 11 = 32 KiB), "threads" (per CTA: 64,
  * 128 (default), 256), "min_run_bits" (log2 of the shortest contiguous run a tile may be built

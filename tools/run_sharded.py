@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--qubits", dest="n", type=int, default=30)
     ap.add_argument("--circuit", default="qft")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--peer", type=int, default=0, help="1: gates on global axes as one kernel over peer memory")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -36,7 +37,7 @@ def main():
     best = None
     for rep in range(a.reps):
         shard = GpuShard(a.n - g, local, rank == 0)
-        sk = ShardedKet(a.n, shard, rank, world)
+        sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer))
         shard.eng.time_passes(True)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -65,7 +66,8 @@ def main():
         st = shard.eng.stats()
         res = dict(circuit=a.circuit, n=a.n, n_gpus=world, seconds=float(t[1]), max_abs_err=float(t[0]),
                    norm=norm, exchanges=sk.exchanges, exchange_bytes_per_rank=sk.exchanged_bytes,
-                   exchange_seconds=float(t[2]), host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
+                   exchange_seconds=float(t[2]), peer=bool(a.peer), peer_gates=sk.peer_gates, peer_seconds=sk.peer_seconds,
+                   host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
                    micro_ops=st["micro_ops"], pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
                    nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges else None,
                    passes_per_rank=st["passes"], api_ops=st["api_ops"], shard_bytes=(2 ** (a.n - g)) * 16,
@@ -79,7 +81,7 @@ def main():
     if rank == 0:
         print(json.dumps(best), flush=True)
         os.makedirs("gpurun_out", exist_ok=True)
-        with open(f"gpurun_out/sharded_{a.circuit}{a.n}_x{world}.json", "w") as f:
+        with open(f"gpurun_out/sharded_{a.circuit}{a.n}_x{world}{'_peer' if a.peer else ''}.json", "w") as f:
             json.dump(best, f)
     dist.destroy_process_group()
 
