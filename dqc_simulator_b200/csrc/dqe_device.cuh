@@ -1014,12 +1014,23 @@ __global__ void k_histogram(const HistParams hp) {
 __global__ void __launch_bounds__(256) k_peer_1q(double2* __restrict__ lo, double2* __restrict__ hi, uint64_t begin,
                                                  uint64_t end, uint64_t ctrl_mask, double2 m00, double2 m01,
                                                  double2 m10, double2 m11) {
+  // 4 independent 16-byte peer loads in flight per thread: NVLink latency (~2 us) needs the depth
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
-    if ((i & ctrl_mask) != ctrl_mask) continue;
-    const double2 a = lo[i], b = hi[i];
-    lo[i] = cfma(m01, b, cmul(m00, a));
-    hi[i] = cfma(m11, b, cmul(m10, a));
+  for (uint64_t i0 = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end; i0 += 4 * stride) {
+    double2 a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t i = i0 + (uint64_t)k * stride;
+      if (i < end && (i & ctrl_mask) == ctrl_mask) { a[k] = lo[i]; b[k] = hi[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t i = i0 + (uint64_t)k * stride;
+      if (i < end && (i & ctrl_mask) == ctrl_mask) {
+        lo[i] = cfma(m01, b[k], cmul(m00, a[k]));
+        hi[i] = cfma(m11, b[k], cmul(m10, a[k]));
+      }
+    }
   }
 }
 
