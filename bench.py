@@ -285,7 +285,12 @@ def main():
         "reference_printed_fidelity": {"ghz": 0.9570522876374276, "grover": 0.1071574284590638,
                                        "qft": 0.6470482939691747}[a.circuit],
         "roofline": {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # dram__bytes_read+write of this kernel, ncu --set full (profiles/r01e_summary.md): 2.10-2.26 GB
+                     # per launch against 2.147 GB algorithmic at 16384 shots -> ratio 1.03 applied here
+                     "traffic": 1.03 * 32.0 * amps / max(n_pass, 1),
+                     "traffic_source": "ncu capture at 16384 shots (profiles/r01e_summary.md), ratio dram/algorithmic = 1.03",
+                     "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
                      "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),
                      "frac_of_nominal_8TBs": achieved / 8000.0},

@@ -291,3 +291,41 @@ def test_errors_are_reported_not_thrown_across_abi():
         e.kraus_1q(0, [np.eye(2)])
     e.apply_1q(0, X)
     assert abs(e.full_state(0)[0, 1] - 1) < 1e-15
+
+
+@pytest.mark.parametrize("ctrl", [-1, 2])
+def test_peer_memory_gate_on_a_global_axis(ctrl):
+    """k_peer_1q (fused gate + transfer for sharded state vectors): two engines on one GPU play
+    ranks 0 and 1 of a register whose top axis is the rank bit; each 'rank' updates both shards on
+    its half of the index range.  Result = the gate applied to axis m of an (m+1)-qubit oracle ket."""
+    import ctypes
+
+    from dqc_simulator_b200.engine import Engine
+
+    m = 6
+    rng = np.random.default_rng(4)
+    psi = rng.normal(size=2 ** (m + 1)) + 1j * rng.normal(size=2 ** (m + 1))
+    psi /= np.linalg.norm(psi)
+    u = rand_unitary(rng, 2)
+    shards = []
+    for r in range(2):
+        e = Engine("ket", m, 1)
+        e.set_state(0, psi[r * 2 ** m:(r + 1) * 2 ** m], list(range(m)))
+        shards.append(e)
+    ptrs = []
+    for e in shards:
+        dev, nbytes = ctypes.c_void_p(), ctypes.c_int64()
+        e._ck(e._lib.dqe_state_ptr(e._h, ctypes.byref(dev), ctypes.byref(nbytes)))
+        ptrs.append(dev.value)
+    for r in range(2):
+        shards[r].peer_1q(ptrs[1 - r], my_bit=r, half=r, m=u, ctrl_axis=ctrl)
+    for e in shards:
+        e.sync()
+    got = np.concatenate([e.full_state(0)[0] for e in shards])
+    want = psi.reshape(2, -1).copy()
+    if ctrl < 0:
+        want = u @ want
+    else:
+        sel = ((np.arange(2 ** m) >> ctrl) & 1).astype(bool)
+        want[:, sel] = u @ want[:, sel]
+    assert np.abs(got - want.reshape(-1)).max() < 1e-12
