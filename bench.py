@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-shots", type=int, default=48, help="shots of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-bits", type=int, default=None)
+    ap.add_argument("--comm-low", type=int, default=0, help="reserve (and pin) the k lowest axes for comm qubits")
     return ap.parse_args()
 
 
@@ -213,7 +214,7 @@ def main():
         def step():
             t0 = time.perf_counter()
             res = experiment.run_shot_batch(ops, dqc, eng, data, ideal, before_flush=lambda: ev0.record(stream),
-                                            after_launch=lambda: ev1.record(stream))
+                                            after_launch=lambda: ev1.record(stream), comm_axes_low=a.comm_low)
             hist = experiment.outcome_histogram(res.creg)
             # the one collective of the path: fidelity sum + outcome histogram (no-op at N = 1)
             mean_f, _n, _h = experiment.all_reduce_results(res.fidelity, hist, device=f"cuda:{local}")

@@ -68,6 +68,7 @@ struct dqe_engine {
   double2* d_consts;
   size_t d_consts_cap;
   uint64_t live_axes;       // axis mask
+  uint64_t pin_axes;        // axes always enumerated by passes, live or not (keeps low bits contiguous)
   uint64_t planned_live;    // physical live mask at the head of the queue
   uint64_t seed, shot_offset, draw;
   int pred;
@@ -831,6 +832,7 @@ struct Planner {
 
   bool close(std::vector<const HostOp*>& cur, uint64_t need, uint64_t live) {
     if (cur.empty()) return true;
+    live |= phys_live(h, h->pin_axes);
     int t = 0;
     uint64_t tile = 0;
     if (!choose_tile(h, need, live, true, &tile, &t)) {
@@ -992,7 +994,7 @@ struct Planner {
       // every op may need a group header in the worst case -> 2 slots per op
       const bool fits = cur.empty() || (h->fuse && 2 * ((int)cur.size() + 1) <= kMaxOpsPerPass &&
                                         nconst + op.nconst <= kMaxConstsPerPass &&
-                                        choose_tile(h, need2, live2, false, &tile, &t));
+                                        choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
         if (!close(cur, need, live)) return false;
         need2 = op.need;
@@ -1181,7 +1183,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->formalism = formalism; h->nmax = max_qubits; h->P = P; h->device = device; h->batch = batch;
   h->own_stream = false; h->own_state = false; h->state = nullptr; h->creg = nullptr;
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
-  h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0;
+  h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
   h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
@@ -1721,6 +1723,9 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->group = value ? 1 : 0;
   } else if (!strcmp(key, "tma")) {
     h->tma = value ? 1 : 0;
+  } else if (!strcmp(key, "pin_mask")) {
+    if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
+    h->pin_axes = (uint64_t)value;
   } else if (!strcmp(key, "variant")) {
     if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "variant in [0, 2]");
     h->variant = (int)value;

@@ -243,7 +243,7 @@ class DQCExecutor:
     """
 
     def __init__(self, qpu_op_dict, dqc, backend, forced_outcomes=None, host_branching=False,
-                 swap_as_three_cnots=True, creg_bits=64, axis_pool=None):
+                 swap_as_three_cnots=True, creg_bits=64, axis_pool=None, comm_axes_low=0):
         self.ops = qpu_op_dict
         self.dqc = dqc if isinstance(dqc, DQCSpec) else DQCSpec(list(dqc))
         self.backend = backend
@@ -256,6 +256,15 @@ class DQCExecutor:
         n_axes = backend.max_qubits if axis_pool is None else axis_pool
         self._n_axes = n_axes
         self._free_axes = list(range(n_axes))
+        # comm_axes_low = k: the k lowest axes are reserved for communication qubits (and pinned in
+        # the engine), so that the column AND row bits touched by every remote-gate primitive sit next
+        # to the contiguous low block of the density matrix: longer HBM runs per tile
+        self._comm_low = int(comm_axes_low)
+        if self._comm_low:
+            self._free_comm = list(range(self._comm_low))
+            self._free_axes = list(range(self._comm_low, n_axes))
+            if hasattr(backend, "set_option"):
+                backend.set_option("pin_mask", (1 << self._comm_low) - 1)
         self.peak_axes = 0
         self.programs_executed = 0
         self.measurements = 0
@@ -271,13 +280,21 @@ class DQCExecutor:
     def _claim_axis(self, is_comm):
         """Processing qubits take the lowest free axis, comm qubits the highest: while a comm
         axis is free the active sub-block of the state stays contiguous in memory."""
-        if not self._free_axes:
-            raise RuntimeError("engine register too small for the live qubits of this circuit")
-        ax = self._free_axes.pop(-1 if is_comm else 0)
-        self.peak_axes = max(self.peak_axes, self._n_axes - len(self._free_axes))
+        if self._comm_low and is_comm and self._free_comm:
+            ax = self._free_comm.pop(0)
+        else:
+            if not self._free_axes:
+                raise RuntimeError("engine register too small for the live qubits of this circuit")
+            ax = self._free_axes.pop(-1 if is_comm else 0)
+        used = self._n_axes - len(self._free_axes) - (len(self._free_comm) if self._comm_low else 0)
+        self.peak_axes = max(self.peak_axes, used)
         return ax
 
     def _release_axis(self, ax):
+        if self._comm_low and ax < self._comm_low:
+            self._free_comm.append(ax)
+            self._free_comm.sort()
+            return
         self._free_axes.append(ax)
         self._free_axes.sort()
 

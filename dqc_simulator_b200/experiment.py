@@ -54,12 +54,13 @@ class ShotBatchResult:
         self.executor = ex
 
 
-def run_shot_batch(qpu_ops, dqc, engine, data_qubits, ideal_ket, before_flush=None, after_launch=None):
+def run_shot_batch(qpu_ops, dqc, engine, data_qubits, ideal_ket, before_flush=None, after_launch=None,
+                   comm_axes_low=0):
     """One batch of shots: reset the register, walk the compiled op lists (enqueue only), flush the
     gate queue as fused passes, then read per-shot fidelity <phi|rho_S|phi> and the classical
     registers back to the host."""
     engine.reinit()
-    ex = executor.DQCExecutor(qpu_ops, dqc, engine).run()
+    ex = executor.DQCExecutor(qpu_ops, dqc, engine, comm_axes_low=comm_axes_low).run()
     axes = ex.axes_of(data_qubits)
     if before_flush:
         before_flush()

@@ -173,7 +173,9 @@ int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* 
  * from, default 5), "fuse" (0: one op per pass), "merge" (0: no host-side folding of axis-local
  * ops), "group" (0: no register-resident qubit-pair sweeps), "tma" (0: per-thread loads instead
  * of cp.async.bulk), "persistent" (1: persistent CTAs with a double-buffered tile ring instead of
- * one tile per CTA), "ctas_per_sm" (cap for the persistent grid). */
+ * one tile per CTA), "ctas_per_sm" (cap for the persistent grid), "pin_mask" (axes that passes always
+ * enumerate, live or free: pinning the lowest axes keeps the low bits of every tile contiguous in HBM
+ * when those axes hold qubits that come and go, e.g. communication qubits). */
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates

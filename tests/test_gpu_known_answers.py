@@ -147,3 +147,23 @@ def test_every_fixture_runs(golden_dir):
         ex, be, _ = rc.run_golden(gpu, os.path.basename(path))
         be.sync()
         assert ex.finished
+
+
+@pytest.mark.parametrize("name", ["c2_qft5_3qpu_cat.json", "c2_ghz5_3qpu_cat.json"])
+def test_config2_with_pinned_low_comm_axes(name):
+    """Executor option comm_axes_low (comm qubits on the lowest, pinned axes: longer contiguous HBM
+    runs per tile): same physics, different axis assignment -- engine vs oracle on the same option,
+    and reduced states equal to the default assignment."""
+    from dqc_simulator_b200 import executor, opstream
+
+    ops, meta = opstream.load(os.path.join(rc.GOLDEN, name))
+    data = [tuple(v) for v in meta["qubit_map"].values()]
+    out = {}
+    for label, mk, low in (("gpu_low", gpu, 2), ("cpu_low", cpu, 2), ("gpu_default", gpu, 0)):
+        be = mk("dm", 7, 3)
+        ex = executor.DQCExecutor(ops, _c2_dqc(), be, comm_axes_low=low).run()
+        axes = ex.axes_of(data)
+        out[label] = ([be.reduced_dm(axes, s) for s in range(3)], be.full_state())
+    assert np.abs(out["gpu_low"][1] - out["cpu_low"][1]).max() < TOL
+    _cmp(out["gpu_low"][0], out["cpu_low"][0])
+    _cmp(out["gpu_low"][0], out["gpu_default"][0])
