@@ -250,6 +250,23 @@ def main():
         pass_ms, n_pass, amps = eng.pass_time()
         eng.time_passes(False)
 
+        # the same kernel in its HBM-bound regime: ONE gate / channel per pass over the resident 1e5-shot
+        # state (what an unfused per-instruction execution would launch), timed the same way
+        live = eng.live
+        h = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+        cnot = np.eye(4, dtype=complex)[[0, 1, 3, 2]]
+        single = [lambda: eng.apply_1q(live[0], h), lambda: eng.apply_2q(live[1], live[2], cnot),
+                  lambda: eng.depolarize([live[3], live[4]], 1e-3), lambda: eng.apply_1q(live[-1], h),
+                  lambda: eng.depolarize([live[2]], 1e-3)]
+        for f in single:   # warm
+            f(); eng.flush()
+        eng.sync()
+        eng.time_passes(True)
+        for f in single:
+            f(); eng.flush()
+        sg_ms, sg_n, sg_amps = eng.pass_time()
+        eng.time_passes(False)
+
     t = torch.tensor([t_total, sum(devs) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,10 +308,18 @@ def main():
                      # per launch against 2.147 GB algorithmic at 16384 shots -> ratio 1.03 applied here
                      "traffic": 1.03 * 32.0 * amps / max(n_pass, 1),
                      "traffic_source": "ncu capture at 16384 shots (profiles/r01e_summary.md), ratio dram/algorithmic = 1.03",
+                     "note": "fused passes (~17 ops each, measurements resolved on chip through cluster DSMEM) are bound "
+                             "by the on-chip sweep work, not by HBM; see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
                      "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),
                      "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline_single_gate": {
+            "what": "k_tile_pass, one gate / channel per pass on the same resident state (1q dense, CNOT, 2q and 1q "
+                    "depolarising), i.e. the per-instruction launches of an unfused execution",
+            "bound": "hbm", "achieved": 32.0 * sg_amps / (sg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": 32.0 * sg_amps / (sg_ms * 1e-3) / 1e9 / peak, "launches": sg_n,
+            "avg_launch_ms": sg_ms / max(sg_n, 1)},
         "clocks": clocks,
     }
     if not a.no_cpu_baseline:

@@ -11,6 +11,7 @@
 // handled as a "ket" on 2n bits: U rho U^dagger is U on the row bit and conj(U) on the column
 // bit, and a channel is a 4x4 superoperator on (row bit, column bit) -- one pass over rho.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,9 @@ enum OpType : int32_t {
   OP_INJECT = 9,      // write a 2-qubit state onto two fresh axes
   OP_PAULI_SAMPLED = 10,  // ket: apply a Pauli string drawn per shot from Philox
   OP_MAT1X2 = 11,     // dm controlled/one-qubit gate, row side + column side in one sweep
+  OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
+                      // Philox draw -> outcome + renormalisation kept on chip; aux = axis bit, flags = creg bit + 1,
+                      // lctrl = forced + 1, p[0] = flip probability, octrl = draw index
   // dm group sweep: every thread holds the 16 elements (ra, rb, ca, cb) of one qubit PAIR (A, B) in
   // registers and runs the following `aux` sub-ops on them -- one shared-memory round trip for a
   // whole run of gates / channels on those two qubits.
@@ -87,7 +91,7 @@ struct PassParams {
   int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
   int32_t store_back, nconsts;
   int32_t use_tma, nthreads;
-  int32_t nbuf, pad2;
+  int32_t nbuf, has_measure;
   uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
@@ -399,10 +403,109 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
   }
 }
 
+
+// Fused measurement for registers whose tiles fit one thread-block cluster (<= 8 CTAs per shot):
+// the tile partials are summed over the cluster through distributed shared memory, every CTA of
+// the shot draws the same Philox number, and the pass simply goes on -- no kernel boundary.
+template <int FORM>
+__device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                               uint64_t base, uint64_t shot, uint64_t cw, double* red,
+                                               double (*part)[2], MeasRec* mrec, int mcount) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int par = mcount & 1;
+  // 1. this tile's partials (same arithmetic as op_probs, result in red[0..1])
+  {
+    MicroOp pr = op;
+    double a0 = 0.0, a1 = 0.0;
+    const int abit = op.aux;
+    if constexpr (FORM == 0) {
+      const int jb = op.b[0];
+      if (jb >= kOuter) {
+        double a = 0.0;
+        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) { const double2 v = tile[i]; a += fma(v.x, v.x, v.y * v.y); }
+        if ((base >> (jb - kOuter)) & 1ull) a1 = a; else a0 = a;
+      } else {
+        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+          const double2 v = tile[i];
+          const double w = fma(v.x, v.x, v.y * v.y);
+          if ((i >> jb) & 1u) a1 += w; else a0 += w;
+        }
+      }
+    } else {
+      const int n = pp.nmax;
+      int nfree = 0;
+      for (int a = 0; a < n; ++a) nfree += pp.ax_col[a] >= 0;
+      for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
+        uint32_t i = 0, va = 0;
+        bool ok = true;
+        int k = 0;
+        for (int a = 0; a < n; ++a) {
+          const int cl = pp.ax_col[a], rl = pp.ax_row[a];
+          const uint32_t v = cl >= 0 ? ((d >> k++) & 1u) : (uint32_t)((base >> a) & 1ull);
+          if (cl >= 0) i |= v << cl;
+          if (rl >= 0) i |= v << rl;
+          else ok = ok && (((base >> (a + n)) & 1ull) == v);
+          if (a == abit) va = v;
+        }
+        if (ok) { const double w = tile[i].x; if (va) a1 += w; else a0 += w; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+      part[par][0] = s0; part[par][1] = s1;
+    }
+    (void)pr;
+  }
+  // 2. every CTA of the shot sums all partials in rank order (identical result everywhere)
+  cluster.sync();
+  if (threadIdx.x == 0) {
+    double p0 = 0.0, p1 = 0.0;
+    const unsigned nr = cluster.num_blocks();
+    for (unsigned r = 0; r < nr; ++r) {
+      const double* rp = cluster.map_shared_rank(&part[par][0], r);
+      p0 += rp[0]; p1 += rp[1];
+    }
+    const double e = op.p[0];
+    const double q0 = (1.0 - e) * p0 + e * p1, q1 = (1.0 - e) * p1 + e * p0;
+    const double tot = q0 + q1;
+    double u, u2;
+    shot_uniforms(pp.seed, pp.shot_offset + shot, op.octrl, u, u2);
+    const int forced = (int)op.lctrl - 1;
+    const int m = forced >= 0 ? forced : ((u * tot < q1) ? 1 : 0);
+    const double pm = m ? q1 : q0;
+    MeasRec r;
+    r.outcome = m; r.pad = 0;
+    r.scale = pm > 0.0 ? (FORM == 1 ? 1.0 / pm : 1.0 / sqrt(pm)) : 0.0;
+    *mrec = r;
+    const int cbit = op.flags - 1;
+    if (cluster.block_rank() == 0) {
+      const_cast<MeasRec*>(pp.rec)[shot] = r;   // the collapse may land in the next pass
+      if (cbit >= 0) {
+        uint64_t* creg = const_cast<uint64_t*>(pp.creg);
+        const uint64_t bit = 1ull << cbit;
+        creg[shot] = (cw & ~bit) | ((uint64_t)m << cbit);
+      }
+    }
+  }
+  __syncthreads();
+  const int cbit = op.flags - 1;
+  if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
+  return cw;
+}
+
 template <int FORM>
 __device__ __forceinline__ void op_collapse(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
-                                            uint64_t shot) {
-  const MeasRec r = pp.rec[shot];
+                                            const MeasRec& r) {
   const int m = r.outcome;
   const double sc = r.scale;
   const bool discard = op.flags & 1;
@@ -667,7 +770,7 @@ __device__ __forceinline__ void g_trace(double2 (&v)[16]) {
 
 __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
                                           const PassParams& pp, const double2* cs_base, uint64_t base,
-                                          uint64_t cw, uint64_t shot) {
+                                          uint64_t cw, const MeasRec* mrec) {
   int s4[4];
   sort4(g.b, s4);
   const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
@@ -700,7 +803,7 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         case G_MAT2ROWS: g_mat2side<true>(v, cs); break;
         case G_MAT2COLS: g_mat2side<false>(v, cs); break;
         case G_COLLAPSE: {
-          const MeasRec r = pp.rec[shot];
+          const MeasRec r = *mrec;
           if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
           else g_collapse<0>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
           break;
@@ -763,6 +866,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[kMaxDiagRun];
+  __shared__ MeasRec s_meas;
+  __shared__ double s_part[2][2];   // [measurement parity][outcome]: this tile's probability partials
 
   const uint32_t T = 1u << pp.t;
   const int c0 = pp.tile_segs[0].len;
@@ -842,7 +947,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       }
       __syncthreads();
     }
-    const uint64_t cw = pp.creg[shot];
+    uint64_t cw = pp.creg[shot];
+    if (threadIdx.x == 0) s_meas = pp.rec[shot];   // outcome recorded by a preceding k_finish_measure
+    __syncthreads();
+    int mcount = 0;
 
     for (int o = 0; o < pp.nops; ++o) {
       const MicroOp& op = s_ops[o];
@@ -864,7 +972,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           }
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
-          case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, shot); break;
+          case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
+          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++); break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
           case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
           default: break;
@@ -872,7 +981,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       } else {                     // ---- density-matrix micro-ops
         switch (op.type) {
           case OP_GROUP:
-            run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, shot);
+            run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, &s_meas);
             o += op.aux;
             break;
           case OP_MAT1X2: {
@@ -887,7 +996,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_PAULI1: op_pauli1(tile, T, op); break;
           case OP_DEPOL2: op_depol2(tile, T, op); break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
-          case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, shot); break;
+          case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
+          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++); break;
           case OP_TRACE: op_trace(tile, T, op); break;
           case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
           default: break;
@@ -933,6 +1043,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   }
   // shared memory must stay valid until the last bulk store has read it
   if (tma && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  // ... and until every CTA of the cluster has read this CTA's probability partials
+  if (pp.has_measure) cooperative_groups::this_cluster().sync();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -76,7 +77,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -670,6 +671,7 @@ int local_of(uint64_t tile, int phys) { return __builtin_popcountll(tile & ((1ul
 
 struct Planner {
   dqe_t* h;
+  std::deque<HostOp> fused;          // OP_MEASURE ops synthesised from PROBS + finish pairs
   std::vector<PlannedPass> passes;
   std::vector<MicroOp> dev_ops;
   std::vector<double2> dev_consts;
@@ -695,12 +697,13 @@ struct Planner {
         const int ph = ho->m.b[i];
         m.b[i] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
       }
-    } else if (m.type != OP_PROBS) {
+    } else if (m.type != OP_PROBS && m.type != OP_MEASURE) {
       for (uint32_t i = 0; i < m.nb; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
     } else {
       const int ph = m.aux;   // measured axis: column / ket bit
       m.b[0] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
     }
+    if (m.type == OP_MEASURE) return m;   // lctrl / octrl / flags carry forced outcome, draw index, creg bit
     m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
     for (int b = 0; b < 64; ++b) {
       if ((ho->pctrl >> b) & 1ull) {
@@ -881,7 +884,7 @@ struct Planner {
     const bool grouping = h->formalism == DQE_DM && h->group && t >= 4;
     for (const HostOp* ho : cur) {
       uint64_t tb = touched_bits(*ho);
-      if (ho->m.type == OP_PROBS) tb = ~0ull;
+      if (ho->m.type == OP_PROBS || ho->m.type == OP_MEASURE) tb = ~0ull;
       int ax[2], nax = 0;
       const bool can = grouping && group_axes(ho, tile, ax, &nax);
       int dep = -1;
@@ -936,7 +939,8 @@ struct Planner {
         writes = true;
       } else {
         for (const HostOp* ho : it.ops) {
-          if (ho->m.type != OP_PROBS) writes = true;
+          if (ho->m.type != OP_PROBS && ho->m.type != OP_MEASURE) writes = true;
+          if (ho->m.type == OP_MEASURE) pp.has_measure = 1;
           dev_ops.push_back(localise(ho, tile, P.const_begin));
         }
       }
@@ -966,11 +970,30 @@ struct Planner {
     return true;
   }
 
+  // every pass of this handle has at most 8 tiles per shot (cluster size limit) when the whole
+  // register is at most 3 bits wider than a tile
+  bool cluster_mode() const { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 3; }
+
   bool plan() {
     std::vector<const HostOp*> cur;
     uint64_t live_now = h->planned_live, need = 0, live = live_now;
     int nconst = 0;
     for (const HostOp& op : h->queue) {
+      if (op.kind == 1 && cluster_mode() && !cur.empty() && cur.back()->m.type == OP_PROBS) {
+        // small registers: all tiles of a shot fit one thread-block cluster, so the measurement is a
+        // micro-op (DSMEM sum + on-chip draw) and the pass goes on
+        HostOp mo = *cur.back();
+        mo.m.type = OP_MEASURE;
+        mo.m.flags = op.creg_bit + 1;
+        mo.m.lctrl = (uint32_t)(op.forced + 1);
+        mo.m.p[0] = op.flip;
+        mo.m.octrl = op.draw;
+        mo.live_after = op.live_after;
+        fused.push_back(mo);
+        cur.back() = &fused.back();
+        live_now = op.live_after;
+        continue;
+      }
       if (op.kind == 1) {
         // the PROBS op is the tail of `cur`
         if (!close(cur, need, live)) return false;
@@ -1100,20 +1123,37 @@ int do_flush(dqe_t* h) {
       CK(cudaEventRecord(e0, h->stream));
     }
     // one kernel per formalism (their micro-op sets are disjoint enough that sharing one
-    // interpreter costs registers); variants = same code under different register budgets
-    const unsigned gr = (unsigned)P.grid;
-    if (h->formalism == DQE_KET) {
-      switch (h->variant) {
-        case 1: k_tile_pass<128, 3, 0><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-        case 2: k_tile_pass<128, 2, 0><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-        default: k_tile_pass<256, 2, 0><<<gr, h->threads, P.smem, h->stream>>>(P.pp); break;
+    // interpreter costs registers); variants = same code under different register budgets.
+    // Passes that carry a fused measurement launch as thread-block clusters: the 2^outer_bits tiles of
+    // a shot form one cluster and exchange their probability partials through DSMEM.
+    {
+      const void* fn;
+      int threads = h->threads;
+      if (h->formalism == DQE_KET) {
+        fn = h->variant == 1 ? (const void*)k_tile_pass<128, 3, 0>
+             : h->variant == 2 ? (const void*)k_tile_pass<128, 2, 0> : (const void*)k_tile_pass<256, 2, 0>;
+      } else {
+        fn = h->variant == 1 ? (const void*)k_tile_pass<128, 3, 1>
+             : h->variant == 2 ? (const void*)k_tile_pass<128, 2, 1> : (const void*)k_tile_pass<256, 2, 1>;
       }
-    } else {
-      switch (h->variant) {
-        case 1: k_tile_pass<128, 3, 1><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-        case 2: k_tile_pass<128, 2, 1><<<gr, std::min(h->threads, 128), P.smem, h->stream>>>(P.pp); break;
-        default: k_tile_pass<256, 2, 1><<<gr, h->threads, P.smem, h->stream>>>(P.pp); break;
+      if (h->variant) threads = std::min(threads, 128);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)P.grid);
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = P.smem;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      if (P.pp.has_measure) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1u << P.pp.outer_bits;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
       }
+      void* args[1] = {(void*)&P.pp};
+      CK(cudaLaunchKernelExC(&cfg, fn, args));
     }
     if (h->timing) {
       CK(cudaEventRecord(e1, h->stream));
@@ -1185,7 +1225,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->timing = false;
+  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1726,6 +1766,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "cluster")) {
+    h->cluster = value ? 1 : 0;
   } else if (!strcmp(key, "variant")) {
     if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "variant in [0, 2]");
     h->variant = (int)value;

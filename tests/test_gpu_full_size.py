@@ -62,7 +62,8 @@ def test_fusion_switches_do_not_change_the_state():
     """Same circuit, same sampled outcomes, planner with and without peephole / pass fusion: the states
     agree to 1e-12 (16M amplitudes)."""
     ref = None
-    for opts in ({}, {"merge": 0}, {"fuse": 0}, {"tile_bits": 9}, {"tma": 0}, {"persistent": 1}, {"threads": 256, "tile_bits": 12}):
+    for opts in ({}, {"merge": 0}, {"fuse": 0}, {"tile_bits": 9}, {"tma": 0}, {"persistent": 1},
+                 {"threads": 256, "tile_bits": 12}, {"cluster": 0}, {"tile_bits": 12, "cluster": 1}):
         e, ex, meta, torch = _run("c3_qft12_4qpu_cat.json", 14, 4, 5, **opts)
         st = e.state_tensor().clone()
         creg = e.read_creg_words()

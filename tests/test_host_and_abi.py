@@ -108,20 +108,24 @@ def _plan(circuit, **opts):
 def test_planner_measurement_bound_pass_count():
     """Every measurement needs a per-shot global sum, so it ends a pass; everything between two
     measurements of the config-2 circuits fuses into one pass (tile = 12 of the 14 dm bits)."""
-    st, ex = _plan("grover", tile_bits=12)
+    st, ex = _plan("grover", tile_bits=12, cluster=0)
     assert ex.measurements == 288 and st["finish_launches"] == 288
     assert 288 <= st["passes"] <= 288 + 20
     assert st["api_ops"] > 3000 and st["merged_ops"] > 500
-    st_q, ex_q = _plan("qft", tile_bits=12)
+    st_q, ex_q = _plan("qft", tile_bits=12, cluster=0)
     assert ex_q.measurements == 44 and 44 <= st_q["passes"] <= 50
-    st11, _ = _plan("grover", tile_bits=11)     # a smaller tile holds fewer high bits: more cuts
+    st11, _ = _plan("grover", tile_bits=11, cluster=0)     # a smaller tile holds fewer high bits: more cuts
     assert st["passes"] < st11["passes"] < 2 * st["passes"]
+    # cluster mode (default): the <= 8 tiles of a shot form a thread-block cluster, the measurement
+    # is a micro-op (DSMEM sum + on-chip draw) and no longer cuts the pass
+    stc, exc = _plan("grover")
+    assert exc.measurements == 288 and stc["finish_launches"] == 0 and stc["passes"] < 0.6 * st11["passes"]
 
 
 def test_planner_switches():
-    full, _ = _plan("qft")
+    full, _ = _plan("qft", cluster=0)
     nofuse, _ = _plan("qft", fuse=0)
-    nomerge, _ = _plan("qft", merge=0, group=0)
+    nomerge, _ = _plan("qft", merge=0, group=0, cluster=0)
     assert nofuse["passes"] > 5 * full["passes"]          # one op per pass
     assert nomerge["merged_ops"] == 0 and full["merged_ops"] > 100
     assert abs(nomerge["passes"] - full["passes"]) <= 4     # merging changes sweeps, hardly the pass cuts
