@@ -252,6 +252,9 @@ def main():
 
         # the same kernel in its HBM-bound regime: ONE gate / channel per pass over the resident 1e5-shot
         # state (what an unfused per-instruction execution would launch), timed the same way
+        for ax in range(eng.max_qubits):   # full 7-qubit register per shot (the comm axes are free after a run)
+            if ax not in eng.live:
+                eng.alloc_axis(ax)
         live = eng.live
         h = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
         cnot = np.eye(4, dtype=complex)[[0, 1, 3, 2]]

@@ -29,6 +29,8 @@ enum OpType : int32_t {
   OP_INJECT = 9,      // write a 2-qubit state onto two fresh axes
   OP_PAULI_SAMPLED = 10,  // ket: apply a Pauli string drawn per shot from Philox
   OP_MAT1X2 = 11,     // dm controlled/one-qubit gate, row side + column side in one sweep
+  OP_XPAT = 14,       // dm 1q channel with the sparse 'X pattern' (diagonal gate composed with Pauli noise):
+                      // e00,e11 mix among themselves and e01,e10 among themselves -- 8 complex coefficients
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
                       // Philox draw -> outcome + renormalisation kept on chip; aux = axis bit, flags = creg bit + 1,
                       // lctrl = forced + 1, p[0] = flip probability, octrl = draw index
@@ -46,6 +48,7 @@ enum OpType : int32_t {
   G_COLLAPSE = 107,
   G_TRACE = 108,
   G_INJECT = 109,
+  G_XPAT = 111,
   G_DIAG = 110,       // p[0..1] hold a 16-byte table-index LUT (one byte per element)
 };
 
@@ -287,6 +290,23 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
       v = cmul(v, s_consts[d.c_off + idx]);
     }
     tile[i] = v;
+  }
+}
+
+
+// cs = {a, b, c, d, f, g, h, k}: e00' = a e00 + b e11, e11' = c e00 + d e11, e01' = f e01 + g e10, e10' = h e01 + k e10
+__device__ __forceinline__ void op_xpat(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
+  const int jr = op.b[0], jc = op.b[1];
+  const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+  const double2 a = cs[0], b = cs[1], c = cs[2], d = cs[3], f = cs[4], g = cs[5], h = cs[6], k = cs[7];
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
+    const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+    const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+    const double2 e00 = tile[i00], e01 = tile[i01], e10 = tile[i10], e11 = tile[i11];
+    tile[i00] = cfma(b, e11, cmul(a, e00));
+    tile[i11] = cfma(d, e11, cmul(c, e00));
+    tile[i01] = cfma(g, e10, cmul(f, e01));
+    tile[i10] = cfma(k, e10, cmul(h, e01));
   }
 }
 
@@ -672,8 +692,58 @@ __device__ __forceinline__ void g_mat2(double2 (&v)[16], const double2* __restri
     }
 }
 
+
+template <int ROLE>
+__device__ __forceinline__ void g_xpat(double2 (&v)[16], const double2* __restrict__ cs) {
+  const double2 a = cs[0], b = cs[1], c = cs[2], d = cs[3], f = cs[4], g = cs[5], h = cs[6], k = cs[7];
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      const double2 e00 = v[EI<ROLE>(0, 0, ro, co)], e01 = v[EI<ROLE>(0, 1, ro, co)];
+      const double2 e10 = v[EI<ROLE>(1, 0, ro, co)], e11 = v[EI<ROLE>(1, 1, ro, co)];
+      v[EI<ROLE>(0, 0, ro, co)] = cfma(b, e11, cmul(a, e00));
+      v[EI<ROLE>(1, 1, ro, co)] = cfma(d, e11, cmul(c, e00));
+      v[EI<ROLE>(0, 1, ro, co)] = cfma(g, e10, cmul(f, e01));
+      v[EI<ROLE>(1, 0, ro, co)] = cfma(k, e10, cmul(h, e01));
+    }
+}
+
 // target axis = ROLE; the control (if any) is either the other axis of the group (in_r / in_c)
 // or outside the tile (r_on / c_on already evaluated on the tile base)
+template <int ROLE>
+__device__ __forceinline__ void g_cx(double2 (&v)[16], bool r_on, bool c_on, bool in_r, bool in_c) {
+  // controlled-X: pure permutation of the register file, no arithmetic
+  if (r_on) {
+#pragma unroll
+    for (int ro = 0; ro < 2; ++ro) {
+      if (in_r && ro == 0) continue;
+#pragma unroll
+      for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const double2 a = v[EI<ROLE>(0, c, ro, co)];
+          v[EI<ROLE>(0, c, ro, co)] = v[EI<ROLE>(1, c, ro, co)];
+          v[EI<ROLE>(1, c, ro, co)] = a;
+        }
+    }
+  }
+  if (c_on) {
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      if (in_c && co == 0) continue;
+#pragma unroll
+      for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double2 a = v[EI<ROLE>(r, 0, ro, co)];
+          v[EI<ROLE>(r, 0, ro, co)] = v[EI<ROLE>(r, 1, ro, co)];
+          v[EI<ROLE>(r, 1, ro, co)] = a;
+        }
+    }
+  }
+}
+
 template <int ROLE>
 __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __restrict__ cs, bool r_on, bool c_on,
                                          bool in_r, bool in_c) {
@@ -793,10 +863,15 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         case G_MAT2:
           if (role) g_mat2<1>(v, cs); else g_mat2<0>(v, cs);
           break;
+        case G_XPAT:
+          if (role) g_xpat<1>(v, cs); else g_xpat<0>(v, cs);
+          break;
         case G_MAT1X2: {
           const bool in_r = op.flags & 2, in_c = op.flags & 4;
           const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
-          if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c); else g_mat1x2<0>(v, cs, r_on, c_on, in_r, in_c);
+          if (op.flags & 16) { if (role) g_cx<1>(v, r_on, c_on, in_r, in_c); else g_cx<0>(v, r_on, c_on, in_r, in_c); }
+          else if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c);
+          else g_mat1x2<0>(v, cs, r_on, c_on, in_r, in_c);
           break;
         }
         case G_DEPOL2: g_depol2(v, op.p[0]); break;
@@ -994,6 +1069,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_DIAG: op_diag(tile, T, op, cs, base); break;
           case OP_PAULI1: op_pauli1(tile, T, op); break;
+          case OP_XPAT: op_xpat(tile, T, op, cs); break;
           case OP_DEPOL2: op_depol2(tile, T, op); break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;

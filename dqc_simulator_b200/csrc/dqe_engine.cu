@@ -145,7 +145,7 @@ void push(dqe_t* h, HostOp& o) {
   if (o.kind == 0 && !o.pctrl && !o.pctrl2) {
     if (h->formalism == DQE_KET) {
       if ((o.m.type == OP_MAT1 || o.m.type == OP_DIAG) && o.m.nb == 1) axis = o.m.b[0];
-    } else if ((o.m.type == OP_MAT2 || o.m.type == OP_PAULI1 || o.m.type == OP_DIAG) && o.m.nb == 2 &&
+    } else if ((o.m.type == OP_MAT2 || o.m.type == OP_PAULI1 || o.m.type == OP_DIAG || o.m.type == OP_XPAT) && o.m.nb == 2 &&
                o.m.b[0] == o.m.b[1] + h->nmax) {
       axis = o.m.b[1];
     }
@@ -244,6 +244,11 @@ bool axis_local_matrix(const dqe_t* h, const HostOp& o, int axis, cplx* M) {
     for (int i = 0; i < 4; ++i) M[i * 5] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
     return true;
   }
+  if (o.m.type == OP_XPAT && o.m.b[0] == rb && o.m.b[1] == axis) {
+    static const int pos[8] = {0, 3, 12, 15, 5, 6, 9, 10};   // a b c d f g h k
+    for (int i = 0; i < 8; ++i) M[pos[i]] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+    return true;
+  }
   return false;
 }
 
@@ -268,13 +273,13 @@ void set_axis_local(dqe_t* h, HostOp& o, int axis, const cplx* M) {
   }
   const int rb = axis + h->nmax;
   o.m.b[0] = (uint8_t)rb; o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
-  bool diag = true, pauli = true;
+  bool diag = true, pauli = true, xpat = true;
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) {
       const cplx v = M[i * 4 + j];
       if (i != j && !is_zero(v)) diag = false;
       const bool in_pat = (i == j) || (i + j == 3);
-      if (!in_pat && !is_zero(v)) pauli = false;
+      if (!in_pat && !is_zero(v)) { pauli = false; xpat = false; }
       if (in_pat && v.imag() != 0.0) pauli = false;
     }
   if (pauli) pauli = M[0] == M[15] && M[3] == M[12] && M[5] == M[10] && M[6] == M[9];
@@ -285,6 +290,10 @@ void set_axis_local(dqe_t* h, HostOp& o, int axis, const cplx* M) {
   } else if (pauli) {
     o.m.type = OP_PAULI1; o.need = (1ull << rb) | (1ull << axis);
     o.m.p[0] = M[0].real(); o.m.p[1] = M[3].real(); o.m.p[2] = M[5].real(); o.m.p[3] = M[6].real();
+  } else if (xpat) {
+    const cplx c8[8] = {M[0], M[3], M[12], M[15], M[5], M[6], M[9], M[10]};
+    o.m.type = OP_XPAT; o.need = (1ull << rb) | (1ull << axis);
+    o.m.c_off = add_consts(h, c8, 8); o.nconst = 8;
   } else {
     o.m.type = OP_MAT2; o.need = (1ull << rb) | (1ull << axis);
     o.m.c_off = add_consts(h, M, 16); o.nconst = 16;
@@ -730,7 +739,7 @@ struct Planner {
     };
     const MicroOp& m = ho->m;
     switch (m.type) {
-      case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE:
+      case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE: case OP_XPAT:
         return add(m.b[1]);
       case OP_MAT2:
         if (ho->pctrl) return false;
@@ -777,6 +786,9 @@ struct Planner {
         m.type = G_PAULI1; m.flags = role(s.b[1]);
         for (int i = 0; i < 4; ++i) m.p[i] = s.p[i];
         break;
+      case OP_XPAT:
+        m.type = G_XPAT; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb);
+        break;
       case OP_MAT2:
         if (s.b[0] == s.b[1] + n) { m.type = G_MAT2; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb); }
         else {
@@ -788,6 +800,12 @@ struct Planner {
         break;
       case OP_MAT1X2: {
         m.type = G_MAT1X2; m.flags = role(s.b[1]);
+        {
+          const double2* u = &h->cpool[ho->m.c_off];
+          if (u[0].x == 0 && u[0].y == 0 && u[3].x == 0 && u[3].y == 0 && u[1].x == 1 && u[1].y == 0 && u[2].x == 1 &&
+              u[2].y == 0)
+            m.flags |= 16;   // Pauli-X: swap instead of multiply
+        }
         if (ho->pctrl) {
           const int b = __builtin_ctzll(ho->pctrl);
           if ((tile >> b) & 1ull) m.flags |= 2; else m.octrl = ho->pctrl;
@@ -1054,9 +1072,9 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT"};
     static const char* gnames[] = {"?", "gPAULI1", "gMAT2", "gMAT1X2", "gDEPOL2", "gROWS", "gCOLS", "gCOLLAPSE",
-                                   "gTRACE", "gINJECT", "gDIAG"};
+                                   "gTRACE", "gINJECT", "gDIAG", "gXPAT"};
     for (PlannedPass& P : pl.passes) {
       if (P.is_finish) { fprintf(stderr, "  finish\n"); continue; }
       fprintf(stderr, "pass t=%d outer=%d nops=%d:", P.pp.t, P.pp.outer_bits, P.pp.nops);
