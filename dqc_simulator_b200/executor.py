@@ -339,12 +339,12 @@ class DQCExecutor:
         source trigger -> both photons arrive ``ent_delay`` later."""
         key = frozenset((node, other))
         link = self.ebit_requests.setdefault(key, {"req": {}, "done": {}})
-        link["req"][node] = (pos, self.qpus[node].clock)
+        link["req"][node] = (pos, self.qpus[node].clock, role)
         self._events += 1
         if other in link["req"]:
             first, second = sorted((node, other))   # qout0 -> side A, qout1 -> side B
-            (pa, ta), (pb, tb) = link["req"][first], link["req"][second]
-            t_arrive = max(ta, tb) + 2 * self.dqc.classical_delay + self.dqc.ent_delay
+            (pa, ta, ra), (pb, tb, rb) = link["req"][first], link["req"][second]
+            t_arrive = self._handshake_done(ta, ra, tb, rb) + self.dqc.ent_delay
             qa, qb = self.qpus[first], self.qpus[second]
             qa._drop(pa)
             qb._drop(pb)
@@ -361,6 +361,24 @@ class DQCExecutor:
         t_arrive = link["done"].pop(node)
         self._events += 1
         self.qpus[node].clock = max(self.qpus[node].clock, t_arrive)
+
+    def _handshake_done(self, ta, ra, tb, rb):
+        """Time at which the client fires the source trigger (``physical_layer.py:269-335``): the
+        client sends HANDSHAKE_READY and re-sends it every ``handshake_wait`` (600 us) until a copy
+        reaches the server while the server is already listening; the server answers at once and
+        the reply takes one more classical hop.  Trigger channel delay is 0
+        (``connections.py:128-141``); both photons arrive ``ent_delay`` later."""
+        d, w = self.dqc.classical_delay, self.dqc.handshake_wait
+        if ra == "client" and rb != "client":
+            tc, ts = ta, tb
+        elif rb == "client" and ra != "client":
+            tc, ts = tb, ta
+        else:                       # symmetric request (not produced by the reference's compilers)
+            return max(ta, tb) + 2 * d
+        k = max(0, math.ceil((ts - tc - d) / w - 1e-12)) if w > 0 else 0
+        if w <= 0:
+            return max(tc + d, ts) + d
+        return tc + k * w + 2 * d
 
     # ---- interpreter ------------------------------------------------------------
     def _flush(self, q, program):
