@@ -61,6 +61,21 @@ def workload_config(a, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+class _StdoutToStderr:
+    """File-descriptor level redirect: NCCL prints its version banner on fd 1 when the communicator is
+    created; stdout must carry exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -198,7 +213,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            warm = torch.zeros(1, device=f"cuda:{local}")
+            dist.all_reduce(warm)          # creates the communicator (and its banner) here
+            torch.cuda.synchronize()
 
     ops, _meta = experiment.load_c2(a.circuit)
     dqc = experiment.c2_hardware(noisy=True)
