@@ -95,6 +95,7 @@ struct PassParams {
   int32_t store_back, nconsts;
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
+  int32_t nfree_cols, pad3;
   uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
@@ -387,8 +388,7 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
     // only the diagonal of rho matters: enumerate it directly.  Free variables = axes whose column
     // bit is inside the tile; the row bit must repeat it (inside the tile, or fixed by the tile base).
     const int n = pp.nmax;
-    int nfree = 0;
-    for (int a = 0; a < n; ++a) nfree += pp.ax_col[a] >= 0;
+    const int nfree = pp.nfree_cols;
     for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
       uint32_t i = 0, va = 0;
       bool ok = true;
@@ -454,8 +454,7 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
       }
     } else {
       const int n = pp.nmax;
-      int nfree = 0;
-      for (int a = 0; a < n; ++a) nfree += pp.ax_col[a] >= 0;
+      const int nfree = pp.nfree_cols;
       for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
         uint32_t i = 0, va = 0;
         bool ok = true;
@@ -841,8 +840,7 @@ __device__ __forceinline__ void g_trace(double2 (&v)[16]) {
 __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
                                           const PassParams& pp, const double2* cs_base, uint64_t base,
                                           uint64_t cw, const MeasRec* mrec) {
-  int s4[4];
-  sort4(g.b, s4);
+  const int s4[4] = {g.b[4], g.b[5], g.b[6], g.b[7]};   // the four bit positions, ascending (host-sorted)
   const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
   const int nsub = g.aux;
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
@@ -916,16 +914,18 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 __device__ __forceinline__ void tma_expect(uint32_t bar_s, uint32_t T) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
 }
+// r0 / rstep must be warp-uniform (every lane runs the loop with the same operands so that the
+// address arithmetic stays on the uniform datapath); only the lane with `leader` set issues.
 __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
-                                              uint32_t T, int c0, uint32_t r0, uint32_t rstep) {
+                                              uint32_t T, int c0, uint32_t r0, uint32_t rstep, bool leader) {
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
-#pragma unroll 4
   for (uint32_t r = r0; r < nruns; r += rstep) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            dst_s + r * run_bytes),
-        "l"(sp + ((uint64_t)pp.run_hi[r] << c0)), "r"(run_bytes), "r"(bar_s)
-        : "memory");
+    const double2* src = sp + ((uint64_t)pp.run_hi[r] << c0);
+    const uint32_t dst = dst_s + r * run_bytes;
+    if (leader)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(run_bytes), "r"(bar_s)
+                   : "memory");
   }
 }
 
@@ -961,11 +961,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     if (blk < pp.ntiles) tma_expect(bar0_s, T);
   }
   __syncthreads();
-  const uint32_t wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform (CUTLASS idiom)
+  const uint32_t wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarps = blockDim.x >> 5;
   const bool issuer = (threadIdx.x & 31u) == 0u;   // lane 0 of every warp issues its share of the copies
-  if (tma && issuer && blk < pp.ntiles) {
+  if (tma && blk < pp.ntiles) {
     const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
-    tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0, wid, nwarps);
+    tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0, wid, nwarps, issuer);
   }
   {  // stage the micro-program once per CTA -- after the first tile's loads are in flight, so the
      // latency of these small global reads hides behind the HBM fetch
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         const uint64_t nbase = deposit(nxt & outer_mask, pp.outer_segs, pp.n_outer_segs);
         tma_expect(bar0_s + 8u * (uint32_t)(b ^ 1), T);
         tma_load_tile(pp, pp.state + ((nxt >> pp.outer_bits) << pp.P) + nbase, tiles_s + (uint32_t)(b ^ 1) * T * 16u,
-                      bar0_s + 8u * (uint32_t)(b ^ 1), T, c0, 0u, 1u);
+                      bar0_s + 8u * (uint32_t)(b ^ 1), T, c0, 0u, 1u, true);
       }
       uint32_t done = 0;
       while (!done) {
@@ -1087,10 +1088,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const bool multi = nbuf == 1;   // persistent mode keeps every bulk group on thread 0
-        if (multi ? issuer : threadIdx.x == 0) {
-#pragma unroll 4
-          for (uint32_t r = multi ? wid : 0u; r < nruns; r += multi ? nwarps : 1u) {
+        if (nbuf == 1) {   // every warp issues its share (uniform loop, leader lane issues + commits)
+          for (uint32_t r = wid; r < nruns; r += nwarps) {
+            double2* dst = sp + ((uint64_t)pp.run_hi[r] << c0);
+            const uint32_t srcs = tile_s + r * run_bytes;
+            if (issuer)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(srcs),
+                           "r"(run_bytes)
+                           : "memory");
+          }
+          if (issuer) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (threadIdx.x == 0) {   // persistent mode keeps every bulk group on thread 0
+          for (uint32_t r = 0; r < nruns; ++r) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
                              sp + ((uint64_t)pp.run_hi[r] << c0)),
                          "r"(tile_s + r * run_bytes), "r"(run_bytes)

@@ -878,6 +878,7 @@ struct Planner {
         if ((tile >> a) & 1ull) pp.ax_col[a] = (int8_t)local_of(tile, a);
         if ((tile >> (a + h->nmax)) & 1ull) pp.ax_row[a] = (int8_t)local_of(tile, a + h->nmax);
       }
+    for (int a = 0; a < h->nmax; ++a) pp.nfree_cols += pp.ax_col[a] >= 0;
     {  // TMA bulk path: low tile segment contiguous from physical bit 0, runs of >= 128 B, <= 128 runs
       const int c0 = pp.tile_segs[0].len;
       pp.use_tma = h->tma && pp.tile_segs[0].dst == 0 && c0 >= 3 && (t - c0) <= 7;
@@ -952,6 +953,8 @@ struct Planner {
         g.type = OP_GROUP; g.pred_bit = -1; g.nb = 4; g.aux = (int)it.ops.size();
         g.b[0] = (uint8_t)local_of(tile, A + n); g.b[1] = (uint8_t)local_of(tile, B + n);
         g.b[2] = (uint8_t)local_of(tile, A); g.b[3] = (uint8_t)local_of(tile, B);
+        for (int i = 0; i < 4; ++i) g.b[4 + i] = g.b[i];
+        std::sort(g.b + 4, g.b + 8);
         dev_ops.push_back(g);
         for (const HostOp* ho : it.ops) dev_ops.push_back(make_sub(ho, A, B, tile, P.const_begin));
         writes = true;
