@@ -100,3 +100,19 @@ def all_reduce_results(fidelity, hist, device=None):
         dist.all_reduce(buf)
     out = buf.cpu().numpy()
     return float(out[0] / max(out[1], 1.0)), int(round(out[1])), np.rint(out[2:]).astype(np.int64)
+
+
+def fidelity_squared(rho, reference):
+    """``qapi.fidelity(qubits, reference, squared=True)`` on a reduced density matrix read back from
+    the engine (``util/helper.py:151, 209-214``; ``examples/run_experiment.py:74-75``): <phi|rho|phi> for
+    a ket reference, Uhlmann's (Tr sqrt(sqrt(sigma) rho sqrt(sigma)))^2 for a density-matrix
+    reference.  Host-side, for the small (<= 2^5) matrices the read-out produces."""
+    rho = np.asarray(rho, dtype=complex)
+    ref = np.asarray(reference, dtype=complex)
+    if ref.ndim == 1 or 1 in ref.shape:
+        v = ref.reshape(-1)
+        return float(np.real(v.conj() @ rho @ v))
+    lam, vec = np.linalg.eigh(ref)
+    sq = (vec * np.sqrt(np.clip(lam, 0, None))) @ vec.conj().T
+    ev = np.linalg.eigvalsh(sq @ rho @ sq)
+    return float(np.sum(np.sqrt(np.clip(ev, 0, None))) ** 2)

@@ -1,0 +1,113 @@
+"""Edge cases of the boundary: the reference's own error paths (dqc_control.py:283-287, 953-974) on the
+executor (CPU), and empty / minimal / maximal inputs on the engine (GPU)."""
+import numpy as np
+import pytest
+
+from dqc_simulator_b200 import executor, hardware
+from dqc_simulator_b200 import instructions as ins
+from oracle.numpy_engine import OracleEngine
+
+H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+X = np.array([[0, 1], [1, 0]], dtype=complex)
+
+
+def test_scheduling_error_when_no_comm_qubit_is_free():
+    """Three remote gates in one slice on QPUs with two comm qubits: the reference raises
+    'Scheduling error: No comm-qubits free' (dqc_control.py:283-287); 'correct' reserves one comm
+    qubit per remote gate until its disentangle_start."""
+    ops = {
+        "node_0": [[(ins.INSTR_INIT, [2, 3, 4]), (2, "node_1", "cat", "entangle"), (3, "node_1", "cat", "entangle"),
+                    (4, "node_1", "cat", "entangle")]],
+        "node_1": [[(ins.INSTR_INIT, [2]), ("node_0", "cat", "correct"), ("node_0", "cat", "correct"),
+                    ("node_0", "cat", "correct")]],
+    }
+    dqc = hardware.DQCSpec.uniform(2, num_positions=6, num_comm_qubits=2)
+    with pytest.raises(Exception, match="No comm-qubits free"):
+        executor.DQCExecutor(ops, dqc, OracleEngine("dm", 8, 1)).run()
+
+
+def test_unfinished_circuit_is_detected():
+    """A 'correct' with no matching 'entangle' never completes: UnfinishedQuantumCircuitError, like
+    DQCMasterProtocol.check_quantum_circuit_finished (dqc_control.py:953-974)."""
+    ops = {"node_0": [[(ins.INSTR_INIT, [2])]], "node_1": [[(ins.INSTR_INIT, [2]), ("node_0", "cat", "correct")]]}
+    dqc = hardware.DQCSpec.uniform(2, num_positions=4, num_comm_qubits=2)
+    with pytest.raises(executor.UnfinishedQuantumCircuitError):
+        executor.DQCExecutor(ops, dqc, OracleEngine("dm", 6, 1)).run()
+
+
+def test_gate_on_empty_memory_position_is_an_error():
+    ops = {"node_0": [[(ins.INSTR_X, 3)]]}
+    dqc = hardware.DQCSpec.uniform(1, num_positions=5)
+    with pytest.raises(RuntimeError, match="holds no qubit"):
+        executor.DQCExecutor(ops, dqc, OracleEngine("ket", 4, 1)).run()
+
+
+def test_empty_circuit_runs():
+    ex = executor.DQCExecutor({"node_0": [[]], "node_1": []}, hardware.DQCSpec.uniform(2), OracleEngine("ket", 2, 1)).run()
+    assert ex.finished and ex.measurements == 0
+
+
+def test_invalid_measurement_result_message():
+    """_apply_if mirrors the reference's ValueError text for outcomes that are not 0/1
+    (dqc_control.py:351-359, 396-403)."""
+    ex = executor.DQCExecutor({"node_0": [[]]}, hardware.DQCSpec.uniform(1), OracleEngine("ket", 2, 1))
+    with pytest.raises(ValueError, match="Measurement result must be an integer with value 0 or 1"):
+        ex._apply_if(executor.QuantumProgram(), ins.INSTR_X, 0, 2)
+
+
+# ---- engine (GPU) ---------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_engine_minimal_and_empty_inputs():
+    from dqc_simulator_b200.engine import Engine
+
+    e = Engine("ket", 1, 1)
+    e.flush(); e.sync()                                    # empty queue
+    assert e.full_state(0)[0, 0] == 1 and e.live == []
+    e.alloc_axis(0)
+    e.apply_1q(0, H)
+    e.measure(0, 63, 1, False, 0.0)                        # last creg bit, forced outcome
+    assert int(e.read_creg_words()[0]) == 1 << 63
+    assert abs(e.full_state(0)[0, 1] - 1) < 1e-15
+    e.free_axis(0)
+    assert e.live == [] and abs(e.full_state(0)[0, 0] - 1) < 1e-15
+    d = Engine("dm", 1, 3)
+    d.alloc_axis(0)
+    d.apply_1q(0, X)
+    d.depolarize([0], 1.0)                                 # fully depolarised
+    assert np.allclose(d.reduced_dm([0], 2), np.eye(2) / 2)
+    assert d.histogram([0]).tolist() == [3, 0]
+
+
+@pytest.mark.gpu
+def test_large_batch_of_tiny_registers():
+    from dqc_simulator_b200.engine import Engine
+
+    e = Engine("ket", 2, 200000, seed=5)
+    for a in range(2):
+        e.alloc_axis(a)
+    e.apply_1q(0, H)
+    e.apply_2q(0, 1, np.eye(4)[[0, 1, 3, 2]])
+    e.measure(0, 0, -1, False, 0.0)
+    e.measure(1, 1, -1, False, 0.0)
+    hist = e.histogram([0, 1])
+    assert hist[1] == 0 and hist[2] == 0 and hist.sum() == 200000      # Bell pair: outcomes agree
+    assert abs(hist[0] - 100000) < 2000
+
+
+@pytest.mark.gpu
+def test_register_capacity_and_argument_errors():
+    from dqc_simulator_b200.engine import Engine, EngineError
+
+    e = Engine("dm", 3, 1)
+    for a in range(3):
+        e.alloc_axis(a)
+    with pytest.raises(EngineError, match="out of range"):
+        e.alloc_axis(3)
+    with pytest.raises(EngineError, match="axes must differ"):
+        e.apply_2q(1, 1, np.eye(4))
+    with pytest.raises(EngineError, match="occupied"):
+        e.inject_2q(0, 1, [1, 0, 0, 0], False)
+    with pytest.raises(EngineError, match="k = 1 or 2"):
+        e.depolarize([0, 1, 2], 0.1)
+    with pytest.raises(EngineError):
+        Engine("ket", 41, 1)

@@ -167,3 +167,22 @@ def test_host_philox_matches_oracle_stream():
         u, u2 = philox.shot_uniforms(seed, np.array([shot]), draw)
         hu, hu2 = philox_host.shot_uniforms(seed, shot, draw)
         assert hu == float(u[0]) and hu2 == float(u2[0])
+
+
+def test_fidelity_squared_ket_and_uhlmann():
+    from dqc_simulator_b200.experiment import fidelity_squared
+
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=4) + 1j * rng.normal(size=4)
+    v /= np.linalg.norm(v)
+    a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    rho = a @ a.conj().T
+    rho /= np.trace(rho)
+    pure = np.outer(v, v.conj())
+    assert abs(fidelity_squared(rho, v) - fidelity_squared(rho, pure)) < 1e-12     # Uhlmann reduces to <v|rho|v>
+    assert abs(fidelity_squared(rho, rho) - 1) < 1e-10
+    b = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    sig = b @ b.conj().T
+    sig /= np.trace(sig)
+    assert abs(fidelity_squared(rho, sig) - fidelity_squared(sig, rho)) < 1e-10      # symmetric
+    assert 0 < fidelity_squared(rho, sig) < 1
