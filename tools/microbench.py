@@ -50,6 +50,7 @@ def main():
     # ---- ket, single shot
     n = a.ket_n
     e = Engine("ket", n, 1, tile_bits=a.tile, fuse=False)
+    e.set_option("merge", 0)          # every API op = one pass (no host-side folding of repeated gates)
     for q in range(n):
         e.alloc_axis(q)
         e.apply_1q(q, H)
@@ -64,6 +65,7 @@ def main():
         report(f"ket{n} 2q dense ({q0},{q1})", *timed(e, lambda: e.apply_2q(q0, q1, u4)))
     report(f"ket{n} diag2 (2,{n-1})", *timed(e, lambda: e.apply_diag([2, n - 1], np.exp(1j * np.arange(4)))))
     e.set_option("fuse", 1)
+    e.set_option("merge", 1)
 
     def many():
         for q in range(8):
@@ -79,6 +81,7 @@ def main():
     # ---- dm, batched
     n, B = a.dm_n, a.dm_batch
     e = Engine("dm", n, B, tile_bits=a.tile, fuse=False)
+    e.set_option("merge", 0)
     for q in range(n):
         e.alloc_axis(q)
         e.apply_1q(q, H)
@@ -92,6 +95,7 @@ def main():
     report(f"dm{n}x{B} 2q dense (1,{n-1})", *timed(e, lambda: e.apply_2q(1, n - 1, u4)))
     report(f"dm{n}x{B} measure q={n-1} keep", *timed(e, lambda: e.measure(n - 1, 0, -1, False, 0.003)))
     e.set_option("fuse", 1)
+    e.set_option("merge", 1)
 
     def seq():
         e.depolarize([0], 1e-3); e.depolarize([1], 1e-3)
