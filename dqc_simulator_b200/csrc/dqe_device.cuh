@@ -54,7 +54,9 @@ enum OpType : int32_t {
 
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
-constexpr int kMaxConstsPerPass = 512;   // double2 entries staged in shared memory per pass (8 KiB)
+constexpr int kMaxConstsKet = 512;       // double2 constants staged in shared memory per pass (8 KiB)
+constexpr int kMaxConstsDm = 256;        // dm: 4 KiB, so that eight 16 KiB-tile CTAs fit one SM
+__host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMaxConstsKet : kMaxConstsDm; }   // double2 entries staged in shared memory per pass (8 KiB)
 constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
 struct __align__(16) MicroOp {
@@ -937,7 +939,7 @@ template <int MAXT, int MINB, int FORM>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
-  __shared__ double2 s_consts[kMaxConstsPerPass];
+  __shared__ double2 s_consts[max_consts(FORM)];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[kMaxDiagRun];

@@ -993,7 +993,7 @@ struct Planner {
 
   // every pass of this handle has at most 8 tiles per shot (cluster size limit) when the whole
   // register is at most 3 bits wider than a tile
-  bool cluster_mode() const { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 3; }
+  bool cluster_mode() const { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 4; }
 
   bool plan() {
     std::vector<const HostOp*> cur;
@@ -1037,7 +1037,7 @@ struct Planner {
       uint64_t tile = 0;
       // every op may need a group header in the worst case -> 2 slots per op
       const bool fits = cur.empty() || (h->fuse && 2 * ((int)cur.size() + 1) <= kMaxOpsPerPass &&
-                                        nconst + op.nconst <= kMaxConstsPerPass &&
+                                        nconst + op.nconst <= max_consts(h->formalism) &&
                                         choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
         if (!close(cur, need, live)) return false;
@@ -1246,7 +1246,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1294,6 +1294,8 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(carveout)", e);
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(cluster16)", e);
     }
   }
   if ((e = cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream)) != cudaSuccess) return bail("memset", e);

@@ -168,8 +168,9 @@ int dqe_ipc_close(dqe_t* h, void* peer_state);
 int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* m, int ctrl_axis);
 
 /* ---- tuning + instrumentation --------------------------------------------------------------- */
-/* key: "tile_bits" (log2 amplitudes staged per CTA, default 11 = 32 KiB), "threads" (per CTA: 64,
- * 128 (default), 256), "min_run_bits" (log2 of the shortest contiguous run a tile may be built
+/* key: "tile_bits" (log2 amplitudes staged per CTA; default 11 = 32 KiB with 128 threads, or 10 = 16 KiB
+ * with 64 threads for registers of <= 14 bits, where the <= 16 tiles of a shot form one thread-block
+ * cluster), "threads" (per CTA: 64, 128, 256), "cluster" (0: measurements always cut a pass), "min_run_bits" (log2 of the shortest contiguous run a tile may be built
  * from, default 5), "fuse" (0: one op per pass), "merge" (0: no host-side folding of axis-local
  * ops), "group" (0: no register-resident qubit-pair sweeps), "tma" (0: per-thread loads instead
  * of cp.async.bulk), "persistent" (1: persistent CTAs with a double-buffered tile ring instead of

@@ -118,8 +118,10 @@ def test_planner_measurement_bound_pass_count():
     assert st["passes"] < st11["passes"] < 2 * st["passes"]
     # cluster mode (default): the <= 8 tiles of a shot form a thread-block cluster, the measurement
     # is a micro-op (DSMEM sum + on-chip draw) and no longer cuts the pass
-    stc, exc = _plan("grover")
+    stc, exc = _plan("grover", tile_bits=11)
     assert exc.measurements == 288 and stc["finish_launches"] == 0 and stc["passes"] < 0.6 * st11["passes"]
+    std, _ = _plan("grover")        # default for a 14-bit register: 2^10 tiles, 16-CTA clusters
+    assert std["finish_launches"] == 0 and std["passes"] < st11["passes"]
 
 
 def test_planner_switches():
