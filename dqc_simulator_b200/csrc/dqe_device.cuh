@@ -1233,6 +1233,29 @@ __global__ void __launch_bounds__(256) k_peer_1q(double2* __restrict__ lo, doubl
   }
 }
 
+// global <-> local axis swap over peer memory: lo[j with bit L = 1] <-> hi[j with bit L = 0]
+__global__ void __launch_bounds__(256) k_peer_swap(double2* __restrict__ lo, double2* __restrict__ hi, uint64_t begin,
+                                                   uint64_t end, int L) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t lowmask = (1ull << L) - 1ull;
+  for (uint64_t j0 = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < end; j0 += 4 * stride) {
+    double2 a[4], b[4];
+    uint64_t il[4], ih[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t j = j0 + (uint64_t)k * stride;
+      ih[k] = ((j & ~lowmask) << 1) | (j & lowmask);   // bit L = 0
+      il[k] = ih[k] | (1ull << L);                      // bit L = 1
+      if (j < end) { a[k] = lo[il[k]]; b[k] = hi[ih[k]]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t j = j0 + (uint64_t)k * stride;
+      if (j < end) { lo[il[k]] = b[k]; hi[ih[k]] = a[k]; }
+    }
+  }
+}
+
 // reduced density matrix / fidelity of <= 5 axes.  `rest` enumerates the live bits that are
 // traced over (dense index -> physical offset through segs).
 struct ReadoutParams {

@@ -1769,6 +1769,24 @@ int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* 
   return 0;
 }
 
+int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_axis) {
+  if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
+  if (h->formalism != DQE_KET || h->batch != 1) return fail(h, DQE_EUNSUPPORTED, "peer_swap: single-shot ket only");
+  if (!peer_state || (my_bit | 1) != 1 || (half | 1) != 1 || local_axis < 0 || local_axis >= h->nmax)
+    return fail(h, DQE_EINVAL, "peer_swap: bad argument");
+  if (h->live_axes != (h->nmax >= 64 ? ~0ull : ((1ull << h->nmax) - 1ull)))
+    return fail(h, DQE_EINVAL, "peer_swap: every local axis must be live");
+  const uint64_t npairs = 1ull << (h->P - 1), mid = npairs >> 1;
+  double2* lo = my_bit == 0 ? h->state : (double2*)peer_state;
+  double2* hi = my_bit == 0 ? (double2*)peer_state : h->state;
+  CK(cudaSetDevice(h->device));
+  k_peer_swap<<<h->num_sms * 8, 256, 0, h->stream>>>(lo, hi, half ? mid : 0, half ? npairs : mid, local_axis);
+  h->stats[2]++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (!h || !key) return DQE_EINVAL;
   if (int rc = do_flush(h)) return rc;

@@ -67,6 +67,7 @@ ABI = {
     "dqe_ipc_close": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "dqe_peer_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p,
                                    ctypes.c_int]),
+    "dqe_peer_swap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dqe_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "dqe_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "dqe_reset_stats": (ctypes.c_int, [ctypes.c_void_p]),
@@ -357,6 +358,9 @@ class Engine:
     def peer_1q(self, peer_ptr, my_bit, half, m, ctrl_axis=-1):
         _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2, 2))
         self._ck(self._lib.dqe_peer_1q(self._h, ctypes.c_void_p(peer_ptr), int(my_bit), int(half), p, int(ctrl_axis)))
+
+    def peer_swap(self, peer_ptr, my_bit, half, local_axis):
+        self._ck(self._lib.dqe_peer_swap(self._h, ctypes.c_void_p(peer_ptr), int(my_bit), int(half), int(local_axis)))
 
     # ------------------------------------------------------------------ instrumentation
     def stats(self):

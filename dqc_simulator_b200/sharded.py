@@ -57,6 +57,12 @@ class GpuShard:
             self._peer_ptrs[partner] = self.eng.ipc_open(self._peer_handles[partner])
         self.eng.peer_1q(self._peer_ptrs[partner], my_bit, my_bit, m, ctrl_axis)
 
+    def peer_swap(self, partner, my_bit, local_axis):
+        """Global <-> local axis swap in place over peer memory (kernel ``k_peer_swap``)."""
+        if partner not in self._peer_ptrs:
+            self._peer_ptrs[partner] = self.eng.ipc_open(self._peer_handles[partner])
+        self.eng.peer_swap(self._peer_ptrs[partner], my_bit, my_bit, local_axis)
+
     def sync(self):
         import torch
 
@@ -89,7 +95,7 @@ class GpuShard:
 
 
 class ShardedKet:
-    def __init__(self, n, shard, rank, world, group=None, seed=0, peer=False):
+    def __init__(self, n, shard, rank, world, group=None, seed=0, peer=False, peer_gates=False):
         g = int(round(np.log2(world)))
         if 2 ** g != world:
             raise ValueError("world size must be a power of two")
@@ -107,8 +113,10 @@ class ShardedKet:
         self.exchanged_bytes = 0
         self.exchange_seconds = 0.0
         self._pending = 1.0 + 0.0j      # rank-local scalar phase not yet applied (folded into the next table)
-        self.peer = bool(peer)          # gates on a global target run as ONE kernel over peer memory
-        self.peer_gates = 0
+        self.peer = bool(peer)          # exchanges run as ONE kernel per rank over peer memory (k_peer_swap)
+        self.peer_gates = bool(peer_gates)  # also run the first gate on a global target in place (k_peer_1q);
+        #                                     measured slower than swap + local gate (twice the NVLink bytes)
+        self.peer_gate_count = 0
         self.peer_seconds = 0.0
         self._peer_uses = {}            # logical axis -> mixing gates served over peer memory while global
         if self.peer:
@@ -146,6 +154,16 @@ class ShardedKet:
 
         self._apply_pending()       # the pending phase belongs to the data that is about to move
         self.shard.sync()
+        if self.peer:               # one kernel per rank over peer memory: no staging, no NCCL
+            dist.barrier(group=self.group)
+            t0 = time.perf_counter()
+            self.shard.peer_swap(self.rank ^ (1 << j), (self.rank >> j) & 1, L)
+            self.shard.sync()
+            dist.barrier(group=self.group)
+            self.exchanges += 1
+            self.exchanged_bytes += (2 ** (self.m - 1)) * 16
+            self.exchange_seconds += time.perf_counter() - t0
+            return
         t0 = time.perf_counter()
         buf = self.shard.buffer()
         mybit = (self.rank >> j) & 1
@@ -183,7 +201,7 @@ class ShardedKet:
         """Policy: the first gate that mixes a global axis runs over peer memory in place (cheaper than
         a swap when the axis is mixed once, e.g. a GHZ ladder); a second one means the axis is hot (a
         QFT target): swap it into a local slot and keep it there."""
-        if not (self.peer and self._is_global(axis)):
+        if not (self.peer and self.peer_gates and self._is_global(axis)):
             return False
         if self._peer_uses.get(axis, 0) >= 1:
             self._peer_uses[axis] = 0
@@ -207,7 +225,7 @@ class ShardedKet:
             self.shard.peer_1q(self.rank ^ (1 << j), (self.rank >> j) & 1, m, ctrl_slot)
         self.shard.sync()
         dist.barrier(group=self.group)
-        self.peer_gates += 1
+        self.peer_gate_count += 1
         self.peer_seconds += time.perf_counter() - t0
 
     def apply_1q(self, axis, m):

@@ -166,6 +166,11 @@ int dqe_ipc_export(dqe_t* h, void* handle64);
 int dqe_ipc_open(dqe_t* h, const void* handle64, void** peer_state);
 int dqe_ipc_close(dqe_t* h, void* peer_state);
 int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* m, int ctrl_axis);
+/* Swap the global axis with LOCAL axis `local_axis` (the data movement of a global<->local qubit swap):
+ * element (global bit 0, local bit 1) <-> (global bit 1, local bit 0) at equal remaining bits, done in
+ * place over peer memory, this rank handling one half of the pairs.  No staging buffer, both NVLink
+ * directions busy at once. */
+int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_axis);
 
 /* ---- tuning + instrumentation --------------------------------------------------------------- */
 /* key: "tile_bits" (log2 amplitudes staged per CTA; default 11 = 32 KiB with 128 threads, or 10 = 16 KiB

@@ -352,3 +352,33 @@ def test_chi_square_dm_trajectory_outcomes():
     exp = shots / 4.0
     chi2 = float(((hist - exp) ** 2 / exp).sum())
     assert chi2 < 25.0, (hist, chi2)     # dof = 3, P(chi2 > 25) ~ 1.5e-5
+
+
+@pytest.mark.parametrize("L", [0, 3, 5])
+def test_peer_memory_axis_swap(L):
+    """k_peer_swap: exchange the rank-bit axis with local axis L in place; two engines on one GPU play
+    the two ranks, each handling half of the pairs."""
+    import ctypes
+
+    from dqc_simulator_b200.engine import Engine
+
+    m = 6
+    rng = np.random.default_rng(8)
+    psi = rng.normal(size=2 ** (m + 1)) + 1j * rng.normal(size=2 ** (m + 1))
+    shards, ptrs = [], []
+    for r in range(2):
+        e = Engine("ket", m, 1)
+        e.set_state(0, psi[r * 2 ** m:(r + 1) * 2 ** m], list(range(m)))
+        dev, nbytes = ctypes.c_void_p(), ctypes.c_int64()
+        e._ck(e._lib.dqe_state_ptr(e._h, ctypes.byref(dev), ctypes.byref(nbytes)))
+        shards.append(e)
+        ptrs.append(dev.value)
+    for r in range(2):
+        shards[r].peer_swap(ptrs[1 - r], my_bit=r, half=r, local_axis=L)
+    for e in shards:
+        e.sync()
+    got = np.concatenate([e.full_state(0)[0] for e in shards])
+    idx = np.arange(2 ** (m + 1))
+    g, l = (idx >> m) & 1, (idx >> L) & 1
+    src = (idx & ~((1 << m) | (1 << L))) | (l << m) | (g << L)     # swap bits m and L
+    assert np.array_equal(got, psi[src])

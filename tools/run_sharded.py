@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--qubits", dest="n", type=int, default=30)
     ap.add_argument("--circuit", default="qft")
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--peer", type=int, default=0, help="1: gates on global axes as one kernel over peer memory")
+    ap.add_argument("--peer", type=int, default=0, help="1: exchanges as one kernel per rank over CUDA-IPC peer memory (k_peer_swap); 2: also in-place peer gates")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -37,7 +37,7 @@ def main():
     best = None
     for rep in range(a.reps):
         shard = GpuShard(a.n - g, local, rank == 0)
-        sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer))
+        sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer), peer_gates=a.peer >= 2)
         shard.eng.time_passes(True)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -66,7 +66,7 @@ def main():
         st = shard.eng.stats()
         res = dict(circuit=a.circuit, n=a.n, n_gpus=world, seconds=float(t[1]), max_abs_err=float(t[0]),
                    norm=norm, exchanges=sk.exchanges, exchange_bytes_per_rank=sk.exchanged_bytes,
-                   exchange_seconds=float(t[2]), peer=bool(a.peer), peer_gates=sk.peer_gates, peer_seconds=sk.peer_seconds,
+                   exchange_seconds=float(t[2]), peer=bool(a.peer), peer_gates=sk.peer_gate_count, peer_seconds=sk.peer_seconds,
                    host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
                    micro_ops=st["micro_ops"], pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
                    nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges else None,
