@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--qubits", dest="n", type=int, default=30)
     ap.add_argument("--circuit", default="qft")
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--peer", type=int, default=0, help="1: exchanges as one kernel per rank over CUDA-IPC peer memory (k_peer_swap); 2: also in-place peer gates")
+    ap.add_argument("--peer", type=int, default=1, help="1: exchanges as one kernel per rank over CUDA-IPC peer memory (k_peer_swap); 2: also in-place peer gates")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
