@@ -283,6 +283,35 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
     prep[threadIdx.x] = d;
   }
   __syncthreads();
+  if (T == 16u * blockDim.x) {
+    // register-blocked form: a thread owns the 16 amplitudes i = tid + e * blockDim.  For every table
+    // the index splits into a part fixed by the thread id (tile bits below log2(blockDim), computed once
+    // per op) and a part that depends on e only (bits above; identical for all threads, compile-time e).
+    const int lb = 31 - __clz(blockDim.x);
+    double2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = tile[threadIdx.x + (uint32_t)e * blockDim.x];
+    for (int k = 0; k < count; ++k) {
+      const DiagPrep d = prep[k];
+      if (!d.on) continue;
+      const uint32_t tid = threadIdx.x;
+      const uint32_t lowmask = blockDim.x - 1u;
+      // thread-fixed contribution: masks that live in the low (thread id) bits
+      const uint32_t tf = d.fixed + (((tid & d.m0 & lowmask)) ? d.s0 : 0u) + (((tid & d.m1 & lowmask)) ? d.s1 : 0u) +
+                          (((tid & d.m2 & lowmask)) ? d.s2 : 0u) + (((tid & d.m3 & lowmask)) ? d.s3 : 0u);
+      // e-dependent masks (shifted down to bit positions of e)
+      const uint32_t h0 = d.m0 >> lb, h1 = d.m1 >> lb, h2 = d.m2 >> lb, h3 = d.m3 >> lb;
+      const double2* tb = s_consts + d.c_off + tf;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const uint32_t idx = ((e & h0) ? d.s0 : 0u) + ((e & h1) ? d.s1 : 0u) + ((e & h2) ? d.s2 : 0u) + ((e & h3) ? d.s3 : 0u);
+        v[e] = cmul(v[e], tb[idx]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) tile[threadIdx.x + (uint32_t)e * blockDim.x] = v[e];
+    return;
+  }
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
     double2 v = tile[i];
     for (int k = 0; k < count; ++k) {
