@@ -100,6 +100,14 @@ struct PassParams {
   int32_t nfree_cols, pad3;
   uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
+  // dm diagonal enumeration (probabilities), host-precomputed.  Free variable k = k-th axis (ascending)
+  // whose column bit lies in the tile.
+  int8_t ax_ord[24];       // free-variable index of an axis, -1 = column bit outside the tile
+  uint32_t dg_mask[16];    // tile-index contribution of free variable k: column bit | row bit (if in the tile)
+  int8_t dg_req[16];       // physical row bit (outside the tile) whose base value variable k must equal, -1 = none
+  int8_t dg_fix_src[16], dg_fix_dst[16];   // column bit outside, row bit inside: tile bit dst = base bit src
+  int32_t dg_nfix;
+  uint32_t dg_eq_mask;     // axes with both bits outside: base bit a must equal base bit a + nmax
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
   Seg tile_segs[16];
   Seg outer_segs[24];
@@ -115,6 +123,17 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 acc) {
   acc.x = fma(-a.y, b.y, acc.x);
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+// conj(a) * b and acc + conj(a) * b without materialising the conjugate (operand negation is free)
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ double2 cfmac(double2 a, double2 b, double2 acc) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
   return acc;
 }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -396,6 +415,32 @@ __device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const Micro
   }
 }
 
+// dm: partial outcome probabilities of axis `abit` over the diagonal elements of rho held by this tile.
+// The enumeration (which tile elements are diagonal, which base bits must agree) is host-precomputed in
+// PassParams; the tile-uniform part costs a few uniform instructions, the per-element part one OR per
+// free variable.
+__device__ __forceinline__ void dm_diag_partials(const double2* tile, const PassParams& pp, uint64_t base, int abit,
+                                                 double& a0, double& a1) {
+  const int n = pp.nmax, nfree = pp.nfree_cols;
+  if ((((base >> n) ^ base) & (uint64_t)pp.dg_eq_mask) != 0ull) return;   // no diagonal element in this tile
+  uint32_t ifix = 0, req_mask = 0, req_val = 0;
+  for (int f = 0; f < pp.dg_nfix; ++f) ifix |= (uint32_t)((base >> pp.dg_fix_src[f]) & 1ull) << pp.dg_fix_dst[f];
+  for (int k = 0; k < nfree; ++k) {
+    const int rb = pp.dg_req[k];
+    if (rb >= 0) { req_mask |= 1u << k; req_val |= (uint32_t)((base >> rb) & 1ull) << k; }
+  }
+  const int kidx = pp.ax_ord[abit];
+  const uint32_t vfix = (uint32_t)((base >> abit) & 1ull);
+  for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
+    if ((d ^ req_val) & req_mask) continue;
+    uint32_t i = ifix;
+    for (int k = 0; k < nfree; ++k) i |= ((d >> k) & 1u) ? pp.dg_mask[k] : 0u;
+    const double w = tile[i].x;
+    const uint32_t va = kidx >= 0 ? ((d >> kidx) & 1u) : vfix;
+    if (va) a1 += w; else a0 += w;
+  }
+}
+
 template <int FORM>
 __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                          uint64_t base, uint64_t blk, double* red) {
@@ -416,27 +461,8 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
       }
     }
   } else {
-    // only the diagonal of rho matters: enumerate it directly.  Free variables = axes whose column
-    // bit is inside the tile; the row bit must repeat it (inside the tile, or fixed by the tile base).
-    const int n = pp.nmax;
-    const int nfree = pp.nfree_cols;
-    for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
-      uint32_t i = 0, va = 0;
-      bool ok = true;
-      int k = 0;
-      for (int a = 0; a < n; ++a) {
-        const int cl = pp.ax_col[a], rl = pp.ax_row[a];
-        const uint32_t v = cl >= 0 ? ((d >> k++) & 1u) : (uint32_t)((base >> a) & 1ull);
-        if (cl >= 0) i |= v << cl;
-        if (rl >= 0) i |= v << rl;
-        else ok = ok && (((base >> (a + n)) & 1ull) == v);
-        if (a == abit) va = v;
-      }
-      if (ok) {
-        const double w = tile[i].x;
-        if (va) a1 += w; else a0 += w;
-      }
-    }
+    // only the diagonal of rho matters: enumerate it directly
+    dm_diag_partials(tile, pp, base, abit, a0, a1);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -455,76 +481,66 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
 }
 
 
-// Fused measurement for registers whose tiles fit one thread-block cluster (<= 8 CTAs per shot):
-// the tile partials are summed over the cluster through distributed shared memory, every CTA of
-// the shot draws the same Philox number, and the pass simply goes on -- no kernel boundary.
+// split-phase cluster barrier (arrive at kernel start, wait before the first DSMEM write: every CTA of
+// the cluster is then known to be running, and nobody stalls for it)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Fused measurement for registers whose tiles fit one thread-block cluster (<= 16 CTAs per shot):
+// every CTA PUSHES its tile partials into the shared memory of all CTAs of the shot (DSMEM stores, fire
+// and forget), one cluster barrier, then each CTA sums the 16 local slots in rank order and draws the same
+// Philox number -- the pass simply goes on, no kernel boundary, no remote loads, no exit barrier.
 template <int FORM>
 __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                uint64_t base, uint64_t shot, uint64_t cw, double* red,
-                                               double (*part)[2], MeasRec* mrec, int mcount) {
+                                               double (*part)[16][2], MeasRec* mrec, int mcount) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int par = mcount & 1;
-  // 1. this tile's partials (same arithmetic as op_probs, result in red[0..1])
-  {
-    MicroOp pr = op;
-    double a0 = 0.0, a1 = 0.0;
-    const int abit = op.aux;
-    if constexpr (FORM == 0) {
-      const int jb = op.b[0];
-      if (jb >= kOuter) {
-        double a = 0.0;
-        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) { const double2 v = tile[i]; a += fma(v.x, v.x, v.y * v.y); }
-        if ((base >> (jb - kOuter)) & 1ull) a1 = a; else a0 = a;
-      } else {
-        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
-          const double2 v = tile[i];
-          const double w = fma(v.x, v.x, v.y * v.y);
-          if ((i >> jb) & 1u) a1 += w; else a0 += w;
-        }
-      }
+  // 1. this tile's partials (same arithmetic as op_probs)
+  double a0 = 0.0, a1 = 0.0;
+  const int abit = op.aux;
+  if constexpr (FORM == 0) {
+    const int jb = op.b[0];
+    if (jb >= kOuter) {
+      double a = 0.0;
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) { const double2 v = tile[i]; a += fma(v.x, v.x, v.y * v.y); }
+      if ((base >> (jb - kOuter)) & 1ull) a1 = a; else a0 = a;
     } else {
-      const int n = pp.nmax;
-      const int nfree = pp.nfree_cols;
-      for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
-        uint32_t i = 0, va = 0;
-        bool ok = true;
-        int k = 0;
-        for (int a = 0; a < n; ++a) {
-          const int cl = pp.ax_col[a], rl = pp.ax_row[a];
-          const uint32_t v = cl >= 0 ? ((d >> k++) & 1u) : (uint32_t)((base >> a) & 1ull);
-          if (cl >= 0) i |= v << cl;
-          if (rl >= 0) i |= v << rl;
-          else ok = ok && (((base >> (a + n)) & 1ull) == v);
-          if (a == abit) va = v;
-        }
-        if (ok) { const double w = tile[i].x; if (va) a1 += w; else a0 += w; }
+      for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+        const double2 v = tile[i];
+        const double w = fma(v.x, v.x, v.y * v.y);
+        if ((i >> jb) & 1u) a1 += w; else a0 += w;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s0 = 0.0, s1 = 0.0;
-      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
-      part[par][0] = s0; part[par][1] = s1;
-    }
-    (void)pr;
+  } else {
+    dm_diag_partials(tile, pp, base, abit, a0, a1);
   }
-  // 2. every CTA of the shot sums all partials in rank order (identical result everywhere)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
+  if (mcount == 0) cluster_wait();   // completes the arrive of the kernel prologue
+  __syncthreads();
+  const unsigned nr = cluster.num_blocks();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+    // 2. push to every CTA of the shot (own slot included)
+    const unsigned me = cluster.block_rank();
+    for (unsigned r = 0; r < nr; ++r) {
+      double* rp = cluster.map_shared_rank(&part[par][me][0], r);
+      rp[0] = s0; rp[1] = s1;
+    }
+  }
   cluster.sync();
+  // 3. every CTA sums the slots in rank order (identical result everywhere) and draws
   if (threadIdx.x == 0) {
     double p0 = 0.0, p1 = 0.0;
-    const unsigned nr = cluster.num_blocks();
-    for (unsigned r = 0; r < nr; ++r) {
-      const double* rp = cluster.map_shared_rank(&part[par][0], r);
-      p0 += rp[0]; p1 += rp[1];
-    }
+    for (unsigned r = 0; r < nr; ++r) { p0 += part[par][r][0]; p1 += part[par][r][1]; }
     const double e = op.p[0];
     const double q0 = (1.0 - e) * p0 + e * p1, q1 = (1.0 - e) * p1 + e * p0;
     const double tot = q0 + q1;
@@ -793,7 +809,6 @@ __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __rest
     }
   }
   if (c_on) {
-    const double2 n00 = conj2(m00), n01 = conj2(m01), n10 = conj2(m10), n11 = conj2(m11);
 #pragma unroll
     for (int co = 0; co < 2; ++co) {
       if (in_c && co == 0) continue;
@@ -802,8 +817,8 @@ __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __rest
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const double2 a = v[EI<ROLE>(r, 0, ro, co)], b = v[EI<ROLE>(r, 1, ro, co)];
-          v[EI<ROLE>(r, 0, ro, co)] = cfma(n01, b, cmul(n00, a));
-          v[EI<ROLE>(r, 1, ro, co)] = cfma(n11, b, cmul(n10, a));
+          v[EI<ROLE>(r, 0, ro, co)] = cfmac(m01, b, cmulc(m00, a));
+          v[EI<ROLE>(r, 1, ro, co)] = cfmac(m11, b, cmulc(m10, a));
         }
     }
   }
@@ -942,8 +957,13 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 // ------------------------------------------------------------------------------------------
 // issue the bulk loads r0, r0+rstep, ... of one tile (a tile = 2^(t-c0) contiguous runs); the
 // issuing lanes of different warps work in parallel -- a single thread needs ~100 cycles per copy
-__device__ __forceinline__ void tma_expect(uint32_t bar_s, uint32_t T) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(T * 16u) : "memory");
+__device__ __forceinline__ void tma_expect(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_bytes(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+               "l"(src), "r"(bytes), "r"(bar_s)
+               : "memory");
 }
 // r0 / rstep must be warp-uniform (every lane runs the loop with the same operands so that the
 // address arithmetic stays on the uniform datapath); only the lane with `leader` set issues.
@@ -964,7 +984,9 @@ __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double
 // the micro-program runs on the tile in buffer b, the TMA load of the CTA's next tile streams into
 // buffer b^1 and the bulk store of the previous tile drains -- the HBM pipe never idles behind the
 // shared-memory / FP64 work of a fused pass.
-template <int MAXT, int MINB, int FORM>
+// PERSIST = false: one tile per CTA (grid = number of tiles) -- the loop state of the persistent form
+// (tile counter, buffer parity, prefetch) disappears at compile time.
+template <int MAXT, int MINB, int FORM, bool PERSIST>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
@@ -973,23 +995,30 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[kMaxDiagRun];
   __shared__ MeasRec s_meas;
-  __shared__ double s_part[2][2];   // [measurement parity][outcome]: this tile's probability partials
+  __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
   const int c0 = pp.tile_segs[0].len;
   const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
-  const int nbuf = pp.nbuf;           // 2 with TMA (prefetch distance 1), 1 otherwise
+  const int nbuf = PERSIST ? pp.nbuf : 1;   // 2 with TMA (prefetch distance 1), 1 otherwise
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
   const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   uint64_t blk = blockIdx.x;
+  if (pp.has_measure) cluster_arrive_relaxed();   // waited for in the first op_measure
   if (tma && threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s + 8u));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (blk < pp.ntiles) tma_expect(bar0_s, T);
+    if (blk < pp.ntiles) {
+      // the micro-program and its constants ride on the first tile's barrier as two more bulk copies
+      const uint32_t ops_bytes = (uint32_t)pp.nops * (uint32_t)sizeof(MicroOp), c_bytes = (uint32_t)pp.nconsts * 16u;
+      tma_expect(bar0_s, T * 16u + ops_bytes + c_bytes);
+      tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_ops), pp.ops, ops_bytes, bar0_s);
+      if (c_bytes) tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_consts), pp.consts, c_bytes, bar0_s);
+    }
   }
   __syncthreads();
   // warp index through a shuffle: the compiler then knows it is warp-uniform (CUTLASS idiom)
@@ -999,15 +1028,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
     tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0, wid, nwarps, issuer);
   }
-  {  // stage the micro-program once per CTA -- after the first tile's loads are in flight, so the
-     // latency of these small global reads hides behind the HBM fetch
+  if (!tma) {  // stage the micro-program with ordinary loads
     const int nw = pp.nops * (int)(sizeof(MicroOp) / 16);
     const uint4* src = reinterpret_cast<const uint4*>(pp.ops);
     uint4* dst = reinterpret_cast<uint4*>(s_ops);
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
     for (int i = threadIdx.x; i < pp.nconsts; i += blockDim.x) s_consts[i] = __ldg(pp.consts + i);
+    __syncthreads();
   }
-  __syncthreads();
 
   uint32_t parity[2] = {0u, 0u};
   for (uint32_t it = 0; blk < pp.ntiles; blk += gridDim.x, ++it) {
@@ -1017,14 +1045,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     const uint64_t shot = blk >> pp.outer_bits;
     const uint64_t base = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
     double2* __restrict__ sp = pp.state + (shot << pp.P) + base;
+    // per-shot classical state: requested before the tile wait so that its latency hides behind the fetch
+    uint64_t cw = pp.creg[shot];
+    MeasRec mr0;
+    if (threadIdx.x == 0) mr0 = pp.rec[shot];   // outcome recorded by a preceding pass / k_finish_measure
 
     if (tma) {
       const uint64_t nxt = blk + gridDim.x;
-      if (threadIdx.x == 0 && nxt < pp.ntiles) {
+      if (PERSIST && threadIdx.x == 0 && nxt < pp.ntiles) {
         // buffer b^1 was stored from at the end of the previous iteration: its reads must be done
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const uint64_t nbase = deposit(nxt & outer_mask, pp.outer_segs, pp.n_outer_segs);
-        tma_expect(bar0_s + 8u * (uint32_t)(b ^ 1), T);
+        tma_expect(bar0_s + 8u * (uint32_t)(b ^ 1), T * 16u);
         tma_load_tile(pp, pp.state + ((nxt >> pp.outer_bits) << pp.P) + nbase, tiles_s + (uint32_t)(b ^ 1) * T * 16u,
                       bar0_s + 8u * (uint32_t)(b ^ 1), T, c0, 0u, 1u, true);
       }
@@ -1054,8 +1086,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       }
       __syncthreads();
     }
-    uint64_t cw = pp.creg[shot];
-    if (threadIdx.x == 0) s_meas = pp.rec[shot];   // outcome recorded by a preceding k_finish_measure
+    if (threadIdx.x == 0) s_meas = mr0;
     __syncthreads();
     int mcount = 0;
 
@@ -1156,11 +1187,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     } else if (!tma) {
       __syncthreads();
     }
+    if constexpr (!PERSIST) break;
   }
   // shared memory must stay valid until the last bulk store has read it
   if (tma && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  // ... and until every CTA of the cluster has read this CTA's probability partials
-  if (pp.has_measure) cooperative_groups::this_cluster().sync();
+  // (fused measurements push their partials and end on a cluster barrier: nothing remote is pending here)
 }
 
 // ------------------------------------------------------------------------------------------

@@ -879,6 +879,28 @@ struct Planner {
         if ((tile >> (a + h->nmax)) & 1ull) pp.ax_row[a] = (int8_t)local_of(tile, a + h->nmax);
       }
     for (int a = 0; a < h->nmax; ++a) pp.nfree_cols += pp.ax_col[a] >= 0;
+    // diagonal enumeration tables for the probability ops (dm_diag_partials)
+    for (int a = 0; a < 24; ++a) pp.ax_ord[a] = -1;
+    for (int k = 0; k < 16; ++k) { pp.dg_mask[k] = 0; pp.dg_req[k] = -1; }
+    if (h->formalism == DQE_DM) {
+      int k = 0;
+      for (int a = 0; a < h->nmax; ++a) {
+        const int cl = pp.ax_col[a], rl = pp.ax_row[a];
+        if (cl >= 0) {
+          if (k >= 16) { err = "planner: too many column bits in a tile"; return false; }
+          pp.ax_ord[a] = (int8_t)k;
+          pp.dg_mask[k] = (1u << cl) | (rl >= 0 ? (1u << rl) : 0u);
+          pp.dg_req[k] = rl >= 0 ? (int8_t)-1 : (int8_t)(a + h->nmax);
+          ++k;
+        } else if (rl >= 0) {
+          if (pp.dg_nfix >= 16) { err = "planner: too many row-only axes in a tile"; return false; }
+          pp.dg_fix_src[pp.dg_nfix] = (int8_t)a; pp.dg_fix_dst[pp.dg_nfix] = (int8_t)rl;
+          ++pp.dg_nfix;
+        } else {
+          pp.dg_eq_mask |= 1u << a;
+        }
+      }
+    }
     {  // TMA bulk path: low tile segment contiguous from physical bit 0, runs of >= 128 B, <= 128 runs
       const int c0 = pp.tile_segs[0].len;
       pp.use_tma = h->tma && pp.tile_segs[0].dst == 0 && c0 >= 3 && (t - c0) <= 7;
@@ -1150,13 +1172,14 @@ int do_flush(dqe_t* h) {
     {
       const void* fn;
       int threads = h->threads;
+      const bool pers = h->persistent != 0;
+#define DQE_KFN(M, B, F) (pers ? (const void*)k_tile_pass<M, B, F, true> : (const void*)k_tile_pass<M, B, F, false>)
       if (h->formalism == DQE_KET) {
-        fn = h->variant == 1 ? (const void*)k_tile_pass<128, 3, 0>
-             : h->variant == 2 ? (const void*)k_tile_pass<128, 2, 0> : (const void*)k_tile_pass<256, 2, 0>;
+        fn = h->variant == 1 ? DQE_KFN(128, 3, 0) : h->variant == 2 ? DQE_KFN(128, 2, 0) : DQE_KFN(256, 2, 0);
       } else {
-        fn = h->variant == 1 ? (const void*)k_tile_pass<128, 3, 1>
-             : h->variant == 2 ? (const void*)k_tile_pass<128, 2, 1> : (const void*)k_tile_pass<256, 2, 1>;
+        fn = h->variant == 1 ? DQE_KFN(128, 3, 1) : h->variant == 2 ? DQE_KFN(128, 2, 1) : DQE_KFN(256, 2, 1);
       }
+#undef DQE_KFN
       if (h->variant) threads = std::min(threads, 128);
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
@@ -1285,9 +1308,10 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   if ((e = cudaMalloc(&h->creg, batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
   if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
   {
-    const void* variants[6] = {(const void*)k_tile_pass<256, 2, 0>, (const void*)k_tile_pass<128, 3, 0>,
-                               (const void*)k_tile_pass<128, 2, 0>, (const void*)k_tile_pass<256, 2, 1>,
-                               (const void*)k_tile_pass<128, 3, 1>, (const void*)k_tile_pass<128, 2, 1>};
+#define DQE_KV(M, B, F) (const void*)k_tile_pass<M, B, F, false>, (const void*)k_tile_pass<M, B, F, true>
+    const void* variants[12] = {DQE_KV(256, 2, 0), DQE_KV(128, 3, 0), DQE_KV(128, 2, 0),
+                                DQE_KV(256, 2, 1), DQE_KV(128, 3, 1), DQE_KV(128, 2, 1)};
+#undef DQE_KV
     for (const void* fn : variants) {
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
         return bail("cudaFuncSetAttribute", e);

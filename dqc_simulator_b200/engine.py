@@ -19,7 +19,8 @@ KET = 0
 DM = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdqcengine.so")
+# DQE_LIB: another build of the same library (A/B measurements of kernel changes); never a fallback
+LIB_PATH = os.environ.get("DQE_LIB") or os.path.join(_HERE, "lib", "libdqcengine.so")
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_dbl_p = ctypes.POINTER(ctypes.c_double)

@@ -202,3 +202,40 @@ def toffoli_want(a, b, t):
     """unit_tests/qlib/test_circuit_identities.py:60-427 truth table: target flips iff a = b = 1."""
     out = [S1 if a else S0, S1 if b else S0, S1 if (t ^ (a & b)) else S0]
     return ket2dm(ft.reduce(np.kron, out))
+
+
+# ---- the reference's PRINTED end-to-end fidelities (16 digits, real NetSquid runs) ------------------------
+# Each example prints the fidelity of ONE density-matrix trajectory (the measurement outcomes NetSquid's RNG
+# happened to draw).  Outcomes enter the state only through the flip noise folded into the collapse, the
+# outcome-dependent correction gates and their simulated durations -- so enumerating the forced outcomes of a
+# circuit with k mid-circuit measurements gives 2^k candidate values, and exactly one of them must be the
+# printed number if (and only if) the whole model -- gate matrices, channel order, Werner ebits, the simulated
+# timeline that sets every memory-noise exponent -- agrees with NetSquid's.  name -> (fixture, QPUs, F_werner,
+# data qubits, target ket, number of measurements, printed value, the trajectory that reproduces it, source).
+C2_NOISE = dict(p_depolar_error_cnot=1e-3, single_qubit_gate_error_prob=2e-5, meas_error_prob=3e-3,
+                comm_qubit_depolar_rate=0.055, proc_qubit_depolar_rate=0.055)
+_GHZ5 = np.zeros(32, dtype=complex)
+_GHZ5[0] = _GHZ5[31] = 2 ** -0.5
+_GHZ5_QUBITS = [(2, "node_0"), (3, "node_0"), (2, "node_1"), (3, "node_1"), (2, "node_2")]
+PRINTED_FIDELITIES = {
+    "getting_started_bell": ("ref_getting_started.json", 3, 0.9, [(2, "node_0"), (2, "node_1")], B00, 2,
+                             0.8921630426886507, (1, 0), "examples/getting_started.py:128-139"),
+    "from_monolithic_ghz5": ("c2_ghz5_3qpu_cat.json", 3, 0.9, _GHZ5_QUBITS, _GHZ5, 4,
+                             0.7928258818055854, (0, 0, 1, 1), "examples/from_monolithic_circuit.py:143-155"),
+    "run_experiment_ghz5": ("c2_ghz5_3qpu_cat.json", 3, 0.99, _GHZ5_QUBITS, _GHZ5, 4,
+                            0.9570522876374276, (1, 1, 1, 0), "examples/run_experiment.py:80-93"),
+}
+
+
+def printed_fidelity(make_backend, case, outcomes):
+    """Fidelity <phi|rho_S|phi> of the trajectory with the given forced measurement outcomes, on the noisy
+    hardware of the example (10 positions, 2 comm qubits, ebits at 182 Hz, Werner F)."""
+    name, nq, F, qubits, target, nmeas, _, _, _ = PRINTED_FIDELITIES[case]
+    assert len(outcomes) == nmeas
+    dqc = hardware.DQCSpec.uniform(nq, state4distribution=hardware.werner_state(F), num_positions=10,
+                                   num_comm_qubits=2, **C2_NOISE)
+    ex, be, _ = run_golden(make_backend, name, "dm", max_qubits=7, forced=list(outcomes) + [0] * 8,
+                           host_branching=True, dqc=dqc)
+    rho = rdm(ex, be, qubits)
+    v = np.asarray(target, dtype=complex).reshape(-1)
+    return float(np.real(v.conj() @ rho @ v))
