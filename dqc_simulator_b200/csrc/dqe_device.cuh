@@ -699,6 +699,22 @@ __device__ __forceinline__ constexpr int EI(int r, int c, int ro, int co) {
   return ROLE == 0 ? (r * 8 + ro * 4 + c * 2 + co) : (ro * 8 + r * 4 + co * 2 + c);
 }
 
+// The group sub-ops below are written "in place": an output is assigned at the instruction where the input
+// it replaces dies, and the only temporaries are partial products computed BEFORE that point.  The sub-op
+// loop of run_group is a switch inside a loop, so v[] must sit in the same registers at every merge; with
+// read-all-then-write-all bodies ptxas could not coalesce and copied the register file (64+ IMAD.MOV per
+// sub-op, 15 % of all executed instructions in the r01k profile).  Arithmetic and rounding are unchanged.
+__device__ __forceinline__ void mix2(double2& x0, double2& x1, double2 m00, double2 m01, double2 m10, double2 m11) {
+  const double2 p = cmul(m10, x0);
+  x0 = cfma(m01, x1, cmul(m00, x0));
+  x1 = cfma(m11, x1, p);
+}
+__device__ __forceinline__ void mix2c(double2& x0, double2& x1, double2 m00, double2 m01, double2 m10, double2 m11) {
+  const double2 p = cmulc(m10, x0);   // conjugated coefficients (column side of U rho U^dagger)
+  x0 = cfmac(m01, x1, cmulc(m00, x0));
+  x1 = cfmac(m11, x1, p);
+}
+
 template <int ROLE>
 __device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
   const double a = op.p[0], b = op.p[1], c = op.p[2], d = op.p[3];
@@ -706,12 +722,13 @@ __device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
   for (int ro = 0; ro < 2; ++ro)
 #pragma unroll
     for (int co = 0; co < 2; ++co) {
-      const double2 e00 = v[EI<ROLE>(0, 0, ro, co)], e01 = v[EI<ROLE>(0, 1, ro, co)];
-      const double2 e10 = v[EI<ROLE>(1, 0, ro, co)], e11 = v[EI<ROLE>(1, 1, ro, co)];
-      v[EI<ROLE>(0, 0, ro, co)] = make_double2(fma(a, e00.x, b * e11.x), fma(a, e00.y, b * e11.y));
-      v[EI<ROLE>(1, 1, ro, co)] = make_double2(fma(a, e11.x, b * e00.x), fma(a, e11.y, b * e00.y));
-      v[EI<ROLE>(0, 1, ro, co)] = make_double2(fma(c, e01.x, d * e10.x), fma(c, e01.y, d * e10.y));
-      v[EI<ROLE>(1, 0, ro, co)] = make_double2(fma(c, e10.x, d * e01.x), fma(c, e10.y, d * e01.y));
+      double2& e00 = v[EI<ROLE>(0, 0, ro, co)]; double2& e01 = v[EI<ROLE>(0, 1, ro, co)];
+      double2& e10 = v[EI<ROLE>(1, 0, ro, co)]; double2& e11 = v[EI<ROLE>(1, 1, ro, co)];
+      const double t0x = b * e00.x, t0y = b * e00.y, t1x = d * e01.x, t1y = d * e01.y;
+      e00.x = fma(a, e00.x, b * e11.x); e00.y = fma(a, e00.y, b * e11.y);
+      e11.x = fma(a, e11.x, t0x); e11.y = fma(a, e11.y, t0y);
+      e01.x = fma(c, e01.x, d * e10.x); e01.y = fma(c, e01.y, d * e10.y);
+      e10.x = fma(c, e10.x, t1x); e10.y = fma(c, e10.y, t1y);
     }
 }
 
@@ -746,50 +763,37 @@ __device__ __forceinline__ void g_xpat(double2 (&v)[16], const double2* __restri
   for (int ro = 0; ro < 2; ++ro)
 #pragma unroll
     for (int co = 0; co < 2; ++co) {
-      const double2 e00 = v[EI<ROLE>(0, 0, ro, co)], e01 = v[EI<ROLE>(0, 1, ro, co)];
-      const double2 e10 = v[EI<ROLE>(1, 0, ro, co)], e11 = v[EI<ROLE>(1, 1, ro, co)];
-      v[EI<ROLE>(0, 0, ro, co)] = cfma(b, e11, cmul(a, e00));
-      v[EI<ROLE>(1, 1, ro, co)] = cfma(d, e11, cmul(c, e00));
-      v[EI<ROLE>(0, 1, ro, co)] = cfma(g, e10, cmul(f, e01));
-      v[EI<ROLE>(1, 0, ro, co)] = cfma(k, e10, cmul(h, e01));
+      mix2(v[EI<ROLE>(0, 0, ro, co)], v[EI<ROLE>(1, 1, ro, co)], a, b, c, d);
+      mix2(v[EI<ROLE>(0, 1, ro, co)], v[EI<ROLE>(1, 0, ro, co)], f, g, h, k);
     }
+}
+
+// Controlled-X / X inside a group is a permutation of the thread's 16 elements -- done in the ADDRESSES of
+// the group's shared-memory loads / stores, never in registers: element e = (ra, rb, ca, cb) trades places
+// with the element whose target row (column) bit is flipped when the row (column) control is on.
+// r[(ra << 1) | rb] / c[(ca << 1) | cb] are the XOR masks on the element's tile index (all warp-uniform).
+struct GPerm { uint32_t r[4], c[4]; };
+// flags: bit0 = role of the target axis, bit1 / bit2 = row / column control is the other axis of the group
+__device__ __forceinline__ GPerm make_perm(bool on, int flags, uint64_t octrl, uint64_t octrl2, uint64_t base,
+                                           uint32_t mra, uint32_t mrb, uint32_t mca, uint32_t mcb) {
+  const int role = flags & 1;
+  const bool in_r = flags & 2, in_c = flags & 4;
+  const bool r_on = on && (base & octrl) == octrl, c_on = on && (base & octrl2) == octrl2;
+  const uint32_t tr = role ? mrb : mra, tc = role ? mcb : mca;
+  const uint32_t r1 = r_on ? tr : 0u, r0 = (r_on && !in_r) ? tr : 0u;
+  const uint32_t c1 = c_on ? tc : 0u, c0 = (c_on && !in_c) ? tc : 0u;
+  GPerm p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ctl = role ? (i >> 1) : (i & 1);   // value of the control-axis bit of the element
+    p.r[i] = ctl ? r1 : r0;
+    p.c[i] = ctl ? c1 : c0;
+  }
+  return p;
 }
 
 // target axis = ROLE; the control (if any) is either the other axis of the group (in_r / in_c)
 // or outside the tile (r_on / c_on already evaluated on the tile base)
-template <int ROLE>
-__device__ __forceinline__ void g_cx(double2 (&v)[16], bool r_on, bool c_on, bool in_r, bool in_c) {
-  // controlled-X: pure permutation of the register file, no arithmetic
-  if (r_on) {
-#pragma unroll
-    for (int ro = 0; ro < 2; ++ro) {
-      if (in_r && ro == 0) continue;
-#pragma unroll
-      for (int co = 0; co < 2; ++co)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const double2 a = v[EI<ROLE>(0, c, ro, co)];
-          v[EI<ROLE>(0, c, ro, co)] = v[EI<ROLE>(1, c, ro, co)];
-          v[EI<ROLE>(1, c, ro, co)] = a;
-        }
-    }
-  }
-  if (c_on) {
-#pragma unroll
-    for (int co = 0; co < 2; ++co) {
-      if (in_c && co == 0) continue;
-#pragma unroll
-      for (int ro = 0; ro < 2; ++ro)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const double2 a = v[EI<ROLE>(r, 0, ro, co)];
-          v[EI<ROLE>(r, 0, ro, co)] = v[EI<ROLE>(r, 1, ro, co)];
-          v[EI<ROLE>(r, 1, ro, co)] = a;
-        }
-    }
-  }
-}
-
 template <int ROLE>
 __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __restrict__ cs, bool r_on, bool c_on,
                                          bool in_r, bool in_c) {
@@ -802,9 +806,7 @@ __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __rest
       for (int co = 0; co < 2; ++co)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const double2 a = v[EI<ROLE>(0, c, ro, co)], b = v[EI<ROLE>(1, c, ro, co)];
-          v[EI<ROLE>(0, c, ro, co)] = cfma(m01, b, cmul(m00, a));
-          v[EI<ROLE>(1, c, ro, co)] = cfma(m11, b, cmul(m10, a));
+          mix2(v[EI<ROLE>(0, c, ro, co)], v[EI<ROLE>(1, c, ro, co)], m00, m01, m10, m11);
         }
     }
   }
@@ -816,9 +818,7 @@ __device__ __forceinline__ void g_mat1x2(double2 (&v)[16], const double2* __rest
       for (int ro = 0; ro < 2; ++ro)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const double2 a = v[EI<ROLE>(r, 0, ro, co)], b = v[EI<ROLE>(r, 1, ro, co)];
-          v[EI<ROLE>(r, 0, ro, co)] = cfmac(m01, b, cmulc(m00, a));
-          v[EI<ROLE>(r, 1, ro, co)] = cfmac(m11, b, cmulc(m10, a));
+          mix2c(v[EI<ROLE>(r, 0, ro, co)], v[EI<ROLE>(r, 1, ro, co)], m00, m01, m10, m11);
         }
     }
   }
@@ -889,12 +889,17 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
   const int s4[4] = {g.b[4], g.b[5], g.b[6], g.b[7]};   // the four bit positions, ascending (host-sorted)
   const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
   const int nsub = g.aux;
+  // X / CX hoisted by the planner to the head (flags bits 0-3: on, role, in_r, in_c; controls octrl / octrl2)
+  // or the tail (bits 4-7; controls in p[0], p[1]) of the group: applied by the load / store addresses
+  const uint64_t* tail_ctrl = reinterpret_cast<const uint64_t*>(&g.p[0]);
+  const GPerm pre = make_perm(g.flags & 1, (g.flags >> 1) & 7, g.octrl, g.octrl2, base, mra, mrb, mca, mcb);
+  const GPerm post = make_perm(g.flags & 16, (g.flags >> 5) & 7, tail_ctrl[0], tail_ctrl[1], base, mra, mrb, mca, mcb);
+#define DQE_GADDR(e) (i0 | (((e) & 8) ? mra : 0u) | (((e) & 4) ? mrb : 0u) | (((e) & 2) ? mca : 0u) | (((e) & 1) ? mcb : 0u))
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
     double2 v[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      v[e] = tile[i0 | ((e & 8) ? mra : 0u) | ((e & 4) ? mrb : 0u) | ((e & 2) ? mca : 0u) | ((e & 1) ? mcb : 0u)];
+    for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e) ^ pre.r[(e >> 2) & 3] ^ pre.c[e & 3]];
     for (int s = 0; s < nsub; ++s) {
       const MicroOp& op = sub[s];
       if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
@@ -904,23 +909,36 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         case G_PAULI1:
           if (role) g_pauli1<1>(v, op); else g_pauli1<0>(v, op);
           break;
+#ifdef DQE_GROUP_HEAVY
         case G_MAT2:
           if (role) g_mat2<1>(v, cs); else g_mat2<0>(v, cs);
           break;
+#endif
         case G_XPAT:
           if (role) g_xpat<1>(v, cs); else g_xpat<0>(v, cs);
           break;
         case G_MAT1X2: {
+          if (op.flags & 16) {
+            // X / CX in the middle of a group: a round trip through the thread's own 16 tile slots with
+            // permuted store addresses (no barrier: nobody else touches them during the sweep)
+            const GPerm mid = make_perm(true, op.flags & 7, op.octrl, op.octrl2, base, mra, mrb, mca, mcb);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ mid.r[(e >> 2) & 3] ^ mid.c[e & 3]] = v[e];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e)];
+            break;
+          }
           const bool in_r = op.flags & 2, in_c = op.flags & 4;
           const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
-          if (op.flags & 16) { if (role) g_cx<1>(v, r_on, c_on, in_r, in_c); else g_cx<0>(v, r_on, c_on, in_r, in_c); }
-          else if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c);
+          if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c);
           else g_mat1x2<0>(v, cs, r_on, c_on, in_r, in_c);
           break;
         }
         case G_DEPOL2: g_depol2(v, op.p[0]); break;
+#ifdef DQE_GROUP_HEAVY
         case G_MAT2ROWS: g_mat2side<true>(v, cs); break;
         case G_MAT2COLS: g_mat2side<false>(v, cs); break;
+#endif
         case G_COLLAPSE: {
           const MeasRec r = *mrec;
           if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
@@ -936,6 +954,7 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           for (int e = 0; e < 16; ++e) v[e] = cmul(x, cs[e]);
           break;
         }
+#ifdef DQE_GROUP_HEAVY
         case G_DIAG: {
           const uint8_t* lut = reinterpret_cast<const uint8_t*>(&op.p[0]);
           uint32_t fixed = 0;
@@ -945,13 +964,14 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], cs[lut[e] | fixed]);
           break;
         }
+#endif
         default: break;
       }
     }
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      tile[i0 | ((e & 8) ? mra : 0u) | ((e & 4) ? mrb : 0u) | ((e & 2) ? mca : 0u) | ((e & 1) ? mcb : 0u)] = v[e];
+    for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ post.r[(e >> 2) & 3] ^ post.c[e & 3]] = v[e];
   }
+#undef DQE_GADDR
 }
 
 // ------------------------------------------------------------------------------------------
@@ -979,6 +999,11 @@ __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double
                    : "memory");
   }
 }
+
+// %tid.x / %ctaid.x through volatile asm: the store phase of the one-tile kernel RE-derives its addressing
+// state instead of keeping a dozen registers alive across the micro-program (the group sweeps need them)
+__device__ __forceinline__ uint32_t fresh_tid() { uint32_t t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }
+__device__ __forceinline__ uint32_t fresh_ctaid() { uint32_t t; asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(t)); return t; }
 
 // Persistent, double-buffered pass kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ... ; while
 // the micro-program runs on the tile in buffer b, the TMA load of the CTA's next tile streams into
@@ -1150,7 +1175,29 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (nbuf == 1) {   // every warp issues its share (uniform loop, leader lane issues + commits)
+        if constexpr (!PERSIST) {   // one tile per CTA: addressing state re-derived here (see fresh_tid)
+          const uint32_t tid2 = fresh_tid();
+          const uint32_t wid2 = __shfl_sync(0xffffffffu, tid2 >> 5, 0), nwarps2 = blockDim.x >> 5;
+          const bool issuer2 = (tid2 & 31u) == 0u;
+          const uint64_t blk2 = fresh_ctaid();
+          const int c02 = pp.tile_segs[0].len;
+          const uint32_t run_bytes2 = 16u << c02, nruns2 = (1u << pp.t) >> c02;
+          const uint64_t base2 = deposit(blk2 & ((1ull << pp.outer_bits) - 1ull), pp.outer_segs, pp.n_outer_segs);
+          double2* __restrict__ sp2 = pp.state + ((blk2 >> pp.outer_bits) << pp.P) + base2;
+          const uint32_t tile_s2 = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
+          for (uint32_t r = wid2; r < nruns2; r += nwarps2) {
+            double2* dst = sp2 + ((uint64_t)pp.run_hi[r] << c02);
+            const uint32_t srcs = tile_s2 + r * run_bytes2;
+            if (issuer2)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(srcs),
+                           "r"(run_bytes2)
+                           : "memory");
+          }
+          if (issuer2) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem stays valid until read
+          }
+        } else if (nbuf == 1) {   // every warp issues its share (uniform loop, leader lane issues + commits)
           for (uint32_t r = wid; r < nruns; r += nwarps) {
             double2* dst = sp + ((uint64_t)pp.run_hi[r] << c0);
             const uint32_t srcs = tile_s + r * run_bytes;
@@ -1190,7 +1237,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     if constexpr (!PERSIST) break;
   }
   // shared memory must stay valid until the last bulk store has read it
-  if (tma && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (PERSIST && tma && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   // (fused measurements push their partials and end on a cluster barrier: nothing remote is pending here)
 }
 

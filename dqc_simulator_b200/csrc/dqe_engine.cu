@@ -77,7 +77,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -743,6 +743,10 @@ struct Planner {
         return add(m.b[1]);
       case OP_MAT2:
         if (ho->pctrl) return false;
+#ifndef DQE_GROUP_HEAVY
+        return false;   // dense 4x4 blocks stay stand-alone sweeps: inside the register-resident group
+                        // interpreter they cost every other sub-op its registers (see run_group)
+#endif
         if (m.b[0] == m.b[1] + n) return add(m.b[1]);
         if (m.b[0] >= n && m.b[1] >= n) return add(m.b[0] - n) && add(m.b[1] - n);
         if (m.b[0] < n && m.b[1] < n) return add(m.b[0]) && add(m.b[1]);
@@ -762,6 +766,9 @@ struct Planner {
         return add(c);                           // needs both bits of the control axis in the tile
       }
       case OP_DIAG:
+#ifndef DQE_GROUP_HEAVY
+        return false;
+#endif
         for (uint32_t i = 0; i < m.nb; ++i) {
           const int ph = m.b[i];
           if (!((tile >> ph) & 1ull)) continue;
@@ -771,6 +778,20 @@ struct Planner {
       default:
         return false;
     }
+  }
+
+  bool is_x(const HostOp* ho) const {
+    if (ho->m.type != OP_MAT1X2) return false;
+    const double2* u = &h->cpool[ho->m.c_off];
+    return u[0].x == 0 && u[0].y == 0 && u[3].x == 0 && u[3].y == 0 && u[1].x == 1 && u[1].y == 0 && u[2].x == 1 &&
+           u[2].y == 0;
+  }
+  // X / CX whose controls (if any) are the other axis of the group or uniform per tile, unpredicated:
+  // can be applied by the group's load / store addresses
+  bool hoistable_x(const HostOp* ho) const { return is_x(ho) && ho->m.pred_bit < 0; }
+  bool x_ctrl_in_group(const HostOp* ho, uint64_t tile) const {
+    if (!ho->pctrl || !ho->pctrl2) return false;
+    return ((tile >> __builtin_ctzll(ho->pctrl)) & 1ull) && ((tile >> __builtin_ctzll(ho->pctrl2)) & 1ull);
   }
 
   MicroOp make_sub(const HostOp* ho, int A, int B, uint64_t tile, size_t pcb) {
@@ -800,12 +821,7 @@ struct Planner {
         break;
       case OP_MAT1X2: {
         m.type = G_MAT1X2; m.flags = role(s.b[1]);
-        {
-          const double2* u = &h->cpool[ho->m.c_off];
-          if (u[0].x == 0 && u[0].y == 0 && u[3].x == 0 && u[3].y == 0 && u[1].x == 1 && u[1].y == 0 && u[2].x == 1 &&
-              u[2].y == 0)
-            m.flags |= 16;   // Pauli-X: swap instead of multiply
-        }
+        if (is_x(ho)) m.flags |= 16;   // Pauli-X: a permutation, done in the addresses (GPerm)
         if (ho->pctrl) {
           const int b = __builtin_ctzll(ho->pctrl);
           if ((tile >> b) & 1ull) m.flags |= 2; else m.octrl = ho->pctrl;
@@ -961,7 +977,8 @@ struct Planner {
     bool writes = false;
     const int n = h->nmax;
     for (Item& it : items) {
-      bool as_group = it.group && it.ops.size() >= 2;
+      bool as_group = it.group && (it.ops.size() >= 2 ||
+                                   (h->cxperm && it.nax == 2 && hoistable_x(it.ops[0]) && x_ctrl_in_group(it.ops[0], tile)));
       int A = it.ax[0], B = it.nax > 1 ? it.ax[1] : -1;
       if (as_group && B < 0) {  // single-axis group: borrow any other axis fully inside the tile
         for (int a = 0; a < n && B < 0; ++a)
@@ -972,13 +989,39 @@ struct Planner {
         // for two-qubit matrices the first listed axis of the op is the MSB; keep A = that axis if any
         MicroOp g;
         memset(&g, 0, sizeof(g));
-        g.type = OP_GROUP; g.pred_bit = -1; g.nb = 4; g.aux = (int)it.ops.size();
+        g.type = OP_GROUP; g.pred_bit = -1; g.nb = 4;
         g.b[0] = (uint8_t)local_of(tile, A + n); g.b[1] = (uint8_t)local_of(tile, B + n);
         g.b[2] = (uint8_t)local_of(tile, A); g.b[3] = (uint8_t)local_of(tile, B);
         for (int i = 0; i < 4; ++i) g.b[4 + i] = g.b[i];
         std::sort(g.b + 4, g.b + 8);
+        // X / CX is a permutation of the pair's 16 elements: when it opens or closes the group it rides in
+        // the load / store addresses of the sweep (GPerm).  The two-qubit depolarising channel on the same
+        // pair commutes with it (unitary covariance), so "CX, DEPOL2" is reordered to put the CX last.
+        std::vector<const HostOp*> ops = it.ops;
+        if (h->cxperm) {
+          for (size_t k = 0; k + 1 < ops.size(); ++k)
+            if (hoistable_x(ops[k]) && x_ctrl_in_group(ops[k], tile) && ops[k + 1]->m.type == OP_DEPOL2 &&
+                ops[k + 1]->m.pred_bit < 0)
+              std::swap(ops[k], ops[k + 1]);
+        }
+        const HostOp* head = nullptr;
+        const HostOp* tail = nullptr;
+        if (h->cxperm && !ops.empty() && hoistable_x(ops.front())) { head = ops.front(); ops.erase(ops.begin()); }
+        if (h->cxperm && !ops.empty() && hoistable_x(ops.back())) { tail = ops.back(); ops.pop_back(); }
+        if (head) {
+          const MicroOp x = make_sub(head, A, B, tile, P.const_begin);   // flags: role, in_r (2), in_c (4), 16
+          g.flags |= 1 | ((x.flags & 7) << 1);
+          g.octrl = x.octrl; g.octrl2 = x.octrl2;
+        }
+        if (tail) {
+          const MicroOp x = make_sub(tail, A, B, tile, P.const_begin);
+          g.flags |= 16 | ((x.flags & 7) << 5);
+          uint64_t* tc = reinterpret_cast<uint64_t*>(&g.p[0]);
+          tc[0] = x.octrl; tc[1] = x.octrl2;
+        }
+        g.aux = (int)ops.size();
         dev_ops.push_back(g);
-        for (const HostOp* ho : it.ops) dev_ops.push_back(make_sub(ho, A, B, tile, P.const_begin));
+        for (const HostOp* ho : ops) dev_ops.push_back(make_sub(ho, A, B, tile, P.const_begin));
         writes = true;
       } else {
         for (const HostOp* ho : it.ops) {
@@ -1106,6 +1149,8 @@ int do_flush(dqe_t* h) {
       for (int i = 0; i < P.pp.nops; ++i) {
         const MicroOp& m = pl.dev_ops[P.op_begin + i];
         if (m.type > 100) { fprintf(stderr, " %s%s.%d", gnames[m.type - 100], m.pred_bit >= 0 ? "?" : "", m.flags & 1); continue; }
+        if (m.type == OP_GROUP && (m.flags & 17))
+          fprintf(stderr, " [%s%s]", (m.flags & 1) ? "x>" : "", (m.flags & 16) ? ">x" : "");
         fprintf(stderr, " %s%s(", names[m.type], m.pred_bit >= 0 ? "?" : "");
         for (uint32_t b = 0; b < m.nb; ++b) fprintf(stderr, "%s%d", b ? "," : "", (int)m.b[b]);
         fprintf(stderr, ")");
@@ -1269,7 +1314,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1831,6 +1876,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "cxperm")) {
+    h->cxperm = value ? 1 : 0;
   } else if (!strcmp(key, "cluster")) {
     h->cluster = value ? 1 : 0;
   } else if (!strcmp(key, "variant")) {
