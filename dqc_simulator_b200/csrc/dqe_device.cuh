@@ -107,6 +107,7 @@ struct PassParams {
   int8_t dg_req[16];       // physical row bit (outside the tile) whose base value variable k must equal, -1 = none
   int8_t dg_fix_src[16], dg_fix_dst[16];   // column bit outside, row bit inside: tile bit dst = base bit src
   int32_t dg_nfix;
+  uint32_t dg_req_mask;    // free variables with a dg_req entry
   uint32_t dg_eq_mask;     // axes with both bits outside: base bit a must equal base bit a + nmax
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
   Seg tile_segs[16];
@@ -149,7 +150,11 @@ __device__ __forceinline__ uint32_t ins0(uint32_t p, int j) {
 template <typename SegT>
 __device__ __forceinline__ uint64_t deposit(uint64_t x, const SegT* segs, int n) {
   uint64_t r = 0;
-  for (int s = 0; s < n; ++s) {
+  // the first segments with constant indices: the descriptors are then immediate param-space operands
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+    if (s < n) r |= ((x >> segs[s].src) & ((1ull << segs[s].len) - 1ull)) << segs[s].dst;
+  for (int s = 3; s < n; ++s) {
     r |= ((x >> segs[s].src) & ((1ull << segs[s].len) - 1ull)) << segs[s].dst;
   }
   return r;
@@ -420,21 +425,26 @@ __device__ __forceinline__ void op_depol2(double2* tile, uint32_t T, const Micro
 // PassParams; the tile-uniform part costs a few uniform instructions, the per-element part one OR per
 // free variable.
 __device__ __forceinline__ void dm_diag_partials(const double2* tile, const PassParams& pp, uint64_t base, int abit,
-                                                 double& a0, double& a1) {
+                                                 int op_ord, double& a0, double& a1) {
   const int n = pp.nmax, nfree = pp.nfree_cols;
   if ((((base >> n) ^ base) & (uint64_t)pp.dg_eq_mask) != 0ull) return;   // no diagonal element in this tile
-  uint32_t ifix = 0, req_mask = 0, req_val = 0;
+  uint32_t ifix = 0, req_val = 0;
   for (int f = 0; f < pp.dg_nfix; ++f) ifix |= (uint32_t)((base >> pp.dg_fix_src[f]) & 1ull) << pp.dg_fix_dst[f];
-  for (int k = 0; k < nfree; ++k) {
-    const int rb = pp.dg_req[k];
-    if (rb >= 0) { req_mask |= 1u << k; req_val |= (uint32_t)((base >> rb) & 1ull) << k; }
-  }
-  const int kidx = pp.ax_ord[abit];
+  const uint32_t req_mask = pp.dg_req_mask;
+  // constant loop bounds + constant indices: dg_req / dg_mask become immediate param-space operands
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if ((req_mask >> k) & 1u) req_val |= (uint32_t)((base >> pp.dg_req[k]) & 1ull) << k;
+  for (int k = 8; k < nfree; ++k)
+    if ((req_mask >> k) & 1u) req_val |= (uint32_t)((base >> pp.dg_req[k]) & 1ull) << k;
+  const int kidx = op_ord;
   const uint32_t vfix = (uint32_t)((base >> abit) & 1ull);
   for (uint32_t d = threadIdx.x; d < (1u << nfree); d += blockDim.x) {
     if ((d ^ req_val) & req_mask) continue;
     uint32_t i = ifix;
-    for (int k = 0; k < nfree; ++k) i |= ((d >> k) & 1u) ? pp.dg_mask[k] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) i |= (0u - ((d >> k) & 1u)) & pp.dg_mask[k];   // unused masks are 0
+    for (int k = 8; k < nfree; ++k) i |= ((d >> k) & 1u) ? pp.dg_mask[k] : 0u;
     const double w = tile[i].x;
     const uint32_t va = kidx >= 0 ? ((d >> kidx) & 1u) : vfix;
     if (va) a1 += w; else a0 += w;
@@ -462,7 +472,7 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
     }
   } else {
     // only the diagonal of rho matters: enumerate it directly
-    dm_diag_partials(tile, pp, base, abit, a0, a1);
+    dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -514,7 +524,7 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
       }
     }
   } else {
-    dm_diag_partials(tile, pp, base, abit, a0, a1);
+    dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1032,6 +1042,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
   const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   uint64_t blk = blockIdx.x;
+  // per-shot classical state of the first tile: requested before anything else, so that its DRAM latency
+  // hides behind the barrier set-up and the tile fetch
+  uint64_t cw_first = 0;
+  MeasRec mr_first;
+  mr_first.scale = 0.0; mr_first.outcome = 0; mr_first.pad = 0;
+  if (blk < pp.ntiles) {
+    const uint64_t shot0 = blk >> pp.outer_bits;
+    cw_first = pp.creg[shot0];
+    if (threadIdx.x == 0) mr_first = pp.rec[shot0];   // outcome recorded by a preceding pass / k_finish_measure
+  }
   if (pp.has_measure) cluster_arrive_relaxed();   // waited for in the first op_measure
   if (tma && threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s));
@@ -1070,10 +1090,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     const uint64_t shot = blk >> pp.outer_bits;
     const uint64_t base = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
     double2* __restrict__ sp = pp.state + (shot << pp.P) + base;
-    // per-shot classical state: requested before the tile wait so that its latency hides behind the fetch
-    uint64_t cw = pp.creg[shot];
-    MeasRec mr0;
-    if (threadIdx.x == 0) mr0 = pp.rec[shot];   // outcome recorded by a preceding pass / k_finish_measure
+    uint64_t cw = cw_first;
+    MeasRec mr0 = mr_first;
+    if (PERSIST && it > 0) {
+      cw = pp.creg[shot];
+      if (threadIdx.x == 0) mr0 = pp.rec[shot];
+    }
 
     if (tma) {
       const uint64_t nxt = blk + gridDim.x;

@@ -26,7 +26,18 @@ typedef std::complex<double> cplx;
 
 namespace {
 
+// Factor of an axis-local density-matrix op: the peephole composes memory noise -> gate -> gate noise
+// into one 4x4 superoperator (one stand-alone sweep); the same op inside a register-resident group sweep
+// runs as its light, in-place factors instead (a dense 4x4 there would cost every sub-op its registers).
+struct Factor {
+  int kind;            // 1 = Pauli channel (a, b, c, d of OP_PAULI1), 2 = unitary U: rho -> U rho U^dagger
+  double d[8];         // kind 1: d[0..3]; kind 2: U row-major, interleaved re / im
+};
+constexpr int kMaxFactors = 4;
+
 struct HostOp {
+  int nf;              // valid factorisation of this (axis-local dm) op: f[0] applied first; 0 = none
+  Factor f[kMaxFactors];
   int kind;            // 0 = micro-op, 1 = measurement finish (pass barrier)
   MicroOp m;           // bit fields hold PHYSICAL positions until the planner localises them
   uint64_t pctrl, pctrl2;  // physical control masks
@@ -77,7 +88,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm, factor;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -136,6 +147,52 @@ HostOp blank(dqe_t* h, int type) {
   o.live_after = phys_live(h, h->live_axes);
   return o;
 }
+Factor pauli_factor(double a, double b, double c, double d) {
+  Factor f;
+  memset(&f, 0, sizeof(f));
+  f.kind = 1; f.d[0] = a; f.d[1] = b; f.d[2] = c; f.d[3] = d;
+  return f;
+}
+Factor unitary_factor(const cplx* u) {
+  Factor f;
+  memset(&f, 0, sizeof(f));
+  f.kind = 2;
+  for (int i = 0; i < 4; ++i) { f.d[2 * i] = u[i].real(); f.d[2 * i + 1] = u[i].imag(); }
+  return f;
+}
+// factors of `first` followed by factors of `then`, neighbours of one kind coalesced; false = no
+// (short enough) factorisation
+bool compose_factors(const HostOp& first, const HostOp& then, int* nf, Factor* out) {
+  *nf = 0;
+  if (first.nf <= 0 || then.nf <= 0) return false;
+  Factor tmp[2 * kMaxFactors];
+  int n = 0;
+  auto add = [&](const Factor& f) {
+    if (n > 0 && tmp[n - 1].kind == f.kind) {
+      Factor& p = tmp[n - 1];
+      if (f.kind == 1) {   // [[a, b], [b, a]] on (e00, e11), [[c, d], [d, c]] on (e01, e10)
+        const double a = f.d[0] * p.d[0] + f.d[1] * p.d[1], b = f.d[0] * p.d[1] + f.d[1] * p.d[0];
+        const double c = f.d[2] * p.d[2] + f.d[3] * p.d[3], d = f.d[2] * p.d[3] + f.d[3] * p.d[2];
+        p.d[0] = a; p.d[1] = b; p.d[2] = c; p.d[3] = d;
+      } else {             // U = U_f . U_p
+        cplx A[4], B[4], R[4];
+        for (int i = 0; i < 4; ++i) { A[i] = cplx(f.d[2 * i], f.d[2 * i + 1]); B[i] = cplx(p.d[2 * i], p.d[2 * i + 1]); }
+        R[0] = A[0] * B[0] + A[1] * B[2]; R[1] = A[0] * B[1] + A[1] * B[3];
+        R[2] = A[2] * B[0] + A[3] * B[2]; R[3] = A[2] * B[1] + A[3] * B[3];
+        p = unitary_factor(R);
+      }
+      return;
+    }
+    tmp[n++] = f;
+  };
+  for (int i = 0; i < first.nf; ++i) add(first.f[i]);
+  for (int i = 0; i < then.nf; ++i) add(then.f[i]);
+  if (n > kMaxFactors) return false;
+  for (int i = 0; i < n; ++i) out[i] = tmp[i];
+  *nf = n;
+  return true;
+}
+
 bool try_merge(dqe_t* h, const HostOp& o, int axis);
 bool try_merge_pair(dqe_t* h, const HostOp& o);
 void diag_merge_at(dqe_t* h, size_t k);
@@ -173,16 +230,18 @@ void q_mat1x2(dqe_t* h, int rbit, int cbit, const cplx* m, uint64_t pctrl_r, uin
   o.m.c_off = add_consts(h, m, 4); o.nconst = 4;
   push(h, o);
 }
-void q_mat2(dqe_t* h, int bh, int bl, const cplx* m, uint64_t pctrl) {
+void q_mat2(dqe_t* h, int bh, int bl, const cplx* m, uint64_t pctrl, const Factor* f = nullptr) {
   HostOp o = blank(h, OP_MAT2);
+  if (f) { o.nf = 1; o.f[0] = *f; }
   o.m.b[0] = (uint8_t)bh; o.m.b[1] = (uint8_t)bl; o.m.nb = 2;
   o.pctrl = pctrl;
   o.need = (1ull << bh) | (1ull << bl);
   o.m.c_off = add_consts(h, m, 16); o.nconst = 16;
   push(h, o);
 }
-void q_diag(dqe_t* h, int nb, const int* bits, const cplx* table) {
+void q_diag(dqe_t* h, int nb, const int* bits, const cplx* table, const Factor* f = nullptr) {
   HostOp o = blank(h, OP_DIAG);
+  if (f) { o.nf = 1; o.f[0] = *f; }
   o.m.nb = nb;
   for (int i = 0; i < nb; ++i) o.m.b[i] = (uint8_t)bits[i];
   o.need = 0;
@@ -194,6 +253,7 @@ void q_pauli1(dqe_t* h, int axis, double pI, double pX, double pY, double pZ) {
   o.m.b[0] = (uint8_t)rowbit(h, axis); o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
   o.need = (1ull << rowbit(h, axis)) | (1ull << axis);
   o.m.p[0] = pI + pZ; o.m.p[1] = pX + pY; o.m.p[2] = pI - pZ; o.m.p[3] = pX - pY;
+  o.nf = 1; o.f[0] = pauli_factor(o.m.p[0], o.m.p[1], o.m.p[2], o.m.p[3]);
   push(h, o);
 }
 
@@ -318,7 +378,12 @@ bool try_merge(dqe_t* h, const HostOp& o, int axis) {
           for (int l = 0; l < d; ++l) acc += Mn[i * d + l] * Mo[l * d + j];
           R[i * d + j] = acc;
         }
+      int nf = 0;
+      Factor fs[kMaxFactors];
+      const bool fact = h->formalism == DQE_DM && compose_factors(e, o, &nf, fs);
       set_axis_local(h, e, axis, R);
+      e.nf = fact ? nf : 0;
+      for (int i = 0; i < e.nf; ++i) e.f[i] = fs[i];
       h->stats[7]++;
       return true;
     }
@@ -528,7 +593,13 @@ int lower_diag(dqe_t* h, int k, const int* axes, const cplx* d) {
   const int n = 1 << k;
   for (int r = 0; r < n; ++r)
     for (int c = 0; c < n; ++c) table[r * n + c] = d[r] * std::conj(d[c]);
-  q_diag(h, 2 * k, bits, table);
+  if (k == 1) {   // D rho D^dagger on one axis: a (diagonal) unitary factor for the group sweeps
+    const cplx u[4] = {d[0], 0.0, 0.0, d[1]};
+    const Factor f = unitary_factor(u);
+    q_diag(h, 2, bits, table, &f);
+  } else {
+    q_diag(h, 2 * k, bits, table);
+  }
   return 0;
 }
 
@@ -546,7 +617,8 @@ int lower_1q(dqe_t* h, int axis, const cplx* m) {
         for (int r2 = 0; r2 < 2; ++r2)
           for (int c2 = 0; c2 < 2; ++c2)
             S[(r * 2 + c) * 4 + (r2 * 2 + c2)] = m[r * 2 + r2] * std::conj(m[c * 2 + c2]);
-    q_mat2(h, rowbit(h, axis), axis, S, 0);
+    const Factor f = unitary_factor(m);
+    q_mat2(h, rowbit(h, axis), axis, S, 0, &f);
   }
   return 0;
 }
@@ -711,6 +783,9 @@ struct Planner {
     } else {
       const int ph = m.aux;   // measured axis: column / ket bit
       m.b[0] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
+      // dm: index of the axis among the free variables of the diagonal enumeration (column bits in the
+      // tile, ascending), 0xff = fixed by the tile base
+      m.b[1] = ((tile >> ph) & 1ull) ? (uint8_t)__builtin_popcountll(tile & ((1ull << ph) - 1ull)) : (uint8_t)0xff;
     }
     if (m.type == OP_MEASURE) return m;   // lctrl / octrl / flags carry forced outcome, draw index, creg bit
     m.lctrl = 0; m.octrl = 0; m.lctrl2 = 0; m.octrl2 = 0;
@@ -744,8 +819,11 @@ struct Planner {
       case OP_MAT2:
         if (ho->pctrl) return false;
 #ifndef DQE_GROUP_HEAVY
-        return false;   // dense 4x4 blocks stay stand-alone sweeps: inside the register-resident group
-                        // interpreter they cost every other sub-op its registers (see run_group)
+        // a dense 4x4 block inside the register-resident group interpreter costs every other sub-op its
+        // registers (see run_group): an axis-local superoperator joins a group as its light factors
+        // (Pauli channels, U rho U^dagger); anything else stays a stand-alone sweep
+        if (m.b[0] == m.b[1] + n && ho->nf > 0 && h->factor) return add(m.b[1]);
+        return false;
 #endif
         if (m.b[0] == m.b[1] + n) return add(m.b[1]);
         if (m.b[0] >= n && m.b[1] >= n) return add(m.b[0] - n) && add(m.b[1] - n);
@@ -767,6 +845,8 @@ struct Planner {
       }
       case OP_DIAG:
 #ifndef DQE_GROUP_HEAVY
+        // D rho D^dagger on one axis rides as an X-pattern sub-op; wider tables stay stand-alone
+        if (m.nb == 2 && m.b[0] == m.b[1] + n && h->factor) return add(m.b[1]);
         return false;
 #endif
         for (uint32_t i = 0; i < m.nb; ++i) {
@@ -860,6 +940,49 @@ struct Planner {
     return m;
   }
 
+  // sub-ops of one host op inside the group on axes (A, B)
+  void emit_sub(const HostOp* ho, int A, int B, uint64_t tile, size_t pcb) {
+    const MicroOp& s = ho->m;
+    const int n = h->nmax;
+    if (s.type == OP_MAT2 && s.b[0] == s.b[1] + n && ho->nf > 0) {
+      for (int i = 0; i < ho->nf; ++i) {
+        const Factor& f = ho->f[i];
+        MicroOp m;
+        memset(&m, 0, sizeof(m));
+        m.pred_bit = s.pred_bit;
+        m.flags = s.b[1] == A ? 0 : 1;
+        if (f.kind == 1) {
+          m.type = G_PAULI1;
+          for (int k = 0; k < 4; ++k) m.p[k] = f.d[k];
+        } else {
+          m.type = G_MAT1X2;
+          if (f.d[0] == 0 && f.d[1] == 0 && f.d[6] == 0 && f.d[7] == 0 && f.d[2] == 1 && f.d[3] == 0 && f.d[4] == 1 &&
+              f.d[5] == 0)
+            m.flags |= 16;
+          m.c_off = (int)(dev_consts.size() - pcb);
+          for (int k = 0; k < 4; ++k) dev_consts.push_back(make_double2(f.d[2 * k], f.d[2 * k + 1]));
+        }
+        dev_ops.push_back(m);
+      }
+      return;
+    }
+    if (s.type == OP_DIAG && s.nb == 2 && s.b[0] == s.b[1] + n) {
+      // table t[r][c] (index r * 2 + c) as the X pattern e00' = a e00, e11' = d e11, e01' = f e01, e10' = k e10
+      MicroOp m;
+      memset(&m, 0, sizeof(m));
+      m.pred_bit = s.pred_bit;
+      m.type = G_XPAT; m.flags = s.b[1] == A ? 0 : 1;
+      m.c_off = (int)(dev_consts.size() - pcb);
+      const double2* t = &h->cpool[s.c_off];
+      const double2 z = make_double2(0.0, 0.0);
+      const double2 c8[8] = {t[0], z, z, t[3], t[1], z, z, t[2]};
+      for (int k = 0; k < 8; ++k) dev_consts.push_back(c8[k]);
+      dev_ops.push_back(m);
+      return;
+    }
+    dev_ops.push_back(make_sub(ho, A, B, tile, pcb));
+  }
+
   struct Item {
     bool group;
     std::vector<const HostOp*> ops;
@@ -906,7 +1029,8 @@ struct Planner {
           if (k >= 16) { err = "planner: too many column bits in a tile"; return false; }
           pp.ax_ord[a] = (int8_t)k;
           pp.dg_mask[k] = (1u << cl) | (rl >= 0 ? (1u << rl) : 0u);
-          pp.dg_req[k] = rl >= 0 ? (int8_t)-1 : (int8_t)(a + h->nmax);
+          pp.dg_req[k] = rl >= 0 ? (int8_t)0 : (int8_t)(a + h->nmax);
+          if (rl < 0) pp.dg_req_mask |= 1u << k;
           ++k;
         } else if (rl >= 0) {
           if (pp.dg_nfix >= 16) { err = "planner: too many row-only axes in a tile"; return false; }
@@ -1019,9 +1143,10 @@ struct Planner {
           uint64_t* tc = reinterpret_cast<uint64_t*>(&g.p[0]);
           tc[0] = x.octrl; tc[1] = x.octrl2;
         }
-        g.aux = (int)ops.size();
+        const size_t hdr = dev_ops.size();
         dev_ops.push_back(g);
-        for (const HostOp* ho : ops) dev_ops.push_back(make_sub(ho, A, B, tile, P.const_begin));
+        for (const HostOp* ho : ops) emit_sub(ho, A, B, tile, P.const_begin);
+        dev_ops[hdr].aux = (int)(dev_ops.size() - hdr - 1);
         writes = true;
       } else {
         for (const HostOp* ho : it.ops) {
@@ -1063,7 +1188,7 @@ struct Planner {
   bool plan() {
     std::vector<const HostOp*> cur;
     uint64_t live_now = h->planned_live, need = 0, live = live_now;
-    int nconst = 0;
+    int nconst = 0, nslots = 0;
     for (const HostOp& op : h->queue) {
       if (op.kind == 1 && cluster_mode() && !cur.empty() && cur.back()->m.type == OP_PROBS) {
         // small registers: all tiles of a shot fit one thread-block cluster, so the measurement is a
@@ -1093,24 +1218,26 @@ struct Planner {
         F.fp.flip = op.flip; F.fp.forced = op.forced; F.fp.creg_bit = op.creg_bit;
         F.fp.is_dm = h->formalism == DQE_DM;
         passes.push_back(F);
-        need = 0; live = live_now; nconst = 0;
+        need = 0; live = live_now; nconst = 0; nslots = 0;
         continue;
       }
       uint64_t need2 = need | op.need;
       uint64_t live2 = live | op.live_after | op.need;
       int t = 0;
       uint64_t tile = 0;
-      // every op may need a group header in the worst case -> 2 slots per op
-      const bool fits = cur.empty() || (h->fuse && 2 * ((int)cur.size() + 1) <= kMaxOpsPerPass &&
-                                        nconst + op.nconst <= max_consts(h->formalism) &&
+      // every op may need a group header in the worst case, and runs as up to nf factors inside a group
+      const int op_slots = 1 + std::max(1, op.nf);
+      const bool fits = cur.empty() || (h->fuse && nslots + op_slots <= kMaxOpsPerPass &&
+                                        nconst + std::max(op.nconst, 8) <= max_consts(h->formalism) &&
                                         choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
         if (!close(cur, need, live)) return false;
         need2 = op.need;
         live2 = live_now | op.live_after | op.need;
-        nconst = 0;
+        nconst = 0; nslots = 0;
       }
-      nconst += op.nconst;
+      nconst += std::max(op.nconst, 8);   // an X-pattern / factor form may need up to 8 constants
+      nslots += op_slots;
       cur.push_back(&op);
       need = need2; live = live2;
       live_now = op.live_after;
@@ -1314,7 +1441,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1876,6 +2003,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "factor")) {
+    h->factor = value ? 1 : 0;
   } else if (!strcmp(key, "cxperm")) {
     h->cxperm = value ? 1 : 0;
   } else if (!strcmp(key, "cluster")) {
