@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-bits", type=int, default=None)
     ap.add_argument("--comm-low", type=int, default=0, help="reserve (and pin) the k lowest axes for comm qubits")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine option for A/B measurements (dqe_set_option), e.g. --opt tmap=0")
     return ap.parse_args()
 
 
@@ -89,6 +91,15 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        self.mode = os.environ.get("DQE_BENCH_SAMPLER", "smi")
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                self._start_nvml()
+                return
+            except Exception:  # pragma: no cover -- fall back to the nvidia-smi loop
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -102,14 +113,41 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def _start_nvml(self):
+        """Same fields through NVML in-process (no nvidia-smi process polling the driver every 200 ms)."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        hd = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self._stop = threading.Event()
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hwt"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "swt"), (nv.nvmlClocksEventReasonSwPowerCap, "swp")]
+
+        def loop():
+            smax = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)), str(smax),
+                                  str(nv.nvmlDeviceGetPowerUsage(hd) / 1000.0)] +
+                                 ["Active" if r & b else "Not Active" for b, _ in bits])
+                self._stop.wait(0.2)
+
+        self.th = threading.Thread(target=loop, daemon=True)
+        self.th.start()
+        self.proc = None
+
     def stop(self):
-        if not self.proc:
+        if getattr(self, "mode", "smi") == "nvml" and getattr(self, "_stop", None) is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -227,6 +265,9 @@ def main():
         data, ideal = experiment.ideal_output_ket(ops, mk)
         eng = Engine("dm", 7, a.shots, seed=2024, shot_offset=rank * a.shots, device=local,
                      stream=stream.cuda_stream, tile_bits=a.tile_bits)
+        for kv in a.opt:
+            k, v = kv.split("=")
+            eng.set_option(k, int(v))
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
 

@@ -12,6 +12,7 @@
 // bit, and a channel is a 4x4 superoperator on (row bit, column bit) -- one pass over rho.
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -109,6 +110,11 @@ struct PassParams {
   int32_t dg_nfix;
   uint32_t dg_req_mask;    // free variables with a dg_req entry
   uint32_t dg_eq_mask;     // axes with both bits outside: base bit a must equal base bit a + nmax
+  // TMA tensor map of the pass (tm_rank != 0): the tile is ONE box -- dimension 0 = the contiguous low run,
+  // one dimension per higher tile segment, plus a box-1 "base" dimension of stride 2^tm_shift amplitudes
+  // whose coordinate carries the shot and the outer bits.  One instruction loads / stores the whole tile.
+  alignas(64) CUtensorMap tmap;
+  int32_t tm_rank, tm_base_dim, tm_shift, prefetch_dist;
   uint32_t run_hi[128];   // TMA: (physical offset of run r) >> c0, for the 2^(t-c0) <= 128 runs of a tile
   Seg tile_segs[16];
   Seg outer_segs[24];
@@ -503,10 +509,17 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 template <int FORM>
 __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                uint64_t base, uint64_t shot, uint64_t cw, double* red,
-                                               double (*part)[16][2], MeasRec* mrec, int mcount) {
+                                               double (*part)[16][2], MeasRec* mrec, int mcount, double* s_draw) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int par = mcount & 1;
+  // the Philox draw does not depend on the probabilities: lane 0 of warp 1 (idle during the diagonal sum of
+  // a small tile) computes it now, off the critical path; thread 0 reads it after the cluster barrier
+  if (threadIdx.x == 32) {
+    double u, u2;
+    shot_uniforms(pp.seed, pp.shot_offset + shot, op.octrl, u, u2);
+    *s_draw = u;
+  }
   // 1. this tile's partials (same arithmetic as op_probs)
   double a0 = 0.0, a1 = 0.0;
   const int abit = op.aux;
@@ -554,8 +567,7 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
     const double e = op.p[0];
     const double q0 = (1.0 - e) * p0 + e * p1, q1 = (1.0 - e) * p1 + e * p0;
     const double tot = q0 + q1;
-    double u, u2;
-    shot_uniforms(pp.seed, pp.shot_offset + shot, op.octrl, u, u2);
+    const double u = *s_draw;
     const int forced = (int)op.lctrl - 1;
     const int m = forced >= 0 ? forced : ((u * tot < q1) ? 1 : 0);
     const double pm = m ? q1 : q0;
@@ -995,6 +1007,50 @@ __device__ __forceinline__ void tma_load_bytes(uint32_t dst_s, const void* src, 
                "l"(src), "r"(bytes), "r"(bar_s)
                : "memory");
 }
+// whole-tile tensor copies (rank 3..5); c[] = box origin, all zero but the base dimension
+__device__ __forceinline__ void tma_tensor_load(const CUtensorMap* tm, int rank, uint32_t dst_s, uint32_t bar_s, const int32_t* c) {
+  const uint64_t tp = reinterpret_cast<uint64_t>(tm);
+  if (rank == 3)
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst_s), "l"(tp), "r"(bar_s), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+  else if (rank == 4)
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst_s), "l"(tp), "r"(bar_s), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst_s), "l"(tp), "r"(bar_s), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tma_tensor_store(const CUtensorMap* tm, int rank, uint32_t src_s, const int32_t* c) {
+  const uint64_t tp = reinterpret_cast<uint64_t>(tm);
+  if (rank == 3)
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tp), "r"(src_s), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+  else if (rank == 4)
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tp), "r"(src_s), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(tp), "r"(src_s), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tma_tensor_prefetch(const CUtensorMap* tm, int rank, const int32_t* c) {
+  const uint64_t tp = reinterpret_cast<uint64_t>(tm);
+  if (rank == 3)
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tp), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+  else if (rank == 4)
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tp), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+  else
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(tp), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tm_coords(const PassParams& pp, uint64_t blk, int32_t* c) {
+  const uint64_t base = deposit(blk & ((1ull << pp.outer_bits) - 1ull), pp.outer_segs, pp.n_outer_segs);
+  const uint64_t off = ((blk >> pp.outer_bits) << pp.P) + base;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) c[i] = 0;
+  const int32_t cb = (int32_t)(off >> pp.tm_shift);
+#pragma unroll
+  for (int i = 1; i < 5; ++i) if (i == pp.tm_base_dim) c[i] = cb;
+}
+
 // r0 / rstep must be warp-uniform (every lane runs the loop with the same operands so that the
 // address arithmetic stays on the uniform datapath); only the lane with `leader` set issues.
 __device__ __forceinline__ void tma_load_tile(const PassParams& pp, const double2* sp, uint32_t dst_s, uint32_t bar_s,
@@ -1023,13 +1079,14 @@ __device__ __forceinline__ uint32_t fresh_ctaid() { uint32_t t; asm volatile("mo
 // (tile counter, buffer parity, prefetch) disappears at compile time.
 template <int MAXT, int MINB, int FORM, bool PERSIST>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
-  extern __shared__ double2 dyn_tiles[];
+  extern __shared__ __align__(128) double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
   __shared__ double2 s_consts[max_consts(FORM)];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[kMaxDiagRun];
   __shared__ MeasRec s_meas;
+  __shared__ double s_draw;
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
@@ -1039,6 +1096,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 
+  const bool tmx = !PERSIST && tma && pp.tm_rank != 0;   // tensor-map path (one copy per tile and direction)
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
   const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   uint64_t blk = blockIdx.x;
@@ -1061,6 +1119,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       // the micro-program and its constants ride on the first tile's barrier as two more bulk copies
       const uint32_t ops_bytes = (uint32_t)pp.nops * (uint32_t)sizeof(MicroOp), c_bytes = (uint32_t)pp.nconsts * 16u;
       tma_expect(bar0_s, T * 16u + ops_bytes + c_bytes);
+      if (tmx) {   // the whole tile in one tensor copy
+        int32_t c[5];
+        tm_coords(pp, blk, c);
+        tma_tensor_load(&pp.tmap, pp.tm_rank, tiles_s, bar0_s, c);
+        // ... and the tile of the CTA that will take this slot next (one wave of resident CTAs ahead) into L2
+        const uint64_t ahead = blk + (uint64_t)pp.prefetch_dist;
+        if (pp.prefetch_dist > 0 && ahead < pp.ntiles) {
+          tm_coords(pp, ahead, c);
+          tma_tensor_prefetch(&pp.tmap, pp.tm_rank, c);
+        }
+      }
       tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_ops), pp.ops, ops_bytes, bar0_s);
       if (c_bytes) tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_consts), pp.consts, c_bytes, bar0_s);
     }
@@ -1069,7 +1138,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   // warp index through a shuffle: the compiler then knows it is warp-uniform (CUTLASS idiom)
   const uint32_t wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarps = blockDim.x >> 5;
   const bool issuer = (threadIdx.x & 31u) == 0u;   // lane 0 of every warp issues its share of the copies
-  if (tma && blk < pp.ntiles) {
+  if (tma && !tmx && blk < pp.ntiles) {
     const uint64_t base0 = deposit(blk & outer_mask, pp.outer_segs, pp.n_outer_segs);
     tma_load_tile(pp, pp.state + ((blk >> pp.outer_bits) << pp.P) + base0, tiles_s, bar0_s, T, c0, wid, nwarps, issuer);
   }
@@ -1158,7 +1227,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           }
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++); break;
+          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
           case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
           default: break;
@@ -1183,7 +1252,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_DEPOL2: op_depol2(tile, T, op); break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++); break;
+          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
           case OP_TRACE: op_trace(tile, T, op); break;
           case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
           default: break;
@@ -1197,7 +1266,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if constexpr (!PERSIST) {   // one tile per CTA: addressing state re-derived here (see fresh_tid)
+        if (!PERSIST && pp.tm_rank != 0) {
+          if (fresh_tid() == 0) {
+            int32_t c[5];
+            tm_coords(pp, (uint64_t)fresh_ctaid(), c);
+            tma_tensor_store(&pp.tmap, pp.tm_rank, (uint32_t)__cvta_generic_to_shared(dyn_tiles), c);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem stays valid until read
+          }
+        } else if constexpr (!PERSIST) {   // one tile per CTA: addressing state re-derived here (see fresh_tid)
           const uint32_t tid2 = fresh_tid();
           const uint32_t wid2 = __shfl_sync(0xffffffffu, tid2 >> 5, 0), nwarps2 = blockDim.x >> 5;
           const bool issuer2 = (tid2 & 31u) == 0u;

@@ -88,7 +88,8 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm, factor;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm, factor, tmap, prefetch;
+  int64_t tmap_used, tmap_refused;
   int64_t stats[8];
   bool timing;
   cudaEvent_t ev0, ev1;
@@ -1248,6 +1249,67 @@ struct Planner {
   }
 };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Tensor map of one pass: the tile as a single TMA box (see PassParams::tmap).  Leaves tm_rank = 0 (bulk-run
+// path) when the tile is one or two runs anyway, when the shape does not fit 5 dimensions, or when the
+// driver refuses the descriptor.
+void build_tensor_map(dqe_t* h, PassParams& pp) {
+  pp.tm_rank = 0;
+  if (!h->tmap || !pp.use_tma || h->persistent) return;
+  const int c0 = pp.tile_segs[0].len;
+  if (c0 > 7 || (pp.t - c0) < 2) return;
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return;
+  struct Dim { uint64_t stride, size; uint32_t box; bool base; };
+  std::vector<Dim> dims;
+  for (int i = 1; i < pp.n_tile_segs; ++i) {
+    const Seg& sg = pp.tile_segs[i];
+    if (sg.len > 8) return;
+    dims.push_back(Dim{16ull << sg.dst, 1ull << sg.len, 1u << sg.len, false});
+  }
+  const int lb = pp.n_outer_segs > 0 && pp.outer_bits > 0 ? pp.outer_segs[0].dst : pp.P;
+  const uint64_t total = (uint64_t)h->batch << pp.P;
+  const uint64_t nbase = total >> lb;
+  if (nbase == 0 || nbase > (1ull << 31)) return;
+  dims.push_back(Dim{16ull << lb, nbase, 1u, true});
+  std::sort(dims.begin(), dims.end(), [](const Dim& a, const Dim& b) { return a.stride < b.stride; });
+  const int rank = 1 + (int)dims.size();
+  if (rank < 3 || rank > 5) return;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  gdim[0] = 2ull << c0; box[0] = 2u << c0;   // complex128 = 2 x FLOAT64
+  int base_dim = 0;
+  for (int i = 0; i < (int)dims.size(); ++i) {
+    if (dims[i].stride >= (1ull << 40)) return;
+    gdim[i + 1] = dims[i].size; box[i + 1] = dims[i].box; gstr[i] = dims[i].stride;
+    if (dims[i].base) base_dim = i + 1;
+  }
+  const CUresult rc = enc(&pp.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, (void*)pp.state, gdim, gstr, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { h->tmap_refused++; return; }
+  pp.tm_rank = rank; pp.tm_base_dim = base_dim; pp.tm_shift = lb;
+  // L2 prefetch distance: one wave of resident CTAs ahead (-1 = automatic: SMs x CTAs per SM)
+  pp.prefetch_dist = h->prefetch >= 0 ? h->prefetch : h->num_sms * (h->threads <= 64 ? 8 : 4);
+}
+
 int ensure_partials(dqe_t* h, size_t n) {
   if (n <= h->partials_cap) return 0;
   if (h->partials) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->partials)); h->partials = nullptr; }
@@ -1332,6 +1394,8 @@ int do_flush(dqe_t* h) {
     if (P.pp.ntiles > (1ull << 40)) return fail(h, DQE_EUNSUPPORTED, "too many tiles");
     P.pp.state = h->state; P.pp.creg = h->creg; P.pp.partials = h->partials; P.pp.rec = h->rec;
     P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
+    build_tensor_map(h, P.pp);
+    if (P.pp.tm_rank) h->tmap_used++;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -1381,6 +1445,9 @@ int do_flush(dqe_t* h) {
     h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
   }
   CK(cudaGetLastError());
+  if (getenv("DQE_DEBUG"))
+    fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
+            (long long)h->tmap_used, (long long)h->tmap_refused);
   h->queue.clear();
   h->cpool.clear();
   h->planned_live = phys_live(h, h->live_axes);
@@ -1433,7 +1500,8 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   *out = nullptr;
   if (formalism != DQE_KET && formalism != DQE_DM) return fail(nullptr, DQE_EINVAL, "formalism must be 0 (ket) or 1 (dm)");
   const int P = formalism == DQE_KET ? max_qubits : 2 * max_qubits;
-  if (max_qubits < 1 || P > 40) return fail(nullptr, DQE_EINVAL, "max_qubits out of range (ket <= 40, dm <= 20)");
+  if (max_qubits < 1 || P > 40 || (formalism == DQE_DM && max_qubits > 16))
+    return fail(nullptr, DQE_EINVAL, "max_qubits out of range (ket <= 40, dm <= 16: 4^16 complex128 = 64 GiB)");
   if (batch < 1) return fail(nullptr, DQE_EINVAL, "batch must be >= 1");
   dqe_t* h = new dqe_engine();
   h->formalism = formalism; h->nmax = max_qubits; h->P = P; h->device = device; h->batch = batch;
@@ -1441,7 +1509,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -2003,6 +2071,11 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "prefetch")) {
+    if (value < -1 || value > (1 << 20)) return fail(h, DQE_EINVAL, "prefetch distance in [-1, 2^20] tiles");
+    h->prefetch = (int)value;
+  } else if (!strcmp(key, "tmap")) {
+    h->tmap = value ? 1 : 0;
   } else if (!strcmp(key, "factor")) {
     h->factor = value ? 1 : 0;
   } else if (!strcmp(key, "cxperm")) {

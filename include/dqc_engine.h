@@ -181,7 +181,12 @@ int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_ax
  * of cp.async.bulk), "persistent" (1: persistent CTAs with a double-buffered tile ring instead of
  * one tile per CTA), "ctas_per_sm" (cap for the persistent grid), "pin_mask" (axes that passes always
  * enumerate, live or free: pinning the lowest axes keeps the low bits of every tile contiguous in HBM
- * when those axes hold qubits that come and go, e.g. communication qubits). */
+ * when those axes hold qubits that come and go, e.g. communication qubits), "cxperm" (0: X / CX inside a
+ * qubit-pair group is arithmetic instead of a permutation of the sweep's load / store addresses), "factor"
+ * (0: composed axis-local superoperators stay dense 4x4 stand-alone sweeps instead of running as their
+ * Pauli-channel / U rho U^dagger factors inside group sweeps), "tmap" (0: a tile is fetched run by run with
+ * cp.async.bulk instead of one cp.async.bulk.tensor box per direction), "prefetch" (tiles ahead whose box is
+ * prefetched into L2 at CTA start; -1 = one wave of resident CTAs, 0 = off). */
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates

@@ -42,10 +42,16 @@ Parity pinning
 --------------
 Pinned against every closed-form state the reference's own tests assert for this path
 (``tests/test_oracle_known_answers.py`` lifts them with file:line citations) and the
-circuit-level states of ``test_dqc_control.py`` / ``test_circuit_identities.py``.  The
-reference pins states only to ~1e-5 fidelity and up to global phase; amplitude-level
-(1e-10) agreement is engine-vs-oracle only.  Histogram sampling is *parity unpinned*
-upstream (no sampling test exists in the reference).
+circuit-level states of ``test_dqc_control.py`` / ``test_circuit_identities.py``, and
+against real NetSquid output: the 16-digit noisy end-to-end fidelities the reference's
+examples print (``examples/getting_started.py:128-139``, ``from_monolithic_circuit.py:143-155``,
+``run_experiment.py:80-93`` GHZ-5) are reproduced to <= 4e-16 by the one trajectory of forced
+measurement outcomes that produced them (``tests/test_reference_printed_fidelities.py``) --
+executor timeline, channel order, Werner ebits and this arithmetic all have to agree with
+NetSquid's for that.  The reference's own tests pin states only to ~1e-5 fidelity and up to
+global phase; amplitude-level (1e-10) agreement beyond those numbers is engine-vs-oracle
+only.  Histogram sampling is *parity unpinned* upstream (no sampling test exists in the
+reference).
 """
 import numpy as np
 

@@ -181,6 +181,20 @@ def test_random_programs_fused(formalism, n, batch, tile, fuse):
         assert st["micro_ops"] > st["passes"]
 
 
+@pytest.mark.parametrize("opts", [dict(cxperm=0), dict(factor=0), dict(tmap=0), dict(prefetch=0), dict(prefetch=3),
+                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0)])
+@pytest.mark.parametrize("n,batch,tile", [(7, 3, 10), (6, 4, 8), (7, 2, 12)])
+def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
+    """Every planner / kernel switch of the density-matrix path (X / CX by address permutation, factored
+    superoperators inside group sweeps, tensor-map tile copies, L2 prefetch, cluster-fused measurement,
+    group sweeps, TMA) gives the oracle's state and classical bits, on or off."""
+    rng = np.random.default_rng(4242 + n + tile)
+    b = Both("dm", n, batch, 9, tile_bits=tile)
+    for k, v in opts.items():
+        b.g.set_option(k, v)
+    random_program(b, rng, 120, "dm", check_every=40)
+
+
 @pytest.mark.parametrize("formalism", ["ket", "dm"])
 def test_forced_outcomes_bit_exact(formalism):
     n = 5
