@@ -61,19 +61,24 @@ __host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMax
 constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
 struct __align__(16) MicroOp {
+  // dispatch header: the first 16 bytes are everything the interpreter needs to decide what to run next,
+  // fetched with ONE shared-memory load one op ahead of its use
   int32_t type;
   int32_t pred_bit;     // creg bit that must be 1 for the shot, -1 = unconditional
+  int32_t flags;
+  int32_t c_off;        // offset of this op's constants in the pass constant pool (double2 units);
+                        // OP_GROUP header: number of sub-ops (= aux), so that skipping a group needs the header only
   uint32_t lctrl;       // control mask, tile-local bits
   uint32_t nb;          // number of entries of b[] in use
+  int32_t aux;          // PROBS: physical bit of the axis; sampled ops: draw index; OP_GROUP: number of sub-ops
+  uint32_t lctrl2;      // MAT1X2: control mask of the column side
   uint64_t octrl;       // control mask, physical bits outside the tile (tested on the tile base)
   uint8_t b[8];         // bit positions (tile-local, or kOuter + physical)
-  int32_t c_off;        // offset of this op's constants in the pass constant pool (double2 units)
-  int32_t flags;
-  int32_t aux;          // PROBS: physical bit of the axis; sampled ops: draw index
-  uint32_t lctrl2;      // MAT1X2: control mask of the column side
   uint64_t octrl2;
   double p[4];
 };
+static_assert(sizeof(MicroOp) == 96, "MicroOp is staged by 16-byte bulk copies");
+__device__ __forceinline__ int4 op_header(const MicroOp* op) { return *reinterpret_cast<const int4*>(op); }
 
 struct Seg {  // bits [src, src+len) of a dense index go to physical bits [dst, dst+len)
   uint8_t src, len, dst, pad;
@@ -914,20 +919,30 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
   // X / CX hoisted by the planner to the head (flags bits 0-3: on, role, in_r, in_c; controls octrl / octrl2)
   // or the tail (bits 4-7; controls in p[0], p[1]) of the group: applied by the load / store addresses
   const uint64_t* tail_ctrl = reinterpret_cast<const uint64_t*>(&g.p[0]);
-  const GPerm pre = make_perm(g.flags & 1, (g.flags >> 1) & 7, g.octrl, g.octrl2, base, mra, mrb, mca, mcb);
-  const GPerm post = make_perm(g.flags & 16, (g.flags >> 5) & 7, tail_ctrl[0], tail_ctrl[1], base, mra, mrb, mca, mcb);
+  const bool has_pre = g.flags & 1, has_post = g.flags & 16;   // most groups carry neither: plain addresses
+  GPerm pre, post;
+  if (has_pre) pre = make_perm(true, (g.flags >> 1) & 7, g.octrl, g.octrl2, base, mra, mrb, mca, mcb);
+  if (has_post) post = make_perm(true, (g.flags >> 5) & 7, tail_ctrl[0], tail_ctrl[1], base, mra, mrb, mca, mcb);
 #define DQE_GADDR(e) (i0 | (((e) & 8) ? mra : 0u) | (((e) & 4) ? mrb : 0u) | (((e) & 2) ? mca : 0u) | (((e) & 1) ? mcb : 0u))
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
     double2 v[16];
+    if (has_pre) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e) ^ pre.r[(e >> 2) & 3] ^ pre.c[e & 3]];
+      for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e) ^ pre.r[(e >> 2) & 3] ^ pre.c[e & 3]];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e)];
+    }
+    int4 hdr = nsub > 0 ? op_header(sub) : make_int4(0, -1, 0, 0);
     for (int s = 0; s < nsub; ++s) {
       const MicroOp& op = sub[s];
-      if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
-      const double2* cs = cs_base + op.c_off;
-      const int role = op.flags & 1;
-      switch (op.type) {
+      const int op_type = hdr.x, op_pred = hdr.y, op_flags = hdr.z, op_coff = hdr.w;
+      if (s + 1 < nsub) hdr = op_header(sub + s + 1);   // next sub-op's header: its latency hides behind this one
+      if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
+      const double2* cs = cs_base + op_coff;
+      const int role = op_flags & 1;
+      switch (op_type) {
         case G_PAULI1:
           if (role) g_pauli1<1>(v, op); else g_pauli1<0>(v, op);
           break;
@@ -940,17 +955,17 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           if (role) g_xpat<1>(v, cs); else g_xpat<0>(v, cs);
           break;
         case G_MAT1X2: {
-          if (op.flags & 16) {
+          if (op_flags & 16) {
             // X / CX in the middle of a group: a round trip through the thread's own 16 tile slots with
             // permuted store addresses (no barrier: nobody else touches them during the sweep)
-            const GPerm mid = make_perm(true, op.flags & 7, op.octrl, op.octrl2, base, mra, mrb, mca, mcb);
+            const GPerm mid = make_perm(true, op_flags & 7, op.octrl, op.octrl2, base, mra, mrb, mca, mcb);
 #pragma unroll
             for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ mid.r[(e >> 2) & 3] ^ mid.c[e & 3]] = v[e];
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e)];
             break;
           }
-          const bool in_r = op.flags & 2, in_c = op.flags & 4;
+          const bool in_r = op_flags & 2, in_c = op_flags & 4;
           const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
           if (role) g_mat1x2<1>(v, cs, r_on, c_on, in_r, in_c);
           else g_mat1x2<0>(v, cs, r_on, c_on, in_r, in_c);
@@ -963,8 +978,8 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 #endif
         case G_COLLAPSE: {
           const MeasRec r = *mrec;
-          if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
-          else g_collapse<0>(v, r.outcome, r.scale, op.p[0], op.flags & 8);
+          if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op_flags & 8);
+          else g_collapse<0>(v, r.outcome, r.scale, op.p[0], op_flags & 8);
           break;
         }
         case G_TRACE:
@@ -990,8 +1005,13 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         default: break;
       }
     }
+    if (has_post) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ post.r[(e >> 2) & 3] ^ post.c[e & 3]] = v[e];
+      for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ post.r[(e >> 2) & 3] ^ post.c[e & 3]] = v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e)] = v[e];
+    }
   }
 #undef DQE_GADDR
 }
@@ -1206,12 +1226,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     __syncthreads();
     int mcount = 0;
 
-    for (int o = 0; o < pp.nops; ++o) {
-      const MicroOp& op = s_ops[o];
-      if (op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull)) continue;
-      const double2* cs = s_consts + op.c_off;
+    // the dispatch header of the NEXT op is fetched before the current op runs (one 16-byte load, its
+    // latency hidden behind the op); a group header carries its sub-op count in c_off, so the skip over
+    // the sub-ops needs nothing else
+    int4 hdr = op_header(&s_ops[0]);
+    for (int o = 0; o < pp.nops;) {
+      const int cur = o;
+      const MicroOp& op = s_ops[cur];
+      const int op_type = hdr.x, op_pred = hdr.y;
+      const double2* cs = s_consts + hdr.w;
+      o = cur + 1 + (op_type == OP_GROUP ? hdr.w : 0);
+      if (o < pp.nops) hdr = op_header(&s_ops[o]);
+      if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if constexpr (FORM == 0) {   // ---- ket micro-ops
-        switch (op.type) {
+        switch (op_type) {
           case OP_MAT1:
             if ((base & op.octrl) == op.octrl) op_mat1(tile, T, op, cs);
             break;
@@ -1220,9 +1248,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_DIAG: {
             int run = 1;
-            while (o + run < pp.nops && run < kMaxDiagRun && s_ops[o + run].type == OP_DIAG) ++run;
+            while (cur + run < pp.nops && run < kMaxDiagRun && s_ops[cur + run].type == OP_DIAG) ++run;
             if (run == 1) op_diag(tile, T, op, cs, base);
-            else { op_diag_run(tile, T, &s_ops[o], run, s_consts, base, cw, s_diag); o += run - 1; }
+            else {
+              op_diag_run(tile, T, &s_ops[cur], run, s_consts, base, cw, s_diag);
+              o = cur + run;
+              if (o < pp.nops) hdr = op_header(&s_ops[o]);
+            }
             break;
           }
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
@@ -1233,10 +1265,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           default: break;
         }
       } else {                     // ---- density-matrix micro-ops
-        switch (op.type) {
+        switch (op_type) {
           case OP_GROUP:
-            run_group(tile, T, op, &s_ops[o + 1], pp, s_consts, base, cw, &s_meas);
-            o += op.aux;
+            run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas);
             break;
           case OP_MAT1X2: {
             const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;

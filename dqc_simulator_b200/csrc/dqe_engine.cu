@@ -1148,6 +1148,7 @@ struct Planner {
         dev_ops.push_back(g);
         for (const HostOp* ho : ops) emit_sub(ho, A, B, tile, P.const_begin);
         dev_ops[hdr].aux = (int)(dev_ops.size() - hdr - 1);
+        dev_ops[hdr].c_off = dev_ops[hdr].aux;   // the interpreter skips the sub-ops from the dispatch header alone
         writes = true;
       } else {
         for (const HostOp* ho : it.ops) {
