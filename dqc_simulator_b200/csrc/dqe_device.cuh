@@ -40,17 +40,13 @@ enum OpType : int32_t {
   // whole run of gates / channels on those two qubits.
   OP_GROUP = 12,
   G_PAULI1 = 101,     // flags bit0 = role of the target axis (0 = A, 1 = B)
-  G_MAT2 = 102,       // 4x4 superoperator on (row, col) of one axis
   G_MAT1X2 = 103,     // U on the row side / conj(U) on the column side; flags bit1/bit2: row/col control
                       // is the OTHER axis of the group (else octrl/octrl2 on the tile base)
   G_DEPOL2 = 104,
-  G_MAT2ROWS = 105,   // dense 4x4 on (ra, rb), A = MSB
-  G_MAT2COLS = 106,   // dense 4x4 on (ca, cb)
   G_COLLAPSE = 107,
   G_TRACE = 108,
   G_INJECT = 109,
   G_XPAT = 111,
-  G_DIAG = 110,       // p[0..1] hold a 16-byte table-index LUT (one byte per element)
 };
 
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
@@ -759,30 +755,6 @@ __device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
     }
 }
 
-__device__ __forceinline__ double2 ldv(const double2* p) {   // ordered shared-memory read: stops ptxas from
-  double2 r;                                                  // hoisting a whole matrix into registers
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-  return r;
-}
-
-template <int ROLE>
-__device__ __forceinline__ void g_mat2(double2 (&v)[16], const double2* __restrict__ cs) {
-  // matrix entries are re-read from shared memory (broadcast) per use: keeping 16 complex
-  // coefficients live next to the 16 data elements would cost 64 more registers per thread
-#pragma unroll
-  for (int ro = 0; ro < 2; ++ro)
-#pragma unroll
-    for (int co = 0; co < 2; ++co) {
-      const double2 x0 = v[EI<ROLE>(0, 0, ro, co)], x1 = v[EI<ROLE>(0, 1, ro, co)];
-      const double2 x2 = v[EI<ROLE>(1, 0, ro, co)], x3 = v[EI<ROLE>(1, 1, ro, co)];
-      v[EI<ROLE>(0, 0, ro, co)] = cfma(cs[3], x3, cfma(cs[2], x2, cfma(cs[1], x1, cmul(cs[0], x0))));
-      v[EI<ROLE>(0, 1, ro, co)] = cfma(cs[7], x3, cfma(cs[6], x2, cfma(cs[5], x1, cmul(cs[4], x0))));
-      v[EI<ROLE>(1, 0, ro, co)] = cfma(cs[11], x3, cfma(cs[10], x2, cfma(cs[9], x1, cmul(cs[8], x0))));
-      v[EI<ROLE>(1, 1, ro, co)] = cfma(cs[15], x3, cfma(cs[14], x2, cfma(cs[13], x1, cmul(cs[12], x0))));
-    }
-}
-
-
 template <int ROLE>
 __device__ __forceinline__ void g_xpat(double2 (&v)[16], const double2* __restrict__ cs) {
   const double2 a = cs[0], b = cs[1], c = cs[2], d = cs[3], f = cs[4], g = cs[5], h = cs[6], k = cs[7];
@@ -862,22 +834,6 @@ __device__ __forceinline__ void g_depol2(double2 (&v)[16], double pp) {
   }
 }
 
-// V[R][C], R = (ra, rb), C = (ca, cb): rows side V <- M V ; cols side V[R][C] <- sum_C' mc[C][C'] V[R][C']
-template <bool ROWS>
-__device__ __forceinline__ void g_mat2side(double2 (&v)[16], const double2* __restrict__ m) {
-#pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    double2 x[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = ROWS ? v[j * 4 + f] : v[f * 4 + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double2 y = cfma(m[i * 4 + 3], x[3], cfma(m[i * 4 + 2], x[2], cfma(m[i * 4 + 1], x[1], cmul(m[i * 4], x[0]))));
-      if (ROWS) v[i * 4 + f] = y; else v[f * 4 + i] = y;
-    }
-  }
-}
-
 template <int ROLE>
 __device__ __forceinline__ void g_collapse(double2 (&v)[16], int m, double sc, double e, bool discard) {
   const double2 zero = make_double2(0.0, 0.0);
@@ -946,11 +902,6 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         case G_PAULI1:
           if (role) g_pauli1<1>(v, op); else g_pauli1<0>(v, op);
           break;
-#ifdef DQE_GROUP_HEAVY
-        case G_MAT2:
-          if (role) g_mat2<1>(v, cs); else g_mat2<0>(v, cs);
-          break;
-#endif
         case G_XPAT:
           if (role) g_xpat<1>(v, cs); else g_xpat<0>(v, cs);
           break;
@@ -972,10 +923,6 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           break;
         }
         case G_DEPOL2: g_depol2(v, op.p[0]); break;
-#ifdef DQE_GROUP_HEAVY
-        case G_MAT2ROWS: g_mat2side<true>(v, cs); break;
-        case G_MAT2COLS: g_mat2side<false>(v, cs); break;
-#endif
         case G_COLLAPSE: {
           const MeasRec r = *mrec;
           if (role) g_collapse<1>(v, r.outcome, r.scale, op.p[0], op_flags & 8);
@@ -991,17 +938,6 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           for (int e = 0; e < 16; ++e) v[e] = cmul(x, cs[e]);
           break;
         }
-#ifdef DQE_GROUP_HEAVY
-        case G_DIAG: {
-          const uint8_t* lut = reinterpret_cast<const uint8_t*>(&op.p[0]);
-          uint32_t fixed = 0;
-          for (uint32_t i = 0; i < op.nb; ++i)
-            if (op.b[i] >= kOuter) fixed |= (uint32_t)((base >> (op.b[i] - kOuter)) & 1ull) << (op.nb - 1 - i);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], cs[lut[e] | fixed]);
-          break;
-        }
-#endif
         default: break;
       }
     }

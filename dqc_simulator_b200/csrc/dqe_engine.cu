@@ -167,6 +167,7 @@ bool compose_factors(const HostOp& first, const HostOp& then, int* nf, Factor* o
   *nf = 0;
   if (first.nf <= 0 || then.nf <= 0) return false;
   Factor tmp[2 * kMaxFactors];
+  memset(tmp, 0, sizeof(tmp));
   int n = 0;
   auto add = [&](const Factor& f) {
     if (n > 0 && tmp[n - 1].kind == f.kind) {
@@ -818,17 +819,11 @@ struct Planner {
       case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE: case OP_XPAT:
         return add(m.b[1]);
       case OP_MAT2:
-        if (ho->pctrl) return false;
-#ifndef DQE_GROUP_HEAVY
         // a dense 4x4 block inside the register-resident group interpreter costs every other sub-op its
         // registers (see run_group): an axis-local superoperator joins a group as its light factors
         // (Pauli channels, U rho U^dagger); anything else stays a stand-alone sweep
+        if (ho->pctrl) return false;
         if (m.b[0] == m.b[1] + n && ho->nf > 0 && h->factor) return add(m.b[1]);
-        return false;
-#endif
-        if (m.b[0] == m.b[1] + n) return add(m.b[1]);
-        if (m.b[0] >= n && m.b[1] >= n) return add(m.b[0] - n) && add(m.b[1] - n);
-        if (m.b[0] < n && m.b[1] < n) return add(m.b[0]) && add(m.b[1]);
         return false;
       case OP_DEPOL2: case OP_INJECT:
         return add(m.b[2]) && add(m.b[3]);
@@ -845,17 +840,9 @@ struct Planner {
         return add(c);                           // needs both bits of the control axis in the tile
       }
       case OP_DIAG:
-#ifndef DQE_GROUP_HEAVY
         // D rho D^dagger on one axis rides as an X-pattern sub-op; wider tables stay stand-alone
         if (m.nb == 2 && m.b[0] == m.b[1] + n && h->factor) return add(m.b[1]);
         return false;
-#endif
-        for (uint32_t i = 0; i < m.nb; ++i) {
-          const int ph = m.b[i];
-          if (!((tile >> ph) & 1ull)) continue;
-          if (!add(ph >= n ? ph - n : ph)) return false;
-        }
-        return true;
       default:
         return false;
     }
@@ -877,7 +864,6 @@ struct Planner {
 
   MicroOp make_sub(const HostOp* ho, int A, int B, uint64_t tile, size_t pcb) {
     static const int kSwap[4] = {0, 2, 1, 3};
-    const int n = h->nmax;
     MicroOp m;
     memset(&m, 0, sizeof(m));
     const MicroOp& s = ho->m;
@@ -890,15 +876,6 @@ struct Planner {
         break;
       case OP_XPAT:
         m.type = G_XPAT; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb);
-        break;
-      case OP_MAT2:
-        if (s.b[0] == s.b[1] + n) { m.type = G_MAT2; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb); }
-        else {
-          const bool rows = s.b[0] >= n;
-          const int x = rows ? s.b[0] - n : s.b[0];
-          m.type = rows ? G_MAT2ROWS : G_MAT2COLS;
-          m.c_off = copy_consts(ho, pcb, x == A ? nullptr : kSwap);
-        }
         break;
       case OP_MAT1X2: {
         m.type = G_MAT1X2; m.flags = role(s.b[1]);
@@ -921,21 +898,6 @@ struct Planner {
         m.type = G_INJECT;
         m.c_off = copy_consts(ho, pcb, s.b[2] == A ? nullptr : kSwap);
         break;
-      case OP_DIAG: {
-        m.type = G_DIAG; m.nb = s.nb;
-        uint8_t* lut = reinterpret_cast<uint8_t*>(&m.p[0]);
-        for (int e = 0; e < 16; ++e) lut[e] = 0;
-        for (uint32_t i = 0; i < s.nb; ++i) {
-          const int ph = s.b[i], sh = (int)s.nb - 1 - (int)i;
-          if (!((tile >> ph) & 1ull)) { m.b[i] = (uint8_t)(kOuter + ph); continue; }
-          m.b[i] = 0;
-          const int axis = ph >= n ? ph - n : ph;
-          const int slot = (ph >= n ? 2 : 0) + (axis == A ? 1 : 0);   // e bit: ra=3 rb=2 ca=1 cb=0
-          for (int e = 0; e < 16; ++e) lut[e] |= (uint8_t)(((e >> slot) & 1) << sh);
-        }
-        m.c_off = copy_consts(ho, pcb);
-        break;
-      }
       default: break;
     }
     return m;
@@ -1331,7 +1293,7 @@ int do_flush(dqe_t* h) {
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
                                   "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT"};
-    static const char* gnames[] = {"?", "gPAULI1", "gMAT2", "gMAT1X2", "gDEPOL2", "gROWS", "gCOLS", "gCOLLAPSE",
+    static const char* gnames[] = {"?", "gPAULI1", "-", "gMAT1X2", "gDEPOL2", "-", "-", "gCOLLAPSE",
                                    "gTRACE", "gINJECT", "gDIAG", "gXPAT"};
     for (PlannedPass& P : pl.passes) {
       if (P.is_finish) { fprintf(stderr, "  finish\n"); continue; }

@@ -159,8 +159,38 @@ class QPU:
 
     # ---- the boundary ----------------------------------------------------------
     def execute_program(self, program):
-        """Run the program's instructions in order on this QPU's clock."""
+        """Run the program's instructions on this QPU's clock, scheduled the way NetSquid's
+        ``QuantumProcessor`` runs a ``QuantumProgram(parallel=True)`` (its default, which is what
+        ``dqc_control.py`` builds): instructions are *issued in order*, one whose physical instruction is
+        ``parallel=True`` (every gate and the measurement, ``quantum_processors.py:344-456``) starts as soon
+        as the positions it acts on are free, so gates of one program on different qubits overlap in
+        simulated time; ``INSTR_INIT`` / ``INSTR_DISCARD`` are ``parallel=False`` and wait for, and hold, the
+        whole processor.  ``execute_program`` returns when every instruction has finished.  The start time
+        of an instruction is what its memory-noise exponent is computed from."""
         be = self.ex.backend
+        overlap = self.ex.parallel_programs
+        t_issue = self.clock      # in-order issue: no instruction starts before its predecessor has started
+        busy = {}                 # pos -> time its running instruction finishes
+
+        def start_of(positions, exclusive):
+            if not overlap:
+                return self.clock
+            t = t_issue
+            for b in (busy.values() if exclusive else (busy.get(p_, t) for p_ in positions)):
+                t = max(t, b)
+            return t
+
+        def finish(positions, start, duration, exclusive):
+            nonlocal t_issue
+            end = start + duration
+            if overlap:
+                for p_ in positions:
+                    busy[p_] = end
+                t_issue = end if exclusive else start
+            else:
+                self.clock = end
+            return end
+
         for instruction, positions, operator, key, predicate in program.instructions:
             tok, mat = ins.resolve((instruction, operator) if operator is not None else instruction)
             ph = self.spec.phys(tok)
@@ -168,40 +198,46 @@ class QPU:
                 # fresh |0> replaces any occupant; noise clock starts when INIT completes
                 for pos in positions:
                     self._drop(pos)
-                self.clock += ph.duration
+                end = finish(positions, start_of(positions, True), ph.duration, True)
                 for pos in positions:
-                    self.pending[pos] = self.clock
+                    self.pending[pos] = end
                 continue
             if tok.kind == "discard":
                 for pos in positions:
                     self._drop(pos)
-                self.clock += ph.duration
+                finish(positions, start_of(positions, True), ph.duration, True)
                 continue
             if tok.kind == "measure":
                 (pos,) = positions
-                (ax,) = self.touch(positions, self.clock)
+                start = start_of(positions, False)
+                (ax,) = self.touch(positions, start)
                 bit = self.ex.creg.alloc()
                 forced = self.ex._next_forced()
                 be.measure(ax, bit, forced, ph.discard, ph.prob)
-                self.clock += ph.duration
+                end = finish(positions, start, ph.duration, False)
                 if ph.discard:
                     self.axis.pop(pos)
                     self.last_access.pop(pos, None)
                     self.ex._release_axis(ax)
                 else:
-                    self.last_access[pos] = self.clock
+                    self.last_access[pos] = end
                 program.output[key] = [self.ex._deliver(bit)]
                 continue
             if tok is ins.INSTR_SWAP and self.ex.swap_as_three_cnots:
-                # NoisyQPU composite instruction (quantum_processors.py:901-909)
+                # NoisyQPU composite instruction (quantum_processors.py:901-909): its own program, run after
+                # everything issued so far has finished
                 a, b = positions
                 sub = QuantumProgram()
                 sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
                 sub.apply(ins.INSTR_CNOT, [b, a], predicate=predicate)
                 sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
+                if overlap:
+                    self.clock = max([t_issue] + list(busy.values()))
                 self.execute_program(sub)
+                t_issue = self.clock
                 continue
-            axes = self.touch(positions, self.clock)
+            start = start_of(positions, False)
+            axes = self.touch(positions, start)
             pred = -1 if predicate is None else predicate.index
             if pred >= 0:
                 be.set_predicate(pred)
@@ -215,10 +251,15 @@ class QPU:
                 be.depolarize(axes, ph.prob)
             if pred >= 0:
                 be.set_predicate(-1)
-            self.clock += ph.duration
+            # a predicated gate (batched shots) runs in the shots whose classical bit is 1 and takes no time
+            # in the others: the shared timeline advances by its expected duration (see DQCExecutor)
+            dur = ph.duration * (self.ex.predicated_time_weight if pred >= 0 else 1.0)
+            end = finish(positions, start, dur, False)
             for pos in positions:
-                self.last_access[pos] = self.clock
+                self.last_access[pos] = end
             program.output[key] = []
+        if overlap:
+            self.clock = max([t_issue] + list(busy.values()))
         # a classical bit is dead once its predicated gate has been enqueued (stream order)
         for b in {pr.index for *_, pr in program.instructions if pr is not None}:
             self.ex.creg.release(b)
@@ -243,12 +284,24 @@ class DQCExecutor:
     """
 
     def __init__(self, qpu_op_dict, dqc, backend, forced_outcomes=None, host_branching=False,
-                 swap_as_three_cnots=True, creg_bits=64, axis_pool=None, comm_axes_low=0):
+                 swap_as_three_cnots=True, creg_bits=64, axis_pool=None, comm_axes_low=0,
+                 parallel_programs=True, predicated_time_weight=0.5):
         self.ops = qpu_op_dict
         self.dqc = dqc if isinstance(dqc, DQCSpec) else DQCSpec(list(dqc))
         self.backend = backend
         self.host_branching = host_branching
         self.swap_as_three_cnots = swap_as_three_cnots
+        # True: instructions of one QuantumProgram on free positions overlap in simulated time (NetSquid's
+        # parallel=True programs, see QPU.execute_program); False: strictly one after the other
+        self.parallel_programs = parallel_programs
+        # Batched shots share ONE simulated timeline, but in the reference a classically controlled X / Z
+        # correction exists (135 us + its gate noise) only in the trajectories whose outcome was 1, and
+        # every later memory-noise exponent inherits that.  The gate and its noise are predicated per shot
+        # on the device (exact); the shared clock advances by weight x duration: 0.5 = the expected timeline
+        # (cat / teleportation outcomes are 50:50), which makes batch means unbiased to first order
+        # (QFT-5: 0.64704 vs 0.64681 with weight 1; per-trajectory reference runs: 0.64704 +- 1e-5).
+        # host_branching=True (batch 1) follows the actual outcomes exactly, like the reference.
+        self.predicated_time_weight = float(predicated_time_weight)
         self.creg = _CregAllocator(creg_bits)
         self._forced = list(forced_outcomes) if forced_outcomes is not None else None
         self._forced_i = 0

@@ -145,21 +145,33 @@ def test_plan_only_handle_refuses_reads():
 
 
 def test_oracle_reproduces_reference_printed_fidelities():
-    """examples/run_experiment.py:89-93 prints (never asserts) three end-to-end noisy fidelities from
-    the real NetSquid run; executor + oracle reproduce them to < 1e-3 relative (residual: simulated
-    timeline of the link-layer handshake)."""
+    """examples/run_experiment.py:89-93 prints (never asserts) end-to-end noisy fidelities from real NetSquid
+    runs.  GHZ-5 is pinned digit for digit by trajectory enumeration (test_reference_printed_fidelities.py);
+    QFT-5 and Grover-5 have 44 / 288 mid-circuit measurements, so here (a) trajectories that follow their own
+    outcomes like the reference (host_branching, batch 1) must contain the printed value inside their
+    spread, and (b) the batched path -- one shared timeline, predicated corrections advancing it by their
+    expected duration -- must give a batch mean within 5e-5 of it (it was 2.4e-4 / 1.7e-4 low while every
+    predicated correction was charged its full 135 us)."""
     from dqc_simulator_b200 import executor, experiment
     from oracle.numpy_engine import OracleEngine
 
-    printed = {"ghz": 0.9570522876374276, "qft": 0.6470482939691747}
+    printed = {"ghz": 0.9570522876374276, "qft": 0.6470482939691747, "grover": 0.1071574284590638}
     mk = lambda f, n, b: OracleEngine(f, n, b, seed=0)
-    for circuit, want in printed.items():
+    for circuit, ntraj, nbatch in (("ghz", 8, 16), ("qft", 16, 32), ("grover", 4, 8)):
+        want = printed[circuit]
         ops, _ = experiment.load_c2(circuit)
         data, ideal = experiment.ideal_output_ket(ops, mk)
-        be = OracleEngine("dm", 7, 2, seed=5)
+        fs = []
+        for s in range(ntraj):
+            be = OracleEngine("dm", 7, 1, seed=100 + s)
+            ex = executor.DQCExecutor(ops, experiment.c2_hardware(noisy=True), be, host_branching=True).run()
+            fs.append(be.fidelity_ket(ex.axes_of(data), ideal, 0))
+        fs = np.array(fs)
+        assert abs(want - fs.mean()) < 4 * fs.std() + 1e-6 and abs(want - fs.mean()) < 1.5e-4, (circuit, fs.mean(), fs.std())
+        be = OracleEngine("dm", 7, nbatch, seed=5)
         ex = executor.DQCExecutor(ops, experiment.c2_hardware(noisy=True), be).run()
-        f = be.fidelity_ket(ex.axes_of(data), ideal, 0)
-        assert abs(f - want) / want < 1e-3, (circuit, f, want)
+        fb = np.mean([be.fidelity_ket(ex.axes_of(data), ideal, s) for s in range(nbatch)])
+        assert abs(fb - want) < 5e-5, (circuit, fb, want)
 
 
 def test_host_philox_matches_oracle_stream():
@@ -188,3 +200,49 @@ def test_fidelity_squared_ket_and_uhlmann():
     sig /= np.trace(sig)
     assert abs(fidelity_squared(rho, sig) - fidelity_squared(sig, rho)) < 1e-10      # symmetric
     assert 0 < fidelity_squared(rho, sig) < 1
+
+
+def _dm_plan_lines(capfd, monkeypatch, opts, tail_h=False):
+    """Plan-only handle (no GPU): queue memory noise -> H -> gate noise -> CNOT -> 2-qubit depolarising on a
+    qubit pair and return the planner's pass dump (DQE_DUMP_PLAN, written by the C library on fd 2)."""
+    monkeypatch.setenv("DQE_DUMP_PLAN", "1")
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    cnot = np.eye(4)[[0, 1, 3, 2]]
+    e = engine.Engine("dm", 4, 1, device=-1)
+    for k, v in opts.items():
+        e.set_option(k, v)
+    for a in (0, 1):
+        e.alloc_axis(a)
+    e.depolarize([0], 0.01); e.apply_1q(0, h); e.depolarize([0], 0.02)
+    e.apply_2q(0, 1, cnot); e.depolarize([0, 1], 0.03)
+    if tail_h:
+        e.apply_1q(1, h)
+    capfd.readouterr()
+    e.flush()
+    st = e.stats()
+    return [ln.strip() for ln in capfd.readouterr().err.splitlines() if ln.startswith("pass ")], st
+
+
+def test_planner_groups_factor_and_hoist_cx(capfd, monkeypatch):
+    """Host logic of the gate-queue flusher, pinned on the plan it emits: the peephole folds noise -> H ->
+    noise into one op (2 merges) but keeps its factors, so the op runs inside the qubit-pair group as
+    Pauli / U rho U^dagger / Pauli; the CNOT commutes behind the 2-qubit depolarising channel and rides in
+    the store addresses of the sweep ([>x]); one pass, one group."""
+    lines, st = _dm_plan_lines(capfd, monkeypatch, {})
+    assert lines == ["pass t=4 outer=0 nops=5: [>x] GROUP(2,3,0,1) gPAULI1.0 gMAT1X2.0 gPAULI1.0 gDEPOL2.0"]
+    assert st["passes"] == 1 and st["merged_ops"] == 2 and st["micro_ops"] == 5
+
+
+def test_planner_keeps_dense_blocks_out_of_groups(capfd, monkeypatch):
+    """factor = 0: the composed 4x4 superoperator stays a stand-alone sweep (never a group sub-op)."""
+    lines, _ = _dm_plan_lines(capfd, monkeypatch, {"factor": 0})
+    assert lines == ["pass t=4 outer=0 nops=3: MAT2(2,0) [>x] GROUP(3,2,1,0) gDEPOL2.0"]
+
+
+def test_planner_cx_in_the_middle_of_a_group(capfd, monkeypatch):
+    """cxperm = 0 keeps queue order (CX before DEPOL2, as a sub-op); with cxperm a CX followed by an op on
+    its control axis cannot move to the tail and stays a (thread-private round trip) sub-op."""
+    lines, _ = _dm_plan_lines(capfd, monkeypatch, {"cxperm": 0})
+    assert lines == ["pass t=4 outer=0 nops=6: GROUP(2,3,0,1) gPAULI1.0 gMAT1X2.0 gPAULI1.0 gMAT1X2.1 gDEPOL2.0"]
+    lines, _ = _dm_plan_lines(capfd, monkeypatch, {}, tail_h=True)
+    assert lines == ["pass t=4 outer=0 nops=7: GROUP(2,3,0,1) gPAULI1.0 gMAT1X2.0 gPAULI1.0 gDEPOL2.0 gMAT1X2.1 gMAT1X2.1"]
