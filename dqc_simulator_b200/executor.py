@@ -221,7 +221,13 @@ class QPU:
                     self.ex._release_axis(ax)
                 else:
                     self.last_access[pos] = end
-                program.output[key] = [self.ex._deliver(bit)]
+                if forced in (0, 1):
+                    # outcome fixed by the caller: known on the host for every shot of the batch, so the
+                    # control flow (and with it the simulated timeline) branches exactly like the reference
+                    self.ex.creg.release(bit)
+                    program.output[key] = [forced]
+                else:
+                    program.output[key] = [self.ex._deliver(bit)]
                 continue
             if tok is ins.INSTR_SWAP and self.ex.swap_as_three_cnots:
                 # NoisyQPU composite instruction (quantum_processors.py:901-909): its own program, run after

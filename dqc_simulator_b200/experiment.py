@@ -116,3 +116,64 @@ def fidelity_squared(rho, reference):
     sq = (vec * np.sqrt(np.clip(lam, 0, None))) @ vec.conj().T
     ev = np.linalg.eigvalsh(sq @ rho @ sq)
     return float(np.sum(np.sqrt(np.clip(ev, 0, None))) ** 2)
+
+
+class DataCollector:
+    """Result frame of a finished run, in the shape of the reference's
+    ``netsquid.util.datacollector.DataCollector`` as ``util/helper.py:112-163`` configures it
+    (``get_data_collector`` / ``get_data_collector4dm``): ``dc.dataframe`` is a pandas frame with NetSquid's
+    ``time_stamp`` (simulated ns at which ``DQCMasterProtocol`` signalled FINISHED) and ``entity_name``
+    columns plus ``fidelity`` -- one row per shot of the batch (the reference produces one row per process,
+    ``docs/source/getting_started.rst:683-770``), so ``dc.dataframe["fidelity"].iloc[0]`` reads the same."""
+
+    def __init__(self, executor, qubit_indices_2b_checked, desired_state):
+        self.executor = executor
+        self.qubits = []
+        for tup in qubit_indices_2b_checked:
+            first, node = tup[0], tup[-1]
+            if isinstance(first, (int, np.integer)):
+                idx = [int(first)]
+            elif isinstance(first, (list, tuple)):
+                idx = [int(i) for i in first]
+            else:   # same check and wording as util/helper.py:139-146
+                raise TypeError(f"{tup} not of correct form."
+                                "The first element of each tuple must be qubit"
+                                " index or list of qubit indices")
+            name = node if isinstance(node, str) else node.name
+            self.qubits += [(i, name) for i in idx]
+        self.desired_state = np.asarray(desired_state, dtype=complex)
+        self._frame = None
+
+    def collect(self):
+        """``qmemory.pop`` of the listed qubits (memory noise up to the end of the run), then
+        ``qapi.fidelity(qubits, desired_state, squared=True)`` per shot; the qubits are discarded."""
+        import pandas as pd
+
+        ex, be = self.executor, self.executor.backend
+        axes = ex.axes_of(self.qubits)
+        ref = self.desired_state
+        if ref.ndim == 1 or 1 in ref.shape:
+            ket = ref.reshape(-1)
+            if hasattr(be, "fidelity_ket_all"):   # the CUDA engine: one kernel for the whole batch
+                fid = np.asarray(be.fidelity_ket_all(axes, ket), dtype=float)
+            else:
+                fid = np.array([be.fidelity_ket(axes, ket, s) for s in range(be.batch)], dtype=float)
+        else:   # density-matrix reference: Uhlmann on the host, one small reduced matrix per shot
+            fid = np.array([fidelity_squared(be.reduced_dm(axes, s), ref) for s in range(be.batch)])
+        self._frame = pd.DataFrame({"time_stamp": float(ex.end_time), "entity_name": "DQCMasterProtocol",
+                                    "fidelity": fid})
+        return self._frame
+
+    @property
+    def dataframe(self):
+        return self._frame if self._frame is not None else self.collect()
+
+
+def get_data_collector(executor, qubit_indices_2b_checked, desired_state):
+    """Same call shape as ``util/helper.py:112`` with the executor in the place of the master protocol:
+    ``qubit_indices_2b_checked`` = [(index or [indices], node or node name), ...], ``desired_state`` a ket or
+    a density matrix.  Read ``.dataframe`` after ``executor.run()``."""
+    return DataCollector(executor, qubit_indices_2b_checked, desired_state)
+
+
+get_data_collector4dm = get_data_collector   # util/helper.py:166-223: same frame, density-matrix reference

@@ -167,3 +167,20 @@ def test_config2_with_pinned_low_comm_axes(name):
     assert np.abs(out["gpu_low"][1] - out["cpu_low"][1]).max() < TOL
     _cmp(out["gpu_low"][0], out["cpu_low"][0])
     _cmp(out["gpu_low"][0], out["gpu_default"][0])
+
+
+def test_data_collector_on_a_shot_batch():
+    """experiment.get_data_collector (util/helper.py:112-163) on the CUDA engine: one frame row per shot, every
+    row of a forced-outcome batch equal to the reference's printed getting_started fidelity."""
+    from dqc_simulator_b200 import executor, experiment, opstream
+
+    ops, _ = opstream.load(os.path.join(os.path.dirname(__file__), "golden", "ref_getting_started.json"))
+    dqc = hardware.DQCSpec.uniform(3, state4distribution=hardware.werner_state(0.9), num_positions=10,
+                                   num_comm_qubits=2, **rc.C2_NOISE)
+    be = gpu("dm", 7, 5)
+    # forced outcomes are known on the host: the executor branches like the reference (no predicated gates),
+    # so every shot of the batch follows the trajectory that produced the printed number
+    ex = executor.DQCExecutor(ops, dqc, be, forced_outcomes=[1, 0] + [0] * 8).run()
+    df = experiment.get_data_collector(ex, [(2, "node_0"), (2, "node_1")], rc.B00).dataframe
+    assert len(df) == 5 and list(df.columns) == ["time_stamp", "entity_name", "fidelity"]
+    assert np.abs(df["fidelity"].to_numpy() - 0.8921630426886507).max() < 1e-13

@@ -246,3 +246,29 @@ def test_planner_cx_in_the_middle_of_a_group(capfd, monkeypatch):
     assert lines == ["pass t=4 outer=0 nops=6: GROUP(2,3,0,1) gPAULI1.0 gMAT1X2.0 gPAULI1.0 gMAT1X2.1 gDEPOL2.0"]
     lines, _ = _dm_plan_lines(capfd, monkeypatch, {}, tail_h=True)
     assert lines == ["pass t=4 outer=0 nops=7: GROUP(2,3,0,1) gPAULI1.0 gMAT1X2.0 gPAULI1.0 gDEPOL2.0 gMAT1X2.1 gMAT1X2.1"]
+
+
+def test_data_collector_frame_matches_reference_shape():
+    """util/helper.py:112-163: dc.dataframe["fidelity"].iloc[0] -- the read-out of every reference example
+    (examples/getting_started.py:121-125).  Run with the trajectory that produced the printed number."""
+    import ref_cases as rc
+    from dqc_simulator_b200 import executor, experiment, hardware
+    from oracle.numpy_engine import OracleEngine
+
+    ops, _ = opstream.load(os.path.join(os.path.dirname(__file__), "golden", "ref_getting_started.json"))
+    dqc = hardware.DQCSpec.uniform(3, state4distribution=hardware.werner_state(0.9), num_positions=10,
+                                   num_comm_qubits=2, **rc.C2_NOISE)
+    bell = np.array([1, 0, 0, 1]) / np.sqrt(2)
+    frames = []
+    for ref in (bell.reshape(4, 1), np.outer(bell, bell)):   # ket column vector (as in the example) or dm
+        be = OracleEngine("dm", 7, 1, seed=1)
+        ex = executor.DQCExecutor(ops, dqc, be, forced_outcomes=[1, 0] + [0] * 8, host_branching=True).run()
+        dc = experiment.get_data_collector(ex, [(2, "node_0"), ([2], "node_1")], ref)
+        frames.append(dc.dataframe)
+    for df in frames:
+        assert list(df.columns) == ["time_stamp", "entity_name", "fidelity"] and len(df) == 1
+        assert df["time_stamp"].iloc[0] > 0 and df["entity_name"].iloc[0] == "DQCMasterProtocol"
+    assert abs(frames[0]["fidelity"].iloc[0] - 0.8921630426886507) < 2e-15
+    assert abs(frames[1]["fidelity"].iloc[0] - 0.8921630426886507) < 1e-7   # Uhlmann through sqrtm-free eigh
+    with pytest.raises(TypeError, match="not of correct form"):
+        experiment.get_data_collector(ex, [("2", "node_0")], bell)
