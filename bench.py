@@ -369,8 +369,9 @@ def main():
                      "frac": achieved / peak,
                      # dram__bytes_read+write of this kernel, ncu --set full (profiles/r01e_summary.md): 2.10-2.26 GB
                      # per launch against 2.147 GB algorithmic at 16384 shots -> ratio 1.03 applied here
-                     "traffic": 1.03 * 32.0 * amps / max(n_pass, 1),
-                     "traffic_source": "ncu capture at 16384 shots (profiles/r01e_summary.md), ratio dram/algorithmic = 1.03",
+                     "traffic": 0.994 * 32.0 * amps / max(n_pass, 1),
+                     "traffic_source": "ncu --set full capture at 16384 shots (profiles/r01q_summary.md: dram read + write "
+                                       "8.54 GB per launch of 262144 tiles x 16 KiB x 2 = 8.59 GB algorithmic), ratio 0.994",
                      "note": "fused passes (~17 ops each, measurements resolved on chip through cluster DSMEM) are bound "
                              "by the on-chip sweep work, not by HBM; see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
