@@ -88,7 +88,7 @@ struct dqe_engine {
   std::vector<double2> cpool;
   std::string err;
   int cuda_failed;
-  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, variant, cluster, cxperm, factor, tmap, prefetch;
+  int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, cluster, cxperm, factor, tmap, prefetch;
   int64_t tmap_used, tmap_refused;
   int64_t stats[8];
   bool timing;
@@ -1365,7 +1365,8 @@ int do_flush(dqe_t* h) {
       CK(cudaEventRecord(e0, h->stream));
     }
     // one kernel per formalism (their micro-op sets are disjoint enough that sharing one
-    // interpreter costs registers); variants = same code under different register budgets.
+    // interpreter costs registers), 128 registers per thread (a 161- and a 187-register build of the same
+    // code were measured slower: fewer resident CTAs).
     // Passes that carry a fused measurement launch as thread-block clusters: the 2^outer_bits tiles of
     // a shot form one cluster and exchange their probability partials through DSMEM.
     {
@@ -1373,13 +1374,8 @@ int do_flush(dqe_t* h) {
       int threads = h->threads;
       const bool pers = h->persistent != 0;
 #define DQE_KFN(M, B, F) (pers ? (const void*)k_tile_pass<M, B, F, true> : (const void*)k_tile_pass<M, B, F, false>)
-      if (h->formalism == DQE_KET) {
-        fn = h->variant == 1 ? DQE_KFN(128, 3, 0) : h->variant == 2 ? DQE_KFN(128, 2, 0) : DQE_KFN(256, 2, 0);
-      } else {
-        fn = h->variant == 1 ? DQE_KFN(128, 3, 1) : h->variant == 2 ? DQE_KFN(128, 2, 1) : DQE_KFN(256, 2, 1);
-      }
+      fn = h->formalism == DQE_KET ? DQE_KFN(256, 2, 0) : DQE_KFN(256, 2, 1);
 #undef DQE_KFN
-      if (h->variant) threads = std::min(threads, 128);
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)P.grid);
@@ -1472,7 +1468,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->variant = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1512,8 +1508,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
   {
 #define DQE_KV(M, B, F) (const void*)k_tile_pass<M, B, F, false>, (const void*)k_tile_pass<M, B, F, true>
-    const void* variants[12] = {DQE_KV(256, 2, 0), DQE_KV(128, 3, 0), DQE_KV(128, 2, 0),
-                                DQE_KV(256, 2, 1), DQE_KV(128, 3, 1), DQE_KV(128, 2, 1)};
+    const void* variants[4] = {DQE_KV(256, 2, 0), DQE_KV(256, 2, 1)};
 #undef DQE_KV
     for (const void* fn : variants) {
       if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess)
@@ -2045,9 +2040,6 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->cxperm = value ? 1 : 0;
   } else if (!strcmp(key, "cluster")) {
     h->cluster = value ? 1 : 0;
-  } else if (!strcmp(key, "variant")) {
-    if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "variant in [0, 2]");
-    h->variant = (int)value;
   } else if (!strcmp(key, "persistent")) {
     h->persistent = value ? 1 : 0;
   } else if (!strcmp(key, "ctas_per_sm")) {

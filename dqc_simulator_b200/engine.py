@@ -148,7 +148,7 @@ class Engine:
             self.set_option("tile_bits", tile_bits)
         if not fuse or os.environ.get("DQE_FUSE") == "0":
             self.set_option("fuse", 0)
-        for key in ("merge", "group", "tma", "min_run_bits", "threads", "ctas_per_sm", "persistent", "variant", "cluster"):  # A/B switches for profiling
+        for key in ("merge", "group", "tma", "min_run_bits", "threads", "ctas_per_sm", "persistent", "cluster"):  # A/B switches for profiling
             v = os.environ.get("DQE_" + key.upper())
             if v is not None:
                 self.set_option(key, int(v))
