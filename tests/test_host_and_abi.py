@@ -272,3 +272,27 @@ def test_data_collector_frame_matches_reference_shape():
     assert abs(frames[1]["fidelity"].iloc[0] - 0.8921630426886507) < 1e-7   # Uhlmann through sqrtm-free eigh
     with pytest.raises(TypeError, match="not of correct form"):
         experiment.get_data_collector(ex, [("2", "node_0")], bell)
+
+
+def test_program_instructions_overlap_on_free_positions():
+    """QPU.execute_program schedules like a NetSquid ``QuantumProgram(parallel=True)`` on physical instructions
+    with ``parallel=True`` (quantum_processors.py:344-456): in-order issue, an instruction starts when its
+    positions are free; INIT is exclusive.  Pinned on the simulated clock (ns)."""
+    from dqc_simulator_b200 import executor, hardware, instructions as ins
+    from oracle.numpy_engine import OracleEngine
+
+    def run(parallel):
+        dqc = hardware.DQCSpec.uniform(1, num_positions=6, num_comm_qubits=2)
+        ex = executor.DQCExecutor({"node_0": [[]]}, dqc, OracleEngine("ket", 6, 1), parallel_programs=parallel)
+        q = ex.qpus["node_0"]
+        prog = executor.QuantumProgram()
+        prog.apply(ins.INSTR_INIT, [2, 3, 4])          # 3 ns, exclusive
+        prog.apply(ins.INSTR_H, [2])                   # 135 us
+        prog.apply(ins.INSTR_H, [3])                   # overlaps with the first H
+        prog.apply(ins.INSTR_CNOT, [2, 3])             # 600 us, waits for both
+        prog.apply(ins.INSTR_X, [4])                   # free position, but issued after the CNOT has started
+        q.execute_program(prog)
+        return q.clock
+
+    assert run(False) == 3 + 135e3 + 135e3 + 600e3 + 135e3
+    assert run(True) == 3 + 135e3 + 600e3              # X [135e3, 270e3] runs under the CNOT [135e3, 735e3]
