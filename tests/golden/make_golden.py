@@ -19,6 +19,8 @@ Fixtures
 * ``c3_qft{N}_4qpu_cat``          config 3 shape (N = 8, 12 for oracle-sized parity, 26 full)
 * ``c4_qft{N}_mono``              config 4 shape: one QPU, all gates local (N = 6, 16)
 * ``c5_{ghz,qft}{N}_mono``        config 5 shape (N = 12 parity size, 30/34 full)
+* ``mqt/{name}_{mono,3qpu_cat}``  the 22 MQT-bench circuits of ``tests/MQT_benchmarking_circuits`` (the
+  reference's front-end test inputs), monolithic and partitioned over 3 QPUs
 * ``ref_*``                       gate-tuple circuits lifted from the reference's own tests
   (``tests/unit_tests/software/test_dqc_control.py:62-162, 249-306``,
   ``tests/unit_tests/qlib/test_circuit_identities.py``) compiled by the reference compiler.
@@ -33,7 +35,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools", "ref_frontend"))
 
+import numpy as np  # noqa: E402
+
 import netsquid_stub  # noqa: E402
+import qasm_textbook  # noqa: E402
 
 netsquid_stub.install()
 warnings.simplefilter("ignore")
@@ -147,6 +152,28 @@ def main():
         for n in (12, 30, 34):
             ops, meta = compile_mono(_qasm_path(gen(n)), n)
             save(f"c5_{kind}{n}_mono", ops, meta, gz=n > 12)
+    # ---- the reference's MQT-bench test circuits (tests/MQT_benchmarking_circuits, 22 x 5 qubits):
+    #      every gate family its front end lowers (u1/u2/u3, rz, sx, cp, ccx decompositions, swap, ...),
+    #      once on a single QPU and once first-come-first-served over 3 QPUs with cat-comm remote gates
+    mqt_dir = "/root/reference/tests/MQT_benchmarking_circuits"
+    os.makedirs(os.path.join(HERE, "mqt"), exist_ok=True)
+    for f in sorted(os.listdir(mqt_dir)):
+        if not f.endswith(".qasm"):
+            continue
+        stem = f[:-len("_indep_qiskit_5.qasm")]
+        # expected output state: an independent simulation of the QASM text (tools/ref_frontend/
+        # qasm_textbook.py) with the reference's two macro deviations replayed; plus how far plain qelib1.inc
+        # semantics are from it (1.0 unless the circuit uses cu1 / cp / crx)
+        text = open(os.path.join(mqt_dir, f)).read()
+        want = qasm_textbook.simulate(text, reference_macros=True)
+        plain = qasm_textbook.simulate(text, reference_macros=False)
+        extra = {"source": f"tests/MQT_benchmarking_circuits/{f}",
+                 "expected_ket": [[float(z.real), float(z.imag)] for z in want],
+                 "qelib1_fidelity": float(abs(np.vdot(plain, want)) ** 2)}
+        ops, meta = compile_mono(os.path.join(mqt_dir, f), 5)
+        save(f"mqt/{stem}_mono", ops, dict(meta, **extra), gz=True)
+        ops, meta = compile_fcfs(os.path.join(mqt_dir, f), 3, 10, 2)
+        save(f"mqt/{stem}_3qpu_cat", ops, dict(meta, **extra), gz=True)
     # ---- circuits from the reference's own tests ---------------------------------------------
     I = instr
     ref = {
