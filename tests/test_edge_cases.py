@@ -111,3 +111,23 @@ def test_register_capacity_and_argument_errors():
         e.depolarize([0, 1, 2], 0.1)
     with pytest.raises(EngineError):
         Engine("ket", 41, 1)
+
+
+def test_handle_limits_and_option_errors_without_a_gpu():
+    """C-ABI argument checks that need no device (plan-only handles): a density matrix is at most 16 qubits
+    (4^16 complex128 = 64 GiB, and the tile-base arithmetic of the diagonal enumeration is sized for it),
+    options reject out-of-range values and unknown keys with a message, never an exception across the ABI."""
+    from dqc_simulator_b200 import engine
+
+    with pytest.raises(engine.EngineError, match="dm <= 16"):
+        engine.Engine("dm", 17, 1, device=-1)
+    engine.Engine("dm", 16, 1, device=-1).close()
+    e = engine.Engine("dm", 4, 2, device=-1)
+    for key, bad in (("prefetch", -2), ("prefetch", 1 << 21), ("threads", 96)):
+        with pytest.raises(engine.EngineError):
+            e.set_option(key, bad)
+    with pytest.raises(engine.EngineError, match="unknown option"):
+        e.set_option("variant", 1)     # the register-budget variants are gone
+    for key, ok in (("prefetch", -1), ("prefetch", 0), ("tmap", 0), ("cxperm", 0), ("factor", 0), ("cluster", 0)):
+        e.set_option(key, ok)
+    e.close()
