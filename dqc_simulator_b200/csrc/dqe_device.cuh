@@ -870,25 +870,33 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
                                           const PassParams& pp, const double2* cs_base, uint64_t base,
                                           uint64_t cw, const MeasRec* mrec) {
   const int s4[4] = {g.b[4], g.b[5], g.b[6], g.b[7]};   // the four bit positions, ascending (host-sorted)
-  const uint32_t mra = 1u << g.b[0], mrb = 1u << g.b[1], mca = 1u << g.b[2], mcb = 1u << g.b[3];
+  // through a shuffle: the compiler then knows the masks (and every combination of them) are warp-uniform
+  const uint32_t mra = __shfl_sync(0xffffffffu, 1u << g.b[0], 0), mrb = __shfl_sync(0xffffffffu, 1u << g.b[1], 0);
+  const uint32_t mca = __shfl_sync(0xffffffffu, 1u << g.b[2], 0), mcb = __shfl_sync(0xffffffffu, 1u << g.b[3], 0);
+  const uint32_t bra = mra << 4, brb = mrb << 4, bca = mca << 4, bcb = mcb << 4;   // as byte offsets
   const int nsub = g.aux;
   // X / CX hoisted by the planner to the head (flags bits 0-3: on, role, in_r, in_c; controls octrl / octrl2)
   // or the tail (bits 4-7; controls in p[0], p[1]) of the group: applied by the load / store addresses
   const uint64_t* tail_ctrl = reinterpret_cast<const uint64_t*>(&g.p[0]);
   const bool has_pre = g.flags & 1, has_post = g.flags & 16;   // most groups carry neither: plain addresses
   GPerm pre, post;
-  if (has_pre) pre = make_perm(true, (g.flags >> 1) & 7, g.octrl, g.octrl2, base, mra, mrb, mca, mcb);
-  if (has_post) post = make_perm(true, (g.flags >> 5) & 7, tail_ctrl[0], tail_ctrl[1], base, mra, mrb, mca, mcb);
-#define DQE_GADDR(e) (i0 | (((e) & 8) ? mra : 0u) | (((e) & 4) ? mrb : 0u) | (((e) & 2) ? mca : 0u) | (((e) & 1) ? mcb : 0u))
+  if (has_pre) pre = make_perm(true, (g.flags >> 1) & 7, g.octrl, g.octrl2, base, bra, brb, bca, bcb);
+  if (has_post) post = make_perm(true, (g.flags >> 5) & 7, tail_ctrl[0], tail_ctrl[1], base, bra, brb, bca, bcb);
+  // element e of the thread's group sits at byte offset DQE_GOFF(e) from &tile[i0]: i0 has zeros at the four
+  // group bits, so the offsets are warp-uniform BYTE offsets (uniform datapath) and each access is one
+  // LDS / STS [R + UR] with no per-thread index arithmetic
+#define DQE_GOFF(e) ((((e) & 8) ? bra : 0u) | (((e) & 4) ? brb : 0u) | (((e) & 2) ? bca : 0u) | (((e) & 1) ? bcb : 0u))
+#define DQE_GEL(off) (*reinterpret_cast<double2*>(tpb + (off)))
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
+    char* __restrict__ tpb = reinterpret_cast<char*>(tile + i0);
     double2 v[16];
     if (has_pre) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e) ^ pre.r[(e >> 2) & 3] ^ pre.c[e & 3]];
+      for (int e = 0; e < 16; ++e) v[e] = DQE_GEL(DQE_GOFF(e) ^ pre.r[(e >> 2) & 3] ^ pre.c[e & 3]);
     } else {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e)];
+      for (int e = 0; e < 16; ++e) v[e] = DQE_GEL(DQE_GOFF(e));
     }
     int4 hdr = nsub > 0 ? op_header(sub) : make_int4(0, -1, 0, 0);
     for (int s = 0; s < nsub; ++s) {
@@ -909,11 +917,11 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
           if (op_flags & 16) {
             // X / CX in the middle of a group: a round trip through the thread's own 16 tile slots with
             // permuted store addresses (no barrier: nobody else touches them during the sweep)
-            const GPerm mid = make_perm(true, op_flags & 7, op.octrl, op.octrl2, base, mra, mrb, mca, mcb);
+            const GPerm mid = make_perm(true, op_flags & 7, op.octrl, op.octrl2, base, bra, brb, bca, bcb);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ mid.r[(e >> 2) & 3] ^ mid.c[e & 3]] = v[e];
+            for (int e = 0; e < 16; ++e) DQE_GEL(DQE_GOFF(e) ^ mid.r[(e >> 2) & 3] ^ mid.c[e & 3]) = v[e];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = tile[DQE_GADDR(e)];
+            for (int e = 0; e < 16; ++e) v[e] = DQE_GEL(DQE_GOFF(e));
             break;
           }
           const bool in_r = op_flags & 2, in_c = op_flags & 4;
@@ -943,13 +951,14 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
     }
     if (has_post) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e) ^ post.r[(e >> 2) & 3] ^ post.c[e & 3]] = v[e];
+      for (int e = 0; e < 16; ++e) DQE_GEL(DQE_GOFF(e) ^ post.r[(e >> 2) & 3] ^ post.c[e & 3]) = v[e];
     } else {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) tile[DQE_GADDR(e)] = v[e];
+      for (int e = 0; e < 16; ++e) DQE_GEL(DQE_GOFF(e)) = v[e];
     }
   }
-#undef DQE_GADDR
+#undef DQE_GOFF
+#undef DQE_GEL
 }
 
 // ------------------------------------------------------------------------------------------
