@@ -67,8 +67,9 @@ def decode(doc):
 def save(path, qpu_op_dict, meta=None):
     data = json.dumps(encode(qpu_op_dict, meta), separators=(",", ":"))
     if str(path).endswith(".gz"):
-        with gzip.open(path, "wt", compresslevel=9) as f:
-            f.write(data)
+        # mtime = 0 and no file name in the header: regenerating a fixture is byte-identical
+        with open(path, "wb") as raw, gzip.GzipFile(filename="", mode="wb", compresslevel=9, fileobj=raw, mtime=0) as f:
+            f.write(data.encode())
     else:
         with open(path, "w") as f:
             f.write(data)

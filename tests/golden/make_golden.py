@@ -19,7 +19,7 @@ Fixtures
 * ``c3_qft{N}_4qpu_cat``          config 3 shape (N = 8, 12 for oracle-sized parity, 26 full)
 * ``c4_qft{N}_mono``              config 4 shape: one QPU, all gates local (N = 6, 16)
 * ``c5_{ghz,qft}{N}_mono``        config 5 shape (N = 12 parity size, 30/34 full)
-* ``mqt/{name}_{mono,3qpu_cat}``  the 22 MQT-bench circuits of ``tests/MQT_benchmarking_circuits`` (the
+* ``mqt/{name}_{mono,3qpu_cat,3qpu_tp_safe}``  the 22 MQT-bench circuits of ``tests/MQT_benchmarking_circuits`` (the
   reference's front-end test inputs), monolithic and partitioned over 3 QPUs
 * ``ref_*``                       gate-tuple circuits lifted from the reference's own tests
   (``tests/unit_tests/software/test_dqc_control.py:62-162, 249-306``,
@@ -174,6 +174,10 @@ def main():
         save(f"mqt/{stem}_mono", ops, dict(meta, **extra), gz=True)
         ops, meta = compile_fcfs(os.path.join(mqt_dir, f), 3, 10, 2)
         save(f"mqt/{stem}_3qpu_cat", ops, dict(meta, **extra), gz=True)
+        # the same partition with teleportation-based remote gates (scheme 'tp_safe': teleport the control
+        # over, apply the gate locally, teleport it back -- compilers.py:255-278)
+        ops, meta = compile_fcfs(os.path.join(mqt_dir, f), 3, 10, 2, scheme="tp_safe")
+        save(f"mqt/{stem}_3qpu_tp_safe", ops, dict(meta, **extra), gz=True)
     # ---- circuits from the reference's own tests ---------------------------------------------
     I = instr
     ref = {

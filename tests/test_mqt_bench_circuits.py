@@ -7,7 +7,7 @@ Expected states come from an INDEPENDENT simulation of the QASM text (``tools/re
 qasm_textbook.py``, qelib1.inc gate definitions, no reference code) with the reference's two documented macro
 deviations replayed (cu1 / cp / crx); ``meta["qelib1_fidelity"]`` records how far plain
 OpenQASM semantics are from what the reference computes (exactly 1 for the 13 circuits without those gates).
-Covered: every gate family the front end lowers (u1/u2/u3, p, rx/ry/rz, h, x, z, t, tdg, cx, cz, cp, cu1, cu3,
+Covered (the tp_safe partition on the oracle only so far): every gate family the front end lowers (u1/u2/u3, p, rx/ry/rz, h, x, z, t, tdg, cx, cz, cp, cu1, cu3,
 crx, ch, rzz, swap, ccx, rccx), the single-QPU path, and the 3-QPU partition with cat-comm remote gates and up
 to 540 sampled mid-circuit measurements per circuit."""
 import glob
@@ -76,6 +76,20 @@ def test_oracle_partitioned_over_3_qpus_matches_independent_simulation(name):
     """cat-comm remote gates with sampled measurement outcomes and their classically controlled corrections:
     the reduced state of the data qubits is the monolithic output state for every outcome history."""
     ex, be, axes, want = _run(cpu, name, "3qpu_cat", "ket", 2, 7)
+    for shot in range(2):
+        rho = be.reduced_dm(axes, shot)
+        assert abs(np.real(want.conj() @ rho @ want) - 1) < 1e-10
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_partitioned_with_teleportation_matches_independent_simulation(name):
+    """Same partition, remote gates by scheme 'tp_safe' (teleport the control qubit over, gate locally,
+    teleport back; ``compilers.py:255-278``, ``dqc_control.py:405-613``): Bell-state measurements, both
+    corrections, the comm-qubit swap -- up to 1080 sampled measurements per circuit (qwalk)."""
+    ops, meta, want, qubits = _load(name, "3qpu_tp_safe")
+    be = cpu("ket", 9, 2, 3)
+    ex = executor.DQCExecutor(ops, hardware.DQCSpec.uniform(3, num_positions=10, num_comm_qubits=2), be).run()
+    axes = ex.axes_of(qubits)
     for shot in range(2):
         rho = be.reduced_dm(axes, shot)
         assert abs(np.real(want.conj() @ rho @ want) - 1) < 1e-10
