@@ -1,4 +1,4 @@
-"""Same-process A/B of one engine option on the config-2 shot batch: python tools/ab_option.py regs96 0 1
+"""Same-process A/B of one engine option on the config-2 shot batch: python tools/ab_option.py prefetch 0 -1
 [--shots N] [--reps R].  Prints device-side ms per step (per-pass CUDA events) for each value, interleaved."""
 import argparse
 import json
