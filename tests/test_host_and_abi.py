@@ -296,3 +296,26 @@ def test_program_instructions_overlap_on_free_positions():
 
     assert run(False) == 3 + 135e3 + 135e3 + 600e3 + 135e3
     assert run(True) == 3 + 135e3 + 600e3              # X [135e3, 270e3] runs under the CNOT [135e3, 735e3]
+
+
+@pytest.mark.parametrize("case,n,want", [
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=292, micro_ops=3193, api_ops=3089, merged_ops=797)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=35, micro_ops=486, api_ops=480, merged_ops=132)),
+    ("c4_qft16_mono.json.gz", 16, dict(passes=67, micro_ops=1196, api_ops=1564, merged_ops=521)),
+])
+def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
+    """Plan-only handles (no GPU): the pass / micro-op counts the measured numbers in profiles/ were taken
+    with (final executor of round 1, r01v-r01z).  A planner change that alters them should be a conscious one."""
+    from dqc_simulator_b200 import executor, experiment, hardware
+
+    ops, _ = opstream.load(os.path.join(os.path.dirname(__file__), "golden", case))
+    if n == 16:
+        dqc = hardware.DQCSpec.uniform(1, num_positions=16, num_comm_qubits=0, **experiment.C2_NOISE)
+    else:
+        dqc = experiment.c2_hardware(noisy=True)
+    e = engine.Engine("dm", n, 1000 if n == 7 else 1, device=-1)
+    executor.DQCExecutor(ops, dqc, e).run()
+    e.flush()
+    st = e.stats()
+    assert {k: st[k] for k in want} == want
+    assert st["finish_launches"] == 0      # every measurement of these circuits is fused into its pass
