@@ -44,9 +44,22 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-bits", type=int, default=None)
     ap.add_argument("--comm-low", type=int, default=0, help="reserve (and pin) the k lowest axes for comm qubits")
+    ap.add_argument("--shared-timeline", action="store_true",
+                    help="round-1 approximation for A/B: the batch shares one expected timeline (not reference-exact)")
+    ap.add_argument("--noise", default="depol", choices=["depol", "depol+dephase"],
+                    help="depol: examples/run_experiment.py:80-87; depol+dephase adds a memory dephasing channel of the "
+                         "same rate (BASELINE.json config 2 names it; not wired by any reference hardware spec)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="engine option for A/B measurements (dqe_set_option), e.g. --opt tmap=0")
     return ap.parse_args()
+
+
+def bench_hardware(a):
+    """examples/setup_hardware.py + run_experiment.py:80-87; --noise depol+dephase adds memory dephasing."""
+    from dqc_simulator_b200 import experiment
+
+    extra = dict(mem_dephase_rate=0.055) if a.noise == "depol+dephase" else {}
+    return experiment.c2_hardware(noisy=True, **extra)
 
 
 def workload_config(a, n_gpus):
@@ -56,7 +69,10 @@ def workload_config(a, n_gpus):
                     "(examples/run_experiment.py:80-87)",
         "formalism": "dm", "max_live_qubits": 7, "shots_per_gpu": a.shots, "shots_total": a.shots * n_gpus,
         "state_bytes_per_gpu": a.shots * (4 ** 7) * 16,
-        "noise": {"F_werner": 0.99, "p_cnot": 1e-3, "p_1q": 2e-5, "p_meas": 3e-3, "mem_rate_hz": 0.055},
+        "noise": {"F_werner": 0.99, "p_cnot": 1e-3, "p_1q": 2e-5, "p_meas": 3e-3, "mem_rate_hz": 0.055,
+                  "mem_dephase_rate_hz": 0.055 if a.noise == "depol+dephase" else 0.0},
+        "timeline": "shared expected timeline (round-1 approximation)" if a.shared_timeline else
+                    "per shot: every shot follows its own simulated timeline, like one reference trajectory",
         "sharding": f"shots x{n_gpus} (Philox keyed by global shot id; one all-reduce per step)",
         "l2_policy": "state (26 GB) >> L2 (126 MB): every pass streams from HBM, no flush needed",
     }
@@ -168,7 +184,7 @@ class ClockSampler:
 def oracle_shots(args_tuple):
     """CPU oracle port: `batch` noisy shots of the workload.  Only the cpu_baseline / reference legs
     call this (oracle/ is test infrastructure, never on the product path)."""
-    circuit, batch, seed, offset = args_tuple
+    circuit, batch, seed, offset, noise = args_tuple
     try:  # one BLAS / OpenMP thread per worker: parallelism comes from the process pool
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=1)
@@ -178,7 +194,7 @@ def oracle_shots(args_tuple):
     from oracle.numpy_engine import OracleEngine
 
     ops, _ = experiment.load_c2(circuit)
-    dqc = experiment.c2_hardware(noisy=True)
+    dqc = experiment.c2_hardware(noisy=True, **(dict(mem_dephase_rate=0.055) if noise == "depol+dephase" else {}))
     be = OracleEngine("dm", 7, batch, seed=seed, shot_offset=offset)
     t0 = time.perf_counter()
     ex = executor.DQCExecutor(ops, dqc, be).run()
@@ -188,8 +204,8 @@ def oracle_shots(args_tuple):
 
 
 def cpu_baseline(a):
-    oracle_shots((a.circuit, 2, 2024, 0))  # warm-up (imports, fixture parse)
-    dt, _ = oracle_shots((a.circuit, a.cpu_shots, 2024, 0))
+    oracle_shots((a.circuit, 2, 2024, 0, a.noise))  # warm-up (imports, fixture parse)
+    dt, _ = oracle_shots((a.circuit, a.cpu_shots, 2024, 0, a.noise))
     return {"value": a.cpu_shots / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{a.cpu_shots} shots of the same circuit+noise on the NumPy oracle (batched over shots), "
                       f"{dt:.1f} s on one host thread"}
@@ -209,7 +225,7 @@ def run_reference(a):
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         def step(i):
-            jobs = [(a.circuit, per, 2024, (i * cores + c) * per) for c in range(cores)]
+            jobs = [(a.circuit, per, 2024, (i * cores + c) * per, a.noise) for c in range(cores)]
             pool.map(oracle_shots, jobs)
         for i in range(a.warmup):
             step(i)
@@ -258,13 +274,14 @@ def main():
             torch.cuda.synchronize()
 
     ops, _meta = experiment.load_c2(a.circuit)
-    dqc = experiment.c2_hardware(noisy=True)
+    dqc = bench_hardware(a)
     stream = torch.cuda.Stream(device=local)
     with torch.cuda.stream(stream):
         mk = lambda f, n, b: Engine(f, n, b, device=local)
         data, ideal = experiment.ideal_output_ket(ops, mk)
         eng = Engine("dm", 7, a.shots, seed=2024, shot_offset=rank * a.shots, device=local,
                      stream=stream.cuda_stream, tile_bits=a.tile_bits)
+        eng.set_option("shot_stride", world)   # batch i of rank r = global shots [(i * world + r) * shots, ...)
         for kv in a.opt:
             k, v = kv.split("=")
             eng.set_option(k, int(v))
@@ -274,7 +291,8 @@ def main():
         def step():
             t0 = time.perf_counter()
             res = experiment.run_shot_batch(ops, dqc, eng, data, ideal, before_flush=lambda: ev0.record(stream),
-                                            after_launch=lambda: ev1.record(stream), comm_axes_low=a.comm_low)
+                                            after_launch=lambda: ev1.record(stream), comm_axes_low=a.comm_low,
+                                            per_shot_time=not a.shared_timeline)
             hist = experiment.outcome_histogram(res.creg)
             # the one collective of the path: fidelity sum + outcome histogram (no-op at N = 1)
             mean_f, _n, _h = experiment.all_reduce_results(res.fidelity, hist, device=f"cuda:{local}")

@@ -32,6 +32,10 @@ enum OpType : int32_t {
   OP_MAT1X2 = 11,     // dm controlled/one-qubit gate, row side + column side in one sweep
   OP_XPAT = 14,       // dm 1q channel with the sparse 'X pattern' (diagonal gate composed with Pauli noise):
                       // e00,e11 mix among themselves and e01,e10 among themselves -- 8 complex coefficients
+  OP_DYN1 = 15,       // dm 1q channel whose strength q is read per shot from classical register `aux`
+                      // (flags = DynKind): idle-time noise of a shot that follows its own simulated timeline
+  OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
+                      // c_off = 0: run in order by thread 0; c_off = 1: independent (QEXP), thread i runs instr i
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
                       // Philox draw -> outcome + renormalisation kept on chip; aux = axis bit, flags = creg bit + 1,
                       // lctrl = forced + 1, p[0] = flip probability, octrl = draw index
@@ -47,7 +51,41 @@ enum OpType : int32_t {
   G_TRACE = 108,
   G_INJECT = 109,
   G_XPAT = 111,
+  G_DYN1 = 115,       // flags bit0 = role, bits 1-2 = DynKind, aux = classical register holding q
 };
+
+// Per-shot classical register machine (include/dqc_engine.h: dqe_classical_op).  It carries the simulated
+// timelines of batched shots: a time that depends on a measurement outcome is a double in the shot's
+// register file, the executor's clock arithmetic becomes these instructions, and idle-time noise channels
+// read their strength from a register.  Opcodes mirror dqc_simulator_b200/timeline.py.
+enum ClOp : uint8_t {
+  CL_CONST = 1,   // d <- imm
+  CL_ADDI = 2,    // d <- a + imm
+  CL_ADD = 3,     // d <- a + b
+  CL_SUB = 4,     // d <- a - b
+  CL_RSUBI = 5,   // d <- imm - a
+  CL_MAX = 6,     // d <- max(a, b)
+  CL_MAXI = 7,    // d <- max(a, imm)
+  CL_SEL = 8,     // d <- creg bit `cbit` ? a : b
+  CL_CEILQ = 9,   // d <- max(0, ceil(a / imm - 1e-12))   (handshake re-sends, physical_layer.py:269-335)
+  CL_FMAI = 10,   // d <- a * imm + b
+  CL_QEXP = 11,   // d <- 1 - exp(-max(0, a) * imm)       (noise_models.py:248-253)
+  CL_BAND = 16,   // creg bit d <- bit a & bit b
+  CL_BANDN = 17,  // d <- a & ~b
+  CL_BOR = 18,
+  CL_BNOT = 19,
+  CL_BCOPY = 20,
+};
+enum DynKind : int32_t { DYN_DEPOL = 0, DYN_DEPHASE = 1, DYN_AMPDAMP = 2 };
+struct ClInstr {   // 8 bytes; ten ride in one MicroOp
+  uint8_t op, dst, a, b;
+  int8_t cbit;
+  uint8_t pad;
+  uint16_t imm;    // index (in doubles) into the pass constant pool
+};
+static_assert(sizeof(ClInstr) == 8, "ClInstr is packed into MicroOp payloads");
+constexpr int kTimeRegs = 128;        // doubles per shot
+constexpr int kClPerOp = 10;          // ClInstr per OP_CLASSICAL micro-op
 
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
@@ -88,9 +126,18 @@ struct MeasRec {
 
 struct PassParams {
   double2* state;
-  const uint64_t* creg;
+  const uint64_t* creg;     // per-shot classical word, read at CTA start
   double* partials;
   const MeasRec* rec;
+  // classical state is double-buffered: a pass that changes it (fused measurement, classical instructions)
+  // reads the `in` copy and the CTA holding a shot's tile 0 writes the `out` copy when it is done, so that
+  // CTAs of the same shot that start later still see the state from before the pass
+  uint64_t* creg_out;
+  MeasRec* rec_out;
+  const double* treg;       // kTimeRegs doubles per shot (null: the pass touches no register)
+  double* treg_out;         // non-null: registers are written back
+  int8_t* olog;             // outcome log [draw][batch] or null
+  int64_t batch;
   const MicroOp* ops;
   const double2* consts;
   uint64_t seed, shot_offset;
@@ -100,6 +147,7 @@ struct PassParams {
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
   int32_t nfree_cols, pad3;
+  int32_t uses_treg, writes_creg, writes_treg, pad4;   // planner: what the pass does to the classical state
   uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
   // dm diagonal enumeration (probabilities), host-precomputed.  Free variable k = k-th axis (ascending)
@@ -373,6 +421,63 @@ __device__ __forceinline__ void op_xpat(double2* tile, uint32_t T, const MicroOp
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// per-shot classical machine
+__device__ __forceinline__ const ClInstr* cl_payload(const MicroOp& op) {
+  return reinterpret_cast<const ClInstr*>(reinterpret_cast<const char*>(&op) + 16);
+}
+// one instruction on the register file `R` (shared or global) and the classical word `cw`
+__device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& cw, const double* imm) {
+  const double c = imm[in.imm];
+  switch (in.op) {
+    case CL_CONST: R[in.dst] = c; break;
+    case CL_ADDI: R[in.dst] = R[in.a] + c; break;
+    case CL_ADD: R[in.dst] = R[in.a] + R[in.b]; break;
+    case CL_SUB: R[in.dst] = R[in.a] - R[in.b]; break;
+    case CL_RSUBI: R[in.dst] = c - R[in.a]; break;
+    case CL_MAX: R[in.dst] = fmax(R[in.a], R[in.b]); break;
+    case CL_MAXI: R[in.dst] = fmax(R[in.a], c); break;
+    case CL_SEL: R[in.dst] = ((cw >> in.cbit) & 1ull) ? R[in.a] : R[in.b]; break;
+    case CL_CEILQ: R[in.dst] = fmax(0.0, ceil(R[in.a] / c - 1e-12)); break;
+    case CL_FMAI: R[in.dst] = __dadd_rn(__dmul_rn(R[in.a], c), R[in.b]); break;   // like the host: no contraction
+    case CL_QEXP: R[in.dst] = 1.0 - exp(-fmax(0.0, R[in.a]) * c); break;
+    case CL_BAND: case CL_BANDN: case CL_BOR: case CL_BNOT: case CL_BCOPY: {
+      const uint64_t x = (cw >> in.a) & 1ull, y = (cw >> in.b) & 1ull;
+      const uint64_t v = in.op == CL_BAND ? (x & y) : in.op == CL_BANDN ? (x & (y ^ 1ull)) : in.op == CL_BOR ? (x | y)
+                       : in.op == CL_BNOT ? (x ^ 1ull) : x;
+      cw = (cw & ~(1ull << in.dst)) | (v << in.dst);
+      break;
+    }
+    default: break;
+  }
+}
+
+// real coefficients of a dynamic one-qubit channel of strength q:
+// e00' = a e00 + b e11, e11' = c e00 + d e11, e01' = f e01, e10' = f e10
+struct DynCoef { double a, b, c, d, f; };
+__device__ __forceinline__ DynCoef dyn_coef(int kind, double q) {
+  DynCoef k;
+  if (kind == DYN_DEPOL) { k.a = k.d = 1.0 - 0.5 * q; k.b = k.c = 0.5 * q; k.f = 1.0 - q; }
+  else if (kind == DYN_DEPHASE) { k.a = k.d = 1.0; k.b = k.c = 0.0; k.f = 1.0 - q; }
+  else { k.a = 1.0; k.b = q; k.c = 0.0; k.d = 1.0 - q; k.f = sqrt(1.0 - q); }
+  return k;
+}
+
+__device__ __forceinline__ void op_dyn1(double2* tile, uint32_t T, const MicroOp& op, const double* treg) {
+  const int jr = op.b[0], jc = op.b[1];
+  const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
+  const DynCoef k = dyn_coef(op.flags, treg[op.aux]);
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
+    const uint32_t i00 = ins0(ins0(p, jlo), jhi);
+    const uint32_t i01 = i00 | (1u << jc), i10 = i00 | (1u << jr), i11 = i01 | (1u << jr);
+    const double2 e00 = tile[i00], e01 = tile[i01], e10 = tile[i10], e11 = tile[i11];
+    tile[i00] = make_double2(fma(k.a, e00.x, k.b * e11.x), fma(k.a, e00.y, k.b * e11.y));
+    tile[i11] = make_double2(fma(k.d, e11.x, k.c * e00.x), fma(k.d, e11.y, k.c * e00.y));
+    tile[i01] = make_double2(k.f * e01.x, k.f * e01.y);
+    tile[i10] = make_double2(k.f * e10.x, k.f * e10.y);
+  }
+}
+
 __device__ __forceinline__ void op_pauli1(double2* tile, uint32_t T, const MicroOp& op) {
   const int jr = op.b[0], jc = op.b[1];
   const int jlo = jr < jc ? jr : jc, jhi = jr < jc ? jc : jr;
@@ -576,15 +681,9 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
     r.outcome = m; r.pad = 0;
     r.scale = pm > 0.0 ? (FORM == 1 ? 1.0 / pm : 1.0 / sqrt(pm)) : 0.0;
     *mrec = r;
-    const int cbit = op.flags - 1;
-    if (cluster.block_rank() == 0) {
-      const_cast<MeasRec*>(pp.rec)[shot] = r;   // the collapse may land in the next pass
-      if (cbit >= 0) {
-        uint64_t* creg = const_cast<uint64_t*>(pp.creg);
-        const uint64_t bit = 1ull << cbit;
-        creg[shot] = (cw & ~bit) | ((uint64_t)m << cbit);
-      }
-    }
+    // the record and the classical word reach global memory when the CTA holding the shot's tile 0 is done
+    // (k_tile_pass epilogue, double-buffered copy): a collapse may land in the next pass
+    if (pp.olog && cluster.block_rank() == 0) pp.olog[op.octrl * (uint64_t)pp.batch + shot] = (int8_t)m;
   }
   __syncthreads();
   const int cbit = op.flags - 1;
@@ -682,12 +781,19 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
 // ket: Pauli string drawn per shot.  flags: 0 = 1q channel with cumulative thresholds p[0..2] on u,
 // 1 = k-qubit depolarising (w0 = p[0], w = p[1]) on u, 2 = X if u2 < p[0] (measurement flip).
 __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, const MicroOp& op,
-                                                 const PassParams& pp, uint64_t shot) {
+                                                 const PassParams& pp, uint64_t shot, const double* treg) {
   double u, u2;
   shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
   const int k = op.nb;
   int digits[2] = {0, 0};
-  if (op.flags == 0) {
+  if (op.flags == 3) {          // depolarising of per-shot strength q = register lctrl (Pauli weights q / 4)
+    const double w = 0.25 * treg[op.lctrl], w0 = 1.0 - 3.0 * w;
+    long long s = 0;
+    if (!(u < w0) && w > 0.0) { s = 1 + (long long)floor((u - w0) / w); if (s > 3) s = 3; }
+    digits[0] = (int)s;
+  } else if (op.flags == 4) {   // dephasing of per-shot strength q: Z with probability q / 2
+    digits[0] = (u >= 1.0 - 0.5 * treg[op.lctrl]) ? 3 : 0;
+  } else if (op.flags == 0) {
     digits[0] = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
   } else if (op.flags == 1) {
     const double w0 = op.p[0], w = op.p[1];
@@ -752,6 +858,22 @@ __device__ __forceinline__ void g_pauli1(double2 (&v)[16], const MicroOp& op) {
       e11.x = fma(a, e11.x, t0x); e11.y = fma(a, e11.y, t0y);
       e01.x = fma(c, e01.x, d * e10.x); e01.y = fma(c, e01.y, d * e10.y);
       e10.x = fma(c, e10.x, t1x); e10.y = fma(c, e10.y, t1y);
+    }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void g_dyn1(double2 (&v)[16], const DynCoef k) {
+#pragma unroll
+  for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+      double2& e00 = v[EI<ROLE>(0, 0, ro, co)]; double2& e01 = v[EI<ROLE>(0, 1, ro, co)];
+      double2& e10 = v[EI<ROLE>(1, 0, ro, co)]; double2& e11 = v[EI<ROLE>(1, 1, ro, co)];
+      const double t0x = k.c * e00.x, t0y = k.c * e00.y;
+      e00.x = fma(k.a, e00.x, k.b * e11.x); e00.y = fma(k.a, e00.y, k.b * e11.y);
+      e11.x = fma(k.d, e11.x, t0x); e11.y = fma(k.d, e11.y, t0y);
+      e01.x *= k.f; e01.y *= k.f;
+      e10.x *= k.f; e10.y *= k.f;
     }
 }
 
@@ -868,7 +990,7 @@ __device__ __forceinline__ void g_trace(double2 (&v)[16]) {
 
 __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
                                           const PassParams& pp, const double2* cs_base, uint64_t base,
-                                          uint64_t cw, const MeasRec* mrec) {
+                                          uint64_t cw, const MeasRec* mrec, const double* treg) {
   const int s4[4] = {g.b[4], g.b[5], g.b[6], g.b[7]};   // the four bit positions, ascending (host-sorted)
   // through a shuffle: the compiler then knows the masks (and every combination of them) are warp-uniform
   const uint32_t mra = __shfl_sync(0xffffffffu, 1u << g.b[0], 0), mrb = __shfl_sync(0xffffffffu, 1u << g.b[1], 0);
@@ -913,6 +1035,11 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
         case G_XPAT:
           if (role) g_xpat<1>(v, cs); else g_xpat<0>(v, cs);
           break;
+        case G_DYN1: {
+          const DynCoef k = dyn_coef((op_flags >> 1) & 3, treg[op.aux]);
+          if (role) g_dyn1<1>(v, k); else g_dyn1<0>(v, k);
+          break;
+        }
         case G_MAT1X2: {
           if (op_flags & 16) {
             // X / CX in the middle of a group: a round trip through the thread's own 16 tile slots with
@@ -1049,9 +1176,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ double2 s_consts[max_consts(FORM)];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
-  __shared__ DiagPrep s_diag[kMaxDiagRun];
+  __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
+  __shared__ double s_treg[kTimeRegs];     // the shot's classical registers (simulated times, channel strengths)
+  __shared__ unsigned long long s_cw;      // classical word after an OP_CLASSICAL run
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
@@ -1074,6 +1203,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     const uint64_t shot0 = blk >> pp.outer_bits;
     cw_first = pp.creg[shot0];
     if (threadIdx.x == 0) mr_first = pp.rec[shot0];   // outcome recorded by a preceding pass / k_finish_measure
+  }
+  if (pp.treg && blk < pp.ntiles) {
+    const double* tr = pp.treg + (blk >> pp.outer_bits) * (uint64_t)kTimeRegs;
+    for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) s_treg[i] = tr[i];
   }
   if (pp.has_measure) cluster_arrive_relaxed();   // waited for in the first op_measure
   if (tma && threadIdx.x == 0) {
@@ -1129,6 +1262,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     if (PERSIST && it > 0) {
       cw = pp.creg[shot];
       if (threadIdx.x == 0) mr0 = pp.rec[shot];
+      if (pp.treg) {
+        const double* tr = pp.treg + shot * (uint64_t)kTimeRegs;
+        for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) s_treg[i] = tr[i];
+      }
     }
 
     if (tma) {
@@ -1183,6 +1320,40 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       o = cur + 1 + (op_type == OP_GROUP ? hdr.w : 0);
       if (o < pp.nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
+      if (op_type == OP_CLASSICAL) {
+        // a run of consecutive classical micro-ops: serial ones on thread 0 in order, then the independent
+        // ones (QEXP: one exp each) spread over the threads
+        int run = 1;
+        while (cur + run < pp.nops && s_ops[cur + run].type == OP_CLASSICAL) ++run;
+        const double* imm = reinterpret_cast<const double*>(s_consts);
+        bool any_par = false;
+        if (threadIdx.x == 0) {
+          uint64_t w = cw;
+          for (int k = 0; k < run; ++k) {
+            const MicroOp& c = s_ops[cur + k];
+            if (c.c_off) continue;
+            const ClInstr* ci = cl_payload(c);
+            for (int i = 0; i < c.flags; ++i) cl_exec(ci[i], s_treg, w, imm);
+          }
+          s_cw = w;
+        }
+        for (int k = 0; k < run; ++k) any_par |= s_ops[cur + k].c_off != 0;
+        if (any_par) {
+          __syncthreads();
+          int slot = threadIdx.x;
+          for (int k = 0; k < run; ++k) {
+            const MicroOp& c = s_ops[cur + k];
+            if (!c.c_off) continue;
+            if (slot >= 0 && slot < c.flags) { uint64_t w = 0; cl_exec(cl_payload(c)[slot], s_treg, w, imm); }
+            slot -= c.flags;
+          }
+        }
+        __syncthreads();
+        cw = s_cw;
+        o = cur + run;
+        if (o < pp.nops) hdr = op_header(&s_ops[o]);
+        continue;
+      }
       if constexpr (FORM == 0) {   // ---- ket micro-ops
         switch (op_type) {
           case OP_MAT1:
@@ -1206,13 +1377,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
           case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
-          case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot); break;
+          case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot, s_treg); break;
           default: break;
         }
       } else {                     // ---- density-matrix micro-ops
         switch (op_type) {
           case OP_GROUP:
-            run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas);
+            run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas, s_treg);
             break;
           case OP_MAT1X2: {
             const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
@@ -1225,6 +1396,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_DIAG: op_diag(tile, T, op, cs, base); break;
           case OP_PAULI1: op_pauli1(tile, T, op); break;
           case OP_XPAT: op_xpat(tile, T, op, cs); break;
+          case OP_DYN1: op_dyn1(tile, T, op, s_treg); break;
           case OP_DEPOL2: op_depol2(tile, T, op); break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
@@ -1237,6 +1409,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       __syncthreads();
     }
 
+    // classical state of the shot -> the `out` copies, by the CTA that holds the shot's tile 0 (every CTA of
+    // the shot computed the same values)
+    if ((pp.creg_out || pp.treg_out) && (blk & outer_mask) == 0) {
+      if (pp.creg_out && threadIdx.x == 0) { pp.creg_out[shot] = cw; pp.rec_out[shot] = s_meas; }
+      if (pp.treg_out) {
+        double* tr = pp.treg_out + shot * (uint64_t)kTimeRegs;
+        for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) tr[i] = s_treg[i];
+      }
+    }
     if (pp.store_back) {
       if (tma) {
         // generic-proxy writes to the tile -> visible to the async proxy, then bulk stores
@@ -1328,6 +1509,7 @@ struct FinishParams {
   uint64_t tiles_per_shot;
   double flip;   // dm only (ket applies the flip as a sampled X before the probabilities)
   int32_t forced, creg_bit, is_dm, pad;
+  int8_t* olog;  // outcome log [draw][batch] or null
 };
 
 __global__ void __launch_bounds__(128) k_finish_measure(const FinishParams fp) {
@@ -1355,6 +1537,7 @@ __global__ void __launch_bounds__(128) k_finish_measure(const FinishParams fp) {
   r.pad = 0;
   r.scale = pm > 0.0 ? (fp.is_dm ? 1.0 / pm : 1.0 / sqrt(pm)) : 0.0;
   fp.rec[shot] = r;
+  if (fp.olog) fp.olog[fp.draw * (uint64_t)fp.batch + (uint64_t)shot] = (int8_t)m;
   if (fp.creg_bit >= 0) {
     const uint64_t bit = 1ull << fp.creg_bit;
     fp.creg[shot] = (fp.creg[shot] & ~bit) | ((uint64_t)m << fp.creg_bit);
@@ -1362,6 +1545,47 @@ __global__ void __launch_bounds__(128) k_finish_measure(const FinishParams fp) {
 }
 
 // ------------------------------------------------------------------------------------------
+// classical instructions with no quantum op around them (e.g. the clock arithmetic that ends a run):
+// one thread per shot, registers updated in place in global memory
+struct ClassicalParams {
+  const MicroOp* ops;
+  const double* imm;
+  uint64_t* creg;
+  double* treg;
+  int64_t batch;
+  int32_t nops, pad;
+};
+__global__ void __launch_bounds__(128) k_classical(const ClassicalParams cp) {
+  const int64_t shot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (shot >= cp.batch) return;
+  uint64_t cw = cp.creg[shot];
+  const uint64_t cw0 = cw;
+  double* R = cp.treg + (uint64_t)shot * kTimeRegs;
+  for (int k = 0; k < cp.nops; ++k) {
+    const MicroOp& c = cp.ops[k];
+    const ClInstr* ci = cl_payload(c);
+    for (int i = 0; i < c.flags; ++i) cl_exec(ci[i], R, cw, cp.imm);
+  }
+  if (cw != cw0) cp.creg[shot] = cw;
+}
+
+// dqe_reinit: zero the sub-block of every shot that the live axes span (everything else is zero by the
+// free-axis invariant), then |0..0>
+struct ResetParams {
+  double2* state;
+  int64_t batch;
+  int32_t P, live_bits, n_segs, pad;
+  Seg segs[24];
+};
+__global__ void __launch_bounds__(256) k_reset_live(const ResetParams rp) {
+  const uint64_t per = 1ull << rp.live_bits, total = (uint64_t)rp.batch << rp.live_bits;
+  const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t shot = i >> rp.live_bits, d = i & (per - 1ull);
+    rp.state[(shot << rp.P) + deposit(d, rp.segs, rp.n_segs)] = d == 0 ? one : zero;
+  }
+}
+
 __global__ void k_init_state(double2* state, int64_t batch, int P) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < batch) state[(uint64_t)s << P] = make_double2(1.0, 0.0);

@@ -38,7 +38,10 @@ constexpr int kMaxFactors = 4;
 struct HostOp {
   int nf;              // valid factorisation of this (axis-local dm) op: f[0] applied first; 0 = none
   Factor f[kMaxFactors];
-  int kind;            // 0 = micro-op, 1 = measurement finish (pass barrier)
+  int kind;            // 0 = micro-op, 1 = measurement finish (pass barrier), 2 = classical instruction (ci, imm),
+                       // 3 = classical fence (later classical instructions are not hoisted over it)
+  ClInstr ci;
+  double imm;
   MicroOp m;           // bit fields hold PHYSICAL positions until the planner localises them
   uint64_t pctrl, pctrl2;  // physical control masks
   uint64_t need;       // physical bits that must lie inside the tile
@@ -58,6 +61,7 @@ struct PlannedPass {
   size_t smem;
   uint64_t amps;       // amplitudes touched per shot
   bool is_finish;
+  bool classical_only;   // nothing but classical instructions: runs as k_classical (one thread per shot)
   FinishParams fp;
 };
 
@@ -71,10 +75,16 @@ struct dqe_engine {
   cudaStream_t stream;
   bool own_stream, own_state;
   double2* state;
-  uint64_t* creg;
+  // classical state, double-buffered (see PassParams): creg_buf[cpar] / rec_buf[cpar] / treg_buf[tpar] are current
+  uint64_t* creg_buf[2];
+  MeasRec* rec_buf[2];
+  double* treg_buf[2];      // allocated on the first classical instruction
+  int cpar, tpar;
+  int8_t* olog;             // outcome log [draw][batch]
+  int64_t olog_draws;
+  bool state_dirty;         // the free-axis invariant may not hold (dqe_set_state): next reinit clears everything
   double* partials;
   size_t partials_cap;
-  MeasRec* rec;
   MicroOp* d_ops;
   size_t d_ops_cap;
   double2* d_consts;
@@ -83,6 +93,7 @@ struct dqe_engine {
   uint64_t pin_axes;        // axes always enumerated by passes, live or not (keeps low bits contiguous)
   uint64_t planned_live;    // physical live mask at the head of the queue
   uint64_t seed, shot_offset, draw;
+  int64_t shot_stride;      // handles that share one global shot numbering (ranks): reinit advances by batch * stride
   int pred;
   std::vector<HostOp> queue;
   std::vector<double2> cpool;
@@ -115,6 +126,9 @@ int fail(dqe_t* h, int code, const std::string& msg) {
       return fail(h, DQE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
     }                                                                                   \
   } while (0)
+
+inline uint64_t* cur_creg(dqe_t* h) { return h->creg_buf[h->cpar]; }
+inline MeasRec* cur_rec(dqe_t* h) { return h->rec_buf[h->cpar]; }
 
 inline uint64_t phys_live(const dqe_t* h, uint64_t axes) {
   return h->formalism == DQE_KET ? axes : (axes | (axes << h->nmax));
@@ -372,6 +386,7 @@ bool try_merge(dqe_t* h, const HostOp& o, int axis) {
   int depth = 0;
   for (size_t k = h->queue.size(); k-- > 0 && depth < 96; ++depth) {
     HostOp& e = h->queue[k];
+    if (e.kind >= 2) continue;   // classical instructions touch no amplitude
     if (e.kind != 0 || e.m.type == OP_PROBS) return false;
     if (e.m.pred_bit == o.m.pred_bit && axis_local_matrix(h, e, axis, Mo)) {
       for (int i = 0; i < d; ++i)
@@ -511,6 +526,7 @@ bool try_merge_pair(dqe_t* h, const HostOp& o) {
   int depth = 0;
   for (size_t k = h->queue.size(); k-- > 0 && depth < 96; ++depth) {
     HostOp& e = h->queue[k];
+    if (e.kind >= 2) continue;
     if (e.kind != 0 || e.m.type == OP_PROBS) return false;
     if (!(touched_bits(e) & mine)) continue;
     if (e.m.pred_bit != o.m.pred_bit) return false;
@@ -546,6 +562,7 @@ void diag_merge_at(dqe_t* h, size_t k) {
   int depth = 0;
   for (size_t j = k; j-- > 0 && depth < 96; ++depth) {
     HostOp& e = h->queue[j];
+    if (e.kind >= 2) continue;
     if (e.kind != 0 || e.m.type == OP_PROBS) return;
     if (e.m.type == OP_DIAG && e.m.pred_bit == d.m.pred_bit) {
       uint8_t bits[8];
@@ -676,6 +693,8 @@ void q_sampled(dqe_t* h, int k, const int* axes, int mode, uint64_t draw, double
 }
 
 int lower_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, double e) {
+  if (h->olog_draws > 0 && (int64_t)h->draw >= h->olog_draws)
+    return fail(h, DQE_EINVAL, "outcome log is full: raise the outcome_log option");
   const uint64_t draw = h->draw++;
   if (h->formalism == DQE_KET && e > 0.0) q_sampled(h, 1, &axis, 2, draw, e, 0, 0);
   {
@@ -816,7 +835,7 @@ struct Planner {
     };
     const MicroOp& m = ho->m;
     switch (m.type) {
-      case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE: case OP_XPAT:
+      case OP_PAULI1: case OP_COLLAPSE: case OP_TRACE: case OP_XPAT: case OP_DYN1:
         return add(m.b[1]);
       case OP_MAT2:
         // a dense 4x4 block inside the register-resident group interpreter costs every other sub-op its
@@ -876,6 +895,9 @@ struct Planner {
         break;
       case OP_XPAT:
         m.type = G_XPAT; m.flags = role(s.b[1]); m.c_off = copy_consts(ho, pcb);
+        break;
+      case OP_DYN1:
+        m.type = G_DYN1; m.flags = role(s.b[1]) | (s.flags << 1); m.aux = s.aux;
         break;
       case OP_MAT1X2: {
         m.type = G_MAT1X2; m.flags = role(s.b[1]);
@@ -948,12 +970,83 @@ struct Planner {
 
   struct Item {
     bool group;
+    bool classical;     // classical instructions of one span, hoisted to the span's start
     std::vector<const HostOp*> ops;
     int ax[2], nax;
     uint64_t touched;
   };
 
-  bool close(std::vector<const HostOp*>& cur, uint64_t need, uint64_t live) {
+  // classical instructions of one span -> OP_CLASSICAL micro-ops: the serial ones in program order, then the
+  // independent QEXP evaluations (the interpreter spreads those over the CTA's threads).  Immediates go to
+  // the pass constant pool as packed doubles (equal values share a slot).
+  void emit_classical(const std::vector<const HostOp*>& ops, size_t pcb) {
+    std::vector<double> vals;
+    std::vector<int> idx(ops.size());
+    for (size_t i = 0; i < ops.size(); ++i) {
+      int f = -1;
+      for (size_t j = 0; j < vals.size() && f < 0; ++j)
+        if (memcmp(&vals[j], &ops[i]->imm, sizeof(double)) == 0) f = (int)j;
+      if (f < 0) { f = (int)vals.size(); vals.push_back(ops[i]->imm); }
+      idx[i] = f;
+    }
+    const int base = (int)(dev_consts.size() - pcb) * 2;
+    for (size_t j = 0; j < vals.size(); j += 2)
+      dev_consts.push_back(make_double2(vals[j], j + 1 < vals.size() ? vals[j + 1] : 0.0));
+    for (int par = 0; par < 2; ++par) {
+      MicroOp m;
+      int n = 0;
+      auto open_op = [&]() {
+        memset(&m, 0, sizeof(m));
+        m.type = OP_CLASSICAL; m.pred_bit = -1;
+        n = 0;
+      };
+      auto close_op = [&]() {
+        if (n == 0) return;
+        // the payload overlays the fields behind the 16-byte dispatch header: set `aux` LAST would clobber
+        // instruction 1, so the serial / parallel marker rides in c_off (header) instead
+        m.flags = n; m.c_off = par;
+        dev_ops.push_back(m);
+      };
+      open_op();
+      for (size_t i = 0; i < ops.size(); ++i) {
+        const HostOp* ho = ops[i];
+        if ((ho->ci.op == CL_QEXP) != (par == 1)) continue;
+        ClInstr ci = ho->ci;
+        ci.imm = (uint16_t)(base + idx[i]);
+        memcpy(reinterpret_cast<char*>(&m) + 16 + 8 * n, &ci, sizeof(ci));
+        if (++n == kClPerOp) { close_op(); open_op(); }
+      }
+      close_op();
+    }
+  }
+
+  // Close `cur` as one pass; when the emitted micro-program overflows the per-pass budget (the planner's
+  // running estimate is optimistic) the list is cut in two and each half becomes its own pass.
+  // live0 = live mask in front of the first op of `cur`.
+  bool close(std::vector<const HostOp*>& cur, uint64_t live0) {
+    if (cur.empty()) return true;
+    uint64_t need = 0, live = live0;
+    for (const HostOp* ho : cur) { need |= ho->need; live |= ho->live_after | ho->need; }
+    const size_t ops_mark = dev_ops.size(), consts_mark = dev_consts.size(), passes_mark = passes.size();
+    std::vector<const HostOp*> keep = cur;
+    overflow = false;
+    if (!close_one(cur, need, live)) {
+      if (!overflow || keep.size() < 2) return false;
+      dev_ops.resize(ops_mark); dev_consts.resize(consts_mark); passes.resize(passes_mark);
+      err.clear();
+      const size_t mid = keep.size() / 2;
+      std::vector<const HostOp*> a(keep.begin(), keep.begin() + mid), b(keep.begin() + mid, keep.end());
+      uint64_t live_mid = live0;
+      for (const HostOp* ho : a) if (ho->kind <= 1 || true) live_mid = ho->live_after;
+      if (!close(a, live0)) return false;
+      if (!close(b, live_mid)) return false;
+      cur.clear();
+    }
+    return true;
+  }
+  bool overflow = false;
+
+  bool close_one(std::vector<const HostOp*>& cur, uint64_t need, uint64_t live) {
     if (cur.empty()) return true;
     live |= phys_live(h, h->pin_axes);
     int t = 0;
@@ -1026,7 +1119,32 @@ struct Planner {
     //      dependency (an item sharing any bit with it) that still spans <= 2 axes
     std::vector<Item> items;
     const bool grouping = h->formalism == DQE_DM && h->group && t >= 4;
+    int cl_item = -1;        // classical item of the current span
+    int span_begin = 0;      // first item index of the current span (just behind the last measurement / fence)
     for (const HostOp* ho : cur) {
+      if (ho->kind == 3) {   // classical fence: later classical instructions stay behind everything queued so far
+        cl_item = -1;
+        span_begin = (int)items.size();
+        for (Item& it : items) it.touched = ~0ull;
+        continue;
+      }
+      if (ho->kind == 2) {
+        // Classical instructions read creg bits of EARLIER measurements and registers written by earlier
+        // classical instructions only, and the registers / bits they write are not read by anything queued
+        // before them in this span (dqe_classical_op contract): they run at the start of the span, so that
+        // the quantum ops around them still group freely.
+        if (cl_item < 0) {
+          Item it;
+          it.group = false; it.classical = true; it.nax = 0; it.ax[0] = it.ax[1] = -1; it.touched = 0;
+          items.insert(items.begin() + span_begin, it);
+          cl_item = span_begin;
+        }
+        items[cl_item].ops.push_back(ho);
+        pp.uses_treg = 1;
+        if (ho->ci.op >= CL_BAND) pp.writes_creg = 1; else pp.writes_treg = 1;
+        continue;
+      }
+      if (ho->m.type == OP_DYN1 || (ho->m.type == OP_PAULI_SAMPLED && ho->m.flags >= 3)) pp.uses_treg = 1;
       uint64_t tb = touched_bits(*ho);
       if (ho->m.type == OP_PROBS || ho->m.type == OP_MEASURE) tb = ~0ull;
       int ax[2], nax = 0;
@@ -1054,9 +1172,13 @@ struct Planner {
       }
       if (!placed) {
         Item it;
-        it.group = can; it.ops.push_back(ho); it.nax = nax; it.ax[0] = nax > 0 ? ax[0] : -1;
+        it.group = can; it.classical = false; it.ops.push_back(ho); it.nax = nax; it.ax[0] = nax > 0 ? ax[0] : -1;
         it.ax[1] = nax > 1 ? ax[1] : -1; it.touched = tb;
         items.push_back(it);
+      }
+      if (ho->m.type == OP_PROBS || ho->m.type == OP_MEASURE) {   // a measurement opens the next span
+        cl_item = -1;
+        span_begin = (int)items.size();
       }
     }
 
@@ -1064,6 +1186,10 @@ struct Planner {
     bool writes = false;
     const int n = h->nmax;
     for (Item& it : items) {
+      if (it.classical) {
+        emit_classical(it.ops, P.const_begin);
+        continue;
+      }
       bool as_group = it.group && (it.ops.size() >= 2 ||
                                    (h->cxperm && it.nax == 2 && hoistable_x(it.ops[0]) && x_ctrl_in_group(it.ops[0], tile)));
       int A = it.ax[0], B = it.nax > 1 ? it.ax[1] : -1;
@@ -1115,13 +1241,20 @@ struct Planner {
       } else {
         for (const HostOp* ho : it.ops) {
           if (ho->m.type != OP_PROBS && ho->m.type != OP_MEASURE) writes = true;
-          if (ho->m.type == OP_MEASURE) pp.has_measure = 1;
+          if (ho->m.type == OP_MEASURE) { pp.has_measure = 1; pp.writes_creg = 1; }
           dev_ops.push_back(localise(ho, tile, P.const_begin));
         }
       }
     }
     pp.nops = (int)(dev_ops.size() - P.op_begin);
     pp.nconsts = (int)(dev_consts.size() - P.const_begin);
+    if (pp.nops > kMaxOpsPerPass || pp.nconsts > max_consts(h->formalism)) {
+      err = "planner: pass exceeds the micro-op / constant budget";
+      overflow = true;
+      return false;
+    }
+    P.classical_only = true;
+    for (const HostOp* ho : cur) if (ho->kind != 2 && ho->kind != 3) P.classical_only = false;
     pp.store_back = writes ? 1 : 0;
     pp.ntiles = (uint64_t)h->batch << pp.outer_bits;
     if (h->persistent) {
@@ -1151,8 +1284,8 @@ struct Planner {
 
   bool plan() {
     std::vector<const HostOp*> cur;
-    uint64_t live_now = h->planned_live, need = 0, live = live_now;
-    int nconst = 0, nslots = 0;
+    uint64_t live_now = h->planned_live, need = 0, live = live_now, live0 = live_now;
+    int nconst = 0, nslots = 0, ncl = 0;
     for (const HostOp& op : h->queue) {
       if (op.kind == 1 && cluster_mode() && !cur.empty() && cur.back()->m.type == OP_PROBS) {
         // small registers: all tiles of a shot fit one thread-block cluster, so the measurement is a
@@ -1171,7 +1304,7 @@ struct Planner {
       }
       if (op.kind == 1) {
         // the PROBS op is the tail of `cur`
-        if (!close(cur, need, live)) return false;
+        if (!close(cur, live0)) return false;
         const PlannedPass& last = passes.back();
         PlannedPass F;
         memset(&F, 0, sizeof(F));
@@ -1182,34 +1315,55 @@ struct Planner {
         F.fp.flip = op.flip; F.fp.forced = op.forced; F.fp.creg_bit = op.creg_bit;
         F.fp.is_dm = h->formalism == DQE_DM;
         passes.push_back(F);
-        need = 0; live = live_now; nconst = 0; nslots = 0;
+        need = 0; live = live_now; live0 = live_now; nconst = 0; nslots = 0; ncl = 0;
         continue;
       }
       uint64_t need2 = need | op.need;
       uint64_t live2 = live | op.live_after | op.need;
       int t = 0;
       uint64_t tile = 0;
-      // every op may need a group header in the worst case, and runs as up to nf factors inside a group
-      const int op_slots = 1 + std::max(1, op.nf);
+      // Running estimate of the pass's micro-program (close() emits the real one and splits the pass if the
+      // estimate was too optimistic): an op runs as max(1, nf) sub-ops, roughly every third op opens a group
+      // (one header), classical instructions pack ten to a micro-op with up to two part-filled micro-ops
+      // (serial + independent) per span.
+      int op_slots = std::max(1, op.nf), op_consts = op.nconst;
+      if (op.kind >= 2) {
+        op_consts = 0;
+        op_slots = 0;
+        if (op.kind == 2) {
+          ++ncl;
+          if (ncl % 2 == 0) op_consts = 1;
+          if (ncl % 8 == 1) op_slots = 1;
+        }
+      } else {
+        if (op.m.type == OP_MEASURE || op.m.type == OP_PROBS) op_slots += 2;
+        if (op.m.type == OP_DIAG && h->formalism == DQE_DM) op_consts = std::max(op_consts, 8);
+        if (op.nf > 0) op_consts = std::max(op_consts, 4 * op.nf);
+        if (++nq3 % 3 == 0) op_slots += 1;
+      }
+      if (cur.empty()) { nslots = 3; ncl = 0; nconst = 0; }
       const bool fits = cur.empty() || (h->fuse && nslots + op_slots <= kMaxOpsPerPass &&
-                                        nconst + std::max(op.nconst, 8) <= max_consts(h->formalism) &&
+                                        nconst + op_consts <= max_consts(h->formalism) &&
                                         choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
-        if (!close(cur, need, live)) return false;
+        if (!close(cur, live0)) return false;
         need2 = op.need;
+        live0 = live_now;
         live2 = live_now | op.live_after | op.need;
-        nconst = 0; nslots = 0;
+        nconst = 0; nslots = 3; ncl = op.kind == 2 ? 1 : 0;
+        if (op.kind == 2) op_slots = 1;
       }
-      nconst += std::max(op.nconst, 8);   // an X-pattern / factor form may need up to 8 constants
+      nconst += op_consts;
       nslots += op_slots;
       cur.push_back(&op);
       need = need2; live = live2;
       live_now = op.live_after;
     }
-    if (!close(cur, need, live)) return false;
+    if (!close(cur, live0)) return false;
     h->planned_live = live_now;
     return true;
   }
+  int nq3 = 0;
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -1292,9 +1446,9 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL"};
     static const char* gnames[] = {"?", "gPAULI1", "-", "gMAT1X2", "gDEPOL2", "-", "-", "gCOLLAPSE",
-                                   "gTRACE", "gINJECT", "gDIAG", "gXPAT"};
+                                   "gTRACE", "gINJECT", "gDIAG", "gXPAT", "-", "-", "-", "gDYN1"};
     for (PlannedPass& P : pl.passes) {
       if (P.is_finish) { fprintf(stderr, "  finish\n"); continue; }
       fprintf(stderr, "pass t=%d outer=%d nops=%d:", P.pp.t, P.pp.outer_bits, P.pp.nops);
@@ -1303,6 +1457,7 @@ int do_flush(dqe_t* h) {
         if (m.type > 100) { fprintf(stderr, " %s%s.%d", gnames[m.type - 100], m.pred_bit >= 0 ? "?" : "", m.flags & 1); continue; }
         if (m.type == OP_GROUP && (m.flags & 17))
           fprintf(stderr, " [%s%s]", (m.flags & 1) ? "x>" : "", (m.flags & 16) ? ">x" : "");
+        if (m.type == OP_CLASSICAL) { fprintf(stderr, " CL%s%d", m.c_off ? "p" : "", m.flags); continue; }
         fprintf(stderr, " %s%s(", names[m.type], m.pred_bit >= 0 ? "?" : "");
         for (uint32_t b = 0; b < m.nb; ++b) fprintf(stderr, "%s%d", b ? "," : "", (int)m.b[b]);
         fprintf(stderr, ")");
@@ -1348,14 +1503,38 @@ int do_flush(dqe_t* h) {
 
   for (PlannedPass& P : pl.passes) {
     if (P.is_finish) {
-      P.fp.partials = h->partials; P.fp.rec = h->rec; P.fp.creg = h->creg;
+      P.fp.partials = h->partials; P.fp.rec = cur_rec(h); P.fp.creg = cur_creg(h);
+      P.fp.olog = (h->olog && (int64_t)P.fp.draw < h->olog_draws) ? h->olog : nullptr;
       const unsigned grid = (unsigned)((h->batch + 3) / 4);
       k_finish_measure<<<grid, 128, 0, h->stream>>>(P.fp);
       h->stats[2]++; h->stats[5]++;
       continue;
     }
+    if (P.pp.uses_treg && !h->treg_buf[0]) return fail(h, DQE_EINVAL, "classical registers used before any classical instruction");
+    if (P.classical_only) {
+      if (P.pp.nops == 0) continue;
+      ClassicalParams cp;
+      memset(&cp, 0, sizeof(cp));
+      cp.ops = h->d_ops + P.op_begin;
+      cp.imm = reinterpret_cast<const double*>(h->d_consts + P.const_begin);
+      cp.creg = cur_creg(h); cp.treg = h->treg_buf[h->tpar]; cp.batch = h->batch; cp.nops = P.pp.nops;
+      k_classical<<<(unsigned)((h->batch + 127) / 128), 128, 0, h->stream>>>(cp);
+      h->stats[2]++;
+      continue;
+    }
     if (P.pp.ntiles > (1ull << 40)) return fail(h, DQE_EUNSUPPORTED, "too many tiles");
-    P.pp.state = h->state; P.pp.creg = h->creg; P.pp.partials = h->partials; P.pp.rec = h->rec;
+    P.pp.state = h->state; P.pp.partials = h->partials;
+    P.pp.creg = cur_creg(h); P.pp.rec = cur_rec(h);
+    P.pp.batch = h->batch;
+    P.pp.olog = h->olog;   // draws beyond the log's capacity are rejected when they are queued
+    if (P.pp.writes_creg) {
+      h->cpar ^= 1;
+      P.pp.creg_out = cur_creg(h); P.pp.rec_out = cur_rec(h);
+    }
+    if (P.pp.uses_treg) {
+      P.pp.treg = h->treg_buf[h->tpar];
+      if (P.pp.writes_treg) { h->tpar ^= 1; P.pp.treg_out = h->treg_buf[h->tpar]; }
+    }
     P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     build_tensor_map(h, P.pp);
     if (P.pp.tm_rank) h->tmap_used++;
@@ -1464,10 +1643,13 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   if (batch < 1) return fail(nullptr, DQE_EINVAL, "batch must be >= 1");
   dqe_t* h = new dqe_engine();
   h->formalism = formalism; h->nmax = max_qubits; h->P = P; h->device = device; h->batch = batch;
-  h->own_stream = false; h->own_state = false; h->state = nullptr; h->creg = nullptr;
-  h->partials = nullptr; h->partials_cap = 0; h->rec = nullptr; h->d_ops = nullptr; h->d_ops_cap = 0;
+  h->own_stream = false; h->own_state = false; h->state = nullptr;
+  h->creg_buf[0] = h->creg_buf[1] = nullptr; h->rec_buf[0] = h->rec_buf[1] = nullptr;
+  h->treg_buf[0] = h->treg_buf[1] = nullptr; h->cpar = 0; h->tpar = 0; h->olog = nullptr; h->olog_draws = 0;
+  h->state_dirty = false;
+  h->partials = nullptr; h->partials_cap = 0; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
-  h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0;
+  h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
@@ -1504,8 +1686,10 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
     if (e != cudaSuccess) return bail("cudaMalloc(state)", e);
     h->own_state = true;
   }
-  if ((e = cudaMalloc(&h->creg, batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
-  if ((e = cudaMalloc(&h->rec, batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaMalloc(&h->creg_buf[i], batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
+    if ((e = cudaMalloc(&h->rec_buf[i], batch * sizeof(MeasRec))) != cudaSuccess) return bail("cudaMalloc(rec)", e);
+  }
   {
 #define DQE_KV(M, B, F) (const void*)k_tile_pass<M, B, F, false>, (const void*)k_tile_pass<M, B, F, true>
     const void* variants[4] = {DQE_KV(256, 2, 0), DQE_KV(256, 2, 1)};
@@ -1521,8 +1705,10 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
     }
   }
   if ((e = cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream)) != cudaSuccess) return bail("memset", e);
-  if ((e = cudaMemsetAsync(h->creg, 0, batch * sizeof(uint64_t), h->stream)) != cudaSuccess) return bail("memset", e);
-  if ((e = cudaMemsetAsync(h->rec, 0, batch * sizeof(MeasRec), h->stream)) != cudaSuccess) return bail("memset", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaMemsetAsync(h->creg_buf[i], 0, batch * sizeof(uint64_t), h->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMemsetAsync(h->rec_buf[i], 0, batch * sizeof(MeasRec), h->stream)) != cudaSuccess) return bail("memset", e);
+  }
   k_init_state<<<(unsigned)((batch + 255) / 256), 256, 0, h->stream>>>(h->state, batch, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("k_init_state", e);
   *out = h;
@@ -1536,8 +1722,12 @@ int dqe_destroy(dqe_t* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   if (h->own_state && h->state) cudaFree(h->state);
-  if (h->creg) cudaFree(h->creg);
-  if (h->rec) cudaFree(h->rec);
+  for (int i = 0; i < 2; ++i) {
+    if (h->creg_buf[i]) cudaFree(h->creg_buf[i]);
+    if (h->rec_buf[i]) cudaFree(h->rec_buf[i]);
+    if (h->treg_buf[i]) cudaFree(h->treg_buf[i]);
+  }
+  if (h->olog) cudaFree(h->olog);
   if (h->partials) cudaFree(h->partials);
   if (h->d_ops) cudaFree(h->d_ops);
   if (h->d_consts) cudaFree(h->d_consts);
@@ -1549,13 +1739,32 @@ int dqe_destroy(dqe_t* h) {
 int dqe_reinit(dqe_t* h) {
   if (int rc = check_ready(h)) return rc;
   h->queue.clear(); h->cpool.clear();
+  // support of the state on the device: live mask at the head of the (dropped) queue, plus whatever is live now
+  const uint64_t was_live = h->planned_live | phys_live(h, h->live_axes | h->pin_axes);
   h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1;
+  // the next batch draws from the next block of global shot ids: reinit alone must not replay the stream
+  h->shot_offset += (uint64_t)h->batch * (uint64_t)h->shot_stride;
   if (h->device < 0) return 0;
   CK(cudaSetDevice(h->device));
-  const size_t elems = (size_t)h->batch << h->P;
-  CK(cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream));
-  CK(cudaMemsetAsync(h->creg, 0, h->batch * sizeof(uint64_t), h->stream));
-  k_init_state<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(h->state, h->batch, h->P);
+  if (h->state_dirty) {
+    const size_t elems = (size_t)h->batch << h->P;
+    CK(cudaMemsetAsync(h->state, 0, elems * sizeof(double2), h->stream));
+    k_init_state<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(h->state, h->batch, h->P);
+    h->state_dirty = false;
+  } else {
+    // free axes are |0> by invariant: only the block the live axes span holds anything but zeros
+    ResetParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.state = h->state; rp.batch = h->batch; rp.P = h->P;
+    rp.live_bits = __builtin_popcountll(was_live);
+    rp.n_segs = build_segs(was_live, rp.segs, 24);
+    if (rp.n_segs < 0) return fail(h, DQE_EUNSUPPORTED, "reinit: too many bit segments");
+    const uint64_t total = (uint64_t)h->batch << rp.live_bits;
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->num_sms * 32);
+    k_reset_live<<<grid, 256, 0, h->stream>>>(rp);
+  }
+  CK(cudaMemsetAsync(cur_creg(h), 0, h->batch * sizeof(uint64_t), h->stream));
+  if (h->olog) CK(cudaMemsetAsync(h->olog, 0xff, (size_t)h->olog_draws * (size_t)h->batch, h->stream));
   h->stats[2]++;
   CK(cudaGetLastError());
   return 0;
@@ -1813,6 +2022,99 @@ int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, doubl
   return rc;
 }
 
+int dqe_n_time_regs(void) { return kTimeRegs; }
+
+static int ensure_tregs(dqe_t* h) {
+  if (h->device < 0 || h->treg_buf[0]) return 0;
+  CK(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)h->batch * kTimeRegs * sizeof(double);
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&h->treg_buf[i], bytes));
+    CK(cudaMemsetAsync(h->treg_buf[i], 0, bytes, h->stream));
+  }
+  return 0;
+}
+
+int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, double imm) {
+  if (int rc = check_ready(h)) return rc;
+  const bool bitop = opcode >= CL_BAND && opcode <= CL_BCOPY;
+  const bool regop = opcode >= CL_CONST && opcode <= CL_QEXP;
+  if (!bitop && !regop) return fail(h, DQE_EINVAL, "classical_op: unknown opcode");
+  const int lim = bitop ? 64 : kTimeRegs;
+  if (dst < 0 || dst >= lim || a < 0 || a >= lim || b < 0 || b >= lim)
+    return fail(h, DQE_EINVAL, bitop ? "classical_op: creg bit out of range" : "classical_op: register out of range");
+  if (opcode == CL_SEL && (cbit < 0 || cbit >= 64)) return fail(h, DQE_EINVAL, "classical_op: SEL needs a creg bit");
+  if (opcode == CL_CEILQ && !(imm > 0.0)) return fail(h, DQE_EINVAL, "classical_op: CEILQ needs a positive divisor");
+  if (int rc = ensure_tregs(h)) return rc;
+  HostOp o = blank(h, 0);
+  o.kind = 2;
+  o.m.pred_bit = -1;
+  o.ci.op = (uint8_t)opcode; o.ci.dst = (uint8_t)dst; o.ci.a = (uint8_t)a; o.ci.b = (uint8_t)b;
+  o.ci.cbit = (int8_t)(opcode == CL_SEL ? cbit : 0); o.ci.pad = 0; o.ci.imm = 0;
+  o.imm = imm;
+  h->queue.push_back(o);
+  h->stats[4]++;
+  return 0;
+}
+
+int dqe_classical_fence(dqe_t* h) {
+  if (int rc = check_ready(h)) return rc;
+  HostOp o = blank(h, 0);
+  o.kind = 3;
+  o.m.pred_bit = -1;
+  h->queue.push_back(o);
+  return 0;
+}
+
+int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = check_live(h, axis, "dyn_channel")) return rc;
+  if (reg < 0 || reg >= kTimeRegs) return fail(h, DQE_EINVAL, "dyn_channel: register out of range");
+  if (kind < DYN_DEPOL || kind > DYN_AMPDAMP) return fail(h, DQE_EINVAL, "dyn_channel: kind in {0 depol, 1 dephase, 2 ampdamp}");
+  if (int rc = ensure_tregs(h)) return rc;
+  h->stats[4]++;
+  if (h->formalism == DQE_DM) {
+    HostOp o = blank(h, OP_DYN1);
+    o.m.b[0] = (uint8_t)rowbit(h, axis); o.m.b[1] = (uint8_t)axis; o.m.nb = 2;
+    o.need = (1ull << rowbit(h, axis)) | (1ull << axis);
+    o.m.flags = kind; o.m.aux = reg;
+    push(h, o);
+    return 0;
+  }
+  if (kind == DYN_AMPDAMP) return fail(h, DQE_EUNSUPPORTED, "amplitude damping is dm-only");
+  HostOp o = blank(h, OP_PAULI_SAMPLED);
+  o.m.nb = 1; o.m.b[0] = (uint8_t)axis; o.need = 1ull << axis;
+  o.m.flags = kind == DYN_DEPOL ? 3 : 4;
+  o.m.aux = (int32_t)h->draw++;
+  o.m.lctrl = (uint32_t)reg;
+  push(h, o);
+  return 0;
+}
+
+int dqe_read_time_reg(dqe_t* h, int reg, double* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (h && h->device < 0) return fail(h, DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state");
+  if (reg < 0 || reg >= kTimeRegs || !out) return fail(h, DQE_EINVAL, "read_time_reg: bad argument");
+  if (!h->treg_buf[0]) return fail(h, DQE_EINVAL, "read_time_reg: no classical instruction has run");
+  CK(cudaMemcpy2DAsync(out, sizeof(double), h->treg_buf[h->tpar] + reg, kTimeRegs * sizeof(double), sizeof(double),
+                       (size_t)h->batch, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dqe_read_outcomes(dqe_t* h, int64_t first, int64_t count, int8_t* out) {
+  if (int rc = do_flush(h)) return rc;
+  if (h && h->device < 0) return fail(h, DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state");
+  if (!h->olog) return fail(h, DQE_EINVAL, "read_outcomes: enable the outcome_log option first");
+  if (first < 0 || count < 0 || first + count > h->olog_draws || !out) return fail(h, DQE_EINVAL, "read_outcomes: range");
+  CK(cudaMemcpyAsync(out, h->olog + (size_t)first * (size_t)h->batch, (size_t)count * (size_t)h->batch,
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t dqe_draw_count(dqe_t* h) { return h ? (int64_t)h->draw : -1; }
+
 int dqe_flush(dqe_t* h) { return do_flush(h); }
 
 #define NEED_DEVICE(h) do { if ((h) && (h)->device < 0) return fail((h), DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state"); } while (0)
@@ -1831,7 +2133,7 @@ int dqe_read_creg(dqe_t* h, int bit, int8_t* out) {
   if (bit < 0 || bit >= 64 || !out) return fail(h, DQE_EINVAL, "read_creg: bad argument");
   int8_t* d = nullptr;
   CK(cudaMalloc(&d, h->batch));
-  k_extract_bit<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(h->creg, bit, d, h->batch);
+  k_extract_bit<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(cur_creg(h), bit, d, h->batch);
   h->stats[2]++;
   CK(cudaMemcpyAsync(out, d, h->batch, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1843,7 +2145,7 @@ int dqe_read_creg_words(dqe_t* h, uint64_t* out) {
   if (int rc = do_flush(h)) return rc;
   NEED_DEVICE(h);
   if (!out) return fail(h, DQE_EINVAL, "read_creg_words: null");
-  CK(cudaMemcpyAsync(out, h->creg, h->batch * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out, cur_creg(h), h->batch * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1854,7 +2156,7 @@ int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out) {
   if (k < 1 || k > 20 || !cbits || !out) return fail(h, DQE_EINVAL, "histogram: 1 <= k <= 20");
   HistParams hp;
   memset(&hp, 0, sizeof(hp));
-  hp.creg = h->creg; hp.batch = h->batch; hp.k = k;
+  hp.creg = cur_creg(h); hp.batch = h->batch; hp.k = k;
   for (int i = 0; i < k; ++i) {
     if (cbits[i] < 0 || cbits[i] >= 64) return fail(h, DQE_EINVAL, "histogram: creg bit out of range");
     hp.bits[i] = cbits[i];
@@ -1927,6 +2229,7 @@ int dqe_set_state(dqe_t* h, int64_t shot, const double* in, uint64_t live_mask) 
   CK(cudaStreamSynchronize(h->stream));
   h->live_axes = live_mask;
   h->planned_live = phys_live(h, live_mask);
+  h->state_dirty = true;
   return 0;
 }
 
@@ -2029,6 +2332,19 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "shot_stride")) {
+    if (value < 1) return fail(h, DQE_EINVAL, "shot_stride >= 1");
+    h->shot_stride = value;
+  } else if (!strcmp(key, "outcome_log")) {
+    if (value < 0 || value > (1 << 20)) return fail(h, DQE_EINVAL, "outcome_log: number of draws in [0, 2^20]");
+    if (h->device < 0) { h->olog_draws = value; return 0; }
+    CK(cudaSetDevice(h->device));
+    if (h->olog) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->olog)); h->olog = nullptr; }
+    h->olog_draws = value;
+    if (value > 0) {
+      CK(cudaMalloc(&h->olog, (size_t)value * (size_t)h->batch));
+      CK(cudaMemsetAsync(h->olog, 0xff, (size_t)value * (size_t)h->batch, h->stream));
+    }
   } else if (!strcmp(key, "prefetch")) {
     if (value < -1 || value > (1 << 20)) return fail(h, DQE_EINVAL, "prefetch distance in [-1, 2^20] tiles");
     h->prefetch = (int)value;

@@ -52,6 +52,15 @@ ABI = {
                                              _c_dbl_p, _c_dbl_p]),
     "dqe_measure": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_double]),
+    "dqe_n_time_regs": (ctypes.c_int, []),
+    "dqe_classical_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_double]),
+    "dqe_classical_fence": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_enqueue_dyn_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dqe_read_time_reg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_read_outcomes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.POINTER(ctypes.c_int8)]),
+    "dqe_draw_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "dqe_flush": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_read_creg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int8)]),
@@ -142,6 +151,7 @@ class Engine:
             self._h = ctypes.c_void_p()
             raise EngineError(f"dqe_create failed ({rc}): {msg}")
         self._ck(self._lib.dqe_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(shot_offset)))
+        self.n_time_regs = int(self._lib.dqe_n_time_regs())
         if tile_bits is None and os.environ.get("DQE_TILE_BITS"):
             tile_bits = int(os.environ["DQE_TILE_BITS"])
         if tile_bits is not None:
@@ -241,6 +251,32 @@ class Engine:
         arr = np.asarray(ks, dtype=complex).reshape(-1, 2, 2)
         _k, p = _cbuf(arr)
         self._ck(self._lib.dqe_enqueue_kraus_1q(self._h, int(axis), arr.shape[0], p))
+
+    # ------------------------------------------------------------------ per-shot classical machine
+    def classical_op(self, opcode, dst, a=0, b=0, cbit=-1, imm=0.0):
+        """One instruction of the per-shot register machine (opcodes: ``timeline.CL_*``)."""
+        self._ck(self._lib.dqe_classical_op(self._h, int(opcode), int(dst), int(a), int(b), int(cbit), float(imm)))
+
+    def classical_fence(self):
+        self._ck(self._lib.dqe_classical_fence(self._h))
+
+    def dyn_channel(self, axis, kind, reg):
+        """One-qubit channel whose strength is read per shot from classical register ``reg``
+        (``timeline.DYN_DEPOL / DYN_DEPHASE / DYN_AMPDAMP``)."""
+        self._ck(self._lib.dqe_enqueue_dyn_channel(self._h, int(axis), int(kind), int(reg)))
+
+    def read_time_reg(self, reg):
+        out = np.empty(self.batch, dtype=np.float64)
+        self._ck(self._lib.dqe_read_time_reg(self._h, int(reg), out.ctypes.data_as(_c_dbl_p)))
+        return out
+
+    def read_outcomes(self):
+        """(number of measurements so far, batch) int8 -- needs ``set_option("outcome_log", n)``."""
+        n = int(self._lib.dqe_draw_count(self._h))
+        out = np.empty((n, self.batch), dtype=np.int8)
+        if n:
+            self._ck(self._lib.dqe_read_outcomes(self._h, 0, n, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int8))))
+        return out[(out >= 0).all(axis=1)]   # draws that were not measurements (sampled noise) hold -1
 
     # ------------------------------------------------------------------ injection
     def inject_2q(self, a, b, state, is_dm):

@@ -22,9 +22,14 @@ compilers emit -- ``qpu_op_dict = {node_name: [[op, ...] per time slice]}``
 
 Batched shots: measurement results never come back to the host.  A measurement writes a
 per-shot classical bit on the device (:class:`CBit`); the classically controlled X / Z
-corrections become per-shot *predicated* gates.  With ``host_branching=True`` (batch 1
-only) the executor instead reads each outcome and branches exactly like the reference
-(including the outcome-dependent simulated durations).
+corrections become per-shot *predicated* gates, and every shot follows ITS OWN simulated
+timeline like a reference trajectory does: once a time depends on an outcome it lives in a
+per-shot classical register of the backend (:mod:`.timeline`), a predicated instruction
+advances the clocks of exactly the shots that run it, ``_cat_disentangle_end`` executes the
+pending program in exactly the shots whose outcome was 1 (``execute_program(when=bit)``),
+and memory-noise channels take their probability from a register.  With
+``host_branching=True`` (batch 1 only) or forced outcomes the executor instead knows each
+outcome on the host and branches exactly like the reference; all times are then floats.
 
 Qubits are materialised lazily: ``INSTR_INIT`` only records the time at which the memory-noise
 clock of a position starts (the reference's tests pin "decoherence starts after
@@ -37,6 +42,7 @@ import math
 import numpy as np
 
 from . import instructions as ins
+from . import timeline as tlm
 from .hardware import DQCSpec
 
 
@@ -56,6 +62,20 @@ class CBit:
         return f"CBit({self.index})"
 
 
+class _Instr:
+    """One pending instruction of a :class:`QuantumProgram`.  ``done`` is the classical bit marking the
+    shots in which an earlier conditional execution (``execute_program(when=bit)``) already ran it."""
+
+    __slots__ = ("instruction", "positions", "operator", "key", "predicate", "done")
+
+    def __init__(self, instruction, positions, operator, key, predicate):
+        self.instruction, self.positions, self.operator = instruction, positions, operator
+        self.key, self.predicate, self.done = key, predicate, None
+
+    def __iter__(self):   # (instruction, positions, operator, key, predicate), the shape tests unpack
+        return iter((self.instruction, self.positions, self.operator, self.key, self.predicate))
+
+
 class QuantumProgram:
     """List of pending instructions; ``output[key]`` is filled by ``execute_program``."""
 
@@ -68,16 +88,22 @@ class QuantumProgram:
             qubit_indices = [int(qubit_indices)]
         else:
             qubit_indices = [int(q) for q in qubit_indices]
-        self.instructions.append((instruction, qubit_indices, operator, output_key, predicate))
+        self.instructions.append(_Instr(instruction, qubit_indices, operator, output_key, predicate))
 
     def __len__(self):
         return len(self.instructions)
 
 
 class _CregAllocator:
+    """Classical bits of the per-shot register word.  A released bit waits until the next measurement
+    before it is handed out again: the backend may run classical instructions earlier than the quantum
+    ops enqueued between them (see :mod:`.timeline`), so a bit must not be rewritten while an op enqueued
+    earlier in the same span is still predicated on it."""
+
     def __init__(self, nbits):
         self.nbits = nbits
         self.free = list(range(nbits))
+        self.limbo = []
         self.peak = 0
 
     def alloc(self):
@@ -88,8 +114,13 @@ class _CregAllocator:
         return b
 
     def release(self, b):
-        self.free.append(b)
-        self.free.sort()
+        if b not in self.limbo and b not in self.free:
+            self.limbo.append(b)
+
+    def fence(self):
+        if self.limbo:
+            self.free = sorted(self.free + self.limbo)
+            self.limbo = []
 
 
 class QPU:
@@ -134,11 +165,25 @@ class QPU:
 
     def _memory_noise(self, pos, now):
         """Idle-time channel on access: p = 1 - exp(-dt * 1e-9 * rate)
-        (``noise_models.py:248-253``; NetSquid ``DepolarNoiseModel`` time dependent)."""
-        dt = now - self.last_access[pos]
+        (``noise_models.py:248-253``; NetSquid ``DepolarNoiseModel`` time dependent).  With per-shot
+        times the exponent is evaluated per shot by the backend (``dyn_channel``)."""
+        last = self.last_access[pos]
+        if now is last:
+            return
+        be, ax, sp, T = self.ex.backend, self.axis[pos], self.spec, self.ex.T
+        rates = ((tlm.DYN_DEPOL, sp.mem_rate(pos)), (tlm.DYN_DEPHASE, sp.mem_dephase_rate),
+                 (tlm.DYN_AMPDAMP, sp.mem_amp_damp_rate))
+        if T.is_reg(now) or T.is_reg(last):
+            if not any(r > 0 for _, r in rates):
+                return
+            dt = T.sub(now, last)
+            for kind, rate in rates:
+                if rate > 0:
+                    be.dyn_channel(ax, kind, T.qexp(dt, 1e-9 * rate).index)
+            return
+        dt = now - last
         if dt <= 0:
             return
-        be, ax, sp = self.ex.backend, self.axis[pos], self.spec
         rate = sp.mem_rate(pos)
         if rate > 0:
             be.depolarize([ax], 1.0 - math.exp(-dt * 1e-9 * rate))
@@ -158,7 +203,7 @@ class QPU:
         return axes
 
     # ---- the boundary ----------------------------------------------------------
-    def execute_program(self, program):
+    def execute_program(self, program, when=None):
         """Run the program's instructions on this QPU's clock, scheduled the way NetSquid's
         ``QuantumProcessor`` runs a ``QuantumProgram(parallel=True)`` (its default, which is what
         ``dqc_control.py`` builds): instructions are *issued in order*, one whose physical instruction is
@@ -166,34 +211,54 @@ class QPU:
         as the positions it acts on are free, so gates of one program on different qubits overlap in
         simulated time; ``INSTR_INIT`` / ``INSTR_DISCARD`` are ``parallel=False`` and wait for, and hold, the
         whole processor.  ``execute_program`` returns when every instruction has finished.  The start time
-        of an instruction is what its memory-noise exponent is computed from."""
-        be = self.ex.backend
-        overlap = self.ex.parallel_programs
-        t_issue = self.clock      # in-order issue: no instruction starts before its predecessor has started
+        of an instruction is what its memory-noise exponent is computed from.
+
+        ``when`` (a :class:`CBit`, batched shots only): the reference reaches this call only in the
+        trajectories where that bit is 1 (``_cat_disentangle_end``, ``dqc_control.py:385-403``).  The
+        instructions run, and the clocks advance, in exactly those shots; the program keeps its
+        instructions, marked done-in-those-shots, and the next unconditional call runs them in the
+        remaining shots."""
+        ex = self.ex
+        be, T = ex.backend, ex.T
+        overlap = ex.parallel_programs
+        exact = ex.per_shot_time
+        t0 = self.clock
+        t_issue = t0              # in-order issue: no instruction starts before its predecessor has started
         busy = {}                 # pos -> time its running instruction finishes
+        temps = []                # derived classical bits of this call
 
         def start_of(positions, exclusive):
             if not overlap:
                 return self.clock
-            t = t_issue
-            for b in (busy.values() if exclusive else (busy.get(p_, t) for p_ in positions)):
-                t = max(t, b)
-            return t
+            if exclusive:
+                return T.max(t_issue, *busy.values())
+            return T.max(t_issue, *[busy[p_] for p_ in positions if p_ in busy])
 
-        def finish(positions, start, duration, exclusive):
+        def finish(positions, start, duration, exclusive, run=None):
             nonlocal t_issue
-            end = start + duration
+            end = T.add(start, duration)
             if overlap:
                 for p_ in positions:
-                    busy[p_] = end
-                t_issue = end if exclusive else start
+                    busy[p_] = T.sel(run, end, busy.get(p_, t0))
+                t_issue = T.sel(run, end if exclusive else start, t_issue)
             else:
-                self.clock = end
+                self.clock = T.sel(run, end, self.clock)
             return end
 
-        for instruction, positions, operator, key, predicate in program.instructions:
+        for it in program.instructions:
+            instruction, positions, operator, key, predicate = it
+            run = predicate
+            if exact:
+                if it.done is not None:
+                    run = ex._p_and(ex._p_not(it.done, temps), run, temps)
+                run = ex._p_and(when, run, temps)
             tok, mat = ins.resolve((instruction, operator) if operator is not None else instruction)
             ph = self.spec.phys(tok)
+            structural = tok.kind in ("init", "discard", "measure") or (tok is ins.INSTR_SWAP and ex.swap_as_three_cnots)
+            if structural and (run is not None):
+                raise NotImplementedError(
+                    f"{self.name}: {tok.name} inside a conditionally executed program is not supported with "
+                    "batched shots (it changes the register layout per shot); run with host_branching=True")
             if tok.kind == "init":
                 # fresh |0> replaces any occupant; noise clock starts when INIT completes
                 for pos in positions:
@@ -211,41 +276,50 @@ class QPU:
                 (pos,) = positions
                 start = start_of(positions, False)
                 (ax,) = self.touch(positions, start)
-                bit = self.ex.creg.alloc()
-                forced = self.ex._next_forced()
+                bit = ex.creg.alloc()
+                forced = ex._next_forced()
                 be.measure(ax, bit, forced, ph.discard, ph.prob)
+                # classical instructions enqueued from here on may be hoisted up to this measurement
+                T.fence()
+                ex.creg.fence()
                 end = finish(positions, start, ph.duration, False)
                 if ph.discard:
                     self.axis.pop(pos)
                     self.last_access.pop(pos, None)
-                    self.ex._release_axis(ax)
+                    ex._release_axis(ax)
                 else:
                     self.last_access[pos] = end
                 if forced in (0, 1):
                     # outcome fixed by the caller: known on the host for every shot of the batch, so the
                     # control flow (and with it the simulated timeline) branches exactly like the reference
-                    self.ex.creg.release(bit)
+                    ex.creg.release(bit)
                     program.output[key] = [forced]
                 else:
-                    program.output[key] = [self.ex._deliver(bit)]
+                    program.output[key] = [ex._deliver(bit)]
                 continue
-            if tok is ins.INSTR_SWAP and self.ex.swap_as_three_cnots:
+            if tok is ins.INSTR_SWAP and ex.swap_as_three_cnots:
                 # NoisyQPU composite instruction (quantum_processors.py:901-909): its own program, run after
                 # everything issued so far has finished
                 a, b = positions
                 sub = QuantumProgram()
-                sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
-                sub.apply(ins.INSTR_CNOT, [b, a], predicate=predicate)
-                sub.apply(ins.INSTR_CNOT, [a, b], predicate=predicate)
+                sub.apply(ins.INSTR_CNOT, [a, b])
+                sub.apply(ins.INSTR_CNOT, [b, a])
+                sub.apply(ins.INSTR_CNOT, [a, b])
                 if overlap:
-                    self.clock = max([t_issue] + list(busy.values()))
+                    self.clock = T.max(t_issue, *busy.values())
                 self.execute_program(sub)
                 t_issue = self.clock
                 continue
             start = start_of(positions, False)
-            axes = self.touch(positions, start)
-            pred = -1 if predicate is None else predicate.index
+            pred = -1 if run is None else run.index
             if pred >= 0:
+                be.set_predicate(pred)
+            if exact or pred < 0:
+                axes = self.touch(positions, start)
+            else:
+                # legacy shared timeline: the idle-time channel is applied to every shot
+                be.set_predicate(-1)
+                axes = self.touch(positions, start)
                 be.set_predicate(pred)
             if len(axes) == 1:
                 be.apply_1q(axes[0], mat)
@@ -257,20 +331,36 @@ class QPU:
                 be.depolarize(axes, ph.prob)
             if pred >= 0:
                 be.set_predicate(-1)
-            # a predicated gate (batched shots) runs in the shots whose classical bit is 1 and takes no time
-            # in the others: the shared timeline advances by its expected duration (see DQCExecutor)
-            dur = ph.duration * (self.ex.predicated_time_weight if pred >= 0 else 1.0)
-            end = finish(positions, start, dur, False)
-            for pos in positions:
-                self.last_access[pos] = end
+            if exact:
+                # a predicated gate exists, takes time and touches its qubits only in the shots that run it
+                end = finish(positions, start, ph.duration, False, run)
+                for pos in positions:
+                    self.last_access[pos] = T.sel(run, end, self.last_access[pos])
+            else:
+                # legacy: one shared timeline that advances by the expected duration (see DQCExecutor)
+                dur = ph.duration * (ex.predicated_time_weight if pred >= 0 else 1.0)
+                end = finish(positions, start, dur, False)
+                for pos in positions:
+                    self.last_access[pos] = end
             program.output[key] = []
         if overlap:
-            self.clock = max([t_issue] + list(busy.values()))
-        # a classical bit is dead once its predicated gate has been enqueued (stream order)
-        for b in {pr.index for *_, pr in program.instructions if pr is not None}:
-            self.ex.creg.release(b)
-        self.ex.programs_executed += 1
-        self.ex._events += 1
+            self.clock = T.max(t_issue, *busy.values())
+        if when is not None and exact:
+            for it in program.instructions:
+                if it.done is None:
+                    it.done = when
+                elif it.done is not when:
+                    it.done = ex._p_or(it.done, when)
+        else:
+            # a classical bit is dead once its predicated gates have been enqueued (stream order)
+            for it in program.instructions:
+                for b in (it.predicate, it.done):
+                    if b is not None:
+                        ex.creg.release(b.index)
+        for b in temps:
+            ex.creg.release(b.index)
+        ex.programs_executed += 1
+        ex._events += 1
 
 
 class _Blocked(Exception):
@@ -291,7 +381,7 @@ class DQCExecutor:
 
     def __init__(self, qpu_op_dict, dqc, backend, forced_outcomes=None, host_branching=False,
                  swap_as_three_cnots=True, creg_bits=64, axis_pool=None, comm_axes_low=0,
-                 parallel_programs=True, predicated_time_weight=0.5):
+                 parallel_programs=True, per_shot_time=True, predicated_time_weight=0.5):
         self.ops = qpu_op_dict
         self.dqc = dqc if isinstance(dqc, DQCSpec) else DQCSpec(list(dqc))
         self.backend = backend
@@ -300,14 +390,15 @@ class DQCExecutor:
         # True: instructions of one QuantumProgram on free positions overlap in simulated time (NetSquid's
         # parallel=True programs, see QPU.execute_program); False: strictly one after the other
         self.parallel_programs = parallel_programs
-        # Batched shots share ONE simulated timeline, but in the reference a classically controlled X / Z
-        # correction exists (135 us + its gate noise) only in the trajectories whose outcome was 1, and
-        # every later memory-noise exponent inherits that.  The gate and its noise are predicated per shot
-        # on the device (exact); the shared clock advances by weight x duration: 0.5 = the expected timeline
-        # (cat / teleportation outcomes are 50:50), which makes batch means unbiased to first order
-        # (QFT-5: 0.64704 vs 0.64681 with weight 1; per-trajectory reference runs: 0.64704 +- 1e-5).
-        # host_branching=True (batch 1) follows the actual outcomes exactly, like the reference.
+        # per_shot_time=True (default): every shot of a batch follows its own simulated timeline, exactly
+        # like one reference trajectory (see the module docstring and timeline.py).
+        # per_shot_time=False is the round-1 approximation kept for A/B measurements: the batch shares ONE
+        # timeline that advances by weight x duration for a predicated correction (0.5 = the expected
+        # timeline, cat / teleportation outcomes being 50:50) -- batch means are right to ~5e-6 but single
+        # shots are off by ~1e-4 in fidelity.
+        self.per_shot_time = bool(per_shot_time)
         self.predicated_time_weight = float(predicated_time_weight)
+        self.T = tlm.Timeline(backend, None if self.per_shot_time else 0)
         self.creg = _CregAllocator(creg_bits)
         self._forced = list(forced_outcomes) if forced_outcomes is not None else None
         self._forced_i = 0
@@ -374,9 +465,32 @@ class DQCExecutor:
             return v
         return CBit(bit)
 
+    # ---- derived classical bits (per-shot predicates) ------------------------------
+    def _p_not(self, a, temps):
+        b = CBit(self.creg.alloc())
+        self.T.bit_op(tlm.CL_BNOT, b.index, a.index)
+        temps.append(b)
+        return b
+
+    def _p_and(self, a, b, temps):
+        """None = every shot."""
+        if a is None or a is b:
+            return b
+        if b is None:
+            return a
+        c = CBit(self.creg.alloc())
+        self.T.bit_op(tlm.CL_BAND, c.index, a.index, b.index)
+        temps.append(c)
+        return c
+
+    def _p_or(self, a, b):
+        c = CBit(self.creg.alloc())
+        self.T.bit_op(tlm.CL_BOR, c.index, a.index, b.index)
+        return c
+
     # ---- classical network ------------------------------------------------------
     def _send(self, src, dst, payload):
-        t = self.qpus[src].clock + self.dqc.classical_delay
+        t = self.T.add(self.qpus[src].clock, self.dqc.classical_delay)
         self.mailbox.setdefault((src, dst), []).append((t, payload))
         self._events += 1
 
@@ -388,7 +502,7 @@ class DQCExecutor:
         t, payload = box.pop(0)
         self._events += 1
         q = self.qpus[dst]
-        q.clock = max(q.clock, t)
+        q.clock = self.T.max(q.clock, t)
         return payload
 
     def _request_entanglement(self, node, role, other, pos):
@@ -403,7 +517,7 @@ class DQCExecutor:
         if other in link["req"]:
             first, second = sorted((node, other))   # qout0 -> side A, qout1 -> side B
             (pa, ta, ra), (pb, tb, rb) = link["req"][first], link["req"][second]
-            t_arrive = self._handshake_done(ta, ra, tb, rb) + self.dqc.ent_delay
+            t_arrive = self.T.add(self._handshake_done(ta, ra, tb, rb), self.dqc.ent_delay)
             qa, qb = self.qpus[first], self.qpus[second]
             qa._drop(pa)
             qb._drop(pb)
@@ -419,7 +533,7 @@ class DQCExecutor:
             yield "ebit"
         t_arrive = link["done"].pop(node)
         self._events += 1
-        self.qpus[node].clock = max(self.qpus[node].clock, t_arrive)
+        self.qpus[node].clock = self.T.max(self.qpus[node].clock, t_arrive)
 
     def _handshake_done(self, ta, ra, tb, rb):
         """Time at which the client fires the source trigger (``physical_layer.py:269-335``): the
@@ -433,11 +547,8 @@ class DQCExecutor:
         elif rb == "client" and ra != "client":
             tc, ts = tb, ta
         else:                       # symmetric request (not produced by the reference's compilers)
-            return max(ta, tb) + 2 * d
-        k = max(0, math.ceil((ts - tc - d) / w - 1e-12)) if w > 0 else 0
-        if w <= 0:
-            return max(tc + d, ts) + d
-        return tc + k * w + 2 * d
+            return self.T.add(self.T.max(ta, tb), 2 * d)
+        return self.T.handshake(tc, ts, d, w)
 
     # ---- interpreter ------------------------------------------------------------
     def _flush(self, q, program):
@@ -528,7 +639,12 @@ class DQCExecutor:
             return comm, QuantumProgram()
         if role == "disentangle_end":                           # :382-403
             mb = yield from self._recv(other, name)
-            if isinstance(mb, CBit) or mb == 1:
+            if isinstance(mb, CBit) and self.per_shot_time:
+                # the reference executes the pending program (local gates + this Z) only in the trajectories
+                # with mb = 1; in the others the local gates stay pending until the next execute_program
+                self._apply_if(program, ins.INSTR_Z, data, mb)
+                q.execute_program(program, when=mb)
+            elif isinstance(mb, CBit) or mb == 1:
                 self._apply_if(program, ins.INSTR_Z, data, mb)
                 q.execute_program(program)
                 program = QuantumProgram()
@@ -592,7 +708,7 @@ class DQCExecutor:
         QPUs start a slice together and the next slice starts when every QPU has finished."""
         n_slices = max(len(v) for v in self.ops.values())
         for s in range(n_slices):
-            start = max(q.clock for q in self.qpus.values())
+            start = self.T.max(*[q.clock for q in self.qpus.values()])
             procs = {}
             for name, slices in self.ops.items():
                 if s < len(slices):
@@ -619,7 +735,7 @@ class DQCExecutor:
                     self._stalled = True
                 else:
                     self._stalled = False
-        self.end_time = max(q.clock for q in self.qpus.values())
+        self.end_time = self.T.max(*[q.clock for q in self.qpus.values()])
         self.finished = True
         return self
 

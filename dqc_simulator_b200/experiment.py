@@ -55,12 +55,13 @@ class ShotBatchResult:
 
 
 def run_shot_batch(qpu_ops, dqc, engine, data_qubits, ideal_ket, before_flush=None, after_launch=None,
-                   comm_axes_low=0):
-    """One batch of shots: reset the register, walk the compiled op lists (enqueue only), flush the
-    gate queue as fused passes, then read per-shot fidelity <phi|rho_S|phi> and the classical
-    registers back to the host."""
+                   comm_axes_low=0, per_shot_time=True):
+    """One batch of shots: reset the register (``reinit`` also moves on to the next block of global shot
+    ids, so consecutive batches are independent samples), walk the compiled op lists (enqueue only), flush
+    the gate queue as fused passes, then read per-shot fidelity <phi|rho_S|phi> and the classical registers
+    back to the host.  Every shot follows its own simulated timeline (``per_shot_time``)."""
     engine.reinit()
-    ex = executor.DQCExecutor(qpu_ops, dqc, engine, comm_axes_low=comm_axes_low).run()
+    ex = executor.DQCExecutor(qpu_ops, dqc, engine, comm_axes_low=comm_axes_low, per_shot_time=per_shot_time).run()
     axes = ex.axes_of(data_qubits)
     if before_flush:
         before_flush()
@@ -160,8 +161,9 @@ class DataCollector:
                 fid = np.array([be.fidelity_ket(axes, ket, s) for s in range(be.batch)], dtype=float)
         else:   # density-matrix reference: Uhlmann on the host, one small reduced matrix per shot
             fid = np.array([fidelity_squared(be.reduced_dm(axes, s), ref) for s in range(be.batch)])
-        self._frame = pd.DataFrame({"time_stamp": float(ex.end_time), "entity_name": "DQCMasterProtocol",
-                                    "fidelity": fid})
+        # simulated ns at which the run finished: one value per shot once the timeline depends on outcomes
+        end = be.read_time_reg(ex.end_time.index) if ex.T.is_reg(ex.end_time) else float(ex.end_time)
+        self._frame = pd.DataFrame({"time_stamp": end, "entity_name": "DQCMasterProtocol", "fidelity": fid})
         return self._frame
 
     @property

@@ -1,0 +1,170 @@
+"""Per-shot simulated time for batched shots.
+
+The reference runs ONE trajectory per ``ns.sim_run()``: a classically controlled X / Z correction
+exists (135 us + its gate noise) only when the measurement outcome was 1
+(``software/dqc_control.py:347-348, 387-390, 497-503``), ``_cat_disentangle_end`` executes the pending
+program only in that case (``:382-403``), and the link layer re-sends its handshake on a 600 us grid
+(``software/physical_layer.py:269-335``).  Every later memory-noise exponent
+(``hardware/noise_models.py:248-253``: p = 1 - exp(-dt * 1e-9 * rate)) inherits those differences, so a
+batch of shots has as many simulated timelines as it has outcome histories.
+
+Here a simulated time is either a host ``float`` (identical for every shot of the batch: everything
+before the first sampled measurement, and every forced / host-branching run) or a :class:`TReg`: a
+per-shot double held in the backend's *classical register file* next to the per-shot creg word.  The
+executor's clock arithmetic (``+``, ``max``, select on a classical bit, the handshake ``ceil``) goes
+through :class:`Timeline`, which evaluates floats on the host and emits one classical instruction per
+operation on registers.  The backend runs those instructions per shot (the CUDA engine inside its tile
+passes, right after the measurement that produced the bits they read) and noise channels take their
+probability from a register (``dyn_channel``).
+
+Register discipline (the contract of ``dqe_classical_op``, include/dqc_engine.h): the engine may run the
+classical instructions enqueued after a measurement EARLIER than the quantum ops enqueued between them
+(it hoists them to just behind that measurement), so a register must not be overwritten while an op
+enqueued earlier in the same span still reads it.  Freed registers therefore wait in ``_limbo`` until
+the next measurement (``fence()``).
+"""
+import math
+
+# classical opcodes (mirrored in csrc/dqe_device.cuh: ClOp)
+CL_CONST, CL_ADDI, CL_ADD, CL_SUB, CL_RSUBI, CL_MAX, CL_MAXI, CL_SEL, CL_CEILQ, CL_FMAI, CL_QEXP = range(1, 12)
+CL_BAND, CL_BANDN, CL_BOR, CL_BNOT, CL_BCOPY = range(16, 21)
+
+# dynamic one-qubit channels whose strength q comes from a register (csrc: DynKind)
+DYN_DEPOL, DYN_DEPHASE, DYN_AMPDAMP = 0, 1, 2
+
+
+class TReg:
+    """Per-shot simulated time (or probability) in classical register ``index``."""
+
+    __slots__ = ("tl", "index")
+
+    def __init__(self, tl, index):
+        self.tl = tl
+        self.index = index
+
+    def __del__(self):
+        tl = self.tl
+        if tl is not None:
+            tl._limbo.append(self.index)
+
+    def __repr__(self):
+        return f"TReg({self.index})"
+
+
+class Timeline:
+    """Clock algebra over floats and :class:`TReg` values for one backend."""
+
+    def __init__(self, backend, nregs=None):
+        self.be = backend
+        n = int(nregs if nregs is not None else getattr(backend, "n_time_regs", 0))
+        self._free = list(range(n))
+        self._limbo = []
+        self.nregs = n
+        self.peak = 0
+        self.ops = 0
+
+    # ---- registers ---------------------------------------------------------------------------
+    def _new(self):
+        if not self._free:
+            if not self._limbo:
+                raise RuntimeError("classical time registers exhausted: the circuit keeps more per-shot "
+                                   f"times alive than the backend's {self.nregs} registers")
+            # mid-span recycling: tell the backend not to hoist later classical ops over this point
+            self.be.classical_fence()
+            self.fence()
+        r = TReg(self, self._free.pop(0))
+        self.peak = max(self.peak, self.nregs - len(self._free))
+        return r
+
+    def fence(self):
+        """A measurement (or an explicit classical fence) has been enqueued: registers freed before it
+        may be reused by instructions enqueued after it."""
+        if self._limbo:
+            self._free.extend(self._limbo)
+            self._limbo.clear()
+            self._free.sort()
+
+    def _emit(self, op, a=None, b=None, cbit=-1, imm=0.0):
+        d = self._new()
+        self.be.classical_op(op, d.index, a.index if a is not None else 0, b.index if b is not None else 0,
+                             int(cbit), float(imm))
+        self.ops += 1
+        return d
+
+    def const(self, x):
+        return self._emit(CL_CONST, imm=float(x))
+
+    @staticmethod
+    def is_reg(t):
+        return isinstance(t, TReg)
+
+    # ---- arithmetic ----------------------------------------------------------------------------
+    def add(self, t, c):
+        """t + c, c a host float."""
+        if not isinstance(t, TReg):
+            return t + c
+        if c == 0:
+            return t
+        return self._emit(CL_ADDI, t, imm=c)
+
+    def sub(self, a, b):
+        """a - b."""
+        ra, rb = isinstance(a, TReg), isinstance(b, TReg)
+        if not ra and not rb:
+            return a - b
+        if ra and rb:
+            return self._emit(CL_SUB, a, b)
+        if ra:
+            return self._emit(CL_ADDI, a, imm=-b)
+        return self._emit(CL_RSUBI, b, imm=a)
+
+    def max(self, *ts):
+        regs, c = [], None
+        for t in ts:
+            if isinstance(t, TReg):
+                if not any(t is r for r in regs):
+                    regs.append(t)
+            else:
+                c = t if c is None else max(c, t)
+        if not regs:
+            return c
+        out = regs[0]
+        for r in regs[1:]:
+            out = self._emit(CL_MAX, out, r)
+        if c is not None:
+            out = self._emit(CL_MAXI, out, imm=c)
+        return out
+
+    def sel(self, pred, a, b):
+        """``a`` in the shots whose classical bit ``pred`` is 1, ``b`` in the others; pred None = all."""
+        if pred is None or a is b:
+            return a
+        if not isinstance(a, TReg) and not isinstance(b, TReg) and a == b:
+            return a
+        ra = a if isinstance(a, TReg) else self.const(a)
+        rb = b if isinstance(b, TReg) else self.const(b)
+        return self._emit(CL_SEL, ra, rb, cbit=pred.index)
+
+    def handshake(self, tc, ts, d, w):
+        """Time at which the client fires the source trigger (``physical_layer.py:269-335``):
+        tc + k w + 2 d with k = max(0, ceil((ts - tc - d) / w - 1e-12)) re-sends of HANDSHAKE_READY."""
+        if not isinstance(tc, TReg) and not isinstance(ts, TReg):
+            if w <= 0:
+                return max(tc + d, ts) + d
+            k = max(0, math.ceil((ts - tc - d) / w - 1e-12))
+            return tc + k * w + 2 * d
+        if w <= 0:
+            return self.add(self.max(self.add(tc, d), ts), d)
+        x = self.add(self.sub(ts, tc), -d)
+        k = self._emit(CL_CEILQ, x, imm=w)
+        tcr = tc if isinstance(tc, TReg) else self.const(tc)
+        return self.add(self._emit(CL_FMAI, k, tcr, imm=w), 2 * d)
+
+    def qexp(self, dt, rate_per_ns):
+        """q = 1 - exp(-max(0, dt) * rate) as a register (dt a register)."""
+        return self._emit(CL_QEXP, dt, imm=rate_per_ns)
+
+    # ---- classical bits --------------------------------------------------------------------------
+    def bit_op(self, op, dst_bit, a_bit, b_bit=0):
+        self.be.classical_op(op, int(dst_bit), int(a_bit), int(b_bit), -1, 0.0)
+        self.ops += 1

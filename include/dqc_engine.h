@@ -77,7 +77,9 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
 int dqe_destroy(dqe_t* h);
 /* Back to |0..0> with no live axis, creg = 0, draw index = 0, queue dropped: start the next batch
  * of shots on the same buffers (the reference instead rebuilds the network per shot,
- * docs/source/getting_started.rst:683-770). */
+ * docs/source/getting_started.rst:683-770).  The global shot id of shot 0 advances by
+ * batch * shot_stride (option "shot_stride", default 1; set it to the number of ranks that share one shot
+ * numbering), so consecutive batches draw fresh random numbers; call dqe_seed to replay a batch. */
 int dqe_reinit(dqe_t* h);
 const char* dqe_last_error(const dqe_t* h);   /* h may be NULL: error of a failed dqe_create */
 const char* dqe_version(void);
@@ -131,6 +133,39 @@ int dqe_inject_2q_mixture(dqe_t* h, int a, int b, int ncomp, const double* probs
  *      (-1 = sample).  flip_prob = MeasurementNoiseModel X-flip probability
  *      (noise_models.py:295-307). ---------------------------------------------------------- */
 int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, double flip_prob);
+
+/* ---- per-shot classical machine: the simulated timeline of every shot --------------------------
+ * The reference runs one trajectory per ns.sim_run(): a classically controlled X / Z correction exists
+ * (135 us + its gate noise) only when the outcome was 1 (dqc_control.py:347-348, 387-390, 497-503),
+ * _cat_disentangle_end executes the pending program only then (:382-403), the link layer re-sends its
+ * handshake on a 600 us grid (physical_layer.py:269-335), and every later memory-noise exponent
+ * p = 1 - exp(-dt * 1e-9 * rate) (noise_models.py:248-253; NetSquid DepolarNoiseModel wired at
+ * quantum_processors.py:868-877) inherits the difference.  A batch of shots therefore has one timeline
+ * per outcome history.  Each shot owns dqe_n_time_regs() double registers next to its creg word;
+ * dqe_classical_op appends one instruction (d = dst, a, b registers -- or creg bits for the B* ops):
+ *    1 CONST d<-imm        2 ADDI d<-a+imm       3 ADD d<-a+b          4 SUB d<-a-b
+ *    5 RSUBI d<-imm-a      6 MAX d<-max(a,b)     7 MAXI d<-max(a,imm)  8 SEL d<-(creg bit cbit ? a : b)
+ *    9 CEILQ d<-max(0, ceil(a/imm - 1e-12))      10 FMAI d<-a*imm+b    11 QEXP d<-1-exp(-max(0,a)*imm)
+ *   16 BAND  17 BANDN (a & ~b)  18 BOR  19 BNOT  20 BCOPY      (creg bit d <- f(bit a, bit b))
+ * Instructions run per shot in queue order relative to each other and AFTER every measurement queued
+ * before them, but the engine may run them EARLIER than quantum ops queued between that measurement and
+ * them (it hoists them to just behind the measurement so that the quantum ops still fuse).  Contract: a
+ * register / bit must not be overwritten while an op queued earlier since the last measurement (or
+ * dqe_classical_fence) still reads it.  Registers are undefined until written; dqe_reinit keeps them.
+ * dqe_enqueue_dyn_channel: one-qubit channel whose strength q is the shot's register `reg`:
+ *   kind 0 depolarising (1-q) rho + q I/2, 1 dephasing (off-diagonals x (1-q)), 2 amplitude damping
+ *   (gamma = q; dm only).  dm: analytic; ket: one branch sampled per shot. */
+int dqe_n_time_regs(void);
+int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, double imm);
+int dqe_classical_fence(dqe_t* h);
+int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg);
+int dqe_read_time_reg(dqe_t* h, int reg, double* out /*batch*/);
+/* Every measurement outcome of every shot, in draw order (the reference's mid-simulation result
+ * collector, util/helper.py:226-263, sees them one signal at a time): enable with
+ * dqe_set_option(h, "outcome_log", max_draws); rows [first, first + count) of the [draw][batch] int8 log
+ * (-1 = not measured).  dqe_draw_count = random draws consumed since dqe_seed / dqe_reinit. */
+int dqe_read_outcomes(dqe_t* h, int64_t first, int64_t count, int8_t* out);
+int64_t dqe_draw_count(dqe_t* h);
 
 /* ---- execution + read-out ------------------------------------------------------------------ */
 int dqe_flush(dqe_t* h);                 /* plan + launch everything queued (asynchronous) */
@@ -186,7 +221,8 @@ int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_ax
  * (0: composed axis-local superoperators stay dense 4x4 stand-alone sweeps instead of running as their
  * Pauli-channel / U rho U^dagger factors inside group sweeps), "tmap" (0: a tile is fetched run by run with
  * cp.async.bulk instead of one cp.async.bulk.tensor box per direction), "prefetch" (tiles ahead whose box is
- * prefetched into L2 at CTA start; -1 = one wave of resident CTAs, 0 = off). */
+ * prefetched into L2 at CTA start; -1 = one wave of resident CTAs, 0 = off), "shot_stride" (see dqe_reinit),
+ * "outcome_log" (see dqe_read_outcomes). */
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
 /* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
  * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates

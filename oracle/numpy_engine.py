@@ -93,6 +93,10 @@ class OracleEngine:
         self.state = np.ones((self.batch,), dtype=complex)
         self.creg = np.zeros((self.batch,), dtype=np.uint64)
         self._pred_bit = -1
+        # per-shot classical register file (simulated times / channel strengths), dqe_classical_op
+        self.n_time_regs = 128
+        self.treg = np.zeros((self.n_time_regs, self.batch), dtype=np.float64)
+        self.outcomes = []   # one int8 array (batch) per measurement, in draw order (dqe_read_outcomes)
         self.seed(seed, shot_offset)
 
     # ------------------------------------------------------------------ bookkeeping
@@ -256,6 +260,103 @@ class OracleEngine:
             acc = acc + _apply_matrix(t, K.conj(), [self._cdim(axis)])
         self._commit(acc)
 
+    # ------------------------------------------------------------------ per-shot classical machine
+    def _bit(self, b):
+        return ((self.creg >> np.uint64(b)) & np.uint64(1)).astype(bool)
+
+    def _set_bit(self, b, v):
+        bit = np.uint64(1) << np.uint64(b)
+        self.creg = (self.creg & ~bit) | (v.astype(np.uint64) << np.uint64(b))
+
+    def classical_op(self, op, dst, a=0, b=0, cbit=-1, imm=0.0):
+        """Restates ``dqe_classical_op`` (include/dqc_engine.h): one instruction of the per-shot register
+        machine that carries the simulated timelines of batched shots (dqc_simulator_b200/timeline.py);
+        opcodes are timeline.CL_*.  Evaluated eagerly here, per shot, in the engine's operation order."""
+        R = self.treg
+        if op == 1:      # CONST
+            R[dst] = imm
+        elif op == 2:    # ADDI
+            R[dst] = R[a] + imm
+        elif op == 3:    # ADD
+            R[dst] = R[a] + R[b]
+        elif op == 4:    # SUB
+            R[dst] = R[a] - R[b]
+        elif op == 5:    # RSUBI
+            R[dst] = imm - R[a]
+        elif op == 6:    # MAX
+            R[dst] = np.maximum(R[a], R[b])
+        elif op == 7:    # MAXI
+            R[dst] = np.maximum(R[a], imm)
+        elif op == 8:    # SEL
+            R[dst] = np.where(self._bit(cbit), R[a], R[b])
+        elif op == 9:    # CEILQ: handshake re-sends, physical_layer.py:269-335
+            R[dst] = np.maximum(0.0, np.ceil(R[a] / imm - 1e-12))
+        elif op == 10:   # FMAI
+            R[dst] = R[a] * imm + R[b]
+        elif op == 11:   # QEXP: noise_models.py:248-253
+            R[dst] = 1.0 - np.exp(-np.maximum(0.0, R[a]) * imm)
+        elif op == 16:   # BAND
+            self._set_bit(dst, self._bit(a) & self._bit(b))
+        elif op == 17:   # BANDN
+            self._set_bit(dst, self._bit(a) & ~self._bit(b))
+        elif op == 18:   # BOR
+            self._set_bit(dst, self._bit(a) | self._bit(b))
+        elif op == 19:   # BNOT
+            self._set_bit(dst, ~self._bit(a))
+        elif op == 20:   # BCOPY
+            self._set_bit(dst, self._bit(a))
+        else:
+            raise ValueError(f"unknown classical opcode {op}")
+
+    def classical_fence(self):
+        pass
+
+    def read_time_reg(self, reg):
+        return self.treg[int(reg)].copy()
+
+    def dyn_channel(self, axis, kind, reg):
+        """One-qubit channel whose strength q is read per shot from classical register ``reg``:
+        kind 0 depolarising (1-q) rho + q I/2, 1 dephasing (off-diagonals x (1-q)), 2 amplitude damping
+        (gamma = q).  DM: analytic; ket: one branch sampled per shot (depolarising / dephasing only)."""
+        q = self.treg[int(reg)]
+        if self.formalism == DM:
+            st = np.moveaxis(self.state, [self._dim(axis), self._cdim(axis)], [1, 2])
+            new = st.copy()
+            qb = q.reshape((-1,) + (1,) * (st.ndim - 3))
+            e00, e01, e10, e11 = st[:, 0, 0], st[:, 0, 1], st[:, 1, 0], st[:, 1, 1]
+            if kind == 0:
+                new[:, 0, 0] = (1 - qb / 2) * e00 + (qb / 2) * e11
+                new[:, 1, 1] = (1 - qb / 2) * e11 + (qb / 2) * e00
+                new[:, 0, 1] = (1 - qb) * e01
+                new[:, 1, 0] = (1 - qb) * e10
+            elif kind == 1:
+                new[:, 0, 1] = (1 - qb) * e01
+                new[:, 1, 0] = (1 - qb) * e10
+            elif kind == 2:
+                new[:, 0, 0] = e00 + qb * e11
+                new[:, 1, 1] = (1 - qb) * e11
+                new[:, 0, 1] = np.sqrt(1 - qb) * e01
+                new[:, 1, 0] = np.sqrt(1 - qb) * e10
+            else:
+                raise ValueError("dyn_channel kind")
+            self._commit(np.moveaxis(new, [1, 2], [self._dim(axis), self._cdim(axis)]))
+            return
+        u, _ = self._next_uniforms()
+        if kind == 0:
+            w = q / 4.0
+            w0 = 1.0 - 3.0 * w
+            with np.errstate(divide="ignore", invalid="ignore"):
+                s = np.where(u < w0, 0, np.where(w > 0, 1 + np.floor((u - w0) / w), 0)).astype(np.int64)
+            s = np.minimum(s, 3)
+        elif kind == 1:
+            s = np.where(u >= 1.0 - q / 2.0, 3, 0)
+        else:
+            raise NotImplementedError("amplitude damping is DM-only")
+        for idx in (1, 2, 3):
+            sel = s == idx
+            if sel.any():
+                self._apply([axis], _PAULI[idx], predicate=sel)
+
     # ------------------------------------------------------------------ injection
     def inject_2q(self, a, b, state, is_dm):
         """Place a 2-qubit state on two free axes (a = most significant)."""
@@ -351,7 +452,12 @@ class OracleEngine:
         if creg_bit is not None and creg_bit >= 0:
             bit = np.uint64(1) << np.uint64(creg_bit)
             self.creg = (self.creg & ~bit) | (m.astype(np.uint64) << np.uint64(creg_bit))
+        self.outcomes.append(m.astype(np.int8))
         return m
+
+    def read_outcomes(self):
+        """(number of measurements, batch) int8: every outcome in draw order."""
+        return np.array(self.outcomes, dtype=np.int8).reshape(len(self.outcomes), self.batch)
 
     # ------------------------------------------------------------------ read-out
     def flush(self):

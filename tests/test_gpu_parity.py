@@ -64,12 +64,50 @@ class Both:
         assert err < TOL, f"{what}: max-abs {err:.3e}"
         assert sorted(self.g.live) == sorted(self.o.live)
         assert np.array_equal(self.g.read_creg_words(), self.o.creg), what
+        for r in sorted(getattr(self, "regs_written", ())):
+            a, b = self.g.read_time_reg(r), self.o.read_time_reg(r)
+            assert np.allclose(a, b, rtol=1e-14, atol=1e-300), f"{what}: time register {r}"
         return err
 
 
-def random_program(b, rng, steps, formalism, check_every=0):
+class ClassicalState:
+    """Bookkeeping that keeps a random program inside the contract of dqe_classical_op: a register / creg
+    bit is not overwritten while an op queued earlier in the same span (since the last measurement or
+    fence) still reads it."""
+
+    def __init__(self, b):
+        self.b = b
+        b.regs_written = set()
+        self.read_regs, self.read_bits = set(), set()
+        self.times, self.qs = [], []          # registers holding times / probabilities
+        self.scratch_bits = []
+
+    def new_span(self):
+        self.read_regs.clear()
+        self.read_bits.clear()
+
+    def fresh_reg(self):
+        for r in range(128):
+            if r not in self.read_regs and r not in self.times[-6:] and r not in self.qs[-6:]:
+                self.b.regs_written.add(r)
+                return r
+        self.b.classical_fence()
+        self.new_span()
+        return self.fresh_reg()
+
+    def fresh_bit(self):
+        for bit in range(40, 64):
+            if bit not in self.read_bits:
+                return bit
+        self.b.classical_fence()
+        self.new_span()
+        return self.fresh_bit()
+
+
+def random_program(b, rng, steps, formalism, check_every=0, classical=False):
     n = b.n
     cbit = 0
+    cs = ClassicalState(b) if classical else None
     for step in range(steps):
         live = list(b.o.live)
         free = [a for a in range(n) if a not in live]
@@ -88,6 +126,10 @@ def random_program(b, rng, steps, formalism, check_every=0):
             choices += ["free", "reset"]
             if formalism == "ket":
                 choices += ["diag3"]
+        if classical:
+            choices += ["cl_time"] * 3 + ["cl_bit"]
+            if live and cs.qs:
+                choices += ["dyn"] * 4
         c = rng.choice(choices)
         pick = lambda k: [int(x) for x in rng.choice(live, size=k, replace=False)]
         if c == "alloc":
@@ -110,8 +152,69 @@ def random_program(b, rng, steps, formalism, check_every=0):
             b.apply_1q(pick(1)[0], H)
         elif c == "diag1":
             b.apply_1q(pick(1)[0], np.diag(np.exp(1j * rng.normal(size=2))))
+        elif c == "cl_time":
+            # a few instructions of clock arithmetic ending in a channel strength q = 1 - exp(-dt * rate)
+            from dqc_simulator_b200 import timeline as tl
+
+            t0 = cs.fresh_reg()
+            b.classical_op(tl.CL_CONST, t0, imm=float(rng.uniform(0, 1e6)))
+            cs.times.append(t0)
+            t1 = cs.fresh_reg()
+            if cbit and rng.integers(2):
+                bit = int(rng.integers(0, min(cbit, 40)))
+                tt = cs.fresh_reg()
+                b.classical_op(tl.CL_ADDI, tt, t0, imm=135e3)
+                cs.times.append(tt)
+                b.classical_op(tl.CL_SEL, t1, tt, t0, cbit=bit)
+                cs.read_bits.add(bit)
+            else:
+                src = int(rng.choice(cs.times))
+                b.classical_op(tl.CL_MAX, t1, t0, src)
+                cs.read_regs.add(src)
+            cs.times.append(t1)
+            kind = int(rng.integers(4))
+            t2 = cs.fresh_reg()
+            if kind == 0:
+                b.classical_op(tl.CL_ADDI, t2, t1, imm=6e5)
+            elif kind == 1:
+                b.classical_op(tl.CL_CEILQ, t2, t1, imm=6e5)
+            elif kind == 2:
+                b.classical_op(tl.CL_FMAI, t2, t1, t0, imm=3.0)
+            else:
+                b.classical_op(tl.CL_RSUBI, t2, t1, imm=5e6)
+            cs.times.append(t2)
+            dt, q = cs.fresh_reg(), cs.fresh_reg()
+            b.classical_op(tl.CL_SUB, dt, t2, t0)
+            cs.times.append(dt)
+            b.classical_op(tl.CL_QEXP, q, dt, imm=float(rng.uniform(1e-8, 3e-7)))
+            cs.qs.append(q)
+            cs.read_regs.update((t0, t1, t2, dt))
+        elif c == "cl_bit":
+            from dqc_simulator_b200 import timeline as tl
+
+            srcs = [int(x) for x in rng.integers(0, max(min(cbit, 40), 1), size=2)] + cs.scratch_bits[-2:]
+            a0, a1 = int(rng.choice(srcs)), int(rng.choice(srcs))
+            d = cs.fresh_bit()
+            b.classical_op(int(rng.choice([tl.CL_BAND, tl.CL_BANDN, tl.CL_BOR, tl.CL_BNOT, tl.CL_BCOPY])), d, a0, a1)
+            cs.read_bits.update((a0, a1))
+            cs.scratch_bits.append(d)
+        elif c == "dyn":
+            q = int(rng.choice(cs.qs[-4:]))
+            kinds = [0, 1, 2] if formalism == "dm" else [0, 1]
+            if cs.scratch_bits and rng.integers(3) == 0:
+                bit = cs.scratch_bits[-1]
+                b.set_predicate(bit)
+                b.dyn_channel(pick(1)[0], int(rng.choice(kinds)), q)
+                b.set_predicate(-1)
+                cs.read_bits.add(bit)
+            else:
+                b.dyn_channel(pick(1)[0], int(rng.choice(kinds)), q)
+            cs.read_regs.add(q)
         elif c == "pred1q":
             bit = int(rng.integers(0, max(cbit, 1))) % 64
+            if cs:
+                bit = bit % 40
+                cs.read_bits.add(bit)
             if rng.integers(2):
                 b.cond_1q(pick(1)[0], X if rng.integers(2) else Z, bit)
             else:
@@ -147,8 +250,11 @@ def random_program(b, rng, steps, formalism, check_every=0):
             b.apply_diag(pick(3), np.exp(1j * rng.normal(size=8)))
         elif c == "measure":
             forced = -1 if rng.integers(4) else int(rng.integers(2))
-            b.measure(pick(1)[0], cbit % 64, forced, bool(rng.integers(2)), float(rng.choice([0.0, 0.0, 0.05])))
+            b.measure(pick(1)[0], cbit % (40 if cs else 64), forced, bool(rng.integers(2)),
+                      float(rng.choice([0.0, 0.0, 0.05])))
             cbit += 1
+            if cs:
+                cs.new_span()
         elif c == "free":
             b.free_axis(pick(1)[0])
         elif c == "reset":
@@ -193,6 +299,74 @@ def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
     for k, v in opts.items():
         b.g.set_option(k, v)
     random_program(b, rng, 120, "dm", check_every=40)
+
+
+@pytest.mark.parametrize("formalism,n,batch,tile", [("dm", 7, 3, 10), ("dm", 6, 4, 8), ("dm", 7, 2, 12), ("dm", 4, 5, 11),
+                                                     ("ket", 12, 3, 8), ("ket", 9, 4, 11)])
+@pytest.mark.parametrize("opts", [dict(), dict(cluster=0), dict(fuse=0)])
+def test_classical_machine_and_dynamic_channels(formalism, n, batch, tile, opts):
+    """Per-shot classical registers (dqe_classical_op): clock arithmetic, selects on creg bits, derived bits,
+    channels whose strength is read from a register -- with the instructions hoisted behind the previous
+    measurement by the planner, in cluster-fused passes, in finish-kernel passes and one op per pass."""
+    rng = np.random.default_rng(99 + n + tile)
+    b = Both(formalism, n, batch, 13, tile_bits=tile)
+    for k, v in opts.items():
+        b.g.set_option(k, v)
+    random_program(b, rng, 140, formalism, check_every=35, classical=True)
+
+
+def test_classical_only_flush_and_outcome_log():
+    """Classical instructions with no quantum op around them run as their own tiny kernel; the outcome log
+    keeps every measurement of every shot in draw order."""
+    from dqc_simulator_b200 import timeline as tl
+
+    b = Both("dm", 3, 6, 21)
+    b.g.set_option("outcome_log", 16)
+    for a in range(3):
+        b.alloc_axis(a)
+        b.apply_1q(a, H)
+    b.measure(0, 0, -1, False, 0.0)
+    b.measure(1, 1, -1, True, 0.02)
+    b.check("measured")
+    b.classical_op(tl.CL_CONST, 3, imm=1000.0)
+    b.classical_op(tl.CL_ADDI, 4, 3, imm=135e3)
+    b.classical_op(tl.CL_SEL, 5, 4, 3, cbit=0)
+    b.classical_op(tl.CL_BANDN, 9, 0, 1)
+    b.regs_written = {3, 4, 5}
+    b.check("classical only")
+    got = b.g.read_time_reg(5)
+    bit0 = b.g.read_creg(0)
+    assert np.array_equal(got, np.where(bit0 == 1, 136e3, 1000.0))
+    log_g, log_o = b.g.read_outcomes(), b.o.read_outcomes()
+    assert log_g.shape == (2, 6) and np.array_equal(log_g, log_o)
+    assert np.array_equal(log_g[0], bit0)
+
+
+def test_reinit_draws_fresh_shots_and_keeps_parity():
+    """consecutive batches on one handle must not replay the same random shots.
+    dqe_reinit advances the global shot ids by batch * shot_stride; dqe_seed replays."""
+    def batch_words(e):
+        for a in range(3):
+            e.alloc_axis(a)
+            e.apply_1q(a, H)
+            e.measure(a, a, -1, False, 0.0)
+        w = e.read_creg_words() if hasattr(e, "read_creg_words") else e.creg
+        return w.copy(), e.full_state()
+
+    g = _engine("dm", 3, 64, seed=7, shot_offset=0)
+    g.set_option("shot_stride", 2)
+    w0, _ = batch_words(g)
+    g.reinit()
+    w1, s1 = batch_words(g)
+    assert not np.array_equal(w0, w1)
+    o = OracleEngine("dm", 3, 64, seed=7, shot_offset=128)      # second batch of rank 0 of 2
+    wo, so = batch_words(o)
+    assert np.array_equal(w1, wo) and np.abs(s1 - so).max() < TOL
+    g.seed(7, 0)
+    g.reinit()                                                      # reinit after seed(…, 0): offset 128 again
+    g.seed(7, 0)
+    w2, _ = batch_words(g)
+    assert np.array_equal(w2, w0)
 
 
 @pytest.mark.parametrize("formalism", ["ket", "dm"])

@@ -299,13 +299,16 @@ def test_program_instructions_overlap_on_free_positions():
 
 
 @pytest.mark.parametrize("case,n,want", [
-    ("c2_grover5_3qpu_cat.json", 7, dict(passes=292, micro_ops=3193, api_ops=3089, merged_ops=797)),
-    ("c2_qft5_3qpu_cat.json", 7, dict(passes=35, micro_ops=486, api_ops=480, merged_ops=132)),
-    ("c4_qft16_mono.json.gz", 16, dict(passes=67, micro_ops=1196, api_ops=1564, merged_ops=521)),
+    # per-shot timelines (round 2): the clock arithmetic rides along as classical instructions
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=295, micro_ops=6452, api_ops=13890, merged_ops=776)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=40, micro_ops=982, api_ops=2133, merged_ops=125)),
+    ("c4_qft16_mono.json.gz", 16, dict(passes=56, micro_ops=1182, api_ops=1564, merged_ops=521)),
 ])
 def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
     """Plan-only handles (no GPU): the pass / micro-op counts the measured numbers in profiles/ were taken
-    with (final executor of round 1, r01v-r01z).  A planner change that alters them should be a conscious one."""
+    with (round 2: every shot follows its own simulated timeline; the monolithic C4 circuit has no
+    measurement, so all of its times stay host constants).  A planner change that alters them should be a
+    conscious one."""
     from dqc_simulator_b200 import executor, experiment, hardware
 
     ops, _ = opstream.load(os.path.join(os.path.dirname(__file__), "golden", case))
@@ -319,3 +322,69 @@ def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
     st = e.stats()
     assert {k: st[k] for k in want} == want
     assert st["finish_launches"] == 0      # every measurement of these circuits is fused into its pass
+
+
+# ---- per-shot simulated timelines -------------------------------------------------
+def _per_shot_case(circuit, batch, seed, make=None):
+    """A sampled batch in which every shot follows its own timeline, and the same shots re-run one at a
+    time with the outcomes forced (the host then knows every outcome and branches exactly like the
+    reference does: dqc_control.py:347-348, 385-403, 497-503; physical_layer.py:269-335)."""
+    from dqc_simulator_b200 import executor, experiment
+    from oracle.numpy_engine import OracleEngine
+
+    ops, _ = experiment.load_c2(circuit)
+    dqc = experiment.c2_hardware(noisy=True)
+    be = (make or OracleEngine)("dm", 7, batch, seed=seed)
+    if hasattr(be, "set_option"):
+        be.set_option("outcome_log", 512)
+    ex = executor.DQCExecutor(ops, dqc, be).run()
+    axes = ex.axes_of(ex.processing_qubits())
+    rho = [be.reduced_dm(axes, s) for s in range(batch)]
+    outcomes = be.read_outcomes()
+    end = be.read_time_reg(ex.end_time.index) if ex.T.is_reg(ex.end_time) else np.full(batch, ex.end_time)
+    singles = []
+    for s in range(batch):
+        b1 = OracleEngine("dm", 7, 1, seed=seed, shot_offset=s)
+        e1 = executor.DQCExecutor(ops, dqc, b1, forced_outcomes=list(outcomes[:, s])).run()
+        singles.append((b1.reduced_dm(e1.axes_of(e1.processing_qubits()), 0), e1.end_time))
+    return rho, end, singles, outcomes, ex
+
+
+@pytest.mark.parametrize("circuit,batch", [("ghz", 16), ("qft", 12)])
+def test_batched_shots_follow_their_own_timeline(circuit, batch):
+    """Shot by shot, a sampled batch equals the single-trajectory run with the same outcomes: rho to 1e-12
+    and the simulated end time exactly -- the batch no longer shares one (expected) timeline."""
+    rho, end, singles, outcomes, ex = _per_shot_case(circuit, batch, seed=11)
+    assert len({tuple(outcomes[:, s]) for s in range(batch)}) > 1          # the shots really differ
+    for s in range(batch):
+        assert np.abs(rho[s] - singles[s][0]).max() < 1e-12
+        assert end[s] == singles[s][1]
+    assert len(set(end.tolist())) > 1                                      # ... and so do their timelines
+    assert ex.T.peak <= 128
+
+
+def test_per_shot_timeline_reproduces_the_trajectory_spread():
+    """The per-shot fidelity spread of a QFT-5 batch is the trajectory spread (6.8e-5 from single-trajectory
+    runs), not the 2.5e-5 of the shared expected timeline of round 1."""
+    from dqc_simulator_b200 import executor, experiment
+    from oracle.numpy_engine import OracleEngine
+
+    ops, _ = experiment.load_c2("qft")
+    data, ideal = experiment.ideal_output_ket(ops, lambda f, n, b: OracleEngine(f, n, b))
+    spreads = {}
+    for exact in (True, False):
+        be = OracleEngine("dm", 7, 64, seed=3)
+        ex = executor.DQCExecutor(ops, experiment.c2_hardware(noisy=True), be, per_shot_time=exact).run()
+        axes = ex.axes_of(data)
+        f = np.array([be.fidelity_ket(axes, ideal, s) for s in range(64)])
+        spreads[exact] = f.std()
+        assert abs(f.mean() - 0.6470482939691747) < 4 * 6.8e-5 / 8 + 1e-5
+    assert 4.5e-5 < spreads[True] < 9.5e-5 and spreads[False] < 0.6 * spreads[True]
+
+
+def test_reinit_advances_the_shot_ids():
+    """dqe_reinit must not replay the random stream (plan-only handle: host logic)."""
+    e = engine.Engine("dm", 3, 4, seed=5, device=-1)
+    e.set_option("shot_stride", 2)
+    e.reinit()     # offset 0 -> 8
+    e.reinit()     # -> 16: no error, the arithmetic itself is covered by the GPU twin
