@@ -61,15 +61,16 @@ enum OpType : int32_t {
 enum ClOp : uint8_t {
   CL_CONST = 1,   // d <- imm
   CL_ADDI = 2,    // d <- a + imm
-  CL_ADD = 3,     // d <- a + b
-  CL_SUB = 4,     // d <- a - b
+  CL_ADD = 3,     // d <- a + b + imm
+  CL_SUB = 4,     // d <- a - b + imm
   CL_RSUBI = 5,   // d <- imm - a
-  CL_MAX = 6,     // d <- max(a, b)
+  CL_MAX = 6,     // d <- max(a, b + imm)
   CL_MAXI = 7,    // d <- max(a, imm)
-  CL_SEL = 8,     // d <- creg bit `cbit` ? a : b
+  CL_SEL = 8,     // d <- creg bit `cbit` ? a + imm : b
   CL_CEILQ = 9,   // d <- max(0, ceil(a / imm - 1e-12))   (handshake re-sends, physical_layer.py:269-335)
   CL_FMAI = 10,   // d <- a * imm + b
   CL_QEXP = 11,   // d <- 1 - exp(-max(0, a) * imm)       (noise_models.py:248-253)
+  CL_ADDIF = 12,  // d <- a + (creg bit `cbit` ? imm : 0)
   CL_BAND = 16,   // creg bit d <- bit a & bit b
   CL_BANDN = 17,  // d <- a & ~b
   CL_BOR = 18,
@@ -432,12 +433,13 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& c
   switch (in.op) {
     case CL_CONST: R[in.dst] = c; break;
     case CL_ADDI: R[in.dst] = R[in.a] + c; break;
-    case CL_ADD: R[in.dst] = R[in.a] + R[in.b]; break;
-    case CL_SUB: R[in.dst] = R[in.a] - R[in.b]; break;
+    case CL_ADD: R[in.dst] = R[in.a] + R[in.b] + c; break;
+    case CL_SUB: R[in.dst] = R[in.a] - R[in.b] + c; break;
     case CL_RSUBI: R[in.dst] = c - R[in.a]; break;
-    case CL_MAX: R[in.dst] = fmax(R[in.a], R[in.b]); break;
+    case CL_MAX: R[in.dst] = fmax(R[in.a], R[in.b] + c); break;
     case CL_MAXI: R[in.dst] = fmax(R[in.a], c); break;
-    case CL_SEL: R[in.dst] = ((cw >> in.cbit) & 1ull) ? R[in.a] : R[in.b]; break;
+    case CL_SEL: R[in.dst] = ((cw >> in.cbit) & 1ull) ? R[in.a] + c : R[in.b]; break;
+    case CL_ADDIF: R[in.dst] = R[in.a] + (((cw >> in.cbit) & 1ull) ? c : 0.0); break;
     case CL_CEILQ: R[in.dst] = fmax(0.0, ceil(R[in.a] / c - 1e-12)); break;
     case CL_FMAI: R[in.dst] = __dadd_rn(__dmul_rn(R[in.a], c), R[in.b]); break;   // like the host: no contraction
     case CL_QEXP: R[in.dst] = 1.0 - exp(-fmax(0.0, R[in.a]) * c); break;
@@ -1323,8 +1325,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       if (op_type == OP_CLASSICAL) {
         // a run of consecutive classical micro-ops: serial ones on thread 0 in order, then the independent
         // ones (QEXP: one exp each) spread over the threads
+        // one span's block is [serial ...][independent ...]; a serial micro-op behind an independent one
+        // belongs to the next span (after a fence) and must wait for this block
         int run = 1;
-        while (cur + run < pp.nops && s_ops[cur + run].type == OP_CLASSICAL) ++run;
+        while (cur + run < pp.nops && s_ops[cur + run].type == OP_CLASSICAL &&
+               !(s_ops[cur + run - 1].c_off != 0 && s_ops[cur + run].c_off == 0))
+          ++run;
         const double* imm = reinterpret_cast<const double*>(s_consts);
         bool any_par = false;
         if (threadIdx.x == 0) {

@@ -2038,19 +2038,20 @@ static int ensure_tregs(dqe_t* h) {
 int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, double imm) {
   if (int rc = check_ready(h)) return rc;
   const bool bitop = opcode >= CL_BAND && opcode <= CL_BCOPY;
-  const bool regop = opcode >= CL_CONST && opcode <= CL_QEXP;
+  const bool regop = opcode >= CL_CONST && opcode <= CL_ADDIF;
   if (!bitop && !regop) return fail(h, DQE_EINVAL, "classical_op: unknown opcode");
   const int lim = bitop ? 64 : kTimeRegs;
   if (dst < 0 || dst >= lim || a < 0 || a >= lim || b < 0 || b >= lim)
     return fail(h, DQE_EINVAL, bitop ? "classical_op: creg bit out of range" : "classical_op: register out of range");
-  if (opcode == CL_SEL && (cbit < 0 || cbit >= 64)) return fail(h, DQE_EINVAL, "classical_op: SEL needs a creg bit");
+  const bool uses_bit = opcode == CL_SEL || opcode == CL_ADDIF;
+  if (uses_bit && (cbit < 0 || cbit >= 64)) return fail(h, DQE_EINVAL, "classical_op: SEL / ADDIF need a creg bit");
   if (opcode == CL_CEILQ && !(imm > 0.0)) return fail(h, DQE_EINVAL, "classical_op: CEILQ needs a positive divisor");
   if (int rc = ensure_tregs(h)) return rc;
   HostOp o = blank(h, 0);
   o.kind = 2;
   o.m.pred_bit = -1;
   o.ci.op = (uint8_t)opcode; o.ci.dst = (uint8_t)dst; o.ci.a = (uint8_t)a; o.ci.b = (uint8_t)b;
-  o.ci.cbit = (int8_t)(opcode == CL_SEL ? cbit : 0); o.ci.pad = 0; o.ci.imm = 0;
+  o.ci.cbit = (int8_t)(uses_bit ? cbit : 0); o.ci.pad = 0; o.ci.imm = 0;
   o.imm = imm;
   h->queue.push_back(o);
   h->stats[4]++;

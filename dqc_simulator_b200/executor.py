@@ -168,20 +168,19 @@ class QPU:
         (``noise_models.py:248-253``; NetSquid ``DepolarNoiseModel`` time dependent).  With per-shot
         times the exponent is evaluated per shot by the backend (``dyn_channel``)."""
         last = self.last_access[pos]
-        if now is last:
-            return
         be, ax, sp, T = self.ex.backend, self.axis[pos], self.spec, self.ex.T
+        if T.same(now, last):
+            return
         rates = ((tlm.DYN_DEPOL, sp.mem_rate(pos)), (tlm.DYN_DEPHASE, sp.mem_dephase_rate),
                  (tlm.DYN_AMPDAMP, sp.mem_amp_damp_rate))
-        if T.is_reg(now) or T.is_reg(last):
-            if not any(r > 0 for _, r in rates):
-                return
-            dt = T.sub(now, last)
+        if not any(r > 0 for _, r in rates):
+            return
+        dt = T.sub(now, last)        # a host float whenever the idle time is the same in every shot
+        if T.is_reg(dt):
             for kind, rate in rates:
                 if rate > 0:
                     be.dyn_channel(ax, kind, T.qexp(dt, 1e-9 * rate).index)
             return
-        dt = now - last
         if dt <= 0:
             return
         rate = sp.mem_rate(pos)
@@ -248,6 +247,8 @@ class QPU:
         for it in program.instructions:
             instruction, positions, operator, key, predicate = it
             run = predicate
+            if exact and it.done is not None and it.done is predicate:
+                continue          # ran wherever its predicate holds (the Z of a conditional execute_program)
             if exact:
                 if it.done is not None:
                     run = ex._p_and(ex._p_not(it.done, temps), run, temps)
@@ -743,6 +744,12 @@ class DQCExecutor:
         return self._events
 
     # ---- read-out ----------------------------------------------------------------
+    def read_time(self, t):
+        """A simulated time as one value per shot (numpy array of ``backend.batch``)."""
+        if self.T.is_reg(t):
+            return np.asarray(self.backend.read_time_reg(self.T.materialise(t).index), dtype=float)
+        return np.full(getattr(self.backend, "batch", 1), float(t))
+
     def axes_of(self, qubits, apply_memory_noise=True):
         """[(position, node_name), ...] -> engine axes, like ``qmemory.pop(positions)`` at the
         end of the run (memory noise up to ``end_time``; ``util/helper.py:136-151``)."""

@@ -162,7 +162,7 @@ class DataCollector:
         else:   # density-matrix reference: Uhlmann on the host, one small reduced matrix per shot
             fid = np.array([fidelity_squared(be.reduced_dm(axes, s), ref) for s in range(be.batch)])
         # simulated ns at which the run finished: one value per shot once the timeline depends on outcomes
-        end = be.read_time_reg(ex.end_time.index) if ex.T.is_reg(ex.end_time) else float(ex.end_time)
+        end = ex.read_time(ex.end_time) if ex.T.is_reg(ex.end_time) else float(ex.end_time)
         self._frame = pd.DataFrame({"time_stamp": end, "entity_name": "DQCMasterProtocol", "fidelity": fid})
         return self._frame
 

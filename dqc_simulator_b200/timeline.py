@@ -26,7 +26,8 @@ the next measurement (``fence()``).
 import math
 
 # classical opcodes (mirrored in csrc/dqe_device.cuh: ClOp)
-CL_CONST, CL_ADDI, CL_ADD, CL_SUB, CL_RSUBI, CL_MAX, CL_MAXI, CL_SEL, CL_CEILQ, CL_FMAI, CL_QEXP = range(1, 12)
+(CL_CONST, CL_ADDI, CL_ADD, CL_SUB, CL_RSUBI, CL_MAX, CL_MAXI, CL_SEL, CL_CEILQ, CL_FMAI, CL_QEXP,
+ CL_ADDIF) = range(1, 13)
 CL_BAND, CL_BANDN, CL_BOR, CL_BNOT, CL_BCOPY = range(16, 21)
 
 # dynamic one-qubit channels whose strength q comes from a register (csrc: DynKind)
@@ -34,7 +35,7 @@ DYN_DEPOL, DYN_DEPHASE, DYN_AMPDAMP = 0, 1, 2
 
 
 class TReg:
-    """Per-shot simulated time (or probability) in classical register ``index``."""
+    """Owner of classical register ``index`` (returned to the pool when the last reference dies)."""
 
     __slots__ = ("tl", "index")
 
@@ -51,8 +52,28 @@ class TReg:
         return f"TReg({self.index})"
 
 
+class TVal:
+    """Per-shot simulated time ``register + offset``.  Keeping the host-known offset out of the register
+    makes most of the executor's clock arithmetic free: durations only move the offset, and two times
+    that hang off the same register differ by a host constant (same idle time in every shot -> the
+    memory-noise probability is a host constant again and the channel fuses like any other)."""
+
+    __slots__ = ("reg", "off")
+
+    def __init__(self, reg, off=0.0):
+        self.reg = reg
+        self.off = float(off)
+
+    @property
+    def index(self):
+        return self.reg.index
+
+    def __repr__(self):
+        return f"TVal(r{self.reg.index}{self.off:+g})"
+
+
 class Timeline:
-    """Clock algebra over floats and :class:`TReg` values for one backend."""
+    """Clock algebra over floats and :class:`TVal` values for one backend."""
 
     def __init__(self, backend, nregs=None):
         self.be = backend
@@ -67,8 +88,11 @@ class Timeline:
     def _new(self):
         if not self._free:
             if not self._limbo:
-                raise RuntimeError("classical time registers exhausted: the circuit keeps more per-shot "
-                                   f"times alive than the backend's {self.nregs} registers")
+                raise RuntimeError(
+                    "classical time registers exhausted: the circuit keeps more per-shot times alive than the "
+                    f"backend's {self.nregs} registers" if self.nregs else
+                    "this backend has no classical register file: batched shots with sampled mid-circuit "
+                    "measurements need one (use host_branching=True, forced outcomes or per_shot_time=False)")
             # mid-span recycling: tell the backend not to hoist later classical ops over this point
             self.be.classical_fence()
             self.fence()
@@ -84,85 +108,111 @@ class Timeline:
             self._limbo.clear()
             self._free.sort()
 
-    def _emit(self, op, a=None, b=None, cbit=-1, imm=0.0):
+    def _emit(self, op, a=None, b=None, cbit=-1, imm=0.0, off=0.0):
         d = self._new()
         self.be.classical_op(op, d.index, a.index if a is not None else 0, b.index if b is not None else 0,
                              int(cbit), float(imm))
         self.ops += 1
-        return d
+        return TVal(d, off)
 
     def const(self, x):
         return self._emit(CL_CONST, imm=float(x))
 
     @staticmethod
     def is_reg(t):
-        return isinstance(t, TReg)
+        return isinstance(t, TVal)
+
+    @staticmethod
+    def same(a, b):
+        """True when a and b are the same time in every shot (known on the host)."""
+        if a is b:
+            return True
+        ra, rb = isinstance(a, TVal), isinstance(b, TVal)
+        if ra and rb:
+            return a.reg is b.reg and a.off == b.off
+        return (not ra) and (not rb) and a == b
+
+    def materialise(self, t):
+        """A register holding exactly ``t`` (offset 0), e.g. for reading it back."""
+        if isinstance(t, TVal):
+            return t if t.off == 0.0 else self._emit(CL_ADDI, t, imm=t.off)
+        return self.const(t)
 
     # ---- arithmetic ----------------------------------------------------------------------------
     def add(self, t, c):
         """t + c, c a host float."""
-        if not isinstance(t, TReg):
+        if not isinstance(t, TVal):
             return t + c
-        if c == 0:
-            return t
-        return self._emit(CL_ADDI, t, imm=c)
+        return t if c == 0 else TVal(t.reg, t.off + c)
 
     def sub(self, a, b):
-        """a - b."""
-        ra, rb = isinstance(a, TReg), isinstance(b, TReg)
+        """a - b: a host float when both hang off the same register."""
+        ra, rb = isinstance(a, TVal), isinstance(b, TVal)
         if not ra and not rb:
             return a - b
         if ra and rb:
-            return self._emit(CL_SUB, a, b)
+            if a.reg is b.reg:
+                return a.off - b.off
+            return self._emit(CL_SUB, a, b, imm=a.off - b.off)
         if ra:
-            return self._emit(CL_ADDI, a, imm=-b)
-        return self._emit(CL_RSUBI, b, imm=a)
+            return TVal(a.reg, a.off - b)
+        return self._emit(CL_RSUBI, b, imm=a - b.off)
 
     def max(self, *ts):
-        regs, c = [], None
+        vals, c = [], None
         for t in ts:
-            if isinstance(t, TReg):
-                if not any(t is r for r in regs):
-                    regs.append(t)
+            if isinstance(t, TVal):
+                for i, v in enumerate(vals):
+                    if v.reg is t.reg:
+                        if t.off > v.off:
+                            vals[i] = t
+                        break
+                else:
+                    vals.append(t)
             else:
                 c = t if c is None else max(c, t)
-        if not regs:
+        if not vals:
             return c
-        out = regs[0]
-        for r in regs[1:]:
-            out = self._emit(CL_MAX, out, r)
+        out = vals[0]
+        for v in vals[1:]:   # max(Ra + oa, Rb + ob) = oa + max(Ra, Rb + (ob - oa))
+            out = self._emit(CL_MAX, out, v, imm=v.off - out.off, off=out.off)
         if c is not None:
-            out = self._emit(CL_MAXI, out, imm=c)
+            out = self._emit(CL_MAXI, out, imm=c - out.off, off=out.off)
         return out
 
     def sel(self, pred, a, b):
         """``a`` in the shots whose classical bit ``pred`` is 1, ``b`` in the others; pred None = all."""
-        if pred is None or a is b:
+        if pred is None or self.same(a, b):
             return a
-        if not isinstance(a, TReg) and not isinstance(b, TReg) and a == b:
-            return a
-        ra = a if isinstance(a, TReg) else self.const(a)
-        rb = b if isinstance(b, TReg) else self.const(b)
-        return self._emit(CL_SEL, ra, rb, cbit=pred.index)
+        ra, rb = isinstance(a, TVal), isinstance(b, TVal)
+        if ra and rb and a.reg is b.reg:   # Rb + ob + (bit ? oa - ob : 0)
+            return self._emit(CL_ADDIF, b, cbit=pred.index, imm=a.off - b.off, off=b.off)
+        va = a if ra else self.const(a)
+        vb = b if rb else self.const(b)
+        return self._emit(CL_SEL, va, vb, cbit=pred.index, imm=va.off - vb.off, off=vb.off)
 
     def handshake(self, tc, ts, d, w):
         """Time at which the client fires the source trigger (``physical_layer.py:269-335``):
         tc + k w + 2 d with k = max(0, ceil((ts - tc - d) / w - 1e-12)) re-sends of HANDSHAKE_READY."""
-        if not isinstance(tc, TReg) and not isinstance(ts, TReg):
+        if not isinstance(tc, TVal) and not isinstance(ts, TVal):
             if w <= 0:
                 return max(tc + d, ts) + d
             k = max(0, math.ceil((ts - tc - d) / w - 1e-12))
             return tc + k * w + 2 * d
         if w <= 0:
             return self.add(self.max(self.add(tc, d), ts), d)
-        x = self.add(self.sub(ts, tc), -d)
+        x = self.sub(ts, tc)
+        if not isinstance(x, TVal):     # same register: the same number of re-sends in every shot
+            k = max(0, math.ceil((x - d) / w - 1e-12))
+            return self.add(tc, k * w + 2 * d)
+        x = self.materialise(self.add(x, -d))
         k = self._emit(CL_CEILQ, x, imm=w)
-        tcr = tc if isinstance(tc, TReg) else self.const(tc)
-        return self.add(self._emit(CL_FMAI, k, tcr, imm=w), 2 * d)
+        tcv = tc if isinstance(tc, TVal) else self.const(tc)
+        return self._emit(CL_FMAI, k, tcv, imm=w, off=tcv.off + 2 * d)
 
     def qexp(self, dt, rate_per_ns):
-        """q = 1 - exp(-max(0, dt) * rate) as a register (dt a register)."""
-        return self._emit(CL_QEXP, dt, imm=rate_per_ns)
+        """q = 1 - exp(-max(0, dt) * rate) as a register (dt a per-shot value)."""
+        return self._emit(CL_QEXP, self.materialise(dt), imm=rate_per_ns)
 
     # ---- classical bits --------------------------------------------------------------------------
     def bit_op(self, op, dst_bit, a_bit, b_bit=0):

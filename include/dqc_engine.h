@@ -143,9 +143,10 @@ int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, doubl
  * quantum_processors.py:868-877) inherits the difference.  A batch of shots therefore has one timeline
  * per outcome history.  Each shot owns dqe_n_time_regs() double registers next to its creg word;
  * dqe_classical_op appends one instruction (d = dst, a, b registers -- or creg bits for the B* ops):
- *    1 CONST d<-imm        2 ADDI d<-a+imm       3 ADD d<-a+b          4 SUB d<-a-b
- *    5 RSUBI d<-imm-a      6 MAX d<-max(a,b)     7 MAXI d<-max(a,imm)  8 SEL d<-(creg bit cbit ? a : b)
+ *    1 CONST d<-imm        2 ADDI d<-a+imm       3 ADD d<-a+b+imm      4 SUB d<-a-b+imm
+ *    5 RSUBI d<-imm-a      6 MAX d<-max(a,b+imm) 7 MAXI d<-max(a,imm)  8 SEL d<-(creg bit cbit ? a+imm : b)
  *    9 CEILQ d<-max(0, ceil(a/imm - 1e-12))      10 FMAI d<-a*imm+b    11 QEXP d<-1-exp(-max(0,a)*imm)
+ *   12 ADDIF d<-a+(creg bit cbit ? imm : 0)
  *   16 BAND  17 BANDN (a & ~b)  18 BOR  19 BNOT  20 BCOPY      (creg bit d <- f(bit a, bit b))
  * Instructions run per shot in queue order relative to each other and AFTER every measurement queued
  * before them, but the engine may run them EARLIER than quantum ops queued between that measurement and

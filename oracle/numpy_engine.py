@@ -278,17 +278,19 @@ class OracleEngine:
         elif op == 2:    # ADDI
             R[dst] = R[a] + imm
         elif op == 3:    # ADD
-            R[dst] = R[a] + R[b]
+            R[dst] = R[a] + R[b] + imm
         elif op == 4:    # SUB
-            R[dst] = R[a] - R[b]
+            R[dst] = R[a] - R[b] + imm
         elif op == 5:    # RSUBI
             R[dst] = imm - R[a]
         elif op == 6:    # MAX
-            R[dst] = np.maximum(R[a], R[b])
+            R[dst] = np.maximum(R[a], R[b] + imm)
         elif op == 7:    # MAXI
             R[dst] = np.maximum(R[a], imm)
         elif op == 8:    # SEL
-            R[dst] = np.where(self._bit(cbit), R[a], R[b])
+            R[dst] = np.where(self._bit(cbit), R[a] + imm, R[b])
+        elif op == 12:   # ADDIF
+            R[dst] = R[a] + np.where(self._bit(cbit), imm, 0.0)
         elif op == 9:    # CEILQ: handshake re-sends, physical_layer.py:269-335
             R[dst] = np.maximum(0.0, np.ceil(R[a] / imm - 1e-12))
         elif op == 10:   # FMAI

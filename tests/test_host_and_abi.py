@@ -300,8 +300,8 @@ def test_program_instructions_overlap_on_free_positions():
 
 @pytest.mark.parametrize("case,n,want", [
     # per-shot timelines (round 2): the clock arithmetic rides along as classical instructions
-    ("c2_grover5_3qpu_cat.json", 7, dict(passes=295, micro_ops=6452, api_ops=13890, merged_ops=776)),
-    ("c2_qft5_3qpu_cat.json", 7, dict(passes=40, micro_ops=982, api_ops=2133, merged_ops=125)),
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=292, micro_ops=4368, api_ops=6071, merged_ops=789)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=34, micro_ops=635, api_ops=919, merged_ops=135)),
     ("c4_qft16_mono.json.gz", 16, dict(passes=56, micro_ops=1182, api_ops=1564, merged_ops=521)),
 ])
 def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
@@ -341,7 +341,7 @@ def _per_shot_case(circuit, batch, seed, make=None):
     axes = ex.axes_of(ex.processing_qubits())
     rho = [be.reduced_dm(axes, s) for s in range(batch)]
     outcomes = be.read_outcomes()
-    end = be.read_time_reg(ex.end_time.index) if ex.T.is_reg(ex.end_time) else np.full(batch, ex.end_time)
+    end = ex.read_time(ex.end_time)
     singles = []
     for s in range(batch):
         b1 = OracleEngine("dm", 7, 1, seed=seed, shot_offset=s)
@@ -358,7 +358,7 @@ def test_batched_shots_follow_their_own_timeline(circuit, batch):
     assert len({tuple(outcomes[:, s]) for s in range(batch)}) > 1          # the shots really differ
     for s in range(batch):
         assert np.abs(rho[s] - singles[s][0]).max() < 1e-12
-        assert end[s] == singles[s][1]
+        assert abs(end[s] - singles[s][1]) < 1e-5      # ns: (register + host offset) vs plain float rounding
     assert len(set(end.tolist())) > 1                                      # ... and so do their timelines
     assert ex.T.peak <= 128
 
