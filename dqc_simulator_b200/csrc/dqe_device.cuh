@@ -35,7 +35,8 @@ enum OpType : int32_t {
   OP_DYN1 = 15,       // dm 1q channel whose strength q is read per shot from classical register `aux`
                       // (flags = DynKind): idle-time noise of a shot that follows its own simulated timeline
   OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
-                      // c_off = 0: run in order by thread 0; c_off = 1: independent (QEXP), thread i runs instr i
+                      // c_off = 0: clock arithmetic, run in order by lane 0 of warp 0; c_off = 1: QEXP evaluations,
+                      // independent of each other, lane i runs the i-th
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
                       // Philox draw -> outcome + renormalisation kept on chip; aux = axis bit, flags = creg bit + 1,
                       // lctrl = forced + 1, p[0] = flip probability, octrl = draw index
@@ -148,7 +149,8 @@ struct PassParams {
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
   int32_t nfree_cols, pad3;
-  int32_t uses_treg, writes_creg, writes_treg, pad4;   // planner: what the pass does to the classical state
+  int32_t uses_treg, writes_creg, writes_treg, nregs;  // planner: what the pass does to the classical state;
+                                                       // nregs (even) = registers [0, nregs) are in use
   uint64_t ntiles;
   int8_t ax_col[24], ax_row[24];   // dm: tile-local position of the column / row bit of each axis, -1 = outside
   // dm diagonal enumeration (probabilities), host-precomputed.  Free variable k = k-th axis (ascending)
@@ -430,7 +432,7 @@ __device__ __forceinline__ const ClInstr* cl_payload(const MicroOp& op) {
 // one instruction on the register file `R` (shared or global) and the classical word `cw`
 __device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& cw, const double* imm) {
   const double c = imm[in.imm];
-  switch (in.op) {
+  switch (in.op) {   // (register operands are read inside the cases: a / b are creg bits for the B* ops)
     case CL_CONST: R[in.dst] = c; break;
     case CL_ADDI: R[in.dst] = R[in.a] + c; break;
     case CL_ADD: R[in.dst] = R[in.a] + R[in.b] + c; break;
@@ -788,13 +790,13 @@ __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, cons
   shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
   const int k = op.nb;
   int digits[2] = {0, 0};
-  if (op.flags == 3) {          // depolarising of per-shot strength q = register lctrl (Pauli weights q / 4)
-    const double w = 0.25 * treg[op.lctrl], w0 = 1.0 - 3.0 * w;
+  if (op.flags == 3) {          // depolarising of per-shot strength q = register p[3] (Pauli weights q / 4)
+    const double w = 0.25 * treg[(int)op.p[3]], w0 = 1.0 - 3.0 * w;
     long long s = 0;
     if (!(u < w0) && w > 0.0) { s = 1 + (long long)floor((u - w0) / w); if (s > 3) s = 3; }
     digits[0] = (int)s;
   } else if (op.flags == 4) {   // dephasing of per-shot strength q: Z with probability q / 2
-    digits[0] = (u >= 1.0 - 0.5 * treg[op.lctrl]) ? 3 : 0;
+    digits[0] = (u >= 1.0 - 0.5 * treg[(int)op.p[3]]) ? 3 : 0;
   } else if (op.flags == 0) {
     digits[0] = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
   } else if (op.flags == 1) {
@@ -1181,7 +1183,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
-  __shared__ double s_treg[kTimeRegs];     // the shot's classical registers (simulated times, channel strengths)
+  __shared__ __align__(16) double s_treg[kTimeRegs];   // the shot's classical registers (simulated times, channel strengths)
   __shared__ unsigned long long s_cw;      // classical word after an OP_CLASSICAL run
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
@@ -1206,9 +1208,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     cw_first = pp.creg[shot0];
     if (threadIdx.x == 0) mr_first = pp.rec[shot0];   // outcome recorded by a preceding pass / k_finish_measure
   }
-  if (pp.treg && blk < pp.ntiles) {
+  if (pp.treg && !tma && blk < pp.ntiles) {   // (with TMA the registers ride on the tile's barrier, below)
     const double* tr = pp.treg + (blk >> pp.outer_bits) * (uint64_t)kTimeRegs;
-    for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) s_treg[i] = tr[i];
+    for (int i = threadIdx.x; i < pp.nregs; i += blockDim.x) s_treg[i] = tr[i];
   }
   if (pp.has_measure) cluster_arrive_relaxed();   // waited for in the first op_measure
   if (tma && threadIdx.x == 0) {
@@ -1218,7 +1220,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     if (blk < pp.ntiles) {
       // the micro-program and its constants ride on the first tile's barrier as two more bulk copies
       const uint32_t ops_bytes = (uint32_t)pp.nops * (uint32_t)sizeof(MicroOp), c_bytes = (uint32_t)pp.nconsts * 16u;
-      tma_expect(bar0_s, T * 16u + ops_bytes + c_bytes);
+      const uint32_t r_bytes = pp.treg ? (uint32_t)pp.nregs * 8u : 0u;   // the shot's classical registers
+      tma_expect(bar0_s, T * 16u + ops_bytes + c_bytes + r_bytes);
+      if (r_bytes)
+        tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_treg), pp.treg + (blk >> pp.outer_bits) * (uint64_t)kTimeRegs,
+                       r_bytes, bar0_s);
       if (tmx) {   // the whole tile in one tensor copy
         int32_t c[5];
         tm_coords(pp, blk, c);
@@ -1266,7 +1272,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       if (threadIdx.x == 0) mr0 = pp.rec[shot];
       if (pp.treg) {
         const double* tr = pp.treg + shot * (uint64_t)kTimeRegs;
-        for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) s_treg[i] = tr[i];
+        for (int i = threadIdx.x; i < pp.nregs; i += blockDim.x) s_treg[i] = tr[i];
       }
     }
 
@@ -1323,36 +1329,32 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       if (o < pp.nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if (op_type == OP_CLASSICAL) {
-        // a run of consecutive classical micro-ops: serial ones on thread 0 in order, then the independent
-        // ones (QEXP: one exp each) spread over the threads
-        // one span's block is [serial ...][independent ...]; a serial micro-op behind an independent one
-        // belongs to the next span (after a fence) and must wait for this block
+        // one span's block = [clock arithmetic ...][QEXP ...]: lane 0 of warp 0 runs the arithmetic in order (it
+        // is a dependency chain), then lane i evaluates the i-th QEXP; one block-wide barrier ends the block.
+        // A serial micro-op behind a QEXP one belongs to the next span (after a fence): next block.
         int run = 1;
         while (cur + run < pp.nops && s_ops[cur + run].type == OP_CLASSICAL &&
                !(s_ops[cur + run - 1].c_off != 0 && s_ops[cur + run].c_off == 0))
           ++run;
-        const double* imm = reinterpret_cast<const double*>(s_consts);
-        bool any_par = false;
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+          const double* imm = reinterpret_cast<const double*>(s_consts);
           uint64_t w = cw;
+          int slot = (int)threadIdx.x;
+          bool synced = false;
           for (int k = 0; k < run; ++k) {
             const MicroOp& c = s_ops[cur + k];
-            if (c.c_off) continue;
+            const int cnt = c.flags;
             const ClInstr* ci = cl_payload(c);
-            for (int i = 0; i < c.flags; ++i) cl_exec(ci[i], s_treg, w, imm);
+            if (!c.c_off) {
+              if (threadIdx.x == 0)
+                for (int i = 0; i < cnt; ++i) cl_exec(ci[i], s_treg, w, imm);
+            } else {
+              if (!synced) { __syncwarp(); synced = true; }
+              if (slot >= 0 && slot < cnt) { uint64_t w2 = 0; cl_exec(ci[slot], s_treg, w2, imm); }
+              slot -= cnt;
+            }
           }
-          s_cw = w;
-        }
-        for (int k = 0; k < run; ++k) any_par |= s_ops[cur + k].c_off != 0;
-        if (any_par) {
-          __syncthreads();
-          int slot = threadIdx.x;
-          for (int k = 0; k < run; ++k) {
-            const MicroOp& c = s_ops[cur + k];
-            if (!c.c_off) continue;
-            if (slot >= 0 && slot < c.flags) { uint64_t w = 0; cl_exec(cl_payload(c)[slot], s_treg, w, imm); }
-            slot -= c.flags;
-          }
+          if (threadIdx.x == 0) s_cw = w;
         }
         __syncthreads();
         cw = s_cw;
@@ -1421,7 +1423,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       if (pp.creg_out && threadIdx.x == 0) { pp.creg_out[shot] = cw; pp.rec_out[shot] = s_meas; }
       if (pp.treg_out) {
         double* tr = pp.treg_out + shot * (uint64_t)kTimeRegs;
-        for (int i = threadIdx.x; i < kTimeRegs; i += blockDim.x) tr[i] = s_treg[i];
+        for (int i = threadIdx.x; i < pp.nregs; i += blockDim.x) tr[i] = s_treg[i];
       }
     }
     if (pp.store_back) {

@@ -80,6 +80,7 @@ struct dqe_engine {
   MeasRec* rec_buf[2];
   double* treg_buf[2];      // allocated on the first classical instruction
   int cpar, tpar;
+  int max_reg;              // highest register index ever written: passes move registers [0, max_reg] only
   int8_t* olog;             // outcome log [draw][batch]
   int64_t olog_draws;
   bool state_dirty;         // the free-axis invariant may not hold (dqe_set_state): next reinit clears everything
@@ -976,9 +977,10 @@ struct Planner {
     uint64_t touched;
   };
 
-  // classical instructions of one span -> OP_CLASSICAL micro-ops: the serial ones in program order, then the
-  // independent QEXP evaluations (the interpreter spreads those over the CTA's threads).  Immediates go to
-  // the pass constant pool as packed doubles (equal values share a slot).
+  // classical instructions of one span -> OP_CLASSICAL micro-ops: the clock arithmetic in program order (it is a
+  // dependency chain: lane 0 of warp 0 runs it), then the QEXP evaluations (independent of each other, one exp
+  // each: lane i runs the i-th).  MicroOp.flags = instruction count, c_off = 1 for the QEXP micro-ops.
+  // Immediates go to the pass constant pool as packed doubles (equal values share a slot).
   void emit_classical(const std::vector<const HostOp*>& ops, size_t pcb) {
     std::vector<double> vals;
     std::vector<int> idx(ops.size());
@@ -1002,8 +1004,7 @@ struct Planner {
       };
       auto close_op = [&]() {
         if (n == 0) return;
-        // the payload overlays the fields behind the 16-byte dispatch header: set `aux` LAST would clobber
-        // instruction 1, so the serial / parallel marker rides in c_off (header) instead
+        // the payload overlays the fields behind the 16-byte dispatch header; the marker rides in c_off
         m.flags = n; m.c_off = par;
         dev_ops.push_back(m);
       };
@@ -1532,6 +1533,7 @@ int do_flush(dqe_t* h) {
       P.pp.creg_out = cur_creg(h); P.pp.rec_out = cur_rec(h);
     }
     if (P.pp.uses_treg) {
+      P.pp.nregs = std::min(kTimeRegs, (h->max_reg + 2) & ~1);
       P.pp.treg = h->treg_buf[h->tpar];
       if (P.pp.writes_treg) { h->tpar ^= 1; P.pp.treg_out = h->treg_buf[h->tpar]; }
     }
@@ -1645,7 +1647,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->formalism = formalism; h->nmax = max_qubits; h->P = P; h->device = device; h->batch = batch;
   h->own_stream = false; h->own_state = false; h->state = nullptr;
   h->creg_buf[0] = h->creg_buf[1] = nullptr; h->rec_buf[0] = h->rec_buf[1] = nullptr;
-  h->treg_buf[0] = h->treg_buf[1] = nullptr; h->cpar = 0; h->tpar = 0; h->olog = nullptr; h->olog_draws = 0;
+  h->treg_buf[0] = h->treg_buf[1] = nullptr; h->cpar = 0; h->tpar = 0; h->max_reg = 0; h->olog = nullptr; h->olog_draws = 0;
   h->state_dirty = false;
   h->partials = nullptr; h->partials_cap = 0; h->d_ops = nullptr; h->d_ops_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
@@ -2053,6 +2055,7 @@ int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, doub
   o.ci.op = (uint8_t)opcode; o.ci.dst = (uint8_t)dst; o.ci.a = (uint8_t)a; o.ci.b = (uint8_t)b;
   o.ci.cbit = (int8_t)(uses_bit ? cbit : 0); o.ci.pad = 0; o.ci.imm = 0;
   o.imm = imm;
+  if (regop) h->max_reg = std::max(h->max_reg, dst);
   h->queue.push_back(o);
   h->stats[4]++;
   return 0;
@@ -2087,7 +2090,7 @@ int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg) {
   o.m.nb = 1; o.m.b[0] = (uint8_t)axis; o.need = 1ull << axis;
   o.m.flags = kind == DYN_DEPOL ? 3 : 4;
   o.m.aux = (int32_t)h->draw++;
-  o.m.lctrl = (uint32_t)reg;
+  o.m.p[3] = (double)reg;   // (lctrl is rebuilt from the control masks when the op is localised)
   push(h, o);
   return 0;
 }

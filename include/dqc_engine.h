@@ -152,7 +152,10 @@ int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, doubl
  * before them, but the engine may run them EARLIER than quantum ops queued between that measurement and
  * them (it hoists them to just behind the measurement so that the quantum ops still fuse).  Contract: a
  * register / bit must not be overwritten while an op queued earlier since the last measurement (or
- * dqe_classical_fence) still reads it.  Registers are undefined until written; dqe_reinit keeps them.
+ * dqe_classical_fence) still reads it, and the result of a QEXP is read by channels only
+ * (dqe_enqueue_dyn_channel), never by another classical instruction: the engine evaluates the QEXPs of
+ * a span after its other instructions, spread over the threads of the CTA.  Registers are undefined until
+ * written; dqe_reinit keeps them.
  * dqe_enqueue_dyn_channel: one-qubit channel whose strength q is the shot's register `reg`:
  *   kind 0 depolarising (1-q) rho + q I/2, 1 dephasing (off-diagonals x (1-q)), 2 amplitude damping
  *   (gamma = q; dm only).  dm: analytic; ket: one branch sampled per shot. */

@@ -183,9 +183,10 @@ def random_program(b, rng, steps, formalism, check_every=0, classical=False):
             else:
                 b.classical_op(tl.CL_RSUBI, t2, t1, imm=5e6)
             cs.times.append(t2)
-            dt, q = cs.fresh_reg(), cs.fresh_reg()
+            dt = cs.fresh_reg()
             b.classical_op(tl.CL_SUB, dt, t2, t0)
             cs.times.append(dt)
+            q = cs.fresh_reg()     # QEXP results feed channels only (dqe_classical_op contract)
             b.classical_op(tl.CL_QEXP, q, dt, imm=float(rng.uniform(1e-8, 3e-7)))
             cs.qs.append(q)
             cs.read_regs.update((t0, t1, t2, dt))
