@@ -72,6 +72,8 @@ enum ClOp : uint8_t {
   CL_FMAI = 10,   // d <- a * imm + b
   CL_QEXP = 11,   // d <- 1 - exp(-max(0, a) * imm)       (noise_models.py:248-253)
   CL_ADDIF = 12,  // d <- a + (creg bit `cbit` ? imm : 0)
+  CL_QEXP2 = 13,  // d <- 1 - exp(-max(0, a - b + imm) * imm2): idle time and strength in one instruction; a / b = 255
+                  // stand for 0, imm2 is a second constant-pool index carried in the (cbit, pad) bytes
   CL_BAND = 16,   // creg bit d <- bit a & bit b
   CL_BANDN = 17,  // d <- a & ~b
   CL_BOR = 18,
@@ -429,9 +431,22 @@ __device__ __forceinline__ void op_xpat(double2* tile, uint32_t T, const MicroOp
 __device__ __forceinline__ const ClInstr* cl_payload(const MicroOp& op) {
   return reinterpret_cast<const ClInstr*>(reinterpret_cast<const char*>(&op) + 16);
 }
-// one instruction on the register file `R` (shared or global) and the classical word `cw`
-__device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& cw, const double* imm) {
-  const double c = imm[in.imm];
+// 1 - exp(-x) for x >= 0.  Idle-time noise lives at x ~ 1e-6 .. 1e-2, where nine Taylor terms are exact to the
+// last bit of 1 - exp(-x) evaluated in double (what the reference's p = 1 - exp(-dt * 1e-9 * rate) is,
+// noise_models.py:248-253) and cost a quarter of exp()'s latency on the one lane that computes it.
+__device__ __forceinline__ double one_minus_exp_neg(double x) {
+  if (x < 0.03125) {
+    double p = -1.0 / 362880.0;
+    p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, -1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0);
+    p = fma(p, x, -1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, -1.0 / 6.0);
+    p = fma(p, x, 0.5);
+    return x - x * x * p;   // x - x^2/2 + x^3/6 - ...
+  }
+  return 1.0 - exp(-x);
+}
+
+// one instruction on the register file `R` (shared or global) and the classical word `cw`; c = its immediate
+__device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double* R, uint64_t& cw, const double* imm) {
   switch (in.op) {   // (register operands are read inside the cases: a / b are creg bits for the B* ops)
     case CL_CONST: R[in.dst] = c; break;
     case CL_ADDI: R[in.dst] = R[in.a] + c; break;
@@ -444,7 +459,13 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& c
     case CL_ADDIF: R[in.dst] = R[in.a] + (((cw >> in.cbit) & 1ull) ? c : 0.0); break;
     case CL_CEILQ: R[in.dst] = fmax(0.0, ceil(R[in.a] / c - 1e-12)); break;
     case CL_FMAI: R[in.dst] = __dadd_rn(__dmul_rn(R[in.a], c), R[in.b]); break;   // like the host: no contraction
-    case CL_QEXP: R[in.dst] = 1.0 - exp(-fmax(0.0, R[in.a]) * c); break;
+    case CL_QEXP: R[in.dst] = one_minus_exp_neg(fmax(0.0, R[in.a]) * c); break;
+    case CL_QEXP2: {
+      const double ra = in.a == 255 ? 0.0 : R[in.a], rb = in.b == 255 ? 0.0 : R[in.b];
+      const double rate = imm[(uint32_t)(uint8_t)in.cbit | ((uint32_t)in.pad << 8)];
+      R[in.dst] = one_minus_exp_neg(fmax(0.0, ra - rb + c) * rate);
+      break;
+    }
     case CL_BAND: case CL_BANDN: case CL_BOR: case CL_BNOT: case CL_BCOPY: {
       const uint64_t x = (cw >> in.a) & 1ull, y = (cw >> in.b) & 1ull;
       const uint64_t v = in.op == CL_BAND ? (x & y) : in.op == CL_BANDN ? (x & (y ^ 1ull)) : in.op == CL_BOR ? (x | y)
@@ -453,6 +474,19 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, double* R, uint64_t& c
       break;
     }
     default: break;
+  }
+}
+// a run of instructions in order on one thread; the fetch of instruction i + 1 (and of its immediate) is issued
+// before instruction i executes, so the chain pays for the register-file round trips only
+__device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt, double* R, uint64_t& cw, const double* imm) {
+  if (cnt <= 0) return;
+  ClInstr nxt = ci[0];
+  double cn = imm[nxt.imm];
+  for (int i = 0; i < cnt; ++i) {
+    const ClInstr in = nxt;
+    const double c = cn;
+    if (i + 1 < cnt) { nxt = ci[i + 1]; cn = imm[nxt.imm]; }
+    cl_exec(in, c, R, cw, imm);
   }
 }
 
@@ -1346,11 +1380,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             const int cnt = c.flags;
             const ClInstr* ci = cl_payload(c);
             if (!c.c_off) {
-              if (threadIdx.x == 0)
-                for (int i = 0; i < cnt; ++i) cl_exec(ci[i], s_treg, w, imm);
+              if (threadIdx.x == 0) cl_run(ci, cnt, s_treg, w, imm);
             } else {
               if (!synced) { __syncwarp(); synced = true; }
-              if (slot >= 0 && slot < cnt) { uint64_t w2 = 0; cl_exec(ci[slot], s_treg, w2, imm); }
+              if (slot >= 0 && slot < cnt) { uint64_t w2 = 0; cl_exec(ci[slot], imm[ci[slot].imm], s_treg, w2, imm); }
               slot -= cnt;
             }
           }
@@ -1571,8 +1604,7 @@ __global__ void __launch_bounds__(128) k_classical(const ClassicalParams cp) {
   double* R = cp.treg + (uint64_t)shot * kTimeRegs;
   for (int k = 0; k < cp.nops; ++k) {
     const MicroOp& c = cp.ops[k];
-    const ClInstr* ci = cl_payload(c);
-    for (int i = 0; i < c.flags; ++i) cl_exec(ci[i], R, cw, cp.imm);
+    cl_run(cl_payload(c), c.flags, R, cw, cp.imm);
   }
   if (cw != cw0) cp.creg[shot] = cw;
 }

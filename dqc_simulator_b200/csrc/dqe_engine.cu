@@ -41,7 +41,7 @@ struct HostOp {
   int kind;            // 0 = micro-op, 1 = measurement finish (pass barrier), 2 = classical instruction (ci, imm),
                        // 3 = classical fence (later classical instructions are not hoisted over it)
   ClInstr ci;
-  double imm;
+  double imm, imm2;    // imm2: rate of a QEXP2
   MicroOp m;           // bit fields hold PHYSICAL positions until the planner localises them
   uint64_t pctrl, pctrl2;  // physical control masks
   uint64_t need;       // physical bits that must lie inside the tile
@@ -983,13 +983,16 @@ struct Planner {
   // Immediates go to the pass constant pool as packed doubles (equal values share a slot).
   void emit_classical(const std::vector<const HostOp*>& ops, size_t pcb) {
     std::vector<double> vals;
-    std::vector<int> idx(ops.size());
+    std::vector<int> idx(ops.size()), idx2(ops.size(), 0);
+    auto slot_of = [&](double v) {
+      for (size_t j = 0; j < vals.size(); ++j)
+        if (memcmp(&vals[j], &v, sizeof(double)) == 0) return (int)j;
+      vals.push_back(v);
+      return (int)vals.size() - 1;
+    };
     for (size_t i = 0; i < ops.size(); ++i) {
-      int f = -1;
-      for (size_t j = 0; j < vals.size() && f < 0; ++j)
-        if (memcmp(&vals[j], &ops[i]->imm, sizeof(double)) == 0) f = (int)j;
-      if (f < 0) { f = (int)vals.size(); vals.push_back(ops[i]->imm); }
-      idx[i] = f;
+      idx[i] = slot_of(ops[i]->imm);
+      if (ops[i]->ci.op == CL_QEXP2) idx2[i] = slot_of(ops[i]->imm2);
     }
     const int base = (int)(dev_consts.size() - pcb) * 2;
     for (size_t j = 0; j < vals.size(); j += 2)
@@ -1011,9 +1014,11 @@ struct Planner {
       open_op();
       for (size_t i = 0; i < ops.size(); ++i) {
         const HostOp* ho = ops[i];
-        if ((ho->ci.op == CL_QEXP) != (par == 1)) continue;
+        const bool is_par = ho->ci.op == CL_QEXP || ho->ci.op == CL_QEXP2;
+        if (is_par != (par == 1)) continue;
         ClInstr ci = ho->ci;
         ci.imm = (uint16_t)(base + idx[i]);
+        if (ci.op == CL_QEXP2) { const int i2 = base + idx2[i]; ci.cbit = (int8_t)(i2 & 0xff); ci.pad = (uint8_t)(i2 >> 8); }
         memcpy(reinterpret_cast<char*>(&m) + 16 + 8 * n, &ci, sizeof(ci));
         if (++n == kClPerOp) { close_op(); open_op(); }
       }
@@ -1333,7 +1338,7 @@ struct Planner {
         op_slots = 0;
         if (op.kind == 2) {
           ++ncl;
-          if (ncl % 2 == 0) op_consts = 1;
+          if (ncl % 2 == 0 || op.ci.op == CL_QEXP2) op_consts = 1;
           if (ncl % 8 == 1) op_slots = 1;
         }
       } else {
@@ -2056,6 +2061,23 @@ int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, doub
   o.ci.cbit = (int8_t)(uses_bit ? cbit : 0); o.ci.pad = 0; o.ci.imm = 0;
   o.imm = imm;
   if (regop) h->max_reg = std::max(h->max_reg, dst);
+  h->queue.push_back(o);
+  h->stats[4]++;
+  return 0;
+}
+
+int dqe_classical_qexp2(dqe_t* h, int dst, int a, int b, double offset, double rate) {
+  if (int rc = check_ready(h)) return rc;
+  auto bad = [](int r) { return r != 255 && (r < 0 || r >= kTimeRegs); };
+  if (dst < 0 || dst >= kTimeRegs || bad(a) || bad(b)) return fail(h, DQE_EINVAL, "classical_qexp2: register out of range");
+  if (int rc = ensure_tregs(h)) return rc;
+  HostOp o = blank(h, 0);
+  o.kind = 2;
+  o.m.pred_bit = -1;
+  o.ci.op = (uint8_t)CL_QEXP2; o.ci.dst = (uint8_t)dst; o.ci.a = (uint8_t)a; o.ci.b = (uint8_t)b;
+  o.ci.cbit = 0; o.ci.pad = 0; o.ci.imm = 0;
+  o.imm = offset; o.imm2 = rate;
+  h->max_reg = std::max(h->max_reg, dst);
   h->queue.push_back(o);
   h->stats[4]++;
   return 0;

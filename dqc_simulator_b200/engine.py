@@ -55,6 +55,8 @@ ABI = {
     "dqe_n_time_regs": (ctypes.c_int, []),
     "dqe_classical_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_double]),
+    "dqe_classical_qexp2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                           ctypes.c_double]),
     "dqe_classical_fence": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_enqueue_dyn_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dqe_read_time_reg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
@@ -256,6 +258,10 @@ class Engine:
     def classical_op(self, opcode, dst, a=0, b=0, cbit=-1, imm=0.0):
         """One instruction of the per-shot register machine (opcodes: ``timeline.CL_*``)."""
         self._ck(self._lib.dqe_classical_op(self._h, int(opcode), int(dst), int(a), int(b), int(cbit), float(imm)))
+
+    def classical_qexp2(self, dst, a, b, offset, rate):
+        """dst <- 1 - exp(-max(0, R[a] - R[b] + offset) * rate); a / b = 255 stand for 0."""
+        self._ck(self._lib.dqe_classical_qexp2(self._h, int(dst), int(a), int(b), float(offset), float(rate)))
 
     def classical_fence(self):
         self._ck(self._lib.dqe_classical_fence(self._h))

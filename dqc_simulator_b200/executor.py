@@ -175,12 +175,12 @@ class QPU:
                  (tlm.DYN_AMPDAMP, sp.mem_amp_damp_rate))
         if not any(r > 0 for _, r in rates):
             return
-        dt = T.sub(now, last)        # a host float whenever the idle time is the same in every shot
-        if T.is_reg(dt):
-            for kind, rate in rates:
+        if (T.is_reg(now) or T.is_reg(last)) and not (T.is_reg(now) and T.is_reg(last) and now.reg is last.reg):
+            for kind, rate in rates:    # the idle time differs from shot to shot
                 if rate > 0:
-                    be.dyn_channel(ax, kind, T.qexp(dt, 1e-9 * rate).index)
+                    be.dyn_channel(ax, kind, T.qexp_between(now, last, 1e-9 * rate).index)
             return
+        dt = T.sub(now, last)           # a host float: the same idle time in every shot
         if dt <= 0:
             return
         rate = sp.mem_rate(pos)

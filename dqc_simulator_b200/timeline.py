@@ -214,6 +214,16 @@ class Timeline:
         """q = 1 - exp(-max(0, dt) * rate) as a register (dt a per-shot value)."""
         return self._emit(CL_QEXP, self.materialise(dt), imm=rate_per_ns)
 
+    def qexp_between(self, now, last, rate_per_ns):
+        """q = 1 - exp(-max(0, now - last) * rate) as a register, in ONE instruction (at least one of the two
+        times is per shot and they hang off different registers)."""
+        ra, rb = isinstance(now, TVal), isinstance(last, TVal)
+        off = (now.off if ra else now) - (last.off if rb else last)
+        d = self._new()
+        self.be.classical_qexp2(d.index, now.index if ra else 255, last.index if rb else 255, off, rate_per_ns)
+        self.ops += 1
+        return TVal(d, 0.0)
+
     # ---- classical bits --------------------------------------------------------------------------
     def bit_op(self, op, dst_bit, a_bit, b_bit=0):
         self.be.classical_op(op, int(dst_bit), int(a_bit), int(b_bit), -1, 0.0)

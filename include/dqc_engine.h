@@ -161,6 +161,9 @@ int dqe_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, doubl
  *   (gamma = q; dm only).  dm: analytic; ket: one branch sampled per shot. */
 int dqe_n_time_regs(void);
 int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, double imm);
+/* d <- 1 - exp(-max(0, a - b + offset) * rate): the strength of an idle-time channel straight from the two
+ * times it lies between (a / b = 255 stand for 0).  Like QEXP, its result is read by channels only. */
+int dqe_classical_qexp2(dqe_t* h, int dst, int a, int b, double offset, double rate);
 int dqe_classical_fence(dqe_t* h);
 int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg);
 int dqe_read_time_reg(dqe_t* h, int reg, double* out /*batch*/);

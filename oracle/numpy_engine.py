@@ -310,6 +310,11 @@ class OracleEngine:
         else:
             raise ValueError(f"unknown classical opcode {op}")
 
+    def classical_qexp2(self, dst, a, b, offset, rate):
+        ra = 0.0 if a == 255 else self.treg[a]
+        rb = 0.0 if b == 255 else self.treg[b]
+        self.treg[dst] = 1.0 - np.exp(-np.maximum(0.0, ra - rb + offset) * rate)
+
     def classical_fence(self):
         pass
 

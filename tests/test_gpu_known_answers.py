@@ -184,3 +184,23 @@ def test_data_collector_on_a_shot_batch():
     df = experiment.get_data_collector(ex, [(2, "node_0"), (2, "node_1")], rc.B00).dataframe
     assert len(df) == 5 and list(df.columns) == ["time_stamp", "entity_name", "fidelity"]
     assert np.abs(df["fidelity"].to_numpy() - 0.8921630426886507).max() < 1e-13
+
+
+@pytest.mark.parametrize("circuit,batch", [("ghz", 64), ("qft", 64), ("grover", 64)])
+def test_batched_shots_follow_their_own_timeline_on_the_engine(circuit, batch):
+    """a sampled batch (>= 64 shots) of the C2 circuits on the CUDA engine matches, shot by
+    shot at 1e-10 in rho, single-trajectory runs forced to the same outcomes (the host then branches exactly like
+    the reference: dqc_control.py:347-348, 385-403, 497-503; physical_layer.py:269-335), and the simulated end
+    times agree: the batch no longer shares one expected timeline."""
+    from test_host_and_abi import _per_shot_case
+
+    from dqc_simulator_b200.engine import Engine
+
+    rho, end, singles, outcomes, ex = _per_shot_case(circuit, batch, seed=17,
+                                                     make=lambda f, n, b, seed: Engine(f, n, b, seed=seed),
+                                                     check=8 if circuit == "grover" else 24)
+    assert len({tuple(outcomes[:, s]) for s in range(batch)}) > batch // 4
+    for s, (r1, e1) in singles.items():
+        assert np.abs(rho[s] - r1).max() < 1e-10
+        assert abs(end[s] - e1) < 1e-5
+    assert len(set(end.tolist())) > 1

@@ -300,8 +300,8 @@ def test_program_instructions_overlap_on_free_positions():
 
 @pytest.mark.parametrize("case,n,want", [
     # per-shot timelines (round 2): the clock arithmetic rides along as classical instructions
-    ("c2_grover5_3qpu_cat.json", 7, dict(passes=292, micro_ops=4368, api_ops=6071, merged_ops=789)),
-    ("c2_qft5_3qpu_cat.json", 7, dict(passes=34, micro_ops=635, api_ops=919, merged_ops=135)),
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=292, micro_ops=4209, api_ops=5313, merged_ops=789)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=34, micro_ops=622, api_ops=812, merged_ops=135)),
     ("c4_qft16_mono.json.gz", 16, dict(passes=56, micro_ops=1182, api_ops=1564, merged_ops=521)),
 ])
 def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
@@ -325,7 +325,7 @@ def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
 
 
 # ---- per-shot simulated timelines -------------------------------------------------
-def _per_shot_case(circuit, batch, seed, make=None):
+def _per_shot_case(circuit, batch, seed, make=None, check=None):
     """A sampled batch in which every shot follows its own timeline, and the same shots re-run one at a
     time with the outcomes forced (the host then knows every outcome and branches exactly like the
     reference does: dqc_control.py:347-348, 385-403, 497-503; physical_layer.py:269-335)."""
@@ -342,11 +342,11 @@ def _per_shot_case(circuit, batch, seed, make=None):
     rho = [be.reduced_dm(axes, s) for s in range(batch)]
     outcomes = be.read_outcomes()
     end = ex.read_time(ex.end_time)
-    singles = []
-    for s in range(batch):
+    singles = {}
+    for s in range(batch if check is None else check):
         b1 = OracleEngine("dm", 7, 1, seed=seed, shot_offset=s)
         e1 = executor.DQCExecutor(ops, dqc, b1, forced_outcomes=list(outcomes[:, s])).run()
-        singles.append((b1.reduced_dm(e1.axes_of(e1.processing_qubits()), 0), e1.end_time))
+        singles[s] = (b1.reduced_dm(e1.axes_of(e1.processing_qubits()), 0), e1.end_time)
     return rho, end, singles, outcomes, ex
 
 
