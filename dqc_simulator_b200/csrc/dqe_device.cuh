@@ -35,8 +35,7 @@ enum OpType : int32_t {
   OP_DYN1 = 15,       // dm 1q channel whose strength q is read per shot from classical register `aux`
                       // (flags = DynKind): idle-time noise of a shot that follows its own simulated timeline
   OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
-                      // c_off = 0: clock arithmetic, run in order by lane 0 of warp 0; c_off = 1: QEXP evaluations,
-                      // independent of each other, lane i runs the i-th
+                      // run redundantly by every thread of the CTA (identical values: no barrier needed)
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
                       // Philox draw -> outcome + renormalisation kept on chip; aux = axis bit, flags = creg bit + 1,
                       // lctrl = forced + 1, p[0] = flip probability, octrl = draw index
@@ -1218,7 +1217,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
   __shared__ __align__(16) double s_treg[kTimeRegs];   // the shot's classical registers (simulated times, channel strengths)
-  __shared__ unsigned long long s_cw;      // classical word after an OP_CLASSICAL run
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
@@ -1357,42 +1355,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     for (int o = 0; o < pp.nops;) {
       const int cur = o;
       const MicroOp& op = s_ops[cur];
-      const int op_type = hdr.x, op_pred = hdr.y;
+      const int op_type = hdr.x, op_pred = hdr.y, op_flags = hdr.z, hdr_coff = hdr.w;
       const double2* cs = s_consts + hdr.w;
       o = cur + 1 + (op_type == OP_GROUP ? hdr.w : 0);
       if (o < pp.nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if (op_type == OP_CLASSICAL) {
-        // one span's block = [clock arithmetic ...][QEXP ...]: lane 0 of warp 0 runs the arithmetic in order (it
-        // is a dependency chain), then lane i evaluates the i-th QEXP; one block-wide barrier ends the block.
-        // A serial micro-op behind a QEXP one belongs to the next span (after a fence): next block.
-        int run = 1;
-        while (cur + run < pp.nops && s_ops[cur + run].type == OP_CLASSICAL &&
-               !(s_ops[cur + run - 1].c_off != 0 && s_ops[cur + run].c_off == 0))
-          ++run;
-        if (threadIdx.x < 32) {
-          const double* imm = reinterpret_cast<const double*>(s_consts);
-          uint64_t w = cw;
-          int slot = (int)threadIdx.x;
-          bool synced = false;
-          for (int k = 0; k < run; ++k) {
-            const MicroOp& c = s_ops[cur + k];
-            const int cnt = c.flags;
-            const ClInstr* ci = cl_payload(c);
-            if (!c.c_off) {
-              if (threadIdx.x == 0) cl_run(ci, cnt, s_treg, w, imm);
-            } else {
-              if (!synced) { __syncwarp(); synced = true; }
-              if (slot >= 0 && slot < cnt) { uint64_t w2 = 0; cl_exec(ci[slot], imm[ci[slot].imm], s_treg, w2, imm); }
-              slot -= cnt;
-            }
-          }
-          if (threadIdx.x == 0) s_cw = w;
-        }
-        __syncthreads();
-        cw = s_cw;
-        o = cur + run;
-        if (o < pp.nops) hdr = op_header(&s_ops[o]);
+        // EVERY thread runs the instructions itself, on its own copy of the classical word and on the shared
+        // register file: all threads store identical values, and a thread only ever depends on what it has
+        // stored itself -- so the block needs no barrier at all (the barrier that ended the previous micro-op
+        // already ordered it behind every earlier reader of the registers it overwrites).
+        if (hdr_coff & 2) __syncthreads();   // block right behind another span's block (fence only in between)
+        cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts));
         continue;
       }
       if constexpr (FORM == 0) {   // ---- ket micro-ops

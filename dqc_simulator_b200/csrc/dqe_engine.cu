@@ -997,6 +997,9 @@ struct Planner {
     const int base = (int)(dev_consts.size() - pcb) * 2;
     for (size_t j = 0; j < vals.size(); j += 2)
       dev_consts.push_back(make_double2(vals[j], j + 1 < vals.size() ? vals[j + 1] : 0.0));
+    // a block right behind another block (two spans separated by a fence only): the threads must meet in
+    // between, or a fast warp's writes of this block race with a slow warp's writes of the previous one
+    bool need_barrier = !dev_ops.empty() && dev_ops.back().type == OP_CLASSICAL;
     for (int par = 0; par < 2; ++par) {
       MicroOp m;
       int n = 0;
@@ -1008,7 +1011,8 @@ struct Planner {
       auto close_op = [&]() {
         if (n == 0) return;
         // the payload overlays the fields behind the 16-byte dispatch header; the marker rides in c_off
-        m.flags = n; m.c_off = par;
+        m.flags = n; m.c_off = par | (need_barrier ? 2 : 0);
+        need_barrier = false;
         dev_ops.push_back(m);
       };
       open_op();

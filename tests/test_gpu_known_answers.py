@@ -199,7 +199,7 @@ def test_batched_shots_follow_their_own_timeline_on_the_engine(circuit, batch):
     rho, end, singles, outcomes, ex = _per_shot_case(circuit, batch, seed=17,
                                                      make=lambda f, n, b, seed: Engine(f, n, b, seed=seed),
                                                      check=8 if circuit == "grover" else 24)
-    assert len({tuple(outcomes[:, s]) for s in range(batch)}) > batch // 4
+    assert len({tuple(outcomes[:, s]) for s in range(batch)}) > min(batch // 4, 2 ** outcomes.shape[0] // 2)
     for s, (r1, e1) in singles.items():
         assert np.abs(rho[s] - r1).max() < 1e-10
         assert abs(end[s] - e1) < 1e-5
