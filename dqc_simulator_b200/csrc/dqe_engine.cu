@@ -86,6 +86,8 @@ struct dqe_engine {
   bool state_dirty;         // the free-axis invariant may not hold (dqe_set_state): next reinit clears everything
   double* partials;
   size_t partials_cap;
+  void* scratch;            // read-out staging (creg bits, histograms, reduced matrices, fidelities): reused
+  size_t scratch_cap;
   MicroOp* d_ops;
   size_t d_ops_cap;
   double2* d_consts;
@@ -1437,6 +1439,9 @@ void build_tensor_map(dqe_t* h, PassParams& pp) {
   pp.prefetch_dist = h->prefetch >= 0 ? h->prefetch : h->num_sms * (h->threads <= 64 ? 8 : 4);
 }
 
+struct Planner;
+int launch_passes(dqe_t* h, Planner& pl);
+
 int ensure_partials(dqe_t* h, size_t n) {
   if (n <= h->partials_cap) return 0;
   if (h->partials) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->partials)); h->partials = nullptr; }
@@ -1510,7 +1515,29 @@ int do_flush(dqe_t* h) {
   for (const PlannedPass& P : pl.passes)
     if (!P.is_finish) need_part = std::max<size_t>(need_part, (size_t)P.pp.ntiles * 2);
   if (int rc = ensure_partials(h, need_part)) return rc;
+  // validate every pass before the first launch: a failure must not leave half of the queue applied
+  for (const PlannedPass& P : pl.passes) {
+    if (P.is_finish) continue;
+    if (P.pp.ntiles > (1ull << 40)) { h->queue.clear(); h->cpool.clear(); return fail(h, DQE_EUNSUPPORTED, "too many tiles"); }
+    if (P.pp.uses_treg && !h->treg_buf[0]) {
+      h->queue.clear(); h->cpool.clear();
+      return fail(h, DQE_EINVAL, "classical registers used before any classical instruction");
+    }
+  }
+  const int rc_launch = launch_passes(h, pl);
+  // whatever happened, the queued ops are gone: either they ran, or a CUDA error made the handle unusable
+  // (sticky); re-applying ops that already ran on the next flush would be worse than either
+  h->queue.clear();
+  h->cpool.clear();
+  h->planned_live = phys_live(h, h->live_axes);
+  if (rc_launch) return rc_launch;
+  if (getenv("DQE_DEBUG"))
+    fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
+            (long long)h->tmap_used, (long long)h->tmap_refused);
+  return 0;
+}
 
+int launch_passes(dqe_t* h, Planner& pl) {
   for (PlannedPass& P : pl.passes) {
     if (P.is_finish) {
       P.fp.partials = h->partials; P.fp.rec = cur_rec(h); P.fp.creg = cur_creg(h);
@@ -1520,7 +1547,6 @@ int do_flush(dqe_t* h) {
       h->stats[2]++; h->stats[5]++;
       continue;
     }
-    if (P.pp.uses_treg && !h->treg_buf[0]) return fail(h, DQE_EINVAL, "classical registers used before any classical instruction");
     if (P.classical_only) {
       if (P.pp.nops == 0) continue;
       ClassicalParams cp;
@@ -1532,7 +1558,6 @@ int do_flush(dqe_t* h) {
       h->stats[2]++;
       continue;
     }
-    if (P.pp.ntiles > (1ull << 40)) return fail(h, DQE_EUNSUPPORTED, "too many tiles");
     P.pp.state = h->state; P.pp.partials = h->partials;
     P.pp.creg = cur_creg(h); P.pp.rec = cur_rec(h);
     P.pp.batch = h->batch;
@@ -1594,12 +1619,16 @@ int do_flush(dqe_t* h) {
     h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
   }
   CK(cudaGetLastError());
-  if (getenv("DQE_DEBUG"))
-    fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
-            (long long)h->tmap_used, (long long)h->tmap_refused);
-  h->queue.clear();
-  h->cpool.clear();
-  h->planned_live = phys_live(h, h->live_axes);
+  return 0;
+}
+
+// read-out staging buffer kept on the handle (no cudaMalloc / cudaFree per read, nothing to leak on an error path)
+int ensure_scratch(dqe_t* h, size_t bytes) {
+  if (bytes <= h->scratch_cap) return 0;
+  if (h->scratch) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->scratch)); h->scratch = nullptr; h->scratch_cap = 0; }
+  const size_t cap = std::max<size_t>(bytes, 1 << 16);
+  CK(cudaMalloc(&h->scratch, cap));
+  h->scratch_cap = cap;
   return 0;
 }
 
@@ -1659,6 +1688,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->treg_buf[0] = h->treg_buf[1] = nullptr; h->cpar = 0; h->tpar = 0; h->max_reg = 0; h->olog = nullptr; h->olog_draws = 0;
   h->state_dirty = false;
   h->partials = nullptr; h->partials_cap = 0; h->d_ops = nullptr; h->d_ops_cap = 0;
+  h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
@@ -1740,6 +1770,7 @@ int dqe_destroy(dqe_t* h) {
   }
   if (h->olog) cudaFree(h->olog);
   if (h->partials) cudaFree(h->partials);
+  if (h->scratch) cudaFree(h->scratch);
   if (h->d_ops) cudaFree(h->d_ops);
   if (h->d_consts) cudaFree(h->d_consts);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -2161,13 +2192,12 @@ int dqe_read_creg(dqe_t* h, int bit, int8_t* out) {
   if (int rc = do_flush(h)) return rc;
   NEED_DEVICE(h);
   if (bit < 0 || bit >= 64 || !out) return fail(h, DQE_EINVAL, "read_creg: bad argument");
-  int8_t* d = nullptr;
-  CK(cudaMalloc(&d, h->batch));
+  if (int rc = ensure_scratch(h, (size_t)h->batch)) return rc;
+  int8_t* d = (int8_t*)h->scratch;
   k_extract_bit<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(cur_creg(h), bit, d, h->batch);
   h->stats[2]++;
   CK(cudaMemcpyAsync(out, d, h->batch, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaFree(d));
   return 0;
 }
 
@@ -2192,13 +2222,13 @@ int dqe_histogram(dqe_t* h, int k, const int* cbits, int64_t* out) {
     hp.bits[i] = cbits[i];
   }
   const size_t nb = (size_t)1 << k;
-  CK(cudaMalloc(&hp.bins, nb * sizeof(unsigned long long)));
+  if (int rc = ensure_scratch(h, nb * sizeof(unsigned long long))) return rc;
+  hp.bins = (unsigned long long*)h->scratch;
   CK(cudaMemsetAsync(hp.bins, 0, nb * sizeof(unsigned long long), h->stream));
   k_histogram<<<(unsigned)((h->batch + 255) / 256), 256, 0, h->stream>>>(hp);
   h->stats[2]++;
   CK(cudaMemcpyAsync(out, hp.bins, nb * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaFree(hp.bins));
   return 0;
 }
 
@@ -2209,12 +2239,12 @@ int dqe_reduced_dm(dqe_t* h, int k, const int* axes, int64_t shot, double* out) 
   ReadoutParams rp;
   if (int rc = build_readout(h, k, axes, &rp)) return rc;
   const size_t n = (size_t)1 << (2 * k);
-  CK(cudaMalloc(&rp.out_rdm, n * sizeof(double2)));
+  if (int rc = ensure_scratch(h, n * sizeof(double2))) return rc;
+  rp.out_rdm = (double2*)h->scratch;
   k_reduced_dm<<<(unsigned)n, 256, 0, h->stream>>>(rp, shot);
   h->stats[2]++;
   CK(cudaMemcpyAsync(out, rp.out_rdm, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaFree(rp.out_rdm));
   return 0;
 }
 
@@ -2225,17 +2255,15 @@ int dqe_fidelity_ket(dqe_t* h, int k, const int* axes, const double* ket, double
   ReadoutParams rp;
   if (int rc = build_readout(h, k, axes, &rp)) return rc;
   const size_t n = (size_t)1 << k;
-  double2* dk = nullptr;
-  CK(cudaMalloc(&dk, n * sizeof(double2)));
-  CK(cudaMalloc(&rp.out_fid, h->batch * sizeof(double)));
+  if (int rc = ensure_scratch(h, n * sizeof(double2) + (size_t)h->batch * sizeof(double))) return rc;
+  double2* dk = (double2*)h->scratch;
+  rp.out_fid = (double*)(dk + n);
   CK(cudaMemcpyAsync(dk, ket, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
   rp.ket = dk;
   k_fidelity_ket<<<(unsigned)h->batch, 128, 0, h->stream>>>(rp);
   h->stats[2]++;
   CK(cudaMemcpyAsync(out, rp.out_fid, h->batch * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaFree(dk));
-  CK(cudaFree(rp.out_fid));
   return 0;
 }
 

@@ -144,6 +144,20 @@ class Engine:
         self.batch = int(batch)
         self.device = int(device)
         self._keepalive = state_tensor
+        if state_tensor is not None:
+            # a caller-provided buffer is written by memset / kernels: a short, strided, host or wrong-device
+            # tensor would mean out-of-bounds device writes
+            import torch
+
+            need = self.batch * (2 ** self.max_qubits if self.formalism == KET else 4 ** self.max_qubits)
+            if not (isinstance(state_tensor, torch.Tensor) and state_tensor.is_cuda):
+                raise EngineError("state_tensor must be a CUDA torch tensor")
+            if state_tensor.device.index != self.device:
+                raise EngineError(f"state_tensor lives on cuda:{state_tensor.device.index}, the engine on cuda:{self.device}")
+            if state_tensor.dtype != torch.complex128 or not state_tensor.is_contiguous():
+                raise EngineError("state_tensor must be a contiguous complex128 tensor")
+            if state_tensor.numel() < need:
+                raise EngineError(f"state_tensor holds {state_tensor.numel()} amplitudes, the register needs {need}")
         ext = ctypes.c_void_p(state_tensor.data_ptr()) if state_tensor is not None else None
         st = ctypes.c_void_p(int(stream)) if stream else None
         rc = self._lib.dqe_create(ctypes.byref(self._h), self.formalism, self.max_qubits, self.batch,

@@ -81,7 +81,10 @@ class QPUSpec:
                              discard=self.measure_discards)
         if token.kind == "discard":
             return PhysInstr(self.single_qubit_gate_time, discard=True)
-        if "neglig" in token.name or "neglible" in token.name:
+        # INSTR_SINGLE_QUBIT_NEGLIGIBLE_TIME / INSTR_TWO_QUBIT_NEGLIGIBLE_TIME (qlib/gates.py:112-115, spelt
+        # "neglibible_time_instr" / "neglible_time_2_qubit" upstream): duration 3 ns, no noise model
+        # (quantum_processors.py:450-455).  Matched by the token names the reference uses.
+        if token.name in ("neglibible_time_instr", "neglible_time_2_qubit"):
             return PhysInstr(3.0)
         if token.num_qubits == 1:
             return PhysInstr(self.single_qubit_gate_time, "depol1", self.single_qubit_gate_error_prob)

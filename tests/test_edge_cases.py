@@ -131,3 +131,15 @@ def test_handle_limits_and_option_errors_without_a_gpu():
     for key, ok in (("prefetch", -1), ("prefetch", 0), ("tmap", 0), ("cxperm", 0), ("factor", 0), ("cluster", 0)):
         e.set_option(key, ok)
     e.close()
+
+
+def test_negligible_time_instructions_have_no_noise_and_three_ns():
+    """the reference's two negligible-time tokens (qlib/gates.py:112-115; physical instructions at
+    quantum_processors.py:450-455) take 3 ns and carry no noise model, whatever the gate error settings."""
+    from dqc_simulator_b200 import hardware, instructions as ins
+
+    spec = hardware.QPUSpec(single_qubit_gate_error_prob=0.01, p_depolar_error_cnot=0.02)
+    for tok in (ins.INSTR_SINGLE_QUBIT_NEGLIGIBLE_TIME, ins.INSTR_TWO_QUBIT_NEGLIGIBLE_TIME):
+        ph = spec.phys(tok)
+        assert ph.duration == 3.0 and ph.noise == "none" and ph.prob == 0.0
+    assert spec.phys(ins.INSTR_H).duration == 135e3 and spec.phys(ins.INSTR_H).noise == "depol1"
