@@ -34,6 +34,9 @@ enum OpType : int32_t {
                       // e00,e11 mix among themselves and e01,e10 among themselves -- 8 complex coefficients
   OP_DYN1 = 15,       // dm 1q channel whose strength q is read per shot from classical register `aux`
                       // (flags = DynKind): idle-time noise of a shot that follows its own simulated timeline
+  OP_KBLOCK = 17,     // dense 2^k x 2^k complex block on k tile bits (k = 3, 4), b[0] = most significant bit of the
+                      // matrix index: a real (2 * 2^k)-square GEMM against the tile on the FP64 tensor cores
+                      // (mma.sync m8n8k4.f64 -> SASS DMMA); the host fuses runs of gates that stay inside k bits
   OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
                       // run redundantly by every thread of the CTA (identical values: no barrier needed)
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
@@ -408,6 +411,118 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Dense k-qubit block (k = 3, 4) on the FP64 tensor cores.
+// The complex map y = U x on the 2^k amplitudes of a column is the real map
+//     [Re y]   [Re U  -Im U] [Re x]
+//     [Im y] = [Im U   Re U] [Im x]
+// i.e. a (2K x 2K) real matrix (K = 2^k) against a (2K x ncols) real matrix whose columns are the tile's
+// T / K amplitude groups.  One warp takes 8 columns at a time: 2K/8 row tiles x 2K/4 k-steps of
+// mma.sync.aligned.m8n8k4 (fp64).  The A fragments (the matrix) are loaded once per op and stay in registers.
+// Fragment layout of m8n8k4.f64: A[8x4]: lane holds A[lane / 4][lane % 4]; B[4x8]: lane holds B[lane % 4][lane / 4];
+// C / D[8x8]: lane holds rows lane / 4, columns 2 * (lane % 4) + {0, 1}.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int KQ>
+__device__ __noinline__ void op_kblock(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
+  constexpr int K = 1 << KQ, R = 2 * K;        // complex dimension, real dimension
+  constexpr int MT = R / 8, KS = R / 4;        // row tiles, k-steps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  // element e of a column (KQ-bit index, b[0] = MSB) sits at tile offset eoff(e)
+  int sb[4];                                   // the block's bit positions, ascending (for the zero insertion)
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) sb[i] = op.b[i];
+#pragma unroll
+  for (int i = 0; i < KQ - 1; ++i)
+#pragma unroll
+    for (int j = 0; j < KQ - 1 - i; ++j)
+      if (sb[j] > sb[j + 1]) { const int t = sb[j]; sb[j] = sb[j + 1]; sb[j + 1] = t; }
+  auto eoff = [&](int e) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < KQ; ++i) o |= (uint32_t)((e >> (KQ - 1 - i)) & 1) << op.b[i];
+    return o;
+  };
+  // A fragments: real matrix Ar[row][col], row / col < R; (row, col) -> U[row % K][col % K] with the 2 x 2 real
+  // embedding by (row / K, col / K): (0,0) Re, (0,1) -Im, (1,0) Im, (1,1) Re
+  double afrag[MT][KS];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int row = 8 * mt + lr, col = 4 * ks + lc;
+      const double2 u = cs[(row % K) * K + (col % K)];
+      const int qr = row / K, qc = col / K;
+      afrag[mt][ks] = qr == qc ? u.x : (qr == 0 ? -u.y : u.y);
+    }
+  // this lane's B rows (one per k-step) and D rows (one per row tile), as byte offsets into a column
+  uint32_t boff[KS], doff[MT];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int row = 4 * ks + lc;
+    boff[ks] = eoff(row % K) * 16u + (row / K) * 8u;
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row = 8 * mt + lr;
+    doff[mt] = eoff(row % K) * 16u + (row / K) * 8u;
+  }
+  const uint32_t ncols = T >> KQ;
+  char* tb = reinterpret_cast<char*>(tile);
+  if (ncols < 8u) {
+    // a register too small for one 8-column MMA tile (< 2^(k+3) amplitudes): plain FMAs, one column per thread
+    for (uint32_t c = threadIdx.x; c < ncols; c += blockDim.x) {
+      uint32_t i0 = c;
+#pragma unroll
+      for (int j = 0; j < KQ; ++j) i0 = ins0(i0, sb[j]);
+      double2 x[K], y[K];
+#pragma unroll
+      for (int e = 0; e < K; ++e) x[e] = tile[i0 | eoff(e)];
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int e = 0; e < K; ++e) acc = cfma(cs[r * K + e], x[e], acc);
+        y[r] = acc;
+      }
+#pragma unroll
+      for (int e = 0; e < K; ++e) tile[i0 | eoff(e)] = y[e];
+    }
+    return;
+  }
+  for (uint32_t c0 = warp * 8u; c0 < ncols; c0 += nwarps * 8u) {
+    // column index -> tile index with zeros at the block's bits
+    auto colbase = [&](uint32_t c) {
+      uint32_t i = c;
+#pragma unroll
+      for (int j = 0; j < KQ; ++j) i = ins0(i, sb[j]);
+      return i * 16u;
+    };
+    const uint32_t bcol = colbase(c0 + lr);                       // B: column lane / 4
+    const uint32_t dcol0 = colbase(c0 + 2 * lc), dcol1 = colbase(c0 + 2 * lc + 1);   // D: columns 2 (lane % 4) + {0, 1}
+    double bfrag[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) bfrag[ks] = *reinterpret_cast<const double*>(tb + bcol + boff[ks]);
+    __syncwarp();   // every lane has read its part of the 8 columns before anyone overwrites them
+    double d0[MT], d1[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) { d0[mt] = 0.0; d1[mt] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) dmma_m8n8k4(d0[mt], d1[mt], afrag[mt][ks], bfrag[ks]);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      *reinterpret_cast<double*>(tb + dcol0 + doff[mt]) = d0[mt];
+      *reinterpret_cast<double*>(tb + dcol1 + doff[mt]) = d1[mt];
+    }
+  }
+}
 
 // cs = {a, b, c, d, f, g, h, k}: e00' = a e00 + b e11, e11' = c e00 + d e11, e01' = f e01 + g e10, e10' = h e01 + k e10
 __device__ __forceinline__ void op_xpat(double2* tile, uint32_t T, const MicroOp& op, const double2* cs) {
@@ -1388,6 +1503,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             }
             break;
           }
+          case OP_KBLOCK:
+            if (op.nb == 4) op_kblock<4>(tile, T, op, cs); else op_kblock<3>(tile, T, op, cs);
+            break;
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
           case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
@@ -1413,6 +1531,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_XPAT: op_xpat(tile, T, op, cs); break;
           case OP_DYN1: op_dyn1(tile, T, op, s_treg); break;
           case OP_DEPOL2: op_depol2(tile, T, op); break;
+          case OP_KBLOCK:
+            if (op.nb == 4) op_kblock<4>(tile, T, op, cs); else op_kblock<3>(tile, T, op, cs);
+            break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
           case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;

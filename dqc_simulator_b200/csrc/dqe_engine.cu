@@ -103,6 +103,8 @@ struct dqe_engine {
   std::string err;
   int cuda_failed;
   int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, cluster, cxperm, factor, tmap, prefetch;
+  int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
+  int64_t kblocks_fused;
   int64_t tmap_used, tmap_refused;
   int64_t stats[8];
   bool timing;
@@ -1032,6 +1034,145 @@ struct Planner {
     }
   }
 
+  // ---- ket: dense k-qubit blocks (OP_KBLOCK, FP64 tensor cores) -----------------------------------------
+  // bits an op reads or writes inside the tile (targets, controls, diagonal bits); false = not fusable
+  bool kb_bits(const HostOp* ho, uint64_t tile, uint64_t* bits) const {
+    if (ho->kind != 0 || ho->m.pred_bit >= 0 || ho->pctrl2) return false;
+    uint64_t b = 0;
+    const MicroOp& m = ho->m;
+    switch (m.type) {
+      case OP_MAT1: b = (1ull << m.b[0]) | ho->pctrl; break;
+      case OP_MAT2: if (ho->pctrl) return false; b = (1ull << m.b[0]) | (1ull << m.b[1]); break;
+      case OP_DIAG: case OP_KBLOCK: for (uint32_t i = 0; i < m.nb; ++i) b |= 1ull << m.b[i]; break;
+      default: return false;
+    }
+    if (b & ~tile) return false;   // a control / diagonal bit outside the tile depends on the tile base
+    *bits = b;
+    return true;
+  }
+  // apply a fusable ket op to every column of M (dimension 2^s, row-major), S = block bits, S[0] = MSB
+  void kb_apply(std::vector<cplx>& M, const std::vector<int>& S, const HostOp* ho) const {
+    const int s = (int)S.size(), D = 1 << s;
+    auto pos = [&](int bit) { for (int i = 0; i < s; ++i) if (S[i] == bit) return s - 1 - i; return -1; };   // weight
+    auto cst = [&](int i) { return cplx(h->cpool[ho->m.c_off + i].x, h->cpool[ho->m.c_off + i].y); };
+    const MicroOp& m = ho->m;
+    std::vector<cplx> out(M.size());
+    for (int col = 0; col < D; ++col) {
+      std::vector<cplx> v(D), w(D);
+      for (int r = 0; r < D; ++r) v[r] = M[r * D + col];
+      if (m.type == OP_MAT1) {
+        const int t = pos(m.b[0]);
+        uint32_t cm = 0;
+        for (int b = 0; b < 64; ++b) if ((ho->pctrl >> b) & 1ull) cm |= 1u << pos(b);
+        w = v;
+        for (int r = 0; r < D; ++r) {
+          if ((r >> t) & 1) continue;
+          if ((r & cm) != cm) continue;
+          const int r1 = r | (1 << t);
+          w[r] = cst(0) * v[r] + cst(1) * v[r1];
+          w[r1] = cst(2) * v[r] + cst(3) * v[r1];
+        }
+      } else if (m.type == OP_MAT2) {
+        const int th = pos(m.b[0]), tl = pos(m.b[1]);
+        w = v;
+        for (int r = 0; r < D; ++r) {
+          if (((r >> th) & 1) || ((r >> tl) & 1)) continue;
+          const int idx[4] = {r, r | (1 << tl), r | (1 << th), r | (1 << th) | (1 << tl)};
+          for (int i = 0; i < 4; ++i) {
+            cplx acc = 0.0;
+            for (int j = 0; j < 4; ++j) acc += cst(i * 4 + j) * v[idx[j]];
+            w[idx[i]] = acc;
+          }
+        }
+      } else if (m.type == OP_DIAG) {
+        for (int r = 0; r < D; ++r) {
+          int t = 0;
+          for (uint32_t i = 0; i < m.nb; ++i) t |= ((r >> pos(m.b[i])) & 1) << (m.nb - 1 - i);
+          w[r] = cst(t) * v[r];
+        }
+      } else {   // OP_KBLOCK on a subset of S
+        const int k = (int)m.nb, K = 1 << k;
+        w = v;
+        for (int r = 0; r < D; ++r) {
+          bool base = true;
+          for (int i = 0; i < k; ++i) if ((r >> pos(m.b[i])) & 1) base = false;
+          if (!base) continue;
+          std::vector<int> idx(K);
+          for (int e = 0; e < K; ++e) {
+            int x = r;
+            for (int i = 0; i < k; ++i) if ((e >> (k - 1 - i)) & 1) x |= 1 << pos(m.b[i]);
+            idx[e] = x;
+          }
+          for (int i = 0; i < K; ++i) {
+            cplx acc = 0.0;
+            for (int j = 0; j < K; ++j) acc += cst(i * K + j) * v[idx[j]];
+            w[idx[i]] = acc;
+          }
+        }
+      }
+      for (int r = 0; r < D; ++r) out[r * D + col] = w[r];
+    }
+    M.swap(out);
+  }
+  std::deque<HostOp> kb_ops;       // synthesised OP_KBLOCK host ops (constants appended to the handle's pool)
+
+  // greedy: consecutive fusable ops whose bits stay inside <= 4 tile bits become one dense block when that saves
+  // enough shared-memory sweeps; ops on disjoint bits pass in front of the pending block (they commute with it)
+  void fuse_kblocks(std::vector<const HostOp*>& cur, uint64_t tile, int t) {
+    if (!h->kblock || h->formalism != DQE_KET || t < 6) return;
+    const int kmax = std::min(4, t - 3);
+    std::vector<const HostOp*> out, blk;
+    uint64_t S = 0;
+    double weight = 0.0;
+    auto flush_blk = [&]() {
+      const int k = __builtin_popcountll(S);
+      bool has_block = false;
+      for (const HostOp* ho : blk) has_block |= ho->m.type == OP_KBLOCK;
+      // cost model (r02h microbench, ket-28): a k = 4 block is 32 DMMA per 128 amplitudes ~ 0.9 ms of FP64 pipe,
+      // a plain in-tile 1q sweep ~ 0.24 ms: the block pays from ~7 one-qubit-gate equivalents on (k = 3: ~4)
+      if (blk.size() >= 2 && k >= 3 && (weight >= (k == 3 ? 4.0 : 7.0) || has_block)) {
+        std::vector<int> bits;
+        for (int b = 63; b >= 0; --b) if ((S >> b) & 1ull) bits.push_back(b);
+        const int D = 1 << k;
+        std::vector<cplx> M((size_t)D * D, cplx(0.0));
+        for (int i = 0; i < D; ++i) M[(size_t)i * D + i] = 1.0;
+        for (const HostOp* ho : blk) kb_apply(M, bits, ho);
+        HostOp o = *blk.back();
+        memset(&o.m, 0, sizeof(o.m));
+        o.nf = 0; o.pctrl = o.pctrl2 = 0;
+        o.m.type = OP_KBLOCK; o.m.pred_bit = -1; o.m.nb = (uint32_t)k;
+        for (int i = 0; i < k; ++i) o.m.b[i] = (uint8_t)bits[i];
+        o.need = S;
+        o.m.c_off = add_consts(h, M.data(), D * D); o.nconst = D * D;
+        kb_ops.push_back(o);
+        out.push_back(&kb_ops.back());
+        h->kblocks_fused++;
+      } else {
+        for (const HostOp* ho : blk) out.push_back(ho);
+      }
+      blk.clear(); S = 0; weight = 0.0;
+    };
+    for (const HostOp* ho : cur) {
+      uint64_t b = 0;
+      if (kb_bits(ho, tile, &b)) {
+        if (__builtin_popcountll(S | b) > kmax) flush_blk();
+        if (__builtin_popcountll(b) <= kmax) {
+          blk.push_back(ho); S |= b;
+          weight += ho->m.type == OP_MAT1 ? (ho->pctrl ? 0.6 : 1.0) : ho->m.type == OP_MAT2 ? 2.0 :
+                    ho->m.type == OP_DIAG ? 0.25 : 4.0;
+          continue;
+        }
+      }
+      if (ho->kind >= 2) { out.push_back(ho); continue; }               // classical: touches no amplitude
+      uint64_t tb = touched_bits(*ho);
+      if (ho->m.type == OP_PROBS || ho->m.type == OP_MEASURE || ho->m.type == OP_COLLAPSE) tb = ~0ull;
+      if (tb & S) flush_blk();
+      out.push_back(ho);
+    }
+    flush_blk();
+    cur.swap(out);
+  }
+
   // Close `cur` as one pass; when the emitted micro-program overflows the per-pass budget (the planner's
   // running estimate is optimistic) the list is cut in two and each half becomes its own pass.
   // live0 = live mask in front of the first op of `cur`.
@@ -1067,6 +1208,7 @@ struct Planner {
       err = "planner: op needs more target bits than the tile holds";
       return false;
     }
+    fuse_kblocks(cur, tile, t);
     PlannedPass P;
     memset(&P, 0, sizeof(P));
     P.is_finish = false;
@@ -1461,7 +1603,7 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL", "KBLOCK"};
     static const char* gnames[] = {"?", "gPAULI1", "-", "gMAT1X2", "gDEPOL2", "-", "-", "gCOLLAPSE",
                                    "gTRACE", "gINJECT", "gDIAG", "gXPAT", "-", "-", "-", "gDYN1"};
     for (PlannedPass& P : pl.passes) {
@@ -1691,7 +1833,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -1907,6 +2049,33 @@ int dqe_enqueue_diag(dqe_t* h, int k, const int* axes, const double* d) {
   to_cplx(d, t, 1 << k);
   h->stats[4]++;
   return lower_diag(h, k, axes, t);
+}
+
+int dqe_enqueue_kq(dqe_t* h, int k, const int* axes, const double* m) {
+  if (int rc = check_ready(h)) return rc;
+  if (k < 1 || k > 4 || !axes || !m) return fail(h, DQE_EUNSUPPORTED, "kq gate: 1 <= k <= 4");
+  for (int i = 0; i < k; ++i) {
+    if (int rc = check_live(h, axes[i], "kq gate")) return rc;
+    for (int j = 0; j < i; ++j) if (axes[i] == axes[j]) return fail(h, DQE_EINVAL, "kq gate: repeated axis");
+  }
+  if (k == 1) return dqe_enqueue_1q(h, axes[0], m);
+  if (k == 2) return dqe_enqueue_2q(h, axes[0], axes[1], m);
+  const int D = 1 << k;
+  std::vector<cplx> u((size_t)D * D);
+  to_cplx(m, u.data(), D * D);
+  h->stats[4]++;
+  for (int side = 0; side < (h->formalism == DQE_DM ? 2 : 1); ++side) {
+    HostOp o = blank(h, OP_KBLOCK);
+    o.m.nb = (uint32_t)k;
+    for (int i = 0; i < k; ++i) {
+      const int bit = (h->formalism == DQE_DM && side == 0) ? rowbit(h, axes[i]) : axes[i];
+      o.m.b[i] = (uint8_t)bit; o.need |= 1ull << bit;
+    }
+    if (side == 1) for (auto& z : u) z = std::conj(z);   // column side of U rho U^dagger
+    o.m.c_off = add_consts(h, u.data(), D * D); o.nconst = D * D;
+    push(h, o);
+  }
+  return 0;
 }
 
 int dqe_set_predicate(dqe_t* h, int creg_bit) {
@@ -2390,6 +2559,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "pin_mask")) {
     if (h->nmax < 64 && ((uint64_t)value >> h->nmax)) return fail(h, DQE_EINVAL, "pin_mask out of range");
     h->pin_axes = (uint64_t)value;
+  } else if (!strcmp(key, "kblock")) {
+    h->kblock = value ? 1 : 0;
   } else if (!strcmp(key, "shot_stride")) {
     if (value < 1) return fail(h, DQE_EINVAL, "shot_stride >= 1");
     h->shot_stride = value;

@@ -42,6 +42,7 @@ ABI = {
     "dqe_enqueue_2q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
     "dqe_enqueue_ctrl_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
     "dqe_enqueue_diag": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
+    "dqe_enqueue_kq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
     "dqe_set_predicate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dqe_enqueue_cond_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
     "dqe_enqueue_pauli_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
@@ -246,6 +247,13 @@ class Engine:
         _a, pa = _ibuf(axes)
         _k, p = _cbuf(np.asarray(d, dtype=complex).reshape(-1))
         self._ck(self._lib.dqe_enqueue_diag(self._h, len(_a), pa, p))
+
+    def apply_kq(self, axes, m):
+        """Dense k-qubit gate (k <= 4, first axis = most significant index): FP64 tensor cores for k >= 3."""
+        _a, pa = _ibuf(axes)
+        k = len(_a)
+        _k, p = _cbuf(np.asarray(m, dtype=complex).reshape(2 ** k, 2 ** k))
+        self._ck(self._lib.dqe_enqueue_kq(self._h, k, pa, p))
 
     def set_predicate(self, creg_bit):
         self._ck(self._lib.dqe_set_predicate(self._h, int(creg_bit)))

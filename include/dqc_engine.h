@@ -103,6 +103,13 @@ int dqe_enqueue_1q(dqe_t* h, int axis, const double* m /*2x2 complex*/);
 int dqe_enqueue_2q(dqe_t* h, int a, int b, const double* m /*4x4 complex, a = MSB*/);
 int dqe_enqueue_ctrl_1q(dqe_t* h, int c, int t, const double* m /*2x2*/);  /* Operator.ctrl */
 int dqe_enqueue_diag(dqe_t* h, int k, const int* axes, const double* d /*2^k complex*/);
+/* Dense k-qubit gate, k <= 4 (first axis = most significant index): k = 3, 4 run as ONE real (2 * 2^k)-square
+ * GEMM against the tile on the FP64 tensor cores (mma.sync m8n8k4.f64, SASS DMMA) -- the only tensor-core op of
+ * the engine: every other gate is <= 4 x 4 per amplitude group and bound by memory, not by math.  The planner
+ * also builds such blocks itself from runs of queued ket gates that stay inside <= 4 tile bits (option
+ * "kblock", default 1).  Replaces qubitapi.operate(qubits, operator) for k-qubit operators
+ * (INSTR_*_UNITARY of qlib/gates.py:107-115 generalised; the reference's own programs stop at k = 2). */
+int dqe_enqueue_kq(dqe_t* h, int k, const int* axes, const double* m /*2^k x 2^k complex*/);
 
 /* Ops enqueued until dqe_set_predicate(h, -1) act only on shots whose creg bit is 1
  * (classically controlled X / Z corrections, dqc_control.py:347-348, 387-390, 497-503). */

@@ -172,6 +172,10 @@ class OracleEngine:
     def apply_diag(self, axes, d):
         self._apply(list(axes), np.diag(np.asarray(d, dtype=complex)))
 
+    def apply_kq(self, axes, m):
+        axes = list(axes)
+        self._apply(axes, np.asarray(m, dtype=complex).reshape(2 ** len(axes), 2 ** len(axes)))
+
     def set_predicate(self, creg_bit):
         """Ops enqueued until ``set_predicate(-1)`` act only on shots whose creg bit is 1."""
         self._pred_bit = int(creg_bit)

@@ -370,6 +370,69 @@ def test_reinit_draws_fresh_shots_and_keeps_parity():
     assert np.array_equal(w2, w0)
 
 
+@pytest.mark.parametrize("formalism,n,batch,tile", [("ket", 12, 2, 11), ("ket", 10, 3, 8), ("ket", 14, 1, 10), ("ket", 5, 4, 11),
+                                                     ("dm", 6, 2, 10), ("dm", 4, 3, 8)])
+def test_dense_k_qubit_blocks(formalism, n, batch, tile):
+    """dqe_enqueue_kq: random dense 3- and 4-qubit matrices (unitary and not), on bits inside and outside the
+    contiguous run, against the oracle -- the FP64 tensor-core path (OP_KBLOCK, SASS DMMA), including registers
+    too small for one MMA tile (scalar fallback) and the two one-sided blocks of a density matrix."""
+    rng = np.random.default_rng(31 + n + tile)
+    b = Both(formalism, n, batch, 17, tile_bits=tile)
+    for a in range(n):
+        b.alloc_axis(a)
+        b.apply_1q(a, rand_unitary(rng, 2))
+    for rep in range(10):
+        k = int(rng.choice([3, 4]))
+        axes = [int(x) for x in rng.choice(n, size=k, replace=False)]
+        m = rand_unitary(rng, 2 ** k)
+        if rep % 4 == 3:      # a block need not be unitary (make_state_gen_op, qlib/gates.py:45-48, is not either)
+            m = m @ np.diag(rng.uniform(0.5, 1.0, size=2 ** k))
+        b.apply_kq(axes, m)
+        if rep % 3 == 0:
+            b.apply_2q(*[int(x) for x in rng.choice(n, size=2, replace=False)], CNOT)
+        b.check(f"block {rep} on {axes}")
+
+
+@pytest.mark.parametrize("n,tile", [(12, 11), (14, 10), (11, 8)])
+def test_planner_fuses_gate_runs_into_dense_blocks(n, tile):
+    """Runs of ket gates that stay inside <= 4 tile bits are composed on the host and run as one dense block;
+    same state as the unfused execution and as the oracle.  Includes the non-unitary state-generation
+    operator of qlib/gates.py:45-48 (diag(alpha, beta) . [[1, 1], [1, -1]])."""
+    from dqc_simulator_b200.instructions import state_gen_matrix
+
+    rng = np.random.default_rng(7 + n)
+
+    def program(b):
+        for a in range(n):
+            b.alloc_axis(a)
+        for layer in range(4):
+            win = [int(x) for x in rng.choice(n, size=4, replace=False)]
+            for _ in range(14):
+                c = rng.integers(4)
+                if c == 0:
+                    b.apply_1q(int(rng.choice(win)), rand_unitary(rng, 2))
+                elif c == 1:
+                    b.apply_2q(*[int(x) for x in rng.choice(win, size=2, replace=False)], rand_unitary(rng, 4))
+                elif c == 2:
+                    b.apply_ctrl_1q(*[int(x) for x in rng.choice(win, size=2, replace=False)], rand_unitary(rng, 2))
+                else:
+                    b.apply_1q(int(rng.choice(win)), state_gen_matrix(0.8, 0.6))
+            b.apply_2q(*[int(x) for x in rng.choice(n, size=2, replace=False)], CNOT)
+        b.check("fused")
+
+    state = np.random.default_rng(7 + n).bit_generator.state
+    b = Both("ket", n, 2, 3, tile_bits=tile)
+    program(b)
+    fused = b.g.full_state()
+    assert b.g.stats()["micro_ops"] < 40
+    rng.bit_generator.state = state
+    b2 = Both("ket", n, 2, 3, tile_bits=tile)
+    b2.g.set_option("kblock", 0)
+    program(b2)
+    assert b2.g.stats()["micro_ops"] > b.g.stats()["micro_ops"]
+    assert np.abs(fused - b2.g.full_state()).max() < TOL
+
+
 @pytest.mark.parametrize("formalism", ["ket", "dm"])
 def test_forced_outcomes_bit_exact(formalism):
     n = 5

@@ -76,6 +76,25 @@ def main():
         for q in range(n - 4, n):
             e.apply_1q(q, u)
     report(f"ket{n} 4x 1q fused (top 4)", *timed(e, many2))
+
+    # dense k-qubit block (OP_KBLOCK, FP64 tensor cores): 24 gates inside bits 0-3, planner-fused vs gate by gate
+    us = [rand_u(rng, 2) for _ in range(16)] + [rand_u(rng, 4) for _ in range(8)]
+
+    def dense4():
+        for i, m in enumerate(us):
+            if m.shape[0] == 2:
+                e.apply_1q(i % 4, m)
+            else:
+                e.apply_2q(i % 4, (i + 1) % 4, m)
+    for kb in (1, 0):
+        e.set_option("kblock", kb)
+        report(f"ket{n} 24 gates on bits 0-3, kblock={kb}", *timed(e, dense4))
+    e.set_option("kblock", 1)
+    u16 = rand_u(rng, 16)
+    report(f"ket{n} dense 4q block (0,1,2,3)", *timed(e, lambda: e.apply_kq([0, 1, 2, 3], u16)))
+    report(f"ket{n} dense 4q block (3,9,17,{n-1})", *timed(e, lambda: e.apply_kq([3, 9, 17, n - 1], u16)))
+    u8 = rand_u(rng, 8)
+    report(f"ket{n} dense 3q block (0,1,2)", *timed(e, lambda: e.apply_kq([0, 1, 2], u8)))
     e.close()
 
     # ---- dm, batched
