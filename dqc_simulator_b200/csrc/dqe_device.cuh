@@ -37,6 +37,10 @@ enum OpType : int32_t {
   OP_KBLOCK = 17,     // dense 2^k x 2^k complex block on k tile bits (k = 3, 4), b[0] = most significant bit of the
                       // matrix index: a real (2 * 2^k)-square GEMM against the tile on the FP64 tensor cores
                       // (mma.sync m8n8k4.f64 -> SASS DMMA); the host fuses runs of gates that stay inside k bits
+  OP_LADDER = 18,     // ket: controlled-phase star  phase(i) = prod_j w_j^(b_q b_j)  (centre bit q = b[0], up to
+                      // kMaxLadderLeaves leaf bits j in the payload bytes, w_j in the constant pool): the whole
+                      // controlled-phase ladder of one QFT stage costs about two complex multiplies per amplitude,
+                      // however many controls it has.  flags = tile-local leaves | outer leaves << 8
   OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
                       // run redundantly by every thread of the CTA (identical values: no barrier needed)
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
@@ -93,6 +97,8 @@ static_assert(sizeof(ClInstr) == 8, "ClInstr is packed into MicroOp payloads");
 constexpr int kTimeRegs = 128;        // doubles per shot
 constexpr int kClPerOp = 10;          // ClInstr per OP_CLASSICAL micro-op
 
+constexpr int kLadderLeafOff = 56;   // leaf bit positions of an OP_LADDER live in bytes [56, 96) of the MicroOp
+constexpr int kMaxLadderLeaves = 40;
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
 constexpr int kMaxConstsKet = 512;       // double2 constants staged in shared memory per pass (8 KiB)
@@ -349,10 +355,52 @@ struct DiagPrep {
   uint32_t s0, s1, s2, s3;     // their weights in the table index
 };
 constexpr int kMaxDiagRun = 16;
+struct LadderPrep {
+  double2 G;         // product of the phases of the outer leaves whose base bit is 1
+  uint32_t qmask;    // tile-local mask of the centre bit (0: centre outside the tile, `on` holds its base bit)
+  int32_t on;
+};
+__device__ __forceinline__ const uint8_t* ladder_leaves(const MicroOp& op) {
+  return reinterpret_cast<const uint8_t*>(&op) + kLadderLeafOff;
+}
 
 __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const MicroOp* ops, int count,
-                                         const double2* s_consts, uint64_t base, uint64_t cw, DiagPrep* prep) {
-  if ((int)threadIdx.x < count) {
+                                         const double2* s_consts, uint64_t base, uint64_t cw, DiagPrep* prep,
+                                         LadderPrep* lprep) {
+  // ladders: the factor of the OUTER leaves is the same for the whole tile -- eight lanes per op multiply their
+  // share of the selected phases and combine through shuffles (uniform trip count: every lane shuffles)
+  {
+    const int grp = threadIdx.x >> 3, part = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+    for (int k0 = 0; k0 < count; k0 += ngrp) {
+      const int k = k0 + grp;
+      const bool act = k < count && ops[k < count ? k : 0].type == OP_LADDER;
+      double2 g = make_double2(1.0, 0.0);
+      if (act) {
+        const MicroOp& op = ops[k];
+        const int nl = op.flags & 0xff, no = (op.flags >> 8) & 0xff;
+        const uint8_t* lf = ladder_leaves(op);
+        for (int j = part; j < no; j += 8)
+          if ((base >> (lf[nl + j] - kOuter)) & 1ull) g = cmul(g, s_consts[op.c_off + nl + j]);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        double2 h;
+        h.x = __shfl_xor_sync(0xffffffffu, g.x, o);
+        h.y = __shfl_xor_sync(0xffffffffu, g.y, o);
+        g = cmul(g, h);
+      }
+      if (act && part == 0) {
+        const MicroOp& op = ops[k];
+        LadderPrep L;
+        L.G = g;
+        L.on = !(op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull));
+        if (op.b[0] >= kOuter) { L.qmask = 0u; L.on = L.on && ((base >> (op.b[0] - kOuter)) & 1ull); }
+        else L.qmask = 1u << op.b[0];
+        lprep[k] = L;
+      }
+    }
+  }
+  if ((int)threadIdx.x < count && ops[threadIdx.x].type == OP_DIAG) {
     const MicroOp& op = ops[threadIdx.x];
     DiagPrep d;
     d.c_off = op.c_off; d.nl = 0; d.fixed = 0;
@@ -378,6 +426,34 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = tile[threadIdx.x + (uint32_t)e * blockDim.x];
     for (int k = 0; k < count; ++k) {
+      if (ops[k].type == OP_LADDER) {
+        const LadderPrep L = lprep[k];
+        if (!L.on) continue;
+        const MicroOp& op = ops[k];
+        const int nl = op.flags & 0xff;
+        const uint8_t* lf = ladder_leaves(op);
+        const double2* w = s_consts + op.c_off;
+        const uint32_t tid = threadIdx.x;
+        // thread part: centre / leaves on thread-id bits (tile-local leaves are sorted ascending)
+        if ((L.qmask & (blockDim.x - 1u)) && !(tid & L.qmask)) continue;
+        double2 sc = L.G;
+        int j = 0;
+        for (; j < nl && lf[j] < lb; ++j)
+          if ((tid >> lf[j]) & 1u) sc = cmul(sc, w[j]);
+        // element part: e = tile bits [lb, lb + 4)
+        const uint32_t qe = L.qmask >> lb;   // 0 when the centre is a thread bit or outside the tile
+        for (; j < nl; ++j) {
+          const uint32_t eb = 1u << (lf[j] - lb);
+          const double2 wj = w[j];
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((e & eb) && (e & qe) == qe) v[e] = cmul(v[e], wj);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if ((e & qe) == qe) v[e] = cmul(v[e], sc);
+        continue;
+      }
       const DiagPrep d = prep[k];
       if (!d.on) continue;
       const uint32_t tid = threadIdx.x;
@@ -401,6 +477,18 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
     double2 v = tile[i];
     for (int k = 0; k < count; ++k) {
+      if (ops[k].type == OP_LADDER) {
+        const LadderPrep& L = lprep[k];
+        if (!L.on || (L.qmask && !(i & L.qmask))) continue;
+        const MicroOp& op = ops[k];
+        const int nl = op.flags & 0xff;
+        const uint8_t* lf = ladder_leaves(op);
+        double2 f = L.G;
+        for (int j = 0; j < nl; ++j)
+          if ((i >> lf[j]) & 1u) f = cmul(f, s_consts[op.c_off + j]);
+        v = cmul(v, f);
+        continue;
+      }
       const DiagPrep& d = prep[k];
       if (!d.on) continue;
       const uint32_t idx = d.fixed + ((i & d.m0) ? d.s0 : 0u) + ((i & d.m1) ? d.s1 : 0u) +
@@ -1329,6 +1417,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
+  __shared__ LadderPrep s_lad[FORM == 0 ? kMaxDiagRun : 1];
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
   __shared__ __align__(16) double s_treg[kTimeRegs];   // the shot's classical registers (simulated times, channel strengths)
@@ -1492,12 +1581,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           case OP_MAT2:
             if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
             break;
-          case OP_DIAG: {
+          case OP_DIAG: case OP_LADDER: {
             int run = 1;
-            while (cur + run < pp.nops && run < kMaxDiagRun && s_ops[cur + run].type == OP_DIAG) ++run;
-            if (run == 1) op_diag(tile, T, op, cs, base);
+            while (cur + run < pp.nops && run < kMaxDiagRun &&
+                   (s_ops[cur + run].type == OP_DIAG || s_ops[cur + run].type == OP_LADDER)) ++run;
+            if (run == 1 && op_type == OP_DIAG) op_diag(tile, T, op, cs, base);
             else {
-              op_diag_run(tile, T, &s_ops[cur], run, s_consts, base, cw, s_diag);
+              op_diag_run(tile, T, &s_ops[cur], run, s_consts, base, cw, s_diag, s_lad);
               o = cur + run;
               if (o < pp.nops) hdr = op_header(&s_ops[o]);
             }

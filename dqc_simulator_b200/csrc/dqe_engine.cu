@@ -103,6 +103,8 @@ struct dqe_engine {
   std::string err;
   int cuda_failed;
   int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, cluster, cxperm, factor, tmap, prefetch;
+  int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
+  int64_t ladders_built;
   int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
   int64_t kblocks_fused;
   int64_t tmap_used, tmap_refused;
@@ -291,6 +293,11 @@ bool is_one(cplx z) { return z.real() == 1.0 && z.imag() == 0.0; }
 uint64_t touched_bits(const HostOp& o) {
   uint64_t t = o.need | o.pctrl | o.pctrl2;
   if (o.m.type == OP_DIAG) for (uint32_t i = 0; i < o.m.nb; ++i) t |= 1ull << o.m.b[i];
+  if (o.m.type == OP_LADDER) {
+    t |= 1ull << o.m.b[0];
+    const uint8_t* lf = reinterpret_cast<const uint8_t*>(&o.m) + kLadderLeafOff;
+    for (int j = 0; j < o.m.aux; ++j) t |= 1ull << lf[j];
+  }
   return t;
 }
 
@@ -731,6 +738,229 @@ int lower_measure(dqe_t* h, int axis, int creg_bit, int forced, int discard, dou
   return 0;
 }
 
+// -------- ket: controlled-phase stars (OP_LADDER), built at flush ---------------------------------
+// Every product of <= 2-bit diagonal gates is a quadratic phase form
+//     phase(i) = g . prod_a u_a^(b_a) . prod_(a<b) w_ab^(b_a b_b).
+// The queued diagonal tables (already merged up to 4 bits by the push-time peepholes) are taken apart into
+// these terms: g and the one-bit phases u_a fold into a neighbouring one-qubit matrix of their axis (the H of
+// the QFT stage), and the pair terms that share a centre bit q collect in ONE star op -- the whole
+// controlled-phase ladder of a QFT stage (qlib/macros4parsing.py:386-463, one cp per lower qubit).  On the
+// device a star costs about two complex multiplies per amplitude whatever its length; the <= 4-bit tables
+// it replaces cost one look-up + multiply per three controls.  Stars that stay short go back to tables.
+struct QuadForm { cplx g, u[4], w[4][4]; };
+bool quad_form(const dqe_t* h, const HostOp& o, QuadForm* q) {
+  const int nb = (int)o.m.nb;
+  if (nb < 1 || nb > 4) return false;
+  auto T = [&](int t) { return cplx(h->cpool[o.m.c_off + t].x, h->cpool[o.m.c_off + t].y); };
+  auto e = [&](int i) { return 1 << (nb - 1 - i); };   // table index of bit b[i] (b[0] = MSB)
+  q->g = T(0);
+  if (std::abs(q->g) == 0.0) return false;
+  for (int i = 0; i < nb; ++i) {
+    if (std::abs(T(e(i))) == 0.0) return false;
+    q->u[i] = T(e(i)) / q->g;
+  }
+  for (int i = 0; i < nb; ++i)
+    for (int j = i + 1; j < nb; ++j) q->w[i][j] = T(e(i) | e(j)) * q->g / (T(e(i)) * T(e(j)));
+  for (int t = 0; t < (1 << nb); ++t) {
+    cplx v = q->g;
+    for (int i = 0; i < nb; ++i) if (t & e(i)) v *= q->u[i];
+    for (int i = 0; i < nb; ++i)
+      for (int j = i + 1; j < nb; ++j) if ((t & e(i)) && (t & e(j))) v *= q->w[i][j];
+    if (std::abs(v - T(t)) > 1e-14 * std::max(1.0, std::abs(T(t)))) return false;
+  }
+  return true;
+}
+inline uint8_t* leaves_of(HostOp& o) { return reinterpret_cast<uint8_t*>(&o.m) + kLadderLeafOff; }
+
+// does `e` stop a diagonal term on bits `mine` from moving in front of it?
+bool blocks_diagonal(const HostOp& e, uint64_t mine) {
+  if (e.kind != 0 || e.m.type == OP_PROBS || e.m.type == OP_MEASURE) return true;
+  if (e.need & mine) return true;
+  if (e.m.type == OP_PAULI_SAMPLED || e.m.type == OP_COLLAPSE || e.m.type == OP_INJECT) return (touched_bits(e) & mine) != 0;
+  return false;
+}
+
+void ladderize(dqe_t* h) {
+  if (h->formalism != DQE_KET || !h->ladder || !h->merge || !h->fuse) return;
+  int ndiag = 0;
+  for (const HostOp& o : h->queue) ndiag += o.kind == 0 && o.m.type == OP_DIAG && o.m.nb >= 2;
+  if (ndiag < 4) return;
+  std::vector<HostOp> out;
+  out.reserve(h->queue.size());
+  const double eps = 1e-15;
+  auto is_id = [&](cplx z) { return std::abs(z - 1.0) < eps; };
+  const int kDepth = 256;
+
+  // one-bit phase diag(d0, d1) on `bit`
+  auto place_phase = [&](const HostOp& src, int bit, cplx d0, cplx d1) {
+    if (is_id(d0) && is_id(d1)) return;
+    const uint64_t mine = 1ull << bit;
+    int depth = 0;
+    for (size_t k = out.size(); k-- > 0 && depth < kDepth; ++depth) {
+      HostOp& e = out[k];
+      if (e.kind >= 2) continue;
+      if (e.kind == 0 && e.m.pred_bit == src.m.pred_bit && !e.pctrl && !e.pctrl2 && e.m.b[0] == bit && e.m.nb == 1) {
+        if (e.m.type == OP_MAT1) {
+          cplx M[4];
+          for (int i = 0; i < 4; ++i) M[i] = cplx(h->cpool[e.m.c_off + i].x, h->cpool[e.m.c_off + i].y);
+          M[0] *= d0; M[1] *= d0; M[2] *= d1; M[3] *= d1;   // D . M
+          e.m.c_off = add_consts(h, M, 4);
+          return;
+        }
+        if (e.m.type == OP_DIAG) {
+          const cplx d[2] = {cplx(h->cpool[e.m.c_off].x, h->cpool[e.m.c_off].y) * d0,
+                             cplx(h->cpool[e.m.c_off + 1].x, h->cpool[e.m.c_off + 1].y) * d1};
+          e.m.c_off = add_consts(h, d, 2);
+          return;
+        }
+      }
+      if (e.kind == 0 && e.m.type == OP_MAT2 && e.m.pred_bit == src.m.pred_bit && !e.pctrl && !e.pctrl2 &&
+          (e.m.b[0] == bit || e.m.b[1] == bit)) {
+        cplx M[16];
+        for (int i = 0; i < 16; ++i) M[i] = cplx(h->cpool[e.m.c_off + i].x, h->cpool[e.m.c_off + i].y);
+        const int sh = e.m.b[0] == bit ? 1 : 0;   // row index = b[0] value * 2 + b[1] value
+        for (int r = 0; r < 4; ++r)
+          for (int c = 0; c < 4; ++c) M[r * 4 + c] *= ((r >> sh) & 1) ? d1 : d0;   // D . M
+        e.m.c_off = add_consts(h, M, 16);
+        return;
+      }
+      if (blocks_diagonal(e, mine)) break;
+    }
+    HostOp o = src;
+    memset(&o.m, 0, sizeof(o.m));
+    o.nf = 0; o.pctrl = o.pctrl2 = 0; o.need = 0;
+    o.m.type = OP_DIAG; o.m.pred_bit = src.m.pred_bit; o.m.nb = 1; o.m.b[0] = (uint8_t)bit;
+    const cplx d[2] = {d0, d1};
+    o.m.c_off = add_consts(h, d, 2); o.nconst = 2;
+    out.push_back(o);
+  };
+
+  // pair term w^(b_a b_b)
+  auto place_cp = [&](const HostOp& src, int a, int b, cplx w) {
+    if (is_id(w)) return;
+    const uint64_t mine = (1ull << a) | (1ull << b);
+    int depth = 0;
+    for (size_t k = out.size(); k-- > 0 && depth < kDepth; ++depth) {
+      HostOp& e = out[k];
+      if (e.kind >= 2) continue;
+      if (e.kind == 0 && e.m.type == OP_LADDER && e.m.pred_bit == src.m.pred_bit) {
+        uint8_t* lf = leaves_of(e);
+        int n = e.m.aux;
+        int q = e.m.b[0];
+        if (n == 1 && q != a && q != b && (lf[0] == a || lf[0] == b)) {   // a single pair term: its centre is free
+          const uint8_t t = lf[0]; lf[0] = (uint8_t)q; e.m.b[0] = t; q = t;
+        }
+        if (q == a || q == b) {
+          const int leaf = q == a ? b : a;
+          int j = 0;
+          while (j < n && lf[j] != leaf) ++j;
+          std::vector<cplx> ws(n + 1);
+          for (int i = 0; i < n; ++i) ws[i] = cplx(h->cpool[e.m.c_off + i].x, h->cpool[e.m.c_off + i].y);
+          if (j < n) ws[j] *= w;
+          else if (n < kMaxLadderLeaves) { lf[n] = (uint8_t)leaf; ws[n] = w; ++n; }
+          else j = -1;
+          if (j >= 0) {
+            e.m.aux = n;
+            e.m.c_off = add_consts(h, ws.data(), n); e.nconst = n;
+            return;
+          }
+        }
+      }
+      if (blocks_diagonal(e, mine)) break;
+    }
+    HostOp o = src;
+    memset(&o.m, 0, sizeof(o.m));
+    o.nf = 0; o.pctrl = o.pctrl2 = 0; o.need = 0;
+    o.m.type = OP_LADDER; o.m.pred_bit = src.m.pred_bit; o.m.nb = 1; o.m.b[0] = (uint8_t)a; o.m.aux = 1;
+    leaves_of(o)[0] = (uint8_t)b;
+    o.m.c_off = add_consts(h, &w, 1); o.nconst = 1;
+    out.push_back(o);
+  };
+
+  for (const HostOp& o : h->queue) {
+    QuadForm q;
+    if (o.kind == 0 && o.m.type == OP_DIAG && quad_form(h, o, &q)) {
+      const int nb = (int)o.m.nb;
+      for (int i = 0; i < nb; ++i) place_phase(o, o.m.b[i], i == 0 ? q.g : cplx(1.0), (i == 0 ? q.g : cplx(1.0)) * q.u[i]);
+      for (int i = 0; i < nb; ++i)
+        for (int j = i + 1; j < nb; ++j) place_cp(o, o.m.b[i], o.m.b[j], q.w[i][j]);
+      continue;
+    }
+    if (o.kind == 0 && o.m.type == OP_MAT1 && !o.pctrl && !o.pctrl2) {
+      // a pending one-bit phase of this axis moves forward into the matrix: M . D
+      const int bit = o.m.b[0];
+      const uint64_t mine = 1ull << bit;
+      int depth = 0;
+      HostOp m = o;
+      for (size_t k = out.size(); k-- > 0 && depth < kDepth; ++depth) {
+        HostOp& e = out[k];
+        if (e.kind >= 2) continue;
+        if (e.kind == 0 && e.m.type == OP_DIAG && e.m.nb == 1 && e.m.b[0] == bit && e.m.pred_bit == o.m.pred_bit) {
+          cplx M[4];
+          for (int i = 0; i < 4; ++i) M[i] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+          const cplx d0(h->cpool[e.m.c_off].x, h->cpool[e.m.c_off].y), d1(h->cpool[e.m.c_off + 1].x, h->cpool[e.m.c_off + 1].y);
+          M[0] *= d0; M[2] *= d0; M[1] *= d1; M[3] *= d1;
+          m.m.c_off = add_consts(h, M, 4);
+          out.erase(out.begin() + k);
+          break;
+        }
+        if (blocks_diagonal(e, mine)) break;
+      }
+      out.push_back(m);
+      continue;
+    }
+    if (o.kind == 0 && o.m.type == OP_MAT2 && !o.pctrl && !o.pctrl2) {
+      HostOp m = o;
+      for (int side = 0; side < 2; ++side) {
+        const int bit = o.m.b[side];
+        const uint64_t mine = 1ull << bit;
+        int depth = 0;
+        for (size_t k = out.size(); k-- > 0 && depth < kDepth; ++depth) {
+          HostOp& e = out[k];
+          if (e.kind >= 2) continue;
+          if (e.kind == 0 && e.m.type == OP_DIAG && e.m.nb == 1 && e.m.b[0] == bit && e.m.pred_bit == o.m.pred_bit) {
+            cplx M[16];
+            for (int i = 0; i < 16; ++i) M[i] = cplx(h->cpool[m.m.c_off + i].x, h->cpool[m.m.c_off + i].y);
+            const cplx d0(h->cpool[e.m.c_off].x, h->cpool[e.m.c_off].y), d1(h->cpool[e.m.c_off + 1].x, h->cpool[e.m.c_off + 1].y);
+            const int sh = side == 0 ? 1 : 0;
+            for (int r = 0; r < 4; ++r)
+              for (int c = 0; c < 4; ++c) M[r * 4 + c] *= ((c >> sh) & 1) ? d1 : d0;   // M . D
+            m.m.c_off = add_consts(h, M, 16);
+            out.erase(out.begin() + k);
+            break;
+          }
+          if (blocks_diagonal(e, mine)) break;
+        }
+      }
+      out.push_back(m);
+      continue;
+    }
+    out.push_back(o);
+  }
+  // short stars are cheaper as one table look-up
+  for (HostOp& o : out) {
+    if (o.kind != 0 || o.m.type != OP_LADDER) continue;
+    const int n = o.m.aux;
+    if (n > 3) { h->ladders_built++; continue; }
+    uint8_t lf[4];
+    cplx w[4];
+    for (int j = 0; j < n; ++j) { lf[j] = leaves_of(o)[j]; w[j] = cplx(h->cpool[o.m.c_off + j].x, h->cpool[o.m.c_off + j].y); }
+    const int q = o.m.b[0], pred = o.m.pred_bit;
+    cplx table[16];
+    for (int t = 0; t < (2 << n); ++t) {
+      cplx v = 1.0;
+      if (t >> n) for (int j = 0; j < n; ++j) if ((t >> (n - 1 - j)) & 1) v *= w[j];
+      table[t] = v;
+    }
+    memset(&o.m, 0, sizeof(o.m));
+    o.m.type = OP_DIAG; o.m.pred_bit = pred; o.m.nb = (uint32_t)(n + 1);
+    o.m.b[0] = (uint8_t)q;
+    for (int j = 0; j < n; ++j) o.m.b[1 + j] = lf[j];
+    o.m.c_off = add_consts(h, table, 2 << n); o.nconst = 2 << n;
+  }
+  h->queue.swap(out);
+}
+
 // -------- planner --------------------------------------------------------------------------
 int build_segs(uint64_t mask, Seg* segs, int cap) {
   int n = 0, src = 0;
@@ -799,6 +1029,26 @@ struct Planner {
   // localise one host op as a stand-alone micro-op of the pass
   MicroOp localise(const HostOp* ho, uint64_t tile, size_t pass_const_begin) {
     MicroOp m = ho->m;
+    if (m.type == OP_LADDER) {
+      // centre like a diagonal bit; leaves: tile-local ones first (ascending, so that the ones on thread-id bits
+      // lead), then the outer ones; the phases follow their leaves
+      const uint8_t* lf = reinterpret_cast<const uint8_t*>(&ho->m) + kLadderLeafOff;
+      uint8_t* out = reinterpret_cast<uint8_t*>(&m) + kLadderLeafOff;
+      const int ph = ho->m.b[0], nl = ho->m.aux;
+      m.b[0] = ((tile >> ph) & 1ull) ? (uint8_t)local_of(tile, ph) : (uint8_t)(kOuter + ph);
+      std::vector<std::pair<int, int>> loc, outer;   // (position, leaf index)
+      for (int j = 0; j < nl; ++j) {
+        if ((tile >> lf[j]) & 1ull) loc.push_back({local_of(tile, lf[j]), j});
+        else outer.push_back({kOuter + lf[j], j});
+      }
+      std::sort(loc.begin(), loc.end());
+      m.c_off = (int)(dev_consts.size() - pass_const_begin);
+      int k = 0;
+      for (auto& pr : loc) { out[k++] = (uint8_t)pr.first; dev_consts.push_back(h->cpool[ho->m.c_off + pr.second]); }
+      for (auto& pr : outer) { out[k++] = (uint8_t)pr.first; dev_consts.push_back(h->cpool[ho->m.c_off + pr.second]); }
+      m.flags = (int)loc.size() | ((int)outer.size() << 8);
+      return m;
+    }
     if (m.type == OP_DIAG) {
       for (uint32_t i = 0; i < m.nb; ++i) {
         const int ph = ho->m.b[i];
@@ -1595,6 +1845,22 @@ int ensure_partials(dqe_t* h, size_t n) {
 int do_flush(dqe_t* h) {
   if (int rc = check_ready(h)) return rc;
   if (h->queue.empty()) return 0;
+  ladderize(h);
+  if (getenv("DQE_DUMP_QUEUE")) {   // the queue the planner sees, with constants (debugging / host-side tests)
+    for (const HostOp& o : h->queue) {
+      if (o.kind != 0) { fprintf(stderr, "Q kind=%d\n", o.kind); continue; }
+      fprintf(stderr, "Q type=%d pred=%d nb=%u aux=%d pctrl=%llu b=", o.m.type, o.m.pred_bit, o.m.nb, o.m.aux,
+              (unsigned long long)o.pctrl);
+      for (uint32_t i = 0; i < o.m.nb; ++i) fprintf(stderr, "%s%d", i ? "," : "", (int)o.m.b[i]);
+      if (o.m.type == OP_LADDER) {
+        fprintf(stderr, " leaves=");
+        for (int j = 0; j < o.m.aux; ++j) fprintf(stderr, "%s%d", j ? "," : "", (int)(reinterpret_cast<const uint8_t*>(&o.m) + kLadderLeafOff)[j]);
+      }
+      fprintf(stderr, " c=");
+      for (int i = 0; i < o.nconst; ++i) fprintf(stderr, "%s%.17g,%.17g", i ? ";" : "", h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+      fprintf(stderr, "\n");
+    }
+  }
   Planner pl;
   pl.h = h;
   if (!pl.plan()) {
@@ -1603,7 +1869,7 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL", "KBLOCK"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL", "KBLOCK", "LADDER"};
     static const char* gnames[] = {"?", "gPAULI1", "-", "gMAT1X2", "gDEPOL2", "-", "-", "gCOLLAPSE",
                                    "gTRACE", "gINJECT", "gDIAG", "gXPAT", "-", "-", "-", "gDYN1"};
     for (PlannedPass& P : pl.passes) {
@@ -1615,6 +1881,10 @@ int do_flush(dqe_t* h) {
         if (m.type == OP_GROUP && (m.flags & 17))
           fprintf(stderr, " [%s%s]", (m.flags & 1) ? "x>" : "", (m.flags & 16) ? ">x" : "");
         if (m.type == OP_CLASSICAL) { fprintf(stderr, " CL%s%d", m.c_off ? "p" : "", m.flags); continue; }
+        if (m.type == OP_LADDER) {
+          fprintf(stderr, " LADDER%s(%d;%d+%d)", m.pred_bit >= 0 ? "?" : "", (int)m.b[0], m.flags & 0xff, (m.flags >> 8) & 0xff);
+          continue;
+        }
         fprintf(stderr, " %s%s(", names[m.type], m.pred_bit >= 0 ? "?" : "");
         for (uint32_t b = 0; b < m.nb; ++b) fprintf(stderr, "%s%d", b ? "," : "", (int)m.b[b]);
         fprintf(stderr, ")");
@@ -1833,7 +2103,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->ladder = 1; h->ladders_built = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -2561,6 +2831,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->pin_axes = (uint64_t)value;
   } else if (!strcmp(key, "kblock")) {
     h->kblock = value ? 1 : 0;
+  } else if (!strcmp(key, "ladder")) {
+    h->ladder = value ? 1 : 0;
   } else if (!strcmp(key, "shot_stride")) {
     if (value < 1) return fail(h, DQE_EINVAL, "shot_stride >= 1");
     h->shot_stride = value;

@@ -433,6 +433,66 @@ def test_planner_fuses_gate_runs_into_dense_blocks(n, tile):
     assert np.abs(fused - b2.g.full_state()).max() < TOL
 
 
+@pytest.mark.parametrize("n,batch,tile,threads", [(14, 2, 11, 128), (13, 1, 10, 64), (12, 3, 8, 64), (9, 2, 11, 128),
+                                                  (16, 1, 11, 256)])
+def test_controlled_phase_stars(n, batch, tile, threads):
+    """OP_LADDER: the controlled-phase ladders of QFT-like circuits (the reference lowers cp to
+    rz . CX . rz . CX . rz, qlib/macros4parsing.py:386-463) are collected at flush into one star op per centre
+    qubit, their one-bit phases fold into the neighbouring H.  Centre and leaves on thread-id bits, element
+    bits and outside the tile; predicated phases; three-qubit diagonals that are no quadratic form (CCZ) and
+    non-unitary diagonals stay tables.  Same state as the oracle and as the engine with the pass disabled."""
+    rng = np.random.default_rng(5 + n + tile)
+
+    def rz(t):
+        return np.diag([np.exp(-0.5j * t), np.exp(0.5j * t)])
+
+    def program(b):
+        for a in range(n):
+            b.alloc_axis(a)
+            b.apply_1q(a, H)
+        order = [int(x) for x in rng.permutation(n)]
+        for stage, q in enumerate(order):
+            b.apply_1q(q, H)
+            for c in order[stage + 1:]:
+                t = float(rng.uniform(0.1, 3.0))
+                kind = rng.integers(5)
+                if kind == 0:      # the reference's lowering, target q
+                    b.apply_1q(q, rz(t / 2)); b.apply_2q(c, q, CNOT); b.apply_1q(q, rz(t / 2)); b.apply_2q(c, q, CNOT)
+                    b.apply_1q(q, rz(t / 2))
+                elif kind == 1:
+                    b.apply_diag([q, c], [1, 1, 1, np.exp(1j * t)])
+                elif kind == 2:
+                    b.apply_ctrl_1q(c, q, np.diag([1, np.exp(1j * t)]))
+                elif kind == 3:
+                    b.apply_diag([c, q], np.exp(1j * rng.uniform(0, 6, size=4)))
+                else:
+                    b.apply_diag([q], [np.exp(0.3j * t), np.exp(-0.1j * t)])
+            if stage % 4 == 1 and stage + 3 < n:
+                b.apply_diag(order[stage + 1:stage + 4], [1, 1, 1, 1, 1, 1, 1, -1])              # CCZ
+                b.apply_diag([q, order[stage + 1]], [1.0, 0.9, 0.8, 0.7j])                         # not unitary
+            if stage == 2:
+                b.apply_1q(order[0], H)       # (the phases alone leave it in |0>: outcome 1 would be impossible)
+                b.measure(order[0], 3, 1, False, 0.0)
+                b.set_predicate(3)
+                for c in order[4:9]:
+                    b.apply_diag([order[1], c], [1, 1, 1, np.exp(0.4j)])
+                b.set_predicate(-1)
+        b.check("stars")
+
+    state = rng.bit_generator.state
+    b = Both("ket", n, batch, 3, tile_bits=tile)
+    b.g.set_option("threads", threads)
+    program(b)
+    with_stars = b.g.full_state()
+    rng.bit_generator.state = state
+    b2 = Both("ket", n, batch, 3, tile_bits=tile)
+    b2.g.set_option("threads", threads)
+    b2.g.set_option("ladder", 0)
+    program(b2)
+    assert b.g.stats()["micro_ops"] < b2.g.stats()["micro_ops"]
+    assert np.abs(with_stars - b2.g.full_state()).max() < TOL
+
+
 @pytest.mark.parametrize("formalism", ["ket", "dm"])
 def test_forced_outcomes_bit_exact(formalism):
     n = 5
