@@ -41,6 +41,17 @@ enum OpType : int32_t {
                       // kMaxLadderLeaves leaf bits j in the payload bytes, w_j in the constant pool): the whole
                       // controlled-phase ladder of one QFT stage costs about two complex multiplies per amplitude,
                       // however many controls it has.  flags = tile-local leaves | outer leaves << 8
+  OP_SWAP = 20,       // ket: exchange two tile bits (a SWAP gate is a permutation: two loads, two stores, no arithmetic)
+  OP_KGROUP = 19,     // ket block sweep: every thread holds the 16 amplitudes spanned by FOUR tile bits (b[0..3],
+                      // ascending, all >= 3 so that a warp's accesses stay conflict-free) in registers and runs the
+                      // following `aux` sub-ops on them -- one-qubit matrices on those bits (controls anywhere),
+                      // diagonal tables and controlled-phase stars on any bits -- in ONE shared-memory round trip:
+                      // the H / phase-ladder alternation of a QFT stage costs one sweep per four stages.
+                      // Sub-ops keep their type (OP_MAT1, OP_DIAG, OP_LADDER) and carry block ranks:
+                      //   MAT1: b[4] = rank of the target, lctrl = thread-side control mask, lctrl2 = element mask
+                      //   DIAG: b[4 + i] = rank + 1 of table bit i when it is a block bit, else 0
+                      //   LADDER: b[1] = rank + 1 of the centre or 0; leaves ordered thread | element (rank) | outer,
+                      //           flags = nt | ne << 8 | no << 16
   OP_CLASSICAL = 16,  // per-shot classical instructions (ClInstr x flags, packed behind the 16-byte header):
                       // run redundantly by every thread of the CTA (identical values: no barrier needed)
   OP_MEASURE = 13,    // fused measurement (cluster launch): tile partials -> DSMEM sum over the shot's CTAs ->
@@ -215,6 +226,11 @@ __device__ __forceinline__ uint32_t ins0(uint32_t p, int j) {
   return ((p & ~lo) << 1) | (p & lo);
 }
 
+__device__ __forceinline__ uint32_t ins0_4(uint32_t p, const int* sorted) {
+  p = ins0(p, sorted[0]); p = ins0(p, sorted[1]); p = ins0(p, sorted[2]); p = ins0(p, sorted[3]);
+  return p;
+}
+
 template <typename SegT>
 __device__ __forceinline__ uint64_t deposit(uint64_t x, const SegT* segs, int n) {
   uint64_t r = 0;
@@ -321,6 +337,19 @@ __device__ __forceinline__ void op_mat2(double2* tile, uint32_t T, const MicroOp
   }
 }
 
+__device__ __forceinline__ void op_swap(double2* tile, uint32_t T, const MicroOp& op) {
+  const int ja = op.b[0], jb = op.b[1];
+  const int jlo = ja < jb ? ja : jb, jhi = ja < jb ? jb : ja;
+  const uint32_t lc = op.lctrl;
+  for (uint32_t p = threadIdx.x; p < (T >> 2); p += blockDim.x) {
+    const uint32_t i0 = ins0(ins0(p, jlo), jhi);
+    if ((i0 & lc) != lc) continue;
+    const uint32_t i1 = i0 | (1u << ja), i2 = i0 | (1u << jb);
+    const double2 x = tile[i1], y = tile[i2];
+    tile[i1] = y; tile[i2] = x;
+  }
+}
+
 __device__ __forceinline__ void op_diag(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
                                         uint64_t base) {
   const int nb = op.nb;
@@ -353,6 +382,7 @@ struct DiagPrep {
   uint32_t fixed;
   uint32_t m0, m1, m2, m3;     // single-bit masks of the tile-local bits (0 when unused)
   uint32_t s0, s1, s2, s3;     // their weights in the table index
+  uint32_t h0, h1, h2, h3;     // block sweeps: element-index masks of the table bits that are block bits
 };
 constexpr int kMaxDiagRun = 16;
 struct LadderPrep {
@@ -499,6 +529,148 @@ __device__ __forceinline__ void op_diag_run(double2* tile, uint32_t T, const Mic
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// ket block sweep (OP_KGROUP).  v[e]: bit k of e <-> block bit s4[k].
+template <int R>
+__device__ __forceinline__ void kg_mat1(double2 (&v)[16], const double2* __restrict__ cs, uint32_t em) {
+  const double2 m00 = cs[0], m01 = cs[1], m10 = cs[2], m11 = cs[3];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (e & (1 << R)) continue;
+    if ((e & em) == em) {     // element-side controls (uniform)
+      double2& x0 = v[e];
+      double2& x1 = v[e | (1 << R)];
+      const double2 p = cmul(m10, x0);
+      x0 = cfma(m01, x1, cmul(m00, x0));
+      x1 = cfma(m11, x1, p);
+    }
+  }
+}
+
+__device__ __noinline__ void run_kgroup(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
+                                        const double2* s_consts, uint64_t base, uint64_t cw, DiagPrep* prep,
+                                        LadderPrep* lprep) {
+  const int nsub = g.aux;
+  // ---- prep: the tile-uniform part of every sub-op
+  {
+    const int grp = threadIdx.x >> 3, part = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+    for (int k0 = 0; k0 < nsub; k0 += ngrp) {
+      const int k = k0 + grp;
+      const bool act = k < nsub && sub[k < nsub ? k : 0].type == OP_LADDER;
+      double2 gg = make_double2(1.0, 0.0);
+      if (act) {
+        const MicroOp& op = sub[k];
+        const int nt = op.flags & 0xff, ne = (op.flags >> 8) & 0xff, no = (op.flags >> 16) & 0xff;
+        const uint8_t* lf = ladder_leaves(op);
+        for (int j = part; j < no; j += 8)
+          if ((base >> (lf[nt + ne + j] - kOuter)) & 1ull) gg = cmul(gg, s_consts[op.c_off + nt + ne + j]);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        double2 hh;
+        hh.x = __shfl_xor_sync(0xffffffffu, gg.x, o);
+        hh.y = __shfl_xor_sync(0xffffffffu, gg.y, o);
+        gg = cmul(gg, hh);
+      }
+      if (act && part == 0) {
+        const MicroOp& op = sub[k];
+        LadderPrep L;
+        L.G = gg;
+        L.on = !(op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull));
+        L.qmask = 0u;
+        if (op.b[0] >= kOuter) L.on = L.on && ((base >> (op.b[0] - kOuter)) & 1ull);
+        else if (op.b[1] == 0) L.qmask = 1u << op.b[0];     // centre on a thread-side tile bit
+        lprep[k] = L;
+      }
+    }
+  }
+  if ((int)threadIdx.x < nsub && sub[threadIdx.x].type == OP_DIAG) {
+    const MicroOp& op = sub[threadIdx.x];
+    DiagPrep d;
+    d.c_off = op.c_off; d.nl = 0; d.fixed = 0;
+    d.on = !(op.pred_bit >= 0 && !((cw >> op.pred_bit) & 1ull));
+    uint32_t mk[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, hk[4] = {0, 0, 0, 0};
+    const int nb = op.nb;
+    for (int s = 0; s < nb; ++s) {
+      const uint32_t w = 1u << (nb - 1 - s);
+      if (op.b[s] >= kOuter) { if ((base >> (op.b[s] - kOuter)) & 1ull) d.fixed |= w; }
+      else {
+        if (op.b[4 + s]) hk[d.nl] = 1u << (op.b[4 + s] - 1); else mk[d.nl] = 1u << op.b[s];
+        sh[d.nl] = w; ++d.nl;
+      }
+    }
+    d.m0 = mk[0]; d.m1 = mk[1]; d.m2 = mk[2]; d.m3 = mk[3];
+    d.s0 = sh[0]; d.s1 = sh[1]; d.s2 = sh[2]; d.s3 = sh[3];
+    d.h0 = hk[0]; d.h1 = hk[1]; d.h2 = hk[2]; d.h3 = hk[3];
+    prep[threadIdx.x] = d;
+  }
+  __syncthreads();
+  // ---- sweep
+  const int s4[4] = {g.b[0], g.b[1], g.b[2], g.b[3]};
+  const uint32_t b0 = __shfl_sync(0xffffffffu, 16u << g.b[0], 0), b1 = __shfl_sync(0xffffffffu, 16u << g.b[1], 0);
+  const uint32_t b2 = __shfl_sync(0xffffffffu, 16u << g.b[2], 0), b3 = __shfl_sync(0xffffffffu, 16u << g.b[3], 0);
+#define DQE_KOFF(e) ((((e) & 1) ? b0 : 0u) | (((e) & 2) ? b1 : 0u) | (((e) & 4) ? b2 : 0u) | (((e) & 8) ? b3 : 0u))
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    char* __restrict__ tpb = reinterpret_cast<char*>(tile + i0);
+    double2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = *reinterpret_cast<double2*>(tpb + DQE_KOFF(e));
+    for (int s = 0; s < nsub; ++s) {
+      const MicroOp& op = sub[s];
+      const int4 hdr = op_header(&op);
+      if (hdr.x == OP_MAT1) {
+        if (hdr.y >= 0 && !((cw >> hdr.y) & 1ull)) continue;
+        if ((base & op.octrl) != op.octrl) continue;
+        if ((i0 & op.lctrl) != op.lctrl) continue;
+        const double2* cs = s_consts + hdr.w;
+        const uint32_t em = op.lctrl2;
+        switch (op.b[4]) {
+          case 0: kg_mat1<0>(v, cs, em); break;
+          case 1: kg_mat1<1>(v, cs, em); break;
+          case 2: kg_mat1<2>(v, cs, em); break;
+          default: kg_mat1<3>(v, cs, em); break;
+        }
+      } else if (hdr.x == OP_DIAG) {
+        const DiagPrep d = prep[s];
+        if (!d.on) continue;
+        const uint32_t tf = d.fixed + ((i0 & d.m0) ? d.s0 : 0u) + ((i0 & d.m1) ? d.s1 : 0u) + ((i0 & d.m2) ? d.s2 : 0u) +
+                            ((i0 & d.m3) ? d.s3 : 0u);
+        const double2* tb = s_consts + d.c_off + tf;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const uint32_t idx = ((e & d.h0) ? d.s0 : 0u) + ((e & d.h1) ? d.s1 : 0u) + ((e & d.h2) ? d.s2 : 0u) + ((e & d.h3) ? d.s3 : 0u);
+          v[e] = cmul(v[e], tb[idx]);
+        }
+      } else {   // OP_LADDER
+        const LadderPrep L = lprep[s];
+        if (!L.on) continue;
+        if (L.qmask && !(i0 & L.qmask)) continue;
+        const int nt = hdr.z & 0xff, ne = (hdr.z >> 8) & 0xff;
+        const uint8_t* lf = ladder_leaves(op);
+        const double2* w = s_consts + hdr.w;
+        double2 sc = L.G;
+        for (int j = 0; j < nt; ++j)
+          if ((i0 >> lf[j]) & 1u) sc = cmul(sc, w[j]);
+        const uint32_t qe = op.b[1] ? (1u << (op.b[1] - 1)) : 0u;
+        for (int j = 0; j < ne; ++j) {
+          const uint32_t eb = 1u << lf[nt + j];
+          const double2 wj = w[nt + j];
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((e & eb) && (e & qe) == qe) v[e] = cmul(v[e], wj);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if ((e & qe) == qe) v[e] = cmul(v[e], sc);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) *reinterpret_cast<double2*>(tpb + DQE_KOFF(e)) = v[e];
+  }
+#undef DQE_KOFF
+}
 
 // ------------------------------------------------------------------------------------------
 // Dense k-qubit block (k = 3, 4) on the FP64 tensor cores.
@@ -733,10 +905,6 @@ __device__ __forceinline__ void op_pauli1(double2* tile, uint32_t T, const Micro
   }
 }
 
-__device__ __forceinline__ uint32_t ins0_4(uint32_t p, const int* sorted) {
-  p = ins0(p, sorted[0]); p = ins0(p, sorted[1]); p = ins0(p, sorted[2]); p = ins0(p, sorted[3]);
-  return p;
-}
 __device__ __forceinline__ void sort4(const uint8_t* b, int* s) {
   s[0] = b[0]; s[1] = b[1]; s[2] = b[2]; s[3] = b[3];
 #pragma unroll
@@ -1561,7 +1729,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       const MicroOp& op = s_ops[cur];
       const int op_type = hdr.x, op_pred = hdr.y, op_flags = hdr.z, hdr_coff = hdr.w;
       const double2* cs = s_consts + hdr.w;
-      o = cur + 1 + (op_type == OP_GROUP ? hdr.w : 0);
+      o = cur + 1 + ((op_type == OP_GROUP || op_type == OP_KGROUP) ? hdr.w : 0);
       if (o < pp.nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if (op_type == OP_CLASSICAL) {
@@ -1595,6 +1763,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           }
           case OP_KBLOCK:
             if (op.nb == 4) op_kblock<4>(tile, T, op, cs); else op_kblock<3>(tile, T, op, cs);
+            break;
+          case OP_SWAP:
+            if ((base & op.octrl) == op.octrl) op_swap(tile, T, op);
+            break;
+          case OP_KGROUP:
+            run_kgroup(tile, T, op, &s_ops[cur + 1], s_consts, base, cw, s_diag, s_lad);
             break;
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;

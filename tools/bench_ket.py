@@ -18,15 +18,23 @@ CASES = [("c3_qft26_4qpu_cat.json.gz", 28, 4, 9), ("c5_qft30_mono.json.gz", 30, 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--case", default="", help="substring filter on the fixture name")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--fused-only", action="store_true")
     a = ap.parse_args()
     out = []
     for name, nq, nqpu, npos in CASES:
+        if a.case not in name:
+            continue
         ops, _ = opstream.load(os.path.join(GOLDEN, name))
         dqc = hardware.DQCSpec.uniform(nqpu, num_positions=npos, num_comm_qubits=2 if nqpu > 1 else 0)
-        for fuse in (1, 0):
+        for fuse in ((1,) if a.fused_only else (1, 0)):
             e = Engine("ket", nq, 1, seed=1)
             e.set_option("fuse", fuse)
             e.set_option("merge", fuse)
+            for kv in a.opt:
+                k, v = kv.split("=")
+                e.set_option(k, int(v))
             best = None
             for rep in range(a.reps + 1):
                 e.reinit()
@@ -41,7 +49,7 @@ def main():
                 e.time_passes(False)
                 st = e.stats()
                 if rep and (best is None or wall < best["wall_s"]):
-                    best = dict(case=name, fused=bool(fuse), wall_s=wall, pass_ms=ms, passes=n,
+                    best = dict(case=name, fused=bool(fuse), opts=a.opt, wall_s=wall, pass_ms=ms, passes=n,
                                 api_ops=st["api_ops"], micro_ops=st["micro_ops"],
                                 GBps=32.0 * amps / (ms * 1e-3) / 1e9,
                                 gate_updates_per_s=st["api_ops"] / wall,
