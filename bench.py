@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--noise", default="depol", choices=["depol", "depol+dephase"],
                     help="depol: examples/run_experiment.py:80-87; depol+dephase adds a memory dephasing channel of the "
                          "same rate (BASELINE.json config 2 names it; not wired by any reference hardware spec)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded state-vector record (config 5)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="engine option for A/B measurements (dqe_set_option), e.g. --opt tmap=0")
     return ap.parse_args()
@@ -246,6 +247,40 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def sharded_ket_records(rank, world, local):
+    """N > 1: QFT-(30 + log2 N) (weak: 16 GiB of amplitudes per GPU) and QFT-30 (strong) as ONE state vector sharded
+    over the ranks; seconds = wall time of the whole circuit (executor walk + passes + exchanges), max over ranks,
+    best of 2.  Self-checked inside (norm 1, |amplitude| = 2^(-n/2) to 1e-10)."""
+    import types
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_sharded
+
+    g = int(round(np.log2(world)))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"what": "config 5: one state vector sharded over the ranks by its high-order qubits; all global axes are "
+                   "exchanged in one device-synchronised kernel over CUDA-IPC peer memory (k_peer_exchange), SWAPs are "
+                   "slot relabellings, measurement / norms through engine kernels",
+           "nvlink_peer_copy_GBps_reference": 770.0, "hbm_peak_GBps": hbm}
+    for label, n in (("weak", 30 + g), ("strong", 30)):
+        with _StdoutToStderr():
+            r = run_sharded.run_fixture(types.SimpleNamespace(n=n, circuit="qft", reps=2, peer=1), rank, world, local)
+        keep = ("circuit", "n", "n_gpus", "seconds", "max_abs_err", "norm", "exchanges", "exchange_bytes_per_rank",
+                "exchange_seconds", "nvlink_GBps_per_dir_per_gpu", "relabelled_swaps", "host_enqueue_seconds", "pass_ms",
+                "passes_per_rank", "pass_GBps", "shard_bytes", "micro_ops")
+        rec = {k: r[k] for k in keep}
+        rec["pass_frac_of_hbm_peak"] = r["pass_GBps"] / hbm
+        rec["nvlink_frac_of_peer_copy"] = (r["nvlink_GBps_per_dir_per_gpu"] or 0.0) / 770.0
+        out[label] = rec
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     a = parse()
@@ -352,6 +387,14 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_total, t_dev = float(t[0]), float(t[1])
+    sharded = None
+    if world > 1 and not a.no_sharded:
+        # BASELINE config 5 under the same launch: the state vector sharded over the N ranks by its high-order
+        # qubits (dqc_simulator_b200/sharded.py), exchanges as one device-synchronised kernel over peer memory
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        sharded = sharded_ket_records(rank, world, local)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,6 +447,8 @@ def main():
             "avg_launch_ms": sg_ms / max(sg_n, 1)},
         "clocks": clocks,
     }
+    if sharded is not None:
+        line["sharded_ket"] = sharded
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)

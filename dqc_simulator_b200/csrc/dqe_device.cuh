@@ -2061,6 +2061,143 @@ __global__ void __launch_bounds__(256) k_peer_swap(double2* __restrict__ lo, dou
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-axis global <-> local exchange over peer memory, synchronised ON THE DEVICE.
+// s rank bits (mask J of the rank id) trade places with s local bits L[0..s): new[R_J = x, L = y] = old[R_J = y, L = x].
+// Rank r swaps, with every partner p that differs from it in the J bits only, its elements whose L value is x_p
+// against the partner's elements whose L value is x_r -- 2^(m-s) pairs per partner, the lower rank of a pair doing
+// the first half of them, the higher rank the second half (both NVLink directions busy, no staging buffer).
+// No host barrier: a flag block behind each shard carries per-partner epoch counters.
+//   start : block 0 stores epoch -> partner.ready_from[r]; every CTA polls its OWN ready_from[p] before it touches p
+//   end   : the last CTA to finish (local atomic counter) stores epoch -> partner.done_from[r] and waits for its own
+//           done_from[p] -- the kernel, hence everything queued behind it on the stream, ends only when every
+//           partner has finished writing into this shard.
+// Polls give up after ~4 s of spinning and raise the error word instead of hanging the GPU.
+constexpr int kPeerFlagWords = 512;          // uint64 words behind the state buffer
+constexpr int kPeerReady = 0, kPeerDone = 64, kPeerCounter = 128, kPeerError = 129;
+struct ExchangeParams {
+  double2* mine;
+  double2* peer[64];        // shard base of every rank (entry `rank` = mine)
+  uint64_t epoch[64];       // per partner: number of this exchange between the two ranks (both count alike)
+  uint64_t flag_off;        // offset (in double2) of the flag block behind a shard
+  int32_t rank, s, m, nparts;
+  int32_t jbits[6];         // the rank bits, ascending
+  int32_t lbits[6];         // the local bits paired with them
+  int32_t lsorted[6];       // the local bits, ascending (zero insertion)
+};
+__device__ __forceinline__ volatile unsigned long long* peer_flags(double2* base, uint64_t off) {
+  return reinterpret_cast<volatile unsigned long long*>(base + off);
+}
+__device__ __forceinline__ bool poll_ge(volatile unsigned long long* w, unsigned long long want, volatile unsigned long long* err) {
+  const long long t0 = clock64();
+  while (*w < want) {
+    if (clock64() - t0 > 8000000000ll) { *err = 1ull; return false; }
+    __nanosleep(64);
+  }
+  return true;
+}
+__global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ ExchangeParams ep) {
+  volatile unsigned long long* myf = peer_flags(ep.mine, ep.flag_off);
+  const int r = ep.rank, s = ep.s;
+  int xr = 0;
+  for (int k = 0; k < s; ++k) xr |= ((r >> ep.jbits[k]) & 1) << k;
+  // ---- start handshake
+  if (blockIdx.x == 0 && (int)threadIdx.x >= 1 && (int)threadIdx.x < (1 << s)) {
+    const int d = threadIdx.x;
+    int p = r;
+    for (int k = 0; k < s; ++k) if ((d >> k) & 1) p ^= 1 << ep.jbits[k];
+    __threadfence_system();
+    peer_flags(ep.peer[p], ep.flag_off)[kPeerReady + r] = ep.epoch[p];
+  }
+  if ((int)threadIdx.x >= 1 && (int)threadIdx.x < (1 << s)) {
+    const int d = threadIdx.x;
+    int p = r;
+    for (int k = 0; k < s; ++k) if ((d >> k) & 1) p ^= 1 << ep.jbits[k];
+    poll_ge(myf + kPeerReady + p, ep.epoch[p], myf + kPeerError);
+  }
+  __syncthreads();
+  __threadfence_system();
+  // ---- the swaps: item = (partner d, pair index q)
+  const uint64_t per = 1ull << (ep.m - s), half = per >> 1;
+  const uint64_t items = (uint64_t)((1 << s) - 1) * half;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t it0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 4 * stride) {
+    double2 a[4], b[4];
+    double2* pa[4];
+    double2* pb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t it = it0 + (uint64_t)u * stride;
+      pa[u] = nullptr;
+      if (it < items) {
+        const int d = 1 + (int)(it / half);
+        uint64_t q = it % half;
+        int p = r;
+        for (int k = 0; k < s; ++k) if ((d >> k) & 1) p ^= 1 << ep.jbits[k];
+        if (r > p) q += half;
+        const int xp = xr ^ d;
+        uint64_t base = q;
+        for (int k = 0; k < s; ++k) {
+          const uint64_t lo = (1ull << ep.lsorted[k]) - 1ull;
+          base = ((base & ~lo) << 1) | (base & lo);
+        }
+        uint64_t im = base, ip = base;
+        for (int k = 0; k < s; ++k) {
+          im |= (uint64_t)((xp >> k) & 1) << ep.lbits[k];
+          ip |= (uint64_t)((xr >> k) & 1) << ep.lbits[k];
+        }
+        pa[u] = ep.mine + im; pb[u] = ep.peer[p] + ip;
+        a[u] = *pa[u]; b[u] = *pb[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (pa[u]) { *pa[u] = b[u]; *pb[u] = a[u]; }
+  }
+  // ---- end handshake
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned long long old = atomicAdd(const_cast<unsigned long long*>(myf + kPeerCounter), 1ull);
+    s_last = old == (unsigned long long)gridDim.x - 1ull;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) { myf[kPeerCounter] = 0ull; __threadfence_system(); }
+  if ((int)threadIdx.x >= 1 && (int)threadIdx.x < (1 << s)) {
+    const int d = threadIdx.x;
+    int p = r;
+    for (int k = 0; k < s; ++k) if ((d >> k) & 1) p ^= 1 << ep.jbits[k];
+    __threadfence_system();
+    peer_flags(ep.peer[p], ep.flag_off)[kPeerDone + r] = ep.epoch[p];
+    poll_ge(myf + kPeerDone + p, ep.epoch[p], myf + kPeerError);
+  }
+}
+
+// (sum |amp|^2 over axis bit = 0, over bit = 1) of a single-shot ket: the local part of a sharded measurement
+__global__ void __launch_bounds__(256) k_probs_bit(const double2* __restrict__ st, uint64_t n, int bit, double* out) {
+  double a0 = 0.0, a1 = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 v = st[i];
+    const double w = fma(v.x, v.x, v.y * v.y);
+    if ((i >> bit) & 1ull) a1 += w; else a0 += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  __shared__ double sa[8][2];
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5][0] = a0; sa[threadIdx.x >> 5][1] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) { t0 += sa[w][0]; t1 += sa[w][1]; }
+    out[2 * blockIdx.x] = t0; out[2 * blockIdx.x + 1] = t1;   // per-block partials: summed on the host in block order
+  }
+}
+
 // reduced density matrix / fidelity of <= 5 axes.  `rest` enumerates the live bits that are
 // traced over (dense index -> physical offset through segs).
 struct ReadoutParams {

@@ -61,6 +61,8 @@ struct PlannedPass {
   size_t smem;
   uint64_t amps;       // amplitudes touched per shot
   bool is_finish;
+  size_t first_op;       // index in the host queue of the first op of the run of ops this pass was cut from
+  uint64_t live_before;  // live mask in front of that op (streaming flush: where planning resumes)
   bool classical_only;   // nothing but classical instructions: runs as k_classical (one thread per shot)
   FinishParams fp;
 };
@@ -103,8 +105,17 @@ struct dqe_engine {
   std::string err;
   int cuda_failed;
   int tile_bits, min_run_bits, fuse, merge, group, tma, threads, ctas_per_sm, num_sms, persistent, cluster, cxperm, factor, tmap, prefetch;
+  int stream_ops;           // streaming flush: closed passes are launched every this many queued ops (0 = off)
+  size_t stream_next;
+  int stream_min_bits;      // ... for registers of at least this many bits (default 22: passes of >= 64 MiB)
+  int64_t stream_flushes;
   int kgroup;               // ket: block sweeps (OP_KGROUP)
   int64_t kgroups_built;
+  uint64_t peer_epoch[64];  // exchanges done with each partner rank (k_peer_exchange handshake)
+  cudaEvent_t xev0, xev1;   // device time of the peer exchanges
+  bool xev_ok, xev_pending;
+  double x_ms;
+  int64_t x_count, x_bytes;
   int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
   int64_t ladders_built;
   int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
@@ -782,6 +793,16 @@ bool blocks_diagonal(const HostOp& e, uint64_t mine) {
   return false;
 }
 
+bool host_is_swap(const dqe_t* h, const HostOp& o) {
+  if (o.m.type != OP_MAT2) return false;
+  const double2* u = &h->cpool[o.m.c_off];
+  for (int i = 0; i < 16; ++i) {
+    const bool is1 = i == 0 || i == 6 || i == 9 || i == 15;
+    if (u[i].y != 0.0 || u[i].x != (is1 ? 1.0 : 0.0)) return false;
+  }
+  return true;
+}
+
 void ladderize(dqe_t* h) {
   if (h->formalism != DQE_KET || !h->ladder || !h->merge || !h->fuse) return;
   int ndiag = 0;
@@ -817,7 +838,7 @@ void ladderize(dqe_t* h) {
         }
       }
       if (e.kind == 0 && e.m.type == OP_MAT2 && e.m.pred_bit == src.m.pred_bit && !e.pctrl && !e.pctrl2 &&
-          (e.m.b[0] == bit || e.m.b[1] == bit)) {
+          (e.m.b[0] == bit || e.m.b[1] == bit) && !host_is_swap(h, e)) {   // (a SWAP stays a pure permutation)
         cplx M[16];
         for (int i = 0; i < 16; ++i) M[i] = cplx(h->cpool[e.m.c_off + i].x, h->cpool[e.m.c_off + i].y);
         const int sh = e.m.b[0] == bit ? 1 : 0;   // row index = b[0] value * 2 + b[1] value
@@ -973,7 +994,7 @@ void ladderize(dqe_t* h) {
       out.push_back(m);
       continue;
     }
-    if (o.kind == 0 && o.m.type == OP_MAT2 && !o.pctrl && !o.pctrl2) {
+    if (o.kind == 0 && o.m.type == OP_MAT2 && !o.pctrl && !o.pctrl2 && !host_is_swap(h, o)) {
       HostOp m = o;
       for (int side = 0; side < 2; ++side) {
         const int bit = o.m.b[side];
@@ -1602,7 +1623,14 @@ struct Planner {
   // Close `cur` as one pass; when the emitted micro-program overflows the per-pass budget (the planner's
   // running estimate is optimistic) the list is cut in two and each half becomes its own pass.
   // live0 = live mask in front of the first op of `cur`.
+  size_t cur_first = 0;    // queue index of the first op of `cur`
   bool close(std::vector<const HostOp*>& cur, uint64_t live0) {
+    const size_t mark = passes.size();
+    const bool ok = close_tagged(cur, live0);
+    for (size_t i = mark; i < passes.size(); ++i) { passes[i].first_op = cur_first; passes[i].live_before = live0; }
+    return ok;
+  }
+  bool close_tagged(std::vector<const HostOp*>& cur, uint64_t live0) {
     if (cur.empty()) return true;
     uint64_t need = 0, live = live0;
     for (const HostOp* ho : cur) { need |= ho->need; live |= ho->live_after | ho->need; }
@@ -1617,8 +1645,8 @@ struct Planner {
       std::vector<const HostOp*> a(keep.begin(), keep.begin() + mid), b(keep.begin() + mid, keep.end());
       uint64_t live_mid = live0;
       for (const HostOp* ho : a) if (ho->kind <= 1 || true) live_mid = ho->live_after;
-      if (!close(a, live0)) return false;
-      if (!close(b, live_mid)) return false;
+      if (!close_tagged(a, live0)) return false;
+      if (!close_tagged(b, live_mid)) return false;
       cur.clear();
     }
     return true;
@@ -1874,6 +1902,7 @@ struct Planner {
     uint64_t live_now = h->planned_live, need = 0, live = live_now, live0 = live_now;
     int nconst = 0, nslots = 0, ncl = 0;
     for (const HostOp& op : h->queue) {
+      if (cur.empty()) cur_first = (size_t)(&op - h->queue.data());
       if (op.kind == 1 && cluster_mode() && !cur.empty() && cur.back()->m.type == OP_PROBS) {
         // small registers: all tiles of a shot fit one thread-block cluster, so the measurement is a
         // micro-op (DSMEM sum + on-chip draw) and the pass goes on
@@ -1934,6 +1963,7 @@ struct Planner {
                                         choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
         if (!close(cur, live0)) return false;
+        cur_first = (size_t)(&op - h->queue.data());
         need2 = op.need;
         live0 = live_now;
         live2 = live_now | op.live_after | op.need;
@@ -2016,6 +2046,8 @@ void build_tensor_map(dqe_t* h, PassParams& pp) {
 
 struct Planner;
 int launch_passes(dqe_t* h, Planner& pl);
+int do_flush(dqe_t* h, bool partial);
+inline int do_flush(dqe_t* h) { return do_flush(h, false); }
 
 int ensure_partials(dqe_t* h, size_t n) {
   if (n <= h->partials_cap) return 0;
@@ -2025,7 +2057,9 @@ int ensure_partials(dqe_t* h, size_t n) {
   return 0;
 }
 
-int do_flush(dqe_t* h) {
+// partial = streaming flush: everything but the last (still open) pass is launched, its ops stay queued, so that
+// the device works on the head of a long program while the host is still enqueueing its tail
+int do_flush(dqe_t* h, bool partial) {
   if (int rc = check_ready(h)) return rc;
   if (h->queue.empty()) return 0;
   ladderize(h);
@@ -2044,6 +2078,7 @@ int do_flush(dqe_t* h) {
       fprintf(stderr, "\n");
     }
   }
+  const uint64_t live_head = h->planned_live;
   Planner pl;
   pl.h = h;
   if (!pl.plan()) {
@@ -2075,6 +2110,25 @@ int do_flush(dqe_t* h) {
       fprintf(stderr, "\n");
     }
   }
+  size_t keep_from = h->queue.size();
+  uint64_t keep_live = 0;
+  if (partial) {
+    h->planned_live = live_head;
+    if (pl.passes.size() < 2 || pl.passes.back().is_finish) return 0;   // nothing closed yet (or nothing open)
+    keep_from = pl.passes.back().first_op;
+    keep_live = pl.passes.back().live_before;
+    while (!pl.passes.empty() && !pl.passes.back().is_finish && pl.passes.back().first_op == keep_from) pl.passes.pop_back();
+    if (pl.passes.empty() || keep_from == 0) return 0;
+  }
+  auto drop_done = [&]() {
+    if (keep_from >= h->queue.size()) {
+      h->queue.clear(); h->cpool.clear();
+      h->planned_live = phys_live(h, h->live_axes);
+    } else {   // the open tail stays (its constants too: c_off indexes the pool)
+      h->queue.erase(h->queue.begin(), h->queue.begin() + keep_from);
+      h->planned_live = keep_live;
+    }
+  };
   if (h->device < 0) {  // plan-only: account and drop
     for (PlannedPass& P : pl.passes) {
       if (P.is_finish) { h->stats[2]++; h->stats[5]++; continue; }
@@ -2082,8 +2136,7 @@ int do_flush(dqe_t* h) {
       h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
     }
     h->stats[6] += (int64_t)(pl.dev_ops.size() * sizeof(MicroOp) + pl.dev_consts.size() * sizeof(double2));
-    h->queue.clear(); h->cpool.clear();
-    h->planned_live = phys_live(h, h->live_axes);
+    drop_done();
     return 0;
   }
   CK(cudaSetDevice(h->device));
@@ -2122,9 +2175,8 @@ int do_flush(dqe_t* h) {
   const int rc_launch = launch_passes(h, pl);
   // whatever happened, the queued ops are gone: either they ran, or a CUDA error made the handle unusable
   // (sticky); re-applying ops that already ran on the next flush would be worse than either
-  h->queue.clear();
-  h->cpool.clear();
-  h->planned_live = phys_live(h, h->live_axes);
+  if (rc_launch) keep_from = h->queue.size();
+  drop_done();
   if (rc_launch) return rc_launch;
   if (getenv("DQE_DEBUG"))
     fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
@@ -2288,7 +2340,8 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
+  h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -2320,9 +2373,12 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   const size_t elems = (size_t)batch << P;
   if (ext_state) h->state = (double2*)ext_state;
   else {
-    e = cudaMalloc(&h->state, elems * sizeof(double2));
+    // engine-owned buffers carry the peer flag block behind the state (same IPC mapping, see k_peer_exchange)
+    e = cudaMalloc(&h->state, elems * sizeof(double2) + kPeerFlagWords * sizeof(uint64_t));
     if (e != cudaSuccess) return bail("cudaMalloc(state)", e);
     h->own_state = true;
+    if ((e = cudaMemsetAsync(h->state + elems, 0, kPeerFlagWords * sizeof(uint64_t), h->stream)) != cudaSuccess)
+      return bail("memset(flags)", e);
   }
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaMalloc(&h->creg_buf[i], batch * sizeof(uint64_t))) != cudaSuccess) return bail("cudaMalloc(creg)", e);
@@ -2359,6 +2415,7 @@ int dqe_destroy(dqe_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& p : h->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (h->xev_ok) { cudaEventDestroy(h->xev0); cudaEventDestroy(h->xev1); }
   if (h->own_state && h->state) cudaFree(h->state);
   for (int i = 0; i < 2; ++i) {
     if (h->creg_buf[i]) cudaFree(h->creg_buf[i]);
@@ -2458,12 +2515,32 @@ int dqe_live_mask(dqe_t* h, uint64_t* mask) {
   return 0;
 }
 
+int dqe_force_live_mask(dqe_t* h, uint64_t mask) {
+  if (int rc = do_flush(h)) return rc;
+  if (h->nmax < 64 && (mask >> h->nmax)) return fail(h, DQE_EINVAL, "force_live_mask: axis out of range");
+  h->live_axes = mask;
+  h->planned_live = phys_live(h, mask);
+  return 0;
+}
+
 static void to_cplx(const double* in, cplx* out, int n) {
   for (int i = 0; i < n; ++i) out[i] = cplx(in[2 * i], in[2 * i + 1]);
 }
 
+// Big single-shot kets (a pass costs milliseconds): every `stream_ops` queued ops the passes that are already
+// closed are launched, so that the device runs the head of the program while the host still walks its tail.
+static int maybe_stream(dqe_t* h) {
+  if (!h->stream_ops || h->formalism != DQE_KET || h->P < h->stream_min_bits || !h->fuse) return 0;
+  if (h->queue.size() < h->stream_next) return 0;
+  const int rc = do_flush(h, true);
+  h->stream_flushes++;
+  h->stream_next = h->queue.size() + (size_t)h->stream_ops;
+  return rc;
+}
+
 int dqe_enqueue_1q(dqe_t* h, int axis, const double* m) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = maybe_stream(h)) return rc;
   if (int rc = check_live(h, axis, "1q gate")) return rc;
   cplx u[4];
   to_cplx(m, u, 4);
@@ -2473,6 +2550,7 @@ int dqe_enqueue_1q(dqe_t* h, int axis, const double* m) {
 
 int dqe_enqueue_2q(dqe_t* h, int a, int b, const double* m) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = maybe_stream(h)) return rc;
   if (int rc = check_live(h, a, "2q gate")) return rc;
   if (int rc = check_live(h, b, "2q gate")) return rc;
   if (a == b) return fail(h, DQE_EINVAL, "2q gate: axes must differ");
@@ -2484,6 +2562,7 @@ int dqe_enqueue_2q(dqe_t* h, int a, int b, const double* m) {
 
 int dqe_enqueue_ctrl_1q(dqe_t* h, int c, int t, const double* m) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = maybe_stream(h)) return rc;
   if (int rc = check_live(h, c, "ctrl gate")) return rc;
   if (int rc = check_live(h, t, "ctrl gate")) return rc;
   if (c == t) return fail(h, DQE_EINVAL, "ctrl gate: axes must differ");
@@ -2495,6 +2574,7 @@ int dqe_enqueue_ctrl_1q(dqe_t* h, int c, int t, const double* m) {
 
 int dqe_enqueue_diag(dqe_t* h, int k, const int* axes, const double* d) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = maybe_stream(h)) return rc;
   if (k < 1 || k > 4) return fail(h, DQE_EUNSUPPORTED, "diag: 1 <= k <= 4");
   for (int i = 0; i < k; ++i) {
     if (int rc = check_live(h, axes[i], "diag")) return rc;
@@ -2994,6 +3074,97 @@ int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_ax
   return 0;
 }
 
+static int collect_exchange_time(dqe_t* h) {
+  if (!h->xev_pending) return 0;
+  float ms = 0.f;
+  CK(cudaEventSynchronize(h->xev1));
+  CK(cudaEventElapsedTime(&ms, h->xev0, h->xev1));
+  h->x_ms += ms;
+  h->xev_pending = false;
+  return 0;
+}
+
+int dqe_peer_exchange(dqe_t* h, void* const* peer_states, int rank, int world, int s, const int* rank_bits,
+                      const int* local_axes) {
+  if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
+  if (h->formalism != DQE_KET || h->batch != 1) return fail(h, DQE_EUNSUPPORTED, "peer_exchange: single-shot ket only");
+  if (!h->own_state) return fail(h, DQE_EUNSUPPORTED, "peer_exchange: engine-owned state buffers only");
+  if (!peer_states || !rank_bits || !local_axes || s < 1 || s > 6 || world < 2 || world > 64 || rank < 0 || rank >= world)
+    return fail(h, DQE_EINVAL, "peer_exchange: bad argument");
+  if (h->P - s < 1) return fail(h, DQE_EINVAL, "peer_exchange: too many axes for this shard");
+  ExchangeParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mine = h->state; ep.flag_off = 1ull << h->P; ep.rank = rank; ep.s = s; ep.m = h->P; ep.nparts = (1 << s) - 1;
+  uint64_t lseen = 0;
+  for (int k = 0; k < s; ++k) {
+    if (rank_bits[k] < 0 || (1 << rank_bits[k]) >= world || local_axes[k] < 0 || local_axes[k] >= h->nmax ||
+        ((lseen >> local_axes[k]) & 1ull) || (k > 0 && rank_bits[k] <= rank_bits[k - 1]))
+      return fail(h, DQE_EINVAL, "peer_exchange: rank bits ascending and inside the world, local axes distinct");
+    lseen |= 1ull << local_axes[k];
+    ep.jbits[k] = rank_bits[k]; ep.lbits[k] = local_axes[k]; ep.lsorted[k] = local_axes[k];
+  }
+  std::sort(ep.lsorted, ep.lsorted + s);
+  for (int p = 0; p < world; ++p) ep.peer[p] = p == rank ? h->state : (double2*)peer_states[p];
+  for (int d = 1; d < (1 << s); ++d) {
+    int p = rank;
+    for (int k = 0; k < s; ++k) if ((d >> k) & 1) p ^= 1 << rank_bits[k];
+    if (!ep.peer[p]) return fail(h, DQE_EINVAL, "peer_exchange: partner shard not mapped");
+    ep.epoch[p] = ++h->peer_epoch[p];
+  }
+  CK(cudaSetDevice(h->device));
+  if (int rc = collect_exchange_time(h)) return rc;
+  if (!h->xev_ok) { CK(cudaEventCreate(&h->xev0)); CK(cudaEventCreate(&h->xev1)); h->xev_ok = true; }
+  CK(cudaEventRecord(h->xev0, h->stream));
+  // every CTA must be resident (the last one to finish waits for the partners): <= 8 CTAs of 256 threads per SM
+  k_peer_exchange<<<h->num_sms * 4, 256, 0, h->stream>>>(ep);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->xev1, h->stream));
+  h->xev_pending = true;
+  h->x_count++;
+  h->x_bytes += (int64_t)((1ull << (h->P - s)) * (uint64_t)((1 << s) - 1) * sizeof(double2));
+  h->stats[2]++;
+  return 0;
+}
+
+int dqe_peer_stats(dqe_t* h, double* ms, int64_t* count, int64_t* bytes_sent, int64_t* error) {
+  if (int rc = check_ready(h)) return rc;
+  NEED_DEVICE(h);
+  CK(cudaSetDevice(h->device));
+  if (int rc = collect_exchange_time(h)) return rc;
+  if (ms) *ms = h->x_ms;
+  if (count) *count = h->x_count;
+  if (bytes_sent) *bytes_sent = h->x_bytes;
+  if (error) {
+    uint64_t e = 0;
+    if (h->own_state) {
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaMemcpy(&e, reinterpret_cast<uint64_t*>(h->state + ((size_t)h->batch << h->P)) + kPeerError, sizeof(e), cudaMemcpyDeviceToHost));
+    }
+    *error = (int64_t)e;
+  }
+  return 0;
+}
+
+int dqe_probs(dqe_t* h, int axis, double* out2) {
+  if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
+  if (h->formalism != DQE_KET || h->batch != 1) return fail(h, DQE_EUNSUPPORTED, "probs: single-shot ket only");
+  if (!out2) return fail(h, DQE_EINVAL, "probs: null");
+  if (int rc = check_live(h, axis, "probs")) return rc;
+  const int nblk = h->num_sms * 8;
+  if (int rc = ensure_scratch(h, (size_t)nblk * 2 * sizeof(double))) return rc;
+  CK(cudaSetDevice(h->device));
+  k_probs_bit<<<nblk, 256, 0, h->stream>>>(h->state, 1ull << h->P, axis, (double*)h->scratch);
+  CK(cudaGetLastError());
+  std::vector<double> part((size_t)nblk * 2);
+  CK(cudaMemcpyAsync(part.data(), h->scratch, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  out2[0] = out2[1] = 0.0;
+  for (int b = 0; b < nblk; ++b) { out2[0] += part[2 * b]; out2[1] += part[2 * b + 1]; }
+  return 0;
+}
+
 int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (!h || !key) return DQE_EINVAL;
   if (int rc = do_flush(h)) return rc;
@@ -3020,6 +3191,11 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->ladder = value ? 1 : 0;
   } else if (!strcmp(key, "kgroup")) {
     h->kgroup = value ? 1 : 0;
+  } else if (!strcmp(key, "stream_ops")) {
+    if (value < 0) return fail(h, DQE_EINVAL, "stream_ops >= 0");
+    h->stream_ops = (int)value; h->stream_next = (size_t)value;
+  } else if (!strcmp(key, "stream_min_bits")) {
+    h->stream_min_bits = (int)value;
   } else if (!strcmp(key, "shot_stride")) {
     if (value < 1) return fail(h, DQE_EINVAL, "shot_stride >= 1");
     h->shot_stride = value;

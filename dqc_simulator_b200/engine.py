@@ -43,6 +43,12 @@ ABI = {
     "dqe_enqueue_ctrl_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
     "dqe_enqueue_diag": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
     "dqe_enqueue_kq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
+    "dqe_peer_exchange": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, _c_int_p, _c_int_p]),
+    "dqe_peer_stats": (ctypes.c_int, [ctypes.c_void_p, _c_dbl_p, ctypes.POINTER(ctypes.c_int64),
+                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "dqe_probs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_force_live_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "dqe_set_predicate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dqe_enqueue_cond_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
     "dqe_enqueue_pauli_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
@@ -211,6 +217,13 @@ class Engine:
         m = ctypes.c_uint64()
         self._ck(self._lib.dqe_live_mask(self._h, ctypes.byref(m)))
         return [a for a in range(self.max_qubits) if (m.value >> a) & 1]
+
+    def force_live(self, axes):
+        """Declare the live axes after a data movement outside the gate queue (every other axis must be in |0>)."""
+        mask = 0
+        for a in axes:
+            mask |= 1 << int(a)
+        self._ck(self._lib.dqe_force_live_mask(self._h, ctypes.c_uint64(mask)))
 
     @property
     def n_live(self):
@@ -426,6 +439,24 @@ class Engine:
 
     def peer_swap(self, peer_ptr, my_bit, half, local_axis):
         self._ck(self._lib.dqe_peer_swap(self._h, ctypes.c_void_p(peer_ptr), int(my_bit), int(half), int(local_axis)))
+
+    def peer_exchange(self, peer_ptrs, rank, rank_bits, local_axes):
+        """Multi-axis global <-> local exchange with every partner in one launch (k_peer_exchange); enqueue only."""
+        world = len(peer_ptrs)
+        arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(p) if p else None for p in peer_ptrs])
+        _a, pj = _ibuf(rank_bits)
+        _b, pl = _ibuf(local_axes)
+        self._ck(self._lib.dqe_peer_exchange(self._h, arr, int(rank), world, len(_a), pj, pl))
+
+    def peer_stats(self):
+        ms, cnt, nbytes, err = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._ck(self._lib.dqe_peer_stats(self._h, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(nbytes), ctypes.byref(err)))
+        return dict(ms=ms.value, count=cnt.value, bytes_sent=nbytes.value, error=err.value)
+
+    def probs(self, axis):
+        out = (ctypes.c_double * 2)()
+        self._ck(self._lib.dqe_probs(self._h, int(axis), out))
+        return float(out[0]), float(out[1])
 
     # ------------------------------------------------------------------ instrumentation
     def stats(self):

@@ -19,28 +19,48 @@ The local backend is any object with ``apply_1q / apply_2q / apply_ctrl_1q / app
 """
 import numpy as np
 
+_SWAP = np.eye(4, dtype=complex)[[0, 2, 1, 3]]
+_CNOT = np.eye(4, dtype=complex)[[0, 1, 3, 2]]
+_X = np.array([[0, 1], [1, 0]], dtype=complex)
+_PAT_SWAP, _PAT_CNOT, _PAT_DIAG = (_SWAP != 0).tobytes(), (_CNOT != 0).tobytes(), (np.eye(4) != 0).tobytes()
+
 
 class GpuShard:
-    """Local shard on one B200: an Engine with every local axis live from the start."""
+    """Local shard on one B200: an Engine with every local axis live from the start.  Everything that touches
+    the amplitudes goes through the C-ABI (gate queue, ``dqe_probs``, ``dqe_measure``, ``dqe_peer_exchange``);
+    torch only lends the process group and, for tests, a view of the buffer."""
 
-    def __init__(self, m, device, first_rank, seed=0):
+    def __init__(self, m, device, first_rank, seed=0, lazy=True):
         from .engine import Engine
 
         self.m = m
         self.eng = Engine("ket", m, 1, seed=seed, device=device)
-        for a in range(m):
-            self.eng.alloc_axis(a)
-        self.eng.sync()
-        if not first_rank:          # |0...0> lives on rank 0 only
-            self.buffer()[0] = 0
-            self._done()
+        # lazy: a local slot goes live when its qubit is first used (``set_live``), like the executor's lazy
+        # INSTR_INIT on one GPU -- the passes of a circuit's first stages then run over the few live bits only
+        self._live = set()
+        for a in (range(1) if lazy else range(m)):
+            self.set_live(a)
+        if not first_rank:          # |0...0> lives on rank 0 only: the other shards start empty
+            self.eng.apply_diag([0], [0.0, 0.0])
+        self.eng.flush()
         self.apply_1q = self.eng.apply_1q
         self.apply_2q = self.eng.apply_2q
         self.apply_ctrl_1q = self.eng.apply_ctrl_1q
         self.apply_diag = self.eng.apply_diag
+        self._peer_ptrs = None
 
     def buffer(self):
         return self.eng.state_tensor()
+
+    def set_live(self, slot):
+        if slot not in self._live:
+            self._live.add(slot)
+            self.eng.alloc_axis(slot)
+
+    def relive(self, slots):
+        """After an exchange: exactly `slots` (plus slot 0, the scratch axis of scalings) hold live qubits."""
+        self._live = set(slots) | {0}
+        self.eng.force_live(sorted(self._live))
 
     # ---- peer memory: partners' shards mapped through CUDA IPC (NVLink loads / stores) -----------
     def enable_peer_access(self, rank, world, group=None):
@@ -48,50 +68,55 @@ class GpuShard:
 
         handles = [None] * world
         dist.all_gather_object(handles, self.eng.ipc_export(), group=group)
-        self._peer_handles, self._peer_ptrs, self._rank = handles, {}, rank
+        self._rank = rank
+        self._peer_ptrs = [None if p == rank else self.eng.ipc_open(handles[p]) for p in range(world)]
+
+    def close(self):
+        """Unmap the partners' shards (``cudaIpcCloseMemHandle``) and free the engine."""
+        if self._peer_ptrs:
+            self.eng.sync()
+            for ptr in self._peer_ptrs:
+                if ptr:
+                    self.eng.ipc_close(ptr)
+            self._peer_ptrs = None
+        self.eng.close()
+
+    def exchange(self, rank_bits, local_axes):
+        """Multi-axis global <-> local exchange with all partners in one launch, synchronised on the device
+        (kernel ``k_peer_exchange``): enqueue only, no host barrier."""
+        self.eng.peer_exchange(self._peer_ptrs, self._rank, rank_bits, local_axes)
 
     def peer_1q(self, partner, my_bit, m, ctrl_axis=-1):
         """Fused gate + transfer on a global axis: this rank updates both shards on its half of the
         local index range (kernel ``k_peer_1q``)."""
-        if partner not in self._peer_ptrs:
-            self._peer_ptrs[partner] = self.eng.ipc_open(self._peer_handles[partner])
         self.eng.peer_1q(self._peer_ptrs[partner], my_bit, my_bit, m, ctrl_axis)
 
     def peer_swap(self, partner, my_bit, local_axis):
-        """Global <-> local axis swap in place over peer memory (kernel ``k_peer_swap``)."""
-        if partner not in self._peer_ptrs:
-            self._peer_ptrs[partner] = self.eng.ipc_open(self._peer_handles[partner])
+        """Global <-> local axis swap in place over peer memory (kernel ``k_peer_swap``; host-synchronised)."""
         self.eng.peer_swap(self._peer_ptrs[partner], my_bit, my_bit, local_axis)
 
     def sync(self):
-        import torch
-
         self.eng.sync()
-        torch.cuda.synchronize()
-
-    def _done(self):
-        import torch
-
-        torch.cuda.synchronize()   # torch ops run on torch's stream, the engine on its own
 
     def scale(self, s):
-        self.sync()
-        self.buffer().mul_(s)
-        self._done()
+        s = complex(s)
+        self.eng.apply_diag([0], [s, s])        # rides in the next pass of the gate queue
 
-    def norm2_by_bit(self, axis):
-        """(sum |amp|^2 over axis bit = 0, over bit = 1) of the local shard."""
-        self.sync()
-        b = self.buffer().view(-1, 2, 2 ** axis)
-        p = (b.real ** 2 + b.imag ** 2).sum(dim=(0, 2))
-        return float(p[0]), float(p[1])
+    def probs(self, axis):
+        """(sum |amp|^2 over axis bit = 0, over bit = 1) of the local shard (kernel ``k_probs_bit``)."""
+        return self.eng.probs(axis)
 
-    def project(self, axis, outcome, scale):
-        self.sync()
-        b = self.buffer().view(-1, 2, 2 ** axis)
-        b[:, 1 - outcome, :] = 0
-        b[:, outcome, :] *= scale
-        self._done()
+    norm2_by_bit = probs
+
+    def project(self, axis, outcome, scale, p_local):
+        """Keep the ``outcome`` half of ``axis`` and rescale: the engine's forced measurement renormalises by the
+        LOCAL probability, the factor that turns that into the global normalisation is returned for the
+        caller's pending scalar."""
+        if p_local <= 0.0:
+            self.eng.apply_diag([0], [0.0, 0.0])
+            return 1.0
+        self.eng.measure(axis, None, int(outcome), False, 0.0)
+        return float(scale) * float(np.sqrt(p_local))
 
 
 class ShardedKet:
@@ -122,6 +147,9 @@ class ShardedKet:
         if self.peer:
             shard.enable_peer_access(rank, world, group)
         self._seed, self._draw = int(seed), 0
+        self._mixed = []                # logical axes in the order they were last mixed (victims of an exchange)
+        self.relabelled_swaps = 0
+        self._cx = []                   # CNOTs held back: CX(a,b) CX(b,a) CX(a,b) is a SWAP, i.e. a relabelling
 
     # ------------------------------------------------------------------ slots
     def _is_global(self, a):
@@ -133,10 +161,42 @@ class ShardedKet:
     def _axis_at(self, slot):
         return self.slot.index(slot)
 
+    def _touch(self, *axes):
+        for a in axes:
+            if a in self._mixed:
+                self._mixed.remove(a)
+            self._mixed.append(a)
+
+    def _localise_all(self, busy):
+        """Peer mode: ALL global axes trade places with local slots in one device-synchronised exchange
+        (``dqe_peer_exchange``): (1 - 2^-g) of the shard crosses NVLink once, where g pairwise swaps move g / 2
+        of it, and nothing blocks on the host.  Victims: local axes that were already mixed (a QFT / GHZ qubit
+        is mixed once and then only controls), latest first; otherwise slots from 4 upwards (16-amplitude =
+        256-byte runs stay contiguous on the wire)."""
+        busy_slots = {self.slot[x] for x in busy}
+        cand = [self.slot[x] for x in reversed(self._mixed) if not self._is_global(x)]
+        cand += [s_ for s_ in range(min(4, self.m - self.g), self.m)] + list(range(self.m))
+        chosen = []
+        for s_ in cand:
+            if s_ not in busy_slots and s_ not in chosen:
+                chosen.append(s_)
+            if len(chosen) == self.g:
+                break
+        self._apply_pending()
+        self.shard.exchange(list(range(self.g)), chosen)
+        for j, L in enumerate(chosen):
+            a_g, other = self._axis_at(self.m + j), self._axis_at(L)
+            self.slot[other], self.slot[a_g] = self.m + j, L
+        self._relive()
+        self.exchanges += 1
+        self.exchanged_bytes += (2 ** (self.m - self.g)) * (self.world - 1) * 16
+
     def _localise(self, a, busy):
         """Make logical axis ``a`` local by swapping its global slot with a free local slot."""
         if not self._is_global(a):
             return
+        if self.peer and not self.peer_gates:
+            return self._localise_all(busy)
         busy_slots = {self.slot[x] for x in busy}
         L = next(s for s in range(self.m - 1, -1, -1) if s not in busy_slots)
         j = self.slot[a] - self.m
@@ -144,6 +204,7 @@ class ShardedKet:
         other = self._axis_at(L)
         self.slot[other], self.slot[a] = self.slot[a], L
         self._peer_uses[other] = 0
+        self._relive()
 
     def _exchange(self, j, L):
         """new[rank bit j = x, local bit L = y] = old[rank bit j = y, local bit L = x]."""
@@ -187,7 +248,16 @@ class ShardedKet:
         if axis < 0:
             axis = min(a for a in range(self.n) if a not in self.live)
         self.live.append(axis)
+        if not self._is_global(axis) and hasattr(self.shard, "set_live"):
+            self.shard.set_live(self.slot[axis])
         return axis
+
+    def _relive(self):
+        """The engine's live slots = the local slots whose logical axis is live (after axes changed slots)."""
+        if hasattr(self.shard, "relive"):
+            want = {self.slot[a] for a in self.live if not self._is_global(a)} | {0}
+            if want != self.shard._live:
+                self.shard.relive(want)
 
     def free_axis(self, axis):
         raise NotImplementedError("sharded registers keep every axis (no comm-qubit churn in config 5)")
@@ -228,16 +298,39 @@ class ShardedKet:
         self.peer_gate_count += 1
         self.peer_seconds += time.perf_counter() - t0
 
+    def _flush_cx(self):
+        if self._cx:
+            held, self._cx = self._cx, []
+            for c, t in held:
+                self.apply_ctrl_1q(c, t, _X)
+
+    def _cnot(self, c, t):
+        """The front end lowers SWAP to three CNOTs: recognised here, the triple costs nothing (slot relabelling)."""
+        k = len(self._cx)
+        if k == 1 and self._cx[0] == (t, c):
+            self._cx.append((c, t))
+        elif k == 2 and self._cx[0] == (c, t):
+            self._cx = []
+            self.slot[c], self.slot[t] = self.slot[t], self.slot[c]
+            self.relabelled_swaps += 1
+            self._relive()
+        else:
+            self._flush_cx()
+            self._cx = [(c, t)]
+
     def apply_1q(self, axis, m):
+        self._flush_cx()
         m = np.asarray(m, dtype=complex).reshape(2, 2)
         if m[0, 1] == 0 and m[1, 0] == 0:
             return self.apply_diag([axis], [m[0, 0], m[1, 1]])
         if self._use_peer(axis):
             return self._peer_gate(axis, m)
         self._localise(axis, [axis])
+        self._touch(axis)
         self.shard.apply_1q(self.slot[axis], m)
 
     def apply_ctrl_1q(self, c, t, m):
+        self._flush_cx()
         m = np.asarray(m, dtype=complex).reshape(2, 2)
         if m[0, 1] == 0 and m[1, 0] == 0:
             return self.apply_diag([c, t], [1, 1, m[0, 0], m[1, 1]])
@@ -246,6 +339,7 @@ class ShardedKet:
                 return self._peer_gate(t, m, active=bool(self._rank_bit(c)))
             return self._peer_gate(t, m, ctrl_slot=self.slot[c])
         self._localise(t, [c, t])
+        self._touch(t)
         if self._is_global(c):
             if self._rank_bit(c):
                 self.shard.apply_1q(self.slot[t], m)
@@ -254,16 +348,27 @@ class ShardedKet:
 
     def apply_2q(self, a, b, m):
         m = np.asarray(m, dtype=complex).reshape(4, 4)
-        off = m - np.diag(np.diag(m))
-        if not off.any():
+        pat = (m != 0).tobytes()
+        if pat == _PAT_CNOT and m[0, 0] == 1 and m[1, 1] == 1 and m[2, 3] == 1 and m[3, 2] == 1:
+            return self._cnot(a, b)
+        self._flush_cx()
+        if pat == _PAT_DIAG:
             return self.apply_diag([a, b], np.diag(m))
-        if not m[:2, 2:].any() and not m[2:, :2].any() and np.array_equal(m[:2, :2], np.eye(2)):
+        if pat == _PAT_SWAP and m[0, 0] == 1 and m[1, 2] == 1 and m[2, 1] == 1 and m[3, 3] == 1:
+            # a SWAP is a relabelling of the slot map: no pass, no exchange, whatever slots the two axes sit in
+            self.slot[a], self.slot[b] = self.slot[b], self.slot[a]
+            self.relabelled_swaps += 1
+            self._relive()
+            return
+        if not m[:2, 2:].any() and not m[2:, :2].any() and m[0, 0] == 1 and m[1, 1] == 1 and m[0, 1] == 0 and m[1, 0] == 0:
             return self.apply_ctrl_1q(a, b, m[2:, 2:])
         self._localise(a, [a, b])
         self._localise(b, [a, b])
+        self._touch(a, b)
         self.shard.apply_2q(self.slot[a], self.slot[b], m)
 
     def apply_diag(self, axes, d):
+        self._flush_cx()
         axes = list(axes)
         k = len(axes)
         d = np.asarray(d, dtype=complex).reshape((2,) * k)
@@ -291,7 +396,9 @@ class ShardedKet:
 
     # ------------------------------------------------------------------ measurement
     def measure(self, axis, creg_bit=None, forced=-1, discard=False, flip_prob=0.0):
-        """Z-basis measurement across shards; returns the outcome (identical on every rank)."""
+        """Z-basis measurement across shards; returns the outcome (identical on every rank): local partial
+        probabilities (engine kernel) -> one all-reduce of two doubles -> every rank draws the same Philox
+        number -> local projection (engine), the global renormalisation rides in the pending scalar."""
         import torch
         import torch.distributed as dist
 
@@ -299,26 +406,28 @@ class ShardedKet:
 
         if discard or flip_prob:
             raise NotImplementedError
-        self._apply_pending()
-        if self._is_global(axis):
-            self.shard.sync()
-            b = self.shard.buffer()
-            tot = float((b.real ** 2 + b.imag ** 2).sum())
+        self._flush_cx()
+        glob = self._is_global(axis)
+        q = list(self.shard.probs(0 if glob else self.slot[axis]))
+        w = abs(self._pending) ** 2            # the pending scalar has not reached the amplitudes yet
+        if glob:
+            tot = (q[0] + q[1]) * w
             p = [tot, 0.0] if self._rank_bit(axis) == 0 else [0.0, tot]
         else:
-            p = list(self.shard.norm2_by_bit(self.slot[axis]))
-        t = torch.tensor(p, dtype=torch.float64, device=self.shard.buffer().device)
+            p = [q[0] * w, q[1] * w]
+        buf = self.shard.buffer()
+        t = torch.tensor(p, dtype=torch.float64, device=buf.device if buf.is_cuda else "cpu")
         dist.all_reduce(t, group=self.group)
-        p0, p1 = float(t[0]), float(t[1])
+        p0, p1 = (float(x) for x in t.cpu())
         u, _ = shot_uniforms(self._seed, 0, self._draw)
         self._draw += 1
         m = int(forced) if forced is not None and forced >= 0 else int(u * (p0 + p1) < p1)
         pm = p1 if m else p0
         scale = 1.0 / np.sqrt(pm) if pm > 0 else 0.0
-        if self._is_global(axis):
-            self.shard.scale(scale if self._rank_bit(axis) == m else 0.0)
+        if glob:
+            self._pending *= scale if self._rank_bit(axis) == m else 0.0
         else:
-            self.shard.project(self.slot[axis], m, scale)
+            self._pending *= self.shard.project(self.slot[axis], m, scale, q[m])
         return m
 
     # ------------------------------------------------------------------ read-out
@@ -328,6 +437,7 @@ class ShardedKet:
             self._pending = 1.0 + 0.0j
 
     def flush(self):
+        self._flush_cx()
         self._apply_pending()
         self.shard.sync()
 
@@ -338,11 +448,21 @@ class ShardedKet:
         import torch
         import torch.distributed as dist
 
-        self.flush()
-        b = self.shard.buffer()
-        t = (b.real ** 2 + b.imag ** 2).sum().reshape(1).to(torch.float64)
+        self._flush_cx()
+        q = self.shard.probs(0)
+        buf = self.shard.buffer()
+        t = torch.tensor([(q[0] + q[1]) * abs(self._pending) ** 2], dtype=torch.float64,
+                         device=buf.device if buf.is_cuda else "cpu")
         dist.all_reduce(t, group=self.group)
         return float(t[0])
+
+    def exchange_stats(self):
+        """Seconds spent in exchanges (device time of ``k_peer_exchange`` in peer mode, host clock otherwise) and
+        the error word of the device-side handshake (1 = a partner never arrived)."""
+        if self.peer and not self.peer_gates and hasattr(self.shard, "eng"):
+            st = self.shard.eng.peer_stats()
+            return dict(seconds=st["ms"] * 1e-3 + self.exchange_seconds, error=st["error"])
+        return dict(seconds=self.exchange_seconds, error=0)
 
     def logical_index_of(self, local_index):
         """Logical basis-state index (axis a = bit a) of local amplitude ``local_index`` on this rank."""

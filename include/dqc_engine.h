@@ -95,6 +95,11 @@ int dqe_alloc_axis(dqe_t* h, int axis);   /* make a free axis live in |0> */
 int dqe_free_axis(dqe_t* h, int axis);    /* dm: partial trace; ket: unrecorded sampled measurement */
 int dqe_reset(dqe_t* h, int axis);        /* INSTR_INIT on an occupied position */
 int dqe_live_mask(dqe_t* h, uint64_t* mask);
+/* Declare which axes hold qubits after the amplitudes were moved by something the gate queue does not see (a
+ * peer exchange, dqe_set_state through dqe_state_ptr): the caller asserts that every axis outside `mask` is in |0>,
+ * i.e. that the halves of the state with such a bit set are exactly zero (the free-axis invariant, section
+ * "state layout" above).  Flushes first. */
+int dqe_force_live_mask(dqe_t* h, uint64_t mask);
 
 /* ---- unitaries (qubitapi.operate via QuantumProgram.apply, dqc_control.py:191-196;
  *      operator matrices qlib/gates.py:29-220).  Matrices need not be unitary
@@ -220,6 +225,23 @@ int dqe_peer_1q(dqe_t* h, void* peer_state, int my_bit, int half, const double* 
  * place over peer memory, this rank handling one half of the pairs.  No staging buffer, both NVLink
  * directions busy at once. */
 int dqe_peer_swap(dqe_t* h, void* peer_state, int my_bit, int half, int local_axis);
+/* Multi-axis exchange, synchronised on the device (kernel k_peer_exchange): the `s` rank bits `rank_bits`
+ * (ascending) trade places with the local axes `local_axes` -- new[R = x, L = y] = old[R = y, L = x] -- in ONE
+ * launch that talks to all 2^s - 1 partners over peer memory: (1 - 2^-s) of the shard crosses NVLink once, where s
+ * pairwise swaps move s / 2 of it.  No host barrier on either side: the ranks meet through epoch counters in a flag
+ * block behind each shard (ready / done per partner), so the call only ENQUEUES and the host goes on planning.
+ * The whole buffer moves, free axes included (their upper halves are zero): which axes are live afterwards is the
+ * caller's business (dqe_force_live_mask).
+ * Every rank of the group must call it with the same rank_bits / local_axes, in the same program order;
+ * peer_states[p] = dqe_ipc_open of rank p's handle (entry `rank` ignored).  The NCCL all-to-all of
+ * SURVEY.md 8e, as a kernel.  dqe_peer_stats: device time, count and bytes sent of the exchanges so far, and the
+ * error word (1 = a partner never arrived within ~4 s; the state is then undefined). */
+int dqe_peer_exchange(dqe_t* h, void* const* peer_states, int rank, int world, int s, const int* rank_bits,
+                      const int* local_axes);
+int dqe_peer_stats(dqe_t* h, double* ms, int64_t* count, int64_t* bytes_sent, int64_t* error);
+/* Local part of a measurement on a sharded state vector (single-shot ket): out2 = (sum |amp|^2 over axis bit 0,
+ * over axis bit 1) of this shard.  The caller all-reduces, draws, and projects with dqe_measure(forced = m). */
+int dqe_probs(dqe_t* h, int axis, double* out2);
 
 /* ---- tuning + instrumentation --------------------------------------------------------------- */
 /* key: "tile_bits" (log2 amplitudes staged per CTA; default 11 = 32 KiB with 128 threads, or 10 = 16 KiB

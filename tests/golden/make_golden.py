@@ -18,7 +18,7 @@ Fixtures
   hardware of ``examples/setup_hardware.py:11-55`` (10 positions, 2 comm qubits, 3 QPUs)
 * ``c3_qft{N}_4qpu_cat``          config 3 shape (N = 8, 12 for oracle-sized parity, 26 full)
 * ``c4_qft{N}_mono``              config 4 shape: one QPU, all gates local (N = 6, 16)
-* ``c5_{ghz,qft}{N}_mono``        config 5 shape (N = 12 parity size, 30/34 full)
+* ``c5_{ghz,qft}{N}_mono``        config 5 shape (N = 12 parity size, 30 .. 34 full: weak scaling over 1, 2, 4, 8, 16 GPUs)
 * ``mqt/{name}_{mono,3qpu_cat,3qpu_tp_safe}``  the 22 MQT-bench circuits of ``tests/MQT_benchmarking_circuits`` (the
   reference's front-end test inputs), monolithic and partitioned over 3 QPUs
 * ``ref_*``                       gate-tuple circuits lifted from the reference's own tests
@@ -149,7 +149,7 @@ def main():
         ops, meta = compile_mono(_qasm_path(circuits.qft_qasm(n)), n)
         save(f"c4_qft{n}_mono", ops, meta, gz=n > 12)
     for kind, gen in (("ghz", circuits.ghz_qasm), ("qft", circuits.qft_qasm)):
-        for n in (12, 30, 34):
+        for n in (12, 30, 31, 32, 33, 34):
             ops, meta = compile_mono(_qasm_path(gen(n)), n)
             save(f"c5_{kind}{n}_mono", ops, meta, gz=n > 12)
     # ---- the reference's MQT-bench test circuits (tests/MQT_benchmarking_circuits, 22 x 5 qubits):

@@ -494,6 +494,19 @@ def test_controlled_phase_stars(n, batch, tile, threads):
         assert np.abs(with_stars - b2.g.full_state()).max() < TOL
 
 
+@pytest.mark.parametrize("stream_ops", [4, 16])
+def test_streaming_flush_keeps_parity(stream_ops):
+    """Streaming flush (big kets: closed passes are launched while the host still enqueues; option stream_ops):
+    forced on for a small register -- same amplitudes, classical bits and live axes as the oracle after every
+    few steps of a random program with measurements, resets and predicated gates."""
+    rng = np.random.default_rng(40 + stream_ops)
+    b = Both("ket", 9, 3, 21, tile_bits=6)
+    b.g.set_option("stream_min_bits", 0)
+    b.g.set_option("stream_ops", stream_ops)
+    random_program(b, rng, 160, "ket", check_every=20)
+    b.check("streaming")
+
+
 @pytest.mark.parametrize("formalism", ["ket", "dm"])
 def test_forced_outcomes_bit_exact(formalism):
     n = 5

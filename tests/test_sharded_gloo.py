@@ -59,14 +59,15 @@ class NumpyShard:
     def scale(self, s):
         self.v *= s
 
-    def norm2_by_bit(self, axis):
+    def probs(self, axis):
         p = (np.abs(self.v) ** 2).reshape(-1, 2, 2 ** axis).sum(axis=(0, 2))
         return float(p[0]), float(p[1])
 
-    def project(self, axis, outcome, scale):
+    def project(self, axis, outcome, scale, p_local):
         b = self.v.reshape(-1, 2, 2 ** axis)
         b[:, 1 - outcome, :] = 0
         b[:, outcome, :] *= scale
+        return 1.0
 
 
 def rand_u(rng, d):

@@ -1,7 +1,8 @@
 """BASELINE config 5: GHZ-n / QFT-n state vector sharded over N GPUs by its high-order qubits.
 Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P tools/run_sharded.py --qubits 30 [--circuit qft|ghz]
-Self-checking (norm, closed-form amplitudes); rank 0 prints one JSON line."""
+        --master-port P tools/run_sharded.py --qubits 30 [--circuit qft|ghz|random]
+Self-checking (norm, closed-form amplitudes; --circuit random: every amplitude and two measurements against
+the NumPy oracle, n <= 16); rank 0 prints one JSON line."""
 import argparse
 import json
 import os
@@ -20,28 +21,100 @@ from dqc_simulator_b200.sharded import GpuShard, ShardedKet  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--qubits", dest="n", type=int, default=30)
-    ap.add_argument("--circuit", default="qft")
-    ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--peer", type=int, default=1, help="1: exchanges as one kernel per rank over CUDA-IPC peer memory (k_peer_swap); 2: also in-place peer gates")
-    a = ap.parse_args()
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+def rand_u(rng, d):
+    q, r = np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def random_ops(n, seed, steps):
+    """Gate list over every op family of ShardedKet (targets, controls and diagonals on global and local axes)."""
+    rng = np.random.default_rng(seed)
+    H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    cnot, swap = np.eye(4)[[0, 1, 3, 2]], np.eye(4)[[0, 2, 1, 3]]
+    ops = [("apply_1q", a, H) for a in range(0, n, 2)]     # (the other half comes alive gate by gate)
+    for _ in range(steps):
+        kind = rng.choice(["1q", "cnot", "2q", "ctrl", "diag1", "diag2", "diag3", "cz", "swap"])
+        ax = [int(x) for x in rng.choice(n, size=3, replace=False)]
+        if kind == "1q":
+            ops.append(("apply_1q", ax[0], rand_u(rng, 2)))
+        elif kind == "cnot":
+            ops.append(("apply_2q", ax[0], ax[1], cnot))
+        elif kind == "swap":
+            ops.append(("apply_2q", ax[0], ax[1], swap))
+        elif kind == "2q":
+            ops.append(("apply_2q", ax[0], ax[1], rand_u(rng, 4)))
+        elif kind == "ctrl":
+            ops.append(("apply_ctrl_1q", ax[0], ax[1], rand_u(rng, 2)))
+        elif kind == "cz":
+            ops.append(("apply_2q", ax[0], ax[1], np.diag([1, 1, 1, -1])))
+        elif kind == "diag1":
+            ops.append(("apply_diag", ax[:1], np.exp(1j * rng.normal(size=2))))
+        elif kind == "diag2":
+            ops.append(("apply_diag", ax[:2], np.exp(1j * rng.normal(size=4))))
+        else:
+            ops.append(("apply_diag", ax, np.exp(1j * rng.normal(size=8))))
+    return ops
+
+
+def run_random(a, rank, world, local):
+    """n <= 16: the sharded engine against the oracle, amplitude by amplitude, before and after measurements."""
+    from oracle.numpy_engine import OracleEngine
+
+    g = int(np.log2(world))
+    shard = GpuShard(a.n - g, local, rank == 0, seed=5)
+    sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer), seed=5)
+    o = OracleEngine("ket", a.n, 1, seed=5)
+    for x in range(a.n):
+        o.alloc_axis(x)
+    worst = 0.0
+    alive = set()
+
+    def touch(axes):       # lazy INSTR_INIT, like the executor: an axis goes live right before its first gate
+        for x in axes:
+            if x not in alive:
+                alive.add(x)
+                sk.alloc_axis(x)
+
+    for part in range(3):
+        for name, *args in random_ops(a.n, 7 + part, 40):
+            touch(args[0] if name == "apply_diag" else [v for v in args if isinstance(v, int)])
+            getattr(sk, name)(*args)
+            getattr(o, name)(*args)
+        got = sk.gather_logical()
+        want = o.full_state(0)[0]
+        worst = max(worst, float(np.abs(got - want).max()))
+        if part < 2:       # one measurement on an axis that is global right now (if any), one on a local one
+            glob = [x for x in range(a.n) if sk._is_global(x)]
+            axis = glob[0] if part == 0 and glob else next(x for x in range(a.n) if not sk._is_global(x))
+            touch([axis])
+            p0, p1 = o.prob_one(axis)
+            m = int(p1[0] > p0[0])
+            assert sk.measure(axis, None, m) == m
+            o.measure(axis, None, m)
+    st = shard.eng.peer_stats() if a.peer else dict(error=0)
+    res = dict(circuit="random", n=a.n, n_gpus=world, max_abs_err=worst, exchanges=sk.exchanges,
+               relabelled_swaps=sk.relabelled_swaps, peer=bool(a.peer), peer_error=st["error"])
+    assert worst < 1e-10 and st["error"] == 0, res
+    t = torch.tensor([worst], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["max_abs_err"] = float(t[0])
+    shard.close()
+    return res
+
+
+def run_fixture(a, rank, world, local):
     g = int(np.log2(world))
     suffix = ".json" if a.n <= 12 else ".json.gz"
     ops, _ = opstream.load(os.path.join(GOLDEN, f"c5_{a.circuit}{a.n}_mono{suffix}"))
     dqc = hardware.DQCSpec.uniform(1, num_positions=a.n, num_comm_qubits=0)
     best = None
     for rep in range(a.reps):
-        shard = GpuShard(a.n - g, local, rank == 0)
+        shard = GpuShard(a.n - g, local, rank == 0, lazy=a.peer < 2)
         sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer), peer_gates=a.peer >= 2)
         shard.eng.time_passes(True)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ex = executor.DQCExecutor(ops, dqc, sk).run()
+        executor.DQCExecutor(ops, dqc, sk).run()
         t_host = time.perf_counter() - t0
         sk.sync()
         dist.barrier(); torch.cuda.synchronize()
@@ -60,28 +133,47 @@ def main():
             cnt = torch.tensor([len(nz)], device=buf.device)
             dist.all_reduce(cnt)
             err = max(err, abs(int(cnt[0]) - 2))
-        t = torch.tensor([err, dt, sk.exchange_seconds], dtype=torch.float64, device=buf.device)
+        del mag
+        xs = sk.exchange_stats()
+        t = torch.tensor([err, dt, xs["seconds"]], dtype=torch.float64, device=buf.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         pass_ms, n_pass, amps = shard.eng.pass_time()
         st = shard.eng.stats()
         res = dict(circuit=a.circuit, n=a.n, n_gpus=world, seconds=float(t[1]), max_abs_err=float(t[0]),
                    norm=norm, exchanges=sk.exchanges, exchange_bytes_per_rank=sk.exchanged_bytes,
-                   exchange_seconds=float(t[2]), peer=bool(a.peer), peer_gates=sk.peer_gate_count, peer_seconds=sk.peer_seconds,
-                   host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
+                   exchange_seconds=float(t[2]), peer=bool(a.peer), relabelled_swaps=sk.relabelled_swaps,
+                   peer_error=xs["error"], host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
                    micro_ops=st["micro_ops"], pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
-                   nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges else None,
+                   nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges and t[2] > 0 else None,
                    passes_per_rank=st["passes"], api_ops=st["api_ops"], shard_bytes=(2 ** (a.n - g)) * 16,
-                   gate_updates_per_s=len([1 for _ in range(1)]) and (sum(len(s) for sl in ops.values() for s in sl) / float(t[1])))
-        assert abs(norm - 1) < 1e-9 and res["max_abs_err"] < 1e-10, res
+                   gate_updates_per_s=sum(len(s) for sl in ops.values() for s in sl) / float(t[1]))
+        assert abs(norm - 1) < 1e-9 and res["max_abs_err"] < 1e-10 and not res["peer_error"], res
         if best is None or res["seconds"] < best["seconds"]:
             best = res
-        shard.eng.close()
-        del shard, sk, buf, mag
+        del buf
+        shard.close()
+        del shard, sk
         torch.cuda.empty_cache()
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", dest="n", type=int, default=30)
+    ap.add_argument("--circuit", default="qft")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--peer", type=int, default=1, help="1: all global axes exchanged in one device-synchronised kernel over "
+                    "CUDA-IPC peer memory (k_peer_exchange); 0: pairwise NCCL send/recv; 2: host-synchronised peer gates")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    best = run_random(a, rank, world, local) if a.circuit == "random" else run_fixture(a, rank, world, local)
     if rank == 0:
         print(json.dumps(best), flush=True)
         os.makedirs("gpurun_out", exist_ok=True)
-        with open(f"gpurun_out/sharded_{a.circuit}{a.n}_x{world}{'_peer' if a.peer else ''}.json", "w") as f:
+        with open(a.out or f"gpurun_out/sharded_{a.circuit}{a.n}_x{world}{'_peer' if a.peer else ''}.json", "w") as f:
             json.dump(best, f)
     dist.destroy_process_group()
 
