@@ -97,7 +97,7 @@ enum ClOp : uint8_t {
   CL_BNOT = 19,
   CL_BCOPY = 20,
 };
-enum DynKind : int32_t { DYN_DEPOL = 0, DYN_DEPHASE = 1, DYN_AMPDAMP = 2 };
+enum DynKind : int32_t { DYN_DEPOL = 0, DYN_DEPHASE = 1, DYN_AMPDAMP = 2, DYN_ZFLIP = 3 };   // ZFLIP: Z with probability q
 struct ClInstr {   // 8 bytes; ten ride in one MicroOp
   uint8_t op, dst, a, b;
   int8_t cbit;
@@ -871,6 +871,7 @@ __device__ __forceinline__ DynCoef dyn_coef(int kind, double q) {
   DynCoef k;
   if (kind == DYN_DEPOL) { k.a = k.d = 1.0 - 0.5 * q; k.b = k.c = 0.5 * q; k.f = 1.0 - q; }
   else if (kind == DYN_DEPHASE) { k.a = k.d = 1.0; k.b = k.c = 0.0; k.f = 1.0 - q; }
+  else if (kind == DYN_ZFLIP) { k.a = k.d = 1.0; k.b = k.c = 0.0; k.f = 1.0 - 2.0 * q; }
   else { k.a = 1.0; k.b = q; k.c = 0.0; k.d = 1.0 - q; k.f = sqrt(1.0 - q); }
   return k;
 }
@@ -1201,6 +1202,8 @@ __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, cons
     digits[0] = (int)s;
   } else if (op.flags == 4) {   // dephasing of per-shot strength q: Z with probability q / 2
     digits[0] = (u >= 1.0 - 0.5 * treg[(int)op.p[3]]) ? 3 : 0;
+  } else if (op.flags == 5) {   // Z with per-shot probability q
+    digits[0] = (u >= 1.0 - treg[(int)op.p[3]]) ? 3 : 0;
   } else if (op.flags == 0) {
     digits[0] = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
   } else if (op.flags == 1) {

@@ -2835,7 +2835,7 @@ int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg) {
   if (int rc = check_ready(h)) return rc;
   if (int rc = check_live(h, axis, "dyn_channel")) return rc;
   if (reg < 0 || reg >= kTimeRegs) return fail(h, DQE_EINVAL, "dyn_channel: register out of range");
-  if (kind < DYN_DEPOL || kind > DYN_AMPDAMP) return fail(h, DQE_EINVAL, "dyn_channel: kind in {0 depol, 1 dephase, 2 ampdamp}");
+  if (kind < DYN_DEPOL || kind > DYN_ZFLIP) return fail(h, DQE_EINVAL, "dyn_channel: kind in {0 depol, 1 dephase, 2 ampdamp, 3 zflip}");
   if (int rc = ensure_tregs(h)) return rc;
   h->stats[4]++;
   if (h->formalism == DQE_DM) {
@@ -2849,7 +2849,7 @@ int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg) {
   if (kind == DYN_AMPDAMP) return fail(h, DQE_EUNSUPPORTED, "amplitude damping is dm-only");
   HostOp o = blank(h, OP_PAULI_SAMPLED);
   o.m.nb = 1; o.m.b[0] = (uint8_t)axis; o.need = 1ull << axis;
-  o.m.flags = kind == DYN_DEPOL ? 3 : 4;
+  o.m.flags = kind == DYN_DEPOL ? 3 : kind == DYN_DEPHASE ? 4 : 5;
   o.m.aux = (int32_t)h->draw++;
   o.m.p[3] = (double)reg;   // (lctrl is rebuilt from the control masks when the op is localised)
   push(h, o);

@@ -171,8 +171,10 @@ class QPU:
         be, ax, sp, T = self.ex.backend, self.axis[pos], self.spec, self.ex.T
         if T.same(now, last):
             return
-        rates = ((tlm.DYN_DEPOL, sp.mem_rate(pos)), (tlm.DYN_DEPHASE, sp.mem_dephase_rate),
-                 (tlm.DYN_AMPDAMP, sp.mem_amp_damp_rate))
+        r_depol, r_dephase, r_amp, r_zflip = sp.mem_rates(pos)
+        # (amplitude damping first, then the dephasing part: the order of NetSquid's T1T2NoiseModel [NS-doc])
+        rates = ((tlm.DYN_DEPOL, r_depol), (tlm.DYN_AMPDAMP, r_amp), (tlm.DYN_DEPHASE, r_dephase),
+                 (tlm.DYN_ZFLIP, r_zflip))
         if not any(r > 0 for _, r in rates):
             return
         if (T.is_reg(now) or T.is_reg(last)) and not (T.is_reg(now) and T.is_reg(last) and now.reg is last.reg):
@@ -183,15 +185,17 @@ class QPU:
         dt = T.sub(now, last)           # a host float: the same idle time in every shot
         if dt <= 0:
             return
-        rate = sp.mem_rate(pos)
-        if rate > 0:
-            be.depolarize([ax], 1.0 - math.exp(-dt * 1e-9 * rate))
-        if sp.mem_dephase_rate > 0:
-            pz = 0.5 * (1.0 - math.exp(-dt * 1e-9 * sp.mem_dephase_rate))
-            be.pauli_channel(ax, [1.0 - pz, 0.0, 0.0, pz])
-        if sp.mem_amp_damp_rate > 0:
-            g = 1.0 - math.exp(-dt * 1e-9 * sp.mem_amp_damp_rate)
+        if r_depol > 0:
+            be.depolarize([ax], 1.0 - math.exp(-dt * 1e-9 * r_depol))
+        if r_amp > 0:
+            g = 1.0 - math.exp(-dt * 1e-9 * r_amp)
             be.kraus_1q(ax, [[[1, 0], [0, math.sqrt(1 - g)]], [[0, math.sqrt(g)], [0, 0]]])
+        if r_dephase > 0:
+            pz = 0.5 * (1.0 - math.exp(-dt * 1e-9 * r_dephase))
+            be.pauli_channel(ax, [1.0 - pz, 0.0, 0.0, pz])
+        if r_zflip > 0:
+            pz = 1.0 - math.exp(-dt * 1e-9 * r_zflip)
+            be.pauli_channel(ax, [1.0 - pz, 0.0, 0.0, pz])
 
     def touch(self, positions, now):
         axes = []
@@ -423,6 +427,7 @@ class DQCExecutor:
         self.mailbox = {}     # (src, dst) -> list of (arrival_time, payload)
         self.ebit_requests = {}  # frozenset({a,b}) -> {node: (role, pos, time)}
         self.logged_results = []  # (node, position, CBit|int) in issue order
+        self.logged_times = []    # simulated time at which each of them was produced
         self.end_time = 0.0
         self.finished = False
         self._events = 0
@@ -581,6 +586,7 @@ class DQCExecutor:
                 q.execute_program(program)
                 res = program.output["result"]
                 self.logged_results.append((name, op[1], res[0] if res else None))
+                self.logged_times.append(q.clock)
                 program = QuantumProgram()
             elif last == "distribute_ebit":                     # dqc_control.py:803-832
                 pos = q.comm_qubits_free[0]

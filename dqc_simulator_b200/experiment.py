@@ -11,7 +11,7 @@ import numpy as np
 
 from . import executor, hardware, opstream
 
-GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 # examples/run_experiment.py:80-87 + examples/setup_hardware.py:18-33
 C2_NOISE = dict(p_depolar_error_cnot=1e-3, single_qubit_gate_error_prob=2e-5, meas_error_prob=3e-3,
@@ -28,7 +28,7 @@ def c2_hardware(noisy=True, F_werner=0.99, **extra):
 
 
 def load_c2(circuit):
-    return opstream.load(os.path.join(GOLDEN, f"c2_{circuit}5_3qpu_cat.json"))
+    return opstream.load(os.path.join(DATA, f"c2_{circuit}5_3qpu_cat.json"))
 
 
 def ideal_output_ket(qpu_ops, make_backend, dqc=None, max_qubits=7):
@@ -179,3 +179,46 @@ def get_data_collector(executor, qubit_indices_2b_checked, desired_state):
 
 
 get_data_collector4dm = get_data_collector   # util/helper.py:166-223: same frame, density-matrix reference
+
+
+class MidSimDataCollector:
+    """Results of the instructions a circuit marks ``"logged"`` (``dqc_control.py:754-791`` signals
+    ``QDCSignals.RESULT_PRODUCED`` with ``(result, ancilla_qubit_index)``), in the frame of
+    ``util/helper.py:236-263`` (``get_data_collector_for_mid_sim_instr_output``): NetSquid's ``time_stamp`` /
+    ``entity_name`` columns plus ``result`` and ``ancilla_qubit_index`` -- one row per logged instruction and shot
+    (column ``shot``; the reference runs one shot per process and so has one row per logged instruction)."""
+
+    def __init__(self, executor):
+        self.executor = executor
+        self._frame = None
+
+    def collect(self):
+        import pandas as pd
+
+        ex, be = self.executor, self.executor.backend
+        rows = []
+        for (node, index, res), when in zip(ex.logged_results, ex.logged_times):
+            if hasattr(res, "index"):          # outcome held per shot on the device
+                vals = np.asarray(be.read_creg(res.index), dtype=np.int64)
+            elif res is None:
+                vals = np.full(be.batch, -1, dtype=np.int64)
+            else:
+                vals = np.full(be.batch, int(res), dtype=np.int64)
+            t = ex.read_time(when) if ex.T.is_reg(when) else np.full(be.batch, float(when))
+            idx = index[0] if isinstance(index, (list, tuple)) and len(index) == 1 else index
+            rows.append(pd.DataFrame({"time_stamp": np.asarray(t, dtype=float), "entity_name": f"interpreter_{node}",
+                                      "result": vals, "ancilla_qubit_index": [idx] * be.batch,
+                                      "shot": np.arange(be.batch)}))
+        cols = ["time_stamp", "entity_name", "result", "ancilla_qubit_index", "shot"]
+        self._frame = pd.concat(rows, ignore_index=True) if rows else pd.DataFrame(columns=cols)
+        return self._frame
+
+    @property
+    def dataframe(self):
+        return self._frame if self._frame is not None else self.collect()
+
+
+def get_data_collector_for_mid_sim_instr_output(executor):
+    """``util/helper.py:236``: collector of the mid-simulation instruction outputs; read ``.dataframe`` after
+    ``executor.run()``."""
+    return MidSimDataCollector(executor)

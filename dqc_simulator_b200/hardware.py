@@ -32,6 +32,62 @@ def werner_state(F):
     return out
 
 
+# ---- memory noise models a user can hand to a QPU (``mem_noise_models`` / ``comm_qubit_mem_noise_model`` /
+# ``processing_qubit_mem_noise_model``, quantum_processors.py:83-123, 183-221, 257-260).  Same
+# constructor arguments as NetSquid's ``netsquid.components.models.qerrormodels`` classes [NS-doc]; here they are
+# parameter holders that the executor turns into idle-time channels of the engine.
+@dataclass
+class DepolarNoiseModel:
+    """(1 - p) rho + p I/2 with p = 1 - exp(-dt * 1e-9 * depolar_rate)  (rate in Hz), or p = depolar_rate when
+    ``time_independent``."""
+    depolar_rate: float = 0.0
+    time_independent: bool = False
+
+
+@dataclass
+class DephaseNoiseModel:
+    """Z with probability p = 1 - exp(-dt * 1e-9 * dephase_rate)  (``qapi.dephase(qubit, prob)``), or
+    p = dephase_rate when ``time_independent``."""
+    dephase_rate: float = 0.0
+    time_independent: bool = False
+
+
+@dataclass
+class T1T2NoiseModel:
+    """Amplitude damping with gamma = 1 - exp(-dt / T1), then pure dephasing that brings the total coherence decay
+    to exp(-dt / T2): off-diagonals x exp(-dt (1/T2 - 1/(2 T1))).  T1, T2 in ns (0 = off), T2 <= 2 T1."""
+    T1: float = 0.0
+    T2: float = 0.0
+
+
+def mem_channel_rates(model):
+    """Noise model -> idle-time channel rates in Hz: dict(depol, dephase (coherence decay), ampdamp, zflip)."""
+    out = dict(depol=0.0, dephase=0.0, ampdamp=0.0, zflip=0.0)
+    if model is None:
+        return out
+    name = type(model).__name__
+    if name == "DepolarNoiseModel":
+        if getattr(model, "time_independent", False):
+            raise ValueError("time-independent memory noise has no idle-time meaning")
+        out["depol"] = float(model.depolar_rate)
+    elif name == "DephaseNoiseModel":
+        if getattr(model, "time_independent", False):
+            raise ValueError("time-independent memory noise has no idle-time meaning")
+        out["zflip"] = float(model.dephase_rate)
+    elif name == "T1T2NoiseModel":
+        T1, T2 = float(model.T1), float(model.T2)
+        if T1 > 0:
+            out["ampdamp"] = 1e9 / T1
+        if T2 > 0:
+            r = 1e9 / T2 - (0.5e9 / T1 if T1 > 0 else 0.0)
+            if r < -1e-12:
+                raise ValueError("T1T2NoiseModel: T2 must not exceed 2 * T1")
+            out["dephase"] = max(r, 0.0)
+    else:
+        raise TypeError(f"unsupported memory noise model {name}")
+    return out
+
+
 @dataclass
 class PhysInstr:
     duration: float
@@ -60,6 +116,12 @@ class QPUSpec:
     # damping).  Not wired by any reference hardware spec; rates in Hz.
     mem_dephase_rate: float = 0.0
     mem_amp_damp_rate: float = 0.0
+    # user-selected models per position type / per position, like the reference's QPU arguments
+    # (quantum_processors.py:83-123): DepolarNoiseModel, DephaseNoiseModel or T1T2NoiseModel (above, or NetSquid's
+    # own objects: duck-typed on the class name and attributes).  They ADD to the rate fields.
+    comm_qubit_mem_noise_model: object = None
+    processing_qubit_mem_noise_model: object = None
+    mem_noise_models: list = None
 
     @property
     def comm_qubit_positions(self):
@@ -71,6 +133,16 @@ class QPUSpec:
 
     def mem_rate(self, pos):
         return self.comm_qubit_depolar_rate if pos < self.num_comm_qubits else self.proc_qubit_depolar_rate
+
+    def mem_rates(self, pos):
+        """Idle-time channel rates (Hz) of memory position ``pos``: (depol, dephase, ampdamp, zflip)."""
+        if self.mem_noise_models is not None:
+            model = self.mem_noise_models[pos]
+        else:
+            model = self.comm_qubit_mem_noise_model if pos < self.num_comm_qubits else self.processing_qubit_mem_noise_model
+        m = mem_channel_rates(model)
+        return (self.mem_rate(pos) + m["depol"], self.mem_dephase_rate + m["dephase"],
+                self.mem_amp_damp_rate + m["ampdamp"], m["zflip"])
 
     def phys(self, token):
         """Row of the physical-instruction table for an instruction token."""

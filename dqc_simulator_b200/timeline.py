@@ -31,7 +31,7 @@ import math
 CL_BAND, CL_BANDN, CL_BOR, CL_BNOT, CL_BCOPY = range(16, 21)
 
 # dynamic one-qubit channels whose strength q comes from a register (csrc: DynKind)
-DYN_DEPOL, DYN_DEPHASE, DYN_AMPDAMP = 0, 1, 2
+DYN_DEPOL, DYN_DEPHASE, DYN_AMPDAMP, DYN_ZFLIP = 0, 1, 2, 3
 
 
 class TReg:

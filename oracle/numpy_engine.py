@@ -343,6 +343,9 @@ class OracleEngine:
             elif kind == 1:
                 new[:, 0, 1] = (1 - qb) * e01
                 new[:, 1, 0] = (1 - qb) * e10
+            elif kind == 3:
+                new[:, 0, 1] = (1 - 2 * qb) * e01
+                new[:, 1, 0] = (1 - 2 * qb) * e10
             elif kind == 2:
                 new[:, 0, 0] = e00 + qb * e11
                 new[:, 1, 1] = (1 - qb) * e11
@@ -361,6 +364,8 @@ class OracleEngine:
             s = np.minimum(s, 3)
         elif kind == 1:
             s = np.where(u >= 1.0 - q / 2.0, 3, 0)
+        elif kind == 3:
+            s = np.where(u >= 1.0 - q, 3, 0)
         else:
             raise NotImplementedError("amplitude damping is DM-only")
         for idx in (1, 2, 3):

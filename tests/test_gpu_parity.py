@@ -201,7 +201,7 @@ def random_program(b, rng, steps, formalism, check_every=0, classical=False):
             cs.scratch_bits.append(d)
         elif c == "dyn":
             q = int(rng.choice(cs.qs[-4:]))
-            kinds = [0, 1, 2] if formalism == "dm" else [0, 1]
+            kinds = [0, 1, 2, 3] if formalism == "dm" else [0, 1, 3]
             if cs.scratch_bits and rng.integers(3) == 0:
                 bit = cs.scratch_bits[-1]
                 b.set_predicate(bit)
