@@ -91,11 +91,14 @@ enum ClOp : uint8_t {
   CL_ADDIF = 12,  // d <- a + (creg bit `cbit` ? imm : 0)
   CL_QEXP2 = 13,  // d <- 1 - exp(-max(0, a - b + imm) * imm2): idle time and strength in one instruction; a / b = 255
                   // stand for 0, imm2 is a second constant-pool index carried in the (cbit, pad) bytes
+  CL_GEOM = 14,   // d <- min(imm2, 1 + floor(ln(u) / imm)), u = the shot's Philox uniform of draw (a | b << 8), imm = ln(1 - p):
+                  // number of attempts of a heralded entanglement link until the first success (geometric law)
   CL_BAND = 16,   // creg bit d <- bit a & bit b
   CL_BANDN = 17,  // d <- a & ~b
   CL_BOR = 18,
   CL_BNOT = 19,
   CL_BCOPY = 20,
+  CL_RANDBIT = 21,  // creg bit d <- (u < imm), u = the shot's Philox uniform of draw (a | b << 8)
 };
 enum DynKind : int32_t { DYN_DEPOL = 0, DYN_DEPHASE = 1, DYN_AMPDAMP = 2, DYN_ZFLIP = 3 };   // ZFLIP: Z with probability q
 struct ClInstr {   // 8 bytes; ten ride in one MicroOp
@@ -820,7 +823,8 @@ __device__ __forceinline__ double one_minus_exp_neg(double x) {
 }
 
 // one instruction on the register file `R` (shared or global) and the classical word `cw`; c = its immediate
-__device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double* R, uint64_t& cw, const double* imm) {
+__device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double* R, uint64_t& cw, const double* imm,
+                                        uint64_t seed, uint64_t gshot) {
   switch (in.op) {   // (register operands are read inside the cases: a / b are creg bits for the B* ops)
     case CL_CONST: R[in.dst] = c; break;
     case CL_ADDI: R[in.dst] = R[in.a] + c; break;
@@ -840,6 +844,18 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double
       R[in.dst] = one_minus_exp_neg(fmax(0.0, ra - rb + c) * rate);
       break;
     }
+    case CL_GEOM: case CL_RANDBIT: {
+      double u, u2;
+      shot_uniforms(seed, gshot, (uint64_t)in.a | ((uint64_t)in.b << 8), u, u2);
+      if (in.op == CL_RANDBIT) {
+        cw = (cw & ~(1ull << in.dst)) | ((uint64_t)(u < c) << in.dst);
+      } else {
+        const double kmax = imm[(uint32_t)(uint8_t)in.cbit | ((uint32_t)in.pad << 8)];
+        const double k = u > 0.0 ? 1.0 + floor(log(u) / c) : kmax;
+        R[in.dst] = fmin(kmax, k);
+      }
+      break;
+    }
     case CL_BAND: case CL_BANDN: case CL_BOR: case CL_BNOT: case CL_BCOPY: {
       const uint64_t x = (cw >> in.a) & 1ull, y = (cw >> in.b) & 1ull;
       const uint64_t v = in.op == CL_BAND ? (x & y) : in.op == CL_BANDN ? (x & (y ^ 1ull)) : in.op == CL_BOR ? (x | y)
@@ -852,7 +868,8 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double
 }
 // a run of instructions in order on one thread; the fetch of instruction i + 1 (and of its immediate) is issued
 // before instruction i executes, so the chain pays for the register-file round trips only
-__device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt, double* R, uint64_t& cw, const double* imm) {
+__device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt, double* R, uint64_t& cw, const double* imm,
+                                       uint64_t seed, uint64_t gshot) {
   if (cnt <= 0) return;
   ClInstr nxt = ci[0];
   double cn = imm[nxt.imm];
@@ -860,7 +877,7 @@ __device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt, double* R, ui
     const ClInstr in = nxt;
     const double c = cn;
     if (i + 1 < cnt) { nxt = ci[i + 1]; cn = imm[nxt.imm]; }
-    cl_exec(in, c, R, cw, imm);
+    cl_exec(in, c, R, cw, imm, seed, gshot);
   }
 }
 
@@ -1741,7 +1758,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         // stored itself -- so the block needs no barrier at all (the barrier that ended the previous micro-op
         // already ordered it behind every earlier reader of the registers it overwrites).
         if (hdr_coff & 2) __syncthreads();   // block right behind another span's block (fence only in between)
-        cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts));
+        cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+               pp.shot_offset + shot);
         continue;
       }
       if constexpr (FORM == 0) {   // ---- ket micro-ops
@@ -1957,6 +1975,7 @@ struct ClassicalParams {
   double* treg;
   int64_t batch;
   int32_t nops, pad;
+  uint64_t seed, shot_offset;
 };
 __global__ void __launch_bounds__(128) k_classical(const ClassicalParams cp) {
   const int64_t shot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1966,7 +1985,7 @@ __global__ void __launch_bounds__(128) k_classical(const ClassicalParams cp) {
   double* R = cp.treg + (uint64_t)shot * kTimeRegs;
   for (int k = 0; k < cp.nops; ++k) {
     const MicroOp& c = cp.ops[k];
-    cl_run(cl_payload(c), c.flags, R, cw, cp.imm);
+    cl_run(cl_payload(c), c.flags, R, cw, cp.imm, cp.seed, cp.shot_offset + (uint64_t)shot);
   }
   if (cw != cw0) cp.creg[shot] = cw;
 }

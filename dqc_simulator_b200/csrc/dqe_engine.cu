@@ -1344,7 +1344,7 @@ struct Planner {
     };
     for (size_t i = 0; i < ops.size(); ++i) {
       idx[i] = slot_of(ops[i]->imm);
-      if (ops[i]->ci.op == CL_QEXP2) idx2[i] = slot_of(ops[i]->imm2);
+      if (ops[i]->ci.op == CL_QEXP2 || ops[i]->ci.op == CL_GEOM) idx2[i] = slot_of(ops[i]->imm2);
     }
     const int base = (int)(dev_consts.size() - pcb) * 2;
     for (size_t j = 0; j < vals.size(); j += 2)
@@ -1374,7 +1374,7 @@ struct Planner {
         if (is_par != (par == 1)) continue;
         ClInstr ci = ho->ci;
         ci.imm = (uint16_t)(base + idx[i]);
-        if (ci.op == CL_QEXP2) { const int i2 = base + idx2[i]; ci.cbit = (int8_t)(i2 & 0xff); ci.pad = (uint8_t)(i2 >> 8); }
+        if (ci.op == CL_QEXP2 || ci.op == CL_GEOM) { const int i2 = base + idx2[i]; ci.cbit = (int8_t)(i2 & 0xff); ci.pad = (uint8_t)(i2 >> 8); }
         memcpy(reinterpret_cast<char*>(&m) + 16 + 8 * n, &ci, sizeof(ci));
         if (++n == kClPerOp) { close_op(); open_op(); }
       }
@@ -1948,7 +1948,7 @@ struct Planner {
         op_slots = 0;
         if (op.kind == 2) {
           ++ncl;
-          if (ncl % 2 == 0 || op.ci.op == CL_QEXP2) op_consts = 1;
+          if (ncl % 2 == 0 || op.ci.op == CL_QEXP2 || op.ci.op == CL_GEOM) op_consts = 1;
           if (ncl % 8 == 1) op_slots = 1;
         }
       } else {
@@ -2201,6 +2201,7 @@ int launch_passes(dqe_t* h, Planner& pl) {
       cp.ops = h->d_ops + P.op_begin;
       cp.imm = reinterpret_cast<const double*>(h->d_consts + P.const_begin);
       cp.creg = cur_creg(h); cp.treg = h->treg_buf[h->tpar]; cp.batch = h->batch; cp.nops = P.pp.nops;
+      cp.seed = h->seed; cp.shot_offset = h->shot_offset;
       k_classical<<<(unsigned)((h->batch + 127) / 128), 128, 0, h->stream>>>(cp);
       h->stats[2]++;
       continue;
@@ -2817,6 +2818,32 @@ int dqe_classical_qexp2(dqe_t* h, int dst, int a, int b, double offset, double r
   o.ci.cbit = 0; o.ci.pad = 0; o.ci.imm = 0;
   o.imm = offset; o.imm2 = rate;
   h->max_reg = std::max(h->max_reg, dst);
+  h->queue.push_back(o);
+  h->stats[4]++;
+  return 0;
+}
+
+// Per-shot random numbers for the classical machine (the heralded entanglement link, physical_layer.py:685-753):
+// kind 0: creg bit dst <- (u < p);  kind 1: register dst <- min(kmax, 1 + floor(ln u / ln(1 - p))), the number of
+// attempts until the first success of probability p.  u = the shot's Philox uniform of the next draw index.
+int dqe_classical_rand(dqe_t* h, int kind, int dst, double p, double kmax) {
+  if (int rc = check_ready(h)) return rc;
+  if (kind != 0 && kind != 1) return fail(h, DQE_EINVAL, "classical_rand: kind 0 (bit) or 1 (geometric)");
+  if (!(p >= 0.0 && p <= 1.0)) return fail(h, DQE_EINVAL, "classical_rand: probability in [0, 1]");
+  if (kind == 0 ? (dst < 0 || dst >= 64) : (dst < 0 || dst >= kTimeRegs)) return fail(h, DQE_EINVAL, "classical_rand: dst out of range");
+  if (h->draw >= 65536) return fail(h, DQE_EUNSUPPORTED, "classical_rand: draw index beyond 16 bits");
+  if (h->olog_draws > 0 && (int64_t)h->draw >= h->olog_draws) return fail(h, DQE_EINVAL, "outcome log is full: raise the outcome_log option");
+  if (int rc = ensure_tregs(h)) return rc;
+  const uint64_t draw = h->draw++;
+  HostOp o = blank(h, 0);
+  o.kind = 2;
+  o.m.pred_bit = -1;
+  o.ci.op = (uint8_t)(kind == 0 ? CL_RANDBIT : CL_GEOM); o.ci.dst = (uint8_t)dst;
+  o.ci.a = (uint8_t)(draw & 0xff); o.ci.b = (uint8_t)(draw >> 8);
+  o.ci.cbit = 0; o.ci.pad = 0; o.ci.imm = 0;
+  if (kind == 0) o.imm = p;
+  else { o.imm = p >= 1.0 ? -1e300 : (p <= 0.0 ? -1e-300 : std::log1p(-p)); o.imm2 = kmax; }
+  if (kind == 1) h->max_reg = std::max(h->max_reg, dst);
   h->queue.push_back(o);
   h->stats[4]++;
   return 0;

@@ -64,6 +64,7 @@ ABI = {
                                         ctypes.c_int, ctypes.c_double]),
     "dqe_classical_qexp2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                            ctypes.c_double]),
+    "dqe_classical_rand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
     "dqe_classical_fence": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_enqueue_dyn_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dqe_read_time_reg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
@@ -300,6 +301,11 @@ class Engine:
 
     def classical_fence(self):
         self._ck(self._lib.dqe_classical_fence(self._h))
+
+    def classical_rand(self, kind, dst, p, kmax=0.0):
+        """kind 0: creg bit dst <- (u < p); kind 1: register dst <- attempts until the first success of probability p
+        (capped at kmax); u = the shot's next Philox uniform."""
+        self._ck(self._lib.dqe_classical_rand(self._h, int(kind), int(dst), float(p), float(kmax)))
 
     def dyn_channel(self, axis, kind, reg):
         """One-qubit channel whose strength is read per shot from classical register ``reg``

@@ -428,6 +428,7 @@ class DQCExecutor:
         self.ebit_requests = {}  # frozenset({a,b}) -> {node: (role, pos, time)}
         self.logged_results = []  # (node, position, CBit|int) in issue order
         self.logged_times = []    # simulated time at which each of them was produced
+        self.heralded_links = []  # per heralded ebit: nodes, server, per-shot herald time, creg bit of the Bell state
         self.end_time = 0.0
         self.finished = False
         self._events = 0
@@ -523,23 +524,70 @@ class DQCExecutor:
         if other in link["req"]:
             first, second = sorted((node, other))   # qout0 -> side A, qout1 -> side B
             (pa, ta, ra), (pb, tb, rb) = link["req"][first], link["req"][second]
-            t_arrive = self.T.add(self._handshake_done(ta, ra, tb, rb), self.dqc.ent_delay)
             qa, qb = self.qpus[first], self.qpus[second]
             qa._drop(pa)
             qb._drop(pb)
             ax_a = self._claim_axis(True)
             ax_b = self._claim_axis(True)
-            self.backend.inject_2q(ax_a, ax_b, self.dqc.state4distribution, self.dqc.ebit_is_dm)
-            qa.axis[pa], qb.axis[pb] = ax_a, ax_b
-            qa.last_access[pa] = qb.last_access[pb] = t_arrive
-            self.ebits += 1
             link["req"] = {}
-            link["done"] = {first: t_arrive, second: t_arrive}
+            self.ebits += 1
+            if self.dqc.heralded is not None:
+                server = second if rb == "server" or ra == "client" else first
+                link["done"] = self._heralded_entangle(first, second, pa, pb, ax_a, ax_b, server,
+                                                       self._handshake_done(ta, ra, tb, rb))
+            else:
+                t_arrive = self.T.add(self._handshake_done(ta, ra, tb, rb), self.dqc.ent_delay)
+                self.backend.inject_2q(ax_a, ax_b, self.dqc.state4distribution, self.dqc.ebit_is_dm)
+                qa.axis[pa], qb.axis[pb] = ax_a, ax_b
+                qa.last_access[pa] = qb.last_access[pb] = t_arrive
+                link["done"] = {first: t_arrive, second: t_arrive}
         while node not in link["done"]:
             yield "ebit"
         t_arrive = link["done"].pop(node)
         self._events += 1
         self.qpus[node].clock = self.T.max(self.qpus[node].clock, t_arrive)
+
+    def _heralded_entangle(self, first, second, pa, pb, ax_a, ax_b, server, t_ready):
+        """``MidpointHeraldingProtocol.entangle_comm_qubits`` (``physical_layer.py:685-753``) for every shot of the
+        batch at once.  Per shot: the number of emit attempts until the midpoint BSM heralds success (geometric law,
+        the shot's own Philox draw) moves that shot's clock by attempts x (INIT + EMIT + round trip); the heralded Bell
+        state is Psi+ or Psi- with probability 1/2 each (a second draw); the server turns it into Phi+ with X, and Z
+        where Psi- was heralded -- gates with their own noise and duration, in exactly those shots -- then tells the
+        client (one classical hop).  Failed attempts leave nothing behind (the comm qubit is re-INITed); a shot that
+        exhausts ``max_num_ent_attempts`` is treated as succeeding on the last one (the reference would signal
+        ``ent_failed`` and stall; probability (1 - p)^100)."""
+        be, T, hl = self.backend, self.T, self.dqc.heralded
+        qa, qb = self.qpus[first], self.qpus[second]
+        cycle = qa.spec.init_time + hl.emit_duration + hl.round_trip
+        if not getattr(be, "n_time_regs", 0):
+            raise NotImplementedError("the heralded link needs a backend with per-shot classical registers")
+        t_herald, _k = T.attempts_then(t_ready, hl.success_probability, hl.max_num_ent_attempts, cycle)
+        bit = self.creg.alloc()
+        be.classical_rand(0, bit, 0.5, 0.0)                 # 1: Psi- heralded
+        T.fence()
+        self.creg.fence()
+        psi_plus = np.array([0, 1, 1, 0], dtype=complex) / math.sqrt(2.0)
+        be.inject_2q(ax_a, ax_b, psi_plus, False)
+        be.set_predicate(bit)
+        be.apply_1q(ax_b, np.diag([1.0 + 0j, -1.0]))        # Psi+ -> Psi- in the shots that heralded it (state preparation)
+        be.set_predicate(-1)
+        if hl.visibility < 1.0:
+            if be.formalism not in (1, "dm"):
+                raise NotImplementedError("heralded link: visibility < 1 needs the density-matrix formalism")
+            be.pauli_channel(ax_b, [0.5 * (1.0 + hl.visibility), 0.0, 0.0, 0.5 * (1.0 - hl.visibility)])
+        qa.axis[pa], qb.axis[pb] = ax_a, ax_b
+        # the spin-photon pairs were emitted one round trip before the herald: memory noise runs from there
+        qa.last_access[pa] = qb.last_access[pb] = T.add(t_herald, -hl.round_trip)
+        qs, ps = (qa, pa) if server == first else (qb, pb)
+        qs.clock = T.max(qs.clock, t_herald)
+        fix = QuantumProgram()
+        fix.apply(ins.INSTR_X, ps)
+        fix.apply(ins.INSTR_Z, ps, predicate=CBit(bit))
+        qs.execute_program(fix)
+        t_server = qs.clock
+        t_client = T.add(t_server, self.dqc.classical_delay)
+        self.heralded_links.append(dict(nodes=(first, second), server=server, herald_time=t_herald, bell_bit=bit))
+        return {first: t_server if server == first else t_client, second: t_server if server == second else t_client}
 
     def _handshake_done(self, ta, ra, tb, rb):
         """Time at which the client fires the source trigger (``physical_layer.py:269-335``): the

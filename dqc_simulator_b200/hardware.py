@@ -164,12 +164,52 @@ class QPUSpec:
 
 
 @dataclass
+class HeraldedLinkSpec:
+    """Probabilistic entangling link: ``create_midpoint_heralded_entangling_link`` (``hardware/connections.py:399-499``,
+    a ``netsquid_physlayer`` ``MiddleHeraldedConnection``) driven by ``MidpointHeraldingProtocol``
+    (``software/physical_layer.py:596-768``).  Each attempt: INIT the comm qubit, ``INSTR_EMIT`` a photon entangled
+    with it on both QPUs, the photons meet at the midpoint Bell-state measurement, the herald comes back.  A linear-
+    optics BSM recognises |Psi+> and |Psi-> only, so an attempt succeeds with probability 1/2 times the two arms'
+    transmission; the server then turns the heralded state into |Phi+> with X (and Z for Psi-).
+    Model [NS-doc, pinned by the reference only in the ideal case, test_physical_layer_and_hardware_integration.py:
+    267-295]: double-click protocol without dark counts; photon loss and detector efficiency lower the success
+    probability, ``visibility`` V leaves the heralded state (1+V)/2 |Psi+-><Psi+-| + (1-V)/2 |Psi-+><Psi-+|."""
+    length_km: float = 2e-3
+    p_loss_init: float = 0.0
+    p_loss_length: float = 0.0          # dB / km
+    speed_of_light: float = 200000.0    # km / s
+    detector_efficiency: float = 1.0
+    visibility: float = 1.0
+    dark_count_probability: float = 0.0
+    emit_duration: float = 0.0          # ns (INSTR_EMIT has no physical instruction in the reference's QPU table)
+    max_num_ent_attempts: int = 100     # physical_layer.py:664
+
+    def __post_init__(self):
+        if self.dark_count_probability:
+            raise NotImplementedError("heralded link: dark counts are outside the modelled (double-click, no false herald) case")
+
+    @property
+    def arm_transmission(self):
+        return (1.0 - self.p_loss_init) * 10.0 ** (-self.p_loss_length * (self.length_km / 2.0) / 10.0) * self.detector_efficiency
+
+    @property
+    def success_probability(self):
+        return 0.5 * self.arm_transmission ** 2
+
+    @property
+    def round_trip(self):
+        """ns from emission to the herald's arrival: photon to the midpoint, outcome back."""
+        return 1e9 * self.length_km / self.speed_of_light
+
+
+@dataclass
 class DQCSpec:
     qpus: list = field(default_factory=list)
     state4distribution: np.ndarray = None  # ket (4,) or dm (4,4); default ks.b00
     ent_delay: float = 1e9 / 182.0         # ns (examples/setup_hardware.py:18,38)
     node_separation_km: float = 2e-3       # dqc_creation.py:512-516
     handshake_wait: float = 600e3          # physical_layer.py:286
+    heralded: HeraldedLinkSpec = None      # None: BlackBoxEntanglingQsourceConnection (deterministic ebits)
 
     def __post_init__(self):
         if self.state4distribution is None:
@@ -193,5 +233,6 @@ class DQCSpec:
     def uniform(cls, num_qpus, state4distribution=None, ent_delay=1e9 / 182.0, **qpu_kwargs):
         """Like ``DQC(entangling_connection_class, num_qpus, ..., qpu_class=NoisyQPU, **kw)``:
         nodes are named ``node_{i}`` (``dqc_creation.py:541-548``)."""
+        heralded = qpu_kwargs.pop("heralded", None)
         return cls([QPUSpec(name=f"node_{i}", **qpu_kwargs) for i in range(num_qpus)],
-                   state4distribution, ent_delay)
+                   state4distribution, ent_delay, heralded=heralded)

@@ -224,6 +224,15 @@ class Timeline:
         self.ops += 1
         return TVal(d, 0.0)
 
+    def attempts_then(self, t0, p, kmax, cycle):
+        """t0 + k * cycle with k = the shot's number of attempts until the first success of probability p (geometric
+        law, capped at kmax; ``dqe_classical_rand`` kind 1): the heralded link's retry loop."""
+        k = self._new()
+        self.be.classical_rand(1, k.index, float(p), float(kmax))
+        self.ops += 1
+        base = t0 if isinstance(t0, TVal) else self.const(t0)
+        return self._emit(CL_FMAI, TVal(k), base, imm=cycle, off=base.off), TVal(k)
+
     # ---- classical bits --------------------------------------------------------------------------
     def bit_op(self, op, dst_bit, a_bit, b_bit=0):
         self.be.classical_op(op, int(dst_bit), int(a_bit), int(b_bit), -1, 0.0)

@@ -177,6 +177,12 @@ int dqe_classical_op(dqe_t* h, int opcode, int dst, int a, int b, int cbit, doub
  * times it lies between (a / b = 255 stand for 0).  Like QEXP, its result is read by channels only. */
 int dqe_classical_qexp2(dqe_t* h, int dst, int a, int b, double offset, double rate);
 int dqe_classical_fence(dqe_t* h);
+/* Per-shot random numbers for the classical machine, drawn from the shot's Philox stream (next draw index, like a
+ * measurement): kind 0: creg bit dst <- (u < p); kind 1: register dst <- min(kmax, 1 + floor(ln u / ln(1 - p))) =
+ * attempts until the first success of probability p.  The probabilistic physical layer needs them: which Bell
+ * state the midpoint BSM heralded and how many emit attempts it took (physical_layer.py:685-753,
+ * connections.py:399-499) differ from shot to shot and shift each shot's simulated clock. */
+int dqe_classical_rand(dqe_t* h, int kind, int dst, double p, double kmax);
 int dqe_enqueue_dyn_channel(dqe_t* h, int axis, int kind, int reg);
 int dqe_read_time_reg(dqe_t* h, int reg, double* out /*batch*/);
 /* Every measurement outcome of every shot, in draw order (the reference's mid-simulation result

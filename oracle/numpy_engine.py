@@ -322,6 +322,18 @@ class OracleEngine:
     def classical_fence(self):
         pass
 
+    def classical_rand(self, kind, dst, p, kmax=0.0):
+        """dqe_classical_rand: per-shot Philox uniform of the next draw; bit <- (u < p) or the geometric attempt count."""
+        u, _ = self._next_uniforms()
+        if kind == 0:
+            bit = np.uint64(1) << np.uint64(dst)
+            self.creg = (self.creg & ~bit) | np.where(u < p, bit, np.uint64(0))
+        else:
+            lnq = -1e300 if p >= 1.0 else (-1e-300 if p <= 0.0 else np.log1p(-p))
+            with np.errstate(divide="ignore"):
+                k = np.where(u > 0.0, 1.0 + np.floor(np.log(np.maximum(u, 1e-300)) / lnq), kmax)
+            self.treg[dst] = np.minimum(kmax, k)
+
     def read_time_reg(self, reg):
         return self.treg[int(reg)].copy()
 

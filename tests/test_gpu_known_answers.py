@@ -204,3 +204,26 @@ def test_batched_shots_follow_their_own_timeline_on_the_engine(circuit, batch):
         assert np.abs(rho[s] - r1).max() < 1e-10
         assert abs(end[s] - e1) < 1e-5
     assert len(set(end.tolist())) > 1
+
+
+def test_heralded_link_engine_equals_oracle_shot_by_shot():
+    """The probabilistic physical layer on the CUDA engine: per-shot attempt counts (CL_GEOM) and heralded Bell
+    states (CL_RANDBIT) come from the shot's Philox stream inside the tile passes -- herald times, Bell bits and the
+    two-qubit states equal the oracle's in every shot; with gate + memory noise the Z fix-up (135 us, its own noise)
+    exists in exactly the Psi- shots."""
+    from dqc_simulator_b200 import hardware
+
+    B00 = np.array([1, 0, 0, 1], dtype=complex) / np.sqrt(2)
+    for kw in (dict(), dict(p_loss_init=0.3, visibility=0.8)):
+        res = []
+        for mk in (gpu, cpu):
+            dqc = hardware.DQCSpec.uniform(2, num_positions=5, heralded=hardware.HeraldedLinkSpec(**kw),
+                                           single_qubit_gate_error_prob=1e-3, comm_qubit_depolar_rate=50.0)
+            ex, be, _ = rc.run_golden(mk, "ref_distribute_ebit.json", "dm", max_qubits=4, batch=96, dqc=dqc)
+            axes = ex.axes_of([(0, "node_0"), (0, "node_1")])
+            link = ex.heralded_links[0]
+            res.append((ex.read_time(link["herald_time"]), np.asarray(be.read_creg(link["bell_bit"])),
+                        np.array([be.reduced_dm(axes, s) for s in range(96)])))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        assert np.abs(res[0][2] - res[1][2]).max() < TOL
+        assert len(set(res[0][0].tolist())) > 2 and 0 < res[0][1].sum() < 96

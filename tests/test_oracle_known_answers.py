@@ -191,3 +191,44 @@ def test_user_selected_memory_noise_models():
             # T1T2, and accept the two candidate start times otherwise
             cands = [want01(t) for t in (6e6, 6e6 - 135e3, 6e6 + 3.0, 6e6 - 135e3 + 3.0, 6e6 + 135e3)]
             assert min(abs(got - abs(c)) for c in cands) < 1e-9, (type(model).__name__, per_shot, got, cands)
+
+
+def _heralded(make_backend, batch=64, **link):
+    from dqc_simulator_b200 import hardware
+
+    hl = hardware.HeraldedLinkSpec(**link)
+    noise = dict(single_qubit_gate_error_prob=link.pop("p1", 0.0)) if "p1" in link else {}
+    dqc = hardware.DQCSpec.uniform(2, num_positions=5, heralded=hl, **noise)
+    ex, be, _ = rc.run_golden(make_backend, "ref_distribute_ebit.json", "dm", max_qubits=4, batch=batch, dqc=dqc)
+    return ex, be, hl
+
+
+def test_heralded_link_distributes_phi_plus_with_per_shot_attempts():
+    """The probabilistic physical layer: ``MidpointHeraldingProtocol`` over a midpoint-BSM link
+    (physical_layer.py:685-753, connections.py:399-499).  The reference's own check -- the two comm qubits end in
+    Phi+ to 1e-5 with either node as client (test_physical_layer_and_hardware_integration.py:267-295) -- holds in
+    every shot; the number of emit attempts is geometric with p = 1/2 (ideal arms) and moves each shot's clock by
+    attempts x (INIT + EMIT + round trip); Psi+ / Psi- heralds are fair; lossy arms lower p; visibility V leaves
+    fidelity (1 + V) / 2."""
+    B00 = np.array([1, 0, 0, 1], dtype=complex) / np.sqrt(2)
+    ex, be, hl = _heralded(make, batch=400)
+    axes = ex.axes_of([(0, "node_0"), (0, "node_1")])
+    fid = np.array([be.fidelity_ket(axes, B00, s) for s in range(400)])
+    assert np.abs(fid - 1.0).max() < 1e-12
+    link = ex.heralded_links[0]
+    t = ex.read_time(link["herald_time"])
+    cycle = 3.0 + hl.round_trip
+    k = (t - t.min()) / cycle + 1.0
+    assert np.abs(k - np.rint(k)).max() < 1e-9 and k.min() == 1.0
+    assert abs(k.mean() - 2.0) < 0.25                      # geometric, p = 1/2: mean 2, sigma sqrt(2) / 20
+    bell = np.asarray(be.read_creg(link["bell_bit"]))
+    assert abs(bell.mean() - 0.5) < 0.1
+    # lossy arms: p = 0.5 * (0.8 * 0.9)^2 = 0.2592 -> mean attempts 3.86
+    ex2, be2, hl2 = _heralded(make, batch=400, p_loss_init=0.2, detector_efficiency=0.9)
+    assert abs(hl2.success_probability - 0.2592) < 1e-12
+    t2 = ex2.read_time(ex2.heralded_links[0]["herald_time"])
+    k2 = (t2 - t2.min()) / cycle + 1.0
+    assert abs(k2.mean() - 1.0 / 0.2592) < 0.6
+    ex3, be3, _ = _heralded(make, batch=8, visibility=0.9)
+    axes3 = ex3.axes_of([(0, "node_0"), (0, "node_1")])
+    assert max(abs(be3.fidelity_ket(axes3, B00, s) - 0.95) for s in range(8)) < 1e-12
