@@ -2220,6 +2220,46 @@ __global__ void __launch_bounds__(256) k_probs_bit(const double2* __restrict__ s
   }
 }
 
+// Density matrix held as a KET on 2n bits (rows | columns) and sharded over GPUs by row bits: the local part of
+// Tr(P_axis rho).  A diagonal element has, for every qubit, equal row and column bit; pair k = (a[k], b[k]) local
+// bit positions that must agree, fixed[k] >= 0: the partner bit is a rank bit of that value (b[k] unused).
+struct DiagProbParams {
+  const double2* state;
+  uint64_t n;
+  int32_t npairs, target;     // target: local bit whose value labels the outcome, or -1 (outcome fixed by the rank)
+  int8_t a[32], b[32], fixed[32];
+  double* out;
+};
+__global__ void __launch_bounds__(256) k_probs_diag(const DiagProbParams dp) {
+  double a0 = 0.0, a1 = 0.0;
+  uint64_t eqmask_a = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dp.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    bool diag = true;
+    for (int k = 0; k < dp.npairs; ++k) {
+      const uint64_t va = (i >> dp.a[k]) & 1ull;
+      const uint64_t vb = dp.fixed[k] >= 0 ? (uint64_t)dp.fixed[k] : ((i >> dp.b[k]) & 1ull);
+      if (va != vb) { diag = false; break; }
+    }
+    if (!diag) continue;
+    const double w = dp.state[i].x;
+    if (dp.target >= 0 && ((i >> dp.target) & 1ull)) a1 += w; else a0 += w;
+  }
+  (void)eqmask_a;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  __shared__ double sa[8][2];
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5][0] = a0; sa[threadIdx.x >> 5][1] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) { t0 += sa[w][0]; t1 += sa[w][1]; }
+    dp.out[2 * blockIdx.x] = t0; dp.out[2 * blockIdx.x + 1] = t1;
+  }
+}
+
 // reduced density matrix / fidelity of <= 5 axes.  `rest` enumerates the live bits that are
 // traced over (dense index -> physical offset through segs).
 struct ReadoutParams {

@@ -3192,6 +3192,34 @@ int dqe_probs(dqe_t* h, int axis, double* out2) {
   return 0;
 }
 
+int dqe_probs_diag(dqe_t* h, int npairs, const int* a, const int* b, const int* fixed, int target, double* out2) {
+  if (int rc = do_flush(h)) return rc;
+  NEED_DEVICE(h);
+  if (h->formalism != DQE_KET || h->batch != 1) return fail(h, DQE_EUNSUPPORTED, "probs_diag: single-shot ket view only");
+  if (!out2 || npairs < 0 || npairs > 32 || (npairs && (!a || !b || !fixed)) || target >= h->nmax)
+    return fail(h, DQE_EINVAL, "probs_diag: bad argument");
+  DiagProbParams dp;
+  memset(&dp, 0, sizeof(dp));
+  dp.state = h->state; dp.n = 1ull << h->P; dp.npairs = npairs; dp.target = target;
+  for (int k = 0; k < npairs; ++k) {
+    if (a[k] < 0 || a[k] >= h->nmax || (fixed[k] < 0 && (b[k] < 0 || b[k] >= h->nmax)) || fixed[k] > 1)
+      return fail(h, DQE_EINVAL, "probs_diag: pair out of range");
+    dp.a[k] = (int8_t)a[k]; dp.b[k] = (int8_t)(fixed[k] < 0 ? b[k] : 0); dp.fixed[k] = (int8_t)fixed[k];
+  }
+  const int nblk = h->num_sms * 8;
+  if (int rc = ensure_scratch(h, (size_t)nblk * 2 * sizeof(double))) return rc;
+  dp.out = (double*)h->scratch;
+  CK(cudaSetDevice(h->device));
+  k_probs_diag<<<nblk, 256, 0, h->stream>>>(dp);
+  CK(cudaGetLastError());
+  std::vector<double> part((size_t)nblk * 2);
+  CK(cudaMemcpyAsync(part.data(), h->scratch, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  out2[0] = out2[1] = 0.0;
+  for (int blk = 0; blk < nblk; ++blk) { out2[0] += part[2 * blk]; out2[1] += part[2 * blk + 1]; }
+  return 0;
+}
+
 int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (!h || !key) return DQE_EINVAL;
   if (int rc = do_flush(h)) return rc;

@@ -48,6 +48,7 @@ ABI = {
     "dqe_peer_stats": (ctypes.c_int, [ctypes.c_void_p, _c_dbl_p, ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "dqe_probs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_probs_diag": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_int_p, _c_int_p, ctypes.c_int, _c_dbl_p]),
     "dqe_force_live_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "dqe_set_predicate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dqe_enqueue_cond_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
@@ -462,6 +463,16 @@ class Engine:
     def probs(self, axis):
         out = (ctypes.c_double * 2)()
         self._ck(self._lib.dqe_probs(self._h, int(axis), out))
+        return float(out[0]), float(out[1])
+
+    def probs_diag(self, pairs, target):
+        """Density matrix as a ket on (rows | columns): sum of this shard's diagonal elements by the value of local bit
+        ``target``; pairs = [(a, b, fixed)], fixed < 0: local bits a and b must agree, else bit a must equal fixed."""
+        _a, pa = _ibuf([p[0] for p in pairs] or [0])
+        _b, pb = _ibuf([p[1] for p in pairs] or [0])
+        _f, pf = _ibuf([p[2] for p in pairs] or [0])
+        out = (ctypes.c_double * 2)()
+        self._ck(self._lib.dqe_probs_diag(self._h, len(pairs), pa, pb, pf, int(target), out))
         return float(out[0]), float(out[1])
 
     # ------------------------------------------------------------------ instrumentation

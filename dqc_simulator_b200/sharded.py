@@ -22,6 +22,7 @@ import numpy as np
 _SWAP = np.eye(4, dtype=complex)[[0, 2, 1, 3]]
 _CNOT = np.eye(4, dtype=complex)[[0, 1, 3, 2]]
 _X = np.array([[0, 1], [1, 0]], dtype=complex)
+_PAULIS = [np.eye(2, dtype=complex), _X, np.array([[0, -1j], [1j, 0]], dtype=complex), np.diag([1.0 + 0j, -1.0])]
 _PAT_SWAP, _PAT_CNOT, _PAT_DIAG = (_SWAP != 0).tobytes(), (_CNOT != 0).tobytes(), (np.eye(4) != 0).tobytes()
 
 
@@ -47,6 +48,7 @@ class GpuShard:
         self.apply_2q = self.eng.apply_2q
         self.apply_ctrl_1q = self.eng.apply_ctrl_1q
         self.apply_diag = self.eng.apply_diag
+        self.apply_kq = self.eng.apply_kq
         self._peer_ptrs = None
 
     def buffer(self):
@@ -107,6 +109,11 @@ class GpuShard:
         return self.eng.probs(axis)
 
     norm2_by_bit = probs
+
+    def probs_diag(self, pairs, target):
+        """Sum of the diagonal elements of a density matrix held as a ket on (rows | columns) bits, by the value of
+        local bit ``target`` (kernel ``k_probs_diag``)."""
+        return self.eng.probs_diag(pairs, target)
 
     def project(self, axis, outcome, scale, p_local):
         """Keep the ``outcome`` half of ``axis`` and rescale: the engine's forced measurement renormalises by the
@@ -367,6 +374,15 @@ class ShardedKet:
         self._touch(a, b)
         self.shard.apply_2q(self.slot[a], self.slot[b], m)
 
+    def apply_kq(self, axes, m):
+        """Dense k-qubit matrix (k <= 4, first axis = most significant index): every axis it touches is made local."""
+        self._flush_cx()
+        axes = list(axes)
+        for a in axes:
+            self._localise(a, axes)
+        self._touch(*axes)
+        self.shard.apply_kq([self.slot[a] for a in axes], m)
+
     def apply_diag(self, axes, d):
         self._flush_cx()
         axes = list(axes)
@@ -484,3 +500,202 @@ class ShardedKet:
         phys = torch.view_as_complex(torch.cat(parts)).cpu().numpy()     # index = rank << m | local
         perm = [self.n - 1 - self.slot[a] for a in range(self.n - 1, -1, -1)]
         return phys.reshape((2,) * self.n).transpose(perm).reshape(-1)
+
+
+class ShardedDM:
+    """ONE density matrix sharded over GPUs by its high-order ROW bits (third row: the C4 variant
+    whose rho exceeds one GPU).  rho on n qubits is held as a ket on 2n bits -- logical axis a = column bit of
+    qubit a, n + a = its row bit, exactly the engine's own dm layout -- and that ket is a :class:`ShardedKet`: the
+    top log2(world) row bits are the rank id.  Everything a density-matrix backend needs is a ket operation on it:
+
+    * U rho U^dagger ............ U on the row bit, conj(U) on the column bit
+    * diagonal gates ............ table on the row bits, conjugate table on the column bits (rank-dependent
+                                  sub-tables where a row bit is global: no communication)
+    * one-qubit channels ........ their 4x4 superoperator as a two-"qubit" gate on (row bit, column bit)
+    * two-qubit depolarising .... its 16x16 superoperator as a dense 4-axis block (OP_KBLOCK)
+    * measurement ............... local sum of diagonal elements (``dqe_probs_diag``) -> all-reduce -> one Philox
+                                  draw -> projection of the row AND the column bit, renormalised by 1 / p
+    * predicated gates .......... the outcome is one bit for the whole matrix (one trajectory per sharded rho):
+                                  ``set_predicate`` turns the following ops on or off on the host
+
+    A gate that mixes a global row bit first exchanges the global axes with local ones (``ShardedKet._localise``:
+    one device-synchronised peer kernel); column bits start local and stay local unless picked as exchange victims.
+    A 17-qubit noisy rho (256 GiB) then runs on 8 x 32 GiB shards."""
+
+    formalism = 1
+
+    def __init__(self, n, shard, rank, world, group=None, seed=0, peer=False):
+        self.n = n
+        self.max_qubits = n
+        self.batch = 1
+        self.ket = ShardedKet(2 * n, shard, rank, world, group=group, seed=seed, peer=peer)
+        self.live = []
+        self._creg = 0
+        self._pred = -1
+        self._seed, self._draw = int(seed), 0
+
+    # ---- register ---------------------------------------------------------------------------------------------
+    def alloc_axis(self, axis=-1):
+        if axis < 0:
+            axis = min(a for a in range(self.n) if a not in self.live)
+        self.live.append(axis)
+        self.ket.alloc_axis(axis)
+        self.ket.alloc_axis(self.n + axis)
+        return axis
+
+    def set_predicate(self, bit):
+        self._pred = int(bit)
+
+    def _on(self):
+        return self._pred < 0 or (self._creg >> self._pred) & 1
+
+    # ---- gates ------------------------------------------------------------------------------------------------
+    def apply_1q(self, axis, m):
+        if not self._on():
+            return
+        m = np.asarray(m, dtype=complex).reshape(2, 2)
+        self.ket.apply_1q(self.n + axis, m)
+        self.ket.apply_1q(axis, m.conj())
+
+    def apply_2q(self, a, b, m):
+        if not self._on():
+            return
+        m = np.asarray(m, dtype=complex).reshape(4, 4)
+        self.ket.apply_2q(self.n + a, self.n + b, m)
+        self.ket.apply_2q(a, b, m.conj())
+
+    def apply_ctrl_1q(self, c, t, m):
+        if not self._on():
+            return
+        m = np.asarray(m, dtype=complex).reshape(2, 2)
+        self.ket.apply_ctrl_1q(self.n + c, self.n + t, m)
+        self.ket.apply_ctrl_1q(c, t, m.conj())
+
+    def apply_diag(self, axes, d):
+        if not self._on():
+            return
+        d = np.asarray(d, dtype=complex).reshape(-1)
+        self.ket.apply_diag([self.n + a for a in axes], d)
+        self.ket.apply_diag(list(axes), d.conj())
+
+    # ---- channels ---------------------------------------------------------------------------------------------
+    def _superop_1q(self, axis, kraus):
+        """sum_i K_i rho K_i^dagger on one qubit: S[(r, c), (r', c')] = sum_i K_i[r, r'] conj(K_i[c, c'])."""
+        S = sum(np.kron(K, K.conj()) for K in (np.asarray(k, dtype=complex).reshape(2, 2) for k in kraus))
+        self.ket.apply_2q(self.n + axis, axis, S)
+
+    def pauli_channel(self, axis, p):
+        if not self._on():
+            return
+        self._superop_1q(axis, [np.sqrt(w) * P for w, P in zip(p, _PAULIS) if w > 0])
+
+    def kraus_1q(self, axis, ks):
+        if self._on():
+            self._superop_1q(axis, ks)
+
+    def depolarize(self, axes, p):
+        """(1 - p) rho + p (I / 2^k (x) Tr_axes rho), k = 1, 2 (noise_models.py:343-366)."""
+        if not self._on() or not p:
+            return
+        axes = list(axes)
+        if len(axes) == 1:
+            return self.pauli_channel(axes[0], [1 - 0.75 * p, 0.25 * p, 0.25 * p, 0.25 * p])
+        a, b = axes
+        S = np.zeros((16, 16), dtype=complex)
+        for i, Pa in enumerate(_PAULIS):
+            for j, Pb in enumerate(_PAULIS):
+                w = (1 - 15 * p / 16) if i == 0 and j == 0 else p / 16
+                P = np.kron(Pa, Pb)
+                S += w * np.kron(P, P.conj())          # index order (ra, rb, ca, cb)
+        self.ket.apply_kq([self.n + a, self.n + b, a, b], S)
+
+    # ---- measurement ------------------------------------------------------------------------------------------
+    def _diag_pairs(self, skip=None):
+        """(local bit, partner local bit, fixed) constraints that make a shard element a diagonal element of rho."""
+        k, pairs = self.ket, []
+        for q in self.live:
+            r, c = k.slot[self.n + q], k.slot[q]
+            rg, cg = r >= k.m, c >= k.m
+            if rg and cg:
+                if ((k.rank >> (r - k.m)) ^ (k.rank >> (c - k.m))) & 1:
+                    return None                        # this shard holds no diagonal element at all
+            elif rg:
+                pairs.append((c, 0, (k.rank >> (r - k.m)) & 1))
+            elif cg:
+                pairs.append((r, 0, (k.rank >> (c - k.m)) & 1))
+            else:
+                pairs.append((r, c, -1))
+        return pairs
+
+    def measure(self, axis, creg_bit=None, forced=-1, discard=False, flip_prob=0.0):
+        import torch
+        import torch.distributed as dist
+
+        from .philox_host import shot_uniforms
+
+        if discard:
+            raise NotImplementedError("sharded density matrices keep every axis")
+        k = self.ket
+        k._flush_cx()
+        pairs = self._diag_pairs()
+        r, c = k.slot[self.n + axis], k.slot[axis]
+        if pairs is None:
+            p = [0.0, 0.0]
+        else:
+            target = c if c < k.m else (r if r < k.m else -1)
+            q0, q1 = k.shard.probs_diag(pairs, target)
+            s = complex(k._pending)                   # rho carries the pending scalar linearly
+            q0, q1 = (q0 * s).real, (q1 * s).real
+            if target < 0:                             # the axis' bits are both rank bits: outcome fixed by the rank
+                v = (k.rank >> (c - k.m)) & 1
+                p = [q0 + q1, 0.0] if v == 0 else [0.0, q0 + q1]
+            else:
+                p = [q0, q1]
+        buf = k.shard.buffer()
+        t = torch.tensor(p, dtype=torch.float64, device=buf.device if buf.is_cuda else "cpu")
+        dist.all_reduce(t, group=k.group)
+        p0, p1 = (float(x) for x in t.cpu())
+        e = float(flip_prob)
+        q0, q1 = (1 - e) * p0 + e * p1, (1 - e) * p1 + e * p0       # MeasurementNoiseModel folded in
+        u, _ = shot_uniforms(self._seed, 0, self._draw)
+        self._draw += 1
+        m = int(forced) if forced is not None and forced >= 0 else int(u * (q0 + q1) < q1)
+        if e:
+            # rho' = [(1 - e) P_m rho P_m + e P_m X rho X P_m] / q_m, kept in the |m><m| block
+            raise NotImplementedError("sharded density matrices: measurement flips are applied by the caller as a Pauli channel")
+        pm = p1 if m else p0
+        proj = np.array([1.0, 0.0]) if m == 0 else np.array([0.0, 1.0])
+        k.apply_diag([self.n + axis], proj)
+        k.apply_diag([axis], proj * (1.0 / pm if pm > 0 else 0.0))
+        if creg_bit is not None and creg_bit >= 0:
+            self._creg = (self._creg & ~(1 << creg_bit)) | (m << creg_bit)
+        return m
+
+    def trace(self):
+        import torch
+        import torch.distributed as dist
+
+        k = self.ket
+        k._flush_cx()
+        pairs = self._diag_pairs()
+        q = (0.0, 0.0) if pairs is None else k.shard.probs_diag(pairs, -1)
+        buf = k.shard.buffer()
+        t = torch.tensor([((q[0] + q[1]) * complex(k._pending)).real], dtype=torch.float64,
+                         device=buf.device if buf.is_cuda else "cpu")
+        dist.all_reduce(t, group=k.group)
+        return float(t[0])
+
+    # ---- read-out ---------------------------------------------------------------------------------------------
+    def flush(self):
+        self.ket.flush()
+
+    sync = flush
+
+    @property
+    def exchanges(self):
+        return self.ket.exchanges
+
+    def gather_rho(self):
+        """Full 2^n x 2^n matrix on every rank (tests only)."""
+        v = self.ket.gather_logical()
+        return v.reshape(2 ** self.n, 2 ** self.n)

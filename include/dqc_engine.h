@@ -248,6 +248,11 @@ int dqe_peer_stats(dqe_t* h, double* ms, int64_t* count, int64_t* bytes_sent, in
 /* Local part of a measurement on a sharded state vector (single-shot ket): out2 = (sum |amp|^2 over axis bit 0,
  * over axis bit 1) of this shard.  The caller all-reduces, draws, and projects with dqe_measure(forced = m). */
 int dqe_probs(dqe_t* h, int axis, double* out2);
+/* The same for a density matrix held as a ket on 2n bits (rows | columns) and sharded by row bits
+ * (sharded.ShardedDM): out2 = local part of (Tr[(1 - Z_t)/2 ... ]) -- the sum of the DIAGONAL elements of rho on this
+ * shard, split by the value of local bit `target` (-1: everything in out2[0]).  An element is diagonal when, for
+ * every pair k, local bit a[k] equals local bit b[k] (fixed[k] < 0) or the rank-bit value fixed[k]. */
+int dqe_probs_diag(dqe_t* h, int npairs, const int* a, const int* b, const int* fixed, int target, double* out2);
 
 /* ---- tuning + instrumentation --------------------------------------------------------------- */
 /* key: "tile_bits" (log2 amplitudes staged per CTA; default 11 = 32 KiB with 128 threads, or 10 = 16 KiB

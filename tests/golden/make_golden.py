@@ -17,7 +17,7 @@ Fixtures
 * ``c2_{ghz,grover,qft}5_3qpu_cat``  config 2, exactly ``examples/setup_sim.py:16-43`` on the
   hardware of ``examples/setup_hardware.py:11-55`` (10 positions, 2 comm qubits, 3 QPUs)
 * ``c3_qft{N}_4qpu_cat``          config 3 shape (N = 8, 12 for oracle-sized parity, 26 full)
-* ``c4_qft{N}_mono``              config 4 shape: one QPU, all gates local (N = 6, 16)
+* ``c4_qft{N}_mono``              config 4 shape: one QPU, all gates local (N = 6, 16; 17 = 256 GiB, one rho sharded over 8 GPUs)
 * ``c5_{ghz,qft}{N}_mono``        config 5 shape (N = 12 parity size, 30 .. 34 full: weak scaling over 1, 2, 4, 8, 16 GPUs)
 * ``mqt/{name}_{mono,3qpu_cat,3qpu_tp_safe}``  the 22 MQT-bench circuits of ``tests/MQT_benchmarking_circuits`` (the
   reference's front-end test inputs), monolithic and partitioned over 3 QPUs
@@ -145,7 +145,7 @@ def main():
         ops, meta = compile_fcfs(_qasm_path(circuits.ghz_qasm(n)), 4, 2 + (n + 3) // 4, 2)
         save(f"c3_ghz{n}_4qpu_cat", ops, meta)
     # ---- config 4 / 5 shapes (single register, all local) ---------------------------------
-    for n in (6, 16):
+    for n in (6, 16, 17):
         ops, meta = compile_mono(_qasm_path(circuits.qft_qasm(n)), n)
         save(f"c4_qft{n}_mono", ops, meta, gz=n > 12)
     for kind, gen in (("ghz", circuits.ghz_qasm), ("qft", circuits.qft_qasm)):

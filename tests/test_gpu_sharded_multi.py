@@ -35,3 +35,23 @@ def test_sharded_ket_matches_oracle_on_real_devices(world, peer, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
     assert res["max_abs_err"] < 1e-10 and res["exchanges"] > 0 and res["relabelled_swaps"] > 0 and not res["peer_error"]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_density_matrix_matches_oracle_on_real_devices(world, tmp_path):
+    """ONE rho (n = 7: 16384 elements) sharded by its high-order row bits over real devices (ShardedDM): gates, 1- and
+    2-qubit depolarising (OP_KBLOCK superoperator), Pauli / Kraus channels, forced measurements with a predicated
+    correction -- element by element against the oracle's density-matrix run."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "res.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_sharded.py"),
+           "--qubits", "7", "--circuit", "random_dm", "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.loads(out.read_text())
+    assert res["max_abs_err"] < 1e-10 and abs(res["trace"] - 1) < 1e-10 and res["exchanges"] > 0

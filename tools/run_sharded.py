@@ -102,6 +102,95 @@ def run_random(a, rank, world, local):
     return res
 
 
+def noisy_dm_program(be, n, seed):
+    """Gates, channels and forced measurements of a noisy density-matrix run (same generator as the gloo test)."""
+    rng = np.random.default_rng(seed)
+    H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    for a in range(n):
+        be.alloc_axis(a)
+        be.apply_1q(a, H)
+    for step in range(40):
+        kind = rng.choice(["1q", "cnot", "2q", "ctrl", "diag2", "dep1", "dep2", "pauli", "damp"])
+        ax = [int(x) for x in rng.choice(n, size=2, replace=False)]
+        if kind == "1q":
+            be.apply_1q(ax[0], rand_u(rng, 2))
+        elif kind == "cnot":
+            be.apply_2q(ax[0], ax[1], np.eye(4)[[0, 1, 3, 2]])
+        elif kind == "2q":
+            be.apply_2q(ax[0], ax[1], rand_u(rng, 4))
+        elif kind == "ctrl":
+            be.apply_ctrl_1q(ax[0], ax[1], rand_u(rng, 2))
+        elif kind == "diag2":
+            be.apply_diag(ax, np.exp(1j * rng.normal(size=4)))
+        elif kind == "dep1":
+            be.depolarize([ax[0]], float(rng.uniform(0.01, 0.3)))
+        elif kind == "dep2":
+            be.depolarize(ax, float(rng.uniform(0.01, 0.3)))
+        elif kind == "pauli":
+            be.pauli_channel(ax[0], [float(x) for x in rng.dirichlet([8, 1, 1, 1])])
+        else:
+            g = float(rng.uniform(0.05, 0.4))
+            be.kraus_1q(ax[0], [np.array([[1, 0], [0, np.sqrt(1 - g)]]), np.array([[0, np.sqrt(g)], [0, 0]])])
+        if step in (15, 30):
+            be.measure(ax[0], 2, int(step == 15), False, 0.0)
+            be.set_predicate(2)
+            be.apply_1q(ax[1], np.array([[0, 1], [1, 0]]))
+            be.set_predicate(-1)
+
+
+def run_random_dm(a, rank, world, local):
+    """ONE density matrix of a.n qubits sharded by row bits (ShardedDM) against the oracle, element by element."""
+    from dqc_simulator_b200.sharded import ShardedDM
+    from oracle.numpy_engine import OracleEngine
+
+    g = int(np.log2(world))
+    shard = GpuShard(2 * a.n - g, local, rank == 0, seed=5)
+    sd = ShardedDM(a.n, shard, rank, world, seed=5, peer=bool(a.peer))
+    noisy_dm_program(sd, a.n, 21)
+    got, tr = sd.gather_rho(), sd.trace()
+    o = OracleEngine("dm", a.n, 1, seed=5)
+    noisy_dm_program(o, a.n, 21)
+    err = float(np.abs(got - o.full_state(0)[0]).max())
+    st = shard.eng.peer_stats() if a.peer else dict(error=0)
+    res = dict(circuit="random_dm", n=a.n, n_gpus=world, max_abs_err=err, trace=tr, exchanges=sd.exchanges,
+               relabelled_swaps=1, peer=bool(a.peer), peer_error=st["error"])
+    assert err < 1e-10 and abs(tr - 1) < 1e-10 and st["error"] == 0, res
+    shard.close()
+    return res
+
+
+def run_noisy_qft_dm(a, rank, world, local):
+    """BASELINE config 4 beyond one GPU: noisy QFT-n as ONE density matrix (4^n complex128) sharded by row bits.
+    Checks Tr rho = 1 and the purity bound; reports seconds and exchanges."""
+    from dqc_simulator_b200.sharded import ShardedDM
+
+    g = int(np.log2(world))
+    ops, _ = opstream.load(os.path.join(GOLDEN, f"c4_qft{a.n}_mono.json.gz" if a.n > 12 else f"c4_qft{a.n}_mono.json"))
+    noise = dict(p_depolar_error_cnot=1e-3, single_qubit_gate_error_prob=2e-5, proc_qubit_depolar_rate=0.055)
+    dqc = hardware.DQCSpec.uniform(1, num_positions=a.n, num_comm_qubits=0, **noise)
+    shard = GpuShard(2 * a.n - g, local, rank == 0)
+    sd = ShardedDM(a.n, shard, rank, world, peer=bool(a.peer))
+    shard.eng.time_passes(True)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    executor.DQCExecutor(ops, dqc, sd).run()
+    sd.sync()
+    dist.barrier(); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tr = sd.trace()
+    pass_ms, n_pass, amps = shard.eng.pass_time()
+    xs = sd.ket.exchange_stats()
+    t = torch.tensor([dt, xs["seconds"]], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = dict(circuit="noisy_qft_dm", n=a.n, n_gpus=world, seconds=float(t[0]), trace=tr, exchanges=sd.exchanges,
+               exchange_seconds=float(t[1]), exchange_bytes_per_rank=sd.ket.exchanged_bytes, pass_ms=pass_ms,
+               passes_per_rank=n_pass, pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
+               rho_bytes=16 * 4 ** a.n, shard_bytes=16 * 4 ** a.n // world, peer_error=xs["error"], relabelled_swaps=sd.ket.relabelled_swaps)
+    assert abs(tr - 1) < 1e-9 and not xs["error"], res
+    shard.close()
+    return res
+
+
 def run_fixture(a, rank, world, local):
     g = int(np.log2(world))
     suffix = ".json" if a.n <= 12 else ".json.gz"
@@ -169,7 +258,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    best = run_random(a, rank, world, local) if a.circuit == "random" else run_fixture(a, rank, world, local)
+    runner = {"random": run_random, "random_dm": run_random_dm, "noisy_qft_dm": run_noisy_qft_dm}.get(a.circuit, run_fixture)
+    best = runner(a, rank, world, local)
     if rank == 0:
         print(json.dumps(best), flush=True)
         os.makedirs("gpurun_out", exist_ok=True)
