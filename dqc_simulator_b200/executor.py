@@ -135,6 +135,7 @@ class QPU:
         self.comm_qubits_free = list(self.comm_qubit_positions)  # quantum_processors.py:122
         self.ebit_ready = False                                   # never set True upstream
         self.clock = 0.0
+        self.alias = set()     # comm positions that are aliases of a remote data qubit's axis (ancilla_free_cat)
         self.axis = {}         # pos -> engine axis (materialised qubits)
         self.pending = {}      # pos -> time the fresh |0> became valid (not yet materialised)
         self.last_access = {}  # pos -> time of last access (materialised qubits)
@@ -156,6 +157,12 @@ class QPU:
 
     def _drop(self, pos):
         """Throw away whatever sits at ``pos``."""
+        if pos in self.alias:                 # an alias of another QPU's data qubit: nothing of its own to free
+            self.alias.discard(pos)
+            self.axis.pop(pos, None)
+            self.last_access.pop(pos, None)
+            self.pending.pop(pos, None)
+            return
         if pos in self.axis:
             ax = self.axis.pop(pos)
             self.ex.backend.free_axis(ax)
@@ -315,6 +322,16 @@ class QPU:
                 self.execute_program(sub)
                 t_issue = self.clock
                 continue
+            if self.alias and any(p_ in self.alias for p_ in positions):
+                # an aliased comm qubit may only CONTROL (first operand of a controlled gate) or carry a diagonal
+                m_ = np.asarray(mat)
+                d_ = m_.shape[0] // 2
+                ctrl_ok = (len(positions) == 2 and positions[0] in self.alias and positions[1] not in self.alias and
+                           not m_[:d_, d_:].any() and not m_[d_:, :d_].any() and np.array_equal(m_[:d_, :d_], np.eye(d_)))
+                if not ctrl_ok and (m_ - np.diag(np.diag(m_))).any():
+                    raise NotImplementedError(f"{self.name}: ancilla_free_cat: a cat-entangled comm qubit is mixed by "
+                                              f"{tok.name}; only controls and diagonal gates commute with the copy")
+                ex.aliased_gates += 1
             start = start_of(positions, False)
             pred = -1 if run is None else run.index
             if pred >= 0:
@@ -386,10 +403,20 @@ class DQCExecutor:
 
     def __init__(self, qpu_op_dict, dqc, backend, forced_outcomes=None, host_branching=False,
                  swap_as_three_cnots=True, creg_bits=64, axis_pool=None, comm_axes_low=0,
-                 parallel_programs=True, per_shot_time=True, predicated_time_weight=0.5):
+                 parallel_programs=True, per_shot_time=True, predicated_time_weight=0.5, ancilla_free_cat=False):
         self.ops = qpu_op_dict
         self.dqc = dqc if isinstance(dqc, DQCSpec) else DQCSpec(list(dqc))
         self.backend = backend
+        # ancilla_free_cat ("ancilla-free lowering"): on IDEAL hardware (no gate / measurement /
+        # memory noise, pure Phi+ ebits) the cat-entangled comm qubit c' is an exact Z-basis copy of the data qubit
+        # d, the gates it controls act as if d controlled them, and the disentangler (H, measure, Z) undoes the
+        # copy -- so the whole primitive is "the remote gates, controlled by d": no ebit, no comm axis, no
+        # measurement, no pass cut.  c' is then an ALIAS of d's engine axis.  The two cat measurement outcomes
+        # are reported as 0 (they are fair coins that never reach the data state).  Refused on noisy hardware.
+        self.ancilla_free_cat = bool(ancilla_free_cat)
+        if self.ancilla_free_cat:
+            self._require_ideal()
+        self.aliased_gates = 0
         self.host_branching = host_branching
         self.swap_as_three_cnots = swap_as_three_cnots
         # True: instructions of one QuantumProgram on free positions overlap in simulated time (NetSquid's
@@ -432,6 +459,16 @@ class DQCExecutor:
         self.end_time = 0.0
         self.finished = False
         self._events = 0
+
+    def _require_ideal(self):
+        st = np.asarray(self.dqc.state4distribution, dtype=complex)
+        ok = st.size == 4 and np.allclose(st.reshape(-1), [2 ** -0.5, 0, 0, 2 ** -0.5]) and self.dqc.heralded is None
+        for sp in self.dqc.qpus:
+            ok = ok and not (sp.p_depolar_error_cnot or sp.single_qubit_gate_error_prob or sp.meas_error_prob)
+            ok = ok and not any(any(sp.mem_rates(p_)) for p_ in (0, sp.num_positions - 1))
+        if not ok:
+            raise ValueError("ancilla_free_cat needs ideal hardware: pure Phi+ ebits, no gate, measurement or memory "
+                             "noise (on noisy hardware the comm qubits carry noise of their own)")
 
     # ---- resources -------------------------------------------------------------
     def _claim_axis(self, is_comm):
@@ -664,6 +701,8 @@ class DQCExecutor:
 
     def _cat(self, q, role, program, other, data, comm):
         name = q.name
+        if self.ancilla_free_cat:
+            return (yield from self._cat_ancilla_free(q, role, program, other, data, comm))
         if role == "entangle":                                  # dqc_control.py:266-314
             program = self._flush(q, program)
             self._no_comm_free(q)
@@ -706,6 +745,38 @@ class DQCExecutor:
             elif mb != 0:
                 raise ValueError("Measurement result must be an integer with value 0 or 1. "
                                  f"The current value, {mb}, does not meet this criteria.")
+            return comm, program
+        raise ValueError("final element of gate_tuple is not valid role")
+
+    def _cat_ancilla_free(self, q, role, program, other, data, comm):
+        """The four cat-comm roles on ideal hardware, without ebit, comm axis or measurement (see __init__)."""
+        name = q.name
+        if role == "entangle":
+            program = self._flush(q, program)
+            self._no_comm_free(q)
+            self._send(name, other, ("alias", q._materialise(data)))
+            return comm, QuantumProgram()
+        if role == "correct":
+            program = self._flush(q, program)
+            self._no_comm_free(q)
+            c = q.comm_qubits_free[0]
+            del q.comm_qubits_free[0]
+            tag, ax = yield from self._recv(other, name)
+            assert tag == "alias"
+            q._drop(c)
+            q.axis[c] = ax
+            q.alias.add(c)
+            q.last_access[c] = q.clock
+            return c, program
+        if role == "disentangle_start":
+            program = self._flush(q, program)          # the gates the copy controls run before it is dropped
+            q._drop(comm)
+            self._send(name, other, 0)
+            q.comm_qubits_free = sorted(q.comm_qubits_free + [comm])
+            return comm, QuantumProgram()
+        if role == "disentangle_end":
+            mb = yield from self._recv(other, name)
+            assert mb == 0
             return comm, program
         raise ValueError("final element of gate_tuple is not valid role")
 

@@ -227,3 +227,24 @@ def test_heralded_link_engine_equals_oracle_shot_by_shot():
         assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
         assert np.abs(res[0][2] - res[1][2]).max() < TOL
         assert len(set(res[0][0].tolist())) > 2 and 0 < res[0][1].sum() < 96
+
+
+def test_ancilla_free_cat_lowering_on_the_engine():
+    """C3 shape (QFT-12 over 4 QPUs, cat-comm, ideal hardware): the ancilla-free lowering on the CUDA engine (12-qubit
+    register, no measurement, a handful of passes) against the explicit protocol on the oracle (14 qubits, 252
+    sampled measurements)."""
+    import os
+
+    from dqc_simulator_b200 import executor, opstream
+
+    ops, meta = opstream.load(os.path.join(rc.GOLDEN, "c3_qft12_4qpu_cat.json"))
+    dqc = hardware.DQCSpec.uniform(4, num_positions=meta["num_positions"], num_comm_qubits=2)
+    qubits = [tuple(meta["qubit_map"][str(i)]) for i in range(12)]
+    o = cpu("ket", 14, 1)
+    exo = executor.DQCExecutor(ops, dqc, o).run()
+    g = gpu("ket", 12, 1)
+    exg = executor.DQCExecutor(ops, dqc, g, ancilla_free_cat=True).run()
+    assert exg.measurements == 0 and g.stats()["passes"] < 12
+    for lo in (0, 4, 7):
+        sub = qubits[lo:lo + 5]
+        _cmp(g.reduced_dm(exg.axes_of(sub), 0), o.reduced_dm(exo.axes_of(sub), 0))

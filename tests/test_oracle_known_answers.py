@@ -232,3 +232,32 @@ def test_heralded_link_distributes_phi_plus_with_per_shot_attempts():
     ex3, be3, _ = _heralded(make, batch=8, visibility=0.9)
     axes3 = ex3.axes_of([(0, "node_0"), (0, "node_1")])
     assert max(abs(be3.fidelity_ket(axes3, B00, s) - 0.95) for s in range(8)) < 1e-12
+
+
+@pytest.mark.parametrize("name,nq", [("c3_qft8_4qpu_cat.json", 8), ("c3_qft12_4qpu_cat.json", 12), ("c3_ghz10_4qpu_cat.json", 10)])
+def test_ancilla_free_cat_lowering_equals_the_explicit_protocol(name, nq):
+    """SURVEY section 7 / VERDICT r1 item 5: on ideal hardware the cat-comm primitive (ebit, CNOT, measure, X fix-up,
+    remote gates controlled by the copy, H, measure, Z fix-up: dqc_control.py:266-403) equals "the remote gates,
+    controlled by the data qubit".  ``ancilla_free_cat=True`` runs it that way -- no ebit, no comm axis, no
+    measurement -- and ends in the same data state as the explicit protocol for any of its outcome histories;
+    noisy hardware refuses the option."""
+    import os
+
+    from dqc_simulator_b200 import executor, hardware, opstream
+
+    ops, meta = opstream.load(os.path.join(rc.GOLDEN, name))
+    dqc = hardware.DQCSpec.uniform(4, num_positions=meta["num_positions"], num_comm_qubits=2)
+    qubits = [tuple(meta["qubit_map"][str(i)]) for i in range(nq)]
+    a = make("ket", nq + 2, 2)
+    exa = executor.DQCExecutor(ops, dqc, a).run()
+    b = make("ket", nq, 1)
+    exb = executor.DQCExecutor(ops, dqc, b, ancilla_free_cat=True).run()
+    assert exa.measurements > 0 and exb.measurements == 0 and exb.ebits == 0 and exb.peak_axes == nq
+    for lo in range(0, nq, 4):
+        sub = qubits[lo:lo + 5]
+        for shot in range(2):     # two different outcome histories of the explicit protocol
+            ra = a.reduced_dm(exa.axes_of(sub), shot)
+            assert np.abs(ra - b.reduced_dm(exb.axes_of(sub), 0)).max() < 1e-12
+    noisy = hardware.DQCSpec.uniform(4, num_positions=meta["num_positions"], num_comm_qubits=2, p_depolar_error_cnot=1e-3)
+    with pytest.raises(ValueError):
+        executor.DQCExecutor(ops, noisy, make("ket", nq, 1), ancilla_free_cat=True)

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--case", default="", help="substring filter on the fixture name")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--fused-only", action="store_true")
+    ap.add_argument("--ancilla-free", action="store_true",
+                    help="ideal hardware: cat-comm primitives as direct remote-controlled gates (executor ancilla_free_cat)")
     a = ap.parse_args()
     out = []
     for name, nq, nqpu, npos in CASES:
@@ -29,7 +31,8 @@ def main():
         ops, _ = opstream.load(os.path.join(GOLDEN, name))
         dqc = hardware.DQCSpec.uniform(nqpu, num_positions=npos, num_comm_qubits=2 if nqpu > 1 else 0)
         for fuse in ((1,) if a.fused_only else (1, 0)):
-            e = Engine("ket", nq, 1, seed=1)
+            af = a.ancilla_free and nqpu > 1
+            e = Engine("ket", nq - 2 if af else nq, 1, seed=1)
             e.set_option("fuse", fuse)
             e.set_option("merge", fuse)
             for kv in a.opt:
@@ -42,14 +45,14 @@ def main():
                 e.sync()
                 e.time_passes(True)
                 t0 = time.perf_counter()
-                ex = executor.DQCExecutor(ops, dqc, e).run()
+                ex = executor.DQCExecutor(ops, dqc, e, ancilla_free_cat=af).run()
                 e.sync()
                 wall = time.perf_counter() - t0
                 ms, n, amps = e.pass_time()
                 e.time_passes(False)
                 st = e.stats()
                 if rep and (best is None or wall < best["wall_s"]):
-                    best = dict(case=name, fused=bool(fuse), opts=a.opt, wall_s=wall, pass_ms=ms, passes=n,
+                    best = dict(case=name, fused=bool(fuse), opts=a.opt, ancilla_free=bool(af), wall_s=wall, pass_ms=ms, passes=n,
                                 api_ops=st["api_ops"], micro_ops=st["micro_ops"],
                                 GBps=32.0 * amps / (ms * 1e-3) / 1e9,
                                 gate_updates_per_s=st["api_ops"] / wall,
