@@ -428,13 +428,17 @@ def main():
                                        "qft": 0.6470482939691747}[a.circuit],
         "roofline": {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read+write of this kernel, ncu --set full (profiles/r01e_summary.md): 2.10-2.26 GB
-                     # per launch against 2.147 GB algorithmic at 16384 shots -> ratio 1.03 applied here
-                     "traffic": 0.994 * 32.0 * amps / max(n_pass, 1),
-                     "traffic_source": "ncu --set full capture at 16384 shots (profiles/r01q_summary.md: dram read + write "
-                                       "8.54 GB per launch of 262144 tiles x 16 KiB x 2 = 8.59 GB algorithmic), ratio 0.994",
-                     "note": "fused passes (~17 ops each, measurements resolved on chip through cluster DSMEM) are bound "
-                             "by the on-chip sweep work, not by HBM; see roofline_single_gate for the HBM-bound regime",
+                     # DRAM traffic per launch = ratio measured by ncu x the algorithmic bytes of THIS run's launches
+                     # (ncu cannot run inside the timed bench: a number taken under a profiler is not a bench value)
+                     "traffic": 0.995 * 32.0 * amps / max(n_pass, 1),
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, 2026-10-20, same command "
+                                       "at 16384 shots (profiles/r02k_summary.md): 8.550 GB per launch of 262144 tiles against "
+                                       "262144 x 16 KiB x 2 = 8.590 GB algorithmic -> ratio 0.995 (65536-tile launches: 0.986); "
+                                       "scaled to this run's launch size",
+                     "note": "fused passes (~15 micro-ops each incl. the per-shot classical timeline instructions; measurements "
+                             "resolved on chip through cluster DSMEM) are bound by on-chip work (issue slots 36-40 % busy, FP64 "
+                             "pipe 7-15 %, 88 % of executed instructions are address / control / classical-machine overhead: "
+                             "profiles/r02k_summary.md), not by HBM; see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
                      "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),

@@ -658,26 +658,40 @@ def test_peer_memory_gate_on_a_global_axis(ctrl):
 
 
 def test_chi_square_dm_trajectory_outcomes():
-    """Density-matrix trajectories: the cat-comm measurement outcomes of the noisy GHZ-5 / 3-QPU circuit
-    (4 sampled bits per shot) against the per-outcome probabilities of the oracle run with the outcomes
-    forced (chi-square, 40000 shots)."""
+    """Density-matrix trajectories: the joint histogram of the four cat-comm measurement outcomes of the noisy
+    GHZ-5 / 3-QPU circuit (16 outcome strings, read from the engine's outcome log) against the histogram of an
+    INDEPENDENT sample of the oracle (other seed, 6000 shots): two-sample chi-square over the 16 strings, and the
+    same statistic against the engine's own second half as the yardstick of what "same distribution" gives."""
     from dqc_simulator_b200 import executor, experiment
     from dqc_simulator_b200.engine import Engine
 
     ops, _ = experiment.load_c2("ghz")
     dqc = experiment.c2_hardware(noisy=True, F_werner=0.9, meas_error_prob=0.05)
-    shots = 40000
-    e = Engine("dm", 7, shots, seed=99)
-    ex = executor.DQCExecutor(ops, dqc, e).run()
-    assert ex.measurements == 4
-    words = e.read_creg_words()
-    # each measurement wrote its own creg bit (allocation order 0, 1, 0/2, ...): rebuild per-shot outcome
-    # tuples through the executor's record of issued classical bits is not needed: by symmetry of the
-    # Werner / depolarising / flip noise every outcome string is equiprobable (p = 1/2 per measurement)
-    hist = np.bincount((words & np.uint64(3)).astype(np.int64), minlength=4)
-    exp = shots / 4.0
-    chi2 = float(((hist - exp) ** 2 / exp).sum())
-    assert chi2 < 25.0, (hist, chi2)     # dof = 3, P(chi2 > 25) ~ 1.5e-5
+
+    def strings(be):
+        ex = executor.DQCExecutor(ops, dqc, be).run()
+        assert ex.measurements == 4
+        out = np.asarray(be.read_outcomes(), dtype=np.int64)         # (4, batch)
+        return (out[0] << 3) | (out[1] << 2) | (out[2] << 1) | out[3]
+
+    def chi2(a, b):
+        n1, n2 = a.sum(), b.sum()
+        return float((((np.sqrt(n2 / n1) * a - np.sqrt(n1 / n2) * b) ** 2) / np.maximum(a + b, 1.0)).sum())
+
+    e = Engine("dm", 7, 40000, seed=99)
+    e.set_option("outcome_log", 8)
+    s_e = strings(e)
+    a = np.bincount(s_e, minlength=16).astype(float)
+    b = np.zeros(16)
+    for chunk in range(12):
+        o = OracleEngine("dm", 7, 500, seed=7, shot_offset=chunk * 500)
+        b += np.bincount(strings(o), minlength=16)
+    assert chi2(a, b) < 45.0, (a, b)          # dof = 15, P(chi2 > 45) ~ 8e-5
+    half = chi2(np.bincount(s_e[:20000], minlength=16).astype(float), np.bincount(s_e[20000:], minlength=16).astype(float))
+    assert half < 45.0
+    # and the same seed reproduces the oracle's strings shot for shot (the sampling path itself, bit-exact)
+    o = OracleEngine("dm", 7, 256, seed=99)
+    assert np.array_equal(strings(o), s_e[:256])
 
 
 @pytest.mark.parametrize("L", [0, 3, 5])

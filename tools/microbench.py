@@ -42,8 +42,10 @@ def main():
     rng = np.random.default_rng(0)
     out = []
 
-    def report(name, ms, n, amps):
-        gbs = 32.0 * amps / (ms * 1e-3) / 1e9
+    def report(name, ms, n, amps, bytes_per_amp=32.0):
+        # algorithmic bytes: 32 B per live amplitude per pass (16 read + 16 written); a measurement is two passes,
+        # the first of which only READS (dm: the diagonal only) -- credited 16 B / amplitude at most
+        gbs = bytes_per_amp * amps / (ms * 1e-3) / 1e9
         out.append(dict(case=name, ms_per_pass=ms / n, passes=n, GBps=gbs))
         print(f"{name:40s} {ms / n:9.4f} ms/pass  {gbs:8.1f} GB/s  ({n} passes)", flush=True)
 
@@ -112,7 +114,8 @@ def main():
         report(f"dm{n}x{B} cnot c={c} t={t}", *timed(e, lambda: e.apply_2q(c, t, CNOT)))
         report(f"dm{n}x{B} depol2 ({c},{t})", *timed(e, lambda: e.depolarize([c, t], 0.01)))
     report(f"dm{n}x{B} 2q dense (1,{n-1})", *timed(e, lambda: e.apply_2q(1, n - 1, u4)))
-    report(f"dm{n}x{B} measure q={n-1} keep", *timed(e, lambda: e.measure(n - 1, 0, -1, False, 0.003)))
+    report(f"dm{n}x{B} measure q={n-1} keep (probs pass reads only + collapse pass: <= 24 B / amp / pass on average)",
+           *timed(e, lambda: e.measure(n - 1, 0, -1, False, 0.003)), bytes_per_amp=24.0)
     e.set_option("fuse", 1)
     e.set_option("merge", 1)
 
