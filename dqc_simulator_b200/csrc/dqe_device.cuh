@@ -1029,6 +1029,61 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
 }
 
 
+// Fused inject -> interact -> measure-and-discard (host: fuse_cat_measure in dqe_engine.cu).  The op carries the bits
+// of a data axis A and of a FRESH axis y (b[0..3] = tile positions of row A, row y, col A, col y; b[4], b[5] = the
+// axes).  A thread owns the 16 elements (rA ry cA cy) of a group; on entry only the four with ry = cy = 0 are
+// non-zero: in[j], j = rA * 2 + cA.  Constants: t_0[4], t_1[4], T_0[16][4], T_1[16][4].
+//   probability of outcome m (flip noise already folded in) = sum over groups that are diagonal in every other
+//   axis of Re(sum_j t_m[j] in[j]);   new elements = scale * sum_j T_m[e][j] in[j].
+__device__ __forceinline__ void catm_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                              const double2* cs, uint64_t base, double& a0, double& a1) {
+  int s4[4];
+  sort4(op.b, s4);
+  const uint32_t mrA = 1u << op.b[0], mcA = 1u << op.b[2];
+  const int n = pp.nmax, axA = op.b[4], axY = op.b[5];
+  // axes with both bits outside the tile: one test for the whole tile
+  for (int a = 0; a < n; ++a) {
+    if (a == axA || a == axY || pp.ax_col[a] >= 0 || pp.ax_row[a] >= 0) continue;
+    if (((base >> a) ^ (base >> (a + n))) & 1ull) return;
+  }
+  const double2 t00 = cs[0], t01 = cs[1], t02 = cs[2], t03 = cs[3], t10 = cs[4], t11 = cs[5], t12 = cs[6], t13 = cs[7];
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    bool ok = true;
+    for (int a = 0; a < n; ++a) {
+      const int cl = pp.ax_col[a], rl = pp.ax_row[a];
+      if (a == axA || a == axY || (cl < 0 && rl < 0)) continue;
+      const uint32_t cb = cl >= 0 ? (i0 >> cl) & 1u : (uint32_t)((base >> a) & 1ull);
+      const uint32_t rb = rl >= 0 ? (i0 >> rl) & 1u : (uint32_t)((base >> (a + n)) & 1ull);
+      ok = ok && cb == rb;
+    }
+    if (!ok) continue;
+    const double2 v0 = tile[i0], v1 = tile[i0 | mcA], v2 = tile[i0 | mrA], v3 = tile[i0 | mrA | mcA];
+    a0 += fma(t00.x, v0.x, -t00.y * v0.y) + fma(t01.x, v1.x, -t01.y * v1.y) + fma(t02.x, v2.x, -t02.y * v2.y) +
+          fma(t03.x, v3.x, -t03.y * v3.y);
+    a1 += fma(t10.x, v0.x, -t10.y * v0.y) + fma(t11.x, v1.x, -t11.y * v1.y) + fma(t12.x, v2.x, -t12.y * v2.y) +
+          fma(t13.x, v3.x, -t13.y * v3.y);
+  }
+}
+__device__ __forceinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
+                                           const MeasRec& r) {
+  int s4[4];
+  sort4(op.b, s4);
+  const uint32_t mrA = 1u << op.b[0], mrY = 1u << op.b[1], mcA = 1u << op.b[2], mcY = 1u << op.b[3];
+  const double2* __restrict__ Tm = cs + 8 + 64 * r.outcome;
+  const double sc = r.scale;
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    const double2 v0 = cscale(tile[i0], sc), v1 = cscale(tile[i0 | mcA], sc), v2 = cscale(tile[i0 | mrA], sc),
+                  v3 = cscale(tile[i0 | mrA | mcA], sc);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const uint32_t idx = i0 | ((e & 8) ? mrA : 0u) | ((e & 4) ? mrY : 0u) | ((e & 2) ? mcA : 0u) | ((e & 1) ? mcY : 0u);
+      tile[idx] = cfma(Tm[4 * e + 3], v3, cfma(Tm[4 * e + 2], v2, cfma(Tm[4 * e + 1], v1, cmul(Tm[4 * e], v0))));
+    }
+  }
+}
+
 // split-phase cluster barrier (arrive at kernel start, wait before the first DSMEM write: every CTA of
 // the cluster is then known to be running, and nobody stalls for it)
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
@@ -1039,9 +1094,10 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // and forget), one cluster barrier, then each CTA sums the 16 local slots in rank order and draws the same
 // Philox number -- the pass simply goes on, no kernel boundary, no remote loads, no exit barrier.
 template <int FORM>
-__device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+__device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                uint64_t base, uint64_t shot, uint64_t cw, double* red,
-                                               double (*part)[16][2], MeasRec* mrec, int mcount, double* s_draw) {
+                                               double (*part)[16][2], MeasRec* mrec, int mcount, double* s_draw,
+                                               const double2* cs) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int par = mcount & 1;
@@ -1069,7 +1125,8 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
       }
     }
   } else {
-    dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
+    if (op.nb == 4) catm_partials(tile, T, op, pp, cs, base, a0, a1);   // fused inject -> interact -> measure
+    else dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1112,6 +1169,9 @@ __device__ __forceinline__ uint64_t op_measure(const double2* tile, uint32_t T, 
     if (pp.olog && cluster.block_rank() == 0) pp.olog[op.octrl * (uint64_t)pp.batch + shot] = (int8_t)m;
   }
   __syncthreads();
+  if constexpr (FORM == 1) {
+    if (op.nb == 4) catm_apply(tile, T, op, cs, *mrec);   // the output block of the drawn outcome, renormalised
+  }
   const int cbit = op.flags - 1;
   if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
   return cw;
@@ -1793,7 +1853,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
+          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs); break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
           case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot, s_treg); break;
           default: break;
@@ -1821,7 +1881,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw); break;
+          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs); break;
           case OP_TRACE: op_trace(tile, T, op); break;
           case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
           default: break;

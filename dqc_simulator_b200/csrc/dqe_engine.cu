@@ -118,6 +118,8 @@ struct dqe_engine {
   int64_t x_count, x_bytes;
   int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
   int64_t ladders_built;
+  int catfuse;              // dm: inject -> interact -> measure-and-discard runs fused at flush (fuse_cat_measure)
+  int64_t cat_fused;
   int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
   int64_t kblocks_fused;
   int64_t tmap_used, tmap_refused;
@@ -1047,6 +1049,206 @@ void ladderize(dqe_t* h) {
 }
 
 // -------- planner --------------------------------------------------------------------------
+// -------- dm: inject -> interact -> measure-and-discard, fused at flush ------------------------------------
+// The remote-gate sub-circuits of the reference (software/dqc_control.py:316-403 cat-entangle, :508-613
+// teleportation) all open the same way: a fresh entangled pair (x, y) lands on two comm qubits
+// (hardware/connections.py:145-150), ONE half x interacts with a data qubit A (CNOT + its gate noise) and is measured
+// and discarded at once.  Executed literally, the register grows by two qubits for those few ops (16x the
+// elements of rho) although x never outlives the pass.  Everything between the injection and the measurement that
+// touches x is a fixed superoperator S on (A, x), so the whole run is ONE linear map from the 4 elements
+// rho[rA', cA'] of the input to the 16 elements rho'[rA ry, cA cy] of the output, per outcome m:
+//     T_m[(rA ry cA cy), (rA' cA')] = sum_{rx' cx'} sum_k w_m(k) S[(rA k cA k), (rA' rx' cA' cx')] W[(rx' ry), (cx' cy)]
+// (W = the injected pair, w_m(k) = 1 - e for k = m, e for k = 1 - m: the measurement flip noise of
+// noise_models.py MeasurementNoiseModel folded in), and the outcome probabilities are the linear functionals
+// t_m[(rA' cA')] = sum_{a b} T_m[(a b a b), (rA' cA')].  The queue is rewritten accordingly: the INJECT, the ops on
+// (A, x) and the COLLAPSE disappear, the PROBS op becomes the fused measurement (nb = 4: bits of A and y; constants
+// t_0, t_1, T_0, T_1), x never goes live -- a cat-entangle pass runs over 4x fewer elements.
+// Index convention of the 16-dimensional operator space of (A, x): i = rA * 8 + rx * 4 + cA * 2 + cx.
+struct Sup16 { cplx m[256]; };
+void sup_identity(Sup16& S) { for (int i = 0; i < 256; ++i) S.m[i] = (i / 16 == i % 16) ? 1.0 : 0.0; }
+void sup_lmul(Sup16& S, const Sup16& L) {   // S <- L S
+  Sup16 R;
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j) {
+      cplx acc = 0.0;
+      for (int k = 0; k < 16; ++k) acc += L.m[i * 16 + k] * S.m[k * 16 + j];
+      R.m[i * 16 + j] = acc;
+    }
+  S = R;
+}
+// role 0 = A (row bit 3, column bit 1 of the index), role 1 = x (row bit 2, column bit 0)
+inline int sup_rbit(int role) { return role == 0 ? 3 : 2; }
+inline int sup_cbit(int role) { return role == 0 ? 1 : 0; }
+void sup_axis_local(Sup16& L, int role, const cplx* M) {   // M: 4x4 on (r, c) of the axis, index r * 2 + c
+  const int rb = sup_rbit(role), cb = sup_cbit(role);
+  const int mine = (1 << rb) | (1 << cb);
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j) {
+      if ((i & ~mine) != (j & ~mine)) { L.m[i * 16 + j] = 0.0; continue; }
+      const int a = ((i >> rb) & 1) * 2 + ((i >> cb) & 1), b = ((j >> rb) & 1) * 2 + ((j >> cb) & 1);
+      L.m[i * 16 + j] = M[a * 4 + b];
+    }
+}
+// U on the row bit of `role` (only where the other axis' row bit is 1 when ctrl_r), conj(U) on its column bit
+void sup_mat1x2(Sup16& L, int role, const cplx* U, bool ctrl_r, bool ctrl_c) {
+  Sup16 Lr, Lc;
+  const int rb = sup_rbit(role), cb = sup_cbit(role), orb = sup_rbit(role ^ 1), ocb = sup_cbit(role ^ 1);
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j) {
+      const bool same_r = (i & ~(1 << rb)) == (j & ~(1 << rb)), same_c = (i & ~(1 << cb)) == (j & ~(1 << cb));
+      const int ri = (i >> rb) & 1, rj = (j >> rb) & 1, ci = (i >> cb) & 1, cj = (j >> cb) & 1;
+      const bool on_r = !ctrl_r || ((i >> orb) & 1), on_c = !ctrl_c || ((i >> ocb) & 1);
+      Lr.m[i * 16 + j] = !same_r ? cplx(0.0) : on_r ? U[ri * 2 + rj] : cplx(ri == rj ? 1.0 : 0.0);
+      Lc.m[i * 16 + j] = !same_c ? cplx(0.0) : on_c ? std::conj(U[ci * 2 + cj]) : cplx(ci == cj ? 1.0 : 0.0);
+    }
+  L = Lr;
+  sup_lmul(L, Lc);
+}
+void sup_depol2(Sup16& L, double p) {
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j) {
+      const bool di = (i >> 2) == (i & 3), dj = (j >> 2) == (j & 3);
+      L.m[i * 16 + j] = (i == j ? 1.0 - p : 0.0) + (di && dj ? 0.25 * p : 0.0);
+    }
+}
+
+bool cat_cluster_mode(const dqe_t* h) { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 4; }
+
+// INJECT at queue index i created axes (x, y); x_first: x is the first axis of the injected pair.  true = rewritten.
+bool try_fuse_cat_at(dqe_t* h, size_t i, int x, int y, bool x_first) {
+  std::vector<HostOp>& Q = h->queue;
+  const int n = h->nmax;
+  const uint64_t xb = (1ull << x) | (1ull << (x + n)), yb = (1ull << y) | (1ull << (y + n));
+  int A = -1;
+  uint64_t Ab = 0;
+  Sup16 S, L;
+  sup_identity(S);
+  std::vector<size_t> absorbed;
+  size_t jp = Q.size();
+  auto set_A = [&](int a) {
+    if (a == x || a == y || a < 0 || a >= n) return false;
+    if (A >= 0) return A == a;
+    A = a; Ab = (1ull << a) | (1ull << (a + n));
+    return true;
+  };
+  cplx M[16];
+  for (size_t j = i + 1; j < Q.size(); ++j) {
+    const HostOp& e = Q[j];
+    if (e.kind != 0) continue;   // classical instructions / fences / finish records of other measurements
+    if (e.m.type == OP_PROBS) {
+      if (e.m.aux == x) { jp = j; break; }
+      if (e.m.aux == y || e.m.aux == A) return false;
+      continue;
+    }
+    const uint64_t tb = touched_bits(e);
+    if (!(tb & (xb | yb | Ab))) continue;   // unrelated: commutes with everything folded, stays where it is
+    if (tb & yb) return false;
+    if (e.m.pred_bit >= 0) return false;
+    if (!(tb & xb)) {            // on A alone, behind the first (A, x) op: constant axis-local channels fold in
+      if ((tb & ~Ab) || !axis_local_matrix(h, e, A, M)) return false;
+      sup_axis_local(L, 0, M);
+    } else if (!(tb & ~xb) && axis_local_matrix(h, e, x, M)) {
+      sup_axis_local(L, 1, M);
+    } else if (e.m.type == OP_MAT1X2) {
+      const int T = e.m.b[1];
+      if (e.m.b[0] != T + n) return false;
+      if (__builtin_popcountll(e.pctrl) > 1 || __builtin_popcountll(e.pctrl2) > 1) return false;
+      const int cr = e.pctrl ? __builtin_ctzll(e.pctrl) - n : -1, cc = e.pctrl2 ? __builtin_ctzll(e.pctrl2) : -1;
+      if (cr >= 0 && cc >= 0 && cr != cc) return false;
+      const int O = cr >= 0 ? cr : cc;
+      if (O == T) return false;
+      if (T != x && !set_A(T)) return false;
+      if (O >= 0 && O != x && !set_A(O)) return false;
+      if (T != x && O != x) return false;
+      cplx U[4];
+      for (int k = 0; k < 4; ++k) U[k] = cplx(h->cpool[e.m.c_off + k].x, h->cpool[e.m.c_off + k].y);
+      sup_mat1x2(L, T == x ? 1 : 0, U, cr >= 0, cc >= 0);
+    } else if (e.m.type == OP_DEPOL2) {
+      const int a = e.m.b[2], b = e.m.b[3];
+      if (a != x && b != x) return false;
+      if (!set_A(a == x ? b : a)) return false;
+      sup_depol2(L, e.m.p[0]);
+    } else {
+      return false;
+    }
+    sup_lmul(S, L);
+    absorbed.push_back(j);
+  }
+  if (jp + 2 >= Q.size() || A < 0) return false;
+  const HostOp& fin = Q[jp + 1];
+  const HostOp& col = Q[jp + 2];
+  if (fin.kind != 1 || col.kind != 0 || col.m.type != OP_COLLAPSE || col.m.b[1] != x || !(col.m.flags & 1)) return false;
+  const double e = fin.flip;
+  // W[(rx ry), (cx cy)] of the injected pair
+  const HostOp& inj = Q[i];
+  auto W = [&](int rx, int ry, int cx, int cy) {
+    const int r = x_first ? rx * 2 + ry : ry * 2 + rx, c = x_first ? cx * 2 + cy : cy * 2 + cx;
+    const double2 v = h->cpool[inj.m.c_off + r * 4 + c];
+    return cplx(v.x, v.y);
+  };
+  cplx K[8 + 128];
+  for (int m = 0; m < 2; ++m) {
+    cplx* T = K + 8 + 64 * m;
+    for (int o = 0; o < 16; ++o) {
+      const int rA = (o >> 3) & 1, ry = (o >> 2) & 1, cA = (o >> 1) & 1, cy = o & 1;
+      for (int jn = 0; jn < 4; ++jn) {
+        const int rA2 = jn >> 1, cA2 = jn & 1;
+        cplx acc = 0.0;
+        for (int k = 0; k < 2; ++k) {
+          const double w = k == m ? 1.0 - e : e;
+          if (w == 0.0) continue;
+          const int row = rA * 8 + k * 4 + cA * 2 + k;
+          for (int rx2 = 0; rx2 < 2; ++rx2)
+            for (int cx2 = 0; cx2 < 2; ++cx2)
+              acc += w * S.m[row * 16 + (rA2 * 8 + rx2 * 4 + cA2 * 2 + cx2)] * W(rx2, ry, cx2, cy);
+        }
+        T[o * 4 + jn] = acc;
+      }
+    }
+    for (int jn = 0; jn < 4; ++jn) {
+      cplx acc = 0.0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) acc += T[(a * 8 + b * 4 + a * 2 + b) * 4 + jn];
+      K[4 * m + jn] = acc;
+    }
+  }
+  HostOp f = Q[jp];   // the PROBS op, reshaped: nb = 4 marks the fused form (Planner::localise, op_measure)
+  f.m.nb = 4;
+  f.m.b[0] = (uint8_t)(A + n); f.m.b[1] = (uint8_t)(y + n); f.m.b[2] = (uint8_t)A; f.m.b[3] = (uint8_t)y;
+  f.m.b[4] = (uint8_t)A; f.m.b[5] = (uint8_t)y;
+  f.need = Ab | yb;
+  f.live_after = col.live_after;
+  f.m.c_off = add_consts(h, K, 8 + 128); f.nconst = 8 + 128;
+  HostOp g = fin;
+  g.flip = 0.0;   // folded into T_m
+  g.live_after = col.live_after;
+  std::vector<HostOp> out;
+  out.reserve(Q.size());
+  size_t na = 0;
+  for (size_t j = 0; j < Q.size(); ++j) {
+    if (j == i || j == jp + 2) continue;
+    if (na < absorbed.size() && absorbed[na] == j) { ++na; continue; }
+    if (j == jp) { out.push_back(f); continue; }
+    if (j == jp + 1) { out.push_back(g); continue; }
+    out.push_back(Q[j]);
+    if (j > i && j < jp) out.back().live_after &= ~(xb | yb);
+  }
+  Q.swap(out);
+  h->stats[7] += (int64_t)absorbed.size() + 2;
+  h->cat_fused++;
+  return true;
+}
+
+void fuse_cat_measure(dqe_t* h) {
+  if (h->formalism != DQE_DM || !h->catfuse || !cat_cluster_mode(h)) return;
+  for (size_t i = 0; i < h->queue.size(); ++i) {
+    const HostOp& o = h->queue[i];
+    if (o.kind != 0 || o.m.type != OP_INJECT || o.m.nb != 4 || (o.m.flags & 2) || o.m.pred_bit >= 0) continue;
+    const int a0 = o.m.b[2], a1 = o.m.b[3];
+    if (try_fuse_cat_at(h, i, a0, a1, true) || try_fuse_cat_at(h, i, a1, a0, false)) --i;   // INJECT erased: rescan slot i
+  }
+}
+
 int build_segs(uint64_t mask, Seg* segs, int cap) {
   int n = 0, src = 0;
   for (int b = 0; b < 64;) {
@@ -1132,6 +1334,13 @@ struct Planner {
       for (auto& pr : loc) { out[k++] = (uint8_t)pr.first; dev_consts.push_back(h->cpool[ho->m.c_off + pr.second]); }
       for (auto& pr : outer) { out[k++] = (uint8_t)pr.first; dev_consts.push_back(h->cpool[ho->m.c_off + pr.second]); }
       m.flags = (int)loc.size() | ((int)outer.size() << 8);
+      return m;
+    }
+    if (m.type == OP_MEASURE && ho->m.nb == 4) {
+      // fused inject -> interact -> measure (fuse_cat_measure): b[0..3] = tile positions of (row A, row y, col A, col y),
+      // b[4], b[5] = the axes A and y themselves (every OTHER axis must be diagonal for an element to count)
+      for (int i = 0; i < 4; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
+      m.c_off = copy_consts(ho, pass_const_begin);
       return m;
     }
     if (m.type == OP_DIAG) {
@@ -2063,6 +2272,7 @@ int do_flush(dqe_t* h, bool partial) {
   if (int rc = check_ready(h)) return rc;
   if (h->queue.empty()) return 0;
   ladderize(h);
+  fuse_cat_measure(h);
   if (getenv("DQE_DUMP_QUEUE")) {   // the queue the planner sees, with constants (debugging / host-side tests)
     for (const HostOp& o : h->queue) {
       if (o.kind != 0) { fprintf(stderr, "Q kind=%d\n", o.kind); continue; }
@@ -2342,7 +2552,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
-  h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->catfuse = 1; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -3242,6 +3452,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->pin_axes = (uint64_t)value;
   } else if (!strcmp(key, "kblock")) {
     h->kblock = value ? 1 : 0;
+  } else if (!strcmp(key, "catfuse")) {
+    h->catfuse = value ? 1 : 0;
   } else if (!strcmp(key, "ladder")) {
     h->ladder = value ? 1 : 0;
   } else if (!strcmp(key, "kgroup")) {

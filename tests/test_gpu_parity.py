@@ -288,8 +288,111 @@ def test_random_programs_fused(formalism, n, batch, tile, fuse):
         assert st["micro_ops"] > st["passes"]
 
 
+def cat_like_program(b, rng, rounds, classical=False):
+    """Remote-gate-shaped programs (dqc_control.py:316-403): a fresh pair (x, y), a short run of constant ops on
+    (A, x) -- CNOT either way, controlled-U, gate noise, one-qubit gates and channels on x or A --, then x measured
+    and discarded; unrelated ops on other axes and predicated corrections in between.  What
+    fuse_cat_measure (dqe_engine.cu) rewrites into one fused measurement, and what it must leave alone."""
+    from dqc_simulator_b200 import timeline as tl
+
+    n = b.n
+    data = list(range(n - 2))
+    for a in data:
+        b.alloc_axis(a)
+        b.apply_1q(a, rand_unitary(rng, 2))
+    for i in range(len(data) - 1):
+        b.apply_2q(data[i], data[i + 1], CNOT)
+    cbit = 0
+    for r in range(rounds):
+        x, y = (n - 1, n - 2) if rng.integers(2) else (n - 2, n - 1)
+        A, other = [int(v) for v in rng.choice(data, size=2, replace=False)]
+        kind = rng.integers(3)
+        first, second = (x, y) if rng.integers(2) else (y, x)
+        if kind == 0:
+            b.inject_2q(first, second, werner(float(rng.uniform(0.7, 1.0))), True)
+        elif kind == 1:
+            v = rng.normal(size=4) + 1j * rng.normal(size=4)
+            b.inject_2q(first, second, v / np.linalg.norm(v), False)
+        else:
+            b.inject_2q(first, second, np.array([1, 0, 0, 1]) / np.sqrt(2), False)
+        if classical:
+            b.classical_op(tl.CL_CONST, 2 * (r % 8), imm=float(rng.uniform(1e5, 1e7)))
+            b.classical_qexp2(2 * (r % 8) + 1, 2 * (r % 8), 255, 0.0, float(rng.uniform(1e-9, 1e-7)))
+            b.dyn_channel(A, 0, 2 * (r % 8) + 1)          # per-shot idle noise in front of the interaction: stays outside
+            b.regs_written.update((2 * (r % 8), 2 * (r % 8) + 1))
+        if rng.integers(3) == 0:
+            b.apply_1q(other, rand_unitary(rng, 2))       # unrelated, commutes
+        spoil = rng.integers(8) == 0                        # now and then something the rewrite must refuse
+        for _ in range(int(rng.integers(1, 5))):
+            c = rng.choice(["cx", "xc", "ctrl", "depol2", "1qx", "paulix", "1qA", "depolA", "hx"])
+            if c == "cx":
+                b.apply_2q(A, x, CNOT)
+            elif c == "xc":
+                b.apply_2q(x, A, CNOT)
+            elif c == "ctrl":
+                b.apply_ctrl_1q(*((A, x) if rng.integers(2) else (x, A)), rand_unitary(rng, 2))
+            elif c == "depol2":
+                b.depolarize([A, x] if rng.integers(2) else [x, A], float(rng.uniform(0, 0.2)))
+            elif c == "1qx":
+                b.apply_1q(x, rand_unitary(rng, 2))
+            elif c == "hx":
+                b.apply_1q(x, H)
+            elif c == "paulix":
+                b.pauli_channel(x, rng.dirichlet([8, 1, 1, 1]))
+            elif c == "1qA":
+                b.apply_1q(A, rand_unitary(rng, 2))
+            else:
+                b.depolarize([A], float(rng.uniform(0, 0.2)))
+        if spoil:
+            c = rng.integers(3)
+            if c == 0:
+                b.apply_2q(A, other, CNOT)                 # A meets a third axis behind the first (A, x) op
+            elif c == 1:
+                b.apply_1q(y, H)                           # the partner is touched before the measurement
+            else:
+                b.apply_2q(y, x, CNOT)
+        forced = -1 if rng.integers(4) else int(rng.integers(2))
+        b.measure(x, cbit % 40, forced, True, float(rng.choice([0.0, 0.003, 0.05])))
+        b.cond_1q(y, X, cbit % 40)
+        cbit += 1
+        # second half: y interacts with another data qubit and is measured out as well
+        b.apply_2q(y, other, CNOT)
+        b.depolarize([y, other], 0.01)
+        b.apply_1q(y, H)
+        b.measure(y, cbit % 40, -1, True, 0.003)
+        b.cond_1q(A, Z, cbit % 40)
+        cbit += 1
+        if (r + 1) % 4 == 0:
+            b.check(f"round {r}")
+    b.check("end")
+
+
+@pytest.mark.parametrize("n,batch,tile", [(7, 5, 10), (6, 4, 8), (7, 3, 12), (5, 6, 10)])
+@pytest.mark.parametrize("classical", [False, True])
+def test_fused_inject_measure_runs_keep_parity(n, batch, tile, classical):
+    """inject -> interact -> measure-and-discard runs are rewritten at flush into one fused measurement whose axis x
+    never goes live (fuse_cat_measure): same state, classical bits and live axes as the oracle running the ops one
+    by one, and as the engine with the rewrite switched off."""
+    rng = np.random.default_rng(31 + n + tile)
+    b = Both("dm", n, batch, 17, tile_bits=tile)
+    if classical:
+        b.regs_written = set()
+    cat_like_program(b, rng, 12, classical)
+    st = b.g.stats()
+    rng = np.random.default_rng(31 + n + tile)
+    b2 = Both("dm", n, batch, 17, tile_bits=tile)
+    b2.g.set_option("catfuse", 0)
+    if classical:
+        b2.regs_written = set()
+    cat_like_program(b2, rng, 12, classical)
+    assert np.abs(b.g.full_state() - b2.g.full_state()).max() < TOL
+    assert np.array_equal(b.g.read_creg_words(), b2.g.read_creg_words())
+    if n - tile // 2 <= 2:   # cluster-fused measurements: the rewrite is active and saves element updates
+        assert st["amp_updates"] < b2.g.stats()["amp_updates"]
+
+
 @pytest.mark.parametrize("opts", [dict(cxperm=0), dict(factor=0), dict(tmap=0), dict(prefetch=0), dict(prefetch=3),
-                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0)])
+                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0), dict(catfuse=0)])
 @pytest.mark.parametrize("n,batch,tile", [(7, 3, 10), (6, 4, 8), (7, 2, 12)])
 def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
     """Every planner / kernel switch of the density-matrix path (X / CX by address permutation, factored
