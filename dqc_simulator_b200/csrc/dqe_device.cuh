@@ -115,9 +115,12 @@ constexpr int kLadderLeafOff = 56;   // leaf bit positions of an OP_LADDER live 
 constexpr int kMaxLadderLeaves = 40;
 constexpr int kOuter = 64;       // MicroOp.b[] >= kOuter: bit lies outside the tile (physical pos = b - 64)
 constexpr int kMaxOpsPerPass = 48;
-constexpr int kMaxConstsKet = 512;       // double2 constants staged in shared memory per pass (8 KiB)
-constexpr int kMaxConstsDm = 256;        // dm: 4 KiB, so that eight 16 KiB-tile CTAs fit one SM
-__host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMaxConstsKet : kMaxConstsDm; }   // double2 entries staged in shared memory per pass (8 KiB)
+// double2 constants staged in shared memory per pass.  The pool lives in DYNAMIC shared memory behind the tile and a
+// pass asks for what it uses (PassParams::nconsts), so the cap costs nothing: an ordinary dm pass stages ~1 KiB (eight
+// 16 KiB-tile CTAs per SM), one that carries fused-measurement tables ~5 KiB
+constexpr int kMaxConstsKet = 512;
+constexpr int kMaxConstsDm = 512;
+__host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMaxConstsKet : kMaxConstsDm; }
 constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
 struct __align__(16) MicroOp {
@@ -1029,35 +1032,44 @@ __device__ __forceinline__ void op_probs(const double2* tile, uint32_t T, const 
 }
 
 
+// shared by the fused-measurement forms: is the group at tile index i0 diagonal in every axis but axA / axY?
+__device__ __forceinline__ bool catm_tile_diagonal(const PassParams& pp, uint64_t base, int axA, int axY) {
+  const int n = pp.nmax;
+  for (int a = 0; a < n; ++a) {   // axes with both bits outside the tile: one test for the whole tile
+    if (a == axA || a == axY || pp.ax_col[a] >= 0 || pp.ax_row[a] >= 0) continue;
+    if (((base >> a) ^ (base >> (a + n))) & 1ull) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ bool catm_group_diagonal(const PassParams& pp, uint64_t base, uint32_t i0, int axA, int axY) {
+  const int n = pp.nmax;
+  bool ok = true;
+  for (int a = 0; a < n; ++a) {
+    const int cl = pp.ax_col[a], rl = pp.ax_row[a];
+    if (a == axA || a == axY || (cl < 0 && rl < 0)) continue;
+    const uint32_t cb = cl >= 0 ? (i0 >> cl) & 1u : (uint32_t)((base >> a) & 1ull);
+    const uint32_t rb = rl >= 0 ? (i0 >> rl) & 1u : (uint32_t)((base >> (a + n)) & 1ull);
+    ok = ok && cb == rb;
+  }
+  return ok;
+}
 // Fused inject -> interact -> measure-and-discard (host: fuse_cat_measure in dqe_engine.cu).  The op carries the bits
 // of a data axis A and of a FRESH axis y (b[0..3] = tile positions of row A, row y, col A, col y; b[4], b[5] = the
 // axes).  A thread owns the 16 elements (rA ry cA cy) of a group; on entry only the four with ry = cy = 0 are
 // non-zero: in[j], j = rA * 2 + cA.  Constants: t_0[4], t_1[4], T_0[16][4], T_1[16][4].
 //   probability of outcome m (flip noise already folded in) = sum over groups that are diagonal in every other
 //   axis of Re(sum_j t_m[j] in[j]);   new elements = scale * sum_j T_m[e][j] in[j].
-__device__ __forceinline__ void catm_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
-                                              const double2* cs, uint64_t base, double& a0, double& a1) {
+__device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                              const double2* __restrict__ cs, uint64_t base, double& a0, double& a1) {
+  if (!catm_tile_diagonal(pp, base, op.b[4], op.b[5])) return;
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mcA = 1u << op.b[2];
-  const int n = pp.nmax, axA = op.b[4], axY = op.b[5];
-  // axes with both bits outside the tile: one test for the whole tile
-  for (int a = 0; a < n; ++a) {
-    if (a == axA || a == axY || pp.ax_col[a] >= 0 || pp.ax_row[a] >= 0) continue;
-    if (((base >> a) ^ (base >> (a + n))) & 1ull) return;
-  }
-  const double2 t00 = cs[0], t01 = cs[1], t02 = cs[2], t03 = cs[3], t10 = cs[4], t11 = cs[5], t12 = cs[6], t13 = cs[7];
+  const double2 t00 = cs[0], t01 = cs[1], t02 = cs[2], t03 = cs[3];
+  const double2 t10 = cs[4], t11 = cs[5], t12 = cs[6], t13 = cs[7];
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
-    bool ok = true;
-    for (int a = 0; a < n; ++a) {
-      const int cl = pp.ax_col[a], rl = pp.ax_row[a];
-      if (a == axA || a == axY || (cl < 0 && rl < 0)) continue;
-      const uint32_t cb = cl >= 0 ? (i0 >> cl) & 1u : (uint32_t)((base >> a) & 1ull);
-      const uint32_t rb = rl >= 0 ? (i0 >> rl) & 1u : (uint32_t)((base >> (a + n)) & 1ull);
-      ok = ok && cb == rb;
-    }
-    if (!ok) continue;
+    if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
     const double2 v0 = tile[i0], v1 = tile[i0 | mcA], v2 = tile[i0 | mrA], v3 = tile[i0 | mrA | mcA];
     a0 += fma(t00.x, v0.x, -t00.y * v0.y) + fma(t01.x, v1.x, -t01.y * v1.y) + fma(t02.x, v2.x, -t02.y * v2.y) +
           fma(t03.x, v3.x, -t03.y * v3.y);
@@ -1065,7 +1077,7 @@ __device__ __forceinline__ void catm_partials(const double2* tile, uint32_t T, c
           fma(t13.x, v3.x, -t13.y * v3.y);
   }
 }
-__device__ __forceinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
+__device__ __noinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
                                            const MeasRec& r) {
   int s4[4];
   sort4(op.b, s4);
@@ -1080,6 +1092,55 @@ __device__ __forceinline__ void catm_apply(double2* tile, uint32_t T, const Micr
     for (int e = 0; e < 16; ++e) {
       const uint32_t idx = i0 | ((e & 8) ? mrA : 0u) | ((e & 4) ? mrY : 0u) | ((e & 2) ? mcA : 0u) | ((e & 1) ? mcY : 0u);
       tile[idx] = cfma(Tm[4 * e + 3], v3, cfma(Tm[4 * e + 2], v2, cfma(Tm[4 * e + 1], v1, cmul(Tm[4 * e], v0))));
+    }
+  }
+}
+
+// Contraction form (b[6] = 1): x = an existing axis, measured and discarded behind a run of constant ops on (A, x).
+// b[0..3] = tile positions of (row A, row x, col A, col x); constants t_0[16], t_1[16], T_0[4][16], T_1[4][16]
+// (element index i = rA * 8 + rx * 4 + cA * 2 + cx).  The four surviving elements land in the |0><0| block of x.
+__device__ __noinline__ void catm2_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
+                                               const double2* __restrict__ cs, uint64_t base, double& a0, double& a1) {
+  if (!catm_tile_diagonal(pp, base, op.b[4], op.b[5])) return;
+  int s4[4];
+  sort4(op.b, s4);
+  const uint32_t mrA = 1u << op.b[0], mrX = 1u << op.b[1], mcA = 1u << op.b[2], mcX = 1u << op.b[3];
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double2 v = tile[i0 | ((i & 8) ? mrA : 0u) | ((i & 4) ? mrX : 0u) | ((i & 2) ? mcA : 0u) | ((i & 1) ? mcX : 0u)];
+      const double2 u0 = cs[i], u1 = cs[16 + i];
+      a0 += fma(u0.x, v.x, -u0.y * v.y);
+      a1 += fma(u1.x, v.x, -u1.y * v.y);
+    }
+  }
+}
+__device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* __restrict__ cs,
+                                            const MeasRec& r) {
+  int s4[4];
+  sort4(op.b, s4);
+  const uint32_t mrA = 1u << op.b[0], mrX = 1u << op.b[1], mcA = 1u << op.b[2], mcX = 1u << op.b[3];
+  const double2* __restrict__ Tm = cs + 32 + 64 * r.outcome;
+  const double sc = r.scale;
+  const double2 zero = make_double2(0.0, 0.0);
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    double2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t idx = i0 | ((i & 8) ? mrA : 0u) | ((i & 4) ? mrX : 0u) | ((i & 2) ? mcA : 0u) | ((i & 1) ? mcX : 0u);
+      v[i] = tile[idx];
+      tile[idx] = zero;
+    }
+#pragma unroll 1
+    for (int o = 0; o < 4; ++o) {     // rolled: one row of T_m at a time keeps the live registers at v[] + a few
+      const double2* __restrict__ row = Tm + 16 * o;
+      double2 acc = zero;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc = cfma(row[i], v[i], acc);
+      tile[i0 | ((o & 2) ? mrA : 0u) | ((o & 1) ? mcA : 0u)] = cscale(acc, sc);
     }
   }
 }
@@ -1125,7 +1186,10 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
       }
     }
   } else {
-    if (op.nb == 4) catm_partials(tile, T, op, pp, cs, base, a0, a1);   // fused inject -> interact -> measure
+    if (op.nb == 4) {   // fused runs
+      if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
+      else catm_partials(tile, T, op, pp, cs, base, a0, a1);
+    }
     else dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
   }
 #pragma unroll
@@ -1170,7 +1234,10 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
   }
   __syncthreads();
   if constexpr (FORM == 1) {
-    if (op.nb == 4) catm_apply(tile, T, op, cs, *mrec);   // the output block of the drawn outcome, renormalised
+    if (op.nb == 4) {   // the output block of the drawn outcome, renormalised
+      if (op.b[6]) catm2_apply(tile, T, op, cs, *mrec);
+      else catm_apply(tile, T, op, cs, *mrec);
+    }
   }
   const int cbit = op.flags - 1;
   if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
@@ -1661,7 +1728,6 @@ template <int MAXT, int MINB, int FORM, bool PERSIST>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ __align__(128) double2 dyn_tiles[];
   __shared__ MicroOp s_ops[kMaxOpsPerPass];
-  __shared__ double2 s_consts[max_consts(FORM)];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
@@ -1675,6 +1741,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   const int c0 = pp.tile_segs[0].len;
   const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
   const int nbuf = PERSIST ? pp.nbuf : 1;   // 2 with TMA (prefetch distance 1), 1 otherwise
+  double2* const s_consts = dyn_tiles + ((size_t)nbuf << pp.t);   // the pass's constants, behind the tile buffer(s)
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 

@@ -1132,12 +1132,20 @@ bool try_fuse_cat_at(dqe_t* h, size_t i, int x, int y, bool x_first) {
     return true;
   };
   cplx M[16];
+  bool unit_trace;
+  {
+    const double2* w = &h->cpool[Q[i].m.c_off];
+    unit_trace = std::abs(w[0].x + w[5].x + w[10].x + w[15].x - 1.0) < 1e-12 &&
+                 std::abs(w[0].y + w[5].y + w[10].y + w[15].y) < 1e-12;
+  }
   for (size_t j = i + 1; j < Q.size(); ++j) {
     const HostOp& e = Q[j];
     if (e.kind != 0) continue;   // classical instructions / fences / finish records of other measurements
     if (e.m.type == OP_PROBS) {
       if (e.m.aux == x) { jp = j; break; }
-      if (e.m.aux == y || e.m.aux == A) return false;
+      // another measurement in between: the injection may move behind it (a normalised pair changes no probability),
+      // folded ops may not (they need not preserve the trace)
+      if (e.m.aux == y || e.m.aux == A || e.m.nb == 4 || !absorbed.empty() || !unit_trace) return false;
       continue;
     }
     const uint64_t tb = touched_bits(e);
@@ -1239,6 +1247,128 @@ bool try_fuse_cat_at(dqe_t* h, size_t i, int x, int y, bool x_first) {
   return true;
 }
 
+// Second form: x is an EXISTING axis (typically the other half of the pair, in the disentangling half of the remote
+// gate: CNOT onto the target, H, measure and discard, dqc_control.py:382-403).  The constant, unpredicated ops on
+// (A, x) right in front of the measurement fold into the measurement the same way, now as a contraction from the 16
+// elements (rA rx cA cx) to the 4 elements (rA cA) left in the |0><0| block of x:
+//     T_m[(rA cA), i] = sum_k w_m(k) S[(rA k cA k), i],      t_m[i] = sum_a T_m[(a a), i].
+// The scan runs backwards from the PROBS op at queue index jp and stops at the first op on x or A it cannot fold.
+bool try_fuse_out_at(dqe_t* h, size_t jp) {
+  std::vector<HostOp>& Q = h->queue;
+  const int n = h->nmax;
+  if (jp + 2 >= Q.size()) return false;
+  const HostOp& pr = Q[jp];
+  const HostOp& fin = Q[jp + 1];
+  const HostOp& col = Q[jp + 2];
+  const int x = pr.m.aux;
+  if (pr.m.nb == 4 || fin.kind != 1 || col.kind != 0 || col.m.type != OP_COLLAPSE || col.m.b[1] != x || !(col.m.flags & 1))
+    return false;
+  const uint64_t xb = (1ull << x) | (1ull << (x + n));
+  int A = -1;
+  uint64_t Ab = 0, skipped = 0;
+  std::vector<size_t> absorbed;      // queue indices, descending
+  std::vector<Sup16> maps;           // their superoperators, same order
+  Sup16 L;
+  cplx M[16];
+  for (size_t j = jp; j-- > 0;) {
+    const HostOp& e = Q[j];
+    if (e.kind != 0) continue;
+    if (e.m.type == OP_PROBS) break;   // folded ops need not preserve the trace: they stay behind earlier measurements
+    const uint64_t tb = touched_bits(e);
+    if (!(tb & (xb | Ab))) { skipped |= tb; continue; }
+    if (e.m.pred_bit >= 0) break;
+    int newA = -1;
+    auto want_A = [&](int a) {      // a second axis joins: it must be THE partner, and nothing skipped may touch it
+      if (a == x || a < 0 || a >= n) return false;
+      if (A >= 0) return A == a;
+      if (skipped & ((1ull << a) | (1ull << (a + n)))) return false;
+      newA = a;
+      return true;
+    };
+    bool ok = true;
+    if (!(tb & xb)) {
+      ok = !(tb & ~Ab) && axis_local_matrix(h, e, A, M);
+      if (ok) sup_axis_local(L, 0, M);
+    } else if (!(tb & ~xb) && axis_local_matrix(h, e, x, M)) {
+      sup_axis_local(L, 1, M);
+    } else if (e.m.type == OP_MAT1X2) {
+      const int T = e.m.b[1];
+      const int cr = e.pctrl ? __builtin_ctzll(e.pctrl) - n : -1, cc = e.pctrl2 ? __builtin_ctzll(e.pctrl2) : -1;
+      const int O = cr >= 0 ? cr : cc;
+      ok = e.m.b[0] == T + n && __builtin_popcountll(e.pctrl) <= 1 && __builtin_popcountll(e.pctrl2) <= 1 &&
+           !(cr >= 0 && cc >= 0 && cr != cc) && O != T && (T == x || O == x) && (T == x || want_A(T)) &&
+           (O < 0 || O == x || want_A(O));
+      if (ok) {
+        cplx U[4];
+        for (int k = 0; k < 4; ++k) U[k] = cplx(h->cpool[e.m.c_off + k].x, h->cpool[e.m.c_off + k].y);
+        sup_mat1x2(L, T == x ? 1 : 0, U, cr >= 0, cc >= 0);
+      }
+    } else if (e.m.type == OP_DEPOL2) {
+      const int a = e.m.b[2], b = e.m.b[3];
+      ok = (a == x || b == x) && want_A(a == x ? b : a);
+      if (ok) sup_depol2(L, e.m.p[0]);
+    } else {
+      ok = false;
+    }
+    if (!ok) break;
+    if (newA >= 0) { A = newA; Ab = (1ull << A) | (1ull << (A + n)); }
+    absorbed.push_back(j);
+    maps.push_back(L);
+  }
+  if (A < 0 || absorbed.empty()) return false;
+  if (getenv("DQE_CAT2_MAX") && h->cat_fused >= atoi(getenv("DQE_CAT2_MAX"))) return false;
+  if (getenv("DQE_DUMP_PLAN")) {
+    fprintf(stderr, "fuse-out x=%d A=%d jp=%zu absorbed:", x, A, jp);
+    for (size_t k : absorbed) fprintf(stderr, " %zu(type %d b=%d,%d,%d,%d pc=%llx pc2=%llx)", k, Q[k].m.type, Q[k].m.b[0], Q[k].m.b[1], Q[k].m.b[2], Q[k].m.b[3], (unsigned long long)Q[k].pctrl, (unsigned long long)Q[k].pctrl2);
+    fprintf(stderr, "\n   window:");
+    for (size_t k = absorbed.back(); k <= jp + 2; ++k) fprintf(stderr, " [%zu k%d t%d p%d b=%d,%d,%d,%d nb%u]", k, Q[k].kind, Q[k].m.type, Q[k].m.pred_bit, Q[k].m.b[0], Q[k].m.b[1], Q[k].m.b[2], Q[k].m.b[3], Q[k].m.nb);
+    fprintf(stderr, "\n");
+  }
+  Sup16 S;
+  sup_identity(S);
+  for (size_t k = maps.size(); k-- > 0;) sup_lmul(S, maps[k]);   // earliest op first
+  const double e = fin.flip;
+  cplx K[32 + 128];
+  for (int m = 0; m < 2; ++m) {
+    cplx* T = K + 32 + 64 * m;
+    for (int o = 0; o < 4; ++o) {
+      const int rA = o >> 1, cA = o & 1;
+      for (int i = 0; i < 16; ++i) {
+        cplx acc = 0.0;
+        for (int k = 0; k < 2; ++k) {
+          const double w = k == m ? 1.0 - e : e;
+          acc += w * S.m[(rA * 8 + k * 4 + cA * 2 + k) * 16 + i];
+        }
+        T[o * 16 + i] = acc;
+      }
+    }
+    for (int i = 0; i < 16; ++i) K[16 * m + i] = T[0 * 16 + i] + T[3 * 16 + i];
+  }
+  HostOp f = pr;
+  f.m.nb = 4;
+  f.m.b[0] = (uint8_t)(A + n); f.m.b[1] = (uint8_t)(x + n); f.m.b[2] = (uint8_t)A; f.m.b[3] = (uint8_t)x;
+  f.m.b[4] = (uint8_t)A; f.m.b[5] = (uint8_t)x; f.m.b[6] = 1;   // b[6] = 1: contraction form
+  f.need = Ab | xb;
+  f.live_after = col.live_after;
+  f.m.c_off = add_consts(h, K, 32 + 128); f.nconst = 32 + 128;
+  HostOp g = fin;
+  g.flip = 0.0;
+  g.live_after = col.live_after;
+  std::vector<HostOp> out;
+  out.reserve(Q.size());
+  for (size_t j = 0; j < Q.size(); ++j) {
+    if (j == jp + 2) continue;
+    if (std::find(absorbed.begin(), absorbed.end(), j) != absorbed.end()) continue;
+    if (j == jp) { out.push_back(f); continue; }
+    if (j == jp + 1) { out.push_back(g); continue; }
+    out.push_back(Q[j]);
+  }
+  Q.swap(out);
+  h->stats[7] += (int64_t)absorbed.size() + 1;
+  h->cat_fused++;
+  return true;
+}
+
 void fuse_cat_measure(dqe_t* h) {
   if (h->formalism != DQE_DM || !h->catfuse || !cat_cluster_mode(h)) return;
   for (size_t i = 0; i < h->queue.size(); ++i) {
@@ -1246,6 +1376,13 @@ void fuse_cat_measure(dqe_t* h) {
     if (o.kind != 0 || o.m.type != OP_INJECT || o.m.nb != 4 || (o.m.flags & 2) || o.m.pred_bit >= 0) continue;
     const int a0 = o.m.b[2], a1 = o.m.b[3];
     if (try_fuse_cat_at(h, i, a0, a1, true) || try_fuse_cat_at(h, i, a1, a0, false)) --i;   // INJECT erased: rescan slot i
+  }
+  if (h->catfuse < 2) return;
+  for (size_t j = 0; j < h->queue.size(); ++j) {
+    const HostOp& o = h->queue[j];
+    if (o.kind != 0 || o.m.type != OP_PROBS || o.m.nb == 4) continue;
+    const size_t before = h->queue.size();
+    if (try_fuse_out_at(h, j)) j -= (before - h->queue.size()) - 1;   // the fused PROBS moved down by the absorbed ops; skip its finish
   }
 }
 
@@ -1561,7 +1698,9 @@ struct Planner {
     // a block right behind another block (two spans separated by a fence only): the threads must meet in
     // between, or a fast warp's writes of this block race with a slow warp's writes of the previous one
     bool need_barrier = !dev_ops.empty() && dev_ops.back().type == OP_CLASSICAL;
-    for (int par = 0; par < 2; ++par) {
+    {
+      // one block in program order (every thread runs every instruction, so there is nothing to gain from
+      // separating the clock chain from the exp() evaluations -- and a micro-op less to dispatch per span)
       MicroOp m;
       int n = 0;
       auto open_op = [&]() {
@@ -1572,15 +1711,13 @@ struct Planner {
       auto close_op = [&]() {
         if (n == 0) return;
         // the payload overlays the fields behind the 16-byte dispatch header; the marker rides in c_off
-        m.flags = n; m.c_off = par | (need_barrier ? 2 : 0);
+        m.flags = n; m.c_off = need_barrier ? 2 : 0;
         need_barrier = false;
         dev_ops.push_back(m);
       };
       open_op();
       for (size_t i = 0; i < ops.size(); ++i) {
         const HostOp* ho = ops[i];
-        const bool is_par = ho->ci.op == CL_QEXP || ho->ci.op == CL_QEXP2;
-        if (is_par != (par == 1)) continue;
         ClInstr ci = ho->ci;
         ci.imm = (uint16_t)(base + idx[i]);
         if (ci.op == CL_QEXP2 || ci.op == CL_GEOM) { const int i2 = base + idx2[i]; ci.cbit = (int8_t)(i2 & 0xff); ci.pad = (uint8_t)(i2 >> 8); }
@@ -2063,7 +2200,7 @@ struct Planner {
         writes = true;
       } else {
         for (const HostOp* ho : it.ops) {
-          if (ho->m.type != OP_PROBS && ho->m.type != OP_MEASURE) writes = true;
+          if ((ho->m.type != OP_PROBS && ho->m.type != OP_MEASURE) || ho->m.nb == 4) writes = true;   // (fused measurements write)
           if (ho->m.type == OP_MEASURE) { pp.has_measure = 1; pp.writes_creg = 1; }
           dev_ops.push_back(localise(ho, tile, P.const_begin));
         }
@@ -2084,15 +2221,15 @@ struct Planner {
     if (h->persistent) {
       // persistent grid + double buffering: as many CTAs as fit the machine (<= 512 threads per SM)
       pp.nbuf = pp.use_tma ? 2 : 1;
-      P.smem = (sizeof(double2) << t) * pp.nbuf;
-      const size_t per_cta = P.smem + 14 * 1024;
+      P.smem = (sizeof(double2) << t) * pp.nbuf + sizeof(double2) * (size_t)pp.nconsts;
+      const size_t per_cta = P.smem + 10 * 1024;
       int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / per_cta, (size_t)(512 / h->threads));
       per_sm = std::max(1, std::min(per_sm, h->ctas_per_sm > 0 ? h->ctas_per_sm : 16));
       P.grid = std::min<uint64_t>(pp.ntiles, (uint64_t)h->num_sms * per_sm);
     } else {
       // one tile per CTA; overlap of load / compute / store comes from 4+ resident CTAs per SM
       pp.nbuf = 1;
-      P.smem = sizeof(double2) << t;
+      P.smem = (sizeof(double2) << t) + sizeof(double2) * (size_t)pp.nconsts;   // tile + the pass's constants
       P.grid = pp.ntiles;
       if (P.grid > 0x7fffffffull) { err = "grid too large: enable the persistent option"; return false; }
     }
@@ -2552,7 +2689,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
-  h->catfuse = 1; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -3453,7 +3590,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "kblock")) {
     h->kblock = value ? 1 : 0;
   } else if (!strcmp(key, "catfuse")) {
-    h->catfuse = value ? 1 : 0;
+    if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "catfuse in {0 off, 1 inject runs, 2 inject + measure-out runs}");
+    h->catfuse = (int)value;
   } else if (!strcmp(key, "ladder")) {
     h->ladder = value ? 1 : 0;
   } else if (!strcmp(key, "kgroup")) {
