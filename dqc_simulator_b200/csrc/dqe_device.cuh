@@ -815,6 +815,12 @@ __device__ __forceinline__ const ClInstr* cl_payload(const MicroOp& op) {
 // last bit of 1 - exp(-x) evaluated in double (what the reference's p = 1 - exp(-dt * 1e-9 * rate) is,
 // noise_models.py:248-253) and cost a quarter of exp()'s latency on the one lane that computes it.
 __device__ __forceinline__ double one_minus_exp_neg(double x) {
+  if (x < 0.0009765625) {   // 2^-10: the terms beyond x^6 / 720 are below 2^-64 x -- five terms are exact
+    double p = 1.0 / 720.0;
+    p = fma(p, x, -1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, -1.0 / 6.0);
+    p = fma(p, x, 0.5);
+    return x - x * x * p;
+  }
   if (x < 0.03125) {
     double p = -1.0 / 362880.0;
     p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, -1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0);
@@ -1056,7 +1062,8 @@ __device__ __forceinline__ bool catm_group_diagonal(const PassParams& pp, uint64
 // Fused inject -> interact -> measure-and-discard (host: fuse_cat_measure in dqe_engine.cu).  The op carries the bits
 // of a data axis A and of a FRESH axis y (b[0..3] = tile positions of row A, row y, col A, col y; b[4], b[5] = the
 // axes).  A thread owns the 16 elements (rA ry cA cy) of a group; on entry only the four with ry = cy = 0 are
-// non-zero: in[j], j = rA * 2 + cA.  Constants: t_0[4], t_1[4], T_0[16][4], T_1[16][4].
+// non-zero: in[j], j = rA * 2 + cA.  Constants: t_0[4], t_1[4], T_0[16][4], T_1[16][4]; b[7] = 1: the tables are real
+// and packed as doubles.
 //   probability of outcome m (flip noise already folded in) = sum over groups that are diagonal in every other
 //   axis of Re(sum_j t_m[j] in[j]);   new elements = scale * sum_j T_m[e][j] in[j].
 __device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
@@ -1077,12 +1084,13 @@ __device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, cons
           fma(t13.x, v3.x, -t13.y * v3.y);
   }
 }
-__device__ __noinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs,
-                                           const MeasRec& r) {
+template <bool REAL>
+__device__ __noinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs, const MeasRec& r) {
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mrY = 1u << op.b[1], mcA = 1u << op.b[2], mcY = 1u << op.b[3];
-  const double2* __restrict__ Tm = cs + 8 + 64 * r.outcome;
+  // table of the drawn outcome: REAL: 64 packed doubles (T_m[e][j] at double index 4 e + j), else 64 complex entries
+  const double2* __restrict__ Tm = cs + 8 + (REAL ? 32 : 64) * r.outcome;
   const double sc = r.scale;
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
@@ -1091,13 +1099,21 @@ __device__ __noinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const uint32_t idx = i0 | ((e & 8) ? mrA : 0u) | ((e & 4) ? mrY : 0u) | ((e & 2) ? mcA : 0u) | ((e & 1) ? mcY : 0u);
-      tile[idx] = cfma(Tm[4 * e + 3], v3, cfma(Tm[4 * e + 2], v2, cfma(Tm[4 * e + 1], v1, cmul(Tm[4 * e], v0))));
+      if constexpr (REAL) {
+        const double2 c01 = Tm[2 * e], c23 = Tm[2 * e + 1];
+        double2 o;
+        o.x = fma(c23.y, v3.x, fma(c23.x, v2.x, fma(c01.y, v1.x, c01.x * v0.x)));
+        o.y = fma(c23.y, v3.y, fma(c23.x, v2.y, fma(c01.y, v1.y, c01.x * v0.y)));
+        tile[idx] = o;
+      } else {
+        tile[idx] = cfma(Tm[4 * e + 3], v3, cfma(Tm[4 * e + 2], v2, cfma(Tm[4 * e + 1], v1, cmul(Tm[4 * e], v0))));
+      }
     }
   }
 }
 
 // Contraction form (b[6] = 1): x = an existing axis, measured and discarded behind a run of constant ops on (A, x).
-// b[0..3] = tile positions of (row A, row x, col A, col x); constants t_0[16], t_1[16], T_0[4][16], T_1[4][16]
+// b[0..3] = tile positions of (row A, row x, col A, col x); constants t_0[16], t_1[16], T_0[4][16], T_1[4][16] (b[7] = 1: real tables, packed doubles)
 // (element index i = rA * 8 + rx * 4 + cA * 2 + cx).  The four surviving elements land in the |0><0| block of x.
 __device__ __noinline__ void catm2_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                const double2* __restrict__ cs, uint64_t base, double& a0, double& a1) {
@@ -1117,12 +1133,13 @@ __device__ __noinline__ void catm2_partials(const double2* tile, uint32_t T, con
     }
   }
 }
+template <bool REAL>
 __device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* __restrict__ cs,
-                                            const MeasRec& r) {
+                                         const MeasRec& r) {
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mrX = 1u << op.b[1], mcA = 1u << op.b[2], mcX = 1u << op.b[3];
-  const double2* __restrict__ Tm = cs + 32 + 64 * r.outcome;
+  const double2* __restrict__ Tm = cs + 32 + (REAL ? 32 : 64) * r.outcome;   // REAL: packed doubles, index 16 o + i
   const double sc = r.scale;
   const double2 zero = make_double2(0.0, 0.0);
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
@@ -1136,10 +1153,20 @@ __device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroO
     }
 #pragma unroll 1
     for (int o = 0; o < 4; ++o) {     // rolled: one row of T_m at a time keeps the live registers at v[] + a few
-      const double2* __restrict__ row = Tm + 16 * o;
       double2 acc = zero;
+      if constexpr (REAL) {
+        const double2* __restrict__ row = Tm + 8 * o;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc = cfma(row[i], v[i], acc);
+        for (int i = 0; i < 8; ++i) {
+          const double2 c = row[i];
+          acc.x = fma(c.x, v[2 * i].x, acc.x); acc.y = fma(c.x, v[2 * i].y, acc.y);
+          acc.x = fma(c.y, v[2 * i + 1].x, acc.x); acc.y = fma(c.y, v[2 * i + 1].y, acc.y);
+        }
+      } else {
+        const double2* __restrict__ row = Tm + 16 * o;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = cfma(row[i], v[i], acc);
+      }
       tile[i0 | ((o & 2) ? mrA : 0u) | ((o & 1) ? mcA : 0u)] = cscale(acc, sc);
     }
   }
@@ -1235,8 +1262,8 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
   __syncthreads();
   if constexpr (FORM == 1) {
     if (op.nb == 4) {   // the output block of the drawn outcome, renormalised
-      if (op.b[6]) catm2_apply(tile, T, op, cs, *mrec);
-      else catm_apply(tile, T, op, cs, *mrec);
+      if (op.b[6]) { if (op.b[7]) catm2_apply<true>(tile, T, op, cs, *mrec); else catm2_apply<false>(tile, T, op, cs, *mrec); }
+      else { if (op.b[7]) catm_apply<true>(tile, T, op, cs, *mrec); else catm_apply<false>(tile, T, op, cs, *mrec); }
     }
   }
   const int cbit = op.flags - 1;
@@ -1734,6 +1761,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ LadderPrep s_lad[FORM == 0 ? kMaxDiagRun : 1];
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
+  __shared__ unsigned long long s_cw;   // classical word handed back by the warp that ran a classical block
   __shared__ __align__(16) double s_treg[kTimeRegs];   // the shot's classical registers (simulated times, channel strengths)
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
@@ -1880,13 +1908,25 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
       if (o < pp.nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if (op_type == OP_CLASSICAL) {
-        // EVERY thread runs the instructions itself, on its own copy of the classical word and on the shared
-        // register file: all threads store identical values, and a thread only ever depends on what it has
-        // stored itself -- so the block needs no barrier at all (the barrier that ended the previous micro-op
-        // already ordered it behind every earlier reader of the registers it overwrites).
-        if (hdr_coff & 2) __syncthreads();   // block right behind another span's block (fence only in between)
-        cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
-               pp.shot_offset + shot);
+        if (blockDim.x <= 64u) {
+          // two warps: EVERY thread runs the instructions itself, on its own copy of the classical word and on the
+          // shared register file: all threads store identical values, and a thread only ever depends on what it
+          // has stored itself -- so the block needs no barrier at all (the barrier that ended the previous
+          // micro-op already ordered it behind every earlier reader of the registers it overwrites).
+          if (hdr_coff & 2) __syncthreads();   // block right behind another span's block (fence only in between)
+          cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+                 pp.shot_offset + shot);
+          continue;
+        }
+        // four or more warps: warp 0 runs the block for the CTA (the chain is latency, not throughput: the other
+        // warps would only burn issue slots on identical work), the classical word comes back through shared memory
+        if (threadIdx.x < 32u) {
+          cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+                 pp.shot_offset + shot);
+          if (threadIdx.x == 0) s_cw = cw;
+        }
+        __syncthreads();
+        cw = s_cw;
         continue;
       }
       if constexpr (FORM == 0) {   // ---- ket micro-ops

@@ -118,6 +118,8 @@ struct dqe_engine {
   int64_t x_count, x_bytes;
   int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
   int64_t ladders_built;
+  int pass_ops;             // planner: micro-op budget of a pass (<= kMaxOpsPerPass)
+  int tile_auto;            // small dm registers (P <= 14): the planner picks tile and CTA size per pass (tile_bits_for)
   int catfuse;              // dm: inject -> interact -> measure-and-discard runs fused at flush (fuse_cat_measure)
   int64_t cat_fused;
   int kblock;               // ket: runs of gates inside <= 4 tile bits become one dense block on the FP64 tensor cores
@@ -1112,7 +1114,7 @@ void sup_depol2(Sup16& L, double p) {
     }
 }
 
-bool cat_cluster_mode(const dqe_t* h) { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 4; }
+bool cat_cluster_mode(const dqe_t* h) { return h->cluster && !h->persistent && h->fuse && h->P - (h->tile_auto ? 10 : h->tile_bits) <= 4; }
 
 // INJECT at queue index i created axes (x, y); x_first: x is the first axis of the injected pair.  true = rewritten.
 bool try_fuse_cat_at(dqe_t* h, size_t i, int x, int y, bool x_first) {
@@ -1220,13 +1222,23 @@ bool try_fuse_cat_at(dqe_t* h, size_t i, int x, int y, bool x_first) {
       K[4 * m + jn] = acc;
     }
   }
+  // Werner pairs, CNOT / H and depolarising noise give REAL tables: they are staged as packed doubles (half the shared
+  // memory, half the multiply-adds); anything complex (a phase gate folded in) keeps the complex form
+  bool real_tab = true;
+  for (int k = 0; k < 8 + 128; ++k) real_tab = real_tab && K[k].imag() == 0.0;
+  int nk = 8 + 128;
+  if (real_tab) {
+    for (int k = 0; k < 64; ++k) K[8 + k] = cplx(K[8 + 2 * k].real(), K[8 + 2 * k + 1].real());
+    nk = 8 + 64;
+  }
   HostOp f = Q[jp];   // the PROBS op, reshaped: nb = 4 marks the fused form (Planner::localise, op_measure)
   f.m.nb = 4;
+  f.m.b[7] = real_tab ? 1 : 0;
   f.m.b[0] = (uint8_t)(A + n); f.m.b[1] = (uint8_t)(y + n); f.m.b[2] = (uint8_t)A; f.m.b[3] = (uint8_t)y;
   f.m.b[4] = (uint8_t)A; f.m.b[5] = (uint8_t)y;
   f.need = Ab | yb;
   f.live_after = col.live_after;
-  f.m.c_off = add_consts(h, K, 8 + 128); f.nconst = 8 + 128;
+  f.m.c_off = add_consts(h, K, nk); f.nconst = nk;
   HostOp g = fin;
   g.flip = 0.0;   // folded into T_m
   g.live_after = col.live_after;
@@ -1344,13 +1356,21 @@ bool try_fuse_out_at(dqe_t* h, size_t jp) {
     }
     for (int i = 0; i < 16; ++i) K[16 * m + i] = T[0 * 16 + i] + T[3 * 16 + i];
   }
+  bool real_tab = true;   // packed doubles when every entry is real, as in the injecting form
+  for (int k = 0; k < 32 + 128; ++k) real_tab = real_tab && K[k].imag() == 0.0;
+  int nk = 32 + 128;
+  if (real_tab) {
+    for (int k = 0; k < 64; ++k) K[32 + k] = cplx(K[32 + 2 * k].real(), K[32 + 2 * k + 1].real());
+    nk = 32 + 64;
+  }
   HostOp f = pr;
   f.m.nb = 4;
+  f.m.b[7] = real_tab ? 1 : 0;
   f.m.b[0] = (uint8_t)(A + n); f.m.b[1] = (uint8_t)(x + n); f.m.b[2] = (uint8_t)A; f.m.b[3] = (uint8_t)x;
   f.m.b[4] = (uint8_t)A; f.m.b[5] = (uint8_t)x; f.m.b[6] = 1;   // b[6] = 1: contraction form
   f.need = Ab | xb;
   f.live_after = col.live_after;
-  f.m.c_off = add_consts(h, K, 32 + 128); f.nconst = 32 + 128;
+  f.m.c_off = add_consts(h, K, nk); f.nconst = nk;
   HostOp g = fin;
   g.flip = 0.0;
   g.live_after = col.live_after;
@@ -1402,9 +1422,21 @@ int build_segs(uint64_t mask, Seg* segs, int cap) {
 
 // tile = lowest c live bits + the needed bits above them; returns the tile mask or 0 if the
 // needed bits do not fit with a contiguous low run of at least min_run bits.
+// Tile size of a pass.  Small density-matrix registers (tile_auto): passes over <= 12 live bits take 2^11 tiles on 128
+// threads (two CTAs per shot: fewer per-CTA prologues, cluster barriers and constant copies -- Grover-5 with fused
+// remote gates: 65k vs 53k shots/s), wider ones 2^10 tiles on 64 threads (16 small CTAs per shot overlap better:
+// 21.0k vs 18.0k shots/s on the unfused 7-qubit passes).  Measured on B200, profiles/r02t_summary.md.
+int tile_bits_for(const dqe_t* h, uint64_t live) {
+  if (!h->tile_auto) return h->tile_bits;
+  return __builtin_popcountll(live) <= 12 ? 11 : 10;
+}
+int threads_for(const dqe_t* h, int t) {
+  if (!h->tile_auto) return h->threads;
+  return t >= 11 ? 128 : 64;
+}
 bool choose_tile(const dqe_t* h, uint64_t need, uint64_t live, bool force, uint64_t* tile_out, int* t_out) {
   const int L = __builtin_popcountll(live);
-  const int t = std::min(h->tile_bits, L);
+  const int t = std::min(tile_bits_for(h, live), L);
   int pos[64];
   int n = 0;
   for (int b = 0; b < 64; ++b) if ((live >> b) & 1ull) pos[n++] = b;
@@ -2020,7 +2052,7 @@ struct Planner {
     pp.n_outer_segs = build_segs(outer, pp.outer_segs, 24);
     if (pp.n_tile_segs < 0 || pp.n_outer_segs < 0) { err = "planner: too many bit segments"; return false; }
     if (pp.n_tile_segs == 0) { pp.n_tile_segs = 1; pp.tile_segs[0] = Seg{0, 0, 0, 0}; }
-    pp.seed = h->seed; pp.shot_offset = h->shot_offset; pp.nthreads = h->threads;
+    pp.seed = h->seed; pp.shot_offset = h->shot_offset; pp.nthreads = threads_for(h, t);
     for (int a = 0; a < 24; ++a) { pp.ax_col[a] = -1; pp.ax_row[a] = -1; }
     if (h->formalism == DQE_DM)
       for (int a = 0; a < h->nmax; ++a) {
@@ -2241,7 +2273,7 @@ struct Planner {
 
   // every pass of this handle has at most 8 tiles per shot (cluster size limit) when the whole
   // register is at most 3 bits wider than a tile
-  bool cluster_mode() const { return h->cluster && !h->persistent && h->fuse && h->P - h->tile_bits <= 4; }
+  bool cluster_mode() const { return cat_cluster_mode(h); }
 
   bool plan() {
     std::vector<const HostOp*> cur;
@@ -2304,7 +2336,7 @@ struct Planner {
         if (++nq3 % 3 == 0) op_slots += 1;
       }
       if (cur.empty()) { nslots = 3; ncl = 0; nconst = 0; }
-      const bool fits = cur.empty() || (h->fuse && nslots + op_slots <= kMaxOpsPerPass &&
+      const bool fits = cur.empty() || (h->fuse && nslots + op_slots <= h->pass_ops &&
                                         nconst + op_consts <= max_consts(h->formalism) &&
                                         choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
       if (!fits) {
@@ -2387,7 +2419,7 @@ void build_tensor_map(dqe_t* h, PassParams& pp) {
   if (rc != CUDA_SUCCESS) { h->tmap_refused++; return; }
   pp.tm_rank = rank; pp.tm_base_dim = base_dim; pp.tm_shift = lb;
   // L2 prefetch distance: one wave of resident CTAs ahead (-1 = automatic: SMs x CTAs per SM)
-  pp.prefetch_dist = h->prefetch >= 0 ? h->prefetch : h->num_sms * (h->threads <= 64 ? 8 : 4);
+  pp.prefetch_dist = h->prefetch >= 0 ? h->prefetch : h->num_sms * (pp.nthreads <= 64 ? 8 : 4);
 }
 
 struct Planner;
@@ -2581,7 +2613,7 @@ int launch_passes(dqe_t* h, Planner& pl) {
     // a shot form one cluster and exchange their probability partials through DSMEM.
     {
       const void* fn;
-      int threads = h->threads;
+      int threads = P.pp.nthreads;
       const bool pers = h->persistent != 0;
 #define DQE_KFN(M, B, F) (pers ? (const void*)k_tile_pass<M, B, F, true> : (const void*)k_tile_pass<M, B, F, false>)
       fn = h->formalism == DQE_KET ? DQE_KFN(256, 2, 0) : DQE_KFN(256, 2, 1);
@@ -2689,7 +2721,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
-  h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -3572,7 +3604,7 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (int rc = do_flush(h)) return rc;
   if (!strcmp(key, "tile_bits")) {
     if (value < 4 || value > 13) return fail(h, DQE_EINVAL, "tile_bits in [4, 13]");
-    h->tile_bits = (int)value;
+    h->tile_bits = (int)value; h->tile_auto = 0;
   } else if (!strcmp(key, "min_run_bits")) {
     if (value < 0 || value > 12) return fail(h, DQE_EINVAL, "min_run_bits in [0, 12]");
     h->min_run_bits = (int)value;
@@ -3589,6 +3621,9 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->pin_axes = (uint64_t)value;
   } else if (!strcmp(key, "kblock")) {
     h->kblock = value ? 1 : 0;
+  } else if (!strcmp(key, "pass_ops")) {
+    if (value < 4 || value > kMaxOpsPerPass) return fail(h, DQE_EINVAL, "pass_ops in [4, 48]");
+    h->pass_ops = (int)value;
   } else if (!strcmp(key, "catfuse")) {
     if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "catfuse in {0 off, 1 inject runs, 2 inject + measure-out runs}");
     h->catfuse = (int)value;
@@ -3631,7 +3666,7 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->ctas_per_sm = (int)value;
   } else if (!strcmp(key, "threads")) {
     if (value != 64 && value != 128 && value != 256) return fail(h, DQE_EINVAL, "threads in {64, 128, 256}");
-    h->threads = (int)value;
+    h->threads = (int)value; h->tile_auto = 0;
   } else return fail(h, DQE_EINVAL, std::string("unknown option ") + key);
   return 0;
 }

@@ -302,8 +302,8 @@ def test_program_instructions_overlap_on_free_positions():
     # per-shot timelines (round 2): the clock arithmetic rides along as classical instructions; cat-entangle runs
     # (inject -> CNOT -> measure-and-discard) and measure-out runs (CNOT -> H -> measure-and-discard) are fused at flush,
     # the first comm qubit never goes live (Grover-5 was 292 passes / 4209 micro-ops before that rewrite)
-    ("c2_grover5_3qpu_cat.json", 7, dict(passes=130, micro_ops=2250, api_ops=5313, merged_ops=1941)),
-    ("c2_qft5_3qpu_cat.json", 7, dict(passes=17, micro_ops=344, api_ops=812, merged_ops=311)),
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=101, micro_ops=2262, api_ops=5313, merged_ops=1941)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=15, micro_ops=342, api_ops=812, merged_ops=311)),
     ("c4_qft16_mono.json.gz", 16, dict(passes=56, micro_ops=1182, api_ops=1564, merged_ops=521)),
 ])
 def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):

@@ -1,4 +1,7 @@
-for cfg in "--tile-bits 11 --opt threads=128 --opt catfuse=0" "--opt catfuse=0" "--tile-bits 11 --opt threads=128 --opt catfuse=1" "--tile-bits 11 --opt threads=128 --circuit qft" "--circuit qft" "--tile-bits 11 --opt threads=128 --noise depol+dephase"; do
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02s_gputests.log 2>&1
+echo tests rc=$?
+tail -3 gpurun_out/r02s_gputests.log
+for cfg in "" "--tile-bits 11 --opt threads=128" "--tile-bits 11 --opt threads=128 --opt pass_ops=30" "--tile-bits 11 --opt threads=128 --opt pass_ops=18" "--opt pass_ops=18" "--tile-bits 11 --opt threads=64 --opt pass_ops=18" "--circuit qft" "--circuit qft --opt pass_ops=18" "--tile-bits 11 --opt threads=128 --circuit qft --opt pass_ops=18"; do
   echo "== $cfg"
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline $cfg 2>&1 | python -c "
 import json,sys
