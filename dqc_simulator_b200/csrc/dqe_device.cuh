@@ -1059,6 +1059,42 @@ __device__ __forceinline__ bool catm_group_diagonal(const PassParams& pp, uint64
   }
   return ok;
 }
+// The same two tests from what the planner resolved per op (Planner::localise): lctrl2 = pairs | mixed << 8 (bit 31:
+// too many, use the generic loops above), p[1..2] = (column, row) tile positions of the axes inside the tile,
+// p[3] = (tile position, base bit) of the axes with one bit outside, octrl2 = axes that live in the base only.
+struct CatDiag {
+  uint32_t np, mixmask, mixwant;
+  uint64_t pw0, pw1;
+  bool generic, any;
+};
+__device__ __forceinline__ CatDiag catm_diag_prepare(const MicroOp& op, const PassParams& pp, uint64_t base) {
+  CatDiag d;
+  d.generic = (op.lctrl2 >> 31) != 0u;
+  d.np = op.lctrl2 & 0xffu; d.mixmask = 0u; d.mixwant = 0u; d.pw0 = 0ull; d.pw1 = 0ull;
+  if (d.generic) { d.any = catm_tile_diagonal(pp, base, op.b[4], op.b[5]); return d; }
+  d.any = ((((base >> pp.nmax) ^ base) & op.octrl2) == 0ull);
+  memcpy(&d.pw0, &op.p[1], 8); memcpy(&d.pw1, &op.p[2], 8);
+  uint64_t mw;
+  memcpy(&mw, &op.p[3], 8);
+  const uint32_t nm = (op.lctrl2 >> 8) & 0xffu;
+  for (uint32_t k = 0; k < nm; ++k) {
+    const uint32_t tp = (uint32_t)(mw >> (16 * k)) & 0xffu, pb = (uint32_t)(mw >> (16 * k + 8)) & 0xffu;
+    d.mixmask |= 1u << tp;
+    d.mixwant |= (uint32_t)((base >> pb) & 1ull) << tp;
+  }
+  return d;
+}
+__device__ __forceinline__ bool catm_diag_test(const CatDiag& d, const MicroOp& op, const PassParams& pp, uint64_t base,
+                                               uint32_t i0) {
+  if (d.generic) return catm_group_diagonal(pp, base, i0, op.b[4], op.b[5]);
+  uint32_t bad = (i0 & d.mixmask) ^ d.mixwant;
+  for (uint32_t k = 0; k < d.np; ++k) {
+    const uint64_t w = k < 4u ? d.pw0 >> (16 * k) : d.pw1 >> (16 * (k - 4u));
+    bad |= ((i0 >> ((uint32_t)w & 0xffu)) ^ (i0 >> ((uint32_t)(w >> 8) & 0xffu))) & 1u;
+  }
+  return bad == 0u;
+}
+
 // Fused inject -> interact -> measure-and-discard (host: fuse_cat_measure in dqe_engine.cu).  The op carries the bits
 // of a data axis A and of a FRESH axis y (b[0..3] = tile positions of row A, row y, col A, col y; b[4], b[5] = the
 // axes).  A thread owns the 16 elements (rA ry cA cy) of a group; on entry only the four with ry = cy = 0 are
@@ -1068,7 +1104,8 @@ __device__ __forceinline__ bool catm_group_diagonal(const PassParams& pp, uint64
 //   axis of Re(sum_j t_m[j] in[j]);   new elements = scale * sum_j T_m[e][j] in[j].
 __device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                               const double2* __restrict__ cs, uint64_t base, double& a0, double& a1) {
-  if (!catm_tile_diagonal(pp, base, op.b[4], op.b[5])) return;
+  const CatDiag dg = catm_diag_prepare(op, pp, base);
+  if (!dg.any) return;
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mcA = 1u << op.b[2];
@@ -1076,7 +1113,7 @@ __device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, cons
   const double2 t10 = cs[4], t11 = cs[5], t12 = cs[6], t13 = cs[7];
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
-    if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
+    if (!catm_diag_test(dg, op, pp, base, i0)) continue;
     const double2 v0 = tile[i0], v1 = tile[i0 | mcA], v2 = tile[i0 | mrA], v3 = tile[i0 | mrA | mcA];
     a0 += fma(t00.x, v0.x, -t00.y * v0.y) + fma(t01.x, v1.x, -t01.y * v1.y) + fma(t02.x, v2.x, -t02.y * v2.y) +
           fma(t03.x, v3.x, -t03.y * v3.y);
@@ -1117,13 +1154,14 @@ __device__ __noinline__ void catm_apply(double2* tile, uint32_t T, const MicroOp
 // (element index i = rA * 8 + rx * 4 + cA * 2 + cx).  The four surviving elements land in the |0><0| block of x.
 __device__ __noinline__ void catm2_partials(const double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                const double2* __restrict__ cs, uint64_t base, double& a0, double& a1) {
-  if (!catm_tile_diagonal(pp, base, op.b[4], op.b[5])) return;
+  const CatDiag dg = catm_diag_prepare(op, pp, base);
+  if (!dg.any) return;
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mrX = 1u << op.b[1], mcA = 1u << op.b[2], mcX = 1u << op.b[3];
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
-    if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
+    if (!catm_diag_test(dg, op, pp, base, i0)) continue;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const double2 v = tile[i0 | ((i & 8) ? mrA : 0u) | ((i & 4) ? mrX : 0u) | ((i & 2) ? mcA : 0u) | ((i & 1) ? mcX : 0u)];
@@ -1670,6 +1708,35 @@ __device__ __forceinline__ void run_group(double2* tile, uint32_t T, const Micro
 #undef DQE_GEL
 }
 
+// every stand-alone density-matrix sweep (ops that ride neither in a group nor in a fused measurement)
+__device__ __noinline__ void dm_standalone(double2* tile, uint32_t T, const MicroOp& op, int op_type, const PassParams& pp,
+                                           const double2* cs, uint64_t base, uint64_t blk, uint64_t shot, double* s_red,
+                                           const MeasRec* s_meas, const double* s_treg) {
+  switch (op_type) {
+    case OP_MAT1X2: {
+      const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
+      if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
+      break;
+    }
+    case OP_MAT2:
+      if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
+      break;
+    case OP_DIAG: op_diag(tile, T, op, cs, base); break;
+    case OP_PAULI1: op_pauli1(tile, T, op); break;
+    case OP_XPAT: op_xpat(tile, T, op, cs); break;
+    case OP_DYN1: op_dyn1(tile, T, op, s_treg); break;
+    case OP_DEPOL2: op_depol2(tile, T, op); break;
+    case OP_KBLOCK:
+      if (op.nb == 4) op_kblock<4>(tile, T, op, cs); else op_kblock<3>(tile, T, op, cs);
+      break;
+    case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
+    case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, *s_meas); break;
+    case OP_TRACE: op_trace(tile, T, op); break;
+    case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
+    default: break;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // issue the bulk loads r0, r0+rstep, ... of one tile (a tile = 2^(t-c0) contiguous runs); the
 // issuing lanes of different warps work in parallel -- a single thread needs ~100 cycles per copy
@@ -1966,33 +2033,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           default: break;
         }
       } else {                     // ---- density-matrix micro-ops
-        switch (op_type) {
-          case OP_GROUP:
-            run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas, s_treg);
-            break;
-          case OP_MAT1X2: {
-            const bool r_on = (base & op.octrl) == op.octrl, c_on = (base & op.octrl2) == op.octrl2;
-            if (r_on || c_on) op_mat1x2(tile, T, op, cs, r_on, c_on);
-            break;
-          }
-          case OP_MAT2:
-            if ((base & op.octrl) == op.octrl) op_mat2(tile, T, op, cs);
-            break;
-          case OP_DIAG: op_diag(tile, T, op, cs, base); break;
-          case OP_PAULI1: op_pauli1(tile, T, op); break;
-          case OP_XPAT: op_xpat(tile, T, op, cs); break;
-          case OP_DYN1: op_dyn1(tile, T, op, s_treg); break;
-          case OP_DEPOL2: op_depol2(tile, T, op); break;
-          case OP_KBLOCK:
-            if (op.nb == 4) op_kblock<4>(tile, T, op, cs); else op_kblock<3>(tile, T, op, cs);
-            break;
-          case OP_PROBS: op_probs<1>(tile, T, op, pp, base, blk, s_red); break;
-          case OP_COLLAPSE: op_collapse<1>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs); break;
-          case OP_TRACE: op_trace(tile, T, op); break;
-          case OP_INJECT: op_inject<1>(tile, T, op, pp, cs, shot); break;
-          default: break;
-        }
+        // the hot ops of the remote-gate passes inline; every stand-alone sweep behind ONE call, so that their loop
+        // set-up is not hoisted into the dispatch of every micro-op
+        if (op_type == OP_GROUP) run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas, s_treg);
+        else if (op_type == OP_MEASURE)
+          cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs);
+        else dm_standalone(tile, T, op, op_type, pp, cs, base, blk, shot, s_red, &s_meas, s_treg);
       }
       __syncthreads();
     }

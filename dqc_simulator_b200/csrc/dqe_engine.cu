@@ -1510,6 +1510,35 @@ struct Planner {
       // b[4], b[5] = the axes A and y themselves (every OTHER axis must be diagonal for an element to count)
       for (int i = 0; i < 4; ++i) m.b[i] = (uint8_t)local_of(tile, ho->m.b[i]);
       m.c_off = copy_consts(ho, pass_const_begin);
+      // which groups count towards the probabilities: those diagonal in every other axis.  Resolved here into
+      // (column, row) tile-position pairs (both bits in the tile), (tile position, base bit) pairs (one bit outside)
+      // and a mask of axes that live in the tile base only -- the kernel tests a few shifts per group
+      const int n = h->nmax, axA = ho->m.b[4], axY = ho->m.b[5];
+      uint8_t pairs[16], mixed[8];
+      int np = 0, nm = 0;
+      bool fallback = false;
+      uint64_t eq = 0;
+      for (int a = 0; a < n; ++a) {
+        if (a == axA || a == axY) continue;
+        const bool in_c = (tile >> a) & 1ull, in_r = (tile >> (a + n)) & 1ull;
+        if (in_c && in_r) {
+          if (np == 8) { fallback = true; break; }
+          pairs[2 * np] = (uint8_t)local_of(tile, a); pairs[2 * np + 1] = (uint8_t)local_of(tile, a + n); ++np;
+        } else if (in_c || in_r) {
+          if (nm == 4) { fallback = true; break; }
+          mixed[2 * nm] = (uint8_t)local_of(tile, in_c ? a : a + n); mixed[2 * nm + 1] = (uint8_t)(in_c ? a + n : a); ++nm;
+        } else {
+          eq |= 1ull << a;
+        }
+      }
+      memset(&m.p[1], 0, 24);
+      if (fallback) m.lctrl2 = 0x80000000u;
+      else {
+        m.lctrl2 = (uint32_t)np | ((uint32_t)nm << 8);
+        memcpy(&m.p[1], pairs, 2 * np);
+        memcpy(&m.p[3], mixed, 2 * nm);
+        m.octrl2 = eq;
+      }
       return m;
     }
     if (m.type == OP_DIAG) {
