@@ -110,6 +110,7 @@ struct ClInstr {   // 8 bytes; ten ride in one MicroOp
 static_assert(sizeof(ClInstr) == 8, "ClInstr is packed into MicroOp payloads");
 constexpr int kTimeRegs = 128;        // doubles per shot
 constexpr int kClPerOp = 10;          // ClInstr per OP_CLASSICAL micro-op
+constexpr uint32_t kMeasRunsClassical = 1u << 30;   // OP_MEASURE.lctrl2: the classical block that follows runs inside the measurement
 
 constexpr int kLadderLeafOff = 56;   // leaf bit positions of an OP_LADDER live in bytes [56, 96) of the MicroOp
 constexpr int kMaxLadderLeaves = 40;
@@ -1084,15 +1085,16 @@ __device__ __forceinline__ CatDiag catm_diag_prepare(const MicroOp& op, const Pa
   }
   return d;
 }
-__device__ __forceinline__ bool catm_diag_test(const CatDiag& d, const MicroOp& op, const PassParams& pp, uint64_t base,
-                                               uint32_t i0) {
-  if (d.generic) return catm_group_diagonal(pp, base, i0, op.b[4], op.b[5]);
-  uint32_t bad = (i0 & d.mixmask) ^ d.mixwant;
+// tile index (zeros at the group's four bits) of the d-th diagonal group of the tile: bit k of d sets both bits of
+// the k-th in-tile axis, the one-bit-outside axes follow the tile base -- a shot has 2^(other axes) such groups out of
+// 4^(other axes), so the probability sums enumerate them directly and most warps skip the op
+__device__ __forceinline__ uint32_t catm_diag_group(const CatDiag& d, uint32_t k_bits) {
+  uint32_t i0 = d.mixwant;
   for (uint32_t k = 0; k < d.np; ++k) {
     const uint64_t w = k < 4u ? d.pw0 >> (16 * k) : d.pw1 >> (16 * (k - 4u));
-    bad |= ((i0 >> ((uint32_t)w & 0xffu)) ^ (i0 >> ((uint32_t)(w >> 8) & 0xffu))) & 1u;
+    if ((k_bits >> k) & 1u) i0 |= (1u << ((uint32_t)w & 0xffu)) | (1u << ((uint32_t)(w >> 8) & 0xffu));
   }
-  return bad == 0u;
+  return i0;
 }
 
 // Fused inject -> interact -> measure-and-discard (host: fuse_cat_measure in dqe_engine.cu).  The op carries the bits
@@ -1111,9 +1113,15 @@ __device__ __noinline__ void catm_partials(const double2* tile, uint32_t T, cons
   const uint32_t mrA = 1u << op.b[0], mcA = 1u << op.b[2];
   const double2 t00 = cs[0], t01 = cs[1], t02 = cs[2], t03 = cs[3];
   const double2 t10 = cs[4], t11 = cs[5], t12 = cs[6], t13 = cs[7];
-  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
-    const uint32_t i0 = ins0_4(q, s4);
-    if (!catm_diag_test(dg, op, pp, base, i0)) continue;
+  const uint32_t ngrp = dg.generic ? (T >> 4) : (1u << dg.np);
+  for (uint32_t q = threadIdx.x; q < ngrp; q += blockDim.x) {
+    uint32_t i0;
+    if (dg.generic) {
+      i0 = ins0_4(q, s4);
+      if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
+    } else {
+      i0 = catm_diag_group(dg, q);
+    }
     const double2 v0 = tile[i0], v1 = tile[i0 | mcA], v2 = tile[i0 | mrA], v3 = tile[i0 | mrA | mcA];
     a0 += fma(t00.x, v0.x, -t00.y * v0.y) + fma(t01.x, v1.x, -t01.y * v1.y) + fma(t02.x, v2.x, -t02.y * v2.y) +
           fma(t03.x, v3.x, -t03.y * v3.y);
@@ -1159,9 +1167,15 @@ __device__ __noinline__ void catm2_partials(const double2* tile, uint32_t T, con
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mrX = 1u << op.b[1], mcA = 1u << op.b[2], mcX = 1u << op.b[3];
-  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
-    const uint32_t i0 = ins0_4(q, s4);
-    if (!catm_diag_test(dg, op, pp, base, i0)) continue;
+  const uint32_t ngrp = dg.generic ? (T >> 4) : (1u << dg.np);
+  for (uint32_t q = threadIdx.x; q < ngrp; q += blockDim.x) {
+    uint32_t i0;
+    if (dg.generic) {
+      i0 = ins0_4(q, s4);
+      if (!catm_group_diagonal(pp, base, i0, op.b[4], op.b[5])) continue;
+    } else {
+      i0 = catm_diag_group(dg, q);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const double2 v = tile[i0 | ((i & 8) ? mrA : 0u) | ((i & 4) ? mrX : 0u) | ((i & 2) ? mcA : 0u) | ((i & 1) ? mcX : 0u)];
@@ -1223,7 +1237,8 @@ template <int FORM>
 __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                uint64_t base, uint64_t shot, uint64_t cw, double* red,
                                                double (*part)[16][2], MeasRec* mrec, int mcount, double* s_draw,
-                                               const double2* cs) {
+                                               const double2* cs, const MicroOp* next_op, double* s_treg,
+                                               const double2* s_consts, unsigned long long* s_cw) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int par = mcount & 1;
@@ -1298,14 +1313,23 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     if (pp.olog && cluster.block_rank() == 0) pp.olog[op.octrl * (uint64_t)pp.batch + shot] = (int8_t)m;
   }
   __syncthreads();
+  const int cbit = op.flags - 1;
+  if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
+  if (op.lctrl2 & kMeasRunsClassical) {
+    // the classical block hoisted behind this measurement runs right here (planner flag): no dispatch and no
+    // barrier of its own; CTAs of four warps let warp 0 run it while the other warps already write the output block
+    if (blockDim.x <= 64u || threadIdx.x < 32u) {
+      cl_run(cl_payload(*next_op), next_op->flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+             pp.shot_offset + shot);
+      if (threadIdx.x == 0) *s_cw = cw;
+    }
+  }
   if constexpr (FORM == 1) {
     if (op.nb == 4) {   // the output block of the drawn outcome, renormalised
       if (op.b[6]) { if (op.b[7]) catm2_apply<true>(tile, T, op, cs, *mrec); else catm2_apply<false>(tile, T, op, cs, *mrec); }
       else { if (op.b[7]) catm_apply<true>(tile, T, op, cs, *mrec); else catm_apply<false>(tile, T, op, cs, *mrec); }
     }
   }
-  const int cbit = op.flags - 1;
-  if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
   return cw;
 }
 
@@ -1961,6 +1985,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     if (threadIdx.x == 0) s_meas = mr0;
     __syncthreads();
     int mcount = 0;
+    bool take_cw = false;
 
     // the dispatch header of the NEXT op is fetched before the current op runs (one 16-byte load, its
     // latency hidden behind the op); a group header carries its sub-op count in c_off, so the skip over
@@ -2027,7 +2052,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
-          case OP_MEASURE: cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs); break;
+          case OP_MEASURE:
+            cw = op_measure<0>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs, &s_ops[cur + 1],
+                               s_treg, s_consts, &s_cw);
+            if (op.lctrl2 & kMeasRunsClassical) {   // the classical block rode inside: skip it
+              o = cur + 2;
+              if (o < pp.nops) hdr = op_header(&s_ops[o]);
+              take_cw = blockDim.x > 64u;
+            }
+            break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
           case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot, s_treg); break;
           default: break;
@@ -2036,11 +2069,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         // the hot ops of the remote-gate passes inline; every stand-alone sweep behind ONE call, so that their loop
         // set-up is not hoisted into the dispatch of every micro-op
         if (op_type == OP_GROUP) run_group(tile, T, op, &s_ops[cur + 1], pp, s_consts, base, cw, &s_meas, s_treg);
-        else if (op_type == OP_MEASURE)
-          cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs);
-        else dm_standalone(tile, T, op, op_type, pp, cs, base, blk, shot, s_red, &s_meas, s_treg);
+        else if (op_type == OP_MEASURE) {
+          cw = op_measure<1>(tile, T, op, pp, base, shot, cw, s_red, s_part, &s_meas, mcount++, &s_draw, cs, &s_ops[cur + 1],
+                             s_treg, s_consts, &s_cw);
+          if (op.lctrl2 & kMeasRunsClassical) {   // the classical block rode inside: skip it
+            o = cur + 2;
+            if (o < pp.nops) hdr = op_header(&s_ops[o]);
+            take_cw = blockDim.x > 64u;
+          }
+        } else dm_standalone(tile, T, op, op_type, pp, cs, base, blk, shot, s_red, &s_meas, s_treg);
       }
       __syncthreads();
+      if (take_cw) { cw = s_cw; take_cw = false; }   // classical word of a block that warp 0 ran inside a measurement
     }
 
     // classical state of the shot -> the `out` copies, by the CTA that holds the shot's tile 0 (every CTA of

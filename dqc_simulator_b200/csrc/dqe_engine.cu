@@ -2268,6 +2268,9 @@ struct Planner {
       }
     }
     if (h->formalism == DQE_KET) emit_ket_seq(kseq, tile, t, pp, P.const_begin, writes);
+    // a classical block right behind a fused measurement runs inside it (op_measure): no dispatch, no barrier of its own
+    for (size_t i = P.op_begin; i + 1 < dev_ops.size(); ++i)
+      if (dev_ops[i].type == OP_MEASURE && dev_ops[i + 1].type == OP_CLASSICAL) dev_ops[i].lctrl2 |= kMeasRunsClassical;
     pp.nops = (int)(dev_ops.size() - P.op_begin);
     pp.nconsts = (int)(dev_consts.size() - P.const_begin);
     if (pp.nops > kMaxOpsPerPass || pp.nconsts > max_consts(h->formalism)) {
