@@ -424,21 +424,30 @@ def main():
         "passes_per_step": st["passes"] // a.steps, "micro_ops_per_step": st["micro_ops"] // a.steps,
         "api_ops_per_step": st["api_ops"] // a.steps,
         "mean_fidelity": float(np.mean(fids)),
+        "unfused_equivalent": {
+            "what": "context, not a roofline: the element updates the SAME step costs with the flush-time rewrite off "
+                    "(--opt catfuse=0: every comm qubit goes live, 292 passes for Grover-5) divided by this run's time",
+            "amp_updates_per_shot_unfused": {"grover": 2999296, "qft": 285952, "ghz": None}[a.circuit],
+            "GBps": (None if a.circuit == "ghz" else
+                     32.0 * {"grover": 2999296, "qft": 285952}[a.circuit] * total_shots / (t_dev / a.steps) / 1e9)},
         "reference_printed_fidelity": {"ghz": 0.9570522876374276, "grover": 0.1071574284590638,
                                        "qft": 0.6470482939691747}[a.circuit],
         "roofline": {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # DRAM traffic per launch = ratio measured by ncu x the algorithmic bytes of THIS run's launches
                      # (ncu cannot run inside the timed bench: a number taken under a profiler is not a bench value)
-                     "traffic": 0.995 * 32.0 * amps / max(n_pass, 1),
+                     "traffic": 0.989 * 32.0 * amps / max(n_pass, 1),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, 2026-10-20, same command "
-                                       "at 16384 shots (profiles/r02k_summary.md): 8.550 GB per launch of 262144 tiles against "
-                                       "262144 x 16 KiB x 2 = 8.590 GB algorithmic -> ratio 0.995 (65536-tile launches: 0.986); "
-                                       "scaled to this run's launch size",
-                     "note": "fused passes (~15 micro-ops each incl. the per-shot classical timeline instructions; measurements "
-                             "resolved on chip through cluster DSMEM) are bound by on-chip work (issue slots 36-40 % busy, FP64 "
-                             "pipe 7-15 %, 88 % of executed instructions are address / control / classical-machine overhead: "
-                             "profiles/r02k_summary.md), not by HBM; see roofline_single_gate for the HBM-bound regime",
+                                       "at 16384 shots (profiles/r02w_summary.md): 2.124 GB per launch of 32768 tiles of 32 KiB "
+                                       "against 32768 x 32 KiB x 2 = 2.147 GB algorithmic -> ratio 0.989; scaled to this run's "
+                                       "launch size",
+                     "note": "algorithmic bytes = 32 B x live elements of rho per pass AFTER the flush-time rewrite that fuses "
+                             "inject -> CNOT -> measure-and-discard runs (the first comm qubit of a remote gate never goes live): "
+                             "the same step needed 5x the bytes and 292 passes before (9.6 TB -> 1.3 TB per 1e5 shots), so "
+                             "`achieved` fell while shots/s rose 3.7x.  The ~22-op passes (fused measurements resolved through "
+                             "cluster DSMEM, per-shot classical timeline, group sweeps) are bound by on-chip latency (issue slots "
+                             "~34 % busy; short-scoreboard 24 %, fixed-latency 21 %, barrier 18 % of stall samples: "
+                             "profiles/r02w_summary.md), not by HBM; see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
                      "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),

@@ -69,6 +69,16 @@ struct PlannedPass {
 
 thread_local std::string g_create_error;
 
+// the last whole-program flush, kept for dqe_replay: the same program on the next batch of shots needs neither
+// the host walk nor the planner again
+struct CachedPlan {
+  std::vector<PlannedPass> passes;
+  std::vector<MicroOp> dev_ops;
+  std::vector<double2> dev_consts;
+  uint64_t live_axes, planned_live, draw;
+  int64_t api_ops;
+};
+
 }  // namespace
 
 struct dqe_engine {
@@ -119,6 +129,10 @@ struct dqe_engine {
   int ladder;               // ket: controlled-phase stars (OP_LADDER) built from the queued diagonal tables at flush
   int64_t ladders_built;
   int pass_ops;             // planner: micro-op budget of a pass (<= kMaxOpsPerPass)
+  int plan_cache;           // keep the plan of a flush that ran a whole program from a fresh register (dqe_replay)
+  CachedPlan* cached;
+  int64_t api_mark;         // stats[4] at the last reinit
+  bool fresh;               // nothing has been launched since the last reinit
   int tile_auto;            // small dm registers (P <= 14): the planner picks tile and CTA size per pass (tile_bits_for)
   int catfuse;              // dm: inject -> interact -> measure-and-discard runs fused at flush (fuse_cat_measure)
   int64_t cat_fused;
@@ -2583,12 +2597,24 @@ int do_flush(dqe_t* h, bool partial) {
       return fail(h, DQE_EINVAL, "classical registers used before any classical instruction");
     }
   }
+  const bool whole_program = h->fresh;   // first launch since the register was reinitialised
+  h->fresh = false;
   const int rc_launch = launch_passes(h, pl);
   // whatever happened, the queued ops are gone: either they ran, or a CUDA error made the handle unusable
   // (sticky); re-applying ops that already ran on the next flush would be worse than either
   if (rc_launch) keep_from = h->queue.size();
   drop_done();
   if (rc_launch) return rc_launch;
+  if (h->plan_cache && !partial && whole_program) {   // a whole program from a fresh register: replayable
+    if (!h->cached) h->cached = new CachedPlan();
+    h->cached->passes = pl.passes;
+    h->cached->dev_ops = pl.dev_ops;
+    h->cached->dev_consts = pl.dev_consts;
+    h->cached->live_axes = h->live_axes; h->cached->planned_live = h->planned_live; h->cached->draw = h->draw;
+    h->cached->api_ops = h->stats[4] - h->api_mark;
+  } else if (h->cached && !h->plan_cache) {
+    delete h->cached; h->cached = nullptr;
+  }
   if (getenv("DQE_DEBUG"))
     fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
             (long long)h->tmap_used, (long long)h->tmap_refused);
@@ -2753,7 +2779,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
-  h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->plan_cache = 0; h->cached = nullptr; h->api_mark = 0; h->fresh = true; h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -2822,6 +2848,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
 }
 
 int dqe_destroy(dqe_t* h) {
+  if (h && h->cached) { delete h->cached; h->cached = nullptr; }
   if (!h) return 0;
   if (h->device < 0) { delete h; return 0; }
   cudaSetDevice(h->device);
@@ -2849,7 +2876,7 @@ int dqe_reinit(dqe_t* h) {
   h->queue.clear(); h->cpool.clear();
   // support of the state on the device: live mask at the head of the (dropped) queue, plus whatever is live now
   const uint64_t was_live = h->planned_live | phys_live(h, h->live_axes | h->pin_axes);
-  h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1;
+  h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1; h->api_mark = h->stats[4]; h->fresh = true;
   // the next batch draws from the next block of global shot ids: reinit alone must not replay the stream
   h->shot_offset += (uint64_t)h->batch * (uint64_t)h->shot_stride;
   if (h->device < 0) return 0;
@@ -3320,6 +3347,36 @@ int64_t dqe_draw_count(dqe_t* h) { return h ? (int64_t)h->draw : -1; }
 
 int dqe_flush(dqe_t* h) { return do_flush(h); }
 
+int dqe_replay(dqe_t* h) {
+  if (int rc = check_ready(h)) return rc;
+  if (h->device < 0) return fail(h, DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state");
+  if (!h->cached) return fail(h, DQE_EINVAL, "replay: no cached plan (set the plan_cache option and flush a whole program first)");
+  if (!h->queue.empty() || !h->fresh || h->live_axes != 0 || h->draw != 0)
+    return fail(h, DQE_EINVAL, "replay: the register must be fresh (dqe_reinit) and the queue empty");
+  CachedPlan& c = *h->cached;
+  CK(cudaSetDevice(h->device));
+  if (c.dev_ops.size() > h->d_ops_cap || c.dev_consts.size() > h->d_consts_cap)
+    return fail(h, DQE_EINVAL, "replay: device program buffers were released");
+  for (PlannedPass& P : c.passes) {   // the one thing that changes from batch to batch: the shots' Philox counters
+    if (P.is_finish) { P.fp.seed = h->seed; P.fp.shot_offset = h->shot_offset; }
+    else { P.pp.seed = h->seed; P.pp.shot_offset = h->shot_offset; P.pp.creg_out = nullptr; P.pp.rec_out = nullptr; P.pp.treg_out = nullptr; }
+  }
+  h->stats[6] += (int64_t)(c.dev_ops.size() * sizeof(MicroOp) + c.dev_consts.size() * sizeof(double2));
+  if (!c.dev_ops.empty())
+    CK(cudaMemcpyAsync(h->d_ops, c.dev_ops.data(), c.dev_ops.size() * sizeof(MicroOp), cudaMemcpyHostToDevice, h->stream));
+  if (!c.dev_consts.empty())
+    CK(cudaMemcpyAsync(h->d_consts, c.dev_consts.data(), c.dev_consts.size() * sizeof(double2), cudaMemcpyHostToDevice,
+                       h->stream));
+  Planner pl;
+  pl.h = h;
+  pl.passes = c.passes;
+  h->fresh = false;
+  if (int rc = launch_passes(h, pl)) return rc;
+  h->live_axes = c.live_axes; h->planned_live = c.planned_live; h->draw = c.draw;
+  h->stats[4] += c.api_ops;
+  return 0;
+}
+
 #define NEED_DEVICE(h) do { if ((h) && (h)->device < 0) return fail((h), DQE_EUNSUPPORTED, "plan-only handle (device < 0) has no state"); } while (0)
 
 int dqe_sync(dqe_t* h) {
@@ -3634,6 +3691,7 @@ int dqe_probs_diag(dqe_t* h, int npairs, const int* a, const int* b, const int* 
 int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   if (!h || !key) return DQE_EINVAL;
   if (int rc = do_flush(h)) return rc;
+  if (h->cached) { delete h->cached; h->cached = nullptr; }   // planned under the old options
   if (!strcmp(key, "tile_bits")) {
     if (value < 4 || value > 13) return fail(h, DQE_EINVAL, "tile_bits in [4, 13]");
     h->tile_bits = (int)value; h->tile_auto = 0;
@@ -3653,6 +3711,8 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     h->pin_axes = (uint64_t)value;
   } else if (!strcmp(key, "kblock")) {
     h->kblock = value ? 1 : 0;
+  } else if (!strcmp(key, "plan_cache")) {
+    h->plan_cache = value ? 1 : 0;
   } else if (!strcmp(key, "pass_ops")) {
     if (value < 4 || value > kMaxOpsPerPass) return fail(h, DQE_EINVAL, "pass_ops in [4, 48]");
     h->pass_ops = (int)value;

@@ -73,6 +73,7 @@ ABI = {
                                          ctypes.POINTER(ctypes.c_int8)]),
     "dqe_draw_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "dqe_flush": (ctypes.c_int, [ctypes.c_void_p]),
+    "dqe_replay": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "dqe_read_creg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int8)]),
     "dqe_read_creg_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
@@ -210,6 +211,8 @@ class Engine:
 
     def set_option(self, key, value):
         self._ck(self._lib.dqe_set_option(self._h, key.encode(), int(value)))
+        if key != "plan_cache":
+            self._shot_batch_plan = None   # the library dropped its cached plan too (experiment.run_shot_batch)
 
     def seed(self, seed, shot_offset=0):
         self._ck(self._lib.dqe_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(shot_offset)))
@@ -357,6 +360,11 @@ class Engine:
 
     def sync(self):
         self._ck(self._lib.dqe_sync(self._h))
+
+    def replay(self):
+        """Launch the cached plan of the last whole-program flush on the freshly reinitialised register
+        (option ``plan_cache``; include/dqc_engine.h: dqe_replay)."""
+        self._ck(self._lib.dqe_replay(self._h))
 
     def read_creg(self, bit):
         out = np.empty(self.batch, dtype=np.int8)

@@ -55,17 +55,33 @@ class ShotBatchResult:
 
 
 def run_shot_batch(qpu_ops, dqc, engine, data_qubits, ideal_ket, before_flush=None, after_launch=None,
-                   comm_axes_low=0, per_shot_time=True):
+                   comm_axes_low=0, per_shot_time=True, reuse_plan=True):
     """One batch of shots: reset the register (``reinit`` also moves on to the next block of global shot
     ids, so consecutive batches are independent samples), walk the compiled op lists (enqueue only), flush
     the gate queue as fused passes, then read per-shot fidelity <phi|rho_S|phi> and the classical registers
-    back to the host.  Every shot follows its own simulated timeline (``per_shot_time``)."""
+    back to the host.  Every shot follows its own simulated timeline (``per_shot_time``).
+
+    ``reuse_plan``: the next batch of the SAME program (same op-list and hardware objects, same options) on the
+    same engine skips the executor walk and the planner: the engine replays the passes it planned for the first
+    batch on the new block of shot ids (``dqe_replay``; the micro-program is uploaded again, nothing else moves)."""
     engine.reinit()
-    ex = executor.DQCExecutor(qpu_ops, dqc, engine, comm_axes_low=comm_axes_low, per_shot_time=per_shot_time).run()
-    axes = ex.axes_of(data_qubits)
-    if before_flush:
-        before_flush()
-    engine.flush()
+    key = (id(qpu_ops), id(dqc), comm_axes_low, per_shot_time)
+    cache = getattr(engine, "_shot_batch_plan", None) if reuse_plan and hasattr(engine, "replay") else None
+    if cache is not None and cache[0] == key:
+        _, axes, ex = cache
+        if before_flush:
+            before_flush()
+        engine.replay()
+    else:
+        if reuse_plan and hasattr(engine, "replay"):
+            engine.set_option("plan_cache", 1)
+        ex = executor.DQCExecutor(qpu_ops, dqc, engine, comm_axes_low=comm_axes_low, per_shot_time=per_shot_time).run()
+        axes = ex.axes_of(data_qubits)
+        if before_flush:
+            before_flush()
+        engine.flush()
+        if reuse_plan and hasattr(engine, "replay"):
+            engine._shot_batch_plan = (key, axes, ex)
     if after_launch:
         after_launch()
     fid = engine.fidelity_ket_all(axes, ideal_ket)

@@ -194,6 +194,13 @@ int64_t dqe_draw_count(dqe_t* h);
 
 /* ---- execution + read-out ------------------------------------------------------------------ */
 int dqe_flush(dqe_t* h);                 /* plan + launch everything queued (asynchronous) */
+/* Run the SAME program on the next batch of shots without walking it again.  With the option plan_cache = 1 a flush
+ * that executed a whole program on a fresh register (dqe_reinit ... dqe_flush) keeps its planned passes; after the next
+ * dqe_reinit, dqe_replay re-uploads the micro-program, launches those passes for the new block of global shot ids and
+ * leaves the handle (live axes, draw counter) as the original walk left it.  The reference runs one subprocess per
+ * shot and rebuilds everything each time (docs/source/getting_started.rst:683-770); a shot batch re-plans nothing.
+ * Errors: no cached plan, queue not empty, register not fresh.  Any dqe_set_option drops the cached plan. */
+int dqe_replay(dqe_t* h);
 int dqe_sync(dqe_t* h);                  /* flush + wait for the stream */
 int dqe_read_creg(dqe_t* h, int bit, int8_t* out /*batch*/);
 int dqe_read_creg_words(dqe_t* h, uint64_t* out /*batch*/);

@@ -825,3 +825,29 @@ def test_peer_memory_axis_swap(L):
     g, l = (idx >> m) & 1, (idx >> L) & 1
     src = (idx & ~((1 << m) | (1 << L))) | (l << m) | (g << L)     # swap bits m and L
     assert np.array_equal(got, psi[src])
+
+
+def test_replayed_plan_equals_a_fresh_walk():
+    """experiment.run_shot_batch keeps the plan of the first batch and replays it on the next block of shot ids
+    (dqe_replay): batch by batch the same classical registers and fidelities as an engine that walks and plans the
+    program again every time."""
+    from dqc_simulator_b200 import experiment
+
+    ops, _ = experiment.load_c2("qft")
+    dqc = experiment.c2_hardware(noisy=True)
+    data, ideal = experiment.ideal_output_ket(ops, lambda f, n, b: _engine(f, n, b))
+    a = _engine("dm", 7, 64, seed=5, shot_offset=0)
+    b = _engine("dm", 7, 64, seed=5, shot_offset=0)
+    for batch in range(3):
+        ra = experiment.run_shot_batch(ops, dqc, a, data, ideal)                      # batches 1, 2: replayed
+        rb = experiment.run_shot_batch(ops, dqc, b, data, ideal, reuse_plan=False)    # walked every time
+        assert np.array_equal(ra.creg, rb.creg), batch
+        assert np.array_equal(ra.fidelity, rb.fidelity), batch
+        assert sorted(a.live) == sorted(b.live)
+    assert a.stats()["api_ops"] == b.stats()["api_ops"]
+    with pytest.raises(Exception, match="fresh"):
+        a.replay()                                   # not reinitialised
+    a.set_option("cxperm", 1)                        # any option change drops the plan
+    a.reinit()
+    with pytest.raises(Exception, match="no cached plan"):
+        a.replay()

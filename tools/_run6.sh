@@ -1,11 +1,5 @@
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02v_gputests.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02w_gputests.log 2>&1
 echo tests rc=$?
-tail -3 gpurun_out/r02v_gputests.log
-for cfg in "" "--circuit qft" "--noise depol+dephase"; do
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline $cfg 2>&1 | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l);print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['ms_per_step'],d['mean_fidelity'],d['passes_per_step'])
-    else: print(l[:300])"
-done
+tail -3 gpurun_out/r02w_gputests.log
+python bench.py --steps 3 --warmup 3 > gpurun_out/r02w_bench_default.json 2>gpurun_out/r02w_bench.err; python -c "
+import json;d=json.load(open('gpurun_out/r02w_bench_default.json'));print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['ms_per_step'],d['mean_fidelity'],d['passes_per_step'],d['cpu_baseline'])"
