@@ -878,16 +878,33 @@ __device__ __forceinline__ void cl_exec(const ClInstr in, const double c, double
 }
 // a run of instructions in order on one thread; the fetch of instruction i + 1 (and of its immediate) is issued
 // before instruction i executes, so the chain pays for the register-file round trips only
-__device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt, double* R, uint64_t& cw, const double* imm,
+// `cnt_flags` = MicroOp.flags of an OP_CLASSICAL: instruction count | (leading serial instructions << 8).  The serial
+// part (the clock chain) runs on every calling thread; the rest are exp() evaluations that feed channels only and are
+// independent of each other: with WARP = true (the callers inside k_tile_pass, whole warps on one shot) lane i takes the
+// i-th, so three idle-time strengths cost one exp() latency instead of three.
+template <bool WARP>
+__device__ __forceinline__ void cl_run(const ClInstr* ci, int cnt_flags, double* R, uint64_t& cw, const double* imm,
                                        uint64_t seed, uint64_t gshot) {
+  const int cnt = cnt_flags & 0xff;
+  const int ns = WARP ? min((cnt_flags >> 8) & 0xff, cnt) : cnt;
   if (cnt <= 0) return;
-  ClInstr nxt = ci[0];
-  double cn = imm[nxt.imm];
-  for (int i = 0; i < cnt; ++i) {
-    const ClInstr in = nxt;
-    const double c = cn;
-    if (i + 1 < cnt) { nxt = ci[i + 1]; cn = imm[nxt.imm]; }
-    cl_exec(in, c, R, cw, imm, seed, gshot);
+  if (ns > 0) {
+    ClInstr nxt = ci[0];
+    double cn = imm[nxt.imm];
+    for (int i = 0; i < ns; ++i) {
+      const ClInstr in = nxt;
+      const double c = cn;
+      if (i + 1 < ns) { nxt = ci[i + 1]; cn = imm[nxt.imm]; }
+      cl_exec(in, c, R, cw, imm, seed, gshot);
+    }
+  }
+  if (WARP && cnt > ns) {
+    __syncwarp();
+    for (int k = ns + (int)(threadIdx.x & 31u); k < cnt; k += 32) {
+      const ClInstr in = ci[k];
+      cl_exec(in, imm[in.imm], R, cw, imm, seed, gshot);
+    }
+    __syncwarp();
   }
 }
 
@@ -1252,6 +1269,10 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
   // 1. this tile's partials (same arithmetic as op_probs)
   double a0 = 0.0, a1 = 0.0;
   const int abit = op.aux;
+  // fused runs whose tile holds at most 32 diagonal groups: warp 0 alone evaluates and reduces them, the other warps
+  // go straight to the cluster barrier (no block-wide reduction, no barrier in front of the DSMEM push)
+  bool solo = false;
+  if constexpr (FORM == 1) solo = op.nb == 4 && !(op.lctrl2 >> 31) && (op.lctrl2 & 0xffu) <= 5u;
   if constexpr (FORM == 0) {
     const int jb = op.b[0];
     if (jb >= kOuter) {
@@ -1267,24 +1288,33 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     }
   } else {
     if (op.nb == 4) {   // fused runs
-      if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
-      else catm_partials(tile, T, op, pp, cs, base, a0, a1);
+      if (!solo || threadIdx.x < 32u) {
+        if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
+        else catm_partials(tile, T, op, pp, cs, base, a0, a1);
+      }
     }
     else dm_diag_partials(tile, pp, base, abit, (int)(int8_t)op.b[1], a0, a1);
   }
+  if (!solo || threadIdx.x < 32u) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
+  if (!solo) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
+  }
   if (mcount == 0) cluster_wait();   // completes the arrive of the kernel prologue
-  __syncthreads();
+  if (!solo) __syncthreads();
   const unsigned nr = cluster.num_blocks();
   if (threadIdx.x == 0) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+    double s0 = a0, s1 = a1;
+    if (!solo) {
+      s0 = 0.0; s1 = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
+    }
     // 2. push to every CTA of the shot (own slot included)
     const unsigned me = cluster.block_rank();
     for (unsigned r = 0; r < nr; ++r) {
@@ -1319,7 +1349,7 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     // the classical block hoisted behind this measurement runs right here (planner flag): no dispatch and no
     // barrier of its own; CTAs of four warps let warp 0 run it while the other warps already write the output block
     if (blockDim.x <= 64u || threadIdx.x < 32u) {
-      cl_run(cl_payload(*next_op), next_op->flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+      cl_run<true>(cl_payload(*next_op), next_op->flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
              pp.shot_offset + shot);
       if (threadIdx.x == 0) *s_cw = cw;
     }
@@ -2006,15 +2036,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           // has stored itself -- so the block needs no barrier at all (the barrier that ended the previous
           // micro-op already ordered it behind every earlier reader of the registers it overwrites).
           if (hdr_coff & 2) __syncthreads();   // block right behind another span's block (fence only in between)
-          cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
-                 pp.shot_offset + shot);
+          cl_run<true>(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+                       pp.shot_offset + shot);
           continue;
         }
         // four or more warps: warp 0 runs the block for the CTA (the chain is latency, not throughput: the other
         // warps would only burn issue slots on identical work), the classical word comes back through shared memory
         if (threadIdx.x < 32u) {
-          cl_run(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
-                 pp.shot_offset + shot);
+          cl_run<true>(cl_payload(op), op_flags, s_treg, cw, reinterpret_cast<const double*>(s_consts), pp.seed,
+                       pp.shot_offset + shot);
           if (threadIdx.x == 0) s_cw = cw;
         }
         __syncthreads();
@@ -2238,7 +2268,7 @@ __global__ void __launch_bounds__(128) k_classical(const ClassicalParams cp) {
   double* R = cp.treg + (uint64_t)shot * kTimeRegs;
   for (int k = 0; k < cp.nops; ++k) {
     const MicroOp& c = cp.ops[k];
-    cl_run(cl_payload(c), c.flags, R, cw, cp.imm, cp.seed, cp.shot_offset + (uint64_t)shot);
+    cl_run<false>(cl_payload(c), c.flags, R, cw, cp.imm, cp.seed, cp.shot_offset + (uint64_t)shot);
   }
   if (cw != cw0) cp.creg[shot] = cw;
 }

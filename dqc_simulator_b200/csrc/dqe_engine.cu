@@ -1777,22 +1777,29 @@ struct Planner {
       // one block in program order (every thread runs every instruction, so there is nothing to gain from
       // separating the clock chain from the exp() evaluations -- and a micro-op less to dispatch per span)
       MicroOp m;
-      int n = 0;
+      int n = 0, nserial = 0;
       auto open_op = [&]() {
         memset(&m, 0, sizeof(m));
         m.type = OP_CLASSICAL; m.pred_bit = -1;
-        n = 0;
+        n = 0; nserial = 0;
       };
       auto close_op = [&]() {
         if (n == 0) return;
         // the payload overlays the fields behind the 16-byte dispatch header; the marker rides in c_off
-        m.flags = n; m.c_off = need_barrier ? 2 : 0;
+        m.flags = n | (nserial << 8); m.c_off = need_barrier ? 2 : 0;
         need_barrier = false;
         dev_ops.push_back(m);
       };
       open_op();
-      for (size_t i = 0; i < ops.size(); ++i) {
+      // the clock chain first, in program order; the exp() evaluations behind it (they feed channels only --
+      // dqe_classical_op contract -- and are independent of each other: the kernel spreads them over lanes)
+      std::vector<size_t> order;
+      for (size_t i = 0; i < ops.size(); ++i) if (!(ops[i]->ci.op == CL_QEXP || ops[i]->ci.op == CL_QEXP2)) order.push_back(i);
+      for (size_t i = 0; i < ops.size(); ++i) if (ops[i]->ci.op == CL_QEXP || ops[i]->ci.op == CL_QEXP2) order.push_back(i);
+      for (size_t oi = 0; oi < order.size(); ++oi) {
+        const size_t i = order[oi];
         const HostOp* ho = ops[i];
+        if (!(ho->ci.op == CL_QEXP || ho->ci.op == CL_QEXP2)) nserial = n + 1;
         ClInstr ci = ho->ci;
         ci.imm = (uint16_t)(base + idx[i]);
         if (ci.op == CL_QEXP2 || ci.op == CL_GEOM) { const int i2 = base + idx2[i]; ci.cbit = (int8_t)(i2 & 0xff); ci.pad = (uint8_t)(i2 >> 8); }
@@ -2523,7 +2530,7 @@ int do_flush(dqe_t* h, bool partial) {
         if (m.type > 100) { fprintf(stderr, " %s%s.%d", gnames[m.type - 100], m.pred_bit >= 0 ? "?" : "", m.flags & 1); continue; }
         if (m.type == OP_GROUP && (m.flags & 17))
           fprintf(stderr, " [%s%s]", (m.flags & 1) ? "x>" : "", (m.flags & 16) ? ">x" : "");
-        if (m.type == OP_CLASSICAL) { fprintf(stderr, " CL%s%d", m.c_off ? "p" : "", m.flags); continue; }
+        if (m.type == OP_CLASSICAL) { fprintf(stderr, " CL%s%d", m.c_off ? "p" : "", m.flags & 0xff); continue; }
         if (m.type == OP_LADDER) {
           fprintf(stderr, " LADDER%s(%d;%d+%d)", m.pred_bit >= 0 ? "?" : "", (int)m.b[0], m.flags & 0xff, (m.flags >> 8) & 0xff);
           continue;
