@@ -390,3 +390,120 @@ def test_reinit_advances_the_shot_ids():
     e.set_option("shot_stride", 2)
     e.reinit()     # offset 0 -> 8
     e.reinit()     # -> 16: no error, the arithmetic itself is covered by the GPU twin
+
+
+# ---- fused remote-gate measurements: the host algebra, checked without a GPU ---------------------
+def _fused_tables(capfd, monkeypatch, build):
+    """Queue a program on a plan-only handle and return the fused measurement ops the flusher wrote
+    (DQE_DUMP_QUEUE: 'Q type=6 ... nb=4 ... b=rowA,rowY,colA,colY,A,Y,form,real c=<constants>')."""
+    monkeypatch.setenv("DQE_DUMP_QUEUE", "1")
+    e = engine.Engine("dm", 4, 1, device=-1, tile_bits=6)
+    build(e)
+    capfd.readouterr()
+    e.flush()
+    out = []
+    for ln in capfd.readouterr().err.splitlines():
+        if ln.startswith("Q type=6") and " nb=4 " in ln:
+            vals = [complex(*map(float, x.split(","))) for x in ln.split(" c=")[1].strip().split(";")]
+            out.append(np.array(vals))
+    return out, e.stats()
+
+
+def _unpack(vals, nt, rows, cols):
+    """(t_0, t_1, T_0, T_1) from the staged constants: complex tables, or real ones packed two doubles to an entry."""
+    t = vals[:2 * nt].reshape(2, nt)
+    body = vals[2 * nt:]
+    if len(body) == rows * cols:          # real-packed: 2 outcomes x rows x cols doubles
+        flat = np.stack([body.real, body.imag], axis=1).reshape(-1)
+        return t, flat.reshape(2, rows, cols).astype(complex)
+    return t, body.reshape(2, rows, cols)
+
+
+@pytest.mark.parametrize("complex_gate", [False, True])
+def test_fused_injecting_run_tables_equal_a_direct_simulation(capfd, monkeypatch, complex_gate):
+    """fuse_cat_measure (dqe_engine.cu): INJECT(x, y) -> [U on x] -> CNOT(A -> x) -> 2-qubit depolarising -> measure x
+    (flip e, discard) becomes ONE op with tables T_m (16 x 4) and functionals t_m.  Every column of T_m must equal the
+    direct density-matrix simulation of the same run on the matrix unit |rA'><cA'| of A (x) the injected pair."""
+    from dqc_simulator_b200 import hardware
+
+    W = np.asarray(hardware.werner_state(0.93), dtype=complex).reshape(4, 4)
+    p2, flip = 0.07, 0.04
+    cnot = np.eye(4)[[0, 1, 3, 2]]
+    rng = np.random.default_rng(3)
+    z = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    U = np.linalg.qr(z)[0] if complex_gate else np.eye(2)
+    A, x, y = 0, 3, 2
+
+    def build(e):
+        e.alloc_axis(A)
+        e.apply_1q(A, np.array([[1, 1], [1, -1]]) / np.sqrt(2))
+        e.inject_2q(x, y, W, True)
+        if complex_gate:
+            e.apply_1q(x, U)
+        e.apply_2q(A, x, cnot)
+        e.depolarize([A, x], p2)
+        e.measure(x, 0, -1, True, flip)
+
+    ops, st = _fused_tables(capfd, monkeypatch, build)
+    assert len(ops) == 1 and st["passes"] == 1
+    t, T = _unpack(ops[0], 4, 16, 4)
+    assert len(ops[0]) == (8 + 128 if complex_gate else 8 + 64)   # real tables are staged as packed doubles
+    # direct simulation on (A, x, y), A = most significant
+    I2 = np.eye(2)
+    CX = np.kron(cnot, I2)                       # control A, target x
+    Ux = np.kron(np.kron(I2, U), I2)
+    for j in range(4):
+        rA, cA = j >> 1, j & 1
+        E = np.zeros((2, 2), complex); E[rA, cA] = 1.0
+        rho = np.kron(E, W)                      # W indexed (x y)
+        rho = Ux @ rho @ Ux.conj().T
+        rho = CX @ rho @ CX.conj().T
+        r6 = rho.reshape(2, 2, 2, 2, 2, 2)       # rA rx ry cA cx cy
+        red = np.einsum("axyaxz->yz", r6)        # Tr over (A, x): what is left on y
+        mixed = np.einsum("ab,xc,yz->axybcz", I2 / 2, I2 / 2, red)
+        r6 = (1 - p2) * r6 + p2 * mixed
+        for m in range(2):
+            kept = (1 - flip) * r6[:, m, :, :, m, :] + flip * r6[:, 1 - m, :, :, 1 - m, :]   # rA ry cA cy
+            assert np.abs(T[m][:, j] - kept.reshape(16)).max() < 1e-14
+            assert abs(t[m][j] - np.einsum("ayay->", kept)) < 1e-14
+
+
+def test_fused_measure_out_run_tables_equal_a_direct_simulation(capfd, monkeypatch):
+    """Contracting form: constant ops on (A, x) right in front of a measure-and-discard of an EXISTING axis x fold into
+    the measurement (4 x 16 tables); per-shot or predicated ops end the run and stay outside."""
+    cnot = np.eye(4)[[0, 1, 3, 2]]
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    p2, p1, flip = 0.05, 0.02, 0.01
+    A, x = 1, 2
+
+    def build(e):
+        for a in (A, x):
+            e.alloc_axis(a)
+        e.apply_1q(A, h)
+        e.cond_1q(x, np.array([[0, 1], [1, 0]]), 5)      # predicated: must stay outside the fused op
+        e.apply_2q(x, A, cnot)                           # control x, target A
+        e.depolarize([x, A], p2)
+        e.apply_1q(x, h)
+        e.depolarize([x], p1)
+        e.measure(x, 1, -1, True, flip)
+
+    ops, st = _fused_tables(capfd, monkeypatch, build)
+    assert len(ops) == 1
+    t, T = _unpack(ops[0], 16, 4, 16)
+    CX = np.zeros((4, 4))
+    for a in range(2):
+        for b in range(2):
+            CX[(a ^ b) * 2 + b, a * 2 + b] = 1.0         # index (A x): control x, target A
+    Hx = np.kron(np.eye(2), h)
+    for i in range(16):
+        rA, rx, cA, cx = (i >> 3) & 1, (i >> 2) & 1, (i >> 1) & 1, i & 1
+        rho = np.zeros((4, 4), complex); rho[rA * 2 + rx, cA * 2 + cx] = 1.0
+        rho = CX @ rho @ CX.T
+        rho = (1 - p2) * rho + p2 * np.trace(rho) * np.eye(4) / 4
+        rho = Hx @ rho @ Hx.T
+        r4 = rho.reshape(2, 2, 2, 2)                     # rA rx cA cx
+        r4 = (1 - p1) * r4 + p1 * np.einsum("axbx->ab", r4)[:, None, :, None] * (np.eye(2) / 2)[None, :, None, :]
+        for m in range(2):
+            kept = (1 - flip) * r4[:, m, :, m] + flip * r4[:, 1 - m, :, 1 - m]
+            assert np.abs(T[m][:, i] - kept.reshape(4)).max() < 1e-14
+            assert abs(t[m][i] - np.trace(kept)) < 1e-14
