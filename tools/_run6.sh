@@ -1,7 +1,8 @@
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02x_gputests.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02y_gputests.log 2>&1
 echo tests rc=$?
-tail -3 gpurun_out/r02x_gputests.log
-for cfg in "" "--circuit qft" "--noise depol+dephase"; do
+tail -3 gpurun_out/r02y_gputests.log
+for cfg in "" "--opt catfuse=2" "--circuit qft" "--noise depol+dephase"; do
+echo "== $cfg"
 python bench.py --steps 3 --warmup 2 --no-cpu-baseline $cfg 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
