@@ -120,7 +120,7 @@ constexpr int kMaxOpsPerPass = 48;
 // pass asks for what it uses (PassParams::nconsts), so the cap costs nothing: an ordinary dm pass stages ~1 KiB (eight
 // 16 KiB-tile CTAs per SM), one that carries fused-measurement tables ~5 KiB
 constexpr int kMaxConstsKet = 512;
-constexpr int kMaxConstsDm = 512;
+constexpr int kMaxConstsDm = 768;
 __host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMaxConstsKet : kMaxConstsDm; }
 constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
@@ -1241,6 +1241,93 @@ __device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroO
   }
 }
 
+// ---- whole remote gate on the data pair (A, B) (host: try_fuse_whole_at).  Constants (double2 units; all tables real,
+// packed two doubles to an entry): K[m1][pred][order][64] at 0, T2[m2][64] at 256, t2[m2][16] at 320, then scratch the
+// kernel fills per CTA: u[2][16] (as double2 with y = 0) at 336, C[256 doubles] at 368.  aux = creg bit of m1 |
+// (predicate bit + 1) << 8 | (register of the per-shot strength q + 1) << 16.
+constexpr int kWhK = 0, kWhT2 = 256, kWht2 = 320, kWhU = 336, kWhC = 368;
+__device__ __forceinline__ const double* whole_K(const MicroOp& op, const double2* cs, uint64_t cw, const double* treg,
+                                                  double& q) {
+  const int m1 = (int)((cw >> (op.aux & 0xff)) & 1ull);
+  const int pb = ((op.aux >> 8) & 0xff) - 1, qr = ((op.aux >> 16) & 0xff) - 1;
+  const int pv = pb >= 0 ? (int)((cw >> pb) & 1ull) : 0;
+  q = qr >= 0 ? treg[qr] : 0.0;
+  return reinterpret_cast<const double*>(cs + kWhK) + ((m1 * 2 + pv) * 2) * 64;   // K0 here, K1 64 doubles on
+}
+// u_m2[(rA' cA' rB' cB')] = sum_{ry cy} t2_m2[(rB' ry cB' cy)] sum_a K[(a a ry cy), (rA' cA')]: the functional that gives
+// p(m2 | m1) on the group's 16 elements; threads 0-31 write one entry each
+__device__ __noinline__ void whole_build_u(const MicroOp& op, double2* cs, uint64_t cw, const double* treg) {
+  if (threadIdx.x >= 32u) return;
+  double q;
+  const double* K0 = whole_K(op, cs, cw, treg, q);
+  const int m2 = threadIdx.x >> 4, c = threadIdx.x & 15;
+  const int rA = (c >> 3) & 1, rB = (c >> 2) & 1, cA = (c >> 1) & 1, cB = c & 1;
+  const double* t2 = reinterpret_cast<const double*>(cs + kWht2) + 16 * m2;
+  double acc = 0.0;
+#pragma unroll
+  for (int yy = 0; yy < 4; ++yy) {
+    double kd = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int k = ((a * 2 + a) * 4 + yy) * 4 + (rA * 2 + cA);
+      kd += fma(q, K0[64 + k], K0[k]);
+    }
+    acc = fma(t2[rB * 8 + (yy >> 1) * 4 + cB * 2 + (yy & 1)], kd, acc);
+  }
+  cs[kWhU + threadIdx.x] = make_double2(acc, 0.0);
+}
+// C[(rA cA rB cB), (rA' cA' rB' cB')] = sum_{ry cy} T2_m2[(rB cB), (rB' ry cB' cy)] K[(rA cA ry cy), (rA' cA')], in the
+// element order of the (A, B) group: e = rA * 8 + rB * 4 + cA * 2 + cB
+__device__ __noinline__ void whole_build_C(const MicroOp& op, double2* cs, uint64_t cw_in, const double* treg, int m2) {
+  double q;
+  const double* K0 = whole_K(op, cs, cw_in, treg, q);
+  const double* T2 = reinterpret_cast<const double*>(cs + kWhT2) + 64 * m2;
+  double* C = reinterpret_cast<double*>(cs + kWhC);
+  for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) {
+    const int eo = t >> 4, ei = t & 15;
+    const int rA = (eo >> 3) & 1, rB = (eo >> 2) & 1, cA = (eo >> 1) & 1, cB = eo & 1;
+    const int rA2 = (ei >> 3) & 1, rB2 = (ei >> 2) & 1, cA2 = (ei >> 1) & 1, cB2 = ei & 1;
+    double acc = 0.0;
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+      const int k = ((rA * 2 + cA) * 4 + yy) * 4 + (rA2 * 2 + cA2);
+      acc = fma(T2[(rB * 2 + cB) * 16 + rB2 * 8 + (yy >> 1) * 4 + cB2 * 2 + (yy & 1)], fma(q, K0[64 + k], K0[k]), acc);
+    }
+    C[t] = acc;
+  }
+}
+// every group of the tile: out = scale * C in (a dense real 16 x 16 matrix against 16 complex elements)
+__device__ __noinline__ void whole_apply(double2* tile, uint32_t T, const MicroOp& op, const double2* cs, const MeasRec& r) {
+  int s4[4];
+  sort4(op.b, s4);
+  const uint32_t mrA = 1u << op.b[0], mrB = 1u << op.b[1], mcA = 1u << op.b[2], mcB = 1u << op.b[3];
+  const double2* __restrict__ C = cs + kWhC;   // row e: 16 doubles = 8 double2
+  const double sc = r.scale;
+  for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
+    const uint32_t i0 = ins0_4(q, s4);
+    double2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = cscale(tile[i0 | ((i & 8) ? mrA : 0u) | ((i & 4) ? mrB : 0u) | ((i & 2) ? mcA : 0u) | ((i & 1) ? mcB : 0u)], sc);
+#pragma unroll 2
+    for (int e = 0; e < 16; ++e) {
+      const double2* __restrict__ row = C + 8 * e;
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double2 c = row[i];
+        acc.x = fma(c.x, v[2 * i].x, acc.x); acc.y = fma(c.x, v[2 * i].y, acc.y);
+        acc.x = fma(c.y, v[2 * i + 1].x, acc.x); acc.y = fma(c.y, v[2 * i + 1].y, acc.y);
+      }
+      tile[i0 | ((e & 8) ? mrA : 0u) | ((e & 4) ? mrB : 0u) | ((e & 2) ? mcA : 0u) | ((e & 1) ? mcB : 0u)] = acc;
+    }
+  }
+}
+// form 3: the first measurement of a whole remote gate only renormalises (its map T1_m1 is applied by form 2 later)
+__device__ __noinline__ void whole_rescale(double2* tile, uint32_t T, double sc) {
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) tile[i] = cscale(tile[i], sc);
+}
+
 // split-phase cluster barrier (arrive at kernel start, wait before the first DSMEM write: every CTA of
 // the cluster is then known to be running, and nobody stalls for it)
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
@@ -1288,8 +1375,13 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     }
   } else {
     if (op.nb == 4) {   // fused runs
+      if (op.b[6] == 2) {   // whole remote gate: the functional of p(m2 | m1) is built per CTA first
+        whole_build_u(op, const_cast<double2*>(cs), cw, s_treg);
+        if (solo) __syncwarp(); else __syncthreads();
+      }
       if (!solo || threadIdx.x < 32u) {
-        if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
+        if (op.b[6] == 2) catm2_partials(tile, T, op, pp, cs + kWhU, base, a0, a1);
+        else if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
         else catm_partials(tile, T, op, pp, cs, base, a0, a1);
       }
     }
@@ -1343,6 +1435,12 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     if (pp.olog && cluster.block_rank() == 0) pp.olog[op.octrl * (uint64_t)pp.batch + shot] = (int8_t)m;
   }
   __syncthreads();
+  if constexpr (FORM == 1) {
+    if (op.nb == 4 && op.b[6] == 2) {   // the 16 x 16 matrix of the drawn outcome (selectors: the word from before this bit)
+      whole_build_C(op, const_cast<double2*>(cs), cw, s_treg, mrec->outcome);
+      __syncthreads();
+    }
+  }
   const int cbit = op.flags - 1;
   if (cbit >= 0) cw = (cw & ~(1ull << cbit)) | ((uint64_t)mrec->outcome << cbit);
   if (op.lctrl2 & kMeasRunsClassical) {
@@ -1356,7 +1454,9 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
   }
   if constexpr (FORM == 1) {
     if (op.nb == 4) {   // the output block of the drawn outcome, renormalised
-      if (op.b[6]) { if (op.b[7]) catm2_apply<true>(tile, T, op, cs, *mrec); else catm2_apply<false>(tile, T, op, cs, *mrec); }
+      if (op.b[6] == 3) whole_rescale(tile, T, mrec->scale);
+      else if (op.b[6] == 2) whole_apply(tile, T, op, cs, *mrec);
+      else if (op.b[6]) { if (op.b[7]) catm2_apply<true>(tile, T, op, cs, *mrec); else catm2_apply<false>(tile, T, op, cs, *mrec); }
       else { if (op.b[7]) catm_apply<true>(tile, T, op, cs, *mrec); else catm_apply<false>(tile, T, op, cs, *mrec); }
     }
   }

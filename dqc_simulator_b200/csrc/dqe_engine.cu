@@ -1403,6 +1403,173 @@ bool try_fuse_out_at(dqe_t* h, size_t jp) {
   return true;
 }
 
+// Third form (catfuse = 3): the WHOLE remote gate as two ops on the data pair (A, B) -- the second comm qubit y never
+// goes live either.  After the two rewrites above a cat-comm remote gate reads
+//     E = fused injecting measurement on (A, y)   ...   light ops on y   ...   C = fused contracting measurement on (B, y)
+// with, in between, only axis-local ops on y: constant ones, ONE predicate bit (the X correction of
+// dqc_control.py:347-348) and ONE per-shot idle-time channel D(q) = D0 + q D1 (depolarising / dephasing / Z flip).
+// Nothing in between may touch A or measure anything (the map T1_m1 on A is applied late, at C).  Then
+//     rho'[(rA cA rB cB)] = sum  T2_m2[(rB cB), (rB' ry cB' cy)]  K[(rA cA ry cy), (rA' cA')]  rho[(rA' cA' rB' cB')],
+//     K = Mid(pred, q) o T1_m1 = K0 + q K1   (per m1 and predicate value),
+// and both outcome distributions are linear functionals of the SAME 5-qubit state: p(m1) = t1_m1 (x) delta(rB, cB)
+// (op E', form 3: probabilities + renormalisation only), p(m2 | m1) = u_m2 built per CTA from t2_m2 and K (op W, form 2,
+// which then applies the 16 x 16 matrix C_m2 = T2_m2 K to every group).  Real tables only (complex ones keep the
+// two-op path).  Constants of W (double2 units): K[m1][pred][order][64 doubles] = 256, T2[m2][64 doubles] = 64,
+// t2[m2][16 doubles] = 16, then 160 of scratch (u: 32, C: 128) that the kernel fills.
+constexpr int kWholeK = 256, kWholeT2 = 64, kWholet2 = 16, kWholeScratch = 160;
+bool try_fuse_whole_at(dqe_t* h, size_t ie) {
+  std::vector<HostOp>& Q = h->queue;
+  const int n = h->nmax;
+  if (ie + 1 >= Q.size()) return false;
+  const HostOp& E = Q[ie];
+  const HostOp& fin1 = Q[ie + 1];
+  if (fin1.kind != 1 || fin1.creg_bit < 0 || !E.m.b[7]) return false;
+  const int A = E.m.b[4], y = E.m.b[5];
+  const uint64_t Ab = (1ull << A) | (1ull << (A + n)), yb = (1ull << y) | (1ull << (y + n));
+  struct Mid { cplx M[16]; int pred; int dyn_reg; int dyn_kind; };
+  std::vector<Mid> mids;
+  std::vector<size_t> mid_idx;
+  size_t jc = Q.size();
+  int pred_bit = -1, dyn_reg = -1;
+  for (size_t j = ie + 2; j < Q.size(); ++j) {
+    const HostOp& e = Q[j];
+    if (e.kind != 0) continue;
+    if (e.m.type == OP_PROBS) {
+      if (e.m.nb == 4 && e.m.b[6] == 1 && e.m.b[5] == y && e.m.b[7]) { jc = j; break; }
+      return false;   // another measurement in between would see the state without T1_m1 applied
+    }
+    const uint64_t tb = touched_bits(e);
+    if (tb & Ab) return false;
+    if (!(tb & yb)) continue;
+    if (tb & ~yb) return false;
+    Mid md;
+    md.pred = e.m.pred_bit; md.dyn_reg = -1; md.dyn_kind = 0;
+    if (e.m.type == OP_DYN1 && e.m.b[1] == y) {
+      if (e.m.pred_bit >= 0 || dyn_reg >= 0 || e.m.flags == DYN_AMPDAMP) return false;
+      md.dyn_reg = dyn_reg = e.m.aux; md.dyn_kind = e.m.flags;
+    } else if (axis_local_matrix(h, e, y, md.M)) {
+      if (e.m.pred_bit >= 0) {
+        if (pred_bit >= 0 && pred_bit != e.m.pred_bit) return false;
+        pred_bit = e.m.pred_bit;
+      }
+    } else {
+      return false;
+    }
+    mids.push_back(md);
+    mid_idx.push_back(j);
+  }
+  if (jc + 1 >= Q.size()) return false;
+  const HostOp& C = Q[jc];
+  const int B = C.m.b[4];
+  if (B == A || B == y) return false;
+  const uint64_t Bb = (1ull << B) | (1ull << (B + n));
+  if ((E.live_after & Bb) != Bb) return false;   // B must hold a qubit already when the first half runs
+  // tables of the two fused ops (real, packed two doubles to an entry)
+  auto dbl = [&](const HostOp& o, int first, int k) {   // k-th double of the packed block starting at constant `first`
+    const double2 v = h->cpool[o.m.c_off + first + k / 2];
+    return (k & 1) ? v.y : v.x;
+  };
+  double T1[2][64], T2[2][64], t1[2][4], t2[2][16];
+  for (int m = 0; m < 2; ++m) {
+    for (int k = 0; k < 64; ++k) { T1[m][k] = dbl(E, 8, 64 * m + k); T2[m][k] = dbl(C, 32, 64 * m + k); }
+    for (int k = 0; k < 4; ++k) t1[m][k] = h->cpool[E.m.c_off + 4 * m + k].x;
+    for (int k = 0; k < 16; ++k) t2[m][k] = h->cpool[C.m.c_off + 16 * m + k].x;
+  }
+  // Mid(pred, order): product of the mid ops in program order, the predicated ones present or not, the dynamic one
+  // replaced by D0 = identity (order 0) or D1 = dD/dq (order 1)
+  std::vector<double> K((size_t)kWholeK * 2, 0.0);
+  for (int pv = 0; pv < 2; ++pv)
+    for (int order = 0; order < 2; ++order) {
+      double Mid[16];
+      for (int i = 0; i < 16; ++i) Mid[i] = (i / 4 == i % 4) ? 1.0 : 0.0;
+      bool zero = order == 1 && dyn_reg < 0;   // no dynamic op: the q-linear part vanishes
+      for (const auto& md : mids) {
+        double L[16];
+        if (md.dyn_reg >= 0) {
+          for (int i = 0; i < 16; ++i) L[i] = 0.0;
+          if (order == 0) { for (int i = 0; i < 4; ++i) L[i * 5] = 1.0; }
+          else if (md.dyn_kind == DYN_DEPOL) {      // D(q) = (1 - q) Id + q R,  R: e00, e11 -> (e00 + e11) / 2, e01 = e10 = 0
+            for (int i = 0; i < 4; ++i) L[i * 5] = -1.0;
+            L[0 * 4 + 0] += 0.5; L[0 * 4 + 3] += 0.5; L[3 * 4 + 0] += 0.5; L[3 * 4 + 3] += 0.5;
+          } else {                                   // dephasing: e01, e10 *= (1 - q); Z flip with probability q: *= (1 - 2 q)
+            const double f = md.dyn_kind == DYN_DEPHASE ? -1.0 : -2.0;
+            L[1 * 4 + 1] = f; L[2 * 4 + 2] = f;
+          }
+        } else {
+          bool real_m = true;
+          for (int i = 0; i < 16; ++i) real_m = real_m && md.M[i].imag() == 0.0;
+          if (!real_m) return false;
+          const bool on = md.pred < 0 || pv == 1;
+          for (int i = 0; i < 16; ++i) L[i] = on ? md.M[i].real() : ((i / 4 == i % 4) ? 1.0 : 0.0);
+        }
+        double R[16];
+        for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += L[i * 4 + k] * Mid[k * 4 + j];
+            R[i * 4 + j] = acc;
+          }
+        for (int i = 0; i < 16; ++i) Mid[i] = R[i];
+      }
+      for (int m1 = 0; m1 < 2; ++m1)
+        for (int rA = 0; rA < 2; ++rA)
+          for (int cA = 0; cA < 2; ++cA)
+            for (int yy = 0; yy < 4; ++yy)        // (ry cy) of the output
+              for (int jn = 0; jn < 4; ++jn) {    // (rA' cA')
+                double acc = 0.0;
+                if (!zero)
+                  for (int y2 = 0; y2 < 4; ++y2) {  // (ry' cy')
+                    const int e1 = rA * 8 + (y2 >> 1) * 4 + cA * 2 + (y2 & 1);
+                    acc += Mid[yy * 4 + y2] * T1[m1][e1 * 4 + jn];
+                  }
+                K[(size_t)(((m1 * 2 + pv) * 2 + order) * 64) + ((rA * 2 + cA) * 4 + yy) * 4 + jn] = acc;
+              }
+    }
+  // ---- E': probabilities of m1 as a functional on the (A, B) group + renormalisation (form 3)
+  std::vector<cplx> KE(32 + 64, cplx(0.0));
+  for (int m = 0; m < 2; ++m)
+    for (int i = 0; i < 16; ++i) {
+      const int rA = (i >> 3) & 1, rB = (i >> 2) & 1, cA = (i >> 1) & 1, cB = i & 1;
+      KE[16 * m + i] = rB == cB ? t1[m][rA * 2 + cA] : 0.0;
+    }
+  HostOp e2 = E;
+  e2.m.b[0] = (uint8_t)(A + n); e2.m.b[1] = (uint8_t)(B + n); e2.m.b[2] = (uint8_t)A; e2.m.b[3] = (uint8_t)B;
+  e2.m.b[4] = (uint8_t)A; e2.m.b[5] = (uint8_t)B; e2.m.b[6] = 3; e2.m.b[7] = 1;
+  e2.need = Ab | Bb;
+  e2.live_after = E.live_after & ~yb;
+  e2.m.c_off = add_consts(h, KE.data(), 32); e2.nconst = 32;
+  HostOp f1 = fin1;
+  f1.live_after &= ~yb;
+  // ---- W: the second measurement and the whole map (form 2)
+  std::vector<cplx> KW((size_t)(kWholeK + kWholeT2 + kWholet2 + kWholeScratch), cplx(0.0));
+  for (int k = 0; k < kWholeK; ++k) KW[k] = cplx(K[2 * k], K[2 * k + 1]);
+  for (int m = 0; m < 2; ++m) {
+    for (int k = 0; k < 32; ++k) KW[kWholeK + 32 * m + k] = cplx(T2[m][2 * k], T2[m][2 * k + 1]);
+    for (int k = 0; k < 8; ++k) KW[kWholeK + kWholeT2 + 8 * m + k] = cplx(t2[m][2 * k], t2[m][2 * k + 1]);
+  }
+  HostOp w = C;
+  w.m.b[0] = (uint8_t)(A + n); w.m.b[1] = (uint8_t)(B + n); w.m.b[2] = (uint8_t)A; w.m.b[3] = (uint8_t)B;
+  w.m.b[4] = (uint8_t)A; w.m.b[5] = (uint8_t)B; w.m.b[6] = 2; w.m.b[7] = 1;
+  w.need = Ab | Bb;
+  w.m.aux = fin1.creg_bit | ((pred_bit + 1) << 8) | ((dyn_reg + 1) << 16);
+  w.m.c_off = add_consts(h, KW.data(), (int)KW.size()); w.nconst = (int)KW.size();
+  std::vector<HostOp> out;
+  out.reserve(Q.size());
+  size_t nm = 0;
+  for (size_t j = 0; j < Q.size(); ++j) {
+    if (nm < mid_idx.size() && mid_idx[nm] == j) { ++nm; continue; }
+    if (j == ie) { out.push_back(e2); continue; }
+    if (j == ie + 1) { out.push_back(f1); continue; }
+    if (j == jc) { out.push_back(w); continue; }
+    out.push_back(Q[j]);
+    if (j > ie && j < jc) out.back().live_after &= ~yb;
+  }
+  Q.swap(out);
+  h->stats[7] += (int64_t)mid_idx.size();
+  h->cat_fused++;
+  return true;
+}
+
 void fuse_cat_measure(dqe_t* h) {
   if (h->formalism != DQE_DM || !h->catfuse || !cat_cluster_mode(h)) return;
   for (size_t i = 0; i < h->queue.size(); ++i) {
@@ -1417,6 +1584,12 @@ void fuse_cat_measure(dqe_t* h) {
     if (o.kind != 0 || o.m.type != OP_PROBS || o.m.nb == 4) continue;
     const size_t before = h->queue.size();
     if (try_fuse_out_at(h, j)) j -= (before - h->queue.size()) - 1;   // the fused PROBS moved down by the absorbed ops; skip its finish
+  }
+  if (h->catfuse < 3) return;
+  for (size_t j = 0; j < h->queue.size(); ++j) {
+    const HostOp& o = h->queue[j];
+    if (o.kind != 0 || o.m.type != OP_PROBS || o.m.nb != 4 || o.m.b[6] != 0) continue;
+    try_fuse_whole_at(h, j);   // (E stays at index j, only ops behind it disappear)
   }
 }
 
@@ -2786,7 +2959,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
   h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
-  h->plan_cache = 0; h->cached = nullptr; h->api_mark = 0; h->fresh = true; h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 2; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
+  h->plan_cache = 0; h->cached = nullptr; h->api_mark = 0; h->fresh = true; h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 3; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
   if (device < 0) {  // plan-only handle: the queue and the planner run, nothing is launched
@@ -3724,7 +3897,7 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
     if (value < 4 || value > kMaxOpsPerPass) return fail(h, DQE_EINVAL, "pass_ops in [4, 48]");
     h->pass_ops = (int)value;
   } else if (!strcmp(key, "catfuse")) {
-    if (value < 0 || value > 2) return fail(h, DQE_EINVAL, "catfuse in {0 off, 1 inject runs, 2 inject + measure-out runs}");
+    if (value < 0 || value > 3) return fail(h, DQE_EINVAL, "catfuse in {0 off, 1 inject runs, 2 + measure-out runs, 3 + whole remote gates on the data pair}");
     h->catfuse = (int)value;
   } else if (!strcmp(key, "ladder")) {
     h->ladder = value ? 1 : 0;

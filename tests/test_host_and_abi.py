@@ -301,9 +301,11 @@ def test_program_instructions_overlap_on_free_positions():
 @pytest.mark.parametrize("case,n,want", [
     # per-shot timelines (round 2): the clock arithmetic rides along as classical instructions; cat-entangle runs
     # (inject -> CNOT -> measure-and-discard) and measure-out runs (CNOT -> H -> measure-and-discard) are fused at flush,
-    # the first comm qubit never goes live (Grover-5 was 292 passes / 4209 micro-ops before that rewrite)
-    ("c2_grover5_3qpu_cat.json", 7, dict(passes=101, micro_ops=2262, api_ops=5313, merged_ops=1941)),
-    ("c2_qft5_3qpu_cat.json", 7, dict(passes=15, micro_ops=342, api_ops=812, merged_ops=311)),
+    # and whole remote gates become two ops on the data pair: NO comm qubit ever goes live, every pass runs on the
+    # 5-qubit rho (Grover-5 was 292 passes / 4209 micro-ops / 3.0 M element updates per shot before these rewrites,
+    # 0.15 M now)
+    ("c2_grover5_3qpu_cat.json", 7, dict(passes=144, micro_ops=1832, api_ops=5313, merged_ops=2229)),
+    ("c2_qft5_3qpu_cat.json", 7, dict(passes=22, micro_ops=271, api_ops=812, merged_ops=355)),
     ("c4_qft16_mono.json.gz", 16, dict(passes=56, micro_ops=1182, api_ops=1564, merged_ops=521)),
 ])
 def test_planner_pass_counts_of_the_benchmark_circuits(case, n, want):
@@ -507,3 +509,100 @@ def test_fused_measure_out_run_tables_equal_a_direct_simulation(capfd, monkeypat
             kept = (1 - flip) * r4[:, m, :, m] + flip * r4[:, 1 - m, :, 1 - m]
             assert np.abs(T[m][:, i] - kept.reshape(4)).max() < 1e-14
             assert abs(t[m][i] - np.trace(kept)) < 1e-14
+
+
+def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
+    """catfuse = 3 (try_fuse_whole_at): a cat-comm remote gate -- pair (x, y), CNOT(A -> x), measure x; X on y if the
+    outcome was 1, per-shot idle noise D(q) on y; CNOT(y -> B), H(y), measure y -- becomes two ops on the DATA pair
+    (A, B); neither comm qubit goes live.  The 16 x 16 matrix C_m2 = T2_m2 (K0 + q K1) the kernel builds from the staged
+    tables must equal the direct density-matrix simulation for every (m1, m2) and two strengths q."""
+    from dqc_simulator_b200 import hardware, timeline as tl
+
+    W = np.asarray(hardware.werner_state(0.95), dtype=complex).reshape(4, 4)
+    cnot = np.eye(4)[[0, 1, 3, 2]]
+    Hm = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    X = np.array([[0, 1], [1, 0]], dtype=float)
+    p2a, p2b, p1, f1, f2, px = 0.03, 0.02, 0.01, 0.004, 0.006, 0.015
+    A, B, x, y = 0, 1, 3, 2
+    monkeypatch.setenv("DQE_DUMP_QUEUE", "1")
+    e = engine.Engine("dm", 4, 1, device=-1, tile_bits=6)
+    for a in (A, B):
+        e.alloc_axis(a)
+        e.apply_1q(a, Hm)
+    e.apply_2q(A, B, cnot)
+    e.classical_op(tl.CL_CONST, 5, imm=0.25)
+    e.inject_2q(x, y, W, True)
+    e.apply_2q(A, x, cnot); e.depolarize([A, x], p2a)
+    e.measure(x, 0, -1, True, f1)
+    e.set_predicate(0); e.depolarize([y], px); e.apply_1q(y, X); e.set_predicate(-1)
+    e.dyn_channel(y, tl.DYN_DEPOL, 5)
+    e.apply_2q(y, B, cnot); e.depolarize([y, B], p2b); e.apply_1q(y, Hm); e.depolarize([y], p1)
+    e.measure(y, 1, -1, True, f2)
+    capfd.readouterr()
+    e.flush()
+    err = capfd.readouterr().err
+    fused = [ln for ln in err.splitlines() if ln.startswith("Q type=6") and " nb=4 " in ln]
+    assert len(fused) == 2 and e.stats()["passes"] == 1
+    wl = [ln for ln in fused if ln.split(" c=")[1].count(";") > 100][0]
+    aux = int(wl.split(" aux=")[1].split()[0])
+    assert aux & 0xff == 0 and ((aux >> 8) & 0xff) - 1 == 0 and ((aux >> 16) & 0xff) - 1 == 5   # m1 bit, predicate, register
+    vals = np.array([complex(*map(float, v.split(","))) for v in wl.split(" c=")[1].strip().split(";")])
+    flat = np.stack([vals.real, vals.imag], axis=1).reshape(-1)
+    K = flat[:512].reshape(2, 2, 2, 16, 4)          # m1, pred, order, (rA cA ry cy), (rA' cA')
+    T2 = flat[512:640].reshape(2, 4, 16)            # m2, (rB cB), (rB' ry cB' cy)
+
+    def chan2(rho, p, keep_shape):                  # two-qubit depolarising on the first two (of 3 or 4) qubits
+        d = rho.shape[0] // 4
+        r = rho.reshape(4, d, 4, d)
+        red = np.einsum("akal->kl", r)
+        return ((1 - p) * r + p * np.einsum("ab,kl->akbl", np.eye(4) / 4, red)).reshape(rho.shape)
+
+    def kron(*ms):
+        out = np.eye(1)
+        for m in ms:
+            out = np.kron(out, m)
+        return out
+
+    I2 = np.eye(2)
+    for m1 in range(2):
+        for m2 in range(2):
+            for q in (0.0, 0.37):
+                C = np.zeros((16, 16))
+                for eo in range(16):
+                    rA, rB, cA, cB = (eo >> 3) & 1, (eo >> 2) & 1, (eo >> 1) & 1, eo & 1
+                    for ei in range(16):
+                        rA2, rB2, cA2, cB2 = (ei >> 3) & 1, (ei >> 2) & 1, (ei >> 1) & 1, ei & 1
+                        acc = 0.0
+                        for yy in range(4):
+                            k = (K[m1, m1, 0] + q * K[m1, m1, 1])[(rA * 2 + cA) * 4 + yy, rA2 * 2 + cA2]
+                            acc += T2[m2, rB * 2 + cB, rB2 * 8 + (yy >> 1) * 4 + cB2 * 2 + (yy & 1)] * k
+                        C[eo, ei] = acc
+                for ei in range(16):                 # matrix unit of (A, B) -> the direct simulation
+                    rA2, rB2, cA2, cB2 = (ei >> 3) & 1, (ei >> 2) & 1, (ei >> 1) & 1, ei & 1
+                    Eu = np.zeros((4, 4)); Eu[rA2 * 2 + rB2, cA2 * 2 + cB2] = 1.0
+                    # qubit order (A, x, y, B): start from (A, B) (x) W(x, y) and move B last
+                    rho = np.einsum("abcd,xyzw->axybczwd", Eu.reshape(2, 2, 2, 2), W.reshape(2, 2, 2, 2).real).reshape(16, 16)
+                    U = kron(cnot, I2, I2); rho = U @ rho @ U.T          # CNOT(A -> x)
+                    rho = chan2(rho, p2a, None)                           # depolarising on (A, x)
+                    r = rho.reshape(2, 2, 4, 2, 2, 4)                     # A x (yB) | A x (yB)
+                    rho = ((1 - f1) * r[:, m1, :, :, m1, :] + f1 * r[:, 1 - m1, :, :, 1 - m1, :]).reshape(8, 8)   # (A, y, B)
+                    if m1:                                                # predicated: noise then X on y
+                        r = rho.reshape(2, 2, 2, 2, 2, 2)
+                        red = np.einsum("aybcyd->abcd", r)
+                        r = (1 - px) * r + px * np.einsum("abcd,yz->aybczd", red, I2 / 2)
+                        rho = r.reshape(8, 8)
+                        U = kron(I2, X, I2); rho = U @ rho @ U.T
+                    r = rho.reshape(2, 2, 2, 2, 2, 2)                     # D(q) on y
+                    red = np.einsum("aybcyd->abcd", r)
+                    rho = ((1 - q) * r + q * np.einsum("abcd,yz->aybczd", red, I2 / 2)).reshape(8, 8)
+                    # CNOT(y -> B), depolarising on (y, B), H on y, depolarising on y; order (A, y, B)
+                    U = kron(I2, cnot); rho = U @ rho @ U.T
+                    r = rho.reshape(2, 4, 2, 4)
+                    red = np.einsum("akbk->ab", r)
+                    rho = ((1 - p2b) * r + p2b * np.einsum("ab,kl->akbl", red, np.eye(4) / 4)).reshape(8, 8)
+                    U = kron(I2, Hm, I2); rho = U @ rho @ U.T
+                    r = rho.reshape(2, 2, 2, 2, 2, 2)
+                    red = np.einsum("aybcyd->abcd", r)
+                    r = (1 - p1) * r + p1 * np.einsum("abcd,yz->aybczd", red, I2 / 2)
+                    kept = (1 - f2) * r[:, m2, :, :, m2, :] + f2 * r[:, 1 - m2, :, :, 1 - m2, :]    # rA rB cA cB
+                    assert np.abs(C[:, ei] - kept.reshape(16)).max() < 1e-14, (m1, m2, q, ei)
