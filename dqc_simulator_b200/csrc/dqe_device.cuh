@@ -120,7 +120,7 @@ constexpr int kMaxOpsPerPass = 48;
 // pass asks for what it uses (PassParams::nconsts), so the cap costs nothing: an ordinary dm pass stages ~1 KiB (eight
 // 16 KiB-tile CTAs per SM), one that carries fused-measurement tables ~5 KiB
 constexpr int kMaxConstsKet = 512;
-constexpr int kMaxConstsDm = 768;
+constexpr int kMaxConstsDm = 1024;
 __host__ __device__ constexpr int max_consts(int form) { return form == 0 ? kMaxConstsKet : kMaxConstsDm; }
 constexpr int kThreads = 256;          // maximum threads per CTA (launch bound); actual count is blockDim.x
 
@@ -1242,57 +1242,63 @@ __device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroO
 }
 
 // ---- whole remote gate on the data pair (A, B) (host: try_fuse_whole_at).  Constants (double2 units; all tables real,
-// packed two doubles to an entry): K[m1][pred][order][64] at 0, T2[m2][64] at 256, t2[m2][16] at 320, then scratch the
-// kernel fills per CTA: u[2][16] (as double2 with y = 0) at 336, C[256 doubles] at 368.  aux = creg bit of m1 |
-// (predicate bit + 1) << 8 | (register of the per-shot strength q + 1) << 16.
-constexpr int kWhK = 0, kWhT2 = 256, kWht2 = 320, kWhU = 336, kWhC = 368;
-__device__ __forceinline__ const double* whole_K(const MicroOp& op, const double2* cs, uint64_t cw, const double* treg,
-                                                  double& q) {
-  const int m1 = (int)((cw >> (op.aux & 0xff)) & 1ull);
-  const int pb = ((op.aux >> 8) & 0xff) - 1, qr = ((op.aux >> 16) & 0xff) - 1;
+// packed two doubles to an entry): K[m1][pred][order][64 doubles] (2 orders: 1, q; b[7] = 2: 4 orders 1, q1, q2, q1 q2),
+// then T2[m2][64], t2[m2][16], then scratch the kernel fills per CTA: u[2][16] (as double2 with y = 0), C[256 doubles].
+// aux = creg bit of m1 | (predicate bit + 1) << 8 | (register of q1 + 1) << 16 | (register of q2 + 1) << 24.
+struct WholeSel { const double* K; double q1, q2; int nord, oT2, ot2, oU, oC; };
+__device__ __forceinline__ WholeSel whole_sel(const MicroOp& op, const double2* cs, uint64_t cw, const double* treg) {
+  WholeSel w;
+  const uint32_t aux = (uint32_t)op.aux;
+  w.nord = op.b[7] == 2 ? 4 : 2;
+  const int nK = 128 * w.nord;   // double2 entries
+  w.oT2 = nK; w.ot2 = nK + 64; w.oU = nK + 80; w.oC = nK + 112;
+  const int m1 = (int)((cw >> (aux & 0xffu)) & 1ull);
+  const int pb = (int)((aux >> 8) & 0xffu) - 1, r1 = (int)((aux >> 16) & 0xffu) - 1, r2 = (int)((aux >> 24) & 0xffu) - 1;
   const int pv = pb >= 0 ? (int)((cw >> pb) & 1ull) : 0;
-  q = qr >= 0 ? treg[qr] : 0.0;
-  return reinterpret_cast<const double*>(cs + kWhK) + ((m1 * 2 + pv) * 2) * 64;   // K0 here, K1 64 doubles on
+  w.q1 = r1 >= 0 ? treg[r1] : 0.0;
+  w.q2 = r2 >= 0 ? treg[r2] : 0.0;
+  w.K = reinterpret_cast<const double*>(cs) + ((m1 * 2 + pv) * w.nord) * 64;
+  return w;
 }
+__device__ __forceinline__ double whole_keff(const WholeSel& w, int k) {
+  double v = fma(w.q1, w.K[64 + k], w.K[k]);
+  if (w.nord == 4) v += w.q2 * fma(w.q1, w.K[192 + k], w.K[128 + k]);
+  return v;
+}
+__device__ __forceinline__ int whole_scratch_u(const MicroOp& op) { return 128 * (op.b[7] == 2 ? 4 : 2) + 80; }
 // u_m2[(rA' cA' rB' cB')] = sum_{ry cy} t2_m2[(rB' ry cB' cy)] sum_a K[(a a ry cy), (rA' cA')]: the functional that gives
 // p(m2 | m1) on the group's 16 elements; threads 0-31 write one entry each
 __device__ __noinline__ void whole_build_u(const MicroOp& op, double2* cs, uint64_t cw, const double* treg) {
   if (threadIdx.x >= 32u) return;
-  double q;
-  const double* K0 = whole_K(op, cs, cw, treg, q);
+  const WholeSel w = whole_sel(op, cs, cw, treg);
   const int m2 = threadIdx.x >> 4, c = threadIdx.x & 15;
   const int rA = (c >> 3) & 1, rB = (c >> 2) & 1, cA = (c >> 1) & 1, cB = c & 1;
-  const double* t2 = reinterpret_cast<const double*>(cs + kWht2) + 16 * m2;
+  const double* t2 = reinterpret_cast<const double*>(cs + w.ot2) + 16 * m2;
   double acc = 0.0;
 #pragma unroll
   for (int yy = 0; yy < 4; ++yy) {
     double kd = 0.0;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int k = ((a * 2 + a) * 4 + yy) * 4 + (rA * 2 + cA);
-      kd += fma(q, K0[64 + k], K0[k]);
-    }
+    for (int a = 0; a < 2; ++a) kd += whole_keff(w, ((a * 2 + a) * 4 + yy) * 4 + (rA * 2 + cA));
     acc = fma(t2[rB * 8 + (yy >> 1) * 4 + cB * 2 + (yy & 1)], kd, acc);
   }
-  cs[kWhU + threadIdx.x] = make_double2(acc, 0.0);
+  cs[w.oU + threadIdx.x] = make_double2(acc, 0.0);
 }
 // C[(rA cA rB cB), (rA' cA' rB' cB')] = sum_{ry cy} T2_m2[(rB cB), (rB' ry cB' cy)] K[(rA cA ry cy), (rA' cA')], in the
 // element order of the (A, B) group: e = rA * 8 + rB * 4 + cA * 2 + cB
 __device__ __noinline__ void whole_build_C(const MicroOp& op, double2* cs, uint64_t cw_in, const double* treg, int m2) {
-  double q;
-  const double* K0 = whole_K(op, cs, cw_in, treg, q);
-  const double* T2 = reinterpret_cast<const double*>(cs + kWhT2) + 64 * m2;
-  double* C = reinterpret_cast<double*>(cs + kWhC);
+  const WholeSel w = whole_sel(op, cs, cw_in, treg);
+  const double* T2 = reinterpret_cast<const double*>(cs + w.oT2) + 64 * m2;
+  double* C = reinterpret_cast<double*>(cs + w.oC);
   for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) {
     const int eo = t >> 4, ei = t & 15;
     const int rA = (eo >> 3) & 1, rB = (eo >> 2) & 1, cA = (eo >> 1) & 1, cB = eo & 1;
     const int rA2 = (ei >> 3) & 1, rB2 = (ei >> 2) & 1, cA2 = (ei >> 1) & 1, cB2 = ei & 1;
     double acc = 0.0;
 #pragma unroll
-    for (int yy = 0; yy < 4; ++yy) {
-      const int k = ((rA * 2 + cA) * 4 + yy) * 4 + (rA2 * 2 + cA2);
-      acc = fma(T2[(rB * 2 + cB) * 16 + rB2 * 8 + (yy >> 1) * 4 + cB2 * 2 + (yy & 1)], fma(q, K0[64 + k], K0[k]), acc);
-    }
+    for (int yy = 0; yy < 4; ++yy)
+      acc = fma(T2[(rB * 2 + cB) * 16 + rB2 * 8 + (yy >> 1) * 4 + cB2 * 2 + (yy & 1)],
+                whole_keff(w, ((rA * 2 + cA) * 4 + yy) * 4 + (rA2 * 2 + cA2)), acc);
     C[t] = acc;
   }
 }
@@ -1301,7 +1307,7 @@ __device__ __noinline__ void whole_apply(double2* tile, uint32_t T, const MicroO
   int s4[4];
   sort4(op.b, s4);
   const uint32_t mrA = 1u << op.b[0], mrB = 1u << op.b[1], mcA = 1u << op.b[2], mcB = 1u << op.b[3];
-  const double2* __restrict__ C = cs + kWhC;   // row e: 16 doubles = 8 double2
+  const double2* __restrict__ C = cs + whole_scratch_u(op) + 32;   // row e: 16 doubles = 8 double2
   const double sc = r.scale;
   for (uint32_t q = threadIdx.x; q < (T >> 4); q += blockDim.x) {
     const uint32_t i0 = ins0_4(q, s4);
@@ -1380,7 +1386,7 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
         if (solo) __syncwarp(); else __syncthreads();
       }
       if (!solo || threadIdx.x < 32u) {
-        if (op.b[6] == 2) catm2_partials(tile, T, op, pp, cs + kWhU, base, a0, a1);
+        if (op.b[6] == 2) catm2_partials(tile, T, op, pp, cs + whole_scratch_u(op), base, a0, a1);
         else if (op.b[6]) catm2_partials(tile, T, op, pp, cs, base, a0, a1);
         else catm_partials(tile, T, op, pp, cs, base, a0, a1);
       }

@@ -1407,7 +1407,8 @@ bool try_fuse_out_at(dqe_t* h, size_t jp) {
 // goes live either.  After the two rewrites above a cat-comm remote gate reads
 //     E = fused injecting measurement on (A, y)   ...   light ops on y   ...   C = fused contracting measurement on (B, y)
 // with, in between, only axis-local ops on y: constant ones, ONE predicate bit (the X correction of
-// dqc_control.py:347-348) and ONE per-shot idle-time channel D(q) = D0 + q D1 (depolarising / dephasing / Z flip).
+// dqc_control.py:347-348) and up to TWO per-shot idle-time channels D(q) = D0 + q D1 (depolarising / dephasing / Z flip;
+// two of them make K bilinear: K00 + q1 K10 + q2 K01 + q1 q2 K11, b[7] = 2).
 // Nothing in between may touch A or measure anything (the map T1_m1 on A is applied late, at C).  Then
 //     rho'[(rA cA rB cB)] = sum  T2_m2[(rB cB), (rB' ry cB' cy)]  K[(rA cA ry cy), (rA' cA')]  rho[(rA' cA' rB' cB')],
 //     K = Mid(pred, q) o T1_m1 = K0 + q K1   (per m1 and predicate value),
@@ -1416,7 +1417,7 @@ bool try_fuse_out_at(dqe_t* h, size_t jp) {
 // which then applies the 16 x 16 matrix C_m2 = T2_m2 K to every group).  Real tables only (complex ones keep the
 // two-op path).  Constants of W (double2 units): K[m1][pred][order][64 doubles] = 256, T2[m2][64 doubles] = 64,
 // t2[m2][16 doubles] = 16, then 160 of scratch (u: 32, C: 128) that the kernel fills.
-constexpr int kWholeK = 256, kWholeT2 = 64, kWholet2 = 16, kWholeScratch = 160;
+constexpr int kWholeK = 256, kWholeT2 = 64, kWholet2 = 16, kWholeScratch = 160;   // kWholeK per pair of q-orders (one dynamic channel)
 bool try_fuse_whole_at(dqe_t* h, size_t ie) {
   std::vector<HostOp>& Q = h->queue;
   const int n = h->nmax;
@@ -1430,7 +1431,7 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
   std::vector<Mid> mids;
   std::vector<size_t> mid_idx;
   size_t jc = Q.size();
-  int pred_bit = -1, dyn_reg = -1;
+  int pred_bit = -1, dyn_reg = -1, dyn_reg2 = -1, ndyn = 0;
   for (size_t j = ie + 2; j < Q.size(); ++j) {
     const HostOp& e = Q[j];
     if (e.kind != 0) continue;
@@ -1445,8 +1446,11 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
     Mid md;
     md.pred = e.m.pred_bit; md.dyn_reg = -1; md.dyn_kind = 0;
     if (e.m.type == OP_DYN1 && e.m.b[1] == y) {
-      if (e.m.pred_bit >= 0 || dyn_reg >= 0 || e.m.flags == DYN_AMPDAMP) return false;
-      md.dyn_reg = dyn_reg = e.m.aux; md.dyn_kind = e.m.flags;
+      if (e.m.pred_bit >= 0 || ndyn >= 2 || e.m.flags == DYN_AMPDAMP) return false;
+      md.dyn_reg = ndyn;   // (index of the dynamic channel, 0 or 1)
+      if (ndyn == 0) dyn_reg = e.m.aux; else dyn_reg2 = e.m.aux;
+      ++ndyn;
+      md.dyn_kind = e.m.flags;
     } else if (axis_local_matrix(h, e, y, md.M)) {
       if (e.m.pred_bit >= 0) {
         if (pred_bit >= 0 && pred_bit != e.m.pred_bit) return false;
@@ -1477,17 +1481,18 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
   }
   // Mid(pred, order): product of the mid ops in program order, the predicated ones present or not, the dynamic one
   // replaced by D0 = identity (order 0) or D1 = dD/dq (order 1)
-  std::vector<double> K((size_t)kWholeK * 2, 0.0);
+  const int nord = ndyn == 2 ? 4 : 2;   // monomials 1, q1 (, q2, q1 q2)
+  std::vector<double> K((size_t)kWholeK * nord, 0.0);
   for (int pv = 0; pv < 2; ++pv)
-    for (int order = 0; order < 2; ++order) {
+    for (int order = 0; order < nord; ++order) {
       double Mid[16];
       for (int i = 0; i < 16; ++i) Mid[i] = (i / 4 == i % 4) ? 1.0 : 0.0;
-      bool zero = order == 1 && dyn_reg < 0;   // no dynamic op: the q-linear part vanishes
+      bool zero = order >= 1 && ndyn == 0;   // no dynamic op: the q-linear part vanishes
       for (const auto& md : mids) {
         double L[16];
         if (md.dyn_reg >= 0) {
           for (int i = 0; i < 16; ++i) L[i] = 0.0;
-          if (order == 0) { for (int i = 0; i < 4; ++i) L[i * 5] = 1.0; }
+          if (((order >> md.dyn_reg) & 1) == 0) { for (int i = 0; i < 4; ++i) L[i * 5] = 1.0; }
           else if (md.dyn_kind == DYN_DEPOL) {      // D(q) = (1 - q) Id + q R,  R: e00, e11 -> (e00 + e11) / 2, e01 = e10 = 0
             for (int i = 0; i < 4; ++i) L[i * 5] = -1.0;
             L[0 * 4 + 0] += 0.5; L[0 * 4 + 3] += 0.5; L[3 * 4 + 0] += 0.5; L[3 * 4 + 3] += 0.5;
@@ -1522,7 +1527,7 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
                     const int e1 = rA * 8 + (y2 >> 1) * 4 + cA * 2 + (y2 & 1);
                     acc += Mid[yy * 4 + y2] * T1[m1][e1 * 4 + jn];
                   }
-                K[(size_t)(((m1 * 2 + pv) * 2 + order) * 64) + ((rA * 2 + cA) * 4 + yy) * 4 + jn] = acc;
+                K[(size_t)(((m1 * 2 + pv) * nord + order) * 64) + ((rA * 2 + cA) * 4 + yy) * 4 + jn] = acc;
               }
     }
   // ---- E': probabilities of m1 as a functional on the (A, B) group + renormalisation (form 3)
@@ -1541,17 +1546,19 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
   HostOp f1 = fin1;
   f1.live_after &= ~yb;
   // ---- W: the second measurement and the whole map (form 2)
-  std::vector<cplx> KW((size_t)(kWholeK + kWholeT2 + kWholet2 + kWholeScratch), cplx(0.0));
-  for (int k = 0; k < kWholeK; ++k) KW[k] = cplx(K[2 * k], K[2 * k + 1]);
+  const int nK = kWholeK * nord / 2;   // double2 entries of K
+  std::vector<cplx> KW((size_t)(nK + kWholeT2 + kWholet2 + kWholeScratch), cplx(0.0));
+  for (int k = 0; k < nK; ++k) KW[k] = cplx(K[2 * k], K[2 * k + 1]);
   for (int m = 0; m < 2; ++m) {
-    for (int k = 0; k < 32; ++k) KW[kWholeK + 32 * m + k] = cplx(T2[m][2 * k], T2[m][2 * k + 1]);
-    for (int k = 0; k < 8; ++k) KW[kWholeK + kWholeT2 + 8 * m + k] = cplx(t2[m][2 * k], t2[m][2 * k + 1]);
+    for (int k = 0; k < 32; ++k) KW[nK + 32 * m + k] = cplx(T2[m][2 * k], T2[m][2 * k + 1]);
+    for (int k = 0; k < 8; ++k) KW[nK + kWholeT2 + 8 * m + k] = cplx(t2[m][2 * k], t2[m][2 * k + 1]);
   }
   HostOp w = C;
   w.m.b[0] = (uint8_t)(A + n); w.m.b[1] = (uint8_t)(B + n); w.m.b[2] = (uint8_t)A; w.m.b[3] = (uint8_t)B;
-  w.m.b[4] = (uint8_t)A; w.m.b[5] = (uint8_t)B; w.m.b[6] = 2; w.m.b[7] = 1;
+  w.m.b[4] = (uint8_t)A; w.m.b[5] = (uint8_t)B; w.m.b[6] = 2; w.m.b[7] = (uint8_t)(nord == 4 ? 2 : 1);
   w.need = Ab | Bb;
-  w.m.aux = fin1.creg_bit | ((pred_bit + 1) << 8) | ((dyn_reg + 1) << 16);
+  w.m.aux = (int32_t)((uint32_t)fin1.creg_bit | ((uint32_t)(pred_bit + 1) << 8) | ((uint32_t)(dyn_reg + 1) << 16) |
+                      ((uint32_t)(dyn_reg2 + 1) << 24));
   w.m.c_off = add_consts(h, KW.data(), (int)KW.size()); w.nconst = (int)KW.size();
   std::vector<HostOp> out;
   out.reserve(Q.size());

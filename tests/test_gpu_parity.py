@@ -355,6 +355,13 @@ def cat_like_program(b, rng, rounds, classical=False):
         b.measure(x, cbit % 40, forced, True, float(rng.choice([0.0, 0.003, 0.05])))
         b.cond_1q(y, X, cbit % 40)
         cbit += 1
+        if classical and rng.integers(3):
+            # per-shot idle noise on the surviving half between the two measurements: folds into the whole-gate op
+            # by linearity in q (depolarising / dephasing / Z flip); amplitude damping is not linear and must not
+            kind = int(rng.choice([tl.DYN_DEPOL, tl.DYN_DEPOL, tl.DYN_DEPHASE, tl.DYN_ZFLIP, tl.DYN_AMPDAMP]))
+            b.dyn_channel(y, kind, 2 * (r % 8) + 1)
+            if rng.integers(4) == 0:
+                b.pauli_channel(y, rng.dirichlet([8, 1, 1, 1]))
         # second half: y interacts with another data qubit and is measured out as well
         b.apply_2q(y, other, CNOT)
         b.depolarize([y, other], 0.01)
@@ -371,8 +378,9 @@ def cat_like_program(b, rng, rounds, classical=False):
 @pytest.mark.parametrize("classical", [False, True])
 def test_fused_inject_measure_runs_keep_parity(n, batch, tile, classical):
     """inject -> interact -> measure-and-discard runs are rewritten at flush into one fused measurement whose axis x
-    never goes live (fuse_cat_measure): same state, classical bits and live axes as the oracle running the ops one
-    by one, and as the engine with the rewrite switched off."""
+    never goes live, measure-out runs likewise, and whole remote gates into two ops on the data pair
+    (fuse_cat_measure, catfuse = 3): same state, classical bits and live axes as the oracle running the ops one by one,
+    and as the engine with the rewrite switched off."""
     rng = np.random.default_rng(31 + n + tile)
     b = Both("dm", n, batch, 17, tile_bits=tile)
     if classical:
@@ -392,7 +400,7 @@ def test_fused_inject_measure_runs_keep_parity(n, batch, tile, classical):
 
 
 @pytest.mark.parametrize("opts", [dict(cxperm=0), dict(factor=0), dict(tmap=0), dict(prefetch=0), dict(prefetch=3),
-                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0), dict(catfuse=0)])
+                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0), dict(catfuse=0), dict(catfuse=1), dict(catfuse=2)])
 @pytest.mark.parametrize("n,batch,tile", [(7, 3, 10), (6, 4, 8), (7, 2, 12)])
 def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
     """Every planner / kernel switch of the density-matrix path (X / CX by address permutation, factored

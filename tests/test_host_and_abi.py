@@ -511,7 +511,8 @@ def test_fused_measure_out_run_tables_equal_a_direct_simulation(capfd, monkeypat
             assert abs(t[m][i] - np.trace(kept)) < 1e-14
 
 
-def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
+@pytest.mark.parametrize("two_dyn", [False, True])
+def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch, two_dyn):
     """catfuse = 3 (try_fuse_whole_at): a cat-comm remote gate -- pair (x, y), CNOT(A -> x), measure x; X on y if the
     outcome was 1, per-shot idle noise D(q) on y; CNOT(y -> B), H(y), measure y -- becomes two ops on the DATA pair
     (A, B); neither comm qubit goes live.  The 16 x 16 matrix C_m2 = T2_m2 (K0 + q K1) the kernel builds from the staged
@@ -536,6 +537,9 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
     e.measure(x, 0, -1, True, f1)
     e.set_predicate(0); e.depolarize([y], px); e.apply_1q(y, X); e.set_predicate(-1)
     e.dyn_channel(y, tl.DYN_DEPOL, 5)
+    if two_dyn:
+        e.classical_op(tl.CL_CONST, 6, imm=0.125)
+        e.dyn_channel(y, tl.DYN_DEPHASE, 6)       # a second per-shot channel: the tables become bilinear in (q1, q2)
     e.apply_2q(y, B, cnot); e.depolarize([y, B], p2b); e.apply_1q(y, Hm); e.depolarize([y], p1)
     e.measure(y, 1, -1, True, f2)
     capfd.readouterr()
@@ -546,10 +550,13 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
     wl = [ln for ln in fused if ln.split(" c=")[1].count(";") > 100][0]
     aux = int(wl.split(" aux=")[1].split()[0])
     assert aux & 0xff == 0 and ((aux >> 8) & 0xff) - 1 == 0 and ((aux >> 16) & 0xff) - 1 == 5   # m1 bit, predicate, register
+    assert ((aux >> 24) & 0xff) - 1 == (6 if two_dyn else -1)
     vals = np.array([complex(*map(float, v.split(","))) for v in wl.split(" c=")[1].strip().split(";")])
     flat = np.stack([vals.real, vals.imag], axis=1).reshape(-1)
-    K = flat[:512].reshape(2, 2, 2, 16, 4)          # m1, pred, order, (rA cA ry cy), (rA' cA')
-    T2 = flat[512:640].reshape(2, 4, 16)            # m2, (rB cB), (rB' ry cB' cy)
+    nord = 4 if two_dyn else 2
+    K = flat[:256 * nord].reshape(2, 2, nord, 16, 4)             # m1, pred, order, (rA cA ry cy), (rA' cA')
+    T2 = flat[256 * nord:256 * nord + 128].reshape(2, 4, 16)     # m2, (rB cB), (rB' ry cB' cy)
+    q2 = 0.21 if two_dyn else 0.0
 
     def chan2(rho, p, keep_shape):                  # two-qubit depolarising on the first two (of 3 or 4) qubits
         d = rho.shape[0] // 4
@@ -574,7 +581,10 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
                         rA2, rB2, cA2, cB2 = (ei >> 3) & 1, (ei >> 2) & 1, (ei >> 1) & 1, ei & 1
                         acc = 0.0
                         for yy in range(4):
-                            k = (K[m1, m1, 0] + q * K[m1, m1, 1])[(rA * 2 + cA) * 4 + yy, rA2 * 2 + cA2]
+                            Ke = K[m1, m1, 0] + q * K[m1, m1, 1]
+                            if two_dyn:
+                                Ke = Ke + q2 * (K[m1, m1, 2] + q * K[m1, m1, 3])
+                            k = Ke[(rA * 2 + cA) * 4 + yy, rA2 * 2 + cA2]
                             acc += T2[m2, rB * 2 + cB, rB2 * 8 + (yy >> 1) * 4 + cB2 * 2 + (yy & 1)] * k
                         C[eo, ei] = acc
                 for ei in range(16):                 # matrix unit of (A, B) -> the direct simulation
@@ -594,7 +604,12 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch):
                         U = kron(I2, X, I2); rho = U @ rho @ U.T
                     r = rho.reshape(2, 2, 2, 2, 2, 2)                     # D(q) on y
                     red = np.einsum("aybcyd->abcd", r)
-                    rho = ((1 - q) * r + q * np.einsum("abcd,yz->aybczd", red, I2 / 2)).reshape(8, 8)
+                    r = (1 - q) * r + q * np.einsum("abcd,yz->aybczd", red, I2 / 2)
+                    if two_dyn:                                           # dephasing of strength q2 on y
+                        r = r.copy()
+                        r[:, 0, :, :, 1, :] *= 1 - q2
+                        r[:, 1, :, :, 0, :] *= 1 - q2
+                    rho = r.reshape(8, 8)
                     # CNOT(y -> B), depolarising on (y, B), H on y, depolarising on y; order (A, y, B)
                     U = kron(I2, cnot); rho = U @ rho @ U.T
                     r = rho.reshape(2, 4, 2, 4)

@@ -1,7 +1,7 @@
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02z_gputests.log 2>&1
 echo tests rc=$?
 tail -4 gpurun_out/r02z_gputests.log
-for cfg in "" "--opt catfuse=2" "--circuit qft" "--noise depol+dephase"; do
+for cfg in "" "--noise depol+dephase" "--circuit qft" "--shared-timeline"; do
 echo "== $cfg"
 python bench.py --steps 3 --warmup 2 --no-cpu-baseline $cfg 2>&1 | python -c "
 import json,sys
