@@ -436,18 +436,19 @@ def main():
                      "frac": achieved / peak,
                      # DRAM traffic per launch = ratio measured by ncu x the algorithmic bytes of THIS run's launches
                      # (ncu cannot run inside the timed bench: a number taken under a profiler is not a bench value)
-                     "traffic": 0.989 * 32.0 * amps / max(n_pass, 1),
+                     "traffic": 0.93 * 32.0 * amps / max(n_pass, 1),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, 2026-10-20, same command "
-                                       "at 16384 shots (profiles/r02w_summary.md): 2.124 GB per launch of 32768 tiles of 32 KiB "
-                                       "against 32768 x 32 KiB x 2 = 2.147 GB algorithmic -> ratio 0.989; scaled to this run's "
-                                       "launch size",
-                     "note": "algorithmic bytes = 32 B x live elements of rho per pass AFTER the flush-time rewrite that fuses "
-                             "inject -> CNOT -> measure-and-discard runs (the first comm qubit of a remote gate never goes live): "
-                             "the same step needed 5x the bytes and 292 passes before (9.6 TB -> 1.3 TB per 1e5 shots), so "
-                             "`achieved` fell while shots/s rose 3.7x.  The ~22-op passes (fused measurements resolved through "
-                             "cluster DSMEM, per-shot classical timeline, group sweeps) are bound by on-chip latency (issue slots "
-                             "~34 % busy; short-scoreboard 24 %, fixed-latency 21 %, barrier 18 % of stall samples: "
-                             "profiles/r02w_summary.md), not by HBM; see roofline_single_gate for the HBM-bound regime",
+                                       "at 16384 shots (profiles/r02z_summary.md): 499 MB per launch of 16384 tiles of 16 KiB "
+                                       "against 16384 x 16 KiB x 2 = 537 MB algorithmic -> ratio 0.93 (part of a pass's output is "
+                                       "still in L2 when the next pass reads it); scaled to this run's launch size",
+                     "note": "algorithmic bytes = 32 B x live elements of rho per pass AFTER the flush-time rewrite that turns "
+                             "every cat-comm remote gate into two ops on its data pair (no comm qubit ever goes live): the same "
+                             "step needed 20x the element updates and 292 passes before (9.6 TB -> 0.47 TB per 1e5 shots), so "
+                             "`achieved` fell while shots/s rose 11x.  The ~13-op passes over one 16 KiB tile per shot (table "
+                             "building, two reductions with a draw, a 16 x 16 real matrix per group, per-shot classical "
+                             "timeline) are bound by on-chip latency (issue slots ~31 % busy; short-scoreboard 25 %, "
+                             "fixed-latency 22 %, no-instruction 19 % of stall samples: profiles/r02z_summary.md), not by HBM; "
+                             "see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
                      "algorithmic_bytes_per_launch": 32.0 * amps / max(n_pass, 1),
