@@ -170,13 +170,20 @@ struct PassParams {
   int64_t batch;
   const MicroOp* ops;
   const double2* consts;
+  // pass chain (nlinks > 1): consecutive passes over the SAME tile layout with one tile per shot run as ONE launch --
+  // the tile stays in shared memory, only the micro-program changes: link k = {first micro-op, micro-ops, first
+  // constant, constants} relative to ops_all / consts_all; ops / nops / consts / nconsts above describe link 0
+  const uint4* links;
+  const MicroOp* ops_all;
+  const double2* consts_all;
   uint64_t seed, shot_offset;
   int32_t nops, t, P, nmax;
   int32_t formalism, outer_bits, n_tile_segs, n_outer_segs;
   int32_t store_back, nconsts;
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
-  int32_t nfree_cols, pad3;
+  int32_t nfree_cols, nlinks;
+  uint64_t tile0;                     // first tile of this launch (chains run the batch as chunks of whole waves)
   int32_t uses_treg, writes_creg, writes_treg, nregs;  // planner: what the pass does to the classical state;
                                                        // nregs (even) = registers [0, nregs) are in use
   uint64_t ntiles;
@@ -1404,7 +1411,7 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { red[2 * w] = a0; red[2 * w + 1] = a1; }
   }
-  if (mcount == 0) cluster_wait();   // completes the arrive of the kernel prologue
+  if (mcount == 0 && pp.outer_bits) cluster_wait();   // completes the arrive of the kernel prologue
   if (!solo) __syncthreads();
   const unsigned nr = cluster.num_blocks();
   if (threadIdx.x == 0) {
@@ -1420,7 +1427,7 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
       rp[0] = s0; rp[1] = s1;
     }
   }
-  cluster.sync();
+  if (pp.outer_bits) cluster.sync(); else __syncthreads();   // one tile per shot: the CTA is the whole cluster
   // 3. every CTA sums the slots in rank order (identical result everywhere) and draws
   if (threadIdx.x == 0) {
     double p0 = 0.0, p1 = 0.0;
@@ -2003,7 +2010,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   const bool tmx = !PERSIST && tma && pp.tm_rank != 0;   // tensor-map path (one copy per tile and direction)
   const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(dyn_tiles);
   const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
-  uint64_t blk = blockIdx.x;
+  uint64_t blk = pp.tile0 + blockIdx.x;
   // per-shot classical state of the first tile: requested before anything else, so that its DRAM latency
   // hides behind the barrier set-up and the tile fetch
   uint64_t cw_first = 0;
@@ -2018,7 +2025,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     const double* tr = pp.treg + (blk >> pp.outer_bits) * (uint64_t)kTimeRegs;
     for (int i = threadIdx.x; i < pp.nregs; i += blockDim.x) s_treg[i] = tr[i];
   }
-  if (pp.has_measure) cluster_arrive_relaxed();   // waited for in the first op_measure
+  if (pp.has_measure && pp.outer_bits) cluster_arrive_relaxed();   // waited for in the first op_measure
   if (tma && threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0_s + 8u));
@@ -2126,14 +2133,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
     // the dispatch header of the NEXT op is fetched before the current op runs (one 16-byte load, its
     // latency hidden behind the op); a group header carries its sub-op count in c_off, so the skip over
     // the sub-ops needs nothing else
+    int nops = pp.nops;
+    for (int link = 0;;) {
     int4 hdr = op_header(&s_ops[0]);
-    for (int o = 0; o < pp.nops;) {
+    for (int o = 0; o < nops;) {
       const int cur = o;
       const MicroOp& op = s_ops[cur];
       const int op_type = hdr.x, op_pred = hdr.y, op_flags = hdr.z, hdr_coff = hdr.w;
       const double2* cs = s_consts + hdr.w;
       o = cur + 1 + ((op_type == OP_GROUP || op_type == OP_KGROUP) ? hdr.w : 0);
-      if (o < pp.nops) hdr = op_header(&s_ops[o]);
+      if (o < nops) hdr = op_header(&s_ops[o]);
       if (op_pred >= 0 && !((cw >> op_pred) & 1ull)) continue;
       if (op_type == OP_CLASSICAL) {
         if (blockDim.x <= 64u) {
@@ -2167,13 +2176,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             break;
           case OP_DIAG: case OP_LADDER: {
             int run = 1;
-            while (cur + run < pp.nops && run < kMaxDiagRun &&
+            while (cur + run < nops && run < kMaxDiagRun &&
                    (s_ops[cur + run].type == OP_DIAG || s_ops[cur + run].type == OP_LADDER)) ++run;
             if (run == 1 && op_type == OP_DIAG) op_diag(tile, T, op, cs, base);
             else {
               op_diag_run(tile, T, &s_ops[cur], run, s_consts, base, cw, s_diag, s_lad);
               o = cur + run;
-              if (o < pp.nops) hdr = op_header(&s_ops[o]);
+              if (o < nops) hdr = op_header(&s_ops[o]);
             }
             break;
           }
@@ -2193,7 +2202,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
                                s_treg, s_consts, &s_cw);
             if (op.lctrl2 & kMeasRunsClassical) {   // the classical block rode inside: skip it
               o = cur + 2;
-              if (o < pp.nops) hdr = op_header(&s_ops[o]);
+              if (o < nops) hdr = op_header(&s_ops[o]);
               take_cw = blockDim.x > 64u;
             }
             break;
@@ -2210,13 +2219,49 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
                              s_treg, s_consts, &s_cw);
           if (op.lctrl2 & kMeasRunsClassical) {   // the classical block rode inside: skip it
             o = cur + 2;
-            if (o < pp.nops) hdr = op_header(&s_ops[o]);
+            if (o < nops) hdr = op_header(&s_ops[o]);
             take_cw = blockDim.x > 64u;
           }
         } else dm_standalone(tile, T, op, op_type, pp, cs, base, blk, shot, s_red, &s_meas, s_treg);
       }
       __syncthreads();
       if (take_cw) { cw = s_cw; take_cw = false; }   // classical word of a block that warp 0 ran inside a measurement
+    }
+    // chained passes: the tile stays where it is, the next link's micro-program and constants replace the current
+    // ones (two bulk copies out of L2 on the tile's mbarrier, or plain loads without TMA)
+    if (PERSIST || ++link >= pp.nlinks) break;   // (persistent CTAs: the host never chains)
+    __syncthreads();   // (a predicated-off or classical op leaves the loop without the closing barrier)
+    {
+      const uint4 L = __ldg(pp.links + link);
+      nops = (int)L.y;
+      if (tma) {
+        if (threadIdx.x == 0) {
+          // generic-proxy writes into the constant area (per-CTA tables of a whole gate) before the async-proxy copy
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const uint32_t ob = L.y * (uint32_t)sizeof(MicroOp), cb = L.w * 16u;
+          tma_expect(bar0_s, ob + cb);
+          if (ob) tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_ops), pp.ops_all + L.x, ob, bar0_s);
+          if (cb) tma_load_bytes((uint32_t)__cvta_generic_to_shared(s_consts), pp.consts_all + L.z, cb, bar0_s);
+        }
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(done)
+              : "r"(bar0_s), "r"(parity[0])
+              : "memory");
+        }
+        parity[0] ^= 1u;
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(pp.ops_all + L.x);
+        uint4* dst = reinterpret_cast<uint4*>(s_ops);
+        for (int i = threadIdx.x; i < nops * (int)(sizeof(MicroOp) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < (int)L.w; i += blockDim.x) s_consts[i] = __ldg(pp.consts_all + L.z + i);
+        __syncthreads();
+      }
+    }
     }
 
     // classical state of the shot -> the `out` copies, by the CTA that holds the shot's tile 0 (every CTA of
@@ -2236,7 +2281,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
         if (!PERSIST && pp.tm_rank != 0) {
           if (fresh_tid() == 0) {
             int32_t c[5];
-            tm_coords(pp, (uint64_t)fresh_ctaid(), c);
+            tm_coords(pp, pp.tile0 + (uint64_t)fresh_ctaid(), c);
             tma_tensor_store(&pp.tmap, pp.tm_rank, (uint32_t)__cvta_generic_to_shared(dyn_tiles), c);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem stays valid until read
@@ -2245,7 +2290,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
           const uint32_t tid2 = fresh_tid();
           const uint32_t wid2 = __shfl_sync(0xffffffffu, tid2 >> 5, 0), nwarps2 = blockDim.x >> 5;
           const bool issuer2 = (tid2 & 31u) == 0u;
-          const uint64_t blk2 = fresh_ctaid();
+          const uint64_t blk2 = pp.tile0 + fresh_ctaid();
           const int c02 = pp.tile_segs[0].len;
           const uint32_t run_bytes2 = 16u << c02, nruns2 = (1u << pp.t) >> c02;
           const uint64_t base2 = deposit(blk2 & ((1ull << pp.outer_bits) - 1ull), pp.outer_segs, pp.n_outer_segs);
@@ -2723,17 +2768,15 @@ __global__ void __launch_bounds__(128) k_fidelity_ket(const ReadoutParams rp) {
       acc += s.x * s.x + s.y * s.y;
     }
   } else {
-    for (uint64_t r = threadIdx.x; r < nrest; r += blockDim.x) {
-      const uint64_t ro = deposit(r, rp.rest_segs, rp.n_rest_segs);
+    // one term conj(phi_i) rho_S[i][j] phi_j per step, threads spread over (rest, i, j) jointly: a register whose
+    // live axes are all listed (rest_bits = 0, the shot batches of config 2) still keeps every lane busy
+    const uint64_t nterms = nrest << (2 * rp.k);
+    for (uint64_t e = threadIdx.x; e < nterms; e += blockDim.x) {
+      const uint32_t j = (uint32_t)e & (dim - 1u), i = (uint32_t)(e >> rp.k) & (dim - 1u);
+      const uint64_t ro = deposit(e >> (2 * rp.k), rp.rest_segs, rp.n_rest_segs);
       const uint64_t rr = (ro << rp.nmax) | ro;
-      for (uint32_t i = 0; i < dim; ++i) {
-        const uint64_t oi = sel_offset(rp, i, rp.nmax);
-        const double2 ci = conj2(rp.ket[i]);
-        for (uint32_t j = 0; j < dim; ++j) {
-          const double2 v = cmul(cmul(ci, st[oi | sel_offset(rp, j, 0) | rr]), rp.ket[j]);
-          acc += v.x;
-        }
-      }
+      const double2 v = cmul(cmul(conj2(rp.ket[i]), st[sel_offset(rp, i, rp.nmax) | sel_offset(rp, j, 0) | rr]), rp.ket[j]);
+      acc += v.x;
     }
   }
   __shared__ double sa[4];

@@ -102,6 +102,13 @@ struct dqe_engine {
   size_t scratch_cap;
   MicroOp* d_ops;
   size_t d_ops_cap;
+  uint4* d_links;           // pass chains: link tables of the launches in flight (launch_passes)
+  size_t d_links_cap;
+  std::vector<uint4> links_host;
+  int chain_waves;          // chains launch the batch in chunks of this many waves of resident CTAs (0 = one grid)
+  int chain_max;            // longest chain (0 = no limit)
+  int chain;                // option: consecutive one-tile-per-shot passes over the same tile layout run as one launch
+  int64_t chained_links;    // statistics: passes that rode in a chain behind its head
   double2* d_consts;
   size_t d_consts_cap;
   uint64_t live_axes;       // axis mask
@@ -2803,13 +2810,66 @@ int do_flush(dqe_t* h, bool partial) {
     delete h->cached; h->cached = nullptr;
   }
   if (getenv("DQE_DEBUG"))
-    fprintf(stderr, "[dqe] flush: %zu passes, tensor maps used %lld refused %lld (cumulative)\n", pl.passes.size(),
-            (long long)h->tmap_used, (long long)h->tmap_refused);
+    fprintf(stderr, "[dqe] flush: %zu passes (%lld chained behind another so far), tensor maps used %lld refused %lld (cumulative)\n",
+            pl.passes.size(), (long long)h->chained_links, (long long)h->tmap_used, (long long)h->tmap_refused);
   return 0;
 }
 
+// Two passes may share a launch when the second finds the tile exactly where the first leaves it: one tile per
+// shot (no cluster, no other CTA of the shot to wait for), the same tile bits in the same order, the same CTA shape.
+bool same_tile_layout(const PassParams& a, const PassParams& b) {
+  return a.outer_bits == 0 && b.outer_bits == 0 && a.t == b.t && a.P == b.P && a.nthreads == b.nthreads &&
+         a.use_tma == b.use_tma && a.nbuf == b.nbuf && a.ntiles == b.ntiles && a.n_tile_segs == b.n_tile_segs &&
+         a.n_outer_segs == b.n_outer_segs && a.nfree_cols == b.nfree_cols && a.dg_nfix == b.dg_nfix &&
+         a.dg_req_mask == b.dg_req_mask && a.dg_eq_mask == b.dg_eq_mask &&
+         !memcmp(a.tile_segs, b.tile_segs, sizeof(a.tile_segs)) && !memcmp(a.outer_segs, b.outer_segs, sizeof(a.outer_segs)) &&
+         !memcmp(a.ax_col, b.ax_col, sizeof(a.ax_col)) && !memcmp(a.ax_row, b.ax_row, sizeof(a.ax_row)) &&
+         !memcmp(a.ax_ord, b.ax_ord, sizeof(a.ax_ord)) && !memcmp(a.dg_mask, b.dg_mask, sizeof(a.dg_mask)) &&
+         !memcmp(a.dg_req, b.dg_req, sizeof(a.dg_req)) && !memcmp(a.dg_fix_src, b.dg_fix_src, sizeof(a.dg_fix_src)) &&
+         !memcmp(a.dg_fix_dst, b.dg_fix_dst, sizeof(a.dg_fix_dst)) && !memcmp(a.run_hi, b.run_hi, sizeof(a.run_hi));
+}
+
+// resident CTAs per SM as far as shared memory decides (228 KiB per SM, 1 KiB reserved per CTA, ~6.3 KiB static)
+int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 6400 + 1024)); }
+
 int launch_passes(dqe_t* h, Planner& pl) {
-  for (PlannedPass& P : pl.passes) {
+  // pass chains: chain_len[i] = number of passes launched together with pass i as their head (0: rides in a chain)
+  const size_t np = pl.passes.size();
+  std::vector<int> chain_len(np, 1);
+  h->links_host.clear();
+  std::vector<size_t> link_at(np, 0);
+  if (h->chain && !h->persistent && h->device >= 0) {
+    for (size_t i = 0; i < np;) {
+      const PlannedPass& A = pl.passes[i];
+      size_t j = i + 1;
+      if (!A.is_finish && !A.classical_only && A.pp.store_back)
+        while (j < np && !pl.passes[j].is_finish && !pl.passes[j].classical_only && pl.passes[j].pp.store_back &&
+               (h->chain_max <= 0 || (int)(j - i) < h->chain_max) && same_tile_layout(A.pp, pl.passes[j].pp) &&
+               ctas_per_sm_by_smem(pl.passes[j].smem) == ctas_per_sm_by_smem(A.smem)) ++j;   // (one fat link must not cost the whole chain a resident CTA)
+      if (j - i > 1) {
+        chain_len[i] = (int)(j - i);
+        link_at[i] = h->links_host.size();
+        for (size_t k = i; k < j; ++k) {
+          chain_len[k] = k == i ? (int)(j - i) : 0;
+          const PlannedPass& Q = pl.passes[k];
+          h->links_host.push_back(make_uint4((unsigned)Q.op_begin, (unsigned)Q.pp.nops, (unsigned)Q.const_begin, (unsigned)Q.pp.nconsts));
+        }
+      }
+      i = j;
+    }
+    if (!h->links_host.empty()) {
+      if (h->links_host.size() > h->d_links_cap) {
+        if (h->d_links) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_links)); h->d_links = nullptr; }
+        h->d_links_cap = std::max<size_t>(h->links_host.size() * 2, 256);
+        CK(cudaMalloc(&h->d_links, h->d_links_cap * sizeof(uint4)));
+      }
+      CK(cudaMemcpyAsync(h->d_links, h->links_host.data(), h->links_host.size() * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
+      h->stats[6] += (int64_t)(h->links_host.size() * sizeof(uint4));
+    }
+  }
+  for (size_t pi = 0; pi < np; ++pi) {
+    PlannedPass& P = pl.passes[pi];
+    if (chain_len[pi] == 0) continue;   // ran inside the launch of its chain's head
     if (P.is_finish) {
       P.fp.partials = h->partials; P.fp.rec = cur_rec(h); P.fp.creg = cur_creg(h);
       P.fp.olog = (h->olog && (int64_t)P.fp.draw < h->olog_draws) ? h->olog : nullptr;
@@ -2834,6 +2894,26 @@ int launch_passes(dqe_t* h, Planner& pl) {
     P.pp.creg = cur_creg(h); P.pp.rec = cur_rec(h);
     P.pp.batch = h->batch;
     P.pp.olog = h->olog;   // draws beyond the log's capacity are rejected when they are queued
+    P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
+    P.pp.nlinks = 1; P.pp.links = nullptr; P.pp.ops_all = h->d_ops; P.pp.consts_all = h->d_consts;
+    size_t smem = P.smem;
+    uint64_t amps = P.amps;
+    int64_t nops_all = P.pp.nops;
+    const int saved_flags[5] = {P.pp.has_measure, P.pp.writes_creg, P.pp.uses_treg, P.pp.writes_treg, 0};
+    if (chain_len[pi] > 1) {
+      // the head's launch carries the union of what its links do to the classical state, and the largest
+      // constant area among them
+      for (int k = 1; k < chain_len[pi]; ++k) {
+        const PlannedPass& Q = pl.passes[pi + k];
+        P.pp.has_measure |= Q.pp.has_measure; P.pp.writes_creg |= Q.pp.writes_creg;
+        P.pp.uses_treg |= Q.pp.uses_treg; P.pp.writes_treg |= Q.pp.writes_treg;
+        smem = std::max(smem, Q.smem);
+        amps += Q.amps; nops_all += Q.pp.nops;
+      }
+      P.pp.nlinks = chain_len[pi];
+      P.pp.links = h->d_links + link_at[pi];
+      h->chained_links += chain_len[pi] - 1;
+    }
     if (P.pp.writes_creg) {
       h->cpar ^= 1;
       P.pp.creg_out = cur_creg(h); P.pp.rec_out = cur_rec(h);
@@ -2843,7 +2923,6 @@ int launch_passes(dqe_t* h, Planner& pl) {
       P.pp.treg = h->treg_buf[h->tpar];
       if (P.pp.writes_treg) { h->tpar ^= 1; P.pp.treg_out = h->treg_buf[h->tpar]; }
     }
-    P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     build_tensor_map(h, P.pp);
     if (P.pp.tm_rank) h->tmap_used++;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -2867,7 +2946,7 @@ int launch_passes(dqe_t* h, Planner& pl) {
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)P.grid);
       cfg.blockDim = dim3((unsigned)threads);
-      cfg.dynamicSmemBytes = P.smem;
+      cfg.dynamicSmemBytes = smem;
       cfg.stream = h->stream;
       cudaLaunchAttribute attr[1];
       if (P.pp.has_measure) {
@@ -2879,16 +2958,35 @@ int launch_passes(dqe_t* h, Planner& pl) {
         cfg.numAttrs = 1;
       }
       void* args[1] = {(void*)&P.pp};
+      P.pp.tile0 = 0;
+      if (P.pp.nlinks > 1 && h->chain_waves > 0) {
+        // a chain keeps its CTAs alive for the whole program: the batch goes through it as chunks of whole waves, so
+        // that the CTAs sharing an SM start together and stay in step (measured: their instruction fetch is shared)
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+        const uint64_t chunk = (uint64_t)std::max(1, occ) * (uint64_t)h->num_sms * (uint64_t)h->chain_waves;
+        for (uint64_t t0 = 0; t0 < P.pp.ntiles; t0 += chunk) {
+          P.pp.tile0 = t0;
+          cfg.gridDim = dim3((unsigned)std::min<uint64_t>(chunk, P.pp.ntiles - t0));
+          CK(cudaLaunchKernelExC(&cfg, fn, args));
+          if (t0) h->stats[2]++;
+        }
+        P.pp.tile0 = 0;
+      } else
       CK(cudaLaunchKernelExC(&cfg, fn, args));
     }
     if (h->timing) {
       CK(cudaEventRecord(e1, h->stream));
       h->ev_pool.push_back(std::make_pair(e0, e1));
+      // a chain streams the state through HBM once, whatever the number of links (a fused run counts once)
       h->ev_amps.push_back(P.amps * (uint64_t)h->batch);
     }
-    h->stats[0]++; h->stats[2]++;
-    h->stats[1] += P.pp.nops;
-    h->stats[3] += (int64_t)(P.amps * (uint64_t)h->batch);
+    h->stats[0] += chain_len[pi]; h->stats[2]++;
+    h->stats[1] += nops_all;
+    h->stats[3] += (int64_t)(amps * (uint64_t)h->batch);
+    // the plan may be launched again (dqe_replay): the head gets its own flags back
+    P.pp.has_measure = saved_flags[0]; P.pp.writes_creg = saved_flags[1]; P.pp.uses_treg = saved_flags[2]; P.pp.writes_treg = saved_flags[3];
+    P.pp.creg_out = nullptr; P.pp.rec_out = nullptr; P.pp.treg_out = nullptr;
   }
   CK(cudaGetLastError());
   return 0;
@@ -2965,7 +3063,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->chain = getenv("DQE_CHAIN") ? atoi(getenv("DQE_CHAIN")) : 0; h->chained_links = 0; h->chain_max = 0; h->chain_waves = 1; h->d_links = nullptr; h->d_links_cap = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
   h->plan_cache = 0; h->cached = nullptr; h->api_mark = 0; h->fresh = true; h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 3; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
@@ -3052,6 +3150,7 @@ int dqe_destroy(dqe_t* h) {
   if (h->partials) cudaFree(h->partials);
   if (h->scratch) cudaFree(h->scratch);
   if (h->d_ops) cudaFree(h->d_ops);
+  if (h->d_links) cudaFree(h->d_links);
   if (h->d_consts) cudaFree(h->d_consts);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -3928,6 +4027,14 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
       CK(cudaMalloc(&h->olog, (size_t)value * (size_t)h->batch));
       CK(cudaMemsetAsync(h->olog, 0xff, (size_t)value * (size_t)h->batch, h->stream));
     }
+  } else if (!strcmp(key, "chain")) {
+    h->chain = value ? 1 : 0;
+  } else if (!strcmp(key, "chain_waves")) {
+    if (value < 0) return fail(h, DQE_EINVAL, "chain_waves >= 0");
+    h->chain_waves = (int)value;
+  } else if (!strcmp(key, "chain_max")) {
+    if (value < 0) return fail(h, DQE_EINVAL, "chain_max >= 0");
+    h->chain_max = (int)value;
   } else if (!strcmp(key, "prefetch")) {
     if (value < -1 || value > (1 << 20)) return fail(h, DQE_EINVAL, "prefetch distance in [-1, 2^20] tiles");
     h->prefetch = (int)value;

@@ -276,15 +276,21 @@ int dqe_probs_diag(dqe_t* h, int npairs, const int* a, const int* b, const int* 
  * Pauli-channel / U rho U^dagger factors inside group sweeps), "tmap" (0: a tile is fetched run by run with
  * cp.async.bulk instead of one cp.async.bulk.tensor box per direction), "prefetch" (tiles ahead whose box is
  * prefetched into L2 at CTA start; -1 = one wave of resident CTAs, 0 = off), "shot_stride" (see dqe_reinit),
- * "outcome_log" (see dqe_read_outcomes), "catfuse" (dm, small registers: 2 = fold inject -> interact -> measure-and-discard
+ * "outcome_log" (see dqe_read_outcomes), "chain" (default 0; 1: consecutive passes that keep one tile per shot in
+ * the same layout run as ONE launch -- the tile stays in shared memory, only the micro-program is re-staged per link,
+ * a whole Grover-5 step reads and writes HBM once; bit-identical results, measured SLOWER on B200: the
+ * long-lived CTAs of an SM drift apart and lose their shared instruction fetch), "chain_waves" (chunks of so many
+ * waves of resident CTAs per chained launch, default 1; 0 = one grid), "chain_max" (longest chain, 0 = no limit),
+ * "catfuse" (dm, small registers: 3 (default) = additionally fold WHOLE cat-comm remote gates into two ops on the data
+ * pair, no comm qubit ever goes live; 2 = fold inject -> interact -> measure-and-discard
  * AND measure-out runs of a remote gate into one fused measurement each at flush -- the first comm qubit of the pair never
  * goes live --, 1 = the injecting runs only, 0 = execute every op as queued; software/dqc_control.py:316-403, 508-613),
  * "pass_ops" (micro-op budget of a pass, <= 48), "plan_cache" (see dqe_replay).  Setting "tile_bits" or "threads" also
  * switches off the per-pass choice of tile / CTA size that density matrices of <= 7 qubits get by default
  * (<= 12 live bits: 2^11 tiles on 128 threads, wider: 2^10 tiles on 64). */
 int dqe_set_option(dqe_t* h, const char* key, int64_t value);
-/* Counters since creation or dqe_reset_stats: [0] passes (tile kernel launches)
- * [1] micro-ops executed in passes  [2] all kernel launches  [3] amplitude-updates
+/* Counters since creation or dqe_reset_stats: [0] passes (links of a pass chain count one each)
+ * [1] micro-ops executed in passes  [2] all kernel launches (a chain is one)  [3] amplitude-updates
  * (elements read+written once per pass)  [4] queued API ops  [5] measure-finish launches
  * [6] bytes of micro-ops + constants copied host->device  [7] ops folded by the peephole. */
 int dqe_get_stats(dqe_t* h, int64_t* out /*8*/);

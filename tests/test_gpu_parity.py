@@ -400,7 +400,8 @@ def test_fused_inject_measure_runs_keep_parity(n, batch, tile, classical):
 
 
 @pytest.mark.parametrize("opts", [dict(cxperm=0), dict(factor=0), dict(tmap=0), dict(prefetch=0), dict(prefetch=3),
-                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0), dict(catfuse=0), dict(catfuse=1), dict(catfuse=2)])
+                                  dict(cxperm=0, factor=0, tmap=0), dict(cluster=0), dict(group=0), dict(tma=0), dict(catfuse=0), dict(catfuse=1), dict(catfuse=2),
+                                  dict(chain=1), dict(chain=1, tma=0), dict(chain=1, chain_waves=0, chain_max=3)])
 @pytest.mark.parametrize("n,batch,tile", [(7, 3, 10), (6, 4, 8), (7, 2, 12)])
 def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
     """Every planner / kernel switch of the density-matrix path (X / CX by address permutation, factored
@@ -415,7 +416,7 @@ def test_dm_kernel_options_keep_parity(n, batch, tile, opts):
 
 @pytest.mark.parametrize("formalism,n,batch,tile", [("dm", 7, 3, 10), ("dm", 6, 4, 8), ("dm", 7, 2, 12), ("dm", 4, 5, 11),
                                                      ("ket", 12, 3, 8), ("ket", 9, 4, 11)])
-@pytest.mark.parametrize("opts", [dict(), dict(cluster=0), dict(fuse=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(cluster=0), dict(fuse=0), dict(chain=1), dict(pass_ops=8, chain=1)])
 def test_classical_machine_and_dynamic_channels(formalism, n, batch, tile, opts):
     """Per-shot classical registers (dqe_classical_op): clock arithmetic, selects on creg bits, derived bits,
     channels whose strength is read from a register -- with the instructions hoisted behind the previous
@@ -859,3 +860,30 @@ def test_replayed_plan_equals_a_fresh_walk():
     a.reinit()
     with pytest.raises(Exception, match="no cached plan"):
         a.replay()
+
+
+@pytest.mark.parametrize("circuit,tma", [("grover", 1), ("qft", 1), ("qft", 0)])
+def test_chained_passes_equal_separate_launches(circuit, tma):
+    """Pass chains (option chain; off by default, it measured slower: DESIGN.md section 9): consecutive passes that keep one tile per shot in the same layout run as
+    ONE launch -- the tile stays in shared memory, only the micro-program is re-staged per link.  Same arithmetic in
+    the same order: states, classical registers and fidelities are bit-identical to one launch per pass, on a fresh
+    walk and on a replayed plan, with far fewer launches."""
+    from dqc_simulator_b200 import experiment
+
+    ops, _ = experiment.load_c2(circuit)
+    dqc = experiment.c2_hardware(noisy=True)
+    data, ideal = experiment.ideal_output_ket(ops, lambda f, n, b: _engine(f, n, b))
+    a = _engine("dm", 7, 48, seed=11, shot_offset=0)
+    b = _engine("dm", 7, 48, seed=11, shot_offset=0)
+    a.set_option("chain", 1)
+    for e in (a, b):
+        e.set_option("tma", tma)
+    for batch in range(2):                               # batch 1 replays the cached plan
+        ra = experiment.run_shot_batch(ops, dqc, a, data, ideal)
+        rb = experiment.run_shot_batch(ops, dqc, b, data, ideal)
+        assert np.array_equal(ra.creg, rb.creg), batch
+        assert np.array_equal(ra.fidelity, rb.fidelity), batch
+        assert np.array_equal(a.full_state(), b.full_state()), batch
+    sa, sb = a.stats(), b.stats()
+    assert sa["passes"] == sb["passes"] and sa["micro_ops"] == sb["micro_ops"] and sa["amp_updates"] == sb["amp_updates"]
+    assert sa["kernel_launches"] < sb["kernel_launches"] - sb["passes"] // 2
