@@ -266,14 +266,17 @@ def sharded_ket_records(rank, world, local):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     out = {"what": "config 5: one state vector sharded over the ranks by its high-order qubits; all global axes are "
                    "exchanged in one device-synchronised kernel over CUDA-IPC peer memory (k_peer_exchange), SWAPs are "
-                   "slot relabellings, measurement / norms through engine kernels",
+                   "slot relabellings, measurement / norms through engine kernels.  `seconds` = best of two repetitions; "
+                   "the second replays the C-ABI call stream recorded during the first (Engine.record / play: no "
+                   "executor walk, like dqe_replay for shot batches); the walked run is first_run_seconds",
            "nvlink_peer_copy_GBps_reference": 770.0, "hbm_peak_GBps": hbm}
     for label, n in (("weak", 30 + g), ("strong", 30)):
         with _StdoutToStderr():
             r = run_sharded.run_fixture(types.SimpleNamespace(n=n, circuit="qft", reps=2, peer=1), rank, world, local)
         keep = ("circuit", "n", "n_gpus", "seconds", "max_abs_err", "norm", "exchanges", "exchange_bytes_per_rank",
                 "exchange_seconds", "nvlink_GBps_per_dir_per_gpu", "relabelled_swaps", "host_enqueue_seconds", "pass_ms",
-                "passes_per_rank", "pass_GBps", "shard_bytes", "micro_ops")
+                "passes_per_rank", "pass_GBps", "shard_bytes", "micro_ops", "replayed", "recorded_calls",
+                "first_run_seconds", "first_run_host_enqueue_seconds")
         rec = {k: r[k] for k in keep}
         rec["pass_frac_of_hbm_peak"] = r["pass_GBps"] / hbm
         rec["nvlink_frac_of_peer_copy"] = (r["nvlink_GBps_per_dir_per_gpu"] or 0.0) / 770.0

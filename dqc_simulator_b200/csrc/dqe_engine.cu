@@ -106,6 +106,7 @@ struct dqe_engine {
   size_t d_links_cap;
   std::vector<uint4> links_host;
   int chain_waves;          // chains launch the batch in chunks of this many waves of resident CTAs (0 = one grid)
+  int smem_pad;             // A/B: extra dynamic shared memory per CTA (bytes), i.e. fewer resident CTAs per SM
   int chain_max;            // longest chain (0 = no limit)
   int chain;                // option: consecutive one-tile-per-shot passes over the same tile layout run as one launch
   int64_t chained_links;    // statistics: passes that rode in a chain behind its head
@@ -2742,6 +2743,7 @@ int do_flush(dqe_t* h, bool partial) {
   auto drop_done = [&]() {
     if (keep_from >= h->queue.size()) {
       h->queue.clear(); h->cpool.clear();
+      h->stream_next = (size_t)h->stream_ops;   // empty queue: the next streaming point counts from here
       h->planned_live = phys_live(h, h->live_axes);
     } else {   // the open tail stays (its constants too: c_off indexes the pool)
       h->queue.erase(h->queue.begin(), h->queue.begin() + keep_from);
@@ -2896,7 +2898,7 @@ int launch_passes(dqe_t* h, Planner& pl) {
     P.pp.olog = h->olog;   // draws beyond the log's capacity are rejected when they are queued
     P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     P.pp.nlinks = 1; P.pp.links = nullptr; P.pp.ops_all = h->d_ops; P.pp.consts_all = h->d_consts;
-    size_t smem = P.smem;
+    size_t smem = P.smem + (size_t)h->smem_pad;
     uint64_t amps = P.amps;
     int64_t nops_all = P.pp.nops;
     const int saved_flags[5] = {P.pp.has_measure, P.pp.writes_creg, P.pp.uses_treg, P.pp.writes_treg, 0};
@@ -3063,7 +3065,7 @@ int dqe_create(dqe_t** out, int formalism, int max_qubits, int64_t batch, int de
   h->scratch = nullptr; h->scratch_cap = 0;
   h->d_consts = nullptr; h->d_consts_cap = 0; h->live_axes = 0; h->planned_live = 0; h->pin_axes = 0;
   h->seed = 0; h->shot_offset = 0; h->draw = 0; h->pred = -1; h->cuda_failed = 0; h->shot_stride = 1;
-  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->chain = getenv("DQE_CHAIN") ? atoi(getenv("DQE_CHAIN")) : 0; h->chained_links = 0; h->chain_max = 0; h->chain_waves = 1; h->d_links = nullptr; h->d_links_cap = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
+  h->tile_bits = P <= 14 ? 10 : 11; h->min_run_bits = 5; h->fuse = 1; h->merge = 1; h->group = 1; h->tma = 1; h->threads = P <= 14 ? 64 : 128; h->ctas_per_sm = 0; h->num_sms = 148; h->persistent = 0; h->chain = getenv("DQE_CHAIN") ? atoi(getenv("DQE_CHAIN")) : 0; h->chained_links = 0; h->chain_max = 0; h->chain_waves = 1; h->smem_pad = 0; h->d_links = nullptr; h->d_links_cap = 0; h->cluster = 1; h->cxperm = 1; h->factor = 1; h->tmap = 1; h->prefetch = -1; h->kblock = 1; h->kblocks_fused = 0; memset(h->peer_epoch, 0, sizeof(h->peer_epoch)); h->xev_ok = false; h->xev_pending = false; h->x_ms = 0; h->x_count = 0; h->x_bytes = 0;
   h->plan_cache = 0; h->cached = nullptr; h->api_mark = 0; h->fresh = true; h->pass_ops = kMaxOpsPerPass; h->tile_auto = (formalism == DQE_DM && P <= 14) ? 1 : 0; h->catfuse = getenv("DQE_CATFUSE") ? atoi(getenv("DQE_CATFUSE")) : 3; h->cat_fused = 0; h->ladder = 1; h->ladders_built = 0; h->kgroup = 1; h->kgroups_built = 0; h->stream_ops = 96; h->stream_next = 96; h->stream_min_bits = 22; h->stream_flushes = 0; h->tmap_used = 0; h->tmap_refused = 0; h->timing = false;
   h->t_ms = 0; h->t_passes = 0; h->t_amps = 0;
   memset(h->stats, 0, sizeof(h->stats));
@@ -3163,6 +3165,7 @@ int dqe_reinit(dqe_t* h) {
   // support of the state on the device: live mask at the head of the (dropped) queue, plus whatever is live now
   const uint64_t was_live = h->planned_live | phys_live(h, h->live_axes | h->pin_axes);
   h->live_axes = 0; h->planned_live = 0; h->draw = 0; h->pred = -1; h->api_mark = h->stats[4]; h->fresh = true;
+  h->stream_next = (size_t)h->stream_ops;   // the same program streams at the same points on every batch
   // the next batch draws from the next block of global shot ids: reinit alone must not replay the stream
   h->shot_offset += (uint64_t)h->batch * (uint64_t)h->shot_stride;
   if (h->device < 0) return 0;
@@ -4032,6 +4035,9 @@ int dqe_set_option(dqe_t* h, const char* key, int64_t value) {
   } else if (!strcmp(key, "chain_waves")) {
     if (value < 0) return fail(h, DQE_EINVAL, "chain_waves >= 0");
     h->chain_waves = (int)value;
+  } else if (!strcmp(key, "smem_pad")) {
+    if (value < 0 || value > 160 * 1024) return fail(h, DQE_EINVAL, "smem_pad in [0, 160 KiB]");
+    h->smem_pad = (int)value;
   } else if (!strcmp(key, "chain_max")) {
     if (value < 0) return fail(h, DQE_EINVAL, "chain_max >= 0");
     h->chain_max = (int)value;

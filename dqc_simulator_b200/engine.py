@@ -135,6 +135,57 @@ def _ibuf(a):
     return arr, arr.ctypes.data_as(_c_int_p)
 
 
+# C-ABI calls that only ENQUEUE (or launch) work and whose arguments do not depend on anything read back from the
+# device: a run made of these alone can be recorded once and replayed on the same handle (Engine.record / play)
+_REPLAYABLE = frozenset((
+    "dqe_alloc_axis", "dqe_free_axis", "dqe_reset", "dqe_force_live_mask", "dqe_enqueue_1q", "dqe_enqueue_2q",
+    "dqe_enqueue_ctrl_1q", "dqe_enqueue_diag", "dqe_enqueue_kq", "dqe_set_predicate", "dqe_enqueue_cond_1q",
+    "dqe_enqueue_pauli_channel", "dqe_enqueue_depolarize", "dqe_enqueue_kraus_1q", "dqe_classical_op",
+    "dqe_classical_qexp2", "dqe_classical_fence", "dqe_classical_rand", "dqe_enqueue_dyn_channel", "dqe_inject_2q",
+    "dqe_inject_2q_mixture", "dqe_measure", "dqe_flush", "dqe_sync", "dqe_peer_exchange"))
+# queries that neither change the handle nor feed device data back into the program
+_NEUTRAL = frozenset(("dqe_live_mask", "dqe_last_error", "dqe_get_stats", "dqe_draw_count", "dqe_n_time_regs",
+                      "dqe_peer_stats", "dqe_pass_time_ms"))
+
+
+class CallRecord:
+    """The C-ABI call stream of one program on one handle (``Engine.record``): (function, argument tuple) pairs
+    with their ctypes buffers kept alive.  ``valid`` turns False when the program called anything whose result
+    could have steered it (a read-back): such a run cannot be replayed."""
+
+    def __init__(self):
+        self.calls = []
+        self.valid = True
+        self.why = ""
+
+    def __len__(self):
+        return len(self.calls)
+
+
+class _RecordingLib:
+    """Stands in for the CDLL while a program is recorded: every call goes through, enqueue-type calls are logged."""
+
+    def __init__(self, lib, rec):
+        self._lib, self._rec = lib, rec
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in _NEUTRAL:
+            return fn
+        rec = self._rec
+        if name not in _REPLAYABLE:
+            def passthrough(*args):
+                rec.valid = False
+                rec.why = rec.why or name
+                return fn(*args)
+            return passthrough
+
+        def logged(*args):
+            rec.calls.append((fn, args))
+            return fn(*args)
+        return logged
+
+
 class Engine:
     """Batched ket / density-matrix register on one B200.
 
@@ -204,6 +255,33 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ recorded programs
+    def record(self):
+        """Context manager: log the C-ABI call stream of the program run inside it (executor walk, adapter logic,
+        argument marshalling all happen once).  ``play`` then re-issues the stream on this handle after a ``reinit``
+        -- the host-side plan cache for programs that span several flushes (sharded state vectors: passes, exchange,
+        passes, ...); ``dqe_replay`` is the in-library one for a single flush."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            rec = CallRecord()
+            real = self._lib
+            self._lib = _RecordingLib(real, rec)
+            try:
+                yield rec
+            finally:
+                self._lib = real
+        return cm()
+
+    def play(self, rec):
+        """Re-issue a recorded call stream (same handle, same initial register state as when it was recorded)."""
+        if not rec.valid:
+            raise EngineError(f"this run read device data back ({rec.why}): it cannot be replayed")
+        for fn, args in rec.calls:
+            if fn(*args) != 0:
+                raise EngineError(f"engine error during replay: {self._lib.dqe_last_error(self._h).decode()}")
 
     def reinit(self):
         """Fresh |0..0> batch on the same buffers (next batch of shots)."""

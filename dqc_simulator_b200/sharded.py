@@ -38,18 +38,29 @@ class GpuShard:
         self.eng = Engine("ket", m, 1, seed=seed, device=device)
         # lazy: a local slot goes live when its qubit is first used (``set_live``), like the executor's lazy
         # INSTR_INIT on one GPU -- the passes of a circuit's first stages then run over the few live bits only
+        self._first_rank, self._lazy = bool(first_rank), bool(lazy)
         self._live = set()
-        for a in (range(1) if lazy else range(m)):
-            self.set_live(a)
-        if not first_rank:          # |0...0> lives on rank 0 only: the other shards start empty
-            self.eng.apply_diag([0], [0.0, 0.0])
-        self.eng.flush()
+        self._initial_state()
         self.apply_1q = self.eng.apply_1q
         self.apply_2q = self.eng.apply_2q
         self.apply_ctrl_1q = self.eng.apply_ctrl_1q
         self.apply_diag = self.eng.apply_diag
         self.apply_kq = self.eng.apply_kq
         self._peer_ptrs = None
+
+    def _initial_state(self):
+        for a in (range(1) if self._lazy else range(self.m)):
+            self.set_live(a)
+        if not self._first_rank:    # |0...0> lives on rank 0 only: the other shards start empty
+            self.eng.apply_diag([0], [0.0, 0.0])
+        self.eng.flush()
+
+    def reset(self):
+        """Back to the state right after construction, on the same handle and peer mappings (a recorded program --
+        ``Engine.record`` / ``play`` -- runs again from here)."""
+        self.eng.reinit()
+        self._live = set()
+        self._initial_state()
 
     def buffer(self):
         return self.eng.state_tensor()

@@ -887,3 +887,25 @@ def test_chained_passes_equal_separate_launches(circuit, tma):
     sa, sb = a.stats(), b.stats()
     assert sa["passes"] == sb["passes"] and sa["micro_ops"] == sb["micro_ops"] and sa["amp_updates"] == sb["amp_updates"]
     assert sa["kernel_launches"] < sb["kernel_launches"] - sb["passes"] // 2
+
+
+def test_recorded_program_replays_bit_identically():
+    """Engine.record / play on the device: the second batch of a sampled, noisy QFT-5 program replayed from the
+    recorded C-ABI stream equals the second batch of an engine that walks the program again (same global shot ids)."""
+    from dqc_simulator_b200 import executor, experiment
+
+    ops, _ = experiment.load_c2("qft")
+    dqc = experiment.c2_hardware(noisy=True)
+    a = _engine("dm", 7, 24, seed=3, shot_offset=0)
+    b = _engine("dm", 7, 24, seed=3, shot_offset=0)
+    with a.record() as rec:
+        executor.DQCExecutor(ops, dqc, a).run()
+        a.flush()
+    executor.DQCExecutor(ops, dqc, b).run()
+    assert rec.valid
+    a.reinit(); b.reinit()
+    a.play(rec)
+    executor.DQCExecutor(ops, dqc, b).run()
+    assert np.array_equal(a.read_creg_words(), b.read_creg_words())
+    assert np.array_equal(a.full_state(), b.full_state())
+    assert sorted(a.live) == sorted(b.live)

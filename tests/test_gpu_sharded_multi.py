@@ -55,3 +55,24 @@ def test_sharded_density_matrix_matches_oracle_on_real_devices(world, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
     assert res["max_abs_err"] < 1e-10 and abs(res["trace"] - 1) < 1e-10 and res["exchanges"] > 0
+
+
+@pytest.mark.parametrize("circuit", ["qft", "ghz"])
+def test_replayed_sharded_program_on_real_devices(circuit, tmp_path):
+    """The second repetition of a sharded program replays the C-ABI call stream recorded during the first
+    (``Engine.record`` / ``play``; passes, the device-synchronised exchange, passes) on the reset shards: same
+    closed-form output (checked inside ``run_fixture``), no executor walk."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "res.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "run_sharded.py"),
+           "--qubits", "12", "--circuit", circuit, "--reps", "3", "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.loads(out.read_text())
+    assert res["replayed"] and res["recorded_calls"] > 10 and res["max_abs_err"] < 1e-10 and not res["peer_error"]
+    assert res["host_enqueue_seconds"] < res["first_run_host_enqueue_seconds"]

@@ -621,3 +621,30 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch, 
                     r = (1 - p1) * r + p1 * np.einsum("abcd,yz->aybczd", red, I2 / 2)
                     kept = (1 - f2) * r[:, m2, :, :, m2, :] + f2 * r[:, 1 - m2, :, :, 1 - m2, :]    # rA rB cA cB
                     assert np.abs(C[:, ei] - kept.reshape(16)).max() < 1e-14, (m1, m2, q, ei)
+
+
+def test_recorded_call_stream_replays_the_same_plan():
+    """Engine.record / play (host-side plan cache for programs that span several flushes, e.g. a sharded state
+    vector's passes - exchange - passes): the replayed C-ABI stream plans exactly what the walked program planned, and
+    a run that reads device data back, or changes an option on the way, refuses to be replayed."""
+    from dqc_simulator_b200 import executor, hardware
+
+    ops, _ = opstream.load(os.path.join(os.path.dirname(__file__), "golden", "c5_qft12_mono.json"))
+    dqc = hardware.DQCSpec.uniform(1, num_positions=12, num_comm_qubits=0)
+    e = engine.Engine("ket", 12, 1, device=-1)
+    with e.record() as rec:
+        executor.DQCExecutor(ops, dqc, e).run()
+        e.flush()
+    assert rec.valid and len(rec) > 100
+    want, live = e.stats(), e.live
+    e.reinit()
+    e.reset_stats()
+    e.play(rec)
+    got = e.stats()
+    assert got == want and e.live == live
+    with e.record() as bad:
+        e.alloc_axis(0) if 0 not in e.live else None
+        e.set_option("merge", 1)
+    assert not bad.valid and bad.why == "dqe_set_option"
+    with pytest.raises(engine.EngineError, match="cannot be replayed"):
+        e.play(bad)

@@ -197,15 +197,37 @@ def run_fixture(a, rank, world, local):
     ops, _ = opstream.load(os.path.join(GOLDEN, f"c5_{a.circuit}{a.n}_mono{suffix}"))
     dqc = hardware.DQCSpec.uniform(1, num_positions=a.n, num_comm_qubits=0)
     best = None
+    # The first repetition walks the program (executor -> ShardedKet -> C-ABI) and records the call stream; the later
+    # ones replay it on the same handle from the same initial state (Engine.record / play: the host-side plan cache
+    # of a program that spans several flushes -- passes, exchange, passes ...), like dqe_replay does for shot batches.
+    replay = getattr(a, "replay", 1) and a.peer == 1
+    shard = sk = rec = None
+    xs_prev = 0.0
     for rep in range(a.reps):
-        shard = GpuShard(a.n - g, local, rank == 0, lazy=a.peer < 2)
-        sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer), peer_gates=a.peer >= 2)
+        if rec is not None and rec.valid and replay:
+            shard.reset()
+            replayed = True
+        else:
+            if shard is not None:
+                shard.close()
+                del shard, sk
+                torch.cuda.empty_cache()
+            shard = GpuShard(a.n - g, local, rank == 0, lazy=a.peer < 2)
+            sk = ShardedKet(a.n, shard, rank, world, peer=bool(a.peer), peer_gates=a.peer >= 2)
+            replayed = False
+            xs_prev = 0.0
+        shard.eng.reset_stats()
         shard.eng.time_passes(True)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        executor.DQCExecutor(ops, dqc, sk).run()
-        t_host = time.perf_counter() - t0
-        sk.sync()
+        if replayed:
+            shard.eng.play(rec)
+            t_host = time.perf_counter() - t0
+        else:
+            with shard.eng.record() as rec:
+                executor.DQCExecutor(ops, dqc, sk).run()
+                t_host = time.perf_counter() - t0
+                sk.sync()
         dist.barrier(); torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         buf = shard.buffer()
@@ -224,14 +246,16 @@ def run_fixture(a, rank, world, local):
             err = max(err, abs(int(cnt[0]) - 2))
         del mag
         xs = sk.exchange_stats()
-        t = torch.tensor([err, dt, xs["seconds"]], dtype=torch.float64, device=buf.device)
+        xs_now = xs["seconds"] - xs_prev      # (the engine's exchange clock runs on across repetitions)
+        xs_prev = xs["seconds"]
+        t = torch.tensor([err, dt, xs_now], dtype=torch.float64, device=buf.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         pass_ms, n_pass, amps = shard.eng.pass_time()
         st = shard.eng.stats()
         res = dict(circuit=a.circuit, n=a.n, n_gpus=world, seconds=float(t[1]), max_abs_err=float(t[0]),
                    norm=norm, exchanges=sk.exchanges, exchange_bytes_per_rank=sk.exchanged_bytes,
                    exchange_seconds=float(t[2]), peer=bool(a.peer), relabelled_swaps=sk.relabelled_swaps,
-                   peer_error=xs["error"], host_enqueue_seconds=t_host, pass_ms=pass_ms, timed_passes=n_pass,
+                   peer_error=xs["error"], host_enqueue_seconds=t_host, replayed=replayed, recorded_calls=len(rec), pass_ms=pass_ms, timed_passes=n_pass,
                    micro_ops=st["micro_ops"], pass_GBps=32.0 * amps / max(pass_ms, 1e-9) / 1e6,
                    nvlink_GBps_per_dir_per_gpu=(sk.exchanged_bytes / float(t[2]) / 1e9) if sk.exchanges and t[2] > 0 else None,
                    passes_per_rank=st["passes"], api_ops=st["api_ops"], shard_bytes=(2 ** (a.n - g)) * 16,
@@ -239,10 +263,14 @@ def run_fixture(a, rank, world, local):
         assert abs(norm - 1) < 1e-9 and res["max_abs_err"] < 1e-10 and not res["peer_error"], res
         if best is None or res["seconds"] < best["seconds"]:
             best = res
+        if not replayed:
+            first = res
         del buf
-        shard.close()
-        del shard, sk
-        torch.cuda.empty_cache()
+    best["first_run_seconds"] = first["seconds"]
+    best["first_run_host_enqueue_seconds"] = first["host_enqueue_seconds"]
+    shard.close()
+    del shard, sk
+    torch.cuda.empty_cache()
     return best
 
 
@@ -253,6 +281,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--peer", type=int, default=1, help="1: all global axes exchanged in one device-synchronised kernel over "
                     "CUDA-IPC peer memory (k_peer_exchange); 0: pairwise NCCL send/recv; 2: host-synchronised peer gates")
+    ap.add_argument("--replay", type=int, default=1, help="0: every repetition walks the program again")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
