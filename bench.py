@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--noise", default="depol", choices=["depol", "depol+dephase"],
                     help="depol: examples/run_experiment.py:80-87; depol+dephase adds a memory dephasing channel of the "
                          "same rate (BASELINE.json config 2 names it; not wired by any reference hardware spec)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the depol+dephase / QFT-5 side measurements")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded state-vector record (config 5)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="engine option for A/B measurements (dqe_set_option), e.g. --opt tmap=0")
@@ -326,7 +327,7 @@ def main():
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
 
-        def step():
+        def step(ops=ops, dqc=dqc, data=data, ideal=ideal):
             t0 = time.perf_counter()
             res = experiment.run_shot_batch(ops, dqc, eng, data, ideal, before_flush=lambda: ev0.record(stream),
                                             after_launch=lambda: ev1.record(stream), comm_axes_low=a.comm_low,
@@ -366,6 +367,30 @@ def main():
         pass_ms, n_pass, amps = eng.pass_time()
         eng.time_passes(False)
 
+        # the other workloads BASELINE.json's config 2 names, on the same engine and batch, measured the same way
+        # (K timed steps after 2 warm-ups: the first walks and plans, the second replays): memory dephasing added
+        # to the depolarising noise, and the QFT-5 circuit
+        variants = {}
+        if not a.no_variants:
+            todo = []
+            if a.noise == "depol":
+                todo.append(("depol+dephase", ops, experiment.c2_hardware(noisy=True, mem_dephase_rate=0.055), data, ideal))
+            if a.circuit != "qft":
+                q_ops, _ = experiment.load_c2("qft")
+                q_data, q_ideal = experiment.ideal_output_ket(q_ops, mk)
+                todo.append(("qft5", q_ops, dqc, q_data, q_ideal))
+            for name, v_ops, v_dqc, v_data, v_ideal in todo:
+                for _ in range(2):
+                    step(v_ops, v_dqc, v_data, v_ideal)
+                barrier()
+                tv = time.perf_counter()
+                v_dev, v_f = 0.0, []
+                for _ in range(a.steps):
+                    _w, d, f = step(v_ops, v_dqc, v_data, v_ideal)
+                    v_dev += d * 1e-3; v_f.append(f)
+                barrier()
+                variants[name] = [time.perf_counter() - tv, v_dev, float(np.mean(v_f))]
+
         # the same kernel in its HBM-bound regime: ONE gate / channel per pass over the resident 1e5-shot
         # state (what an unfused per-instruction execution would launch), timed the same way
         for ax in range(eng.max_qubits):   # full 7-qubit register per shot (the comm axes are free after a run)
@@ -386,10 +411,13 @@ def main():
         sg_ms, sg_n, sg_amps = eng.pass_time()
         eng.time_passes(False)
 
-    t = torch.tensor([t_total, sum(devs) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
+    vt = [x for v in variants.values() for x in v[:2]]
+    t = torch.tensor([t_total, sum(devs) * 1e-3] + vt, dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_total, t_dev = float(t[0]), float(t[1])
+    for i, v in enumerate(variants.values()):
+        v[0], v[1] = float(t[2 + 2 * i]), float(t[3 + 2 * i])
     sharded = None
     if world > 1 and not a.no_sharded:
         # BASELINE config 5 under the same launch: the state vector sharded over the N ranks by its high-order
@@ -464,6 +492,14 @@ def main():
             "avg_launch_ms": sg_ms / max(sg_n, 1)},
         "clocks": clocks,
     }
+    if variants:
+        line["variants"] = {
+            name: {"value": total_shots * a.steps / dev, "e2e": total_shots * a.steps / wall, "unit": UNIT,
+                   "ms_per_step": 1e3 * dev / a.steps, "mean_fidelity": f}
+            for name, (wall, dev, f) in variants.items()}
+        line["variants"]["what"] = ("same engine, batch, steps and timing as the headline (device-timed value, end-to-end e2e): "
+                                    "depol+dephase = BASELINE config 2's wording (memory dephasing at 0.055 Hz added; not in the "
+                                    "reference's example, oracle-only parity), qft5 = the other circuit config 2 names")
     if sharded is not None:
         line["sharded_ket"] = sharded
     if not a.no_cpu_baseline:
