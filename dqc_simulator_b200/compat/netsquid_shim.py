@@ -192,7 +192,7 @@ def install():
     dmtools = _mod("netsquid.qubits.dmtools", DenseDMRepr=_Anything)
     dmutil = _mod("netsquid.qubits.dmutil", partialtrace=None, reorder_dm=None)
     qformalism = _mod("netsquid.qubits.qformalism",
-                      QFormalism=types.SimpleNamespace(KET="ket", DM="dm"),
+                      QFormalism=types.SimpleNamespace(KET="ket", DM="dm", SPARSEDM="sparsedm", STAB="stab", GSLC="gslc"),
                       set_qstate_formalism=lambda f: None)
     qubit = _mod("netsquid.qubits.qubit", Qubit=_Anything)
     qubits = _mod("netsquid.qubits", operators=operators, ketstates=ketstates, ketutil=ketutil,

@@ -17,6 +17,21 @@ import numpy as np
 
 KET = 0
 DM = 1
+# NetSquid's QFormalism members a user can select (docs/source/getting_started.rst:616-622 of the reference points at
+# them): the two dense ones are the engine's own; SPARSEDM holds the same rho as DM (dense arithmetic here, identical
+# results), STAB and GSLC hold stabiliser states, every one of which is a state vector -- Clifford circuits run on the
+# ket engine unchanged (no tableau arithmetic is built: nothing dense to accelerate).
+_FORMALISMS = {"ket": KET, "dm": DM, "sparsedm": DM, "stab": KET, "gslc": KET}
+
+
+def resolve_formalism(f):
+    """KET / DM constant for a formalism given as 0 / 1 or as a (NetSquid) name, case-insensitive."""
+    if f in (KET, DM) and not isinstance(f, str):
+        return int(f)
+    name = str(getattr(f, "name", f)).lower()
+    if name not in _FORMALISMS:
+        raise ValueError(f"unknown state formalism {f!r}: one of {sorted(_FORMALISMS)}")
+    return _FORMALISMS[name]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DQE_LIB: another build of the same library (A/B measurements of kernel changes); never a fallback
@@ -200,7 +215,7 @@ class Engine:
                  state_tensor=None, stream=None, tile_bits=None, fuse=True):
         self._h = ctypes.c_void_p()
         self._lib = load_library()
-        self.formalism = KET if formalism in (KET, "ket") else DM
+        self.formalism = resolve_formalism(formalism)
         self.max_qubits = int(max_qubits)
         self.batch = int(batch)
         self.device = int(device)

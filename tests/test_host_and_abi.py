@@ -648,3 +648,16 @@ def test_recorded_call_stream_replays_the_same_plan():
     assert not bad.valid and bad.why == "dqe_set_option"
     with pytest.raises(engine.EngineError, match="cannot be replayed"):
         e.play(bad)
+
+
+def test_netsquid_formalism_names_resolve_to_the_two_engines():
+    """Every QFormalism member a NetSquid user can select lands on one of the two dense engines: SPARSEDM on the
+    density-matrix one (same rho), STAB / GSLC on the state-vector one (every stabiliser state is a ket)."""
+    for name, want in (("ket", engine.KET), ("KET", engine.KET), ("dm", engine.DM), ("SPARSEDM", engine.DM),
+                       ("stab", engine.KET), ("GSLC", engine.KET), (0, engine.KET), (1, engine.DM)):
+        assert engine.resolve_formalism(name) == want
+    e = engine.Engine("sparsedm", 3, 1, device=-1)
+    assert e.formalism == engine.DM
+    e.close()
+    with pytest.raises(ValueError, match="unknown state formalism"):
+        engine.Engine("mps", 3, 1, device=-1)
