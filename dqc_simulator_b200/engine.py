@@ -168,10 +168,11 @@ class CallRecord:
     with their ctypes buffers kept alive.  ``valid`` turns False when the program called anything whose result
     could have steered it (a read-back): such a run cannot be replayed."""
 
-    def __init__(self):
+    def __init__(self, owner=None):
         self.calls = []
         self.valid = True
         self.why = ""
+        self.owner = owner      # handle value the calls are bound to
 
     def __len__(self):
         return len(self.calls)
@@ -281,7 +282,7 @@ class Engine:
 
         @contextlib.contextmanager
         def cm():
-            rec = CallRecord()
+            rec = CallRecord(self._h.value)
             real = self._lib
             self._lib = _RecordingLib(real, rec)
             try:
@@ -294,6 +295,8 @@ class Engine:
         """Re-issue a recorded call stream (same handle, same initial register state as when it was recorded)."""
         if not rec.valid:
             raise EngineError(f"this run read device data back ({rec.why}): it cannot be replayed")
+        if not self._h.value or rec.owner != self._h.value:
+            raise EngineError("a recorded program replays on the (open) handle it was recorded on only")
         for fn, args in rec.calls:
             if fn(*args) != 0:
                 raise EngineError(f"engine error during replay: {self._lib.dqe_last_error(self._h).decode()}")

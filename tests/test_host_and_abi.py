@@ -648,6 +648,9 @@ def test_recorded_call_stream_replays_the_same_plan():
     assert not bad.valid and bad.why == "dqe_set_option"
     with pytest.raises(engine.EngineError, match="cannot be replayed"):
         e.play(bad)
+    other = engine.Engine("ket", 12, 1, device=-1)
+    with pytest.raises(engine.EngineError, match="handle it was recorded on"):
+        other.play(rec)
 
 
 def test_netsquid_formalism_names_resolve_to_the_two_engines():
