@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--noise", default="depol", choices=["depol", "depol+dephase"],
                     help="depol: examples/run_experiment.py:80-87; depol+dephase adds a memory dephasing channel of the "
                          "same rate (BASELINE.json config 2 names it; not wired by any reference hardware spec)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="N = 1: skip the configs 3 / 4 / 5-shape side records (about 20 s)")
     ap.add_argument("--no-variants", action="store_true", help="skip the depol+dephase / QFT-5 side measurements")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded state-vector record (config 5)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
@@ -285,6 +287,70 @@ def sharded_ket_records(rank, world, local):
     return out
 
 
+def other_config_records(local, hbm):
+    """BASELINE configs 3, 4 and 5-shape on ONE GPU, under the same launch as the headline (N = 1 only; one box has
+    the memory for them once the shot-batch engine is closed): seconds, passes, algorithmic GB/s against the HBM peak,
+    each with a closed-form check of the final state.  A failure is reported in the record, never raised."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {"what": "configs 3 / 4 / 5-shape on one GPU: wall_s = best timed run (replayed = the C-ABI call stream "
+                   "recorded during the first run is re-issued, Engine.play; walked_wall_s = executor walk every time); "
+                   "GBps = 32 B x amplitudes of the pass-live register per pass / device time of the passes",
+           "hbm_peak_GBps": hbm}
+
+    def guarded(key, fn):
+        try:
+            with _StdoutToStderr():
+                r = fn()
+            r["frac_of_hbm_peak"] = r["GBps"] / hbm
+            out[key] = r
+        except Exception as e:  # noqa: BLE001  (a side record must not take the headline down)
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    def c4():
+        import numpy as np
+
+        from dqc_simulator_b200 import executor, experiment, hardware, opstream
+        from dqc_simulator_b200.engine import Engine
+
+        ops, _ = opstream.load(os.path.join(ROOT, "tests", "golden", "c4_qft16_mono.json.gz"))
+        dqc = hardware.DQCSpec.uniform(1, num_positions=16, num_comm_qubits=0, **experiment.C2_NOISE)
+        e = Engine("dm", 16, 1, seed=3, device=local)
+        best = None
+        for rep in range(2):
+            e.reinit(); e.reset_stats(); e.sync()
+            e.time_passes(True)
+            t0 = time.perf_counter()
+            ex = executor.DQCExecutor(ops, dqc, e).run()
+            e.sync()
+            wall = time.perf_counter() - t0
+            ms, npass, amps = e.pass_time()
+            e.time_passes(False)
+            st = e.stats()
+            best = dict(case="c4_qft16_mono (noisy QFT-16 density matrix, 4^16 complex128 = 64 GiB, one trajectory)",
+                        wall_s=wall, pass_ms=ms, passes=npass, api_ops=st["api_ops"], micro_ops=st["micro_ops"],
+                        GBps=32.0 * amps / (ms * 1e-3) / 1e9, state_GiB=64.0, trajectories_per_s=1.0 / wall)
+        axes = ex.axes_of(ex.processing_qubits())
+        r3 = e.reduced_dm(axes[:3], 0)
+        best["check"] = dict(trace=float(np.real(np.trace(r3))), purity_3q=float(np.real(np.trace(r3 @ r3))))
+        best["check_ok"] = abs(best["check"]["trace"] - 1) < 1e-9 and 0.125 - 1e-9 <= best["check"]["purity_3q"] < 1
+        e.close()
+        return best
+
+    import bench_ket
+
+    guarded("c3_qft26_4qpu_cat", lambda: bench_ket.run_case("c3_qft26_4qpu_cat.json.gz", 28, 4, 9, reps=3, replay=True,
+                                                            device=local, check=True))
+    guarded("c3_qft26_4qpu_cat_ancilla_free", lambda: bench_ket.run_case("c3_qft26_4qpu_cat.json.gz", 28, 4, 9, reps=3,
+                                                                         replay=True, ancilla_free=True, device=local,
+                                                                         check=True))
+    guarded("c5_qft30_one_gpu", lambda: bench_ket.run_case("c5_qft30_mono.json.gz", 30, 1, 30, reps=3, replay=True,
+                                                           device=local, check=True))
+    guarded("c5_ghz30_one_gpu", lambda: bench_ket.run_case("c5_ghz30_mono.json.gz", 30, 1, 30, reps=3, replay=True,
+                                                           device=local, check=True))
+    guarded("c4_noisy_qft16_dm", c4)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     a = parse()
@@ -502,6 +568,14 @@ def main():
                                     "reference's example, oracle-only parity), qft5 = the other circuit config 2 names")
     if sharded is not None:
         line["sharded_ket"] = sharded
+    if world == 1 and not a.no_other_configs:
+        try:
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001
+            pass
+        line["other_configs"] = other_config_records(local, peak)
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
