@@ -597,11 +597,12 @@ def test_controlled_phase_stars(n, batch, tile, threads):
     program(b)
     with_stars = b.g.full_state()
     rng.bit_generator.state = state
-    for opt in ("ladder", "kgroup"):     # the same program without the stars / without the block sweeps
+    # the same program without the stars / without the block sweeps / with leftover one-bit phases sharing tables
+    for opt, val in (("ladder", 0), ("kgroup", 0), ("phase_tables", 1)):
         rng.bit_generator.state = state
         b2 = Both("ket", n, batch, 3, tile_bits=tile)
         b2.g.set_option("threads", threads)
-        b2.g.set_option(opt, 0)
+        b2.g.set_option(opt, val)
         program(b2)
         assert np.abs(with_stars - b2.g.full_state()).max() < TOL
 
