@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-DQE_PRINT_PASS_MS=1 python tools/bench_ket.py --case qft30 --fused-only --reps 1 --check 2>&1 | tail -11
-python tools/bench_ket.py --case qft30 --fused-only --reps 2 --opt phase_tables=0 2>&1 | tail -1
+ncu --set full --import-source on --clock-control none -k regex:k_tile_pass --launch-skip 3 --launch-count 2 -f -o gpurun_out/r03h_qft30 python tools/bench_ket.py --case qft30 --fused-only --reps 1 > gpurun_out/r03h_ncu.log 2>&1
+tail -4 gpurun_out/r03h_ncu.log | cut -c1-200
+ls -la gpurun_out/*.ncu-rep
