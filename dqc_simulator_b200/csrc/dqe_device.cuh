@@ -1566,7 +1566,8 @@ __device__ __forceinline__ void op_inject(double2* tile, uint32_t T, const Micro
 // ket: Pauli string drawn per shot.  flags: 0 = 1q channel with cumulative thresholds p[0..2] on u,
 // 1 = k-qubit depolarising (w0 = p[0], w = p[1]) on u, 2 = X if u2 < p[0] (measurement flip).
 __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, const MicroOp& op,
-                                                 const PassParams& pp, uint64_t shot, const double* treg) {
+                                                 const PassParams& pp, uint64_t shot, const double* treg,
+                                                 const double2* cs) {
   double u, u2;
   shot_uniforms(pp.seed, pp.shot_offset + shot, (uint64_t)(uint32_t)op.aux, u, u2);
   const int k = op.nb;
@@ -1580,6 +1581,11 @@ __device__ __forceinline__ void op_pauli_sampled(double2* tile, uint32_t T, cons
     digits[0] = (u >= 1.0 - 0.5 * treg[(int)op.p[3]]) ? 3 : 0;
   } else if (op.flags == 5) {   // Z with per-shot probability q
     digits[0] = (u >= 1.0 - treg[(int)op.p[3]]) ? 3 : 0;
+  } else if (op.flags == 6) {   // general two-qubit Pauli channel: 15 cumulative weights in the constant pool
+    const double* cum = reinterpret_cast<const double*>(cs);
+    int s = 0;
+    for (int i = 0; i < 15; ++i) s += (u >= cum[i]) ? 1 : 0;
+    digits[0] = (s >> 2) & 3; digits[1] = s & 3;
   } else if (op.flags == 0) {
     digits[0] = (u >= op.p[0]) + (u >= op.p[1]) + (u >= op.p[2]);
   } else if (op.flags == 1) {
@@ -2207,7 +2213,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             }
             break;
           case OP_INJECT: op_inject<0>(tile, T, op, pp, cs, shot); break;
-          case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot, s_treg); break;
+          case OP_PAULI_SAMPLED: op_pauli_sampled(tile, T, op, pp, shot, s_treg, cs); break;
           default: break;
         }
       } else {                     // ---- density-matrix micro-ops

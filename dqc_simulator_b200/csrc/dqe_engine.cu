@@ -2417,7 +2417,7 @@ struct Planner {
         if (ho->ci.op >= CL_BAND) pp.writes_creg = 1; else pp.writes_treg = 1;
         continue;
       }
-      if (ho->m.type == OP_DYN1 || (ho->m.type == OP_PAULI_SAMPLED && ho->m.flags >= 3)) pp.uses_treg = 1;
+      if (ho->m.type == OP_DYN1 || (ho->m.type == OP_PAULI_SAMPLED && ho->m.flags >= 3 && ho->m.flags <= 5)) pp.uses_treg = 1;
       uint64_t tb = touched_bits(*ho);
       if (ho->m.type == OP_PROBS || ho->m.type == OP_MEASURE) tb = ~0ull;
       int ax[2], nax = 0;
@@ -3416,6 +3416,58 @@ int dqe_enqueue_pauli_channel(dqe_t* h, int axis, const double* p) {
   } else {
     const uint64_t draw = h->draw++;
     q_sampled(h, 1, &axis, 0, draw, p[0], p[0] + p[1], p[0] + p[1] + p[2]);
+  }
+  return 0;
+}
+
+// k-qubit Pauli channel sum_s p[s] P_s rho P_s (s = 4 * (Pauli on axes[0]) + (Pauli on axes[1]), order I X Y Z).
+// dm: the channel's 16 x 16 superoperator on the bits (row a, row b, col a, col b) as ONE dense block (OP_KBLOCK, FP64
+// tensor cores) -- any correlated two-qubit Pauli noise costs one op; ket: one Pauli pair drawn per shot.
+int dqe_enqueue_pauli_channel_k(dqe_t* h, int k, const int* axes, const double* p) {
+  if (int rc = check_ready(h)) return rc;
+  if (!axes || !p) return fail(h, DQE_EINVAL, "pauli_channel: null");
+  if (k == 1) return dqe_enqueue_pauli_channel(h, axes[0], p);
+  if (k != 2) return fail(h, DQE_EUNSUPPORTED, "pauli_channel: k = 1 or 2");
+  for (int i = 0; i < 2; ++i) if (int rc = check_live(h, axes[i], "pauli_channel")) return rc;
+  if (axes[0] == axes[1]) return fail(h, DQE_EINVAL, "pauli_channel: axes must differ");
+  double tot = 0.0;
+  for (int i = 0; i < 16; ++i) { if (!(p[i] >= 0.0)) return fail(h, DQE_EINVAL, "pauli_channel: negative weight"); tot += p[i]; }
+  if (std::abs(tot - 1.0) > 1e-9) return fail(h, DQE_EINVAL, "pauli_channel: weights must sum to 1");
+  h->stats[4]++;
+  if (h->formalism == DQE_DM) {
+    static const cplx I1(0.0, 1.0);
+    const cplx P[4][4] = {{1.0, 0.0, 0.0, 1.0}, {0.0, 1.0, 1.0, 0.0}, {0.0, -I1, I1, 0.0}, {1.0, 0.0, 0.0, -1.0}};
+    std::vector<cplx> S(256, cplx(0.0, 0.0));
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) {
+        const double w = p[4 * a + b];
+        if (w == 0.0) continue;
+        for (int o = 0; o < 16; ++o)
+          for (int i = 0; i < 16; ++i) {
+            const int rA = (o >> 3) & 1, rB = (o >> 2) & 1, cA = (o >> 1) & 1, cB = o & 1;
+            const int rA2 = (i >> 3) & 1, rB2 = (i >> 2) & 1, cA2 = (i >> 1) & 1, cB2 = i & 1;
+            S[o * 16 + i] += w * P[a][rA * 2 + rA2] * P[b][rB * 2 + rB2] * std::conj(P[a][cA * 2 + cA2]) *
+                             std::conj(P[b][cB * 2 + cB2]);
+          }
+      }
+    HostOp o = blank(h, OP_KBLOCK);
+    o.m.nb = 4;
+    const int bits[4] = {rowbit(h, axes[0]), rowbit(h, axes[1]), axes[0], axes[1]};
+    for (int i = 0; i < 4; ++i) { o.m.b[i] = (uint8_t)bits[i]; o.need |= 1ull << bits[i]; }
+    o.m.c_off = add_consts(h, S.data(), 256); o.nconst = 256;
+    push(h, o);
+  } else {
+    HostOp o = blank(h, OP_PAULI_SAMPLED);
+    o.m.nb = 2;
+    for (int i = 0; i < 2; ++i) { o.m.b[i] = (uint8_t)axes[i]; o.need |= 1ull << axes[i]; }
+    o.m.flags = 6;
+    o.m.aux = (int32_t)h->draw++;
+    cplx cum[8];
+    double run = 0.0, c[16];
+    for (int i = 0; i < 16; ++i) { run += p[i]; c[i] = run; }
+    for (int i = 0; i < 8; ++i) cum[i] = cplx(c[2 * i], c[2 * i + 1]);
+    o.m.c_off = add_consts(h, cum, 8); o.nconst = 8;
+    push(h, o);
   }
   return 0;
 }

@@ -68,6 +68,7 @@ ABI = {
     "dqe_set_predicate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dqe_enqueue_cond_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
     "dqe_enqueue_pauli_channel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]),
+    "dqe_enqueue_pauli_channel_k": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, _c_dbl_p]),
     "dqe_enqueue_depolarize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_int_p, ctypes.c_double]),
     "dqe_enqueue_kraus_1q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p]),
     "dqe_inject_2q": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dbl_p, ctypes.c_int]),
@@ -155,7 +156,7 @@ def _ibuf(a):
 _REPLAYABLE = frozenset((
     "dqe_alloc_axis", "dqe_free_axis", "dqe_reset", "dqe_force_live_mask", "dqe_enqueue_1q", "dqe_enqueue_2q",
     "dqe_enqueue_ctrl_1q", "dqe_enqueue_diag", "dqe_enqueue_kq", "dqe_set_predicate", "dqe_enqueue_cond_1q",
-    "dqe_enqueue_pauli_channel", "dqe_enqueue_depolarize", "dqe_enqueue_kraus_1q", "dqe_classical_op",
+    "dqe_enqueue_pauli_channel", "dqe_enqueue_pauli_channel_k", "dqe_enqueue_depolarize", "dqe_enqueue_kraus_1q", "dqe_classical_op",
     "dqe_classical_qexp2", "dqe_classical_fence", "dqe_classical_rand", "dqe_enqueue_dyn_channel", "dqe_inject_2q",
     "dqe_inject_2q_mixture", "dqe_measure", "dqe_flush", "dqe_sync", "dqe_peer_exchange"))
 # queries that neither change the handle nor feed device data back into the program
@@ -378,6 +379,13 @@ class Engine:
 
     # ------------------------------------------------------------------ channels
     def pauli_channel(self, axis, p):
+        """One axis and (pI, pX, pY, pZ), or a list of two axes and 16 weights p[4 * (Pauli on axes[0]) + (Pauli on
+        axes[1])] -- any correlated two-qubit Pauli noise (``dqe_enqueue_pauli_channel_k``)."""
+        if isinstance(axis, (list, tuple, np.ndarray)):
+            _a, pa = _ibuf(axis)
+            arr = np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(4 ** len(_a)))
+            self._ck(self._lib.dqe_enqueue_pauli_channel_k(self._h, len(_a), pa, arr.ctypes.data_as(_c_dbl_p)))
+            return
         arr = np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(4))
         self._ck(self._lib.dqe_enqueue_pauli_channel(self._h, int(axis), arr.ctypes.data_as(_c_dbl_p)))
 

@@ -125,6 +125,11 @@ int dqe_enqueue_cond_1q(dqe_t* h, int axis, const double* m, int creg_bit);
  *      NetSquid DepolarNoiseModel wired at quantum_processors.py:868-877).
  *      dm: applied analytically in one pass; ket: one branch sampled per shot. ------------- */
 int dqe_enqueue_pauli_channel(dqe_t* h, int axis, const double* p /*pI,pX,pY,pZ*/);
+/* The k-qubit form of SURVEY 8b (k = 1, 2): p[4^k], index = 4 * (Pauli on axes[0]) + (Pauli on axes[1]) in the order
+ * I, X, Y, Z -- NetSquid's qubitapi.apply_pauli_noise on each qubit is the product case, NDimDepolarNoiseModel
+ * (hardware/noise_models.py:295-366) the uniform one; any correlated two-qubit Pauli noise fits.  dm: ONE dense
+ * 16 x 16 superoperator block on (row a, row b, col a, col b); ket: one Pauli pair drawn per shot. */
+int dqe_enqueue_pauli_channel_k(dqe_t* h, int k, const int* axes, const double* p /*4^k*/);
 int dqe_enqueue_depolarize(dqe_t* h, int k, const int* axes, double p);  /* k = 1, 2 */
 int dqe_enqueue_kraus_1q(dqe_t* h, int axis, int nk, const double* K /*nk x 2x2 complex*/);
 

@@ -204,6 +204,37 @@ class OracleEngine:
     # ------------------------------------------------------------------ channels
     def pauli_channel(self, axis, p):
         p = np.asarray(p, dtype=float)
+        if isinstance(axis, (list, tuple, np.ndarray)) and len(axis) == 2:
+            # two-qubit Pauli channel sum_ab p[4a + b] (P_a x P_b) rho (P_a x P_b) (restates what NetSquid's
+            # qubitapi.apply_pauli_noise does qubit by qubit, noise_models.py:343-366, for correlated weights);
+            # ket: one pair per shot from the shot's next uniform, cumulative order s = 4a + b
+            a0, a1 = int(axis[0]), int(axis[1])
+            if self.formalism == DM:
+                acc = 0
+                for s_ in range(16):
+                    w = p[s_]
+                    if w == 0.0:
+                        continue
+                    Pa, Pb = _PAULI[s_ >> 2], _PAULI[s_ & 3]
+                    t = _apply_matrix(self.state, Pa, [self._dim(a0)])
+                    t = _apply_matrix(t, Pb, [self._dim(a1)])
+                    t = _apply_matrix(t, Pa.conj(), [self._cdim(a0)])
+                    acc = acc + w * _apply_matrix(t, Pb.conj(), [self._cdim(a1)])
+                self._commit(acc)
+            else:
+                u, _ = self._next_uniforms()
+                cum = np.cumsum(p)
+                choice = np.zeros(u.shape, dtype=int)
+                for i in range(15):
+                    choice = choice + (u >= cum[i])
+                for q, ax in ((choice >> 2, a0), (choice & 3, a1)):
+                    for idx in (1, 2, 3):
+                        sel = q == idx
+                        if sel.any():
+                            self._apply([ax], _PAULI[idx], predicate=sel)
+            return
+        if isinstance(axis, (list, tuple, np.ndarray)):
+            axis = int(axis[0])
         if self.formalism == DM:
             acc = 0
             for w, P in zip(p, _PAULI):

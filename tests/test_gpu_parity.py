@@ -910,3 +910,52 @@ def test_recorded_program_replays_bit_identically():
     assert np.array_equal(a.read_creg_words(), b.read_creg_words())
     assert np.array_equal(a.full_state(), b.full_state())
     assert sorted(a.live) == sorted(b.live)
+
+
+@pytest.mark.parametrize("formalism,n,batch,tile", [("dm", 6, 3, 10), ("dm", 7, 2, 8), ("dm", 5, 4, 12), ("dm", 9, 1, 11),
+                                                     ("ket", 10, 6, 8), ("ket", 13, 3, 11)])
+def test_two_qubit_pauli_channel(formalism, n, batch, tile):
+    """dqe_enqueue_pauli_channel_k (k, axes, 4^k weights): correlated two-qubit Pauli noise between gates
+    and measurements -- dm: one dense 16 x 16 superoperator block on (row a, row b, col a, col b), ket: one Pauli
+    pair drawn per shot -- against the oracle; the product case equals two one-qubit channels, the uniform case the
+    two-qubit depolarising channel of noise_models.py:295-366."""
+    rng = np.random.default_rng(77 + n + tile)
+    b = Both(formalism, n, batch, 19, tile_bits=tile)
+    for a in range(n):
+        b.alloc_axis(a)
+        b.apply_1q(a, rand_unitary(rng, 2))
+    for step in range(30):
+        a0, a1 = [int(x) for x in rng.choice(n, size=2, replace=False)]
+        kind = step % 5
+        if kind == 0:
+            b.apply_2q(a0, a1, rand_unitary(rng, 4))
+        elif kind == 1:
+            b.pauli_channel([a0, a1], rng.dirichlet([12] + [1] * 15))
+        elif kind == 2:
+            b.apply_2q(a0, a1, CNOT)
+            w = np.zeros(16); w[0], w[5], w[10], w[15] = 0.7, 0.1, 0.1, 0.1        # correlated: XX, YY, ZZ
+            b.pauli_channel([a1, a0], w)
+        elif kind == 3:
+            b.apply_1q(a0, rand_unitary(rng, 2))
+            b.pauli_channel([a0], rng.dirichlet([8, 1, 1, 1]))                      # k = 1 through the same entry point
+        else:
+            b.measure(a0, step % 30, -1 if step % 2 else int(rng.integers(2)), False, 0.01)
+        if step % 10 == 9:
+            b.check(f"step {step}")
+    b.check("end")
+    if formalism == "dm":
+        # product weights = two one-qubit channels; uniform non-identity weights = two-qubit depolarising
+        e1, e2 = _engine("dm", 4, 1, seed=1), _engine("dm", 4, 1, seed=1)
+        for e in (e1, e2):
+            for a in range(4):
+                e.alloc_axis(a)
+                e.apply_1q(a, rand_unitary(np.random.default_rng(a), 2))
+            e.apply_2q(0, 1, CNOT); e.apply_2q(2, 3, CNOT); e.apply_2q(1, 2, rand_unitary(np.random.default_rng(9), 4))
+        pa, pb = rng.dirichlet([8, 1, 1, 1]), rng.dirichlet([6, 2, 1, 1])
+        e1.pauli_channel([1, 3], np.outer(pa, pb).reshape(16))
+        e2.pauli_channel(1, pa); e2.pauli_channel(3, pb)
+        p = 0.23
+        w = np.full(16, p / 16); w[0] = 1 - 15 * p / 16
+        e1.pauli_channel([0, 2], w)
+        e2.depolarize([0, 2], p)
+        assert np.abs(e1.full_state() - e2.full_state()).max() < TOL

@@ -261,3 +261,46 @@ def test_ancilla_free_cat_lowering_equals_the_explicit_protocol(name, nq):
     noisy = hardware.DQCSpec.uniform(4, num_positions=meta["num_positions"], num_comm_qubits=2, p_depolar_error_cnot=1e-3)
     with pytest.raises(ValueError):
         executor.DQCExecutor(ops, noisy, make("ket", nq, 1), ancilla_free_cat=True)
+
+
+def test_oracle_two_qubit_pauli_channel_reduces_to_the_known_cases():
+    """Oracle restatement of the k = 2 Pauli channel: product weights equal two one-qubit channels, uniform
+    non-identity weights equal NDimDepolarNoiseModel's two-qubit depolarising (noise_models.py:295-366), and the
+    state-vector trajectories average to the density-matrix result."""
+    from oracle.numpy_engine import OracleEngine
+
+    rng = np.random.default_rng(3)
+
+    def prep(e):
+        r = np.random.default_rng(1)
+        for a in range(3):
+            e.alloc_axis(a)
+            z = r.normal(size=(2, 2)) + 1j * r.normal(size=(2, 2))
+            q, _ = np.linalg.qr(z)
+            e.apply_1q(a, q)
+        e.apply_2q(0, 1, np.eye(4)[[0, 1, 3, 2]])
+        e.apply_2q(1, 2, np.eye(4)[[0, 1, 3, 2]])
+
+    pa, pb = rng.dirichlet([8, 1, 1, 1]), rng.dirichlet([6, 2, 1, 1])
+    a, b = OracleEngine("dm", 3, 1, seed=0), OracleEngine("dm", 3, 1, seed=0)
+    prep(a); prep(b)
+    a.pauli_channel([0, 2], np.outer(pa, pb).reshape(16))
+    b.pauli_channel(0, pa); b.pauli_channel(2, pb)
+    assert np.abs(a.full_state() - b.full_state()).max() < 1e-14
+    p = 0.3
+    w = np.full(16, p / 16); w[0] = 1 - 15 * p / 16
+    a.pauli_channel([1, 2], w)
+    b.depolarize([1, 2], p)
+    assert np.abs(a.full_state() - b.full_state()).max() < 1e-14
+    # trajectories: correlated weights (XX / YY / ZZ)
+    w = np.zeros(16); w[0], w[5], w[10], w[15] = 0.55, 0.2, 0.15, 0.1
+    d = OracleEngine("dm", 3, 1, seed=0)
+    prep(d)
+    d.pauli_channel([0, 1], w)
+    shots = 4000
+    k = OracleEngine("ket", 3, shots, seed=5)
+    prep(k)
+    k.pauli_channel([0, 1], w)
+    psi = k.full_state()
+    rho = np.einsum("si,sj->ij", psi, psi.conj()) / shots
+    assert np.abs(rho - d.full_state()[0]).max() < 5 / np.sqrt(shots)
