@@ -564,7 +564,7 @@ __device__ __forceinline__ void kg_mat1(double2 (&v)[16], const double2* __restr
 
 __device__ __noinline__ void run_kgroup(double2* tile, uint32_t T, const MicroOp& g, const MicroOp* sub,
                                         const double2* s_consts, uint64_t base, uint64_t cw, DiagPrep* prep,
-                                        LadderPrep* lprep) {
+                                        LadderPrep* lprep, double2* letab) {
   const int nsub = g.aux;
   // ---- prep: the tile-uniform part of every sub-op
   {
@@ -596,6 +596,22 @@ __device__ __noinline__ void run_kgroup(double2* tile, uint32_t T, const MicroOp
         if (op.b[0] >= kOuter) L.on = L.on && ((base >> (op.b[0] - kOuter)) & 1ull);
         else if (op.b[1] == 0) L.qmask = 1u << op.b[0];     // centre on a thread-side tile bit
         lprep[k] = L;
+      }
+      if (act) {
+        // stars with two or more leaves on register-resident bits: the phase of element e from those leaves is the
+        // same for every thread -- a 16-entry table per star, built here once per CTA (two entries per lane), turns
+        // "one predicated multiplication per element per leaf" into one per element
+        const MicroOp& op = sub[k];
+        const int nt = op.flags & 0xff, ne = (op.flags >> 8) & 0xff;
+        if (ne >= 2) {
+          const uint8_t* lf = ladder_leaves(op);
+          for (int e = part; e < 16; e += 8) {
+            double2 ph = make_double2(1.0, 0.0);
+            for (int j = 0; j < ne; ++j)
+              if ((e >> lf[nt + j]) & 1) ph = cmul(ph, s_consts[op.c_off + nt + j]);
+            letab[k * 16 + e] = ph;
+          }
+        }
       }
     }
   }
@@ -664,20 +680,33 @@ __device__ __noinline__ void run_kgroup(double2* tile, uint32_t T, const MicroOp
         const int nt = hdr.z & 0xff, ne = (hdr.z >> 8) & 0xff;
         const uint8_t* lf = ladder_leaves(op);
         const double2* w = s_consts + hdr.w;
-        double2 sc = L.G;
-        for (int j = 0; j < nt; ++j)
+        // the product over the thread-index leaves as two independent chains (half the dependent latency)
+        double2 sc = L.G, sc2 = make_double2(1.0, 0.0);
+        int j = 0;
+        for (; j + 1 < nt; j += 2) {
           if ((i0 >> lf[j]) & 1u) sc = cmul(sc, w[j]);
+          if ((i0 >> lf[j + 1]) & 1u) sc2 = cmul(sc2, w[j + 1]);
+        }
+        if (j < nt && ((i0 >> lf[j]) & 1u)) sc = cmul(sc, w[j]);
+        sc = cmul(sc, sc2);
         const uint32_t qe = op.b[1] ? (1u << (op.b[1] - 1)) : 0u;
-        for (int j = 0; j < ne; ++j) {
-          const uint32_t eb = 1u << lf[nt + j];
-          const double2 wj = w[nt + j];
+        if (ne >= 2) {       // element-phase table of the star (prep phase): one multiplication per element
+          const double2* et = letab + s * 16;
 #pragma unroll
           for (int e = 0; e < 16; ++e)
-            if ((e & eb) && (e & qe) == qe) v[e] = cmul(v[e], wj);
-        }
+            if ((e & qe) == qe) v[e] = cmul(v[e], cmul(sc, et[e]));
+        } else {
+          if (ne == 1) {
+            const uint32_t eb = 1u << lf[nt];
+            const double2 wj = w[nt];
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if ((e & qe) == qe) v[e] = cmul(v[e], sc);
+            for (int e = 0; e < 16; ++e)
+              if ((e & eb) && (e & qe) == qe) v[e] = cmul(v[e], wj);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((e & qe) == qe) v[e] = cmul(v[e], sc);
+        }
       }
     }
 #pragma unroll
@@ -1999,6 +2028,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
   __shared__ LadderPrep s_lad[FORM == 0 ? kMaxDiagRun : 1];
+  __shared__ double2 s_let[FORM == 0 ? kMaxDiagRun * 16 : 1];   // ket block sweeps: element-phase tables of the stars
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
   __shared__ unsigned long long s_cw;   // classical word handed back by the warp that ran a classical block
@@ -2199,7 +2229,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
             if ((base & op.octrl) == op.octrl) op_swap(tile, T, op);
             break;
           case OP_KGROUP:
-            run_kgroup(tile, T, op, &s_ops[cur + 1], s_consts, base, cw, s_diag, s_lad);
+            run_kgroup(tile, T, op, &s_ops[cur + 1], s_consts, base, cw, s_diag, s_lad, s_let);
             break;
           case OP_PROBS: op_probs<0>(tile, T, op, pp, base, blk, s_red); break;
           case OP_COLLAPSE: op_collapse<0>(tile, T, op, pp, s_meas); break;
