@@ -252,8 +252,8 @@ def run_reference(a):
 
 def sharded_ket_records(rank, world, local):
     """N > 1: QFT-(30 + log2 N) (weak: 16 GiB of amplitudes per GPU) and QFT-30 (strong) as ONE state vector sharded
-    over the ranks; seconds = wall time of the whole circuit (executor walk + passes + exchanges), max over ranks,
-    best of 2.  Self-checked inside (norm 1, |amplitude| = 2^(-n/2) to 1e-10)."""
+    over the ranks; seconds = wall time of the whole circuit (host enqueue + passes + exchanges), max over ranks,
+    best of 2 (the second repetition replays the recorded call stream).  Self-checked inside (norm 1, |amplitude| = 2^(-n/2) to 1e-10)."""
     import types
 
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -271,7 +271,9 @@ def sharded_ket_records(rank, world, local):
                    "exchanged in one device-synchronised kernel over CUDA-IPC peer memory (k_peer_exchange), SWAPs are "
                    "slot relabellings, measurement / norms through engine kernels.  `seconds` = best of two repetitions; "
                    "the second replays the C-ABI call stream recorded during the first (Engine.record / play: no "
-                   "executor walk, like dqe_replay for shot batches); the walked run is first_run_seconds",
+                   "executor walk, like dqe_replay for shot batches); the walked run is first_run_seconds (cold: it also pays the "
+                   "one-time set-up of a fresh handle; warm walked runs measured 0.065 s for QFT-30 on 2 GPUs, "
+                   "profiles/r02w_bench_x2.json)",
            "nvlink_peer_copy_GBps_reference": 770.0, "hbm_peak_GBps": hbm}
     for label, n in (("weak", 30 + g), ("strong", 30)):
         with _StdoutToStderr():
