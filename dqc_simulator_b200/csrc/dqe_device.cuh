@@ -183,6 +183,8 @@ struct PassParams {
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
   int32_t nfree_cols, nlinks;
+  int32_t cap_consts, pad4;           // constants the dynamic shared-memory area holds (>= nconsts; chains: the largest
+                                      // link): the micro-ops are staged right behind them
   uint64_t tile0;                     // first tile of this launch (chains run the batch as chunks of whole waves)
   int32_t uses_treg, writes_creg, writes_treg, nregs;  // planner: what the pass does to the classical state;
                                                        // nregs (even) = registers [0, nregs) are in use
@@ -2023,7 +2025,6 @@ __device__ __forceinline__ uint32_t fresh_ctaid() { uint32_t t; asm volatile("mo
 template <int MAXT, int MINB, int FORM, bool PERSIST>
 __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant__ PassParams pp) {
   extern __shared__ __align__(128) double2 dyn_tiles[];
-  __shared__ MicroOp s_ops[kMaxOpsPerPass];
   __shared__ double s_red[2 * (kThreads / 32)];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ DiagPrep s_diag[FORM == 0 ? kMaxDiagRun : 1];   // ket only (multi-diagonal sweeps)
@@ -2040,6 +2041,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   const bool tma = pp.use_tma != 0;   // planner: low segment contiguous, <= 128 runs per tile
   const int nbuf = PERSIST ? pp.nbuf : 1;   // 2 with TMA (prefetch distance 1), 1 otherwise
   double2* const s_consts = dyn_tiles + ((size_t)nbuf << pp.t);   // the pass's constants, behind the tile buffer(s)
+  // ... and its micro-ops behind the constants, sized by the pass (a fixed 48-op array cost the whole-gate passes of
+  // small density matrices their eighth resident CTA)
+  MicroOp* const s_ops = reinterpret_cast<MicroOp*>(s_consts + pp.cap_consts);
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 

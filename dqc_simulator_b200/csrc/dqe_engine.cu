@@ -2543,15 +2543,16 @@ struct Planner {
     if (h->persistent) {
       // persistent grid + double buffering: as many CTAs as fit the machine (<= 512 threads per SM)
       pp.nbuf = pp.use_tma ? 2 : 1;
-      P.smem = (sizeof(double2) << t) * pp.nbuf + sizeof(double2) * (size_t)pp.nconsts;
-      const size_t per_cta = P.smem + 10 * 1024;
+      P.smem = (sizeof(double2) << t) * pp.nbuf + sizeof(double2) * (size_t)pp.nconsts + sizeof(MicroOp) * (size_t)pp.nops;
+      const size_t per_cta = P.smem + 8 * 1024;
       int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / per_cta, (size_t)(512 / h->threads));
       per_sm = std::max(1, std::min(per_sm, h->ctas_per_sm > 0 ? h->ctas_per_sm : 16));
       P.grid = std::min<uint64_t>(pp.ntiles, (uint64_t)h->num_sms * per_sm);
     } else {
       // one tile per CTA; overlap of load / compute / store comes from 4+ resident CTAs per SM
       pp.nbuf = 1;
-      P.smem = (sizeof(double2) << t) + sizeof(double2) * (size_t)pp.nconsts;   // tile + the pass's constants
+      P.smem = (sizeof(double2) << t) + sizeof(double2) * (size_t)pp.nconsts +   // tile + the pass's constants
+               sizeof(MicroOp) * (size_t)pp.nops;                                  // + its micro-ops
       P.grid = pp.ntiles;
       if (P.grid > 0x7fffffffull) { err = "grid too large: enable the persistent option"; return false; }
     }
@@ -2881,7 +2882,7 @@ bool same_tile_layout(const PassParams& a, const PassParams& b) {
 }
 
 // resident CTAs per SM as far as shared memory decides (228 KiB per SM, 1 KiB reserved per CTA, ~6.3 KiB static)
-int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 6400 + 1024)); }
+int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 1792 + 1024)); }
 
 int launch_passes(dqe_t* h, Planner& pl) {
   // pass chains: chain_len[i] = number of passes launched together with pass i as their head (0: rides in a chain)
@@ -2948,6 +2949,8 @@ int launch_passes(dqe_t* h, Planner& pl) {
     P.pp.ops = h->d_ops + P.op_begin; P.pp.consts = h->d_consts + P.const_begin;
     P.pp.nlinks = 1; P.pp.links = nullptr; P.pp.ops_all = h->d_ops; P.pp.consts_all = h->d_consts;
     size_t smem = P.smem + (size_t)h->smem_pad;
+    P.pp.cap_consts = P.pp.nconsts;
+    int cap_ops = P.pp.nops;
     uint64_t amps = P.amps;
     int64_t nops_all = P.pp.nops;
     const int saved_flags[5] = {P.pp.has_measure, P.pp.writes_creg, P.pp.uses_treg, P.pp.writes_treg, 0};
@@ -2958,9 +2961,12 @@ int launch_passes(dqe_t* h, Planner& pl) {
         const PlannedPass& Q = pl.passes[pi + k];
         P.pp.has_measure |= Q.pp.has_measure; P.pp.writes_creg |= Q.pp.writes_creg;
         P.pp.uses_treg |= Q.pp.uses_treg; P.pp.writes_treg |= Q.pp.writes_treg;
-        smem = std::max(smem, Q.smem);
+        P.pp.cap_consts = std::max(P.pp.cap_consts, Q.pp.nconsts);
+        cap_ops = std::max(cap_ops, Q.pp.nops);
         amps += Q.amps; nops_all += Q.pp.nops;
       }
+      smem = (sizeof(double2) << P.pp.t) + sizeof(double2) * (size_t)P.pp.cap_consts + sizeof(MicroOp) * (size_t)cap_ops +
+             (size_t)h->smem_pad;
       P.pp.nlinks = chain_len[pi];
       P.pp.links = h->d_links + link_at[pi];
       h->chained_links += chain_len[pi] - 1;
