@@ -183,8 +183,9 @@ struct PassParams {
   int32_t use_tma, nthreads;
   int32_t nbuf, has_measure;
   int32_t nfree_cols, nlinks;
-  int32_t cap_consts, pad4;           // constants the dynamic shared-memory area holds (>= nconsts; chains: the largest
-                                      // link): the micro-ops are staged right behind them
+  int32_t cap_consts, cap_ops;        // constants / micro-ops the dynamic shared-memory area holds (>= nconsts / nops;
+                                      // chains: the largest link): constants, then micro-ops, then the nregs classical
+                                      // registers of the shot
   uint64_t tile0;                     // first tile of this launch (chains run the batch as chunks of whole waves)
   int32_t uses_treg, writes_creg, writes_treg, nregs;  // planner: what the pass does to the classical state;
                                                        // nregs (even) = registers [0, nregs) are in use
@@ -2033,7 +2034,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
   __shared__ unsigned long long s_cw;   // classical word handed back by the warp that ran a classical block
-  __shared__ __align__(16) double s_treg[kTimeRegs];   // the shot's classical registers (simulated times, channel strengths)
   __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
@@ -2044,6 +2044,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   // ... and its micro-ops behind the constants, sized by the pass (a fixed 48-op array cost the whole-gate passes of
   // small density matrices their eighth resident CTA)
   MicroOp* const s_ops = reinterpret_cast<MicroOp*>(s_consts + pp.cap_consts);
+  // the shot's classical registers (simulated times, channel strengths): the nregs in use, behind the micro-ops
+  double* const s_treg = reinterpret_cast<double*>(s_ops + pp.cap_ops);
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 

@@ -2780,6 +2780,9 @@ int do_flush(dqe_t* h, bool partial) {
       fprintf(stderr, "\n");
     }
   }
+  if (getenv("DQE_DUMP_SMEM"))   // shared-memory budget of every pass (debugging / occupancy planning)
+    for (const PlannedPass& P : pl.passes)
+      if (!P.is_finish) fprintf(stderr, "smem t=%d nops=%d nconsts=%d dyn=%zu max_reg=%d\n", P.pp.t, P.pp.nops, P.pp.nconsts, P.smem, h->max_reg);
   size_t keep_from = h->queue.size();
   uint64_t keep_live = 0;
   if (partial) {
@@ -2882,7 +2885,7 @@ bool same_tile_layout(const PassParams& a, const PassParams& b) {
 }
 
 // resident CTAs per SM as far as shared memory decides (228 KiB per SM, 1 KiB reserved per CTA, ~6.3 KiB static)
-int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 1792 + 1024)); }
+int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 1024 + 1024)); }
 
 int launch_passes(dqe_t* h, Planner& pl) {
   // pass chains: chain_len[i] = number of passes launched together with pass i as their head (0: rides in a chain)
@@ -2951,6 +2954,7 @@ int launch_passes(dqe_t* h, Planner& pl) {
     size_t smem = P.smem + (size_t)h->smem_pad;
     P.pp.cap_consts = P.pp.nconsts;
     int cap_ops = P.pp.nops;
+    P.pp.nregs = 0;
     uint64_t amps = P.amps;
     int64_t nops_all = P.pp.nops;
     const int saved_flags[5] = {P.pp.has_measure, P.pp.writes_creg, P.pp.uses_treg, P.pp.writes_treg, 0};
@@ -2980,6 +2984,8 @@ int launch_passes(dqe_t* h, Planner& pl) {
       P.pp.treg = h->treg_buf[h->tpar];
       if (P.pp.writes_treg) { h->tpar ^= 1; P.pp.treg_out = h->treg_buf[h->tpar]; }
     }
+    P.pp.cap_ops = cap_ops;
+    smem += sizeof(double) * (size_t)P.pp.nregs;   // the classical registers in use ride behind the micro-ops
     build_tensor_map(h, P.pp);
     if (P.pp.tm_rank) h->tmap_used++;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
