@@ -1281,22 +1281,24 @@ __device__ __noinline__ void catm2_apply(double2* tile, uint32_t T, const MicroO
 }
 
 // ---- whole remote gate on the data pair (A, B) (host: try_fuse_whole_at).  Constants (double2 units; all tables real,
-// packed two doubles to an entry): K[m1][pred][order][64 doubles] (2 orders: 1, q; b[7] = 2: 4 orders 1, q1, q2, q1 q2),
+// packed two doubles to an entry): K[m1][pred][order][64 doubles] (2 orders: 1, q; b[7] & 3 = 2: 4 orders 1, q1, q2, q1 q2;
+// b[7] & 4: compact, K[m1][order] -- the predicate is the first outcome or absent),
 // then T2[m2][64], t2[m2][16], then scratch the kernel fills per CTA: u[2][16] (as double2 with y = 0), C[256 doubles].
 // aux = creg bit of m1 | (predicate bit + 1) << 8 | (register of q1 + 1) << 16 | (register of q2 + 1) << 24.
 struct WholeSel { const double* K; double q1, q2; int nord, oT2, ot2, oU, oC; };
 __device__ __forceinline__ WholeSel whole_sel(const MicroOp& op, const double2* cs, uint64_t cw, const double* treg) {
   WholeSel w;
   const uint32_t aux = (uint32_t)op.aux;
-  w.nord = op.b[7] == 2 ? 4 : 2;
-  const int nK = 128 * w.nord;   // double2 entries
+  w.nord = (op.b[7] & 3) == 2 ? 4 : 2;
+  const bool compact = (op.b[7] & 4) != 0;   // K[m1][order] only: the predicate is the first outcome (or absent)
+  const int nK = (compact ? 64 : 128) * w.nord;   // double2 entries
   w.oT2 = nK; w.ot2 = nK + 64; w.oU = nK + 80; w.oC = nK + 112;
   const int m1 = (int)((cw >> (aux & 0xffu)) & 1ull);
   const int pb = (int)((aux >> 8) & 0xffu) - 1, r1 = (int)((aux >> 16) & 0xffu) - 1, r2 = (int)((aux >> 24) & 0xffu) - 1;
   const int pv = pb >= 0 ? (int)((cw >> pb) & 1ull) : 0;
   w.q1 = r1 >= 0 ? treg[r1] : 0.0;
   w.q2 = r2 >= 0 ? treg[r2] : 0.0;
-  w.K = reinterpret_cast<const double*>(cs) + ((m1 * 2 + pv) * w.nord) * 64;
+  w.K = reinterpret_cast<const double*>(cs) + ((compact ? m1 : m1 * 2 + pv) * w.nord) * 64;
   return w;
 }
 __device__ __forceinline__ double whole_keff(const WholeSel& w, int k) {
@@ -1304,7 +1306,9 @@ __device__ __forceinline__ double whole_keff(const WholeSel& w, int k) {
   if (w.nord == 4) v += w.q2 * fma(w.q1, w.K[192 + k], w.K[128 + k]);
   return v;
 }
-__device__ __forceinline__ int whole_scratch_u(const MicroOp& op) { return 128 * (op.b[7] == 2 ? 4 : 2) + 80; }
+__device__ __forceinline__ int whole_scratch_u(const MicroOp& op) {
+  return ((op.b[7] & 4) ? 64 : 128) * ((op.b[7] & 3) == 2 ? 4 : 2) + 80;
+}
 // u_m2[(rA' cA' rB' cB')] = sum_{ry cy} t2_m2[(rB' ry cB' cy)] sum_a K[(a a ry cy), (rA' cA')]: the functional that gives
 // p(m2 | m1) on the group's 16 elements; threads 0-31 write one entry each
 __device__ __noinline__ void whole_build_u(const MicroOp& op, double2* cs, uint64_t cw, const double* treg) {

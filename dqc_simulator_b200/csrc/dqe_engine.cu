@@ -1603,16 +1603,28 @@ bool try_fuse_whole_at(dqe_t* h, size_t ie) {
   HostOp f1 = fin1;
   f1.live_after &= ~yb;
   // ---- W: the second measurement and the whole map (form 2)
-  const int nK = kWholeK * nord / 2;   // double2 entries of K
+  // The predicate of the mid ops is nearly always the first outcome itself (the X correction of dqc_control.py:347-348)
+  // or absent: then only K[m1][pred = m1] (or pred = 0) can ever be selected, and the table ships without the other
+  // half (2 KiB less per gate, 4 KiB with two idle channels: shared memory per CTA and L2 traffic per pass)
+  const bool compact = pred_bit < 0 || pred_bit == fin1.creg_bit;
+  const int nK = (compact ? kWholeK / 2 : kWholeK) * nord / 2;   // double2 entries of K
   std::vector<cplx> KW((size_t)(nK + kWholeT2 + kWholet2 + kWholeScratch), cplx(0.0));
-  for (int k = 0; k < nK; ++k) KW[k] = cplx(K[2 * k], K[2 * k + 1]);
+  if (compact) {
+    for (int m1 = 0; m1 < 2; ++m1) {
+      const int pv = pred_bit < 0 ? 0 : m1;
+      const size_t src = (size_t)((m1 * 2 + pv) * nord) * 64, dst = (size_t)(m1 * nord) * 64;
+      for (int k = 0; k < nord * 32; ++k) KW[dst / 2 + k] = cplx(K[src + 2 * k], K[src + 2 * k + 1]);
+    }
+  } else {
+    for (int k = 0; k < nK; ++k) KW[k] = cplx(K[2 * k], K[2 * k + 1]);
+  }
   for (int m = 0; m < 2; ++m) {
     for (int k = 0; k < 32; ++k) KW[nK + 32 * m + k] = cplx(T2[m][2 * k], T2[m][2 * k + 1]);
     for (int k = 0; k < 8; ++k) KW[nK + kWholeT2 + 8 * m + k] = cplx(t2[m][2 * k], t2[m][2 * k + 1]);
   }
   HostOp w = C;
   w.m.b[0] = (uint8_t)(A + n); w.m.b[1] = (uint8_t)(B + n); w.m.b[2] = (uint8_t)A; w.m.b[3] = (uint8_t)B;
-  w.m.b[4] = (uint8_t)A; w.m.b[5] = (uint8_t)B; w.m.b[6] = 2; w.m.b[7] = (uint8_t)(nord == 4 ? 2 : 1);
+  w.m.b[4] = (uint8_t)A; w.m.b[5] = (uint8_t)B; w.m.b[6] = 2; w.m.b[7] = (uint8_t)((nord == 4 ? 2 : 1) | (compact ? 4 : 0));
   w.need = Ab | Bb;
   w.m.aux = (int32_t)((uint32_t)fin1.creg_bit | ((uint32_t)(pred_bit + 1) << 8) | ((uint32_t)(dyn_reg + 1) << 16) |
                       ((uint32_t)(dyn_reg2 + 1) << 24));
@@ -2627,9 +2639,23 @@ struct Planner {
         if (++nq3 % 3 == 0) op_slots += 1;
       }
       if (cur.empty()) { nslots = 3; ncl = 0; nconst = 0; }
+      // Small density matrices (one 64-thread CTA per <= 2^10 tile): a pass may stage only as many constants as leave
+      // room for EIGHT resident CTAs per SM (registers allow exactly eight) -- tile + constants + ~20 micro-ops + the
+      // classical registers in use + 768 B static + 1 KiB reserved <= 228 KiB / 8.  One whole remote gate fits (416
+      // constants, 544 with two idle channels); a second one would cost every CTA of the pass its eighth neighbour.
+      auto const_cap = [&](int tt) {
+        int cap = max_consts(h->formalism);
+        if (h->formalism == DQE_DM && h->tile_auto && tt <= 10) {
+          const int regs = std::min(kTimeRegs, (h->max_reg + 2) & ~1);
+          const int room = (228 * 1024) / 8 - 1024 - 768 - (16 << tt) - 20 * (int)sizeof(MicroOp) - 8 * regs;
+          cap = std::max(64, std::min(std::min(cap, room / 16), 560));   // (560: one gate per pass on smaller tiles too --
+                                                                         //  two per pass measured 2 % slower on QFT-5)
+        }
+        return cap;
+      };
       const bool fits = cur.empty() || (h->fuse && nslots + op_slots <= h->pass_ops &&
-                                        nconst + op_consts <= max_consts(h->formalism) &&
-                                        choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t));
+                                        choose_tile(h, need2, live2 | phys_live(h, h->pin_axes), false, &tile, &t) &&
+                                        nconst + op_consts <= const_cap(t));
       if (!fits) {
         if (!close(cur, live0)) return false;
         cur_first = (size_t)(&op - h->queue.data());

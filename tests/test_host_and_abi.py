@@ -554,8 +554,10 @@ def test_whole_remote_gate_tables_equal_a_direct_simulation(capfd, monkeypatch, 
     vals = np.array([complex(*map(float, v.split(","))) for v in wl.split(" c=")[1].strip().split(";")])
     flat = np.stack([vals.real, vals.imag], axis=1).reshape(-1)
     nord = 4 if two_dyn else 2
-    K = flat[:256 * nord].reshape(2, 2, nord, 16, 4)             # m1, pred, order, (rA cA ry cy), (rA' cA')
-    T2 = flat[256 * nord:256 * nord + 128].reshape(2, 4, 16)     # m2, (rB cB), (rB' ry cB' cy)
+    # the predicate IS the first outcome here: the table ships compact, K[m1][order] (= K[m1][pred = m1][order])
+    Kc = flat[:128 * nord].reshape(2, nord, 16, 4)               # m1, order, (rA cA ry cy), (rA' cA')
+    K = np.stack([Kc, Kc], axis=1)                               # indexed [m1, m1, order] below
+    T2 = flat[128 * nord:128 * nord + 128].reshape(2, 4, 16)     # m2, (rB cB), (rB' ry cB' cy)
     q2 = 0.21 if two_dyn else 0.0
 
     def chan2(rho, p, keep_shape):                  # two-qubit depolarising on the first two (of 3 or 4) qubits
