@@ -1389,7 +1389,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 template <int FORM>
 __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const MicroOp& op, const PassParams& pp,
                                                uint64_t base, uint64_t shot, uint64_t cw, double* red,
-                                               double (*part)[16][2], MeasRec* mrec, int mcount, double* s_draw,
+                                               double* part, MeasRec* mrec, int mcount, double* s_draw,
                                                const double2* cs, const MicroOp* next_op, double* s_treg,
                                                const double2* s_consts, unsigned long long* s_cw) {
   namespace cg = cooperative_groups;
@@ -1449,25 +1449,33 @@ __device__ __forceinline__ uint64_t op_measure(double2* tile, uint32_t T, const 
   }
   if (mcount == 0 && pp.outer_bits) cluster_wait();   // completes the arrive of the kernel prologue
   if (!solo) __syncthreads();
-  const unsigned nr = cluster.num_blocks();
-  if (threadIdx.x == 0) {
-    double s0 = a0, s1 = a1;
-    if (!solo) {
-      s0 = 0.0; s1 = 0.0;
-      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
-    }
-    // 2. push to every CTA of the shot (own slot included)
-    const unsigned me = cluster.block_rank();
-    for (unsigned r = 0; r < nr; ++r) {
-      double* rp = cluster.map_shared_rank(&part[par][me][0], r);
-      rp[0] = s0; rp[1] = s1;
-    }
+  double s0 = a0, s1 = a1;   // (thread 0's copy is the one that counts)
+  if (threadIdx.x == 0 && !solo) {
+    s0 = 0.0; s1 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[2 * i]; s1 += red[2 * i + 1]; }
   }
-  if (pp.outer_bits) cluster.sync(); else __syncthreads();   // one tile per shot: the CTA is the whole cluster
-  // 3. every CTA sums the slots in rank order (identical result everywhere) and draws
+  if (pp.outer_bits) {
+    // 2. push to every CTA of the shot (own slot included)
+    const unsigned nr = cluster.num_blocks();
+    if (threadIdx.x == 0) {
+      const unsigned me = cluster.block_rank();
+      for (unsigned r = 0; r < nr; ++r) {
+        double* rp = cluster.map_shared_rank(part + 2u * ((unsigned)par * nr + me), r);   // [parity][rank][outcome]
+        rp[0] = s0; rp[1] = s1;
+      }
+    }
+    cluster.sync();
+    // 3. every CTA sums the slots in rank order (identical result everywhere)
+    if (threadIdx.x == 0) {
+      s0 = 0.0; s1 = 0.0;
+      for (unsigned r = 0; r < nr; ++r) { s0 += part[2u * ((unsigned)par * nr + r)]; s1 += part[2u * ((unsigned)par * nr + r) + 1u]; }
+    }
+  } else {
+    __syncthreads();   // one tile per shot: the CTA's own sums are the shot's (the draw of thread 32 becomes visible here)
+  }
+  // ... and draws
   if (threadIdx.x == 0) {
-    double p0 = 0.0, p1 = 0.0;
-    for (unsigned r = 0; r < nr; ++r) { p0 += part[par][r][0]; p1 += part[par][r][1]; }
+    const double p0 = s0, p1 = s1;
     const double e = op.p[0];
     const double q0 = (1.0 - e) * p0 + e * p1, q1 = (1.0 - e) * p1 + e * p0;
     const double tot = q0 + q1;
@@ -2038,7 +2046,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   __shared__ MeasRec s_meas;
   __shared__ double s_draw;
   __shared__ unsigned long long s_cw;   // classical word handed back by the warp that ran a classical block
-  __shared__ double s_part[2][16][2];   // [measurement parity][cluster rank][outcome]: pushed by the shot's CTAs
 
   const uint32_t T = 1u << pp.t;
   const int c0 = pp.tile_segs[0].len;
@@ -2050,6 +2057,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_pass(const __grid_constant_
   MicroOp* const s_ops = reinterpret_cast<MicroOp*>(s_consts + pp.cap_consts);
   // the shot's classical registers (simulated times, channel strengths): the nregs in use, behind the micro-ops
   double* const s_treg = reinterpret_cast<double*>(s_ops + pp.cap_ops);
+  // [measurement parity][cluster rank][outcome] partials pushed by the shot's CTAs: 32 B for a one-tile shot, behind
+  // the registers (a fixed [2][16][2] cost the two-channel whole-gate passes their eighth resident CTA)
+  double* const s_part = s_treg + pp.nregs;
   const uint32_t run_bytes = 16u << c0, nruns = T >> c0;
   const uint64_t outer_mask = (1ull << pp.outer_bits) - 1ull;
 

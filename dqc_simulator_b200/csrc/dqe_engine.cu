@@ -2647,7 +2647,7 @@ struct Planner {
         int cap = max_consts(h->formalism);
         if (h->formalism == DQE_DM && h->tile_auto && tt <= 10) {
           const int regs = std::min(kTimeRegs, (h->max_reg + 2) & ~1);
-          const int room = (228 * 1024) / 8 - 1024 - 768 - (16 << tt) - 20 * (int)sizeof(MicroOp) - 8 * regs;
+          const int room = (228 * 1024) / 8 - 1024 - 256 - (16 << tt) - 20 * (int)sizeof(MicroOp) - 8 * regs;
           cap = std::max(64, std::min(std::min(cap, room / 16), 560));   // (560: one gate per pass on smaller tiles too --
                                                                          //  two per pass measured 2 % slower on QFT-5)
         }
@@ -2911,7 +2911,7 @@ bool same_tile_layout(const PassParams& a, const PassParams& b) {
 }
 
 // resident CTAs per SM as far as shared memory decides (228 KiB per SM, 1 KiB reserved per CTA, ~6.3 KiB static)
-int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 1024 + 1024)); }
+int ctas_per_sm_by_smem(size_t dyn) { return (int)((size_t)(228 * 1024) / (dyn + 512 + 1024)); }
 
 int launch_passes(dqe_t* h, Planner& pl) {
   // pass chains: chain_len[i] = number of passes launched together with pass i as their head (0: rides in a chain)
@@ -3012,6 +3012,8 @@ int launch_passes(dqe_t* h, Planner& pl) {
     }
     P.pp.cap_ops = cap_ops;
     smem += sizeof(double) * (size_t)P.pp.nregs;   // the classical registers in use ride behind the micro-ops
+    if (P.pp.has_measure && P.pp.outer_bits) smem += 32u << P.pp.outer_bits;   // ... and the measurement partials of the
+                                                                               // shot's CTAs (a cluster of <= 16) behind them
     build_tensor_map(h, P.pp);
     if (P.pp.tm_rank) h->tmap_used++;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
