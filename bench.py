@@ -537,7 +537,7 @@ def main():
                      # (ncu cannot run inside the timed bench: a number taken under a profiler is not a bench value)
                      "traffic": 0.93 * 32.0 * amps / max(n_pass, 1),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, 2026-10-20, same command "
-                                       "at 16384 shots (profiles/r02z_summary.md): 499 MB per launch of 16384 tiles of 16 KiB "
+                                       "at 16384 shots (profiles/r03_summary.md section 10): 502 MB per launch of 16384 tiles of 16 KiB "
                                        "against 16384 x 16 KiB x 2 = 537 MB algorithmic -> ratio 0.93 (part of a pass's output is "
                                        "still in L2 when the next pass reads it); scaled to this run's launch size",
                      "note": "algorithmic bytes = 32 B x live elements of rho per pass AFTER the flush-time rewrite that turns "
@@ -545,8 +545,9 @@ def main():
                              "step needed 20x the element updates and 292 passes before (9.6 TB -> 0.47 TB per 1e5 shots), so "
                              "`achieved` fell while shots/s rose 11x.  The ~13-op passes over one 16 KiB tile per shot (table "
                              "building, two reductions with a draw, a 16 x 16 real matrix per group, per-shot classical "
-                             "timeline) are bound by on-chip latency (issue slots ~31 % busy; short-scoreboard 25 %, "
-                             "fixed-latency 22 %, no-instruction 19 % of stall samples: profiles/r02z_summary.md), not by HBM; "
+                             "timeline) are bound by on-chip latency at 8 CTAs of 64 threads per SM, the register file's limit "
+                             "(issue slots ~36 % busy; short-scoreboard 21 %, fixed-latency 21 %, no-instruction 16 % of stall "
+                             "samples: profiles/r03_summary.md section 10), not by HBM; "
                              "see roofline_single_gate for the HBM-bound regime",
                      "peak_source": peak_src,
                      "launches": n_pass, "avg_launch_ms": pass_ms / max(n_pass, 1),
