@@ -290,6 +290,7 @@ int dqe_probs_diag(dqe_t* h, int npairs, const int* a, const int* b, const int* 
  * pair, no comm qubit ever goes live; 2 = fold inject -> interact -> measure-and-discard
  * AND measure-out runs of a remote gate into one fused measurement each at flush -- the first comm qubit of the pair never
  * goes live --, 1 = the injecting runs only, 0 = execute every op as queued; software/dqc_control.py:316-403, 508-613),
+ * "smem_pad" (A/B only: extra bytes of dynamic shared memory per CTA, i.e. fewer resident CTAs per SM),
  * "phase_tables" (ket, default 0: leftover one-bit phases share diagonal tables at flush; measured neutral),
  * "pass_ops" (micro-op budget of a pass, <= 48), "plan_cache" (see dqe_replay).  Setting "tile_bits" or "threads" also
  * switches off the per-pass choice of tile / CTA size that density matrices of <= 7 qubits get by default
