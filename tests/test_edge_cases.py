@@ -143,3 +143,49 @@ def test_negligible_time_instructions_have_no_noise_and_three_ns():
         ph = spec.phys(tok)
         assert ph.duration == 3.0 and ph.noise == "none" and ph.prob == 0.0
     assert spec.phys(ins.INSTR_H).duration == 135e3 and spec.phys(ins.INSTR_H).noise == "depol1"
+
+
+def test_planner_limits_at_the_edge(capfd, monkeypatch):
+    """The silent limits of the planner, on a plan-only handle: a run of ops longer than the 48-micro-op budget of a
+    pass is CUT into passes that each respect it (never an error, never an over-full pass); the classical register
+    has exactly 64 bits (bit 63 works, bit 64 is refused with a message)."""
+    from dqc_simulator_b200 import engine
+
+    rng = np.random.default_rng(0)
+
+    def ru(d):
+        q, _ = np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))
+        return q
+
+    cnot = np.eye(4)[[0, 1, 3, 2]]
+    monkeypatch.setenv("DQE_DUMP_SMEM", "1")
+    for formalism, n in (("ket", 9), ("dm", 5)):
+        e = engine.Engine(formalism, n, 2, device=-1)
+        for a in range(n):
+            e.alloc_axis(a)
+        for i in range(400):                       # nothing here folds away: a dense gate, then a CNOT across axes
+            e.apply_1q(i % n, ru(2))
+            e.apply_2q(i % n, (i + 1 + i % 3) % n, cnot)
+        capfd.readouterr()
+        e.flush()
+        lines = [ln for ln in capfd.readouterr().err.splitlines() if ln.startswith("smem ")]
+        nops = [int(ln.split("nops=")[1].split()[0]) for ln in lines]
+        assert len(nops) == e.stats()["passes"] > 800 // 48
+        assert max(nops) <= 48 and sum(nops) == e.stats()["micro_ops"]
+        e.set_option("pass_ops", 8)                # the same program under a tighter budget
+        e.reinit()
+        for a in range(n):
+            e.alloc_axis(a)
+        for i in range(60):
+            e.apply_1q(i % n, ru(2))
+            e.apply_2q(i % n, (i + 1) % n, cnot)
+        capfd.readouterr()
+        e.flush()
+        lines = [ln for ln in capfd.readouterr().err.splitlines() if ln.startswith("smem ")]
+        assert lines and all(int(ln.split("nops=")[1].split()[0]) <= 16 for ln in lines)   # (a group header may ride on top)
+        e.measure(0, 63, 1, False, 0.0)            # the last classical bit
+        with pytest.raises(engine.EngineError, match="64 bits"):
+            e.measure(1, 64, 1, False, 0.0)
+        with pytest.raises(engine.EngineError, match="out of range"):
+            e.cond_1q(1, np.eye(2), 64)
+        e.close()
