@@ -103,6 +103,17 @@ class B200Repr(_Base):
             return self._eng.pauli_channel(ax[0], probs)
         if len(ax) == 2 and len(mats) == 16 and np.allclose(w[1:], w[1]):
             return self._eng.depolarize(ax, 16.0 * w[1])      # (1 - 15p/16, p/16 ...) == NDimDepolarNoiseModel
+        if len(ax) == 2:
+            # any mixture of two-qubit Pauli products (correlated noise): one k = 2 Pauli channel
+            # (dqe_enqueue_pauli_channel_k: a single 16 x 16 superoperator block in the dm formalism)
+            products = [np.kron(a, b) for a in _PAULI for b in _PAULI]
+            probs = np.zeros(16)
+            for m, p in zip(mats, w):
+                k = next((i for i, P in enumerate(products) if m.shape == (4, 4) and np.allclose(m, P)), None)
+                if k is None:
+                    raise NotImplementedError("stochastic_operate: two-qubit operators must be Pauli products")
+                probs[k] += p
+            return self._eng.pauli_channel(ax, probs)
         raise NotImplementedError("stochastic_operate: unsupported operator set")
 
     def apply_pauli_noise(self, index, probs):

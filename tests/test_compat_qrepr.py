@@ -118,3 +118,20 @@ def test_ket_repr_and_generic_channels(factory):
     hz = H @ np.diag([0.25, 0.75]) @ H
     hz[0, 1] *= 0.6; hz[1, 0] *= 0.6
     assert np.abs(d.dm - hz).max() < 1e-12
+
+
+@pytest.mark.parametrize("factory", BACKENDS)
+def test_correlated_two_qubit_pauli_mixture(factory):
+    """qubitapi.stochastic_operate with a NON-uniform set of two-qubit Pauli products (correlated XX / ZZ noise on a
+    Bell pair): one k = 2 Pauli channel on the engine; expected value by plain NumPy."""
+    r = B200DMRepr(num_qubits=2, max_qubits=3, engine_factory=factory)
+    r.operate(Op(H), [0])
+    r.operate(Op(CNOT), [0, 1])
+    ops = [Op(np.kron(I2, I2)), Op(np.kron(X, X)), Op(np.kron(Z, Z)), Op(np.kron(X, Z))]
+    w = [0.7, 0.15, 0.1, 0.05]
+    r.stochastic_operate(ops, w, [0, 1])
+    rho0 = np.outer(B00, B00.conj())
+    want = sum(p * o.arr @ rho0 @ o.arr.conj().T for o, p in zip(ops, w))
+    assert np.abs(r.dm - want).max() < 1e-12
+    with pytest.raises(NotImplementedError, match="Pauli products"):
+        r.stochastic_operate([Op(np.kron(H, I2))], [1.0], [0, 1])
